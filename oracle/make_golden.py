@@ -1,0 +1,86 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference generator.
+
+TEST INFRASTRUCTURE (see oracle/__init__.py).  Run in the build container,
+where /root/reference exists:
+
+    python oracle/make_golden.py
+
+It imports ``climsr.models.esrgan.ESRGANGenerator`` from /root/reference
+(read-only), feeds it seeded inputs, and stores small fixtures.  The GPU box
+has no /root/reference; tests there read only the committed .npz files.
+
+Fixtures
+  gen_tiny_refinit.npz  - reference ctor + torch.manual_seed(0) default init (nb=1, gc=16, in=2 as in
+                          tests/models/test_esrgan.py:10-12); FULL state_dict + inputs + output + L1 grads of
+                          three representative weights.
+  gen_hydra_seeded.npz  - Hydra cfg (nb=11, gc=16, in=4) with oracle.synth.make_state_dict(seed=0) weights
+                          loaded through load_state_dict(strict=True): inputs are re-derivable from seeds, only
+                          the output (and its gain=4 "trained-like" variant) is stored.
+  gen_default_seeded.npz- class default (nb=23, gc=32, in=4), same recipe, smaller raster.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+sys.path.insert(0, "/root/reference")
+
+from climsr.models.esrgan import ESRGANGenerator  # noqa: E402  (the reference itself)
+
+from oracle import synth  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def tiny_refinit():
+    torch.manual_seed(0)
+    net = ESRGANGenerator(in_channels=2, out_channels=1, nf=64, nb=1, gc=16).eval()
+    x, elev, mask = synth.make_inputs(2, 2, 8, 8, seed=11)
+    hr = synth.make_targets(torch.zeros(2, 1, 32, 32), seed=14)["hr"]
+    sr = net(x, elev, mask)
+    loss = torch.nn.functional.l1_loss(sr, hr)
+    loss.backward()
+    blob = {"x": x.numpy(), "elev": elev.numpy(), "mask": mask.numpy(), "hr": hr.numpy(),
+            "sr": sr.detach().numpy(), "loss": loss.detach().numpy()}
+    for k, v in net.state_dict().items():
+        blob["sd/" + k] = v.numpy()
+    for k in ("conv_first.weight", "RRDB_trunk.0.RDB2.conv3.weight", "srcnn.conv3.bias"):
+        blob["grad/" + k] = dict(net.named_parameters())[k].grad.numpy()
+    np.savez_compressed(os.path.join(OUT, "gen_tiny_refinit.npz"), **blob)
+    print("tiny_refinit", sr.shape, float(sr.std()), float(loss))
+
+
+def seeded(name, in_ch, nb, gc, n, h, w):
+    blob = {}
+    for gain in (1.0, 4.0):
+        sd = synth.make_state_dict(in_ch, 1, 64, nb, gc, seed=0, gain=gain if gain == 1.0 else _trained_gain(nb, gc))
+        net = ESRGANGenerator(in_channels=in_ch, out_channels=1, nf=64, nb=nb, gc=gc, scale_factor=4).eval()
+        net.load_state_dict(sd, strict=True)
+        x, elev, mask = synth.make_inputs(n, in_ch, h, w, seed=1)
+        with torch.no_grad():
+            sr = net(x, elev, mask)
+        tag = "sr" if gain == 1.0 else "sr_trained"
+        blob[tag] = sr.numpy()
+        print(name, tag, sr.shape, "std", float(sr.std()), "absmax", float(sr.abs().max()))
+    blob["meta"] = np.array([in_ch, nb, gc, n, h, w], dtype=np.int64)
+    blob["trained_gain"] = np.array(_trained_gain(nb, gc))
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **blob)
+
+
+def _trained_gain(nb, gc):
+    # chosen so the output std is O(0.3-1): the 1e-2 abs budget is then a tight test
+    return 1.8 if gc == 16 else 1.4
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(8)
+    tiny_refinit()
+    seeded("gen_hydra_seeded", 4, 11, 16, 2, 16, 16)
+    seeded("gen_default_seeded", 4, 23, 32, 1, 12, 12)

@@ -1,0 +1,117 @@
+"""Pin the oracle: golden vectors from the reference module, numpy cross-check, metric KATs."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import generator as og
+from oracle import metrics as om
+from oracle import np_ops, synth
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name))
+
+
+def test_tiny_refinit_matches_reference_forward_and_grads(golden_dir):
+    z = _load(golden_dir, "gen_tiny_refinit.npz")
+    sd = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd/")}
+    x, elev, mask, hr = (torch.from_numpy(z[k]) for k in ("x", "elev", "mask", "hr"))
+    sr, loss, grads = og.generator_forward_backward(sd, x, elev, mask, hr, "l1")
+    assert sr.shape == (2, 1, 32, 32)
+    assert np.abs(sr.numpy() - z["sr"]).max() <= 1e-6
+    assert abs(float(loss) - float(z["loss"])) <= 1e-7
+    for k in z.files:
+        if k.startswith("grad/"):
+            g = grads[k[5:]].numpy()
+            assert np.abs(g - z[k]).max() <= 1e-6 * max(1.0, np.abs(z[k]).max())
+
+
+def test_state_dict_names_match_reference(golden_dir):
+    z = _load(golden_dir, "gen_tiny_refinit.npz")
+    ref_names = [k[3:] for k in z.files if k.startswith("sd/")]
+    ours = synth.make_state_dict(2, 1, 64, 1, 16)
+    assert list(ours.keys()) == ref_names
+    for k in ref_names:
+        assert tuple(ours[k].shape) == z["sd/" + k].shape
+
+
+@pytest.mark.parametrize("name", ["gen_hydra_seeded.npz", "gen_default_seeded.npz"])
+def test_seeded_configs_match_reference(golden_dir, name):
+    z = _load(golden_dir, name)
+    in_ch, nb, gc, n, h, w = (int(v) for v in z["meta"])
+    x, elev, mask = synth.make_inputs(n, in_ch, h, w, seed=1)
+    for tag, gain in (("sr", 1.0), ("sr_trained", float(z["trained_gain"]))):
+        sd = synth.make_state_dict(in_ch, 1, 64, nb, gc, seed=0, gain=gain)
+        with torch.no_grad():
+            sr = og.generator_forward(sd, x, elev, mask)
+        ref = z[tag]
+        assert sr.shape == ref.shape
+        assert np.abs(sr.numpy() - ref).max() <= 2e-5 * max(1.0, np.abs(ref).max())
+
+
+def test_numpy_restatement_agrees_with_torch_graph():
+    sd = synth.make_state_dict(3, 1, 64, 1, 16, seed=3)
+    x, elev, mask = synth.make_inputs(1, 3, 6, 5, seed=7)
+    with torch.no_grad():
+        a = og.generator_forward(sd, x, elev, mask).numpy()
+    b = np_ops.generator_forward({k: v.numpy() for k, v in sd.items()}, x.numpy(), elev.numpy(), mask.numpy())
+    assert a.shape == (1, 1, 24, 20)
+    assert np.abs(a - b).max() <= 1e-5
+
+
+def test_reference_shape_case():
+    """tests/models/test_esrgan.py:7-22 of the reference (shape only), on a smaller batch for CPU time."""
+    sd = synth.make_state_dict(2, 1, 64, 1, 16)
+    x = torch.rand(2, 2, 32, 32)
+    e = torch.rand(2, 1, 128, 128)
+    m = torch.rand(2, 1, 128, 128)
+    with torch.no_grad():
+        assert og.generator_forward(sd, x, e, m).shape == (2, 1, 128, 128)
+
+
+def test_flop_model_matches_survey():
+    assert og.flops_per_hr_pixel(3, 64, 11, 16) == pytest.approx(721880.0)
+    assert og.flops_per_hr_pixel(4, 64, 11, 16) == pytest.approx(721952.0)
+    assert og.flops_per_hr_pixel(4, 64, 23, 32) == pytest.approx(2275424.0)
+
+
+# ---- RegressionAccuracy known-answer cases: tests/metrics/test_regresion_accuracy.py:12-108 ----
+SHAPE = (3, 128, 128)
+
+
+def _kat_cases():
+    for eps in (0.1, 1.0, 0.25):
+        yield eps, torch.zeros(SHAPE), torch.ones(SHAPE) + (1 if eps == 1.0 else 0), 0.0
+        yield eps, torch.ones(SHAPE), torch.ones(SHAPE), 1.0
+        g = torch.Generator().manual_seed(int(eps * 100))
+        yield eps, torch.ones(SHAPE) - torch.rand(SHAPE, generator=g) / 100, torch.ones(SHAPE), 1.0
+
+
+@pytest.mark.parametrize("eps,preds,targets,expected", list(_kat_cases()))
+def test_regression_accuracy_kats(eps, preds, targets, expected):
+    assert float(om.regression_accuracy(preds, targets, eps)) == expected
+
+
+def test_val_step_properties():
+    g = torch.Generator().manual_seed(0)
+    n, H, W = 2, 40, 36
+    sr = torch.rand(n, 1, H, W, generator=g) * 2 - 1
+    t = synth.make_targets(sr, seed=4)
+    mask = (torch.rand(n, 1, H, W, generator=g) > 0.3).float()
+    orig = om.denormalized_original(t["hr"], t["min"], t["max"])
+    out = om.val_test_step(sr, t["hr"], orig, mask, t["min"], t["max"])
+    assert set(om.ACC_KEYS) <= set(out)
+    # identical inputs -> perfect scores
+    same = om.val_test_step(t["hr"], t["hr"], orig, mask, t["min"], t["max"])
+    assert float(same["mae"]) < 1e-5 and float(same["acc@0.1"]) == 1.0 and abs(float(same["ssim"]) - 1) < 1e-9
+    # masked pixels do not contribute: perturb the ocean only
+    sr2 = sr.clone()
+    sr2[~mask.bool()] += 5.0
+    out2 = om.val_test_step(sr2, t["hr"], orig, mask, t["min"], t["max"])
+    for k in out:
+        assert float(out[k]) == pytest.approx(float(out2[k]), rel=1e-12, abs=1e-12)
+    # denominators are numel, not land count
+    d = (om.minmax_denormalize(sr.double(), t["min"].double(), t["max"].double()) - orig.double()).abs() * mask
+    assert float(out["mae"]) == pytest.approx(float(d.sum() / d.numel()), rel=1e-9)
