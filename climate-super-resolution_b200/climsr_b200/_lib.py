@@ -1,0 +1,94 @@
+"""ctypes binding of include/climsr_b200.h (the C-ABI drop-in boundary).  Fails loudly if the .so is missing."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libclimsr_b200.so")
+
+CSR_OK = 0
+NUM_METRICS = 18
+METRIC_KEYS = ("acc@0.1", "acc@0.25", "acc@0.5", "acc@0.75", "acc@1", "acc@01.25", "acc@1.5", "acc@2", "psnr", "ssim", "mae",
+               "mse", "rmse", "mape", "smape", "r2", "l1_loss", "mse_loss")   # key names of core/task.py:318-334 (typo kept)
+
+
+class CsrError(RuntimeError):
+    pass
+
+
+class NetDesc(C.Structure):
+    _fields_ = [("in_channels", C.c_int32), ("out_channels", C.c_int32), ("nf", C.c_int32), ("nb", C.c_int32),
+                ("gc", C.c_int32), ("scale", C.c_int32)]
+
+
+class ConvDesc(C.Structure):
+    _fields_ = [("n", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("cin", C.c_int32), ("cout", C.c_int32),
+                ("kh", C.c_int32), ("kw", C.c_int32), ("in_c", C.c_int32), ("out_c", C.c_int32), ("out_coff", C.c_int32),
+                ("act", C.c_int32), ("out_mode", C.c_int32), ("scale1", C.c_float), ("scale2", C.c_float),
+                ("res1_c", C.c_int32), ("res1_coff", C.c_int32), ("res2_c", C.c_int32), ("res2_coff", C.c_int32)]
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise CsrError(f"{LIB_PATH} is missing: build it with `python climate-super-resolution_b200/build.py` "
+                       "(no CPU fallback exists for this path)")
+    L = C.CDLL(LIB_PATH)
+    vp, i32, sz, f32 = C.c_void_p, C.c_int32, C.c_size_t, C.c_float
+    nd, cd = C.POINTER(NetDesc), C.POINTER(ConvDesc)
+    sig = {
+        "csr_abi_version": (C.c_int, []),
+        "csr_last_error": (C.c_char_p, []),
+        "csr_device_check": (C.c_int, []),
+        "csr_set_option": (C.c_int, [i32, i32]),
+        "csr_kernel_launch_count": (C.c_int64, []),
+        "csr_num_layers": (C.c_int, [nd]),
+        "csr_layer_shape": (C.c_int, [nd, i32, C.POINTER(i32 * 4), C.c_char_p, sz]),
+        "csr_packed_weight_bytes": (sz, [nd]),
+        "csr_pack_weights": (C.c_int, [nd, C.POINTER(vp), C.POINTER(vp), vp, sz, vp]),
+        "csr_workspace_bytes": (sz, [nd, i32, i32, i32]),
+        "csr_plan_create": (C.c_int, [nd, i32, i32, i32, vp, sz, C.POINTER(vp)]),
+        "csr_plan_forward": (C.c_int, [vp, vp, vp, vp, vp, vp, vp]),
+        "csr_plan_num_launches": (C.c_int, [vp]),
+        "csr_plan_destroy": (None, [vp]),
+        "csr_generator_forward": (C.c_int, [nd, vp, vp, vp, vp, vp, vp, sz, i32, i32, i32, vp]),
+        "csr_conv2d_scratch_bytes": (sz, [cd]),
+        "csr_conv2d_nhwc": (C.c_int, [cd, vp, vp, vp, vp, vp, vp, vp, sz, vp]),
+        "csr_nchw_f32_to_nhwc_bf16": (C.c_int, [vp, vp, i32, i32, i32, i32, i32, i32, vp]),
+        "csr_nhwc_bf16_to_nchw_f32": (C.c_int, [vp, vp, i32, i32, i32, i32, i32, i32, vp]),
+        "csr_metrics_scratch_bytes": (sz, [i32, i32, i32]),
+        "csr_masked_metrics": (C.c_int, [vp, vp, vp, vp, vp, vp, f32, f32, f32, f32, i32, i32, i32, vp, vp, sz, vp]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)
+        fn.restype = res
+        fn.argtypes = args
+    return L
+
+
+lib = _load()
+EXPORTS = ("csr_abi_version", "csr_last_error", "csr_device_check", "csr_set_option", "csr_kernel_launch_count", "csr_num_layers",
+           "csr_layer_shape", "csr_packed_weight_bytes", "csr_pack_weights", "csr_workspace_bytes", "csr_plan_create",
+           "csr_plan_forward", "csr_plan_num_launches", "csr_plan_destroy", "csr_generator_forward", "csr_conv2d_scratch_bytes",
+           "csr_conv2d_nhwc", "csr_nchw_f32_to_nhwc_bf16", "csr_nhwc_bf16_to_nchw_f32", "csr_metrics_scratch_bytes",
+           "csr_masked_metrics")
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != CSR_OK:
+        msg = lib.csr_last_error().decode("utf-8", "replace")
+        raise CsrError(f"{what or 'climsr_b200'} failed (status {rc}): {msg}")
+
+
+def device_check() -> None:
+    """Raise unless an sm_100 (B200) device is current and usable."""
+    check(lib.csr_device_check(), "csr_device_check")
+
+
+def kernel_launch_count() -> int:
+    return int(lib.csr_kernel_launch_count())
+
+
+def current_stream_ptr() -> int:
+    import torch
+    return int(torch.cuda.current_stream().cuda_stream)

@@ -1,0 +1,182 @@
+"""Drop-in ESRGANGenerator backed by the sm_100a kernels of libclimsr_b200.so.
+
+Mirrors climsr/models/esrgan.py:57-102 of the reference: same constructor signature (stray kwargs such as the
+Hydra key ``scale_factor`` are swallowed, conf/generator/default.yaml:3), same sub-module / parameter names and
+OIHW fp32 shapes (so Lightning checkpoints and ``load_state_dict`` work unchanged), same default initialisation
+(the parameter containers are plain nn.Conv2d created in the reference's order, so torch.manual_seed(s) gives
+bit-identical initial weights), same ``forward(x, elev, mask) -> (N, 1, 4h, 4w)``.
+
+The nn.Conv2d modules are never *called*: forward() hands the fp32 master weights to csr_pack_weights (bf16 UMMA
+tiles, re-packed only when a parameter's version counter changes) and runs the whole generator through
+csr_plan_forward on torch's current CUDA stream.  There is no eager / CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional, Tuple
+
+import torch
+import torch.nn as nn
+from torch import Tensor
+
+from .._lib import CsrError, NetDesc, check, current_stream_ptr, lib
+
+
+class _RDBParams(nn.Module):
+    """Parameter container with the names of ResidualDenseBlock (esrgan.py:17-27)."""
+
+    def __init__(self, nf: int = 64, gc: int = 32, bias: bool = True):
+        super().__init__()
+        self.conv1 = nn.Conv2d(nf, gc, 3, 1, 1, bias=bias)
+        self.conv2 = nn.Conv2d(nf + gc, gc, 3, 1, 1, bias=bias)
+        self.conv3 = nn.Conv2d(nf + 2 * gc, gc, 3, 1, 1, bias=bias)
+        self.conv4 = nn.Conv2d(nf + 3 * gc, gc, 3, 1, 1, bias=bias)
+        self.conv5 = nn.Conv2d(nf + 4 * gc, nf, 3, 1, 1, bias=bias)
+
+
+class _RRDBParams(nn.Module):
+    """Names of ResidualInResidualDenseBlock (esrgan.py:41-48)."""
+
+    def __init__(self, nf: int, gc: int = 32):
+        super().__init__()
+        self.RDB1 = _RDBParams(nf, gc)
+        self.RDB2 = _RDBParams(nf, gc)
+        self.RDB3 = _RDBParams(nf, gc)
+
+
+class _SRCNNParams(nn.Module):
+    """Names of SRCNN (srcnn.py:6-11)."""
+
+    def __init__(self, in_channels: int = 3, out_channels: int = 1):
+        super().__init__()
+        self.conv1 = nn.Conv2d(in_channels, 64, kernel_size=9, padding=4)
+        self.conv2 = nn.Conv2d(64, 32, kernel_size=1, padding=0)
+        self.conv3 = nn.Conv2d(32, out_channels, kernel_size=5, padding=2)
+
+
+class ESRGANGenerator(nn.Module):
+    def __init__(self, in_channels: int = 3, out_channels: int = 3, nf: int = 64, nb: int = 23, gc: int = 32,
+                 scaling_factor: int = 4, **kwargs):
+        super().__init__()
+        self.scale_factor = scaling_factor
+        self.in_channels, self.out_channels, self.nf, self.nb, self.gc = in_channels, out_channels, nf, nb, gc
+        if out_channels != 1:
+            # the reference's own tail hard-wires 1+1+1 channels (esrgan.py:87,100), so only 1 ever worked there too
+            raise ValueError("ESRGANGenerator: out_channels must be 1 (SRCNN tail takes cat([out, elev, mask]))")
+        if scaling_factor != 4 or nf != 64 or gc not in (16, 32) or not (1 <= in_channels <= 16):
+            raise ValueError("climsr_b200 ESRGANGenerator supports scaling_factor=4, nf=64, gc in {16,32}, 1<=in_channels<=16")
+        # same creation order as esrgan.py:72-87 -> same RNG stream -> same default init
+        self.conv_first = nn.Conv2d(in_channels, nf, 3, 1, 1, bias=True)
+        self.RRDB_trunk = nn.Sequential(*[_RRDBParams(nf=nf, gc=gc) for _ in range(nb)])
+        self.trunk_conv = nn.Conv2d(nf, nf, 3, 1, 1, bias=True)
+        self.upconv1 = nn.Conv2d(nf, nf, 3, 1, 1, bias=True)
+        self.upconv2 = nn.Conv2d(nf, nf, 3, 1, 1, bias=True)
+        self.HRconv = nn.Conv2d(nf, nf, 3, 1, 1, bias=True)
+        self.conv_last = nn.Conv2d(nf, out_channels, 3, 1, 1, bias=True)
+        self.srcnn = _SRCNNParams(in_channels=3, out_channels=out_channels)
+        self._desc = NetDesc(in_channels, out_channels, nf, nb, gc, scaling_factor)
+        self._packed: Optional[Tensor] = None
+        self._packed_key: Optional[Tuple] = None
+        self._plans: Dict[Tuple, Tuple[int, Tensor]] = {}
+
+    # ------------------------------------------------------------------ weights
+    def _ordered_params(self):
+        """(weight, bias) pairs in state_dict order == csr layer order."""
+        n = lib.csr_num_layers(C.byref(self._desc))
+        if n < 0:
+            check(n, "csr_num_layers")
+        sd = dict(self.named_parameters())
+        out = []
+        shape = (C.c_int32 * 4)()
+        name = C.create_string_buffer(128)
+        for i in range(n):
+            check(lib.csr_layer_shape(C.byref(self._desc), i, C.byref(shape), name, 128), "csr_layer_shape")
+            key = name.value.decode()
+            w, b = sd[key + ".weight"], sd[key + ".bias"]
+            if tuple(w.shape) != tuple(shape):
+                raise CsrError(f"parameter {key}.weight has shape {tuple(w.shape)}, expected {tuple(shape)}")
+            out.append((w, b))
+        return out
+
+    def packed_weights(self) -> Tensor:
+        """bf16 UMMA weight tiles + fp32 biases; rebuilt when any parameter changed (optimizer step, load_state_dict)."""
+        pairs = self._ordered_params()
+        dev = pairs[0][0].device
+        key = (dev,) + tuple((p.data_ptr(), p._version) for wb in pairs for p in wb)
+        if self._packed is not None and key == self._packed_key:
+            return self._packed
+        if dev.type != "cuda":
+            raise CsrError("ESRGANGenerator parameters must live on a CUDA (B200) device; there is no CPU path")
+        nbytes = lib.csr_packed_weight_bytes(C.byref(self._desc))
+        if self._packed is None or self._packed.device != dev:
+            self._packed = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        keep = []
+        n = len(pairs)
+        wp, bp = (C.c_void_p * n)(), (C.c_void_p * n)()
+        for i, (w, b) in enumerate(pairs):
+            wc = w.detach().contiguous().float()
+            bc = b.detach().contiguous().float()
+            keep += [wc, bc]
+            wp[i], bp[i] = wc.data_ptr(), bc.data_ptr()
+        with torch.cuda.device(dev):
+            check(lib.csr_pack_weights(C.byref(self._desc), wp, bp, self._packed.data_ptr(), nbytes, current_stream_ptr()),
+                  "csr_pack_weights")
+        self._packed_key = key
+        return self._packed
+
+    # ------------------------------------------------------------------ plan cache
+    def _plan(self, n: int, h: int, w: int, dev: torch.device):
+        key = (n, h, w, dev)
+        hit = self._plans.get(key)
+        if hit is not None:
+            return hit[0]
+        nbytes = lib.csr_workspace_bytes(C.byref(self._desc), n, h, w)
+        ws = torch.empty(nbytes + 1024, dtype=torch.uint8, device=dev)
+        base = (ws.data_ptr() + 1023) // 1024 * 1024
+        plan = C.c_void_p()
+        with torch.cuda.device(dev):
+            check(lib.csr_plan_create(C.byref(self._desc), n, h, w, base, nbytes, C.byref(plan)), "csr_plan_create")
+        if len(self._plans) >= 4:   # bound the cached workspaces
+            for _, (p, _t) in list(self._plans.items()):
+                lib.csr_plan_destroy(p)
+            self._plans.clear()
+        self._plans[key] = (plan.value, ws)
+        return plan.value
+
+    def __del__(self):
+        try:
+            for p, _t in self._plans.values():
+                lib.csr_plan_destroy(p)
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, x: Tensor, elev: Tensor, mask: Tensor) -> Tensor:
+        if x.dim() != 4 or elev.dim() != 4 or mask.dim() != 4:
+            raise ValueError("expected x (N,C,h,w), elev (N,1,4h,4w), mask (N,1,4h,4w)")
+        n, c, h, w = x.shape
+        if c != self.in_channels:
+            raise ValueError(f"x has {c} channels, generator was built with in_channels={self.in_channels}")
+        hr_shape = (n, 1, 4 * h, 4 * w)
+        if tuple(elev.shape) != hr_shape or tuple(mask.shape) != hr_shape:
+            raise ValueError(f"elev/mask must have shape {hr_shape}, got {tuple(elev.shape)} / {tuple(mask.shape)}")
+        if not x.is_cuda:
+            raise CsrError("climsr_b200 ESRGANGenerator runs on CUDA (sm_100a) only; there is no CPU fallback")
+        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
+            from ..autograd import generator_apply
+            return generator_apply(self, x, elev, mask)
+        return self._forward_impl(x, elev, mask)
+
+    def _forward_impl(self, x: Tensor, elev: Tensor, mask: Tensor) -> Tensor:
+        n, _, h, w = x.shape
+        dev = x.device
+        xs = x.detach().contiguous().float()
+        es = elev.detach().to(dev).contiguous().float()
+        ms = mask.detach().to(dev).contiguous().float()
+        packed = self.packed_weights()
+        plan = self._plan(n, h, w, dev)
+        out = torch.empty((n, 1, 4 * h, 4 * w), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            check(lib.csr_plan_forward(plan, packed.data_ptr(), xs.data_ptr(), es.data_ptr(), ms.data_ptr(), out.data_ptr(),
+                                       current_stream_ptr()), "csr_plan_forward")
+        return out

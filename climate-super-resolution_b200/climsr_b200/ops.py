@@ -1,0 +1,61 @@
+"""Single-op wrappers over the C-ABI (used by parity tests and as building blocks)."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+from torch import Tensor
+
+from ._lib import ConvDesc, check, current_stream_ptr, lib
+
+ACT = {"none": 0, "lrelu": 1, "relu": 2}
+OUT_MODE = {"nhwc": 0, "nhwc_up2": 1, "f32_planar": 2}
+
+
+def nchw_to_nhwc_bf16(x: Tensor, dst_c: int = 64) -> Tensor:
+    """fp32 NCHW (c <= 16) -> bf16 NHWC with dst_c channels per pixel (channels >= c are zero)."""
+    n, c, h, w = x.shape
+    out = torch.zeros((n, h, w, dst_c), dtype=torch.bfloat16, device=x.device)
+    xs = x.contiguous().float()
+    check(lib.csr_nchw_f32_to_nhwc_bf16(xs.data_ptr(), out.data_ptr(), n, c, h, w, dst_c, 16 if dst_c >= 16 else 8,
+                                        current_stream_ptr()), "csr_nchw_f32_to_nhwc_bf16")
+    return out
+
+
+def nhwc_bf16_to_nchw(x: Tensor, c: int, coff: int = 0) -> Tensor:
+    n, h, w, cc = x.shape
+    out = torch.empty((n, c, h, w), dtype=torch.float32, device=x.device)
+    check(lib.csr_nhwc_bf16_to_nchw_f32(x.data_ptr(), out.data_ptr(), n, c, h, w, cc, coff, current_stream_ptr()),
+          "csr_nhwc_bf16_to_nchw_f32")
+    return out
+
+
+def conv2d_nhwc(inp: Tensor, weight: Tensor, bias: Tensor, *, act: str = "none", out: Optional[Tensor] = None,
+                out_coff: int = 0, out_mode: str = "nhwc", res1: Optional[Tensor] = None, res1_coff: int = 0,
+                scale1: float = 1.0, res2: Optional[Tensor] = None, res2_coff: int = 0, scale2: float = 1.0) -> Tensor:
+    """One KxK stride-1 'same' conv on a bf16 NHWC buffer (channels-per-pixel multiple of 64) via csr_conv2d_nhwc.
+
+    Reads input channels [0, cin); writes act(conv+bias) (then *scale1+res1, *scale2+res2) into channels
+    [out_coff, out_coff+cout) of `out` (allocated as a 64-channel-padded buffer when None).
+    """
+    n, h, w, in_c = inp.shape
+    cout, cin, kh, kw = weight.shape
+    mode = OUT_MODE[out_mode]
+    if out is None:
+        if mode == 2:
+            out = torch.empty((n, 1, h, w), dtype=torch.float32, device=inp.device)
+        else:
+            s = 2 if mode == 1 else 1
+            oc = (out_coff + cout + 63) // 64 * 64
+            out = torch.zeros((n, s * h, s * w, oc), dtype=torch.bfloat16, device=inp.device)
+    out_c = 1 if mode == 2 else out.shape[-1]
+    d = ConvDesc(n, h, w, cin, cout, kh, kw, in_c, out_c, out_coff, ACT[act], mode, scale1, scale2,
+                 res1.shape[-1] if res1 is not None else 0, res1_coff, res2.shape[-1] if res2 is not None else 0, res2_coff)
+    nbytes = lib.csr_conv2d_scratch_bytes(C.byref(d))
+    scratch = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=inp.device)
+    wc, bc = weight.contiguous().float(), bias.contiguous().float()
+    check(lib.csr_conv2d_nhwc(C.byref(d), inp.data_ptr(), wc.data_ptr(), bc.data_ptr(), out.data_ptr(),
+                              res1.data_ptr() if res1 is not None else None, res2.data_ptr() if res2 is not None else None,
+                              scratch.data_ptr(), nbytes, current_stream_ptr()), "csr_conv2d_nhwc")
+    return out

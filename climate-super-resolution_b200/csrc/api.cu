@@ -1,0 +1,586 @@
+// Host side of the C-ABI (include/climsr_b200.h): layer table, weight-pack layout, tile selection, TMA tensor
+// maps, the forward plan (buffer carving + launch list) and the exported entry points.
+#include <algorithm>
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/climsr_b200.h"
+#include "conv_tc.cuh"
+#include "elementwise.cuh"
+#include "metrics.cuh"
+
+namespace csr {
+
+// ------------------------------------------------------------------------------------------- errors
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+static int g_opt_base_off_mode = 0;
+static int g_opt_force_sw = 0;
+static int g_opt_max_slots = 8;
+
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define CSR_CUDA(expr)                                                                          \
+  do {                                                                                          \
+    cudaError_t _e = (expr);                                                                    \
+    if (_e != cudaSuccess) return fail(CSR_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(_e)); \
+  } while (0)
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// ------------------------------------------------------------------------------------------- device
+struct DeviceInfo {
+  bool ok = false;
+  int sms = 0;
+  int dev = -1;
+};
+static int device_info(DeviceInfo* out) {
+  int dev = 0;
+  CSR_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  CSR_CUDA(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10) return fail(CSR_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library is sm_100a only", dev, prop.major, prop.minor);
+  out->ok = true;
+  out->sms = prop.multiProcessorCount;
+  out->dev = dev;
+  return CSR_OK;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(p);
+  return fn;
+}
+
+// NHWC bf16 activation buffer as a 4-D (C, W, H, N) tensor; box = 64 channels x box_w x box_h x 1, 128B swizzle,
+// out-of-bounds -> zeros (this IS the convolution's zero padding).
+static int encode_act_map(CUtensorMap* m, const void* base, int N, int H, int W, int C, int box_w, int box_h) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return fail(CSR_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(CSR_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for N%d H%d W%d C%d box %dx%d", (int)r, N, H, W, C, box_w, box_h);
+  return CSR_OK;
+}
+
+// ------------------------------------------------------------------------------------------- layer table
+struct LayerSpec {
+  std::string name;
+  int cout, cin, kh, kw;
+};
+
+static int check_net(const CsrNetDesc* net) {
+  if (!net) return fail(CSR_ERR_BAD_ARG, "net descriptor is null");
+  if (net->in_channels < 1 || net->in_channels > 16) return fail(CSR_ERR_UNSUPPORTED, "in_channels %d not in [1,16]", net->in_channels);
+  if (net->out_channels != 1) return fail(CSR_ERR_UNSUPPORTED, "out_channels must be 1 (SRCNN tail takes 1+1+1 channels, esrgan.py:87)");
+  if (net->nf != 64) return fail(CSR_ERR_UNSUPPORTED, "nf must be 64");
+  if (net->gc != 16 && net->gc != 32) return fail(CSR_ERR_UNSUPPORTED, "gc must be 16 or 32");
+  if (net->nb < 1 || net->nb > 64) return fail(CSR_ERR_UNSUPPORTED, "nb %d not in [1,64]", net->nb);
+  if (net->scale != 4) return fail(CSR_ERR_UNSUPPORTED, "scale must be 4");
+  return CSR_OK;
+}
+
+// state_dict order of the reference generator (esrgan.py:72-87, srcnn.py:9-11)
+static std::vector<LayerSpec> layer_table(const CsrNetDesc& d) {
+  std::vector<LayerSpec> v;
+  v.push_back({"conv_first", d.nf, d.in_channels, 3, 3});
+  for (int i = 0; i < d.nb; ++i)
+    for (int r = 1; r <= 3; ++r) {
+      const std::string pre = "RRDB_trunk." + std::to_string(i) + ".RDB" + std::to_string(r) + ".conv";
+      for (int k = 1; k <= 4; ++k) v.push_back({pre + std::to_string(k), d.gc, d.nf + (k - 1) * d.gc, 3, 3});
+      v.push_back({pre + "5", d.nf, d.nf + 4 * d.gc, 3, 3});
+    }
+  v.push_back({"trunk_conv", d.nf, d.nf, 3, 3});
+  v.push_back({"upconv1", d.nf, d.nf, 3, 3});
+  v.push_back({"upconv2", d.nf, d.nf, 3, 3});
+  v.push_back({"HRconv", d.nf, d.nf, 3, 3});
+  v.push_back({"conv_last", d.out_channels, d.nf, 3, 3});
+  v.push_back({"srcnn.conv1", 64, 3, 9, 9});
+  v.push_back({"srcnn.conv2", 32, 64, 1, 1});
+  v.push_back({"srcnn.conv3", d.out_channels, 32, 5, 5});
+  return v;
+}
+
+// Packed form of one layer: the output channels may be split so that one part's weights fit in shared memory.
+constexpr int kMaxResidentWeightBytes = 168 * 1024;
+struct PackPart {
+  int co_lo, n_store, npad;
+  size_t w_off, b_off;
+  int w_bytes;
+};
+struct PackLayer {
+  int cin_pad;
+  std::vector<PackPart> parts;
+};
+static int part_weight_bytes(const LayerSpec& L, int npad) { return L.kh * L.kw * ((L.cin + 15) / 16 * 16) * npad * 2; }
+
+static std::vector<PackLayer> pack_layout(const std::vector<LayerSpec>& layers, size_t* total) {
+  std::vector<PackLayer> out;
+  size_t off = 0;
+  for (const auto& L : layers) {
+    PackLayer pl;
+    pl.cin_pad = (L.cin + 15) / 16 * 16;
+    const int npad_full = (L.cout + 15) / 16 * 16;
+    int nsplit = 1;
+    while (part_weight_bytes(L, ceil_div(npad_full / 16, nsplit) * 16) > kMaxResidentWeightBytes && nsplit < npad_full / 16) ++nsplit;
+    const int per = ceil_div(npad_full / 16, nsplit) * 16;
+    for (int lo = 0; lo < npad_full; lo += per) {
+      PackPart pp;
+      pp.co_lo = lo;
+      pp.npad = std::min(per, npad_full - lo);
+      pp.n_store = std::min(L.cout - lo, pp.npad);
+      pp.w_bytes = part_weight_bytes(L, pp.npad);
+      pp.w_off = off;
+      off = align_up(off + pp.w_bytes, 128);
+      pp.b_off = off;
+      off = align_up(off + pp.npad * 4, 128);
+      pl.parts.push_back(pp);
+    }
+    out.push_back(pl);
+  }
+  *total = off;
+  return out;
+}
+
+// ------------------------------------------------------------------------------------------- tiling
+struct Tiling {
+  int SW, TH, TW, win_rows, win_bytes, slot_bytes, n_slots;
+};
+static int choose_tiling(int H, int W, int KH, int KW, int w_bytes, int n_kblocks, Tiling* out) {
+  const int fixed = 1024 + (int)align_up(w_bytes, 128) + 1024 + 512;
+  double best = -1;
+  for (int SW = 16; SW <= 128; SW *= 2) {
+    if (g_opt_force_sw && SW != g_opt_force_sw) continue;
+    const int TW = SW - (KW - 1);
+    if (TW < 1) continue;
+    const int TH = kTileM / SW;
+    const int win_rows = TH + KH - 1;
+    const int win_bytes = win_rows * SW * 128;
+    const int slot_bytes = (int)align_up(win_bytes + (KW - 1) * 128, 1024);
+    const int slots = std::min(g_opt_max_slots, (kSmemLimit - fixed) / slot_bytes);
+    if (slots < 1) continue;
+    const double tiles = (double)ceil_div(H, TH) * ceil_div(W, TW);
+    double eff = (double)H * W / (tiles * kTileM);
+    if (slots < std::min(2, n_kblocks + 1)) eff *= 0.7;  // no load/MMA overlap
+    eff -= 1e-4 * win_bytes / (double)(kTileM * 128);    // tie-break: less halo traffic
+    if (eff > best) {
+      best = eff;
+      *out = {SW, TH, TW, win_rows, win_bytes, slot_bytes, slots};
+    }
+  }
+  if (best < 0) return fail(CSR_ERR_UNSUPPORTED, "no tile shape fits shared memory (weights %d bytes, %dx%d kernel)", w_bytes, KH, KW);
+  return CSR_OK;
+}
+
+// One launch: parameters + its input tensor map.
+struct ConvLaunch {
+  ConvParams p;
+  CUtensorMap tmap;
+  size_t w_off = 0, b_off = 0;  // offsets into the packed blob (resolved at forward time)
+};
+
+struct ConvIO {
+  const void* in; int in_C, cin_off;
+  void* out; int out_C, out_coff, out_mode;
+  int act;
+  const void* r1; int r1_C, r1_coff; float s1;
+  const void* r2; int r2_C, r2_coff; float s2;
+};
+
+static int build_conv(const LayerSpec& L, const PackLayer& pl, const PackPart& pp, int N, int H, int W, const ConvIO& io,
+                      ConvLaunch* cl) {
+  if (io.in_C % 64 != 0) return fail(CSR_ERR_BAD_ARG, "input buffer channels (%d) must be a multiple of 64", io.in_C);
+  if ((io.out_mode != CSR_OUT_F32_PLANAR) && ((io.out_C % 8) || (io.out_coff % 8))) return fail(CSR_ERR_BAD_ARG, "output channel stride/offset must be multiples of 8");
+  ConvParams& p = cl->p;
+  memset(&p, 0, sizeof(p));
+  p.N = N; p.H = H; p.W = W;
+  p.KH = L.kh; p.KW = L.kw; p.PH = L.kh / 2; p.PW = L.kw / 2;
+  p.cin_off = io.cin_off;
+  p.cin = pl.cin_pad;
+  if (io.cin_off + p.cin > io.in_C)
+    return fail(CSR_ERR_BAD_ARG, "conv reads channels [%d,%d) of a %d-channel buffer", io.cin_off, io.cin_off + p.cin, io.in_C);
+  p.npad = pp.npad;
+  p.n_store = pp.n_store;
+  p.n_kblocks = ceil_div(p.cin, 64);
+  p.w_bytes = pp.w_bytes;
+  Tiling tl;
+  int rc = choose_tiling(H, W, L.kh, L.kw, p.w_bytes, p.n_kblocks, &tl);
+  if (rc) return rc;
+  p.SW = tl.SW; p.TH = tl.TH; p.TW = tl.TW;
+  p.sw_shift = 0;
+  while ((1 << p.sw_shift) < p.SW) ++p.sw_shift;
+  p.tiles_x = ceil_div(W, p.TW);
+  p.tiles_y = ceil_div(H, p.TH);
+  p.num_tiles = p.tiles_x * p.tiles_y * N;
+  p.win_rows = tl.win_rows; p.win_bytes = tl.win_bytes; p.slot_bytes = tl.slot_bytes; p.n_slots = tl.n_slots;
+  int cols = 32;
+  while (cols < 2 * p.npad) cols *= 2;
+  if (cols > 512) return fail(CSR_ERR_UNSUPPORTED, "npad %d needs more than 512 TMEM columns", p.npad);
+  p.tmem_cols = cols;
+  p.a_base_off_mode = g_opt_base_off_mode;
+  p.act = io.act;
+  p.s1 = io.s1; p.s2 = io.s2;
+  p.r1 = io.r1; p.r1_C = io.r1_C; p.r1_coff = io.r1_coff + pp.co_lo;
+  p.r2 = io.r2; p.r2_C = io.r2_C; p.r2_coff = io.r2_coff + pp.co_lo;
+  p.out = io.out; p.out_C = io.out_C; p.out_coff = io.out_coff + pp.co_lo; p.out_mode = io.out_mode;
+  cl->w_off = pp.w_off; cl->b_off = pp.b_off;
+  return encode_act_map(&cl->tmap, io.in, N, H, W, io.in_C, p.SW, p.win_rows);
+}
+
+// ------------------------------------------------------------------------------------------- plan
+}  // namespace csr
+
+struct CsrPlan {
+  CsrNetDesc net;
+  int N, h, w;
+  int sms;
+  std::vector<csr::ConvLaunch> convs;   // in execution order
+  int idx_conv_last;                    // pack_aux runs right before this conv
+  void* xin; void* sin;
+  size_t packed_bytes;
+};
+
+namespace csr {
+
+struct WsLayout {
+  size_t xin, fea0, cat[3], up1, up2, hrA, hrB, total;
+  int ccat;
+};
+static WsLayout ws_layout(const CsrNetDesc& d, int N, int h, int w) {
+  WsLayout L;
+  const size_t lr = (size_t)N * h * w, mid = lr * 4, hr = lr * 16;
+  L.ccat = (int)align_up(d.nf + 4 * d.gc, 64);
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 1024); return o; };
+  L.xin = take(lr * 64 * 2);
+  L.fea0 = take(lr * 64 * 2);
+  for (int i = 0; i < 3; ++i) L.cat[i] = take(lr * L.ccat * 2);
+  L.up1 = take(mid * 64 * 2);
+  L.up2 = take(hr * 64 * 2);   // upconv2 input, later reused as the SRCNN input [out, elev, mask, 0...]
+  L.hrA = take(hr * 64 * 2);
+  L.hrB = take(hr * 64 * 2);
+  L.total = off;
+  return L;
+}
+
+static int plan_build(CsrPlan* P, void* ws) {
+  const CsrNetDesc& d = P->net;
+  const int N = P->N, h = P->h, w = P->w;
+  const WsLayout L = ws_layout(d, N, h, w);
+  uint8_t* base = reinterpret_cast<uint8_t*>(ws);
+  void* xin = base + L.xin; void* fea0 = base + L.fea0;
+  void* cat[3] = {base + L.cat[0], base + L.cat[1], base + L.cat[2]};
+  void* up1 = base + L.up1; void* up2 = base + L.up2; void* hrA = base + L.hrA; void* hrB = base + L.hrB;
+  P->xin = xin; P->sin = up2;
+  const std::vector<LayerSpec> layers = layer_table(d);
+  size_t total = 0;
+  const std::vector<PackLayer> packs = pack_layout(layers, &total);
+  P->packed_bytes = total;
+  const int C = L.ccat, nf = d.nf, gc = d.gc;
+  int li = 0;
+  auto add = [&](int H, int W, ConvIO io, bool advance = true) -> int {
+    const LayerSpec& Ls = layers[li];
+    const PackLayer& pl = packs[li];
+    for (const PackPart& pp : pl.parts) {
+      ConvLaunch cl;
+      int rc = build_conv(Ls, pl, pp, N, H, W, io, &cl);
+      if (rc) return rc;
+      P->convs.push_back(cl);
+    }
+    if (advance) ++li;
+    return CSR_OK;
+  };
+  int rc;
+  // conv_first (esrgan.py:90) has two consumers: the first RRDB (reads x from concat buffer A) and the trunk skip-add
+  // 33 layers later (A is overwritten by then).  The layer is tiny (K = 16), so it is simply run into both places.
+  rc = add(h, w, {xin, 64, 0, fea0, 64, 0, CSR_OUT_BF16_NHWC, CSR_ACT_NONE, nullptr, 0, 0, 1.f, nullptr, 0, 0, 1.f}, false);
+  if (rc) return rc;
+  rc = add(h, w, {xin, 64, 0, cat[0], C, 0, CSR_OUT_BF16_NHWC, CSR_ACT_NONE, nullptr, 0, 0, 1.f, nullptr, 0, 0, 1.f});
+  if (rc) return rc;
+  for (int i = 0; i < d.nb; ++i) {
+    // RRDB i: its input x lives in channels [0,nf) of concat buffer A; the three RDBs rotate A->B->C->A, so A's x
+    // survives until RDB3's epilogue reads it as the RRDB residual and overwrites it in place.
+    for (int r = 0; r < 3; ++r) {
+      void* src = cat[r];
+      void* dst = cat[(r + 1) % 3];
+      for (int k = 1; k <= 4; ++k) {
+        // x_k = lrelu(conv_k(cat(x, x1..x_{k-1})))  written into its concat slice  (esrgan.py:33-36)
+        rc = add(h, w, {src, C, 0, src, C, nf + (k - 1) * gc, CSR_OUT_BF16_NHWC, CSR_ACT_LRELU02, nullptr, 0, 0, 1.f, nullptr, 0, 0, 1.f});
+        if (rc) return rc;
+      }
+      // x5*0.2 + x  (esrgan.py:37-38); RDB3 additionally applies the RRDB residual out*0.2 + x_rrdb (esrgan.py:54)
+      if (r < 2)
+        rc = add(h, w, {src, C, 0, dst, C, 0, CSR_OUT_BF16_NHWC, CSR_ACT_NONE, src, C, 0, 0.2f, nullptr, 0, 0, 1.f});
+      else
+        rc = add(h, w, {src, C, 0, cat[0], C, 0, CSR_OUT_BF16_NHWC, CSR_ACT_NONE, src, C, 0, 0.2f, cat[0], C, 0, 0.2f});
+      if (rc) return rc;
+    }
+  }
+  // trunk_conv + skip (esrgan.py:91-92), stored nearest-x2 upsampled (esrgan.py:94)
+  rc = add(h, w, {cat[0], C, 0, up1, 64, 0, CSR_OUT_BF16_NHWC_UP2, CSR_ACT_NONE, fea0, 64, 0, 1.f, nullptr, 0, 0, 1.f});
+  if (rc) return rc;
+  // upconv1 + lrelu, stored nearest-x2 upsampled (esrgan.py:94,97)
+  rc = add(2 * h, 2 * w, {up1, 64, 0, up2, 64, 0, CSR_OUT_BF16_NHWC_UP2, CSR_ACT_LRELU02, nullptr, 0, 0, 1.f, nullptr, 0, 0, 1.f});
+  if (rc) return rc;
+  const int H = 4 * h, W = 4 * w;
+  rc = add(H, W, {up2, 64, 0, hrA, 64, 0, CSR_OUT_BF16_NHWC, CSR_ACT_LRELU02, nullptr, 0, 0, 1.f, nullptr, 0, 0, 1.f});  // upconv2
+  if (rc) return rc;
+  rc = add(H, W, {hrA, 64, 0, hrB, 64, 0, CSR_OUT_BF16_NHWC, CSR_ACT_LRELU02, nullptr, 0, 0, 1.f, nullptr, 0, 0, 1.f});  // HRconv (esrgan.py:99)
+  if (rc) return rc;
+  P->idx_conv_last = (int)P->convs.size();
+  rc = add(H, W, {hrB, 64, 0, up2, 64, 0, CSR_OUT_BF16_NHWC, CSR_ACT_NONE, nullptr, 0, 0, 1.f, nullptr, 0, 0, 1.f});     // conv_last -> sin ch0
+  if (rc) return rc;
+  rc = add(H, W, {up2, 64, 0, hrA, 64, 0, CSR_OUT_BF16_NHWC, CSR_ACT_RELU, nullptr, 0, 0, 1.f, nullptr, 0, 0, 1.f});     // srcnn.conv1 9x9
+  if (rc) return rc;
+  rc = add(H, W, {hrA, 64, 0, hrB, 64, 0, CSR_OUT_BF16_NHWC, CSR_ACT_RELU, nullptr, 0, 0, 1.f, nullptr, 0, 0, 1.f});     // srcnn.conv2 1x1
+  if (rc) return rc;
+  rc = add(H, W, {hrB, 64, 0, nullptr, 1, 0, CSR_OUT_F32_PLANAR, CSR_ACT_NONE, nullptr, 0, 0, 1.f, nullptr, 0, 0, 1.f}); // srcnn.conv3 5x5
+  return rc;
+}
+
+}  // namespace csr
+
+using namespace csr;
+
+// =========================================================================================== C-ABI
+extern "C" {
+
+int csr_abi_version(void) { return CSR_ABI_VERSION; }
+const char* csr_last_error(void) { return g_err; }
+
+int csr_device_check(void) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) return fail(CSR_ERR_CUDA, "no CUDA device: %s", cudaGetErrorString(e));
+  DeviceInfo di;
+  return device_info(&di);
+}
+
+int csr_set_option(int32_t key, int32_t value) {
+  switch (key) {
+    case 1: g_opt_base_off_mode = value; return CSR_OK;
+    case 2: g_opt_force_sw = value; return CSR_OK;
+    case 3: g_opt_max_slots = value < 1 ? 1 : value; return CSR_OK;
+    default: return fail(CSR_ERR_BAD_ARG, "unknown option key %d", key);
+  }
+}
+
+int64_t csr_kernel_launch_count(void) { return g_launches.load(); }
+
+int csr_num_layers(const CsrNetDesc* net) {
+  int rc = check_net(net);
+  if (rc) return rc;
+  return (int)layer_table(*net).size();
+}
+
+int csr_layer_shape(const CsrNetDesc* net, int32_t i, int32_t shape4[4], char* name, size_t name_cap) {
+  int rc = check_net(net);
+  if (rc) return rc;
+  const auto t = layer_table(*net);
+  if (i < 0 || i >= (int)t.size() || !shape4) return fail(CSR_ERR_BAD_ARG, "layer index %d out of range", i);
+  shape4[0] = t[i].cout; shape4[1] = t[i].cin; shape4[2] = t[i].kh; shape4[3] = t[i].kw;
+  if (name && name_cap) snprintf(name, name_cap, "%s", t[i].name.c_str());
+  return CSR_OK;
+}
+
+size_t csr_packed_weight_bytes(const CsrNetDesc* net) {
+  if (check_net(net)) return 0;
+  size_t total = 0;
+  pack_layout(layer_table(*net), &total);
+  return total;
+}
+
+int csr_pack_weights(const CsrNetDesc* net, const float* const* w, const float* const* b, void* packed, size_t packed_bytes,
+                     void* stream) {
+  int rc = check_net(net);
+  if (rc) return rc;
+  if (!w || !b || !packed) return fail(CSR_ERR_BAD_ARG, "null pointer");
+  const auto layers = layer_table(*net);
+  size_t total = 0;
+  const auto packs = pack_layout(layers, &total);
+  if (packed_bytes < total) return fail(CSR_ERR_WORKSPACE, "packed buffer %zu < %zu bytes", packed_bytes, total);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  uint8_t* base = reinterpret_cast<uint8_t*>(packed);
+  for (size_t i = 0; i < layers.size(); ++i) {
+    if (!w[i] || !b[i]) return fail(CSR_ERR_BAD_ARG, "null weight/bias pointer for layer %zu", i);
+    for (const PackPart& pp : packs[i].parts) {
+      CSR_CUDA(launch_pack_weight(w[i], base + pp.w_off, layers[i].cout, layers[i].cin, layers[i].kh, layers[i].kw, pp.co_lo, pp.npad,
+                                  packs[i].cin_pad, s));
+      CSR_CUDA(launch_pack_bias(b[i], reinterpret_cast<float*>(base + pp.b_off), layers[i].cout, pp.co_lo, pp.npad, s));
+      g_launches += 2;
+    }
+  }
+  return CSR_OK;
+}
+
+size_t csr_workspace_bytes(const CsrNetDesc* net, int32_t n, int32_t h, int32_t w) {
+  if (check_net(net) || n < 1 || h < 1 || w < 1) return 0;
+  return ws_layout(*net, n, h, w).total;
+}
+
+int csr_plan_create(const CsrNetDesc* net, int32_t n, int32_t h, int32_t w, void* workspace, size_t workspace_bytes, CsrPlan** plan) {
+  int rc = check_net(net);
+  if (rc) return rc;
+  if (!plan || !workspace) return fail(CSR_ERR_BAD_ARG, "null pointer");
+  if (n < 1 || h < 1 || w < 1) return fail(CSR_ERR_BAD_ARG, "non-positive shape n=%d h=%d w=%d", n, h, w);
+  if (reinterpret_cast<uintptr_t>(workspace) % 1024) return fail(CSR_ERR_BAD_ARG, "workspace must be 1024-byte aligned");
+  const size_t need = ws_layout(*net, n, h, w).total;
+  if (workspace_bytes < need) return fail(CSR_ERR_WORKSPACE, "workspace %zu < %zu bytes", workspace_bytes, need);
+  DeviceInfo di;
+  rc = device_info(&di);
+  if (rc) return rc;
+  CsrPlan* P = new CsrPlan();
+  P->net = *net; P->N = n; P->h = h; P->w = w; P->sms = di.sms;
+  rc = plan_build(P, workspace);
+  if (rc) { delete P; return rc; }
+  *plan = P;
+  return CSR_OK;
+}
+
+int csr_plan_num_launches(const CsrPlan* plan) { return plan ? (int)plan->convs.size() + 2 : 0; }
+
+void csr_plan_destroy(CsrPlan* plan) { delete plan; }
+
+int csr_plan_forward(CsrPlan* P, const void* packed, const float* x, const float* elev, const float* mask, float* out, void* stream) {
+  if (!P || !packed || !x || !elev || !mask || !out) return fail(CSR_ERR_BAD_ARG, "null pointer");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const uint8_t* pk = reinterpret_cast<const uint8_t*>(packed);
+  CSR_CUDA(launch_nchw_to_nhwc(x, P->xin, P->N, P->net.in_channels, P->h, P->w, 64, 16, s));
+  ++g_launches;
+  for (size_t i = 0; i < P->convs.size(); ++i) {
+    if ((int)i == P->idx_conv_last) {
+      CSR_CUDA(launch_pack_aux(elev, mask, P->sin, (long)P->N * P->h * P->w * 16, 64, s));
+      ++g_launches;
+    }
+    ConvLaunch& cl = P->convs[i];
+    cl.p.wpk = pk + cl.w_off;
+    cl.p.bias = reinterpret_cast<const float*>(pk + cl.b_off);
+    if (cl.p.out_mode == CSR_OUT_F32_PLANAR) cl.p.out = out;
+    int e = launch_conv_tc(cl.p, cl.tmap, P->sms, s);
+    if (e) return fail(CSR_ERR_CUDA, "conv launch %zu failed: %s", i, cudaGetErrorString((cudaError_t)e));
+    ++g_launches;
+  }
+  return CSR_OK;
+}
+
+int csr_generator_forward(const CsrNetDesc* net, const void* packed, const float* x, const float* elev, const float* mask, float* out,
+                          void* workspace, size_t workspace_bytes, int32_t n, int32_t h, int32_t w, void* stream) {
+  CsrPlan* P = nullptr;
+  int rc = csr_plan_create(net, n, h, w, workspace, workspace_bytes, &P);
+  if (rc) return rc;
+  rc = csr_plan_forward(P, packed, x, elev, mask, out, stream);
+  csr_plan_destroy(P);
+  return rc;
+}
+
+// ---- single conv --------------------------------------------------------------------------------------
+static int conv_desc_to_layer(const CsrConvDesc* d, LayerSpec* L) {
+  if (!d) return fail(CSR_ERR_BAD_ARG, "conv descriptor is null");
+  if (d->n < 1 || d->h < 1 || d->w < 1 || d->cin < 1 || d->cout < 1) return fail(CSR_ERR_BAD_ARG, "non-positive conv shape");
+  if (!(d->kh & 1) || !(d->kw & 1) || d->kh > 9 || d->kw > 9) return fail(CSR_ERR_UNSUPPORTED, "kernel %dx%d (odd, <= 9 supported)", d->kh, d->kw);
+  if (d->cout > 256) return fail(CSR_ERR_UNSUPPORTED, "cout %d > 256", d->cout);
+  if (d->out_mode == CSR_OUT_F32_PLANAR && d->cout != 1) return fail(CSR_ERR_UNSUPPORTED, "fp32 planar output needs cout == 1");
+  *L = {"conv", d->cout, d->cin, d->kh, d->kw};
+  return CSR_OK;
+}
+
+size_t csr_conv2d_scratch_bytes(const CsrConvDesc* d) {
+  LayerSpec L;
+  if (conv_desc_to_layer(d, &L)) return 0;
+  size_t total = 0;
+  pack_layout({L}, &total);
+  return total;
+}
+
+int csr_conv2d_nhwc(const CsrConvDesc* d, const void* in, const float* weight, const float* bias, void* out, const void* res1,
+                    const void* res2, void* scratch, size_t scratch_bytes, void* stream) {
+  LayerSpec L;
+  int rc = conv_desc_to_layer(d, &L);
+  if (rc) return rc;
+  if (!in || !weight || !bias || !out || !scratch) return fail(CSR_ERR_BAD_ARG, "null pointer");
+  DeviceInfo di;
+  rc = device_info(&di);
+  if (rc) return rc;
+  size_t total = 0;
+  const auto packs = pack_layout({L}, &total);
+  if (scratch_bytes < total) return fail(CSR_ERR_WORKSPACE, "scratch %zu < %zu bytes", scratch_bytes, total);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  uint8_t* base = reinterpret_cast<uint8_t*>(scratch);
+  ConvIO io = {in, d->in_c, 0, out, d->out_c, d->out_coff, d->out_mode, d->act,
+               res1, d->res1_c, d->res1_coff, d->scale1, res2, d->res2_c, d->res2_coff, d->scale2};
+  for (const PackPart& pp : packs[0].parts) {
+    CSR_CUDA(launch_pack_weight(weight, base + pp.w_off, L.cout, L.cin, L.kh, L.kw, pp.co_lo, pp.npad, packs[0].cin_pad, s));
+    CSR_CUDA(launch_pack_bias(bias, reinterpret_cast<float*>(base + pp.b_off), L.cout, pp.co_lo, pp.npad, s));
+    ConvLaunch cl;
+    rc = build_conv(L, packs[0], pp, d->n, d->h, d->w, io, &cl);
+    if (rc) return rc;
+    cl.p.wpk = base + pp.w_off;
+    cl.p.bias = reinterpret_cast<const float*>(base + pp.b_off);
+    int e = launch_conv_tc(cl.p, cl.tmap, di.sms, s);
+    if (e) return fail(CSR_ERR_CUDA, "conv launch failed: %s", cudaGetErrorString((cudaError_t)e));
+    g_launches += 3;
+  }
+  return CSR_OK;
+}
+
+// ---- layout helpers -----------------------------------------------------------------------------------
+int csr_nchw_f32_to_nhwc_bf16(const float* src, void* dst, int32_t n, int32_t c, int32_t h, int32_t w, int32_t dst_c, int32_t zero_to,
+                              void* stream) {
+  if (!src || !dst) return fail(CSR_ERR_BAD_ARG, "null pointer");
+  if (c < 1 || c > 16 || (zero_to != 8 && zero_to != 16) || c > zero_to || dst_c % 8 || dst_c < zero_to)
+    return fail(CSR_ERR_UNSUPPORTED, "c=%d zero_to=%d dst_c=%d", c, zero_to, dst_c);
+  CSR_CUDA(launch_nchw_to_nhwc(src, dst, n, c, h, w, dst_c, zero_to, reinterpret_cast<cudaStream_t>(stream)));
+  ++g_launches;
+  return CSR_OK;
+}
+
+int csr_nhwc_bf16_to_nchw_f32(const void* src, float* dst, int32_t n, int32_t c, int32_t h, int32_t w, int32_t src_c, int32_t src_coff,
+                              void* stream) {
+  if (!src || !dst) return fail(CSR_ERR_BAD_ARG, "null pointer");
+  CSR_CUDA(launch_nhwc_to_nchw(src, dst, n, c, h, w, src_c, src_coff, reinterpret_cast<cudaStream_t>(stream)));
+  ++g_launches;
+  return CSR_OK;
+}
+
+// ---- metrics ------------------------------------------------------------------------------------------
+size_t csr_metrics_scratch_bytes(int32_t n, int32_t h, int32_t w) { return metrics_scratch_bytes(n, h, w); }
+
+int csr_masked_metrics(const float* sr, const float* hr, const float* original, const float* mask, const float* mn, const float* mx,
+                       float zmean, float zstd, float range_a, float range_b, int32_t n, int32_t h, int32_t w, float* out, void* scratch,
+                       size_t scratch_bytes, void* stream) {
+  if (!sr || !hr || !original || !mask || !out || !scratch) return fail(CSR_ERR_BAD_ARG, "null pointer");
+  if ((mn == nullptr) != (mx == nullptr)) return fail(CSR_ERR_BAD_ARG, "mn and mx must both be given or both be null");
+  if (n < 1 || h < 11 || w < 11) return fail(CSR_ERR_UNSUPPORTED, "need n>=1 and h,w >= 11 (SSIM window), got %d %d %d", n, h, w);
+  if (scratch_bytes < metrics_scratch_bytes(n, h, w)) return fail(CSR_ERR_WORKSPACE, "metrics scratch too small");
+  int launches = 0;
+  cudaError_t e = launch_masked_metrics(sr, hr, original, mask, mn, mx, zmean, zstd, range_a, range_b, n, h, w, out, scratch,
+                                        reinterpret_cast<cudaStream_t>(stream), &launches);
+  g_launches += launches;
+  if (e != cudaSuccess) return fail(CSR_ERR_CUDA, "metrics launch failed: %s", cudaGetErrorString(e));
+  return CSR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,283 @@
+// KHxKW stride-1 "same" convolution over NHWC bf16 as an implicit GEMM on tcgen05 (sm_100a).
+//
+//   D[128 pixels][npad] (fp32, TMEM)  +=  A[128 pixels][16 ch] (smem, K-major, 128B swizzle)
+//                                       x  B[npad][16 ch]       (smem, K-major, 8x16B core matrices)
+//   summed over taps (dy,dx) and 16-channel k-steps.
+//
+// Halo reuse: one TMA box per 64-channel k-block brings the (TH+KH-1) x SW pixel window of a tile into
+// shared memory ONCE (out-of-bounds pixels are zero-filled by TMA == the conv's zero padding).  A tile's 128
+// GEMM rows are the flattened window positions m = ty*SW + tx, so the A operand of tap (dy,dx) is the same
+// window read from byte offset (dy*SW+dx)*128: only the descriptor start address changes between taps.  The
+// last KW-1 columns of every window row are GEMM rows that wrap into the next row; they are computed and
+// discarded (TW = SW-(KW-1) real columns).
+//
+// Roles: warp 0 = TMA producer, warp 1 = MMA issuer (one lane) + TMEM owner, warps 2..5 = epilogue
+// (TMEM -> registers -> bias/activation/residuals -> bf16/fp32 global stores).  Accumulators are double
+// buffered in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1; the layer's packed weights stay
+// resident in shared memory for the whole persistent CTA.
+//
+// Replaces one nn.Conv2d(+LeakyReLU/ReLU, *0.2+x, cat, nearest-x2) call site of the reference generator:
+// climsr/models/esrgan.py:33-38, 50-54, 90-100 and climsr/models/srcnn.py:14-16.
+#include <cstdio>
+
+#include "conv_tc.cuh"
+#include "ptx.cuh"
+
+namespace csr {
+
+namespace {
+
+struct Tile {
+  int n, y0, x0;
+};
+
+__device__ __forceinline__ Tile decode_tile(const ConvParams& p, int t) {
+  const int per_img = p.tiles_x * p.tiles_y;
+  Tile r;
+  r.n = t / per_img;
+  const int rem = t - r.n * per_img;
+  const int ty = rem / p.tiles_x;
+  r.y0 = ty * p.TH;
+  r.x0 = (rem - ty * p.tiles_x) * p.TW;
+  return r;
+}
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  if (act == 1) return v >= 0.f ? v : 0.2f * v;
+  if (act == 2) return fmaxf(v, 0.f);
+  return v;
+}
+
+__device__ __forceinline__ void add_residual16(float (&v)[16], const void* base, size_t pix, int C, int coff, float scale) {
+  const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(base) + pix * C + coff);
+  const uint4 a = src[0];
+  const uint4 b = src[1];
+  const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    v[2 * i] = v[2 * i] * scale + bf16lo(w[i]);
+    v[2 * i + 1] = v[2 * i + 1] * scale + bf16hi(w[i]);
+  }
+}
+
+__device__ __forceinline__ void store16_bf16(void* base, size_t pix, int C, int coff, const float (&v)[16]) {
+  uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(base) + pix * C + coff);
+  uint4 a, b;
+  a.x = pack_bf16x2(v[0], v[1]);
+  a.y = pack_bf16x2(v[2], v[3]);
+  a.z = pack_bf16x2(v[4], v[5]);
+  a.w = pack_bf16x2(v[6], v[7]);
+  b.x = pack_bf16x2(v[8], v[9]);
+  b.y = pack_bf16x2(v[10], v[11]);
+  b.z = pack_bf16x2(v[12], v[13]);
+  b.w = pack_bf16x2(v[14], v[15]);
+  dst[0] = a;
+  dst[1] = b;
+}
+
+}  // namespace
+
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
+  extern __shared__ uint8_t smem_raw[];
+  // 1024-byte alignment: the 128B-swizzle pattern repeats every 8 rows x 128 B.
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t slots_addr = smem_base;
+  const uint32_t w_addr = slots_addr + static_cast<uint32_t>(p.n_slots) * p.slot_bytes;
+  const uint32_t bias_addr = w_addr + ((p.w_bytes + 127) & ~127);
+  const uint32_t bar_addr = bias_addr + 1024;           // up to 256 fp32 biases
+  // barriers: [0] weights, [1..S] a_full, [1+S..2S] a_empty, then acc_full[2], acc_empty[2]
+  const int S = p.n_slots;
+  auto bar_w = bar_addr;
+  auto bar_a_full = [&](int s) { return bar_addr + 8u * (1 + s); };
+  auto bar_a_empty = [&](int s) { return bar_addr + 8u * (1 + S + s); };
+  auto bar_acc_full = [&](int b) { return bar_addr + 8u * (1 + 2 * S + b); };
+  auto bar_acc_empty = [&](int b) { return bar_addr + 8u * (3 + 2 * S + b); };
+  const uint32_t tmem_slot_addr = bar_addr + 8u * (5 + 2 * S);
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  float* bias_s = reinterpret_cast<float*>(smem_gen + (bias_addr - smem_base));
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot_addr - smem_base));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmap);
+    mbar_init(bar_w, 1);
+    for (int s = 0; s < S; ++s) {
+      mbar_init(bar_a_full(s), 1);
+      mbar_init(bar_a_empty(s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(bar_acc_full(b), 1);
+      mbar_init(bar_acc_empty(b), 128);
+    }
+    fence_mbar_init();
+    fence_proxy_async_smem();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot_addr, p.tmem_cols);
+    tmem_relinquish();
+  }
+  for (int i = threadIdx.x; i < p.npad; i += blockDim.x) bias_s[i] = p.bias[i];
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int taps = p.KH * p.KW;
+  const int ksteps_total = p.cin >> 4;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      // layer weights: resident for the whole CTA
+      mbar_arrive_expect_tx(bar_w, p.w_bytes);
+      const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.wpk);
+      for (int off = 0; off < p.w_bytes; off += 32768) {
+        const int nbytes = min(32768, p.w_bytes - off);
+        bulk_load(w_addr + off, wsrc + off, nbytes, bar_w);
+      }
+      int j = 0;
+      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+        const Tile tl = decode_tile(p, t);
+        for (int kb = 0; kb < p.n_kblocks; ++kb, ++j) {
+          const int slot = j % S;
+          const int use = j / S;
+          mbar_wait(bar_a_empty(slot), (use & 1) ^ 1);
+          mbar_arrive_expect_tx(bar_a_full(slot), p.win_bytes);
+          tma_load_4d(slots_addr + slot * p.slot_bytes, &tmap, bar_a_full(slot), p.cin_off + kb * 64, tl.x0 - p.PW,
+                      tl.y0 - p.PH, tl.n);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(kTileM, p.npad);
+      const uint32_t b_step = p.npad * 32;  // bytes of one (tap,kstep) weight block
+      mbar_wait(bar_w, 0);
+      tc_fence_after();
+      int j = 0, it = 0;
+      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
+        const int buf = it & 1;
+        mbar_wait(bar_acc_empty(buf), ((it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + buf * p.npad;
+        uint32_t accumulate = 0;
+        for (int kb = 0; kb < p.n_kblocks; ++kb, ++j) {
+          const int slot = j % S;
+          mbar_wait(bar_a_full(slot), (j / S) & 1);
+          tc_fence_after();
+          const uint32_t a_base = slots_addr + slot * p.slot_bytes;
+          const int ks_here = min(4, ksteps_total - kb * 4);
+          for (int tap = 0; tap < taps; ++tap) {
+            const int dy = tap / p.KW;
+            const int dx = tap - dy * p.KW;
+            const uint32_t a_tap = a_base + static_cast<uint32_t>(dy * p.SW + dx) * 128u;
+            const uint32_t b_tap = w_addr + static_cast<uint32_t>(tap * ksteps_total + kb * 4) * b_step;
+            for (int ks = 0; ks < ks_here; ++ks) {
+              const uint32_t a_addr = a_tap + ks * 32;
+              const uint32_t boff = p.a_base_off_mode ? ((a_addr >> 7) & 7u) : 0u;
+              const uint64_t adesc = make_sdesc(a_addr, 16, 1024, 2, boff);
+              const uint64_t bdesc = make_sdesc(b_tap + ks * b_step, 128, 256, 0, 0);
+              umma_bf16(d_tmem, adesc, bdesc, idesc, accumulate);
+              accumulate = 1;
+            }
+          }
+          umma_commit(bar_a_empty(slot));  // window slot reusable once these MMAs have read it
+        }
+        umma_commit(bar_acc_full(buf));    // accumulator complete -> epilogue
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5 -> TMEM lane groups 2,3,0,1) =====================
+    const int lane_grp = warp & 3;
+    const int m = lane_grp * 32 + lane;
+    const int ty = m >> p.sw_shift;
+    const int tx = m & (p.SW - 1);
+    const int n_chunks = p.npad >> 4;
+    int it = 0;
+    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
+      const Tile tl = decode_tile(p, t);
+      const int buf = it & 1;
+      const int y = tl.y0 + ty;
+      const int x = tl.x0 + tx;
+      const bool valid = (tx < p.TW) && (y < p.H) && (x < p.W);
+      const size_t pix = (static_cast<size_t>(tl.n) * p.H + y) * p.W + x;
+      mbar_wait(bar_acc_full(buf), (it >> 1) & 1);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16) + buf * p.npad;
+      for (int c = 0; c < n_chunks; ++c) {
+        uint32_t raw[16];
+        tmem_ld16(t_addr + c * 16, raw);
+        tmem_ld_wait();
+        const int ch0 = c * 16;
+        if (valid && ch0 < p.n_store) {
+          float v[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = apply_act(__uint_as_float(raw[i]) + bias_s[ch0 + i], p.act);
+          if (p.r1) add_residual16(v, p.r1, pix, p.r1_C, p.r1_coff + ch0, p.s1);
+          if (p.r2) add_residual16(v, p.r2, pix, p.r2_C, p.r2_coff + ch0, p.s2);
+          if (p.out_mode == 2) {
+            reinterpret_cast<float*>(p.out)[pix] = v[0];
+          } else if (p.n_store - ch0 >= 16) {
+            if (p.out_mode == 0) {
+              store16_bf16(p.out, pix, p.out_C, p.out_coff + ch0, v);
+            } else {
+              const int W2 = 2 * p.W;
+              const size_t q = (static_cast<size_t>(tl.n) * 2 * p.H + 2 * y) * W2 + 2 * x;
+              store16_bf16(p.out, q, p.out_C, p.out_coff + ch0, v);
+              store16_bf16(p.out, q + 1, p.out_C, p.out_coff + ch0, v);
+              store16_bf16(p.out, q + W2, p.out_C, p.out_coff + ch0, v);
+              store16_bf16(p.out, q + W2 + 1, p.out_C, p.out_coff + ch0, v);
+            }
+          } else {
+            // ragged tail (e.g. conv_last: one real channel)
+            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out);
+            for (int i = 0; i < p.n_store - ch0; ++i) {
+              const __nv_bfloat16 bv = __float2bfloat16_rn(v[i]);
+              if (p.out_mode == 0) {
+                o[pix * p.out_C + p.out_coff + ch0 + i] = bv;
+              } else {
+                const int W2 = 2 * p.W;
+                const size_t q = (static_cast<size_t>(tl.n) * 2 * p.H + 2 * y) * W2 + 2 * x;
+                const size_t cofs = p.out_coff + ch0 + i;
+                o[q * p.out_C + cofs] = bv;
+                o[(q + 1) * p.out_C + cofs] = bv;
+                o[(q + W2) * p.out_C + cofs] = bv;
+                o[(q + W2 + 1) * p.out_C + cofs] = bv;
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(bar_acc_empty(buf));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+int launch_conv_tc(const ConvParams& p, const CUtensorMap& tmap, int num_sms, cudaStream_t stream) {
+  const size_t smem = 1024 /*alignment slack*/ + static_cast<size_t>(p.n_slots) * p.slot_bytes + ((p.w_bytes + 127) & ~127) +
+                      1024 /*bias*/ + 8 * (5 + 2 * p.n_slots) + 16;
+  if (smem > static_cast<size_t>(kSmemLimit)) return static_cast<int>(cudaErrorInvalidValue);
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    configured = kSmemLimit;
+  }
+  const int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
+  conv_tc_kernel<<<grid, kConvThreads, smem, stream>>>(p, tmap);
+  return static_cast<int>(cudaGetLastError());
+}
+
+}  // namespace csr

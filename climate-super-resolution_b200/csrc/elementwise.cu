@@ -1,0 +1,124 @@
+// Layout / packing kernels around the conv hot path (all HBM-bound, vectorised, coalesced).
+#include "elementwise.cuh"
+#include "ptx.cuh"
+
+namespace csr {
+
+// ---- weights: fp32 OIHW -> bf16 UMMA B tiles ------------------------------------------------------------
+// Packed layout per layer: [tap][kstep = cin_pad/16][ngrp = npad/8][kchunk 2][row 8][elem 8]; one (tap,kstep)
+// block is an npad x 16 K-major operand made of 8x16-byte core matrices (LBO 128 B between the two k-chunks,
+// SBO 256 B between 8-row groups).  Rows >= cout and channels >= cin are zero.
+__global__ void pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ dst, int cout, int cin, int kh,
+                                   int kw, int co_lo, int npad, int cin_pad) {
+  const int ksteps = cin_pad >> 4;
+  const long total = static_cast<long>(kh) * kw * ksteps * npad * 16;
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const int e = i & 7;
+    const int row = (i >> 3) & 7;
+    const int kchunk = (i >> 6) & 1;
+    long r = i >> 7;
+    const int ngrp = r % (npad >> 3);
+    r /= (npad >> 3);
+    const int ks = r % ksteps;
+    const int tap = r / ksteps;
+    const int co = co_lo + ngrp * 8 + row;
+    const int ci = ks * 16 + kchunk * 8 + e;
+    float v = 0.f;
+    if (ngrp * 8 + row < npad && co < cout && ci < cin) {
+      const int dy = tap / kw, dx = tap % kw;
+      v = w[((static_cast<long>(co) * cin + ci) * kh + dy) * kw + dx];
+    }
+    dst[i] = __float2bfloat16_rn(v);
+  }
+}
+
+__global__ void pack_bias_kernel(const float* __restrict__ b, float* __restrict__ dst, int cout, int co_lo, int npad) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < npad) dst[i] = (co_lo + i < cout) ? b[co_lo + i] : 0.f;
+}
+
+// ---- activations -----------------------------------------------------------------------------------------
+// fp32 NCHW (n,c,h,w) -> bf16 NHWC (n,h,w,dst_c): channels [0,c) converted, [c,zero_to) zeroed (zero_to <= 16,
+// multiple of 8).  One thread per pixel; reads are coalesced across pixels for each channel plane.
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long npix_per_img,
+                                    long total_pix, int c, int dst_c, int zero_to) {
+  for (long p = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; p < total_pix; p += static_cast<long>(gridDim.x) * blockDim.x) {
+    const long n = p / npix_per_img;
+    const long r = p - n * npix_per_img;
+    float v[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = (i < c) ? src[(n * c + i) * npix_per_img + r] : 0.f;
+    uint4* o = reinterpret_cast<uint4*>(dst + p * dst_c);
+    uint4 a;
+    a.x = pack_bf16x2(v[0], v[1]); a.y = pack_bf16x2(v[2], v[3]); a.z = pack_bf16x2(v[4], v[5]); a.w = pack_bf16x2(v[6], v[7]);
+    o[0] = a;
+    if (zero_to > 8) {
+      a.x = pack_bf16x2(v[8], v[9]); a.y = pack_bf16x2(v[10], v[11]); a.z = pack_bf16x2(v[12], v[13]); a.w = pack_bf16x2(v[14], v[15]);
+      o[1] = a;
+    }
+  }
+}
+
+// elev, mask fp32 (n,1,H,W) -> channels 1,2 of the SRCNN input buffer; channel 0 (conv_last's output, written later
+// by the conv epilogue) and 3..15 are zeroed.  torch.cat([out, elev, mask], 1), esrgan.py:100.
+__global__ void pack_aux_kernel(const float* __restrict__ elev, const float* __restrict__ mask, __nv_bfloat16* __restrict__ dst,
+                                long total_pix, int dst_c) {
+  for (long p = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; p < total_pix; p += static_cast<long>(gridDim.x) * blockDim.x) {
+    uint4* o = reinterpret_cast<uint4*>(dst + p * dst_c);
+    uint4 a;
+    a.x = pack_bf16x2(0.f, elev[p]);
+    a.y = pack_bf16x2(mask[p], 0.f);
+    a.z = 0u;
+    a.w = 0u;
+    o[0] = a;
+    o[1] = make_uint4(0u, 0u, 0u, 0u);
+  }
+}
+
+__global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst, long npix_per_img, long total,
+                                    int c, int src_c, int src_coff) {
+  // one thread per output element, pixel-fastest so fp32 writes coalesce
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const long r = i % npix_per_img;
+    const long nc = i / npix_per_img;
+    const long n = nc / c;
+    const int ch = nc - n * c;
+    dst[i] = __bfloat162float(src[(n * npix_per_img + r) * src_c + src_coff + ch]);
+  }
+}
+
+static inline int grid_for(long total, int block, int cap = 148 * 16) {
+  long g = (total + block - 1) / block;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return static_cast<int>(g);
+}
+
+cudaError_t launch_pack_weight(const float* w, void* dst, int cout, int cin, int kh, int kw, int co_lo, int npad, int cin_pad,
+                               cudaStream_t s) {
+  const long total = static_cast<long>(kh) * kw * (cin_pad >> 4) * npad * 16;
+  pack_weight_kernel<<<grid_for(total, 256), 256, 0, s>>>(w, reinterpret_cast<__nv_bfloat16*>(dst), cout, cin, kh, kw, co_lo, npad,
+                                                          cin_pad);
+  return cudaGetLastError();
+}
+cudaError_t launch_pack_bias(const float* b, float* dst, int cout, int co_lo, int npad, cudaStream_t s) {
+  pack_bias_kernel<<<(npad + 127) / 128, 128, 0, s>>>(b, dst, cout, co_lo, npad);
+  return cudaGetLastError();
+}
+cudaError_t launch_nchw_to_nhwc(const float* src, void* dst, int n, int c, int h, int w, int dst_c, int zero_to, cudaStream_t s) {
+  const long per = static_cast<long>(h) * w, total = per * n;
+  nchw_to_nhwc_kernel<<<grid_for(total, 256), 256, 0, s>>>(src, reinterpret_cast<__nv_bfloat16*>(dst), per, total, c, dst_c, zero_to);
+  return cudaGetLastError();
+}
+cudaError_t launch_pack_aux(const float* elev, const float* mask, void* dst, long total_pix, int dst_c, cudaStream_t s) {
+  pack_aux_kernel<<<grid_for(total_pix, 256), 256, 0, s>>>(elev, mask, reinterpret_cast<__nv_bfloat16*>(dst), total_pix, dst_c);
+  return cudaGetLastError();
+}
+cudaError_t launch_nhwc_to_nchw(const void* src, float* dst, int n, int c, int h, int w, int src_c, int src_coff, cudaStream_t s) {
+  const long per = static_cast<long>(h) * w, total = per * n * c;
+  nhwc_to_nchw_kernel<<<grid_for(total, 256), 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(src), dst, per, total, c, src_c,
+                                                           src_coff);
+  return cudaGetLastError();
+}
+
+}  // namespace csr

@@ -1,0 +1,293 @@
+// Masked validation/test step of the reference as two HBM-bound passes (+ two tiny finalisers).
+//
+// Reference arithmetic (climsr/core/task.py:262-300, 342-380; climsr/metrics/regression_accuracy.py:15-22;
+// climsr/data/normalization.py:63-84,115): denormalise sr per sample, zero-fill sr/hr/denorm_sr/original where
+// mask == 0, then L1/MSE loss and 16 metrics, every mean taken over ALL pixels.  The reference runs ~10 full-tensor
+// passes plus 16 torchmetrics calls; here pass 1 reads sr, hr, original, mask exactly once (16 B / pixel) and
+// produces every sum / count / min / max, pass 2 reads sr, hr, mask once more (12 B / pixel) for the 11x11
+// Gaussian SSIM.  Reductions are deterministic: per-block partials in double, reduced in a fixed order.
+#include "metrics.cuh"
+
+#include <cfloat>
+
+namespace csr {
+
+namespace {
+
+constexpr int kP1Threads = 256;
+constexpr int kSums = 16;     // 8 accuracy counts, |d|, d^2, t, t^2, smape, mape, l1, mse(normalised)
+constexpr int kMinMax = 6;    // min/max of original, masked sr, masked hr
+constexpr int kPart = kSums + kMinMax;
+constexpr float kMapeEps = 1.17e-06f;
+
+struct Acc {
+  float s[kSums];
+  float mn[3], mx[3];
+};
+
+__device__ __forceinline__ void acc_pixel(Acc& a, float sr, float hr, float orig, float mask, float dscale_inv, float dmin, bool zs,
+                                          float zmean, float zstd) {
+  const bool land = mask != 0.f;                        // (~mask.bool()) -> 0.0, task.py:288-291
+  const float den = zs ? sr * zstd + zmean : (sr - dmin) * dscale_inv;   // normalization.py:115 / :80-82
+  const float srn = land ? sr : 0.f;
+  const float hrn = land ? hr : 0.f;
+  const float dsr = land ? den : 0.f;
+  const float org = land ? orig : 0.f;
+  const float d = fabsf(dsr - org);
+  a.s[0] += d <= 0.1f;  a.s[1] += d <= 0.25f; a.s[2] += d <= 0.5f;  a.s[3] += d <= 0.75f;
+  a.s[4] += d <= 1.0f;  a.s[5] += d <= 1.25f; a.s[6] += d <= 1.5f;  a.s[7] += d <= 2.0f;
+  a.s[8] += d;
+  a.s[9] += d * d;
+  a.s[10] += org;
+  a.s[11] += org * org;
+  a.s[12] += 2.f * d / fmaxf(fabsf(org) + fabsf(dsr), kMapeEps);
+  const float dn = fabsf(srn - hrn);
+  a.s[13] += dn / fmaxf(fabsf(hrn), kMapeEps);
+  a.s[14] += dn;
+  a.s[15] += dn * dn;
+  a.mn[0] = fminf(a.mn[0], org); a.mx[0] = fmaxf(a.mx[0], org);
+  a.mn[1] = fminf(a.mn[1], srn); a.mx[1] = fmaxf(a.mx[1], srn);
+  a.mn[2] = fminf(a.mn[2], hrn); a.mx[2] = fmaxf(a.mx[2], hrn);
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_min(float v) {
+  for (int o = 16; o; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+  for (int o = 16; o; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// grid = (blocks_per_image, N).  Each thread walks groups of 4 pixels of one image.
+__global__ void __launch_bounds__(kP1Threads)
+metrics_pass1_kernel(const float* __restrict__ sr, const float* __restrict__ hr, const float* __restrict__ orig,
+                     const float* __restrict__ mask, const float* __restrict__ mn, const float* __restrict__ mx, float zmean, float zstd,
+                     float ra, float rb, long hw, double* __restrict__ partials) {
+  const int n = blockIdx.y;
+  const bool zs = (mn == nullptr);
+  float dmin = 0.f, dscale_inv = 1.f;
+  if (!zs) {
+    // scale = (b-a)/((max-min)+eps); min_ = a - min*scale; out = (arr - min_)/scale   (normalization.py:70-82)
+    const float scale = (rb - ra) / ((mx[n] - mn[n]) + 1e-8f);
+    dmin = ra - mn[n] * scale;
+    dscale_inv = 1.f / scale;
+  }
+  Acc a;
+#pragma unroll
+  for (int i = 0; i < kSums; ++i) a.s[i] = 0.f;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) { a.mn[i] = FLT_MAX; a.mx[i] = -FLT_MAX; }
+  const long base = static_cast<long>(n) * hw;
+  const long groups = (hw + 3) >> 2;
+  const bool vec = (hw & 3) == 0;
+  for (long g = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; g < groups; g += static_cast<long>(gridDim.x) * blockDim.x) {
+    const long p = base + g * 4;
+    if (vec) {
+      const float4 s4 = __ldg(reinterpret_cast<const float4*>(sr + p));
+      const float4 h4 = __ldg(reinterpret_cast<const float4*>(hr + p));
+      const float4 o4 = __ldg(reinterpret_cast<const float4*>(orig + p));
+      const float4 m4 = __ldg(reinterpret_cast<const float4*>(mask + p));
+      acc_pixel(a, s4.x, h4.x, o4.x, m4.x, dscale_inv, dmin, zs, zmean, zstd);
+      acc_pixel(a, s4.y, h4.y, o4.y, m4.y, dscale_inv, dmin, zs, zmean, zstd);
+      acc_pixel(a, s4.z, h4.z, o4.z, m4.z, dscale_inv, dmin, zs, zmean, zstd);
+      acc_pixel(a, s4.w, h4.w, o4.w, m4.w, dscale_inv, dmin, zs, zmean, zstd);
+    } else {
+      for (int k = 0; k < 4 && g * 4 + k < hw; ++k)
+        acc_pixel(a, sr[p + k], hr[p + k], orig[p + k], mask[p + k], dscale_inv, dmin, zs, zmean, zstd);
+    }
+  }
+  __shared__ double sh_s[kP1Threads / 32][kSums];
+  __shared__ float sh_m[kP1Threads / 32][kMinMax];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int i = 0; i < kSums; ++i) {
+    const double v = warp_sum(static_cast<double>(a.s[i]));
+    if (lane == 0) sh_s[warp][i] = v;
+  }
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const float lo = warp_min(a.mn[i]), hi = warp_max(a.mx[i]);
+    if (lane == 0) { sh_m[warp][2 * i] = lo; sh_m[warp][2 * i + 1] = hi; }
+  }
+  __syncthreads();
+  if (threadIdx.x < kPart) {
+    double* out = partials + (static_cast<long>(blockIdx.y) * gridDim.x + blockIdx.x) * kPart;
+    if (threadIdx.x < kSums) {
+      double v = 0;
+      for (int w = 0; w < kP1Threads / 32; ++w) v += sh_s[w][threadIdx.x];
+      out[threadIdx.x] = v;
+    } else {
+      const int i = threadIdx.x - kSums;
+      float v = sh_m[0][i];
+      for (int w = 1; w < kP1Threads / 32; ++w) v = (i & 1) ? fmaxf(v, sh_m[w][i]) : fminf(v, sh_m[w][i]);
+      out[threadIdx.x] = v;
+    }
+  }
+}
+
+// Single block: fixed-order reduction of the pass-1 partials -> totals[kPart] (double) and SSIM constants c1,c2.
+__global__ void metrics_reduce1_kernel(const double* __restrict__ partials, int nblocks, double* __restrict__ totals, float* __restrict__ c12) {
+  __shared__ double sh[kPart];
+  if (threadIdx.x < kPart) {
+    const int i = threadIdx.x;
+    double v = partials[i];
+    for (int b = 1; b < nblocks; ++b) {
+      const double q = partials[static_cast<long>(b) * kPart + i];
+      if (i < kSums) v += q;
+      else v = ((i - kSums) & 1) ? fmax(v, q) : fmin(v, q);
+    }
+    totals[i] = v;
+    sh[i] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    // torchmetrics SSIM: data_range = max(p.max()-p.min(), t.max()-t.min()); c = (k*range)^2
+    const double range = fmax(sh[kSums + 3] - sh[kSums + 2], sh[kSums + 5] - sh[kSums + 4]);
+    c12[0] = static_cast<float>((0.01 * range) * (0.01 * range));
+    c12[1] = static_cast<float>((0.03 * range) * (0.03 * range));
+  }
+}
+
+// ---- SSIM: 11x11 Gaussian (sigma 1.5), valid region only (torchmetrics reflect-pads by 5 and then crops 5, so
+// padding never reaches a retained output).  One block = 32x32 outputs; separable filter through shared memory.
+constexpr int kST = 32;            // output tile edge
+constexpr int kSI = kST + 10;      // input tile edge
+__constant__ float c_gauss[11];
+
+__global__ void __launch_bounds__(256)
+ssim_kernel(const float* __restrict__ sr, const float* __restrict__ hr, const float* __restrict__ mask, int H, int W,
+            const float* __restrict__ c12, double* __restrict__ partials) {
+  __shared__ float s_p[kSI][kSI + 1];
+  __shared__ float s_t[kSI][kSI + 1];
+  __shared__ float s_h[5][kSI][kST + 1];
+  __shared__ double s_red[8];
+  const int n = blockIdx.z;
+  const int oy = 5 + blockIdx.y * kST, ox = 5 + blockIdx.x * kST;   // first output pixel of this tile
+  const float* psr = sr + static_cast<long>(n) * H * W;
+  const float* phr = hr + static_cast<long>(n) * H * W;
+  const float* pm = mask + static_cast<long>(n) * H * W;
+  for (int i = threadIdx.x; i < kSI * kSI; i += blockDim.x) {
+    const int r = i / kSI, c = i - r * kSI;
+    const int y = min(oy - 5 + r, H - 1), x = min(ox - 5 + c, W - 1);
+    const long q = static_cast<long>(y) * W + x;
+    const bool land = pm[q] != 0.f;
+    s_p[r][c] = land ? psr[q] : 0.f;
+    s_t[r][c] = land ? phr[q] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < kSI * kST; i += blockDim.x) {
+    const int r = i / kST, c = i - r * kST;
+    float a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0;
+#pragma unroll
+    for (int k = 0; k < 11; ++k) {
+      const float g = c_gauss[k], p = s_p[r][c + k], t = s_t[r][c + k];
+      a0 += g * p; a1 += g * t; a2 += g * p * p; a3 += g * t * t; a4 += g * p * t;
+    }
+    s_h[0][r][c] = a0; s_h[1][r][c] = a1; s_h[2][r][c] = a2; s_h[3][r][c] = a3; s_h[4][r][c] = a4;
+  }
+  __syncthreads();
+  const float c1 = c12[0], c2 = c12[1];
+  double local = 0;
+  for (int i = threadIdx.x; i < kST * kST; i += blockDim.x) {
+    const int r = i / kST, c = i - r * kST;
+    const int y = oy + r, x = ox + c;
+    if (y >= H - 5 || x >= W - 5) continue;
+    float m[5] = {0, 0, 0, 0, 0};
+#pragma unroll
+    for (int k = 0; k < 11; ++k) {
+      const float g = c_gauss[k];
+#pragma unroll
+      for (int q = 0; q < 5; ++q) m[q] += g * s_h[q][r + k][c];
+    }
+    const float mu_p2 = m[0] * m[0], mu_t2 = m[1] * m[1], mu_pt = m[0] * m[1];
+    const float sp = m[2] - mu_p2, st = m[3] - mu_t2, spt = m[4] - mu_pt;
+    local += static_cast<double>(((2.f * mu_pt + c1) * (2.f * spt + c2)) / ((mu_p2 + mu_t2 + c1) * (sp + st + c2)));
+  }
+  local = warp_sum(local);
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = local;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double v = 0;
+    for (int w = 0; w < 8; ++w) v += s_red[w];
+    partials[(static_cast<long>(blockIdx.z) * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = v;
+  }
+}
+
+// Single block: SSIM partial sum + closed forms of the 16 metrics and the two losses.
+__global__ void metrics_final_kernel(const double* __restrict__ totals, const double* __restrict__ ssim_partials, int n_ssim, double n_pix,
+                                     double n_ssim_pix, float* __restrict__ out) {
+  if (threadIdx.x != 0) return;
+  double ssim = 0;
+  for (int i = 0; i < n_ssim; ++i) ssim += ssim_partials[i];
+  const double* t = totals;
+  for (int k = 0; k < 8; ++k) out[k] = static_cast<float>(t[k] / n_pix);             // RegressionAccuracy.compute
+  const double mse = t[9] / n_pix;
+  const double tmin = fmin(t[kSums + 0], 0.0), tmax = fmax(t[kSums + 1], 0.0);       // PSNR states start at 0.0
+  const double range = tmax - tmin;
+  out[8] = static_cast<float>(10.0 * log10(range * range / mse));
+  out[9] = static_cast<float>(ssim / n_ssim_pix);
+  out[10] = static_cast<float>(t[8] / n_pix);
+  out[11] = static_cast<float>(mse);
+  out[12] = static_cast<float>(sqrt(mse));
+  out[13] = static_cast<float>(t[13] / n_pix);
+  out[14] = static_cast<float>(t[12] / n_pix);
+  out[15] = static_cast<float>(1.0 - t[9] / (t[11] - t[10] * t[10] / n_pix));         // R2Score, flattened
+  out[16] = static_cast<float>(t[14] / n_pix);                                        // nn.L1Loss (task.py:141)
+  out[17] = static_cast<float>(t[15] / n_pix);                                        // nn.MSELoss
+}
+
+int p1_blocks_per_image(int n, long hw) {
+  long want = (hw / 4 + kP1Threads * 4 - 1) / (kP1Threads * 4);   // >= 4 groups per thread
+  long cap = (148L * 8 + n - 1) / n;
+  if (want > cap) want = cap;
+  if (want < 1) want = 1;
+  return static_cast<int>(want);
+}
+
+}  // namespace
+
+size_t metrics_scratch_bytes(int n, int h, int w) {
+  const long hw = static_cast<long>(h) * w;
+  const int bpi = p1_blocks_per_image(n, hw);
+  const long ssim_blocks = static_cast<long>(n) * ((h - 10 + kST - 1) / kST) * ((w - 10 + kST - 1) / kST);
+  return static_cast<size_t>(bpi) * n * kPart * 8 + kPart * 8 + 64 + (ssim_blocks > 0 ? ssim_blocks : 1) * 8 + 256;
+}
+
+cudaError_t launch_masked_metrics(const float* sr, const float* hr, const float* orig, const float* mask, const float* mn, const float* mx,
+                                  float zmean, float zstd, float ra, float rb, int n, int h, int w, float* out, void* scratch,
+                                  cudaStream_t s, int* launches) {
+  static bool gauss_ready = false;
+  if (!gauss_ready) {
+    // torchmetrics _gaussian: exp(-(d/sigma)^2/2) normalised, d = -5..5, sigma = 1.5
+    float g[11];
+    double sum = 0;
+    for (int i = 0; i < 11; ++i) { g[i] = static_cast<float>(exp(-((i - 5) / 1.5) * ((i - 5) / 1.5) / 2.0)); sum += g[i]; }
+    for (int i = 0; i < 11; ++i) g[i] = static_cast<float>(g[i] / sum);
+    cudaError_t e = cudaMemcpyToSymbol(c_gauss, g, sizeof(g));
+    if (e != cudaSuccess) return e;
+    gauss_ready = true;
+  }
+  const long hw = static_cast<long>(h) * w;
+  const int bpi = p1_blocks_per_image(n, hw);
+  const int gy = (h - 10 + kST - 1) / kST, gx = (w - 10 + kST - 1) / kST;
+  const int ssim_blocks = n * gy * gx;
+  uint8_t* base = reinterpret_cast<uint8_t*>(scratch);
+  double* partials = reinterpret_cast<double*>(base);
+  double* totals = partials + static_cast<long>(bpi) * n * kPart;
+  float* c12 = reinterpret_cast<float*>(totals + kPart);
+  double* ssim_part = reinterpret_cast<double*>(reinterpret_cast<uint8_t*>(c12) + 64);
+  metrics_pass1_kernel<<<dim3(bpi, n), kP1Threads, 0, s>>>(sr, hr, orig, mask, mn, mx, zmean, zstd, ra, rb, hw, partials);
+  metrics_reduce1_kernel<<<1, 32, 0, s>>>(partials, bpi * n, totals, c12);
+  ssim_kernel<<<dim3(gx, gy, n), 256, 0, s>>>(sr, hr, mask, h, w, c12, ssim_part);
+  metrics_final_kernel<<<1, 32, 0, s>>>(totals, ssim_part, ssim_blocks, static_cast<double>(hw) * n,
+                                        static_cast<double>(n) * (h - 10) * (w - 10), out);
+  *launches = 4;
+  return cudaGetLastError();
+}
+
+}  // namespace csr

@@ -1,0 +1,152 @@
+/*
+ * climsr_b200.h - C-ABI of the B200-native (sm_100a) generator hot path of
+ * xultaeculcis/climate-super-resolution.
+ *
+ * Plain C: pointers, sizes and ints only.  All data pointers are DEVICE pointers
+ * unless a parameter says "host".  `stream` is a cudaStream_t passed as void*.
+ * Every function returns CSR_OK (0) or a negative CsrStatus and never throws or
+ * synchronises the device (work is enqueued on `stream`); csr_last_error() gives
+ * the message of the last failure on the calling thread.  There is NO CPU
+ * fallback: on a machine without an sm_100 device every compute entry point
+ * returns CSR_ERR_CUDA / CSR_ERR_UNSUPPORTED.
+ *
+ * Reference interfaces replaced (paths relative to the reference repo):
+ *   csr_plan_forward / csr_generator_forward
+ *        <- ESRGANGenerator.forward(x, elev, mask)           climsr/models/esrgan.py:89-102
+ *           (+ RDB / RRDB / SRCNN forwards                    esrgan.py:32-38,50-54; srcnn.py:13-18)
+ *           called from TaskSuperResolutionModule.forward     climsr/core/task.py:235-239
+ *           and inference_on_full_images                      climsr/inference/inference.py:70
+ *   csr_pack_weights
+ *        <- the generator state_dict (names/shapes/order)     esrgan.py:72-87, srcnn.py:9-11
+ *   csr_conv2d_nhwc
+ *        <- one nn.Conv2d + LeakyReLU/ReLU/residual call site esrgan.py:33-38,90-100
+ *   csr_masked_metrics / csr_ssim
+ *        <- common_val_test_step + compute_metrics            climsr/core/task.py:262-300,342-380
+ *           RegressionAccuracy.update/compute                 climsr/metrics/regression_accuracy.py:15-22
+ *           MinMaxScaler._denormalize / StandardScaler        climsr/data/normalization.py:63-84,115
+ *   csr_l1_loss / csr_mse_loss (+ _backward)
+ *        <- self.loss(sr, hr)                                 climsr/core/task.py:141;
+ *                                                             climsr/task/pl_generator_pre_training.py:29-30
+ */
+#ifndef CLIMSR_B200_H
+#define CLIMSR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CSR_ABI_VERSION 1
+
+typedef enum CsrStatus {
+  CSR_OK = 0,
+  CSR_ERR_BAD_ARG = -1,      /* null pointer, non-positive size, misaligned pointer            */
+  CSR_ERR_UNSUPPORTED = -2,  /* shape/config outside what the kernels implement                 */
+  CSR_ERR_CUDA = -3,         /* CUDA runtime/driver error (launch failure, no sm_100 device...) */
+  CSR_ERR_WORKSPACE = -4     /* workspace / packed buffer too small                             */
+} CsrStatus;
+
+/* ESRGANGenerator.__init__ arguments (esrgan.py:58-67).  out_channels must be 1 (the SRCNN tail
+ * hard-wires 1+1+1 input channels, esrgan.py:87,100); scale must be 4 (conf/generator/esrgan.yaml). */
+typedef struct CsrNetDesc {
+  int32_t in_channels;
+  int32_t out_channels;
+  int32_t nf;
+  int32_t nb;
+  int32_t gc;
+  int32_t scale;
+} CsrNetDesc;
+
+/* Epilogue of a single convolution (csr_conv2d_nhwc). */
+typedef enum CsrAct { CSR_ACT_NONE = 0, CSR_ACT_LRELU02 = 1, CSR_ACT_RELU = 2 } CsrAct;
+typedef enum CsrOutMode {
+  CSR_OUT_BF16_NHWC = 0,     /* bf16, channel slice [out_coff, out_coff+cout) of an NHWC buffer          */
+  CSR_OUT_BF16_NHWC_UP2 = 1, /* same, each pixel replicated 2x2 into a (2H,2W) buffer (nearest x2)        */
+  CSR_OUT_F32_PLANAR = 2     /* fp32 (N,1,H,W); cout must be 1                                            */
+} CsrOutMode;
+
+typedef struct CsrConvDesc {
+  int32_t n, h, w;            /* input (== conv output) batch / height / width                            */
+  int32_t cin, cout;          /* real channel counts                                                       */
+  int32_t kh, kw;             /* odd kernel size; stride 1, padding (k-1)/2 ("same")                       */
+  int32_t in_c;               /* channels per pixel of the input buffer (multiple of 64)                   */
+  int32_t out_c, out_coff;    /* channels per pixel of the output buffer, first output channel             */
+  int32_t act;                /* CsrAct                                                                    */
+  int32_t out_mode;           /* CsrOutMode                                                                */
+  float   scale1;             /* v = act(conv+bias); if res1: v = v*scale1 + res1; if res2: v = v*scale2+res2 */
+  float   scale2;
+  int32_t res1_c, res1_coff;  /* residual buffers: bf16 NHWC with res*_c channels per pixel                */
+  int32_t res2_c, res2_coff;
+} CsrConvDesc;
+
+/* ---- library ------------------------------------------------------------------------------- */
+int         csr_abi_version(void);
+const char* csr_last_error(void);
+/* 0 when an sm_100 device is current and usable, CSR_ERR_CUDA / CSR_ERR_UNSUPPORTED otherwise. */
+int         csr_device_check(void);
+/* debug / tuning knobs (key, value); unknown keys return CSR_ERR_BAD_ARG. */
+int         csr_set_option(int32_t key, int32_t value);
+int64_t     csr_kernel_launch_count(void);           /* kernels launched by this library so far   */
+
+/* ---- weights --------------------------------------------------------------------------------
+ * Number of conv layers (== number of weight tensors) of the generator, in state_dict order.    */
+int     csr_num_layers(const CsrNetDesc* net);
+/* Shape of layer i as (cout, cin, kh, kw); name is written into name[name_cap] (state_dict prefix). */
+int     csr_layer_shape(const CsrNetDesc* net, int32_t i, int32_t shape4[4], char* name, size_t name_cap);
+size_t  csr_packed_weight_bytes(const CsrNetDesc* net);
+/* w/b: HOST arrays of csr_num_layers() DEVICE pointers to fp32 OIHW weights / biases.           */
+int     csr_pack_weights(const CsrNetDesc* net, const float* const* w, const float* const* b,
+                         void* packed, size_t packed_bytes, void* stream);
+
+/* ---- generator forward ----------------------------------------------------------------------
+ * x (N,Cin,h,w) fp32 NCHW; elev, mask (N,1,4h,4w) fp32; out (N,1,4h,4w) fp32.                    */
+size_t  csr_workspace_bytes(const CsrNetDesc* net, int32_t n, int32_t h, int32_t w);
+typedef struct CsrPlan CsrPlan;
+int     csr_plan_create(const CsrNetDesc* net, int32_t n, int32_t h, int32_t w,
+                        void* workspace, size_t workspace_bytes, CsrPlan** plan);
+int     csr_plan_forward(CsrPlan* plan, const void* packed, const float* x, const float* elev,
+                         const float* mask, float* out, void* stream);
+int     csr_plan_num_launches(const CsrPlan* plan);
+void    csr_plan_destroy(CsrPlan* plan);
+/* one-shot convenience: plan_create + plan_forward + plan_destroy                               */
+int     csr_generator_forward(const CsrNetDesc* net, const void* packed, const float* x,
+                              const float* elev, const float* mask, float* out,
+                              void* workspace, size_t workspace_bytes,
+                              int32_t n, int32_t h, int32_t w, void* stream);
+
+/* ---- single convolution (building block; used by the parity tests) --------------------------
+ * in: bf16 NHWC (n,h,w,in_c); weight fp32 OIHW (cout,cin,kh,kw); bias fp32 (cout).
+ * scratch: >= csr_conv2d_scratch_bytes() device bytes for the packed weights.                   */
+size_t  csr_conv2d_scratch_bytes(const CsrConvDesc* d);
+int     csr_conv2d_nhwc(const CsrConvDesc* d, const void* in, const float* weight, const float* bias,
+                        void* out, const void* res1, const void* res2,
+                        void* scratch, size_t scratch_bytes, void* stream);
+
+/* ---- layout helpers -------------------------------------------------------------------------- */
+/* fp32 NCHW (n,c,h,w) -> bf16 NHWC (n,h,w,dst_c) channels [0,c), channels [c, zero_to) zeroed.  */
+int     csr_nchw_f32_to_nhwc_bf16(const float* src, void* dst, int32_t n, int32_t c, int32_t h, int32_t w,
+                                  int32_t dst_c, int32_t zero_to, void* stream);
+/* bf16 NHWC channel slice -> fp32 NCHW (n,c,h,w)                                                 */
+int     csr_nhwc_bf16_to_nchw_f32(const void* src, float* dst, int32_t n, int32_t c, int32_t h, int32_t w,
+                                  int32_t src_c, int32_t src_coff, void* stream);
+
+/* ---- masked loss + metrics (one fused HBM pass + SSIM pass) ----------------------------------
+ * sr, hr, original, mask: fp32 (N,1,H,W).  mn/mx: fp32 (N) per-sample min/max (min-max scaler) or
+ * NULL with zmean/zstd used instead (z-score).  out: CSR_NUM_METRICS floats (device), see enum.   */
+enum {
+  CSR_M_ACC_0_1 = 0, CSR_M_ACC_0_25, CSR_M_ACC_0_5, CSR_M_ACC_0_75, CSR_M_ACC_1, CSR_M_ACC_1_25,
+  CSR_M_ACC_1_5, CSR_M_ACC_2, CSR_M_PSNR, CSR_M_SSIM, CSR_M_MAE, CSR_M_MSE, CSR_M_RMSE, CSR_M_MAPE,
+  CSR_M_SMAPE, CSR_M_R2, CSR_M_L1_LOSS, CSR_M_MSE_LOSS, CSR_NUM_METRICS
+};
+size_t  csr_metrics_scratch_bytes(int32_t n, int32_t h, int32_t w);
+int     csr_masked_metrics(const float* sr, const float* hr, const float* original, const float* mask,
+                           const float* mn, const float* mx, float zmean, float zstd,
+                           float range_a, float range_b, int32_t n, int32_t h, int32_t w,
+                           float* out, void* scratch, size_t scratch_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CLIMSR_B200_H */
