@@ -1,0 +1,277 @@
+#!/usr/bin/env python
+"""Headline benchmark: ESRGAN/RRDBNet generator inference throughput (HR-output Mpixel/s) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg2_default|cfg1]
+
+Workload (BASELINE.json configs[1]): Hydra generator (nf=64, nb=11, gc=16, in_channels=4), batch 64 of 256x256 HR tiles
+(LR 64x64) per GPU, synthetic inputs, random-init weights.  One "step" = one generator forward over the batch.
+  value  : whole-job HR Mpixel/s with inputs resident in HBM (CUDA events, max over ranks)
+  e2e    : same metric through the public API (climsr_b200.models.ESRGANGenerator) from pinned HOST buffers,
+           H2D of x/elev/mask and D2H of the result inside the timed region
+  roofline: tensor bound - algorithmic FLOPs (SURVEY.md section 8a model, no credit for padding / halo recompute)
+           / measured step time vs MEASURED_PEAKS.json bf16 peak
+  cpu_baseline: the oracle port of the reference generator (oracle/generator.py, torch CPU fp32 == the reference's own
+           ATen/oneDNN arithmetic) timed on this box's host cores on a bounded sample of the same workload
+N > 1 (torchrun): independent tile batches per rank, no data-path collective -> "weak" scaling.
+--impl reference: times the reference's CPU implementation (oracle port; /root/reference does not exist on the GPU box).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "climate-super-resolution_b200"))
+
+WORKLOADS = {
+    # name: (in_ch, nb, gc, tiles per GPU, LR h, LR w)
+    "cfg2": (4, 11, 16, 64, 64, 64),            # BASELINE configs[1], Hydra cfg, HR-tile reading
+    "cfg2_default": (4, 23, 32, 64, 64, 64),    # class-default RRDBNet
+    "cfg2_lr256": (4, 11, 16, 4, 256, 256),     # LR-tile reading (LR 256^2 -> HR 1024^2), reduced batch
+    "cfg1": (4, 11, 16, 16, 32, 32),            # BASELINE configs[0] shape
+}
+
+
+def flops_per_hr_pixel(in_ch, nf, nb, gc):
+    rdb = gc * (4 * nf + 6 * gc) + (nf + 4 * gc) * nf
+    macs_lr = 9 * (in_ch * nf + nb * 3 * rdb + nf * nf) + 4 * 9 * nf * nf + 2 * 16 * 9 * nf * nf + 16 * 9 * nf
+    macs_lr += 16 * (81 * 3 * 64 + 64 * 32 + 25 * 32)
+    return 2.0 * macs_lr / 16.0
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return {"bf16_burst": d.get("bf16_tflops"), "bf16_sustained": d.get("bf16_tflops_sustained"), "hbm": d.get("hbm_gbs"),
+                "source": "measured"}
+    return {"bf16_burst": 1590.0, "bf16_sustained": 1400.0, "hbm": 6650.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """Samples SM clock and throttle reasons of one GPU while the timed region runs (pynvml, 100 ms period)."""
+
+    def __init__(self, index: int):
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake_slowdown",
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                get = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+                r = get(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._thread:
+            self._thread.join(timeout=2)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def cpu_reference_rate(in_ch, nb, gc, h, w, sample_tiles, iters, threads=None):
+    """Oracle port of the reference generator on host cores: HR Mpixel/s on `sample_tiles` tiles of the workload."""
+    import torch
+    from oracle import generator as og
+    from oracle import synth
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    sd = synth.make_state_dict(in_ch, 1, 64, nb, gc, seed=0)
+    x, elev, mask = synth.make_inputs(sample_tiles, in_ch, h, w, seed=1)
+    with torch.no_grad():
+        og.generator_forward(sd, x, elev, mask)          # warm-up
+        times = []
+        for _ in range(iters):
+            t0 = time.perf_counter()
+            og.generator_forward(sd, x, elev, mask)
+            times.append(time.perf_counter() - t0)
+    px = sample_tiles * 16 * h * w
+    return px / statistics.median(times) / 1e6, threads, times
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    in_ch, nb, gc, tiles, h, w = WORKLOADS[args.workload]
+    sample = 8 if h * w <= 64 * 64 else 1
+    t0 = time.perf_counter()
+    rate, threads, times = cpu_reference_rate(in_ch, nb, gc, h, w, sample, max(args.steps, 1))
+    ms = statistics.median(times) * 1e3
+    line = {
+        "impl": "reference", "metric": "generator_inference_hr_mpixel_per_s", "value": rate, "unit": "Mpixel/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": 1, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: RRDBNet nb={nb} gc={gc} in={in_ch}, {sample} of {tiles} tiles LR {h}x{w} -> HR {4*h}x{4*w} per step (bounded CPU sample)"},
+        "cpu_baseline": {"value": rate, "unit": "Mpixel/s", "cores": threads, "kind": "port",
+                         "sample": f"{sample} tiles x {max(args.steps, 1)} iterations, torch CPU fp32 (oneDNN), oracle/generator.py"},
+        "e2e": {"value": rate, "unit": "Mpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "wall_s": time.perf_counter() - t0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from climsr_b200 import device_check, kernel_launch_count
+    from climsr_b200.models import ESRGANGenerator
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    device_check()
+    dev = torch.device("cuda", local)
+    in_ch, nb, gc, tiles, h, w = WORKLOADS[args.workload]
+    H, W = 4 * h, 4 * w
+
+    torch.manual_seed(0)
+    net = ESRGANGenerator(in_ch, 1, 64, nb, gc).to(dev).eval()      # reference default init (random weights)
+    g = torch.Generator().manual_seed(1 + rank)
+    x = torch.rand((tiles, in_ch, h, w), generator=g) * 2 - 1        # synthetic tiles (SURVEY.md section 8d recipe)
+    mask = (torch.rand((tiles, 1, H, W), generator=g) > 0.3).float()
+    elev = (torch.rand((tiles, 1, H, W), generator=g) * 2 - 1) * mask
+    xp, ep, mp = x.pin_memory(), elev.pin_memory(), mask.pin_memory()
+    xd, ed, md = x.to(dev), elev.to(dev), mask.to(dev)
+    out_host = torch.empty((tiles, 1, H, W), dtype=torch.float32).pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    with torch.no_grad():
+        for _ in range(max(args.warmup, 3)):
+            out = net(xd, ed, md)
+        barrier()
+        # ---------------- device-resident timing
+        l0 = kernel_launch_count()
+        with ClockSampler(local) as clk:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            e0.record()
+            for _ in range(args.steps):
+                out = net(xd, ed, md)
+            e1.record()
+            barrier()
+            ms_total = e0.elapsed_time(e1)
+        launches = kernel_launch_count() - l0
+        ms_step = max_over_ranks(ms_total / args.steps)
+        # ---------------- end-to-end timing (host pinned -> device -> host)
+        for _ in range(2):
+            xd.copy_(xp, non_blocking=True); ed.copy_(ep, non_blocking=True); md.copy_(mp, non_blocking=True)
+            out_host.copy_(net(xd, ed, md), non_blocking=True)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            xd.copy_(xp, non_blocking=True); ed.copy_(ep, non_blocking=True); md.copy_(mp, non_blocking=True)
+            out_host.copy_(net(xd, ed, md), non_blocking=True)
+        e1.record()
+        barrier()
+        ms_e2e = max_over_ranks(e0.elapsed_time(e1) / args.steps)
+
+    px_step = tiles * H * W
+    value = world * px_step / (ms_step * 1e-3) / 1e6
+    e2e_value = world * px_step / (ms_e2e * 1e-3) / 1e6
+    fl = flops_per_hr_pixel(in_ch, 64, nb, gc)
+    peaks = load_peaks()
+    achieved = px_step * fl / (ms_step * 1e-3) / 1e12          # per GPU, TFLOP/s (algorithmic)
+    peak = peaks["bf16_sustained"]
+    line = {
+        "metric": "generator_inference_hr_mpixel_per_s", "value": value, "unit": "Mpixel/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: RRDBNet generator nf=64 nb={nb} gc={gc} in={in_ch}, {tiles} tiles/GPU LR {h}x{w} -> HR {H}x{W}, "
+                               "random-init weights (seeded), bf16 activations/weights, fp32 accumulate",
+                   "l2_policy": "per-step activation working set (about 2 GB of NHWC buffers) exceeds the 126 MB L2; no flush needed",
+                   "parallelism": f"independent tile batches per rank x{world}, no collective"},
+        "e2e": {"value": e2e_value, "unit": "Mpixel/s", "h2d_bytes_per_step": int(x.numel() + elev.numel() + mask.numel()) * 4,
+                "d2h_bytes_per_step": int(out_host.numel()) * 4, "ms_per_step": ms_e2e},
+        "gpu_launches": int(launches),
+        "clocks": clk.summary(),
+        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                     "traffic": None, "peak_source": f"{peaks['source']} bf16_tflops_sustained (burst {peaks['bf16_burst']})",
+                     "flop_per_hr_pixel": fl,
+                     "note": "dominant kernel conv_tc_kernel (all conv launches of a step); algorithmic FLOPs of the whole forward / step time"},
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sample = 8 if h * w <= 64 * 64 else 1
+        rate, threads, _ = cpu_reference_rate(in_ch, nb, gc, h, w, sample, 3)
+        line["cpu_baseline"] = {"value": rate, "unit": "Mpixel/s", "cores": threads, "kind": "port",
+                                "sample": f"{sample} of {tiles} tiles, 1 warm-up + 3 timed forwards, torch CPU fp32, oracle/generator.py"}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

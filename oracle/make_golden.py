@@ -57,25 +57,26 @@ def tiny_refinit():
 
 
 def seeded(name, in_ch, nb, gc, n, h, w):
+    """Three weight scalings: default init (gain 1), "trained-like" O(0.1-0.5) outputs where the 1e-2 absolute budget of
+    BASELINE.json is a tight test, and a chaotic "stress" gain where any bf16-I/O implementation (the reference under
+    bf16 included) is only accurate to ~2 % of the output range."""
     blob = {}
-    for gain in (1.0, 4.0):
-        sd = synth.make_state_dict(in_ch, 1, 64, nb, gc, seed=0, gain=gain if gain == 1.0 else _trained_gain(nb, gc))
+    gains = GAINS[gc]
+    for tag, gain in zip(("sr", "sr_trained", "sr_stress"), gains):
+        sd = synth.make_state_dict(in_ch, 1, 64, nb, gc, seed=0, gain=gain)
         net = ESRGANGenerator(in_channels=in_ch, out_channels=1, nf=64, nb=nb, gc=gc, scale_factor=4).eval()
         net.load_state_dict(sd, strict=True)
         x, elev, mask = synth.make_inputs(n, in_ch, h, w, seed=1)
         with torch.no_grad():
             sr = net(x, elev, mask)
-        tag = "sr" if gain == 1.0 else "sr_trained"
         blob[tag] = sr.numpy()
-        print(name, tag, sr.shape, "std", float(sr.std()), "absmax", float(sr.abs().max()))
+        print(name, tag, gain, sr.shape, "std", float(sr.std()), "absmax", float(sr.abs().max()))
     blob["meta"] = np.array([in_ch, nb, gc, n, h, w], dtype=np.int64)
-    blob["trained_gain"] = np.array(_trained_gain(nb, gc))
+    blob["gains"] = np.array(gains)
     np.savez_compressed(os.path.join(OUT, name + ".npz"), **blob)
 
 
-def _trained_gain(nb, gc):
-    # chosen so the output std is O(0.3-1): the 1e-2 abs budget is then a tight test
-    return 1.8 if gc == 16 else 1.4
+GAINS = {16: (1.0, 1.5, 1.8), 32: (1.0, 1.25, 1.4)}
 
 
 if __name__ == "__main__":

@@ -42,7 +42,7 @@ def test_seeded_configs_match_reference(golden_dir, name):
     z = _load(golden_dir, name)
     in_ch, nb, gc, n, h, w = (int(v) for v in z["meta"])
     x, elev, mask = synth.make_inputs(n, in_ch, h, w, seed=1)
-    for tag, gain in (("sr", 1.0), ("sr_trained", float(z["trained_gain"]))):
+    for tag, gain in zip(("sr", "sr_trained", "sr_stress"), (float(g) for g in z["gains"])):
         sd = synth.make_state_dict(in_ch, 1, 64, nb, gc, seed=0, gain=gain)
         with torch.no_grad():
             sr = og.generator_forward(sd, x, elev, mask)
