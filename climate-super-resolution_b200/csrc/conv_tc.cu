@@ -125,12 +125,11 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int taps = p.KH * p.KW;
   const int ksteps_total = p.cin >> 4;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
+    // ===================== TMA producer (whole warp walks the loop, one elected lane issues) =====================
+    if (elect_one()) {
       // layer weights: resident for the whole CTA
       mbar_arrive_expect_tx(bar_w, p.w_bytes);
       const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.wpk);
@@ -138,56 +137,67 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
         const int nbytes = min(32768, p.w_bytes - off);
         bulk_load(w_addr + off, wsrc + off, nbytes, bar_w);
       }
-      int j = 0;
-      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
-        const Tile tl = decode_tile(p, t);
-        for (int kb = 0; kb < p.n_kblocks; ++kb, ++j) {
-          const int slot = j % S;
-          const int use = j / S;
-          mbar_wait(bar_a_empty(slot), (use & 1) ^ 1);
+    }
+    __syncwarp();
+    int slot = 0;
+    uint32_t phase = 0;
+    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+      const Tile tl = decode_tile(p, t);
+      for (int kb = 0; kb < p.n_kblocks; ++kb) {
+        mbar_wait(bar_a_empty(slot), phase ^ 1);
+        if (elect_one()) {
           mbar_arrive_expect_tx(bar_a_full(slot), p.win_bytes);
-          tma_load_4d(slots_addr + slot * p.slot_bytes, &tmap, bar_a_full(slot), p.cin_off + kb * 64, tl.x0 - p.PW,
-                      tl.y0 - p.PH, tl.n);
+          tma_load_4d(slots_addr + slot * p.slot_bytes, &tmap, bar_a_full(slot), p.cin_off + kb * 64, tl.x0 - p.PW, tl.y0 - p.PH,
+                      tl.n);
         }
+        __syncwarp();
+        if (++slot == S) { slot = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(kTileM, p.npad);
-      const uint32_t b_step = p.npad * 32;  // bytes of one (tap,kstep) weight block
-      mbar_wait(bar_w, 0);
+    // All 32 lanes run the (warp-uniform) control flow so addresses live in uniform registers; one elected lane
+    // issues.  Per MMA only the descriptor start-address fields change: two 32-bit adds.
+    const uint32_t idesc = make_idesc_bf16(kTileM, p.npad);
+    const uint32_t b_step16 = static_cast<uint32_t>(p.npad * 32) >> 4;         // one (tap,kstep) weight block, in 16-byte units
+    const uint32_t b_tap16 = static_cast<uint32_t>(ksteps_total) * b_step16;  // one tap
+    const uint32_t a_hi = (1024u >> 4) | (1u << 14) | (2u << 29);             // SBO 1024 B, version 1, 128B swizzle
+    const uint32_t b_hi = (256u >> 4) | (1u << 14);                           // SBO 256 B, version 1, no swizzle
+    const uint32_t a_lbo = (16u >> 4) << 16, b_lbo = (128u >> 4) << 16;
+    const uint32_t row16 = static_cast<uint32_t>(p.SW) * 8u;                  // one window row (SW pixels x 128 B) in 16-byte units
+    mbar_wait(bar_w, 0);
+    tc_fence_after();
+    int slot = 0, it = 0;
+    uint32_t phase = 0;
+    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
+      const int buf = it & 1;
+      mbar_wait(bar_acc_empty(buf), ((it >> 1) & 1) ^ 1);
       tc_fence_after();
-      int j = 0, it = 0;
-      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
-        const int buf = it & 1;
-        mbar_wait(bar_acc_empty(buf), ((it >> 1) & 1) ^ 1);
+      const uint32_t d_tmem = tmem_base + buf * p.npad;
+      uint32_t accumulate = 0;
+      for (int kb = 0; kb < p.n_kblocks; ++kb) {
+        mbar_wait(bar_a_full(slot), phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + buf * p.npad;
-        uint32_t accumulate = 0;
-        for (int kb = 0; kb < p.n_kblocks; ++kb, ++j) {
-          const int slot = j % S;
-          mbar_wait(bar_a_full(slot), (j / S) & 1);
-          tc_fence_after();
-          const uint32_t a_base = slots_addr + slot * p.slot_bytes;
-          const int ks_here = min(4, ksteps_total - kb * 4);
-          for (int tap = 0; tap < taps; ++tap) {
-            const int dy = tap / p.KW;
-            const int dx = tap - dy * p.KW;
-            const uint32_t a_tap = a_base + static_cast<uint32_t>(dy * p.SW + dx) * 128u;
-            const uint32_t b_tap = w_addr + static_cast<uint32_t>(tap * ksteps_total + kb * 4) * b_step;
-            for (int ks = 0; ks < ks_here; ++ks) {
-              const uint32_t a_addr = a_tap + ks * 32;
-              const uint32_t boff = p.a_base_off_mode ? ((a_addr >> 7) & 7u) : 0u;
-              const uint64_t adesc = make_sdesc(a_addr, 16, 1024, 2, boff);
-              const uint64_t bdesc = make_sdesc(b_tap + ks * b_step, 128, 256, 0, 0);
-              umma_bf16(d_tmem, adesc, bdesc, idesc, accumulate);
+        const int ks_here = min(4, ksteps_total - kb * 4);
+        uint32_t a_row = ((slots_addr + slot * p.slot_bytes) >> 4) | a_lbo;
+        uint32_t b_lo = ((w_addr >> 4) + static_cast<uint32_t>(kb * 4) * b_step16) | b_lbo;
+        if (elect_one()) {
+          for (int dy = 0; dy < p.KH; ++dy, a_row += row16) {
+            uint32_t a_lo = a_row;
+            for (int dx = 0; dx < p.KW; ++dx, a_lo += 8, b_lo += b_tap16) {
+              umma_bf16_split(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, accumulate);
               accumulate = 1;
+              if (ks_here > 1) umma_bf16_split(d_tmem, a_lo + 2, a_hi, b_lo + b_step16, b_hi, idesc, 1);
+              if (ks_here > 2) umma_bf16_split(d_tmem, a_lo + 4, a_hi, b_lo + 2 * b_step16, b_hi, idesc, 1);
+              if (ks_here > 3) umma_bf16_split(d_tmem, a_lo + 6, a_hi, b_lo + 3 * b_step16, b_hi, idesc, 1);
             }
           }
-          umma_commit(bar_a_empty(slot));  // window slot reusable once these MMAs have read it
+          umma_commit(bar_a_empty(slot));                                  // window slot reusable once these MMAs have read it
+          if (kb == p.n_kblocks - 1) umma_commit(bar_acc_full(buf));       // accumulator complete -> epilogue
         }
-        umma_commit(bar_acc_full(buf));    // accumulator complete -> epilogue
+        __syncwarp();
+        accumulate = 1;
+        if (++slot == S) { slot = 0; phase ^= 1; }
       }
     }
   } else {
@@ -260,6 +270,7 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
+    __syncwarp();
     tc_fence_after();
     tmem_dealloc(tmem_base, p.tmem_cols);
   }
