@@ -18,7 +18,7 @@ namespace csr {
 // ------------------------------------------------------------------------------------------- errors
 static thread_local char g_err[512] = "";
 static std::atomic<long long> g_launches{0};
-static int g_opt_base_off_mode = 0;
+static int g_opt_generic_issue = 0;
 static int g_opt_force_sw = 0;
 static int g_opt_max_slots = 8;
 
@@ -173,7 +173,7 @@ static int choose_tiling(int H, int W, int KH, int KW, int w_bytes, int n_kblock
   const int fixed = 1024 + (int)align_up(w_bytes, 128) + 1024 + 512;
   double best = -1;
   for (int SW = 16; SW <= 128; SW *= 2) {
-    if (g_opt_force_sw && SW != g_opt_force_sw) continue;
+    if (g_opt_force_sw ? SW != g_opt_force_sw : SW > 32) continue;   // 16/32 have unrolled MMA-issue instantiations
     const int TW = SW - (KW - 1);
     if (TW < 1) continue;
     const int TH = kTileM / SW;
@@ -240,7 +240,14 @@ static int build_conv(const LayerSpec& L, const PackLayer& pl, const PackPart& p
   while (cols < 2 * p.npad) cols *= 2;
   if (cols > 512) return fail(CSR_ERR_UNSUPPORTED, "npad %d needs more than 512 TMEM columns", p.npad);
   p.tmem_cols = cols;
-  p.a_base_off_mode = g_opt_base_off_mode;
+  p.issue_code = 0;
+  if (!g_opt_generic_issue) {
+    const int nidx = p.npad == 16 ? 0 : p.npad == 32 ? 1 : p.npad == 64 ? 2 : -1;
+    if (L.kh == 3 && L.kw == 3 && nidx >= 0 && (p.SW == 16 || p.SW == 32)) p.issue_code = (p.SW == 16 ? 1 : 4) + nidx;
+    else if (L.kh == 9 && L.kw == 9 && p.SW == 32 && p.npad == 64 && p.cin == 16) p.issue_code = 7;
+    else if (L.kh == 5 && L.kw == 5 && p.SW == 32 && p.npad == 16 && p.cin == 32) p.issue_code = 8;
+    else if (L.kh == 1 && L.kw == 1 && p.SW == 32 && p.npad == 32 && p.cin == 64) p.issue_code = 9;
+  }
   p.act = io.act;
   p.s1 = io.s1; p.s2 = io.s2;
   p.r1 = io.r1; p.r1_C = io.r1_C; p.r1_coff = io.r1_coff + pp.co_lo;
@@ -381,7 +388,7 @@ int csr_device_check(void) {
 
 int csr_set_option(int32_t key, int32_t value) {
   switch (key) {
-    case 1: g_opt_base_off_mode = value; return CSR_OK;
+    case 1: g_opt_generic_issue = value; return CSR_OK;   // 1 = force the rolled MMA-issue loop
     case 2: g_opt_force_sw = value; return CSR_OK;
     case 3: g_opt_max_slots = value < 1 ? 1 : value; return CSR_OK;
     default: return fail(CSR_ERR_BAD_ARG, "unknown option key %d", key);

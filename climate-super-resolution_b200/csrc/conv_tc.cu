@@ -75,6 +75,50 @@ __device__ __forceinline__ void store16_bf16(void* base, size_t pix, int C, int 
   dst[1] = b;
 }
 
+// Fully unrolled MMA issue for one k-block: every descriptor is (uniform base + compile-time immediate), so the
+// elected lane runs a straight line of UTCHMMA with no address arithmetic in between (the tcgen05 SS-mode floor is
+// ~45 clk per M=128,K=16 MMA; a rolled loop with runtime strides was issue-bound at ~85 clk).
+// Weight blocks of a k-block are stored [tap][ks] (see pack_weight_kernel).
+template <int KH, int KW, int SW, int NPAD, int KS>
+__device__ __forceinline__ void issue_kblock(uint32_t d_tmem, uint32_t a16, uint32_t b16, uint32_t a_hi, uint32_t b_hi, uint32_t idesc,
+                                             uint32_t acc0) {
+#pragma unroll
+  for (int dy = 0; dy < KH; ++dy)
+#pragma unroll
+    for (int dx = 0; dx < KW; ++dx)
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks)
+        umma_bf16_split(d_tmem, a16 + (dy * SW + dx) * 8 + ks * 2, a_hi, b16 + ((dy * KW + dx) * KS + ks) * (NPAD * 2), b_hi, idesc,
+                        (dy | dx | ks) ? 1u : acc0);
+}
+
+template <int KH, int KW, int SW, int NPAD>
+__device__ __forceinline__ void issue_kblock_ks(int ks_here, uint32_t d_tmem, uint32_t a16, uint32_t b16, uint32_t a_hi, uint32_t b_hi,
+                                                uint32_t idesc, uint32_t acc0) {
+  switch (ks_here) {
+    case 1: issue_kblock<KH, KW, SW, NPAD, 1>(d_tmem, a16, b16, a_hi, b_hi, idesc, acc0); break;
+    case 2: issue_kblock<KH, KW, SW, NPAD, 2>(d_tmem, a16, b16, a_hi, b_hi, idesc, acc0); break;
+    case 3: issue_kblock<KH, KW, SW, NPAD, 3>(d_tmem, a16, b16, a_hi, b_hi, idesc, acc0); break;
+    default: issue_kblock<KH, KW, SW, NPAD, 4>(d_tmem, a16, b16, a_hi, b_hi, idesc, acc0); break;
+  }
+}
+
+// Generic (rolled) issue for shapes without an unrolled instantiation.
+__device__ __forceinline__ void issue_kblock_generic(const ConvParams& p, int ks_here, uint32_t d_tmem, uint32_t a16, uint32_t b16,
+                                                     uint32_t a_hi, uint32_t b_hi, uint32_t idesc, uint32_t acc0) {
+  const uint32_t b_step16 = static_cast<uint32_t>(p.npad * 32) >> 4;
+  const uint32_t row16 = static_cast<uint32_t>(p.SW) * 8u;
+  uint32_t acc = acc0;
+  for (int dy = 0; dy < p.KH; ++dy, a16 += row16) {
+    uint32_t a_lo = a16;
+    for (int dx = 0; dx < p.KW; ++dx, a_lo += 8)
+      for (int ks = 0; ks < ks_here; ++ks, b16 += b_step16) {
+        umma_bf16_split(d_tmem, a_lo + ks * 2, a_hi, b16, b_hi, idesc, acc);
+        acc = 1;
+      }
+  }
+}
+
 }  // namespace
 
 __global__ void __launch_bounds__(kConvThreads, 1)
@@ -159,12 +203,10 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
     // All 32 lanes run the (warp-uniform) control flow so addresses live in uniform registers; one elected lane
     // issues.  Per MMA only the descriptor start-address fields change: two 32-bit adds.
     const uint32_t idesc = make_idesc_bf16(kTileM, p.npad);
-    const uint32_t b_step16 = static_cast<uint32_t>(p.npad * 32) >> 4;         // one (tap,kstep) weight block, in 16-byte units
-    const uint32_t b_tap16 = static_cast<uint32_t>(ksteps_total) * b_step16;  // one tap
     const uint32_t a_hi = (1024u >> 4) | (1u << 14) | (2u << 29);             // SBO 1024 B, version 1, 128B swizzle
     const uint32_t b_hi = (256u >> 4) | (1u << 14);                           // SBO 256 B, version 1, no swizzle
     const uint32_t a_lbo = (16u >> 4) << 16, b_lbo = (128u >> 4) << 16;
-    const uint32_t row16 = static_cast<uint32_t>(p.SW) * 8u;                  // one window row (SW pixels x 128 B) in 16-byte units
+    const uint32_t kb_w16 = static_cast<uint32_t>(p.KH * p.KW * 4 * p.npad * 32) >> 4;   // weights of one full k-block, 16 B units
     mbar_wait(bar_w, 0);
     tc_fence_after();
     int slot = 0, it = 0;
@@ -174,29 +216,30 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
       mbar_wait(bar_acc_empty(buf), ((it >> 1) & 1) ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + buf * p.npad;
-      uint32_t accumulate = 0;
       for (int kb = 0; kb < p.n_kblocks; ++kb) {
         mbar_wait(bar_a_full(slot), phase);
         tc_fence_after();
         const int ks_here = min(4, ksteps_total - kb * 4);
-        uint32_t a_row = ((slots_addr + slot * p.slot_bytes) >> 4) | a_lbo;
-        uint32_t b_lo = ((w_addr >> 4) + static_cast<uint32_t>(kb * 4) * b_step16) | b_lbo;
+        const uint32_t a16 = ((slots_addr + slot * p.slot_bytes) >> 4) | a_lbo;
+        const uint32_t b16 = ((w_addr >> 4) + static_cast<uint32_t>(kb) * kb_w16) | b_lbo;
+        const uint32_t acc0 = kb ? 1u : 0u;
         if (elect_one()) {
-          for (int dy = 0; dy < p.KH; ++dy, a_row += row16) {
-            uint32_t a_lo = a_row;
-            for (int dx = 0; dx < p.KW; ++dx, a_lo += 8, b_lo += b_tap16) {
-              umma_bf16_split(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, accumulate);
-              accumulate = 1;
-              if (ks_here > 1) umma_bf16_split(d_tmem, a_lo + 2, a_hi, b_lo + b_step16, b_hi, idesc, 1);
-              if (ks_here > 2) umma_bf16_split(d_tmem, a_lo + 4, a_hi, b_lo + 2 * b_step16, b_hi, idesc, 1);
-              if (ks_here > 3) umma_bf16_split(d_tmem, a_lo + 6, a_hi, b_lo + 3 * b_step16, b_hi, idesc, 1);
-            }
+          switch (p.issue_code) {
+            case 1: issue_kblock_ks<3, 3, 16, 16>(ks_here, d_tmem, a16, b16, a_hi, b_hi, idesc, acc0); break;
+            case 2: issue_kblock_ks<3, 3, 16, 32>(ks_here, d_tmem, a16, b16, a_hi, b_hi, idesc, acc0); break;
+            case 3: issue_kblock_ks<3, 3, 16, 64>(ks_here, d_tmem, a16, b16, a_hi, b_hi, idesc, acc0); break;
+            case 4: issue_kblock_ks<3, 3, 32, 16>(ks_here, d_tmem, a16, b16, a_hi, b_hi, idesc, acc0); break;
+            case 5: issue_kblock_ks<3, 3, 32, 32>(ks_here, d_tmem, a16, b16, a_hi, b_hi, idesc, acc0); break;
+            case 6: issue_kblock_ks<3, 3, 32, 64>(ks_here, d_tmem, a16, b16, a_hi, b_hi, idesc, acc0); break;
+            case 7: issue_kblock<9, 9, 32, 64, 1>(d_tmem, a16, b16, a_hi, b_hi, idesc, acc0); break;
+            case 8: issue_kblock<5, 5, 32, 16, 2>(d_tmem, a16, b16, a_hi, b_hi, idesc, acc0); break;
+            case 9: issue_kblock<1, 1, 32, 32, 4>(d_tmem, a16, b16, a_hi, b_hi, idesc, acc0); break;
+            default: issue_kblock_generic(p, ks_here, d_tmem, a16, b16, a_hi, b_hi, idesc, acc0); break;
           }
           umma_commit(bar_a_empty(slot));                                  // window slot reusable once these MMAs have read it
           if (kb == p.n_kblocks - 1) umma_commit(bar_acc_full(buf));       // accumulator complete -> epilogue
         }
         __syncwarp();
-        accumulate = 1;
         if (++slot == S) { slot = 0; phase ^= 1; }
       }
     }

@@ -28,10 +28,10 @@ struct ConvParams {
   int n_slots;     // activation-window ring depth
   int w_bytes;     // packed weights: taps * (cin/16) * npad * 32
   int tmem_cols;   // power of two >= max(32, 2*npad)
-  int a_base_off_mode;  // debug: 0 -> descriptor base_offset 0, 1 -> (start_addr>>7)&7
+  int issue_code;  // selects a fully unrolled MMA-issue instantiation (0 = generic rolled loop), see conv_tc.cu
   // epilogue
   const float* bias;   // [npad] fp32 (zero padded)
-  const void* wpk;     // packed bf16 weights (global), layout [tap][kstep][npad/8][2][8][8]
+  const void* wpk;     // packed bf16 weights (global), layout [kblock][tap][kstep in kblock][npad/8][2][8][8]
   int act;             // 0 none, 1 leaky-relu 0.2, 2 relu
   float s1, s2;
   const void* r1; int r1_C, r1_coff;

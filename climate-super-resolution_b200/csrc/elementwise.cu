@@ -5,26 +5,39 @@
 namespace csr {
 
 // ---- weights: fp32 OIHW -> bf16 UMMA B tiles ------------------------------------------------------------
-// Packed layout per layer: [tap][kstep = cin_pad/16][ngrp = npad/8][kchunk 2][row 8][elem 8]; one (tap,kstep)
-// block is an npad x 16 K-major operand made of 8x16-byte core matrices (LBO 128 B between the two k-chunks,
-// SBO 256 B between 8-row groups).  Rows >= cout and channels >= cin are zero.
+// Packed layout per layer: [kblock = 64 input channels][tap][kstep within the k-block][ngrp = npad/8][kchunk 2][row 8][elem 8];
+// one (tap,kstep) block is an npad x 16 K-major operand made of 8x16-byte core matrices (LBO 128 B between the two
+// k-chunks, SBO 256 B between 8-row groups).  The last k-block may hold fewer than 4 k-steps.  Rows >= cout and
+// channels >= cin are zero.
 __global__ void pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ dst, int cout, int cin, int kh,
                                    int kw, int co_lo, int npad, int cin_pad) {
   const int ksteps = cin_pad >> 4;
-  const long total = static_cast<long>(kh) * kw * ksteps * npad * 16;
+  const int taps = kh * kw;
+  const int full_kb = ksteps >> 2, rem = ksteps & 3;
+  const long total = static_cast<long>(taps) * ksteps * npad * 16;
   for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long>(gridDim.x) * blockDim.x) {
     const int e = i & 7;
     const int row = (i >> 3) & 7;
     const int kchunk = (i >> 6) & 1;
     long r = i >> 7;
     const int ngrp = r % (npad >> 3);
-    r /= (npad >> 3);
-    const int ks = r % ksteps;
-    const int tap = r / ksteps;
+    int blk = static_cast<int>(r / (npad >> 3));          // block index in [kblock][tap][ks] order
+    int kb, tap, ks;
+    if (blk < full_kb * taps * 4) {
+      kb = blk / (taps * 4);
+      blk -= kb * taps * 4;
+      tap = blk >> 2;
+      ks = blk & 3;
+    } else {
+      blk -= full_kb * taps * 4;
+      kb = full_kb;
+      tap = blk / rem;
+      ks = blk - tap * rem;
+    }
     const int co = co_lo + ngrp * 8 + row;
-    const int ci = ks * 16 + kchunk * 8 + e;
+    const int ci = (kb * 4 + ks) * 16 + kchunk * 8 + e;
     float v = 0.f;
-    if (ngrp * 8 + row < npad && co < cout && ci < cin) {
+    if (co < cout && ci < cin) {
       const int dy = tap / kw, dx = tap % kw;
       v = w[((static_cast<long>(co) * cin + ci) * kh + dy) * kw + dx];
     }
