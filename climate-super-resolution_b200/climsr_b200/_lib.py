@@ -42,6 +42,7 @@ def _load():
         "csr_device_check": (C.c_int, []),
         "csr_set_option": (C.c_int, [i32, i32]),
         "csr_kernel_launch_count": (C.c_int64, []),
+        "csr_debug_set_trace": (C.c_int, [vp]),
         "csr_num_layers": (C.c_int, [nd]),
         "csr_layer_shape": (C.c_int, [nd, i32, C.POINTER(i32 * 4), C.c_char_p, sz]),
         "csr_packed_weight_bytes": (sz, [nd]),
@@ -67,7 +68,7 @@ def _load():
 
 
 lib = _load()
-EXPORTS = ("csr_abi_version", "csr_last_error", "csr_device_check", "csr_set_option", "csr_kernel_launch_count", "csr_num_layers",
+EXPORTS = ("csr_abi_version", "csr_last_error", "csr_device_check", "csr_set_option", "csr_kernel_launch_count", "csr_debug_set_trace", "csr_num_layers",
            "csr_layer_shape", "csr_packed_weight_bytes", "csr_pack_weights", "csr_workspace_bytes", "csr_plan_create",
            "csr_plan_forward", "csr_plan_num_launches", "csr_plan_destroy", "csr_generator_forward", "csr_conv2d_scratch_bytes",
            "csr_conv2d_nhwc", "csr_nchw_f32_to_nhwc_bf16", "csr_nhwc_bf16_to_nchw_f32", "csr_metrics_scratch_bytes",

@@ -19,6 +19,7 @@ namespace csr {
 static thread_local char g_err[512] = "";
 static std::atomic<long long> g_launches{0};
 static int g_opt_generic_issue = 0;
+static long long* g_trace = nullptr;
 static int g_opt_force_sw = 0;
 static int g_opt_max_slots = 8;
 
@@ -240,6 +241,7 @@ static int build_conv(const LayerSpec& L, const PackLayer& pl, const PackPart& p
   while (cols < 2 * p.npad) cols *= 2;
   if (cols > 512) return fail(CSR_ERR_UNSUPPORTED, "npad %d needs more than 512 TMEM columns", p.npad);
   p.tmem_cols = cols;
+  p.trace = g_trace;
   p.issue_code = 0;
   if (!g_opt_generic_issue) {
     const int nidx = p.npad == 16 ? 0 : p.npad == 32 ? 1 : p.npad == 64 ? 2 : -1;
@@ -396,6 +398,11 @@ int csr_set_option(int32_t key, int32_t value) {
 }
 
 int64_t csr_kernel_launch_count(void) { return g_launches.load(); }
+
+int csr_debug_set_trace(void* device_buffer) {
+  g_trace = reinterpret_cast<long long*>(device_buffer);
+  return CSR_OK;
+}
 
 int csr_num_layers(const CsrNetDesc* net) {
   int rc = check_net(net);

@@ -27,6 +27,11 @@ namespace csr {
 
 namespace {
 
+#define CSR_TRACE(role, tile_it, ev)                                                             \
+  do {                                                                                          \
+    if (p.trace && blockIdx.x == 0 && (tile_it) < 64) p.trace[((role) * 64 + (tile_it)) * 4 + (ev)] = clock64(); \
+  } while (0)
+
 struct Tile {
   int n, y0, x0;
 };
@@ -183,12 +188,14 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
       }
     }
     __syncwarp();
-    int slot = 0;
+    int slot = 0, pit = 0;
     uint32_t phase = 0;
-    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++pit) {
       const Tile tl = decode_tile(p, t);
       for (int kb = 0; kb < p.n_kblocks; ++kb) {
+        if (kb == 0 && lane == 0) CSR_TRACE(0, pit, 0);
         mbar_wait(bar_a_empty(slot), phase ^ 1);
+        if (kb == 0 && lane == 0) CSR_TRACE(0, pit, 1);
         if (elect_one()) {
           mbar_arrive_expect_tx(bar_a_full(slot), p.win_bytes);
           tma_load_4d(slots_addr + slot * p.slot_bytes, &tmap, bar_a_full(slot), p.cin_off + kb * 64, tl.x0 - p.PW, tl.y0 - p.PH,
@@ -213,12 +220,15 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
     uint32_t phase = 0;
     for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
       const int buf = it & 1;
+      if (lane == 0) CSR_TRACE(1, it, 0);
       mbar_wait(bar_acc_empty(buf), ((it >> 1) & 1) ^ 1);
       tc_fence_after();
+      if (lane == 0) CSR_TRACE(1, it, 1);
       const uint32_t d_tmem = tmem_base + buf * p.npad;
       for (int kb = 0; kb < p.n_kblocks; ++kb) {
         mbar_wait(bar_a_full(slot), phase);
         tc_fence_after();
+        if (kb == 0 && lane == 0) CSR_TRACE(1, it, 2);
         const int ks_here = min(4, ksteps_total - kb * 4);
         const uint32_t a16 = ((slots_addr + slot * p.slot_bytes) >> 4) | a_lbo;
         const uint32_t b16 = ((w_addr >> 4) + static_cast<uint32_t>(kb) * kb_w16) | b_lbo;
@@ -240,6 +250,7 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
           if (kb == p.n_kblocks - 1) umma_commit(bar_acc_full(buf));       // accumulator complete -> epilogue
         }
         __syncwarp();
+        if (kb == p.n_kblocks - 1 && lane == 0) CSR_TRACE(1, it, 3);
         if (++slot == S) { slot = 0; phase ^= 1; }
       }
     }
@@ -258,8 +269,10 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
       const int x = tl.x0 + tx;
       const bool valid = (tx < p.TW) && (y < p.H) && (x < p.W);
       const size_t pix = (static_cast<size_t>(tl.n) * p.H + y) * p.W + x;
+      if (threadIdx.x == 64) CSR_TRACE(2, it, 0);
       mbar_wait(bar_acc_full(buf), (it >> 1) & 1);
       tc_fence_after();
+      if (threadIdx.x == 64) CSR_TRACE(2, it, 1);
       const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16) + buf * p.npad;
       for (int c = 0; c < n_chunks; ++c) {
         uint32_t raw[16];
@@ -305,6 +318,7 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
           }
         }
       }
+      if (threadIdx.x == 64) CSR_TRACE(2, it, 2);
       tc_fence_before();
       mbar_arrive(bar_acc_empty(buf));
     }

@@ -37,6 +37,7 @@ struct ConvParams {
   const void* r1; int r1_C, r1_coff;
   const void* r2; int r2_C, r2_coff;
   void* out; int out_C, out_coff; int out_mode;   // CsrOutMode
+  long long* trace;   // debug: per-role clock64 timestamps of CTA 0 (nullptr = off), [3 roles][64 tiles][4 events]
 };
 
 // Returns cudaError_t (as int). tmap: 4-D (C, W, H, N) bf16 tensor map with box (64, SW, win_rows, 1), SWIZZLE_128B.

@@ -1,0 +1,43 @@
+"""Per-role pipeline trace of one conv launch (CTA 0): where does a tile's time go?  Debug tool, run on a B200."""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "climate-super-resolution_b200"))
+from climsr_b200 import ops  # noqa: E402
+from climsr_b200._lib import lib  # noqa: E402
+
+
+def run(name, n, h, w, cin, cout, k, in_c, act="lrelu", out_coff=0):
+    x = torch.zeros((n, h, w, in_c), dtype=torch.bfloat16, device="cuda")
+    wt = torch.rand((cout, cin, k, k), device="cuda") - 0.5
+    b = torch.rand((cout,), device="cuda")
+    trace = torch.zeros(3 * 64 * 4, dtype=torch.int64, device="cuda")
+    out = torch.zeros((n, h, w, max(in_c, 64)), dtype=torch.bfloat16, device="cuda") if cout > 1 else None
+    for rep in range(2):
+        lib.csr_debug_set_trace(trace.data_ptr())
+        if out is not None:
+            ops.conv2d_nhwc(x, wt, b, act=act, out=out, out_coff=out_coff)
+        else:
+            ops.conv2d_nhwc(x, wt, b, act=act)
+        torch.cuda.synchronize()
+    lib.csr_debug_set_trace(None)
+    t = trace.cpu().view(3, 64, 4)
+    t0 = int(t[0, 0, 0])
+    print(f"== {name}: n{n} {h}x{w} cin{cin} cout{cout} k{k}")
+    print(" tile | prod: wait_empty_start wait_done | mma: start accempty_ok afull_ok issued | epi: start accfull_ok done")
+    for i in range(0, 18):
+        if int(t[1, i, 0]) == 0:
+            break
+        r = lambda v: int(v) - t0  # noqa: E731
+        print(f" {i:4d} | {r(t[0,i,0]):8d} {r(t[0,i,1]):8d} | {r(t[1,i,0]):8d} {r(t[1,i,1]):8d} {r(t[1,i,2]):8d} {r(t[1,i,3]):8d} | "
+              f"{r(t[2,i,0]):8d} {r(t[2,i,1]):8d} {r(t[2,i,2]):8d}")
+
+
+if __name__ == "__main__":
+    run("rdb.conv1", 64, 64, 64, 64, 16, 3, 128, out_coff=64)
+    run("rdb.conv5", 64, 64, 64, 128, 64, 3, 128, act="none")
+    run("HRconv", 16, 256, 256, 64, 64, 3, 64)
+    run("conv_first", 64, 64, 64, 4, 64, 3, 64, act="none")
