@@ -18,7 +18,7 @@ namespace csr {
 // ------------------------------------------------------------------------------------------- errors
 static thread_local char g_err[512] = "";
 static std::atomic<long long> g_launches{0};
-static int g_opt_generic_issue = 0;
+static int g_opt_pdl = 1;
 static long long* g_trace = nullptr;
 static int g_opt_force_sw = 0;
 static int g_opt_max_slots = 8;
@@ -90,7 +90,10 @@ static int encode_act_map(CUtensorMap* m, const void* base, int N, int H, int W,
 // ------------------------------------------------------------------------------------------- layer table
 struct LayerSpec {
   std::string name;
-  int cout, cin, kh, kw;
+  int cout, cin, kh, kw;   // reference (state_dict) shape
+  int fold = 0;            // 1: executed as a kh x 1 conv over an x-im2col input with kw*cin channels (srcnn.conv1)
+  int ekw() const { return fold ? 1 : kw; }
+  int ecin() const { return fold ? cin * kw : cin; }
 };
 
 static int check_net(const CsrNetDesc* net) {
@@ -119,7 +122,7 @@ static std::vector<LayerSpec> layer_table(const CsrNetDesc& d) {
   v.push_back({"upconv2", d.nf, d.nf, 3, 3});
   v.push_back({"HRconv", d.nf, d.nf, 3, 3});
   v.push_back({"conv_last", d.out_channels, d.nf, 3, 3});
-  v.push_back({"srcnn.conv1", 64, 3, 9, 9});
+  v.push_back({"srcnn.conv1", 64, 3, 9, 9, 1});
   v.push_back({"srcnn.conv2", 32, 64, 1, 1});
   v.push_back({"srcnn.conv3", d.out_channels, 32, 5, 5});
   return v;
@@ -136,17 +139,20 @@ struct PackLayer {
   int cin_pad;
   std::vector<PackPart> parts;
 };
-static int part_weight_bytes(const LayerSpec& L, int npad) { return L.kh * L.kw * ((L.cin + 15) / 16 * 16) * npad * 2; }
+static int part_weight_bytes(const LayerSpec& L, int npad) { return L.kh * L.ekw() * ((L.ecin() + 15) / 16 * 16) * npad * 2; }
+// UMMA N = KW*npad <= 256 and two accumulator buffers of KW*npad fp32 columns must fit the 512 TMEM columns.
+static int max_npad(const LayerSpec& L) { return std::max(16, 256 / L.ekw() / 16 * 16); }
 
 static std::vector<PackLayer> pack_layout(const std::vector<LayerSpec>& layers, size_t* total) {
   std::vector<PackLayer> out;
   size_t off = 0;
   for (const auto& L : layers) {
     PackLayer pl;
-    pl.cin_pad = (L.cin + 15) / 16 * 16;
+    pl.cin_pad = (L.ecin() + 15) / 16 * 16;
     const int npad_full = (L.cout + 15) / 16 * 16;
     int nsplit = 1;
-    while (part_weight_bytes(L, ceil_div(npad_full / 16, nsplit) * 16) > kMaxResidentWeightBytes && nsplit < npad_full / 16) ++nsplit;
+    while ((part_weight_bytes(L, ceil_div(npad_full / 16, nsplit) * 16) > kMaxResidentWeightBytes ||
+            ceil_div(npad_full / 16, nsplit) * 16 > max_npad(L)) && nsplit < npad_full / 16) ++nsplit;
     const int per = ceil_div(npad_full / 16, nsplit) * 16;
     for (int lo = 0; lo < npad_full; lo += per) {
       PackPart pp;
@@ -174,13 +180,15 @@ static int choose_tiling(int H, int W, int KH, int KW, int w_bytes, int n_kblock
   const int fixed = 1024 + (int)align_up(w_bytes, 128) + 1024 + 512;
   double best = -1;
   for (int SW = 16; SW <= 128; SW *= 2) {
-    if (g_opt_force_sw ? SW != g_opt_force_sw : SW > 32) continue;   // 16/32 have unrolled MMA-issue instantiations
+    if (g_opt_force_sw && SW != g_opt_force_sw) continue;
+    // The epilogue sums the folded horizontal taps with warp shuffles: a window row must not straddle two warps.
+    if (KW > 1 && SW > 32) continue;
     const int TW = SW - (KW - 1);
     if (TW < 1) continue;
     const int TH = kTileM / SW;
     const int win_rows = TH + KH - 1;
     const int win_bytes = win_rows * SW * 128;
-    const int slot_bytes = (int)align_up(win_bytes + (KW - 1) * 128, 1024);
+    const int slot_bytes = (int)align_up(win_bytes, 1024);
     const int slots = std::min(g_opt_max_slots, (kSmemLimit - fixed) / slot_bytes);
     if (slots < 1) continue;
     const double tiles = (double)ceil_div(H, TH) * ceil_div(W, TW);
@@ -201,6 +209,7 @@ struct ConvLaunch {
   ConvParams p;
   CUtensorMap tmap;
   size_t w_off = 0, b_off = 0;  // offsets into the packed blob (resolved at forward time)
+  bool keep_out = false;        // fp32-planar output that is NOT the caller's `out` tensor
 };
 
 struct ConvIO {
@@ -218,7 +227,7 @@ static int build_conv(const LayerSpec& L, const PackLayer& pl, const PackPart& p
   ConvParams& p = cl->p;
   memset(&p, 0, sizeof(p));
   p.N = N; p.H = H; p.W = W;
-  p.KH = L.kh; p.KW = L.kw; p.PH = L.kh / 2; p.PW = L.kw / 2;
+  p.KH = L.kh; p.KW = L.ekw(); p.PH = L.kh / 2; p.PW = L.ekw() / 2;
   p.cin_off = io.cin_off;
   p.cin = pl.cin_pad;
   if (io.cin_off + p.cin > io.in_C)
@@ -228,7 +237,7 @@ static int build_conv(const LayerSpec& L, const PackLayer& pl, const PackPart& p
   p.n_kblocks = ceil_div(p.cin, 64);
   p.w_bytes = pp.w_bytes;
   Tiling tl;
-  int rc = choose_tiling(H, W, L.kh, L.kw, p.w_bytes, p.n_kblocks, &tl);
+  int rc = choose_tiling(H, W, L.kh, L.ekw(), p.w_bytes, p.n_kblocks, &tl);
   if (rc) return rc;
   p.SW = tl.SW; p.TH = tl.TH; p.TW = tl.TW;
   p.sw_shift = 0;
@@ -238,18 +247,11 @@ static int build_conv(const LayerSpec& L, const PackLayer& pl, const PackPart& p
   p.num_tiles = p.tiles_x * p.tiles_y * N;
   p.win_rows = tl.win_rows; p.win_bytes = tl.win_bytes; p.slot_bytes = tl.slot_bytes; p.n_slots = tl.n_slots;
   int cols = 32;
-  while (cols < 2 * p.npad) cols *= 2;
-  if (cols > 512) return fail(CSR_ERR_UNSUPPORTED, "npad %d needs more than 512 TMEM columns", p.npad);
+  while (cols < 2 * p.KW * p.npad) cols *= 2;
+  if (cols > 512 || p.KW * p.npad > 256) return fail(CSR_ERR_UNSUPPORTED, "KW*npad = %d exceeds the UMMA N / TMEM budget", p.KW * p.npad);
   p.tmem_cols = cols;
   p.trace = g_trace;
-  p.issue_code = 0;
-  if (!g_opt_generic_issue) {
-    const int nidx = p.npad == 16 ? 0 : p.npad == 32 ? 1 : p.npad == 64 ? 2 : -1;
-    if (L.kh == 3 && L.kw == 3 && nidx >= 0 && (p.SW == 16 || p.SW == 32)) p.issue_code = (p.SW == 16 ? 1 : 4) + nidx;
-    else if (L.kh == 9 && L.kw == 9 && p.SW == 32 && p.npad == 64 && p.cin == 16) p.issue_code = 7;
-    else if (L.kh == 5 && L.kw == 5 && p.SW == 32 && p.npad == 16 && p.cin == 32) p.issue_code = 8;
-    else if (L.kh == 1 && L.kw == 1 && p.SW == 32 && p.npad == 32 && p.cin == 64) p.issue_code = 9;
-  }
+  p.use_pdl = g_opt_pdl;
   p.act = io.act;
   p.s1 = io.s1; p.s2 = io.s2;
   p.r1 = io.r1; p.r1_C = io.r1_C; p.r1_coff = io.r1_coff + pp.co_lo;
@@ -267,15 +269,15 @@ struct CsrPlan {
   int N, h, w;
   int sms;
   std::vector<csr::ConvLaunch> convs;   // in execution order
-  int idx_conv_last;                    // pack_aux runs right before this conv
-  void* xin; void* sin;
+  int idx_srcnn1;                       // the SRCNN x-im2col pack kernel runs right before this conv
+  void* xin; void* sin; float* tlast;
   size_t packed_bytes;
 };
 
 namespace csr {
 
 struct WsLayout {
-  size_t xin, fea0, cat[3], up1, up2, hrA, hrB, total;
+  size_t xin, fea0, cat[3], up1, up2, hrA, hrB, tlast, total;
   int ccat;
 };
 static WsLayout ws_layout(const CsrNetDesc& d, int N, int h, int w) {
@@ -291,6 +293,7 @@ static WsLayout ws_layout(const CsrNetDesc& d, int N, int h, int w) {
   L.up2 = take(hr * 64 * 2);   // upconv2 input, later reused as the SRCNN input [out, elev, mask, 0...]
   L.hrA = take(hr * 64 * 2);
   L.hrB = take(hr * 64 * 2);
+  L.tlast = take(hr * 4);      // conv_last output, fp32 planar
   L.total = off;
   return L;
 }
@@ -303,7 +306,7 @@ static int plan_build(CsrPlan* P, void* ws) {
   void* xin = base + L.xin; void* fea0 = base + L.fea0;
   void* cat[3] = {base + L.cat[0], base + L.cat[1], base + L.cat[2]};
   void* up1 = base + L.up1; void* up2 = base + L.up2; void* hrA = base + L.hrA; void* hrB = base + L.hrB;
-  P->xin = xin; P->sin = up2;
+  P->xin = xin; P->sin = up2; P->tlast = reinterpret_cast<float*>(base + L.tlast);
   const std::vector<LayerSpec> layers = layer_table(d);
   size_t total = 0;
   const std::vector<PackLayer> packs = pack_layout(layers, &total);
@@ -359,10 +362,12 @@ static int plan_build(CsrPlan* P, void* ws) {
   if (rc) return rc;
   rc = add(H, W, {hrA, 64, 0, hrB, 64, 0, CSR_OUT_BF16_NHWC, CSR_ACT_LRELU02, nullptr, 0, 0, 1.f, nullptr, 0, 0, 1.f});  // HRconv (esrgan.py:99)
   if (rc) return rc;
-  P->idx_conv_last = (int)P->convs.size();
-  rc = add(H, W, {hrB, 64, 0, up2, 64, 0, CSR_OUT_BF16_NHWC, CSR_ACT_NONE, nullptr, 0, 0, 1.f, nullptr, 0, 0, 1.f});     // conv_last -> sin ch0
+  // conv_last -> fp32 planar temp; then [out, elev, mask] is packed (with srcnn.conv1's horizontal window) into `up2`
+  rc = add(H, W, {hrB, 64, 0, P->tlast, 1, 0, CSR_OUT_F32_PLANAR, CSR_ACT_NONE, nullptr, 0, 0, 1.f, nullptr, 0, 0, 1.f});
   if (rc) return rc;
-  rc = add(H, W, {up2, 64, 0, hrA, 64, 0, CSR_OUT_BF16_NHWC, CSR_ACT_RELU, nullptr, 0, 0, 1.f, nullptr, 0, 0, 1.f});     // srcnn.conv1 9x9
+  P->convs.back().keep_out = true;
+  P->idx_srcnn1 = (int)P->convs.size();
+  rc = add(H, W, {up2, 64, 0, hrA, 64, 0, CSR_OUT_BF16_NHWC, CSR_ACT_RELU, nullptr, 0, 0, 1.f, nullptr, 0, 0, 1.f});     // srcnn.conv1 (9x1 folded)
   if (rc) return rc;
   rc = add(H, W, {hrA, 64, 0, hrB, 64, 0, CSR_OUT_BF16_NHWC, CSR_ACT_RELU, nullptr, 0, 0, 1.f, nullptr, 0, 0, 1.f});     // srcnn.conv2 1x1
   if (rc) return rc;
@@ -390,7 +395,7 @@ int csr_device_check(void) {
 
 int csr_set_option(int32_t key, int32_t value) {
   switch (key) {
-    case 1: g_opt_generic_issue = value; return CSR_OK;   // 1 = force the rolled MMA-issue loop
+    case 1: g_opt_pdl = value ? 1 : 0; return CSR_OK;      // programmatic dependent launch on/off
     case 2: g_opt_force_sw = value; return CSR_OK;
     case 3: g_opt_max_slots = value < 1 ? 1 : value; return CSR_OK;
     default: return fail(CSR_ERR_BAD_ARG, "unknown option key %d", key);
@@ -441,8 +446,8 @@ int csr_pack_weights(const CsrNetDesc* net, const float* const* w, const float* 
   for (size_t i = 0; i < layers.size(); ++i) {
     if (!w[i] || !b[i]) return fail(CSR_ERR_BAD_ARG, "null weight/bias pointer for layer %zu", i);
     for (const PackPart& pp : packs[i].parts) {
-      CSR_CUDA(launch_pack_weight(w[i], base + pp.w_off, layers[i].cout, layers[i].cin, layers[i].kh, layers[i].kw, pp.co_lo, pp.npad,
-                                  packs[i].cin_pad, s));
+      CSR_CUDA(launch_pack_weight(w[i], base + pp.w_off, layers[i].cout, layers[i].cin, layers[i].kh, layers[i].kw, layers[i].fold,
+                                  pp.co_lo, pp.npad, packs[i].cin_pad, s));
       CSR_CUDA(launch_pack_bias(b[i], reinterpret_cast<float*>(base + pp.b_off), layers[i].cout, pp.co_lo, pp.npad, s));
       g_launches += 2;
     }
@@ -485,14 +490,14 @@ int csr_plan_forward(CsrPlan* P, const void* packed, const float* x, const float
   CSR_CUDA(launch_nchw_to_nhwc(x, P->xin, P->N, P->net.in_channels, P->h, P->w, 64, 16, s));
   ++g_launches;
   for (size_t i = 0; i < P->convs.size(); ++i) {
-    if ((int)i == P->idx_conv_last) {
-      CSR_CUDA(launch_pack_aux(elev, mask, P->sin, (long)P->N * P->h * P->w * 16, 64, s));
+    if ((int)i == P->idx_srcnn1) {
+      CSR_CUDA(launch_pack_srcnn_in(P->tlast, elev, mask, P->sin, 4 * P->w, (long)P->N * P->h * P->w * 16, 64, s));
       ++g_launches;
     }
     ConvLaunch& cl = P->convs[i];
     cl.p.wpk = pk + cl.w_off;
     cl.p.bias = reinterpret_cast<const float*>(pk + cl.b_off);
-    if (cl.p.out_mode == CSR_OUT_F32_PLANAR) cl.p.out = out;
+    if (cl.p.out_mode == CSR_OUT_F32_PLANAR && !cl.keep_out) cl.p.out = out;
     int e = launch_conv_tc(cl.p, cl.tmap, P->sms, s);
     if (e) return fail(CSR_ERR_CUDA, "conv launch %zu failed: %s", i, cudaGetErrorString((cudaError_t)e));
     ++g_launches;
@@ -517,7 +522,7 @@ static int conv_desc_to_layer(const CsrConvDesc* d, LayerSpec* L) {
   if (!(d->kh & 1) || !(d->kw & 1) || d->kh > 9 || d->kw > 9) return fail(CSR_ERR_UNSUPPORTED, "kernel %dx%d (odd, <= 9 supported)", d->kh, d->kw);
   if (d->cout > 256) return fail(CSR_ERR_UNSUPPORTED, "cout %d > 256", d->cout);
   if (d->out_mode == CSR_OUT_F32_PLANAR && d->cout != 1) return fail(CSR_ERR_UNSUPPORTED, "fp32 planar output needs cout == 1");
-  *L = {"conv", d->cout, d->cin, d->kh, d->kw};
+  *L = {"conv", d->cout, d->cin, d->kh, d->kw, 0};
   return CSR_OK;
 }
 
@@ -546,7 +551,7 @@ int csr_conv2d_nhwc(const CsrConvDesc* d, const void* in, const float* weight, c
   ConvIO io = {in, d->in_c, 0, out, d->out_c, d->out_coff, d->out_mode, d->act,
                res1, d->res1_c, d->res1_coff, d->scale1, res2, d->res2_c, d->res2_coff, d->scale2};
   for (const PackPart& pp : packs[0].parts) {
-    CSR_CUDA(launch_pack_weight(weight, base + pp.w_off, L.cout, L.cin, L.kh, L.kw, pp.co_lo, pp.npad, packs[0].cin_pad, s));
+    CSR_CUDA(launch_pack_weight(weight, base + pp.w_off, L.cout, L.cin, L.kh, L.kw, 0, pp.co_lo, pp.npad, packs[0].cin_pad, s));
     CSR_CUDA(launch_pack_bias(bias, reinterpret_cast<float*>(base + pp.b_off), L.cout, pp.co_lo, pp.npad, s));
     ConvLaunch cl;
     rc = build_conv(L, packs[0], pp, d->n, d->h, d->w, io, &cl);

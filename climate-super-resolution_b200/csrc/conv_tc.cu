@@ -1,20 +1,26 @@
 // KHxKW stride-1 "same" convolution over NHWC bf16 as an implicit GEMM on tcgen05 (sm_100a).
 //
-//   D[128 pixels][npad] (fp32, TMEM)  +=  A[128 pixels][16 ch] (smem, K-major, 128B swizzle)
-//                                       x  B[npad][16 ch]       (smem, K-major, 8x16B core matrices)
-//   summed over taps (dy,dx) and 16-channel k-steps.
+// Measured on B200 (profiles/r01_umma_probe.txt): in SS mode an M=128,K=16 bf16 MMA costs ~45-55 clk for any N <= 64
+// (the 4 KB A-operand read from shared memory is the floor), ~71 clk at N=128, ~135 at N=256.  A conv whose GEMM N is
+// only Cout = 16..64 therefore wastes most of each MMA.  This kernel folds the KW horizontal taps into N:
 //
-// Halo reuse: one TMA box per 64-channel k-block brings the (TH+KH-1) x SW pixel window of a tile into
-// shared memory ONCE (out-of-bounds pixels are zero-filled by TMA == the conv's zero padding).  A tile's 128
-// GEMM rows are the flattened window positions m = ty*SW + tx, so the A operand of tap (dy,dx) is the same
-// window read from byte offset (dy*SW+dx)*128: only the descriptor start address changes between taps.  The
-// last KW-1 columns of every window row are GEMM rows that wrap into the next row; they are computed and
-// discarded (TW = SW-(KW-1) real columns).
+//   D[128 window pixels][dx*npad + co] (fp32, TMEM) += A_dy[128 pixels][16 ch] x B_dy[KW*npad][16 ch]
 //
-// Roles: warp 0 = TMA producer, warp 1 = MMA issuer (one lane) + TMEM owner, warps 2..5 = epilogue
-// (TMEM -> registers -> bias/activation/residuals -> bf16/fp32 global stores).  Accumulators are double
-// buffered in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1; the layer's packed weights stay
-// resident in shared memory for the whole persistent CTA.
+// for every vertical tap dy and 16-channel k-step: KH (not KH*KW) MMAs per k-step, each KW times wider.  The epilogue
+// finishes the horizontal sum with warp shuffles:  out[m] = sum_dx D[m + dx - PW][dx*npad + co]  (GEMM rows m are
+// flattened window positions, one TMEM lane == one thread per row, neighbours in x are neighbour lanes).
+//
+// Halo reuse: one TMA box per 64-channel k-block brings the (TH+KH-1) x SW pixel window of a tile into shared memory
+// ONCE (out-of-bounds pixels are zero-filled by TMA == the conv's zero padding).  The A operand of vertical tap dy is
+// the same window read from byte offset dy*SW*128: only the descriptor start address changes between taps (UMMA
+// applies the 128B swizzle on absolute smem address bits, so any 128-byte-aligned start works - verified on HW).
+// Window columns 0..PW-1 and SW-PW..SW-1 only feed their neighbours: TW = SW-(KW-1) real outputs per row.
+//
+// Roles: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane) + TMEM owner, warps 2..9 = epilogue (two warps
+// per TMEM lane quadrant, splitting the 16-channel output chunks).  Accumulators are double buffered in TMEM so the
+// epilogue of tile i overlaps the MMAs of tile i+1; the layer's packed weights stay resident in shared memory for
+// the whole persistent CTA.  Programmatic dependent launch: everything before griddepcontrol.wait (barrier init, TMEM
+// alloc, weight/bias loads) overlaps the tail of the previous layer's kernel.
 //
 // Replaces one nn.Conv2d(+LeakyReLU/ReLU, *0.2+x, cat, nearest-x2) call site of the reference generator:
 // climsr/models/esrgan.py:33-38, 50-54, 90-100 and climsr/models/srcnn.py:14-16.
@@ -27,9 +33,9 @@ namespace csr {
 
 namespace {
 
-#define CSR_TRACE(role, tile_it, ev)                                                             \
-  do {                                                                                          \
-    if (p.trace && blockIdx.x == 0 && (tile_it) < 64) p.trace[((role) * 64 + (tile_it)) * 4 + (ev)] = clock64(); \
+#define CSR_TRACE(role, tile_it, ev)                                                                                  \
+  do {                                                                                                                \
+    if (p.trace && blockIdx.x == 0 && (tile_it) < 64) p.trace[((role) * 64 + (tile_it)) * 4 + (ev)] = clock64();      \
   } while (0)
 
 struct Tile {
@@ -80,47 +86,15 @@ __device__ __forceinline__ void store16_bf16(void* base, size_t pix, int C, int 
   dst[1] = b;
 }
 
-// Fully unrolled MMA issue for one k-block: every descriptor is (uniform base + compile-time immediate), so the
-// elected lane runs a straight line of UTCHMMA with no address arithmetic in between (the tcgen05 SS-mode floor is
-// ~45 clk per M=128,K=16 MMA; a rolled loop with runtime strides was issue-bound at ~85 clk).
-// Weight blocks of a k-block are stored [tap][ks] (see pack_weight_kernel).
-template <int KH, int KW, int SW, int NPAD, int KS>
-__device__ __forceinline__ void issue_kblock(uint32_t d_tmem, uint32_t a16, uint32_t b16, uint32_t a_hi, uint32_t b_hi, uint32_t idesc,
-                                             uint32_t acc0) {
+// acc[j] += value of raw[j] held by lane (lane + delta); delta == 0 -> own value.  Executed by all 32 lanes.
+__device__ __forceinline__ void gather_add16(float (&acc)[16], const uint32_t (&raw)[16], int delta, int lane) {
+  if (delta == 0) {
 #pragma unroll
-  for (int dy = 0; dy < KH; ++dy)
+    for (int j = 0; j < 16; ++j) acc[j] += __uint_as_float(raw[j]);
+  } else {
+    const int src = (lane + delta) & 31;
 #pragma unroll
-    for (int dx = 0; dx < KW; ++dx)
-#pragma unroll
-      for (int ks = 0; ks < KS; ++ks)
-        umma_bf16_split(d_tmem, a16 + (dy * SW + dx) * 8 + ks * 2, a_hi, b16 + ((dy * KW + dx) * KS + ks) * (NPAD * 2), b_hi, idesc,
-                        (dy | dx | ks) ? 1u : acc0);
-}
-
-template <int KH, int KW, int SW, int NPAD>
-__device__ __forceinline__ void issue_kblock_ks(int ks_here, uint32_t d_tmem, uint32_t a16, uint32_t b16, uint32_t a_hi, uint32_t b_hi,
-                                                uint32_t idesc, uint32_t acc0) {
-  switch (ks_here) {
-    case 1: issue_kblock<KH, KW, SW, NPAD, 1>(d_tmem, a16, b16, a_hi, b_hi, idesc, acc0); break;
-    case 2: issue_kblock<KH, KW, SW, NPAD, 2>(d_tmem, a16, b16, a_hi, b_hi, idesc, acc0); break;
-    case 3: issue_kblock<KH, KW, SW, NPAD, 3>(d_tmem, a16, b16, a_hi, b_hi, idesc, acc0); break;
-    default: issue_kblock<KH, KW, SW, NPAD, 4>(d_tmem, a16, b16, a_hi, b_hi, idesc, acc0); break;
-  }
-}
-
-// Generic (rolled) issue for shapes without an unrolled instantiation.
-__device__ __forceinline__ void issue_kblock_generic(const ConvParams& p, int ks_here, uint32_t d_tmem, uint32_t a16, uint32_t b16,
-                                                     uint32_t a_hi, uint32_t b_hi, uint32_t idesc, uint32_t acc0) {
-  const uint32_t b_step16 = static_cast<uint32_t>(p.npad * 32) >> 4;
-  const uint32_t row16 = static_cast<uint32_t>(p.SW) * 8u;
-  uint32_t acc = acc0;
-  for (int dy = 0; dy < p.KH; ++dy, a16 += row16) {
-    uint32_t a_lo = a16;
-    for (int dx = 0; dx < p.KW; ++dx, a_lo += 8)
-      for (int ks = 0; ks < ks_here; ++ks, b16 += b_step16) {
-        umma_bf16_split(d_tmem, a_lo + ks * 2, a_hi, b16, b_hi, idesc, acc);
-        acc = 1;
-      }
+    for (int j = 0; j < 16; ++j) acc[j] += __uint_as_float(__shfl_sync(0xffffffffu, raw[j], src));
   }
 }
 
@@ -150,6 +124,9 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
+  // Let the next layer's grid start its own prologue as early as the hardware allows (PDL).
+  griddep_launch_dependents();
+
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmap);
     mbar_init(bar_w, 1);
@@ -159,10 +136,17 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(bar_acc_full(b), 1);
-      mbar_init(bar_acc_empty(b), 128);
+      mbar_init(bar_acc_empty(b), kEpilogueThreads);
     }
     fence_mbar_init();
     fence_proxy_async_smem();
+    // layer weights (constant data, not produced by the previous kernel): resident for the whole CTA
+    mbar_arrive_expect_tx(bar_w, p.w_bytes);
+    const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.wpk);
+    for (int off = 0; off < p.w_bytes; off += 32768) {
+      const int nbytes = min(32768, p.w_bytes - off);
+      bulk_load(w_addr + off, wsrc + off, nbytes, bar_w);
+    }
   }
   if (warp == 1) {
     tmem_alloc(tmem_slot_addr, p.tmem_cols);
@@ -174,20 +158,14 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // Everything below reads / writes activations of the previous layer(s): wait for the prerequisite grid.
+  griddep_wait();
+
   const int ksteps_total = p.cin >> 4;
+  const int nmma = p.KW * p.npad;                        // UMMA N: horizontal taps folded into the output columns
 
   if (warp == 0) {
     // ===================== TMA producer (whole warp walks the loop, one elected lane issues) =====================
-    if (elect_one()) {
-      // layer weights: resident for the whole CTA
-      mbar_arrive_expect_tx(bar_w, p.w_bytes);
-      const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.wpk);
-      for (int off = 0; off < p.w_bytes; off += 32768) {
-        const int nbytes = min(32768, p.w_bytes - off);
-        bulk_load(w_addr + off, wsrc + off, nbytes, bar_w);
-      }
-    }
-    __syncwarp();
     int slot = 0, pit = 0;
     uint32_t phase = 0;
     for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++pit) {
@@ -207,13 +185,15 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    // All 32 lanes run the (warp-uniform) control flow so addresses live in uniform registers; one elected lane
-    // issues.  Per MMA only the descriptor start-address fields change: two 32-bit adds.
-    const uint32_t idesc = make_idesc_bf16(kTileM, p.npad);
+    // All 32 lanes run the warp-uniform control flow; one elected lane issues.  Per MMA only the 14-bit start-address
+    // fields of the two descriptors change.
+    const uint32_t idesc = make_idesc_bf16(kTileM, nmma);
+    const uint32_t b_step16 = static_cast<uint32_t>(nmma * 32) >> 4;          // one (dy,kstep) weight block in 16-byte units
+    const uint32_t kb_w16 = static_cast<uint32_t>(p.KH * 4) * b_step16;       // one full k-block of weights
+    const uint32_t row16 = static_cast<uint32_t>(p.SW) * 8u;                  // one window row (SW pixels x 128 B)
     const uint32_t a_hi = (1024u >> 4) | (1u << 14) | (2u << 29);             // SBO 1024 B, version 1, 128B swizzle
     const uint32_t b_hi = (256u >> 4) | (1u << 14);                           // SBO 256 B, version 1, no swizzle
     const uint32_t a_lbo = (16u >> 4) << 16, b_lbo = (128u >> 4) << 16;
-    const uint32_t kb_w16 = static_cast<uint32_t>(p.KH * p.KW * 4 * p.npad * 32) >> 4;   // weights of one full k-block, 16 B units
     mbar_wait(bar_w, 0);
     tc_fence_after();
     int slot = 0, it = 0;
@@ -224,27 +204,21 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
       mbar_wait(bar_acc_empty(buf), ((it >> 1) & 1) ^ 1);
       tc_fence_after();
       if (lane == 0) CSR_TRACE(1, it, 1);
-      const uint32_t d_tmem = tmem_base + buf * p.npad;
+      const uint32_t d_tmem = tmem_base + buf * nmma;
       for (int kb = 0; kb < p.n_kblocks; ++kb) {
         mbar_wait(bar_a_full(slot), phase);
         tc_fence_after();
         if (kb == 0 && lane == 0) CSR_TRACE(1, it, 2);
         const int ks_here = min(4, ksteps_total - kb * 4);
-        const uint32_t a16 = ((slots_addr + slot * p.slot_bytes) >> 4) | a_lbo;
-        const uint32_t b16 = ((w_addr >> 4) + static_cast<uint32_t>(kb) * kb_w16) | b_lbo;
-        const uint32_t acc0 = kb ? 1u : 0u;
+        uint32_t a16 = ((slots_addr + slot * p.slot_bytes) >> 4) | a_lbo;
+        uint32_t b16 = ((w_addr >> 4) + static_cast<uint32_t>(kb) * kb_w16) | b_lbo;
         if (elect_one()) {
-          switch (p.issue_code) {
-            case 1: issue_kblock_ks<3, 3, 16, 16>(ks_here, d_tmem, a16, b16, a_hi, b_hi, idesc, acc0); break;
-            case 2: issue_kblock_ks<3, 3, 16, 32>(ks_here, d_tmem, a16, b16, a_hi, b_hi, idesc, acc0); break;
-            case 3: issue_kblock_ks<3, 3, 16, 64>(ks_here, d_tmem, a16, b16, a_hi, b_hi, idesc, acc0); break;
-            case 4: issue_kblock_ks<3, 3, 32, 16>(ks_here, d_tmem, a16, b16, a_hi, b_hi, idesc, acc0); break;
-            case 5: issue_kblock_ks<3, 3, 32, 32>(ks_here, d_tmem, a16, b16, a_hi, b_hi, idesc, acc0); break;
-            case 6: issue_kblock_ks<3, 3, 32, 64>(ks_here, d_tmem, a16, b16, a_hi, b_hi, idesc, acc0); break;
-            case 7: issue_kblock<9, 9, 32, 64, 1>(d_tmem, a16, b16, a_hi, b_hi, idesc, acc0); break;
-            case 8: issue_kblock<5, 5, 32, 16, 2>(d_tmem, a16, b16, a_hi, b_hi, idesc, acc0); break;
-            case 9: issue_kblock<1, 1, 32, 32, 4>(d_tmem, a16, b16, a_hi, b_hi, idesc, acc0); break;
-            default: issue_kblock_generic(p, ks_here, d_tmem, a16, b16, a_hi, b_hi, idesc, acc0); break;
+          uint32_t acc = kb ? 1u : 0u;
+          for (int dy = 0; dy < p.KH; ++dy, a16 += row16) {
+            for (int ks = 0; ks < ks_here; ++ks, b16 += b_step16) {
+              umma_bf16_split(d_tmem, a16 + ks * 2, a_hi, b16, b_hi, idesc, acc);
+              acc = 1;
+            }
           }
           umma_commit(bar_a_empty(slot));                                  // window slot reusable once these MMAs have read it
           if (kb == p.n_kblocks - 1) umma_commit(bar_acc_full(buf));       // accumulator complete -> epilogue
@@ -255,34 +229,51 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5 -> TMEM lane groups 2,3,0,1) =====================
+    // ===================== epilogue: warps 2..9, TMEM lane quadrant = warp % 4, two warps per quadrant =====================
     const int lane_grp = warp & 3;
+    const int half = (warp - 2) >> 2;                    // 0/1: which alternate 16-channel chunks this warp handles
     const int m = lane_grp * 32 + lane;
     const int ty = m >> p.sw_shift;
-    const int tx = m & (p.SW - 1);
+    const int tx = m & (p.SW - 1);                       // window column
     const int n_chunks = p.npad >> 4;
     int it = 0;
     for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
       const Tile tl = decode_tile(p, t);
       const int buf = it & 1;
       const int y = tl.y0 + ty;
-      const int x = tl.x0 + tx;
-      const bool valid = (tx < p.TW) && (y < p.H) && (x < p.W);
+      const int x = tl.x0 - p.PW + tx;
+      const bool valid = (tx >= p.PW) && (tx < p.PW + p.TW) && (y < p.H) && (x < p.W);
       const size_t pix = (static_cast<size_t>(tl.n) * p.H + y) * p.W + x;
       if (threadIdx.x == 64) CSR_TRACE(2, it, 0);
       mbar_wait(bar_acc_full(buf), (it >> 1) & 1);
       tc_fence_after();
       if (threadIdx.x == 64) CSR_TRACE(2, it, 1);
-      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16) + buf * p.npad;
-      for (int c = 0; c < n_chunks; ++c) {
-        uint32_t raw[16];
-        tmem_ld16(t_addr + c * 16, raw);
-        tmem_ld_wait();
+      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16) + buf * nmma;
+      for (int c = half; c < n_chunks; c += 2) {
         const int ch0 = c * 16;
-        if (valid && ch0 < p.n_store) {
-          float v[16];
+        float v[16];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = apply_act(__uint_as_float(raw[i]) + bias_s[ch0 + i], p.act);
+        for (int i = 0; i < 16; ++i) v[i] = bias_s[ch0 + i];
+        if (p.KW == 3) {
+          uint32_t r0[16], r1[16], r2[16];
+          tmem_ld16(t_addr + ch0, r0);
+          tmem_ld16(t_addr + p.npad + ch0, r1);
+          tmem_ld16(t_addr + 2 * p.npad + ch0, r2);
+          tmem_ld_wait();
+          gather_add16(v, r0, -1, lane);
+          gather_add16(v, r1, 0, lane);
+          gather_add16(v, r2, 1, lane);
+        } else {
+          for (int dx = 0; dx < p.KW; ++dx) {
+            uint32_t r[16];
+            tmem_ld16(t_addr + dx * p.npad + ch0, r);
+            tmem_ld_wait();
+            gather_add16(v, r, dx - p.PW, lane);
+          }
+        }
+        if (valid && ch0 < p.n_store) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = apply_act(v[i], p.act);
           if (p.r1) add_residual16(v, p.r1, pix, p.r1_C, p.r1_coff + ch0, p.s1);
           if (p.r2) add_residual16(v, p.r2, pix, p.r2_C, p.r2_coff + ch0, p.s2);
           if (p.out_mode == 2) {
@@ -337,15 +328,23 @@ int launch_conv_tc(const ConvParams& p, const CUtensorMap& tmap, int num_sms, cu
   const size_t smem = 1024 /*alignment slack*/ + static_cast<size_t>(p.n_slots) * p.slot_bytes + ((p.w_bytes + 127) & ~127) +
                       1024 /*bias*/ + 8 * (5 + 2 * p.n_slots) + 16;
   if (smem > static_cast<size_t>(kSmemLimit)) return static_cast<int>(cudaErrorInvalidValue);
-  static size_t configured = 0;
-  if (smem > configured) {
+  static bool configured = false;
+  if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
     if (e != cudaSuccess) return static_cast<int>(e);
-    configured = kSmemLimit;
+    configured = true;
   }
-  const int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
-  conv_tc_kernel<<<grid, kConvThreads, smem, stream>>>(p, tmap);
-  return static_cast<int>(cudaGetLastError());
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(p.num_tiles < num_sms ? p.num_tiles : num_sms);
+  cfg.blockDim = dim3(kConvThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = p.use_pdl ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return static_cast<int>(cudaLaunchKernelEx(&cfg, conv_tc_kernel, p, tmap));
 }
 
 }  // namespace csr

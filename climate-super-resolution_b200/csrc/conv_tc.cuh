@@ -6,7 +6,8 @@
 
 namespace csr {
 
-constexpr int kConvThreads = 192;     // warp0 TMA producer, warp1 MMA issuer (+TMEM alloc), warps2-5 epilogue
+constexpr int kConvThreads = 320;     // warp0 TMA producer, warp1 MMA issuer (+TMEM alloc), warps2-9 epilogue
+constexpr int kEpilogueThreads = 256;
 constexpr int kTileM = 128;           // output pixels (UMMA M) per tile = TH * SW
 constexpr int kSmemLimit = 232448;    // 227 KB opt-in dynamic shared memory per CTA on sm_100
 
@@ -16,22 +17,22 @@ struct ConvParams {
   int KH, KW, PH, PW;
   int cin_off;     // first input channel inside the input buffer (multiple of 8)
   int cin;         // input channels used, padded to a multiple of 16 (k-steps = cin/16)
-  int npad;        // UMMA N: output channels padded to a multiple of 16
+  int npad;        // output channels of this launch padded to a multiple of 16; UMMA N = KW * npad (<= 256)
   int n_store;     // real output channels
   // tiling: a tile is TH rows x SW smem-pitch columns of which the first TW = SW-(KW-1) are real outputs
   int SW, sw_shift, TH, TW;
   int tiles_x, tiles_y, num_tiles;
   int win_rows;    // TH + KH - 1
   int win_bytes;   // win_rows * SW * 128  (== TMA box bytes per 64-channel k-block)
-  int slot_bytes;  // win_bytes + (KW-1)*128 rounded up to 1024
+  int slot_bytes;  // win_bytes rounded up to 1024
   int n_kblocks;   // ceil(cin / 64)
   int n_slots;     // activation-window ring depth
-  int w_bytes;     // packed weights: taps * (cin/16) * npad * 32
-  int tmem_cols;   // power of two >= max(32, 2*npad)
-  int issue_code;  // selects a fully unrolled MMA-issue instantiation (0 = generic rolled loop), see conv_tc.cu
+  int w_bytes;     // packed weights: KH * (cin/16) * KW * npad * 32
+  int tmem_cols;   // power of two >= max(32, 2*KW*npad)
+  int use_pdl;     // launch with programmatic stream serialization (prologue overlaps the previous kernel's tail)
   // epilogue
   const float* bias;   // [npad] fp32 (zero padded)
-  const void* wpk;     // packed bf16 weights (global), layout [kblock][tap][kstep in kblock][npad/8][2][8][8]
+  const void* wpk;     // packed bf16 weights (global), layout [kblock][dy][kstep in kblock][KW*npad/8][2][8][8]
   int act;             // 0 none, 1 leaky-relu 0.2, 2 relu
   float s1, s2;
   const void* r1; int r1_C, r1_coff;

@@ -5,40 +5,49 @@
 namespace csr {
 
 // ---- weights: fp32 OIHW -> bf16 UMMA B tiles ------------------------------------------------------------
-// Packed layout per layer: [kblock = 64 input channels][tap][kstep within the k-block][ngrp = npad/8][kchunk 2][row 8][elem 8];
-// one (tap,kstep) block is an npad x 16 K-major operand made of 8x16-byte core matrices (LBO 128 B between the two
-// k-chunks, SBO 256 B between 8-row groups).  The last k-block may hold fewer than 4 k-steps.  Rows >= cout and
-// channels >= cin are zero.
+// Packed layout per launch part: [kblock = 64 input channels][dy][kstep within the k-block] blocks; one block is the
+// B operand of one MMA: (KW*npad) x 16 K-major, rows ordered (dx, co) so the horizontal taps become output columns,
+// stored as 8x16-byte core matrices [row group][k-chunk 2][row 8][elem 8] (LBO 128 B, SBO 256 B).  The last k-block may
+// hold fewer than 4 k-steps.  Rows >= cout and channels >= cin are zero.
+// fold != 0: the layer is executed as a KH x 1 conv over an x-im2col input whose channel (dx*cin + c) holds input
+// channel c at horizontal offset dx - kw/2 (used for srcnn.conv1, 9x9 with 3 input channels -> 9x1 with 27).
 __global__ void pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ dst, int cout, int cin, int kh,
-                                   int kw, int co_lo, int npad, int cin_pad) {
+                                   int kw, int fold, int co_lo, int npad, int cin_pad) {
+  const int ekw = fold ? 1 : kw;
   const int ksteps = cin_pad >> 4;
-  const int taps = kh * kw;
   const int full_kb = ksteps >> 2, rem = ksteps & 3;
-  const long total = static_cast<long>(taps) * ksteps * npad * 16;
+  const int groups = (ekw * npad) >> 3;
+  const long total = static_cast<long>(kh) * ksteps * ekw * npad * 16;
   for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long>(gridDim.x) * blockDim.x) {
     const int e = i & 7;
     const int row = (i >> 3) & 7;
     const int kchunk = (i >> 6) & 1;
     long r = i >> 7;
-    const int ngrp = r % (npad >> 3);
-    int blk = static_cast<int>(r / (npad >> 3));          // block index in [kblock][tap][ks] order
-    int kb, tap, ks;
-    if (blk < full_kb * taps * 4) {
-      kb = blk / (taps * 4);
-      blk -= kb * taps * 4;
-      tap = blk >> 2;
+    const int grp = r % groups;
+    int blk = static_cast<int>(r / groups);               // block index in [kblock][dy][ks] order
+    int kb, dy, ks;
+    if (blk < full_kb * kh * 4) {
+      kb = blk / (kh * 4);
+      blk -= kb * kh * 4;
+      dy = blk >> 2;
       ks = blk & 3;
     } else {
-      blk -= full_kb * taps * 4;
+      blk -= full_kb * kh * 4;
       kb = full_kb;
-      tap = blk / rem;
-      ks = blk - tap * rem;
+      dy = blk / rem;
+      ks = blk - dy * rem;
     }
-    const int co = co_lo + ngrp * 8 + row;
-    const int ci = (kb * 4 + ks) * 16 + kchunk * 8 + e;
+    const int rr = grp * 8 + row;
+    int dx = rr / npad;
+    const int co = co_lo + (rr - dx * npad);
+    int ci = (kb * 4 + ks) * 16 + kchunk * 8 + e;
     float v = 0.f;
-    if (co < cout && ci < cin) {
-      const int dy = tap / kw, dx = tap % kw;
+    const int cin_eff = fold ? cin * kw : cin;
+    if (co < cout && ci < cin_eff) {
+      if (fold) {
+        dx = ci / cin;
+        ci -= dx * cin;
+      }
       v = w[((static_cast<long>(co) * cin + ci) * kh + dy) * kw + dx];
     }
     dst[i] = __float2bfloat16_rn(v);
@@ -72,19 +81,36 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, __nv_bfloat16
   }
 }
 
-// elev, mask fp32 (n,1,H,W) -> channels 1,2 of the SRCNN input buffer; channel 0 (conv_last's output, written later
-// by the conv epilogue) and 3..15 are zeroed.  torch.cat([out, elev, mask], 1), esrgan.py:100.
-__global__ void pack_aux_kernel(const float* __restrict__ elev, const float* __restrict__ mask, __nv_bfloat16* __restrict__ dst,
-                                long total_pix, int dst_c) {
+// SRCNN input as an x-im2col buffer: torch.cat([out, elev, mask], 1) (esrgan.py:100) followed by the horizontal half of
+// srcnn.conv1's 9x9 window.  For pixel (n,y,x) channel dx*3 + c (dx = 0..8, c = 0: conv_last output, 1: elev, 2: mask)
+// holds source c at (y, x+dx-4), zero outside the image (the conv's zero padding); channels 27..31 are zero.  The 9x9
+// conv over 3 channels then runs as a 9x1 conv over 27(32) channels: 18 instead of 81 MMAs per tile.
+__global__ void pack_srcnn_in_kernel(const float* __restrict__ t, const float* __restrict__ elev, const float* __restrict__ mask,
+                                     __nv_bfloat16* __restrict__ dst, int W, long total_pix, int dst_c) {
   for (long p = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; p < total_pix; p += static_cast<long>(gridDim.x) * blockDim.x) {
+    const int x = static_cast<int>(p % W);
+    float v[32];
+#pragma unroll
+    for (int dx = 0; dx < 9; ++dx) {
+      const int xs = x + dx - 4;
+      const bool in = xs >= 0 && xs < W;
+      const long q = p + dx - 4;
+      v[dx * 3 + 0] = in ? t[q] : 0.f;
+      v[dx * 3 + 1] = in ? elev[q] : 0.f;
+      v[dx * 3 + 2] = in ? mask[q] : 0.f;
+    }
+#pragma unroll
+    for (int i = 27; i < 32; ++i) v[i] = 0.f;
     uint4* o = reinterpret_cast<uint4*>(dst + p * dst_c);
-    uint4 a;
-    a.x = pack_bf16x2(0.f, elev[p]);
-    a.y = pack_bf16x2(mask[p], 0.f);
-    a.z = 0u;
-    a.w = 0u;
-    o[0] = a;
-    o[1] = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      uint4 a;
+      a.x = pack_bf16x2(v[8 * k + 0], v[8 * k + 1]);
+      a.y = pack_bf16x2(v[8 * k + 2], v[8 * k + 3]);
+      a.z = pack_bf16x2(v[8 * k + 4], v[8 * k + 5]);
+      a.w = pack_bf16x2(v[8 * k + 6], v[8 * k + 7]);
+      o[k] = a;
+    }
   }
 }
 
@@ -107,11 +133,11 @@ static inline int grid_for(long total, int block, int cap = 148 * 16) {
   return static_cast<int>(g);
 }
 
-cudaError_t launch_pack_weight(const float* w, void* dst, int cout, int cin, int kh, int kw, int co_lo, int npad, int cin_pad,
+cudaError_t launch_pack_weight(const float* w, void* dst, int cout, int cin, int kh, int kw, int fold, int co_lo, int npad, int cin_pad,
                                cudaStream_t s) {
-  const long total = static_cast<long>(kh) * kw * (cin_pad >> 4) * npad * 16;
-  pack_weight_kernel<<<grid_for(total, 256), 256, 0, s>>>(w, reinterpret_cast<__nv_bfloat16*>(dst), cout, cin, kh, kw, co_lo, npad,
-                                                          cin_pad);
+  const long total = static_cast<long>(kh) * (fold ? 1 : kw) * (cin_pad >> 4) * npad * 16;
+  pack_weight_kernel<<<grid_for(total, 256), 256, 0, s>>>(w, reinterpret_cast<__nv_bfloat16*>(dst), cout, cin, kh, kw, fold, co_lo,
+                                                          npad, cin_pad);
   return cudaGetLastError();
 }
 cudaError_t launch_pack_bias(const float* b, float* dst, int cout, int co_lo, int npad, cudaStream_t s) {
@@ -123,8 +149,10 @@ cudaError_t launch_nchw_to_nhwc(const float* src, void* dst, int n, int c, int h
   nchw_to_nhwc_kernel<<<grid_for(total, 256), 256, 0, s>>>(src, reinterpret_cast<__nv_bfloat16*>(dst), per, total, c, dst_c, zero_to);
   return cudaGetLastError();
 }
-cudaError_t launch_pack_aux(const float* elev, const float* mask, void* dst, long total_pix, int dst_c, cudaStream_t s) {
-  pack_aux_kernel<<<grid_for(total_pix, 256), 256, 0, s>>>(elev, mask, reinterpret_cast<__nv_bfloat16*>(dst), total_pix, dst_c);
+cudaError_t launch_pack_srcnn_in(const float* t, const float* elev, const float* mask, void* dst, int W, long total_pix, int dst_c,
+                                 cudaStream_t s) {
+  pack_srcnn_in_kernel<<<grid_for(total_pix, 256, 148 * 32), 256, 0, s>>>(t, elev, mask, reinterpret_cast<__nv_bfloat16*>(dst), W, total_pix,
+                                                                         dst_c);
   return cudaGetLastError();
 }
 cudaError_t launch_nhwc_to_nchw(const void* src, float* dst, int n, int c, int h, int w, int src_c, int src_coff, cudaStream_t s) {
