@@ -24,9 +24,11 @@ class NetDesc(C.Structure):
 
 class ConvDesc(C.Structure):
     _fields_ = [("n", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("cin", C.c_int32), ("cout", C.c_int32),
-                ("kh", C.c_int32), ("kw", C.c_int32), ("in_c", C.c_int32), ("out_c", C.c_int32), ("out_coff", C.c_int32),
-                ("act", C.c_int32), ("out_mode", C.c_int32), ("scale1", C.c_float), ("scale2", C.c_float),
-                ("res1_c", C.c_int32), ("res1_coff", C.c_int32), ("res2_c", C.c_int32), ("res2_coff", C.c_int32)]
+                ("kh", C.c_int32), ("kw", C.c_int32), ("in_c", C.c_int32), ("in_coff", C.c_int32), ("out_c", C.c_int32),
+                ("out_coff", C.c_int32), ("act", C.c_int32), ("out_mode", C.c_int32), ("in_up2", C.c_int32),
+                ("transposed", C.c_int32), ("scale1", C.c_float), ("scale2", C.c_float),
+                ("res1_c", C.c_int32), ("res1_coff", C.c_int32), ("res2_c", C.c_int32), ("res2_coff", C.c_int32),
+                ("gate_c", C.c_int32), ("gate_coff", C.c_int32), ("gate_from", C.c_int32), ("gate_neg", C.c_float)]
 
 
 def _load():
@@ -54,7 +56,7 @@ def _load():
         "csr_plan_destroy": (None, [vp]),
         "csr_generator_forward": (C.c_int, [nd, vp, vp, vp, vp, vp, vp, sz, i32, i32, i32, vp]),
         "csr_conv2d_scratch_bytes": (sz, [cd]),
-        "csr_conv2d_nhwc": (C.c_int, [cd, vp, vp, vp, vp, vp, vp, vp, sz, vp]),
+        "csr_conv2d_nhwc": (C.c_int, [cd, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]),
         "csr_nchw_f32_to_nhwc_bf16": (C.c_int, [vp, vp, i32, i32, i32, i32, i32, i32, vp]),
         "csr_nhwc_bf16_to_nchw_f32": (C.c_int, [vp, vp, i32, i32, i32, i32, i32, i32, vp]),
         "csr_metrics_scratch_bytes": (sz, [i32, i32, i32]),

@@ -10,7 +10,7 @@ from torch import Tensor
 from ._lib import ConvDesc, check, current_stream_ptr, lib
 
 ACT = {"none": 0, "lrelu": 1, "relu": 2}
-OUT_MODE = {"nhwc": 0, "nhwc_up2": 1, "f32_planar": 2}
+OUT_MODE = {"nhwc": 0, "f32_planar": 2, "f32_nhwc": 3}
 
 
 def nchw_to_nhwc_bf16(x: Tensor, dst_c: int = 64) -> Tensor:
@@ -31,31 +31,42 @@ def nhwc_bf16_to_nchw(x: Tensor, c: int, coff: int = 0) -> Tensor:
     return out
 
 
-def conv2d_nhwc(inp: Tensor, weight: Tensor, bias: Tensor, *, act: str = "none", out: Optional[Tensor] = None,
-                out_coff: int = 0, out_mode: str = "nhwc", res1: Optional[Tensor] = None, res1_coff: int = 0,
-                scale1: float = 1.0, res2: Optional[Tensor] = None, res2_coff: int = 0, scale2: float = 1.0) -> Tensor:
-    """One KxK stride-1 'same' conv on a bf16 NHWC buffer (channels-per-pixel multiple of 64) via csr_conv2d_nhwc.
+def conv2d_nhwc(inp: Tensor, weight: Tensor, bias: Optional[Tensor], *, act: str = "none", out: Optional[Tensor] = None,
+                out_coff: int = 0, out_mode: str = "nhwc", in_coff: int = 0, in_up2: bool = False, transposed: bool = False,
+                res1: Optional[Tensor] = None, res1_coff: int = 0, scale1: float = 1.0,
+                res2: Optional[Tensor] = None, res2_coff: int = 0, scale2: float = 1.0,
+                gate: Optional[Tensor] = None, gate_coff: int = 0, gate_from: int = 0, gate_neg: float = 0.2) -> Tensor:
+    """One KxK stride-1 'same' conv on a bf16 NHWC buffer via csr_conv2d_nhwc.
 
-    Reads input channels [0, cin); writes act(conv+bias) (then *scale1+res1, *scale2+res2) into channels
-    [out_coff, out_coff+cout) of `out` (allocated as a 64-channel-padded buffer when None).
+    Reads input channels [in_coff, in_coff+cin); writes act(conv+bias) (then *scale1+res1, *scale2+res2, lrelu-gate) into
+    channels [out_coff, out_coff+cout) of `out` (allocated as a 64-channel-padded buffer when None).  in_up2: the input
+    is nearest-x2 upsampled first (output is 2h x 2w).  transposed: `weight` is the forward layer's OIHW tensor and the
+    op computed is that layer's input gradient (cin/cout swap roles).
     """
     n, h, w, in_c = inp.shape
-    cout, cin, kh, kw = weight.shape
+    if transposed:
+        cin, cout, kh, kw = weight.shape
+    else:
+        cout, cin, kh, kw = weight.shape
     mode = OUT_MODE[out_mode]
+    s = 2 if in_up2 else 1
     if out is None:
         if mode == 2:
-            out = torch.empty((n, 1, h, w), dtype=torch.float32, device=inp.device)
+            out = torch.empty((n, 1, s * h, s * w), dtype=torch.float32, device=inp.device)
         else:
-            s = 2 if mode == 1 else 1
             oc = (out_coff + cout + 63) // 64 * 64
-            out = torch.zeros((n, s * h, s * w, oc), dtype=torch.bfloat16, device=inp.device)
+            out = torch.zeros((n, s * h, s * w, oc), dtype=torch.float32 if mode == 3 else torch.bfloat16, device=inp.device)
     out_c = 1 if mode == 2 else out.shape[-1]
-    d = ConvDesc(n, h, w, cin, cout, kh, kw, in_c, out_c, out_coff, ACT[act], mode, scale1, scale2,
-                 res1.shape[-1] if res1 is not None else 0, res1_coff, res2.shape[-1] if res2 is not None else 0, res2_coff)
+    d = ConvDesc(n, h, w, cin, cout, kh, kw, in_c, in_coff, out_c, out_coff, ACT[act], mode, int(in_up2), int(transposed),
+                 scale1, scale2, res1.shape[-1] if res1 is not None else 0, res1_coff,
+                 res2.shape[-1] if res2 is not None else 0, res2_coff,
+                 gate.shape[-1] if gate is not None else 0, gate_coff, gate_from, gate_neg)
     nbytes = lib.csr_conv2d_scratch_bytes(C.byref(d))
     scratch = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=inp.device)
-    wc, bc = weight.contiguous().float(), bias.contiguous().float()
-    check(lib.csr_conv2d_nhwc(C.byref(d), inp.data_ptr(), wc.data_ptr(), bc.data_ptr(), out.data_ptr(),
+    wc = weight.contiguous().float()
+    bc = bias.contiguous().float() if bias is not None else None
+    check(lib.csr_conv2d_nhwc(C.byref(d), inp.data_ptr(), wc.data_ptr(), bc.data_ptr() if bc is not None else None, out.data_ptr(),
                               res1.data_ptr() if res1 is not None else None, res2.data_ptr() if res2 is not None else None,
+                              gate.data_ptr() if gate is not None else None,
                               scratch.data_ptr(), nbytes, current_stream_ptr()), "csr_conv2d_nhwc")
     return out

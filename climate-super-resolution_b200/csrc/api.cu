@@ -22,6 +22,7 @@ static int g_opt_pdl = 1;
 static long long* g_trace = nullptr;
 static int g_opt_force_sw = 0;
 static int g_opt_max_slots = 8;
+static int g_opt_no_tma_store = 0;
 
 static int fail(int code, const char* fmt, ...) {
   va_list ap;
@@ -87,11 +88,34 @@ static int encode_act_map(CUtensorMap* m, const void* base, int N, int H, int W,
   return CSR_OK;
 }
 
+// Output view of one launch: conv-output pixel (y, x) of image n lives at buffer pixel (y*sy + oy, x*sx + ox) of an
+// (N, out_H, out_W, C) bf16 NHWC buffer (sy = sx = 1 for a plain conv; 2 with (oy, ox) = the sub-pixel phase of a
+// nearest-x2 + conv layer).  Box = n_store channels x TW x TH x 1; rows of 128 B are staged 128B-swizzled.
+static int encode_out_map(CUtensorMap* m, void* base, int N, int H, int W, int C, int out_H, int out_W, int sy, int sx, int oy, int ox,
+                          int box_c, int box_w, int box_h) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return fail(CSR_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  uint8_t* b = reinterpret_cast<uint8_t*>(base) + ((size_t)oy * out_W + ox) * C * 2;
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)sx * C * 2, (cuuint64_t)sy * out_W * C * 2, (cuuint64_t)out_H * out_W * C * 2};
+  cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, b, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  box_c * 2 == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(CSR_ERR_CUDA, "cuTensorMapEncodeTiled (output) failed (%d) for N%d H%d W%d C%d box %dx%dx%d", (int)r, N, H, W, C, box_c, box_w, box_h);
+  return CSR_OK;
+}
+
 // ------------------------------------------------------------------------------------------- layer table
 struct LayerSpec {
   std::string name;
   int cout, cin, kh, kw;   // reference (state_dict) shape
   int fold = 0;            // 1: executed as a kh x 1 conv over an x-im2col input with kw*cin channels (srcnn.conv1)
+  int up2 = 0;             // 1: the layer's input is nearest-x2 upsampled first (esrgan.py:94,97): executed as four
+                           //    sub-pixel phases, each a 2x2 conv over the low-resolution input with summed weights
+  int transposed = 0;      // 1: input-gradient conv: weight read as w[ci][co][KH-1-dy][KW-1-dx] (autograd of the layer)
   int ekw() const { return fold ? 1 : kw; }
   int ecin() const { return fold ? cin * kw : cin; }
 };
@@ -118,8 +142,8 @@ static std::vector<LayerSpec> layer_table(const CsrNetDesc& d) {
       v.push_back({pre + "5", d.nf, d.nf + 4 * d.gc, 3, 3});
     }
   v.push_back({"trunk_conv", d.nf, d.nf, 3, 3});
-  v.push_back({"upconv1", d.nf, d.nf, 3, 3});
-  v.push_back({"upconv2", d.nf, d.nf, 3, 3});
+  v.push_back({"upconv1", d.nf, d.nf, 3, 3, 0, 1});
+  v.push_back({"upconv2", d.nf, d.nf, 3, 3, 0, 1});
   v.push_back({"HRconv", d.nf, d.nf, 3, 3});
   v.push_back({"conv_last", d.out_channels, d.nf, 3, 3});
   v.push_back({"srcnn.conv1", 64, 3, 9, 9, 1});
@@ -128,9 +152,12 @@ static std::vector<LayerSpec> layer_table(const CsrNetDesc& d) {
   return v;
 }
 
-// Packed form of one layer: the output channels may be split so that one part's weights fit in shared memory.
-constexpr int kMaxResidentWeightBytes = 168 * 1024;
+// Packed form of one layer: one or four (sub-pixel phases) kernels, each possibly split over output channels so that
+// one part's weights fit in shared memory and its epilogue handles <= kMaxNpad channels.
+constexpr int kMaxResidentWeightBytes = 150 * 1024;
 struct PackPart {
+  int kh, kw, ph, pw;      // effective taps / padding of this launch
+  int phase;               // -1, or a*2+b: output pixel (2y+a, 2x+b)
   int co_lo, n_store, npad;
   size_t w_off, b_off;
   int w_bytes;
@@ -139,9 +166,9 @@ struct PackLayer {
   int cin_pad;
   std::vector<PackPart> parts;
 };
-static int part_weight_bytes(const LayerSpec& L, int npad) { return L.kh * L.ekw() * ((L.ecin() + 15) / 16 * 16) * npad * 2; }
+static int part_weight_bytes(int kh, int kw, int cin_pad, int npad) { return kh * kw * cin_pad * npad * 2; }
 // UMMA N = KW*npad <= 256 and two accumulator buffers of KW*npad fp32 columns must fit the 512 TMEM columns.
-static int max_npad(const LayerSpec& L) { return std::max(16, 256 / L.ekw() / 16 * 16); }
+static int max_npad(int kw) { return std::max(16, std::min(kMaxNpad, 256 / kw / 16 * 16)); }
 
 static std::vector<PackLayer> pack_layout(const std::vector<LayerSpec>& layers, size_t* total) {
   std::vector<PackLayer> out;
@@ -150,21 +177,28 @@ static std::vector<PackLayer> pack_layout(const std::vector<LayerSpec>& layers, 
     PackLayer pl;
     pl.cin_pad = (L.ecin() + 15) / 16 * 16;
     const int npad_full = (L.cout + 15) / 16 * 16;
+    const int kh = L.up2 ? 2 : L.kh, kw = L.up2 ? 2 : L.ekw();
     int nsplit = 1;
-    while ((part_weight_bytes(L, ceil_div(npad_full / 16, nsplit) * 16) > kMaxResidentWeightBytes ||
-            ceil_div(npad_full / 16, nsplit) * 16 > max_npad(L)) && nsplit < npad_full / 16) ++nsplit;
+    while ((part_weight_bytes(kh, kw, pl.cin_pad, ceil_div(npad_full / 16, nsplit) * 16) > kMaxResidentWeightBytes ||
+            ceil_div(npad_full / 16, nsplit) * 16 > max_npad(kw)) && nsplit < npad_full / 16) ++nsplit;
     const int per = ceil_div(npad_full / 16, nsplit) * 16;
-    for (int lo = 0; lo < npad_full; lo += per) {
-      PackPart pp;
-      pp.co_lo = lo;
-      pp.npad = std::min(per, npad_full - lo);
-      pp.n_store = std::min(L.cout - lo, pp.npad);
-      pp.w_bytes = part_weight_bytes(L, pp.npad);
-      pp.w_off = off;
-      off = align_up(off + pp.w_bytes, 128);
-      pp.b_off = off;
-      off = align_up(off + pp.npad * 4, 128);
-      pl.parts.push_back(pp);
+    for (int phase = L.up2 ? 0 : -1; phase < (L.up2 ? 4 : 0); ++phase) {
+      for (int lo = 0; lo < npad_full; lo += per) {
+        PackPart pp;
+        pp.kh = kh; pp.kw = kw;
+        pp.ph = L.up2 ? 1 - (phase >> 1) : L.kh / 2;
+        pp.pw = L.up2 ? 1 - (phase & 1) : L.ekw() / 2;
+        pp.phase = phase;
+        pp.co_lo = lo;
+        pp.npad = std::min(per, npad_full - lo);
+        pp.n_store = std::min(L.cout - lo, pp.npad);
+        pp.w_bytes = part_weight_bytes(kh, kw, pl.cin_pad, pp.npad);
+        pp.w_off = off;
+        off = align_up(off + pp.w_bytes, 128);
+        pp.b_off = off;
+        off = align_up(off + pp.npad * 4, 128);
+        pl.parts.push_back(pp);
+      }
     }
     out.push_back(pl);
   }
@@ -174,10 +208,9 @@ static std::vector<PackLayer> pack_layout(const std::vector<LayerSpec>& layers, 
 
 // ------------------------------------------------------------------------------------------- tiling
 struct Tiling {
-  int SW, TH, TW, win_rows, win_bytes, slot_bytes, n_slots;
+  int SW, TH, TW, win_rows, win_bytes, slot_bytes, n_slots, stage_bytes;
 };
-static int choose_tiling(int H, int W, int KH, int KW, int w_bytes, int n_kblocks, Tiling* out) {
-  const int fixed = 1024 + (int)align_up(w_bytes, 128) + 1024 + 512;
+static int choose_tiling(int H, int W, int KH, int KW, int w_bytes, int n_kblocks, int stage_row_bytes, Tiling* out) {
   double best = -1;
   for (int SW = 16; SW <= 128; SW *= 2) {
     if (g_opt_force_sw && SW != g_opt_force_sw) continue;
@@ -189,6 +222,8 @@ static int choose_tiling(int H, int W, int KH, int KW, int w_bytes, int n_kblock
     const int win_rows = TH + KH - 1;
     const int win_bytes = win_rows * SW * 128;
     const int slot_bytes = (int)align_up(win_bytes, 1024);
+    const int stage_bytes = stage_row_bytes ? (int)align_up((size_t)TH * TW * stage_row_bytes, 1024) : 0;
+    const int fixed = 1024 + (int)align_up(w_bytes, 128) + 256 + 512 + 2 * stage_bytes;
     const int slots = std::min(g_opt_max_slots, (kSmemLimit - fixed) / slot_bytes);
     if (slots < 1) continue;
     const double tiles = (double)ceil_div(H, TH) * ceil_div(W, TW);
@@ -197,47 +232,51 @@ static int choose_tiling(int H, int W, int KH, int KW, int w_bytes, int n_kblock
     eff -= 1e-4 * win_bytes / (double)(kTileM * 128);    // tie-break: less halo traffic
     if (eff > best) {
       best = eff;
-      *out = {SW, TH, TW, win_rows, win_bytes, slot_bytes, slots};
+      *out = {SW, TH, TW, win_rows, win_bytes, slot_bytes, slots, stage_bytes};
     }
   }
   if (best < 0) return fail(CSR_ERR_UNSUPPORTED, "no tile shape fits shared memory (weights %d bytes, %dx%d kernel)", w_bytes, KH, KW);
   return CSR_OK;
 }
 
-// One launch: parameters + its input tensor map.
+// One launch: parameters + its tensor maps.
 struct ConvLaunch {
   ConvParams p;
-  CUtensorMap tmap;
+  CUtensorMap tmap, tmap_out;
   size_t w_off = 0, b_off = 0;  // offsets into the packed blob (resolved at forward time)
-  bool keep_out = false;        // fp32-planar output that is NOT the caller's `out` tensor
+  bool final_out = false;       // fp32-planar output that IS the caller's `out` tensor
 };
 
+enum OutKind { kOutBf16 = 0, kOutF32Planar = 1, kOutF32Nhwc = 2 };
 struct ConvIO {
-  const void* in; int in_C, cin_off;
-  void* out; int out_C, out_coff, out_mode;
-  int act;
-  const void* r1; int r1_C, r1_coff; float s1;
-  const void* r2; int r2_C, r2_coff; float s2;
+  const void* in = nullptr; int in_C = 0, cin_off = 0;
+  void* out = nullptr; int out_C = 0, out_coff = 0; int out_kind = kOutBf16;
+  int act = CSR_ACT_NONE;
+  const void* r1 = nullptr; int r1_C = 0, r1_coff = 0; float s1 = 1.f;
+  const void* r2 = nullptr; int r2_C = 0, r2_coff = 0; float s2 = 1.f;
+  const void* gate = nullptr; int gate_C = 0, gate_coff = 0, gate_from = 0; float gate_neg = 0.2f;
 };
 
-static int build_conv(const LayerSpec& L, const PackLayer& pl, const PackPart& pp, int N, int H, int W, const ConvIO& io,
-                      ConvLaunch* cl) {
-  if (io.in_C % 64 != 0) return fail(CSR_ERR_BAD_ARG, "input buffer channels (%d) must be a multiple of 64", io.in_C);
-  if ((io.out_mode != CSR_OUT_F32_PLANAR) && ((io.out_C % 8) || (io.out_coff % 8))) return fail(CSR_ERR_BAD_ARG, "output channel stride/offset must be multiples of 8");
+// H, W: spatial size of the launch's input (for an up2 layer: the low-resolution input; its output is 2H x 2W).
+static int build_conv(const PackLayer& pl, const PackPart& pp, int N, int H, int W, const ConvIO& io, ConvLaunch* cl) {
+  if (io.in_C % 8 != 0 || io.cin_off % 8 != 0) return fail(CSR_ERR_BAD_ARG, "input buffer channels (%d) / offset (%d) must be multiples of 8", io.in_C, io.cin_off);
+  if (io.out_kind == kOutBf16 && ((io.out_C % 8) || (io.out_coff % 8))) return fail(CSR_ERR_BAD_ARG, "output channel stride/offset must be multiples of 8");
   ConvParams& p = cl->p;
   memset(&p, 0, sizeof(p));
   p.N = N; p.H = H; p.W = W;
-  p.KH = L.kh; p.KW = L.ekw(); p.PH = L.kh / 2; p.PW = L.ekw() / 2;
+  p.KH = pp.kh; p.KW = pp.kw; p.PH = pp.ph; p.PW = pp.pw;
   p.cin_off = io.cin_off;
   p.cin = pl.cin_pad;
-  if (io.cin_off + p.cin > io.in_C)
-    return fail(CSR_ERR_BAD_ARG, "conv reads channels [%d,%d) of a %d-channel buffer", io.cin_off, io.cin_off + p.cin, io.in_C);
   p.npad = pp.npad;
   p.n_store = pp.n_store;
   p.n_kblocks = ceil_div(p.cin, 64);
   p.w_bytes = pp.w_bytes;
+  const int up = pp.phase >= 0 ? 2 : 1;
+  const bool tma_out = io.out_kind == kOutBf16 && pp.n_store % 8 == 0 && !g_opt_no_tma_store;
+  p.store_mode = tma_out ? kStoreTma : io.out_kind == kOutBf16 ? kStoreDirect : io.out_kind == kOutF32Planar ? kStoreF32Planar : kStoreF32Nhwc;
+  p.stage_row_bytes = tma_out ? pp.n_store * 2 : 0;
   Tiling tl;
-  int rc = choose_tiling(H, W, L.kh, L.ekw(), p.w_bytes, p.n_kblocks, &tl);
+  int rc = choose_tiling(H, W, pp.kh, pp.kw, p.w_bytes, p.n_kblocks, p.stage_row_bytes, &tl);
   if (rc) return rc;
   p.SW = tl.SW; p.TH = tl.TH; p.TW = tl.TW;
   p.sw_shift = 0;
@@ -246,6 +285,7 @@ static int build_conv(const LayerSpec& L, const PackLayer& pl, const PackPart& p
   p.tiles_y = ceil_div(H, p.TH);
   p.num_tiles = p.tiles_x * p.tiles_y * N;
   p.win_rows = tl.win_rows; p.win_bytes = tl.win_bytes; p.slot_bytes = tl.slot_bytes; p.n_slots = tl.n_slots;
+  p.stage_bytes = tl.stage_bytes;
   int cols = 32;
   while (cols < 2 * p.KW * p.npad) cols *= 2;
   if (cols > 512 || p.KW * p.npad > 256) return fail(CSR_ERR_UNSUPPORTED, "KW*npad = %d exceeds the UMMA N / TMEM budget", p.KW * p.npad);
@@ -256,9 +296,24 @@ static int build_conv(const LayerSpec& L, const PackLayer& pl, const PackPart& p
   p.s1 = io.s1; p.s2 = io.s2;
   p.r1 = io.r1; p.r1_C = io.r1_C; p.r1_coff = io.r1_coff + pp.co_lo;
   p.r2 = io.r2; p.r2_C = io.r2_C; p.r2_coff = io.r2_coff + pp.co_lo;
-  p.out = io.out; p.out_C = io.out_C; p.out_coff = io.out_coff + pp.co_lo; p.out_mode = io.out_mode;
+  p.gate = io.gate; p.gate_C = io.gate_C; p.gate_coff = io.gate_coff + pp.co_lo; p.gate_from = io.gate_from - pp.co_lo; p.gate_neg = io.gate_neg;
+  if ((io.r1 || io.r2 || io.gate) && up != 1) return fail(CSR_ERR_UNSUPPORTED, "residual / gate operands are not supported on nearest-x2 layers");
+  p.out = io.out; p.out_C = io.out_C; p.out_coff = io.out_coff + pp.co_lo;
+  p.out_sy = p.out_sx = up;
+  p.out_oy = pp.phase >= 0 ? (pp.phase >> 1) : 0;
+  p.out_ox = pp.phase >= 0 ? (pp.phase & 1) : 0;
+  p.out_H = up * H; p.out_W = up * W;
   cl->w_off = pp.w_off; cl->b_off = pp.b_off;
-  return encode_act_map(&cl->tmap, io.in, N, H, W, io.in_C, p.SW, p.win_rows);
+  if (conv_smem_bytes(p) > (size_t)kSmemLimit) return fail(CSR_ERR_UNSUPPORTED, "conv needs %zu bytes of shared memory", conv_smem_bytes(p));
+  rc = encode_act_map(&cl->tmap, io.in, N, H, W, io.in_C, p.SW, p.win_rows);
+  if (rc) return rc;
+  if (tma_out) {
+    rc = encode_out_map(&cl->tmap_out, io.out, N, H, W, io.out_C, p.out_H, p.out_W, up, up, p.out_oy, p.out_ox, pp.n_store, p.TW, p.TH);
+    if (rc) return rc;
+  } else {
+    cl->tmap_out = cl->tmap;
+  }
+  return CSR_OK;
 }
 
 // ------------------------------------------------------------------------------------------- plan
@@ -277,7 +332,7 @@ struct CsrPlan {
 namespace csr {
 
 struct WsLayout {
-  size_t xin, fea0, cat[3], up1, up2, hrA, hrB, tlast, total;
+  size_t xin, fea0, cat[3], t0, m1, hrA, hrB, hrC, tlast, total;
   int ccat;
 };
 static WsLayout ws_layout(const CsrNetDesc& d, int N, int h, int w) {
@@ -289,10 +344,11 @@ static WsLayout ws_layout(const CsrNetDesc& d, int N, int h, int w) {
   L.xin = take(lr * 64 * 2);
   L.fea0 = take(lr * 64 * 2);
   for (int i = 0; i < 3; ++i) L.cat[i] = take(lr * L.ccat * 2);
-  L.up1 = take(mid * 64 * 2);
-  L.up2 = take(hr * 64 * 2);   // upconv2 input, later reused as the SRCNN input [out, elev, mask, 0...]
-  L.hrA = take(hr * 64 * 2);
-  L.hrB = take(hr * 64 * 2);
+  L.t0 = take(lr * 64 * 2);    // trunk_conv + skip
+  L.m1 = take(mid * 64 * 2);   // upconv1 output (2h x 2w)
+  L.hrA = take(hr * 64 * 2);   // upconv2 output, later srcnn.conv1 output
+  L.hrB = take(hr * 64 * 2);   // HRconv output, later srcnn.conv2 output
+  L.hrC = take(hr * 64 * 2);   // SRCNN input [out, elev, mask] x 9 horizontal taps
   L.tlast = take(hr * 4);      // conv_last output, fp32 planar
   L.total = off;
   return L;
@@ -305,32 +361,36 @@ static int plan_build(CsrPlan* P, void* ws) {
   uint8_t* base = reinterpret_cast<uint8_t*>(ws);
   void* xin = base + L.xin; void* fea0 = base + L.fea0;
   void* cat[3] = {base + L.cat[0], base + L.cat[1], base + L.cat[2]};
-  void* up1 = base + L.up1; void* up2 = base + L.up2; void* hrA = base + L.hrA; void* hrB = base + L.hrB;
-  P->xin = xin; P->sin = up2; P->tlast = reinterpret_cast<float*>(base + L.tlast);
+  void* t0 = base + L.t0; void* m1 = base + L.m1; void* hrA = base + L.hrA; void* hrB = base + L.hrB; void* hrC = base + L.hrC;
+  P->xin = xin; P->sin = hrC; P->tlast = reinterpret_cast<float*>(base + L.tlast);
   const std::vector<LayerSpec> layers = layer_table(d);
   size_t total = 0;
   const std::vector<PackLayer> packs = pack_layout(layers, &total);
   P->packed_bytes = total;
   const int C = L.ccat, nf = d.nf, gc = d.gc;
   int li = 0;
-  auto add = [&](int H, int W, ConvIO io, bool advance = true) -> int {
-    const LayerSpec& Ls = layers[li];
+  auto add = [&](int H, int W, const ConvIO& io, bool advance = true) -> int {
     const PackLayer& pl = packs[li];
     for (const PackPart& pp : pl.parts) {
       ConvLaunch cl;
-      int rc = build_conv(Ls, pl, pp, N, H, W, io, &cl);
+      int rc = build_conv(pl, pp, N, H, W, io, &cl);
       if (rc) return rc;
       P->convs.push_back(cl);
     }
     if (advance) ++li;
     return CSR_OK;
   };
+  auto io_of = [](const void* in, int in_C, void* out, int out_C, int out_coff, int act) {
+    ConvIO io;
+    io.in = in; io.in_C = in_C; io.out = out; io.out_C = out_C; io.out_coff = out_coff; io.act = act;
+    return io;
+  };
   int rc;
   // conv_first (esrgan.py:90) has two consumers: the first RRDB (reads x from concat buffer A) and the trunk skip-add
   // 33 layers later (A is overwritten by then).  The layer is tiny (K = 16), so it is simply run into both places.
-  rc = add(h, w, {xin, 64, 0, fea0, 64, 0, CSR_OUT_BF16_NHWC, CSR_ACT_NONE, nullptr, 0, 0, 1.f, nullptr, 0, 0, 1.f}, false);
+  rc = add(h, w, io_of(xin, 64, fea0, 64, 0, CSR_ACT_NONE), false);
   if (rc) return rc;
-  rc = add(h, w, {xin, 64, 0, cat[0], C, 0, CSR_OUT_BF16_NHWC, CSR_ACT_NONE, nullptr, 0, 0, 1.f, nullptr, 0, 0, 1.f});
+  rc = add(h, w, io_of(xin, 64, cat[0], C, 0, CSR_ACT_NONE));
   if (rc) return rc;
   for (int i = 0; i < d.nb; ++i) {
     // RRDB i: its input x lives in channels [0,nf) of concat buffer A; the three RDBs rotate A->B->C->A, so A's x
@@ -340,38 +400,51 @@ static int plan_build(CsrPlan* P, void* ws) {
       void* dst = cat[(r + 1) % 3];
       for (int k = 1; k <= 4; ++k) {
         // x_k = lrelu(conv_k(cat(x, x1..x_{k-1})))  written into its concat slice  (esrgan.py:33-36)
-        rc = add(h, w, {src, C, 0, src, C, nf + (k - 1) * gc, CSR_OUT_BF16_NHWC, CSR_ACT_LRELU02, nullptr, 0, 0, 1.f, nullptr, 0, 0, 1.f});
+        rc = add(h, w, io_of(src, C, src, C, nf + (k - 1) * gc, CSR_ACT_LRELU02));
         if (rc) return rc;
       }
       // x5*0.2 + x  (esrgan.py:37-38); RDB3 additionally applies the RRDB residual out*0.2 + x_rrdb (esrgan.py:54)
-      if (r < 2)
-        rc = add(h, w, {src, C, 0, dst, C, 0, CSR_OUT_BF16_NHWC, CSR_ACT_NONE, src, C, 0, 0.2f, nullptr, 0, 0, 1.f});
-      else
-        rc = add(h, w, {src, C, 0, cat[0], C, 0, CSR_OUT_BF16_NHWC, CSR_ACT_NONE, src, C, 0, 0.2f, cat[0], C, 0, 0.2f});
+      ConvIO io = io_of(src, C, r < 2 ? dst : cat[0], C, 0, CSR_ACT_NONE);
+      io.r1 = src; io.r1_C = C; io.s1 = 0.2f;
+      if (r == 2) { io.r2 = cat[0]; io.r2_C = C; io.s2 = 0.2f; }
+      rc = add(h, w, io);
       if (rc) return rc;
     }
   }
-  // trunk_conv + skip (esrgan.py:91-92), stored nearest-x2 upsampled (esrgan.py:94)
-  rc = add(h, w, {cat[0], C, 0, up1, 64, 0, CSR_OUT_BF16_NHWC_UP2, CSR_ACT_NONE, fea0, 64, 0, 1.f, nullptr, 0, 0, 1.f});
+  // trunk_conv + skip (esrgan.py:91-92)
+  {
+    ConvIO io = io_of(cat[0], C, t0, 64, 0, CSR_ACT_NONE);
+    io.r1 = fea0; io.r1_C = 64; io.s1 = 1.f;
+    rc = add(h, w, io);
+    if (rc) return rc;
+  }
+  // lrelu(upconv1(nearest x2)) and lrelu(upconv2(nearest x2)) (esrgan.py:94,97): four sub-pixel phases each
+  rc = add(h, w, io_of(t0, 64, m1, 64, 0, CSR_ACT_LRELU02));
   if (rc) return rc;
-  // upconv1 + lrelu, stored nearest-x2 upsampled (esrgan.py:94,97)
-  rc = add(2 * h, 2 * w, {up1, 64, 0, up2, 64, 0, CSR_OUT_BF16_NHWC_UP2, CSR_ACT_LRELU02, nullptr, 0, 0, 1.f, nullptr, 0, 0, 1.f});
+  rc = add(2 * h, 2 * w, io_of(m1, 64, hrA, 64, 0, CSR_ACT_LRELU02));
   if (rc) return rc;
   const int H = 4 * h, W = 4 * w;
-  rc = add(H, W, {up2, 64, 0, hrA, 64, 0, CSR_OUT_BF16_NHWC, CSR_ACT_LRELU02, nullptr, 0, 0, 1.f, nullptr, 0, 0, 1.f});  // upconv2
+  rc = add(H, W, io_of(hrA, 64, hrB, 64, 0, CSR_ACT_LRELU02));  // HRconv (esrgan.py:99)
   if (rc) return rc;
-  rc = add(H, W, {hrA, 64, 0, hrB, 64, 0, CSR_OUT_BF16_NHWC, CSR_ACT_LRELU02, nullptr, 0, 0, 1.f, nullptr, 0, 0, 1.f});  // HRconv (esrgan.py:99)
-  if (rc) return rc;
-  // conv_last -> fp32 planar temp; then [out, elev, mask] is packed (with srcnn.conv1's horizontal window) into `up2`
-  rc = add(H, W, {hrB, 64, 0, P->tlast, 1, 0, CSR_OUT_F32_PLANAR, CSR_ACT_NONE, nullptr, 0, 0, 1.f, nullptr, 0, 0, 1.f});
-  if (rc) return rc;
-  P->convs.back().keep_out = true;
+  // conv_last -> fp32 planar temp; then [out, elev, mask] is packed (with srcnn.conv1's horizontal window) into hrC
+  {
+    ConvIO io = io_of(hrB, 64, P->tlast, 1, 0, CSR_ACT_NONE);
+    io.out_kind = kOutF32Planar;
+    rc = add(H, W, io);
+    if (rc) return rc;
+  }
   P->idx_srcnn1 = (int)P->convs.size();
-  rc = add(H, W, {up2, 64, 0, hrA, 64, 0, CSR_OUT_BF16_NHWC, CSR_ACT_RELU, nullptr, 0, 0, 1.f, nullptr, 0, 0, 1.f});     // srcnn.conv1 (9x1 folded)
+  rc = add(H, W, io_of(hrC, 64, hrA, 64, 0, CSR_ACT_RELU));     // srcnn.conv1 (9x1 folded)
   if (rc) return rc;
-  rc = add(H, W, {hrA, 64, 0, hrB, 64, 0, CSR_OUT_BF16_NHWC, CSR_ACT_RELU, nullptr, 0, 0, 1.f, nullptr, 0, 0, 1.f});     // srcnn.conv2 1x1
+  rc = add(H, W, io_of(hrA, 64, hrB, 64, 0, CSR_ACT_RELU));     // srcnn.conv2 1x1
   if (rc) return rc;
-  rc = add(H, W, {hrB, 64, 0, nullptr, 1, 0, CSR_OUT_F32_PLANAR, CSR_ACT_NONE, nullptr, 0, 0, 1.f, nullptr, 0, 0, 1.f}); // srcnn.conv3 5x5
+  {
+    ConvIO io = io_of(hrB, 64, nullptr, 1, 0, CSR_ACT_NONE);    // srcnn.conv3 5x5 -> the caller's output tensor
+    io.out_kind = kOutF32Planar;
+    rc = add(H, W, io);
+    if (rc) return rc;
+    P->convs.back().final_out = true;
+  }
   return rc;
 }
 
@@ -398,6 +471,7 @@ int csr_set_option(int32_t key, int32_t value) {
     case 1: g_opt_pdl = value ? 1 : 0; return CSR_OK;      // programmatic dependent launch on/off
     case 2: g_opt_force_sw = value; return CSR_OK;
     case 3: g_opt_max_slots = value < 1 ? 1 : value; return CSR_OK;
+    case 4: g_opt_no_tma_store = value ? 1 : 0; return CSR_OK;   // debug: per-element global stores instead of TMA
     default: return fail(CSR_ERR_BAD_ARG, "unknown option key %d", key);
   }
 }
@@ -447,7 +521,7 @@ int csr_pack_weights(const CsrNetDesc* net, const float* const* w, const float* 
     if (!w[i] || !b[i]) return fail(CSR_ERR_BAD_ARG, "null weight/bias pointer for layer %zu", i);
     for (const PackPart& pp : packs[i].parts) {
       CSR_CUDA(launch_pack_weight(w[i], base + pp.w_off, layers[i].cout, layers[i].cin, layers[i].kh, layers[i].kw, layers[i].fold,
-                                  pp.co_lo, pp.npad, packs[i].cin_pad, s));
+                                  pp.phase, 0, pp.co_lo, pp.npad, packs[i].cin_pad, s));
       CSR_CUDA(launch_pack_bias(b[i], reinterpret_cast<float*>(base + pp.b_off), layers[i].cout, pp.co_lo, pp.npad, s));
       g_launches += 2;
     }
@@ -497,8 +571,8 @@ int csr_plan_forward(CsrPlan* P, const void* packed, const float* x, const float
     ConvLaunch& cl = P->convs[i];
     cl.p.wpk = pk + cl.w_off;
     cl.p.bias = reinterpret_cast<const float*>(pk + cl.b_off);
-    if (cl.p.out_mode == CSR_OUT_F32_PLANAR && !cl.keep_out) cl.p.out = out;
-    int e = launch_conv_tc(cl.p, cl.tmap, P->sms, s);
+    if (cl.final_out) cl.p.out = out;
+    int e = launch_conv_tc(cl.p, cl.tmap, cl.tmap_out, P->sms, s);
     if (e) return fail(CSR_ERR_CUDA, "conv launch %zu failed: %s", i, cudaGetErrorString((cudaError_t)e));
     ++g_launches;
   }
@@ -521,8 +595,12 @@ static int conv_desc_to_layer(const CsrConvDesc* d, LayerSpec* L) {
   if (d->n < 1 || d->h < 1 || d->w < 1 || d->cin < 1 || d->cout < 1) return fail(CSR_ERR_BAD_ARG, "non-positive conv shape");
   if (!(d->kh & 1) || !(d->kw & 1) || d->kh > 9 || d->kw > 9) return fail(CSR_ERR_UNSUPPORTED, "kernel %dx%d (odd, <= 9 supported)", d->kh, d->kw);
   if (d->cout > 256) return fail(CSR_ERR_UNSUPPORTED, "cout %d > 256", d->cout);
+  if (d->out_mode != CSR_OUT_BF16_NHWC && d->out_mode != CSR_OUT_F32_PLANAR && d->out_mode != CSR_OUT_F32_NHWC)
+    return fail(CSR_ERR_BAD_ARG, "unknown out_mode %d", d->out_mode);
   if (d->out_mode == CSR_OUT_F32_PLANAR && d->cout != 1) return fail(CSR_ERR_UNSUPPORTED, "fp32 planar output needs cout == 1");
-  *L = {"conv", d->cout, d->cin, d->kh, d->kw, 0};
+  if (d->in_up2 && (d->kh != 3 || d->kw != 3)) return fail(CSR_ERR_UNSUPPORTED, "nearest-x2 input needs a 3x3 kernel");
+  if (d->in_up2 && d->transposed) return fail(CSR_ERR_UNSUPPORTED, "in_up2 and transposed cannot be combined");
+  *L = {"conv", d->cout, d->cin, d->kh, d->kw, 0, d->in_up2 ? 1 : 0, d->transposed ? 1 : 0};
   return CSR_OK;
 }
 
@@ -535,11 +613,11 @@ size_t csr_conv2d_scratch_bytes(const CsrConvDesc* d) {
 }
 
 int csr_conv2d_nhwc(const CsrConvDesc* d, const void* in, const float* weight, const float* bias, void* out, const void* res1,
-                    const void* res2, void* scratch, size_t scratch_bytes, void* stream) {
+                    const void* res2, const void* gate, void* scratch, size_t scratch_bytes, void* stream) {
   LayerSpec L;
   int rc = conv_desc_to_layer(d, &L);
   if (rc) return rc;
-  if (!in || !weight || !bias || !out || !scratch) return fail(CSR_ERR_BAD_ARG, "null pointer");
+  if (!in || !weight || !out || !scratch) return fail(CSR_ERR_BAD_ARG, "null pointer");
   DeviceInfo di;
   rc = device_info(&di);
   if (rc) return rc;
@@ -548,17 +626,24 @@ int csr_conv2d_nhwc(const CsrConvDesc* d, const void* in, const float* weight, c
   if (scratch_bytes < total) return fail(CSR_ERR_WORKSPACE, "scratch %zu < %zu bytes", scratch_bytes, total);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   uint8_t* base = reinterpret_cast<uint8_t*>(scratch);
-  ConvIO io = {in, d->in_c, 0, out, d->out_c, d->out_coff, d->out_mode, d->act,
-               res1, d->res1_c, d->res1_coff, d->scale1, res2, d->res2_c, d->res2_coff, d->scale2};
+  ConvIO io;
+  io.in = in; io.in_C = d->in_c; io.cin_off = d->in_coff;
+  io.out = out; io.out_C = d->out_c; io.out_coff = d->out_coff;
+  io.out_kind = d->out_mode == CSR_OUT_BF16_NHWC ? kOutBf16 : d->out_mode == CSR_OUT_F32_PLANAR ? kOutF32Planar : kOutF32Nhwc;
+  io.act = d->act;
+  io.r1 = res1; io.r1_C = d->res1_c; io.r1_coff = d->res1_coff; io.s1 = d->scale1;
+  io.r2 = res2; io.r2_C = d->res2_c; io.r2_coff = d->res2_coff; io.s2 = d->scale2;
+  io.gate = gate; io.gate_C = d->gate_c; io.gate_coff = d->gate_coff; io.gate_from = d->gate_from; io.gate_neg = d->gate_neg;
   for (const PackPart& pp : packs[0].parts) {
-    CSR_CUDA(launch_pack_weight(weight, base + pp.w_off, L.cout, L.cin, L.kh, L.kw, 0, pp.co_lo, pp.npad, packs[0].cin_pad, s));
-    CSR_CUDA(launch_pack_bias(bias, reinterpret_cast<float*>(base + pp.b_off), L.cout, pp.co_lo, pp.npad, s));
+    CSR_CUDA(launch_pack_weight(weight, base + pp.w_off, L.cout, L.cin, L.kh, L.kw, 0, pp.phase, L.transposed, pp.co_lo, pp.npad,
+                                packs[0].cin_pad, s));
+    CSR_CUDA(launch_pack_bias(bias, reinterpret_cast<float*>(base + pp.b_off), bias ? L.cout : 0, pp.co_lo, pp.npad, s));
     ConvLaunch cl;
-    rc = build_conv(L, packs[0], pp, d->n, d->h, d->w, io, &cl);
+    rc = build_conv(packs[0], pp, d->n, d->h, d->w, io, &cl);
     if (rc) return rc;
     cl.p.wpk = base + pp.w_off;
     cl.p.bias = reinterpret_cast<const float*>(base + pp.b_off);
-    int e = launch_conv_tc(cl.p, cl.tmap, di.sms, s);
+    int e = launch_conv_tc(cl.p, cl.tmap, cl.tmap_out, di.sms, s);
     if (e) return fail(CSR_ERR_CUDA, "conv launch failed: %s", cudaGetErrorString((cudaError_t)e));
     g_launches += 3;
   }

@@ -6,20 +6,30 @@
 
 namespace csr {
 
-constexpr int kConvThreads = 320;     // warp0 TMA producer, warp1 MMA issuer (+TMEM alloc), warps2-9 epilogue
-constexpr int kEpilogueThreads = 256;
-constexpr int kTileM = 128;           // output pixels (UMMA M) per tile = TH * SW
+constexpr int kEpilogueWarps = 16;    // four warps per TMEM lane quadrant, each owning every 4th 8-channel chunk
+constexpr int kEpilogueThreads = kEpilogueWarps * 32;
+constexpr int kConvThreads = 64 + kEpilogueThreads;   // warp0 TMA producer, warp1 MMA issuer (+TMEM alloc), then epilogue
+constexpr int kTileM = 128;           // window positions (UMMA M) per tile = TH * SW
 constexpr int kSmemLimit = 232448;    // 227 KB opt-in dynamic shared memory per CTA on sm_100
+constexpr int kMaxNpad = 64;          // output channels per launch part (epilogue: <= 2 chunks of 8 per warp)
+
+enum StoreMode {
+  kStoreTma = 0,        // bf16 NHWC through a swizzled shared-memory staging tile + cp.async.bulk.tensor store
+  kStoreDirect = 1,     // bf16 NHWC, per-element global stores (ragged channel counts)
+  kStoreF32Planar = 2,  // fp32 (N,1,H,W), channel 0 only
+  kStoreF32Nhwc = 3     // fp32 NHWC (n_store channels per pixel, pitch out_C): gradient / debug outputs
+};
 
 struct ConvParams {
-  // geometry (input spatial == conv output spatial; stride 1, "same" padding)
+  // geometry (input spatial == conv output spatial; stride 1).  Output pixel (y,x) = sum over taps (dy,dx) of
+  // input pixel (y + dy - PH, x + dx - PW); PH/PW need not be (K-1)/2 (sub-pixel phases of nearest-x2 + conv).
   int N, H, W;
   int KH, KW, PH, PW;
   int cin_off;     // first input channel inside the input buffer (multiple of 8)
   int cin;         // input channels used, padded to a multiple of 16 (k-steps = cin/16)
-  int npad;        // output channels of this launch padded to a multiple of 16; UMMA N = KW * npad (<= 256)
+  int npad;        // output channels of this launch padded to a multiple of 16 (<= kMaxNpad); UMMA N = KW * npad
   int n_store;     // real output channels
-  // tiling: a tile is TH rows x SW smem-pitch columns of which the first TW = SW-(KW-1) are real outputs
+  // tiling: a tile is TH rows x SW window columns of which TW = SW-(KW-1) are real outputs (columns [PW, PW+TW))
   int SW, sw_shift, TH, TW;
   int tiles_x, tiles_y, num_tiles;
   int win_rows;    // TH + KH - 1
@@ -30,18 +40,28 @@ struct ConvParams {
   int w_bytes;     // packed weights: KH * (cin/16) * KW * npad * 32
   int tmem_cols;   // power of two >= max(32, 2*KW*npad)
   int use_pdl;     // launch with programmatic stream serialization (prologue overlaps the previous kernel's tail)
-  // epilogue
+  // epilogue:  v = act(acc + bias);  if r1: v = v*s1 + r1;  if r2: v = v*s2 + r2;  if gate: v *= (gate > 0 ? 1 : gate_neg)
   const float* bias;   // [npad] fp32 (zero padded)
   const void* wpk;     // packed bf16 weights (global), layout [kblock][dy][kstep in kblock][KW*npad/8][2][8][8]
   int act;             // 0 none, 1 leaky-relu 0.2, 2 relu
   float s1, s2;
   const void* r1; int r1_C, r1_coff;
   const void* r2; int r2_C, r2_coff;
-  void* out; int out_C, out_coff; int out_mode;   // CsrOutMode
-  long long* trace;   // debug: per-role clock64 timestamps of CTA 0 (nullptr = off), [3 roles][64 tiles][4 events]
+  const void* gate; int gate_C, gate_coff; int gate_from; float gate_neg;   // applied to output channels >= gate_from
+  void* out; int out_C, out_coff;
+  int store_mode;      // StoreMode
+  int out_sy, out_sx, out_oy, out_ox;   // direct modes: output pixel (y,x) lives at (y*out_sy+out_oy, x*out_sx+out_ox)
+  int out_H, out_W;                     // spatial size of the output buffer (direct modes)
+  int stage_row_bytes; // kStoreTma: bytes per staged pixel (n_store * 2: 16..128)
+  int stage_bytes;     // one staging buffer (TH*TW*stage_row_bytes rounded up to 1024)
+  long long* trace;    // debug: per-role clock64 timestamps of CTA 0 (nullptr = off), [3 roles][64 tiles][4 events]
 };
 
-// Returns cudaError_t (as int). tmap: 4-D (C, W, H, N) bf16 tensor map with box (64, SW, win_rows, 1), SWIZZLE_128B.
-int launch_conv_tc(const ConvParams& p, const CUtensorMap& tmap, int num_sms, cudaStream_t stream);
+// Returns cudaError_t (as int).
+//   tmap_in : 4-D (C, W, H, N) bf16 map, box (64, SW, win_rows, 1), SWIZZLE_128B, zero OOB fill (= the conv padding)
+//   tmap_out: 4-D (C, W, H, N) bf16 map (possibly strided: one sub-pixel phase), box (n_store, TW, TH, 1); ignored
+//             unless store_mode == kStoreTma
+size_t conv_smem_bytes(const ConvParams& p);
+int launch_conv_tc(const ConvParams& p, const CUtensorMap& tmap_in, const CUtensorMap& tmap_out, int num_sms, cudaStream_t stream);
 
 }  // namespace csr

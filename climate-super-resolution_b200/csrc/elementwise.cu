@@ -8,16 +8,29 @@ namespace csr {
 // Packed layout per launch part: [kblock = 64 input channels][dy][kstep within the k-block] blocks; one block is the
 // B operand of one MMA: (KW*npad) x 16 K-major, rows ordered (dx, co) so the horizontal taps become output columns,
 // stored as 8x16-byte core matrices [row group][k-chunk 2][row 8][elem 8] (LBO 128 B, SBO 256 B).  The last k-block may
-// hold fewer than 4 k-steps.  Rows >= cout and channels >= cin are zero.
-// fold != 0: the layer is executed as a KH x 1 conv over an x-im2col input whose channel (dx*cin + c) holds input
-// channel c at horizontal offset dx - kw/2 (used for srcnn.conv1, 9x9 with 3 input channels -> 9x1 with 27).
+// hold fewer than 4 k-steps.  Rows >= cout and channels >= cin are zero.  (cout, cin, kh, kw) describe the conv being
+// EXECUTED; the source tensor is:
+//   plain      : w[co][ci][dy][dx]                                   (the layer's OIHW weight)
+//   fold != 0  : the layer is executed as a KH x 1 conv over an x-im2col input whose channel (dx*cin_src + c) holds
+//                input channel c at horizontal offset dx - kw_src/2 (srcnn.conv1, 9x9 with 3 channels -> 9x1 with 27)
+//   phase >= 0 : sub-pixel phase (a,b) = (phase>>1, phase&1) of "nearest-x2 upsample then 3x3 conv" (esrgan.py:94,97):
+//                a 2x2 conv over the low-resolution input whose tap (ry, rx) is the SUM of the 3x3 taps that land on
+//                the same source pixel: a=0: ry0<-{0}, ry1<-{1,2};  a=1: ry0<-{0,1}, ry1<-{2}  (same in x)
+//   transposed : input-gradient conv of the layer: w_src[ci][co][KH-1-dy][KW-1-dx] with w_src of shape (cin, cout, kh, kw)
+__device__ __forceinline__ void phase_taps(int a, int r, int* lo, int* hi) {
+  if (a == 0) { *lo = r == 0 ? 0 : 1; *hi = r == 0 ? 0 : 2; }
+  else        { *lo = r == 0 ? 0 : 2; *hi = r == 0 ? 1 : 2; }
+}
+
 __global__ void pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ dst, int cout, int cin, int kh,
-                                   int kw, int fold, int co_lo, int npad, int cin_pad) {
-  const int ekw = fold ? 1 : kw;
+                                   int kw, int fold, int phase, int transposed, int co_lo, int npad, int cin_pad) {
+  // executed taps
+  const int ekh = phase >= 0 ? 2 : kh;
+  const int ekw = phase >= 0 ? 2 : (fold ? 1 : kw);
   const int ksteps = cin_pad >> 4;
   const int full_kb = ksteps >> 2, rem = ksteps & 3;
   const int groups = (ekw * npad) >> 3;
-  const long total = static_cast<long>(kh) * ksteps * ekw * npad * 16;
+  const long total = static_cast<long>(ekh) * ksteps * ekw * npad * 16;
   for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long>(gridDim.x) * blockDim.x) {
     const int e = i & 7;
     const int row = (i >> 3) & 7;
@@ -26,13 +39,13 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* _
     const int grp = r % groups;
     int blk = static_cast<int>(r / groups);               // block index in [kblock][dy][ks] order
     int kb, dy, ks;
-    if (blk < full_kb * kh * 4) {
-      kb = blk / (kh * 4);
-      blk -= kb * kh * 4;
+    if (blk < full_kb * ekh * 4) {
+      kb = blk / (ekh * 4);
+      blk -= kb * ekh * 4;
       dy = blk >> 2;
       ks = blk & 3;
     } else {
-      blk -= full_kb * kh * 4;
+      blk -= full_kb * ekh * 4;
       kb = full_kb;
       dy = blk / rem;
       ks = blk - dy * rem;
@@ -48,7 +61,17 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* _
         dx = ci / cin;
         ci -= dx * cin;
       }
-      v = w[((static_cast<long>(co) * cin + ci) * kh + dy) * kw + dx];
+      if (phase >= 0) {
+        int y0, y1, x0, x1;
+        phase_taps(phase >> 1, dy, &y0, &y1);
+        phase_taps(phase & 1, dx, &x0, &x1);
+        for (int yy = y0; yy <= y1; ++yy)
+          for (int xx = x0; xx <= x1; ++xx) v += w[((static_cast<long>(co) * cin + ci) * kh + yy) * kw + xx];
+      } else if (transposed) {
+        v = w[((static_cast<long>(ci) * cout + co) * kh + (kh - 1 - dy)) * kw + (kw - 1 - dx)];
+      } else {
+        v = w[((static_cast<long>(co) * cin + ci) * kh + dy) * kw + dx];
+      }
     }
     dst[i] = __float2bfloat16_rn(v);
   }
@@ -133,11 +156,12 @@ static inline int grid_for(long total, int block, int cap = 148 * 16) {
   return static_cast<int>(g);
 }
 
-cudaError_t launch_pack_weight(const float* w, void* dst, int cout, int cin, int kh, int kw, int fold, int co_lo, int npad, int cin_pad,
-                               cudaStream_t s) {
-  const long total = static_cast<long>(kh) * (fold ? 1 : kw) * (cin_pad >> 4) * npad * 16;
-  pack_weight_kernel<<<grid_for(total, 256), 256, 0, s>>>(w, reinterpret_cast<__nv_bfloat16*>(dst), cout, cin, kh, kw, fold, co_lo,
-                                                          npad, cin_pad);
+cudaError_t launch_pack_weight(const float* w, void* dst, int cout, int cin, int kh, int kw, int fold, int phase, int transposed,
+                               int co_lo, int npad, int cin_pad, cudaStream_t s) {
+  const int ekh = phase >= 0 ? 2 : kh, ekw = phase >= 0 ? 2 : (fold ? 1 : kw);
+  const long total = static_cast<long>(ekh) * ekw * (cin_pad >> 4) * npad * 16;
+  pack_weight_kernel<<<grid_for(total, 256), 256, 0, s>>>(w, reinterpret_cast<__nv_bfloat16*>(dst), cout, cin, kh, kw, fold, phase,
+                                                          transposed, co_lo, npad, cin_pad);
   return cudaGetLastError();
 }
 cudaError_t launch_pack_bias(const float* b, float* dst, int cout, int co_lo, int npad, cudaStream_t s) {

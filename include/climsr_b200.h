@@ -63,22 +63,29 @@ typedef struct CsrNetDesc {
 typedef enum CsrAct { CSR_ACT_NONE = 0, CSR_ACT_LRELU02 = 1, CSR_ACT_RELU = 2 } CsrAct;
 typedef enum CsrOutMode {
   CSR_OUT_BF16_NHWC = 0,     /* bf16, channel slice [out_coff, out_coff+cout) of an NHWC buffer          */
-  CSR_OUT_BF16_NHWC_UP2 = 1, /* same, each pixel replicated 2x2 into a (2H,2W) buffer (nearest x2)        */
-  CSR_OUT_F32_PLANAR = 2     /* fp32 (N,1,H,W); cout must be 1                                            */
+  CSR_OUT_F32_PLANAR = 2,    /* fp32 (N,1,H,W); cout must be 1                                            */
+  CSR_OUT_F32_NHWC = 3       /* fp32 NHWC, channel slice [out_coff, out_coff+cout) (gradients, debugging) */
 } CsrOutMode;
 
 typedef struct CsrConvDesc {
-  int32_t n, h, w;            /* input (== conv output) batch / height / width                            */
-  int32_t cin, cout;          /* real channel counts                                                       */
+  int32_t n, h, w;            /* input batch / height / width (output is 2h x 2w when in_up2, else h x w)  */
+  int32_t cin, cout;          /* real channel counts of the conv being executed                            */
   int32_t kh, kw;             /* odd kernel size; stride 1, padding (k-1)/2 ("same")                       */
-  int32_t in_c;               /* channels per pixel of the input buffer (multiple of 64)                   */
+  int32_t in_c, in_coff;      /* channels per pixel of the input buffer, first input channel (multiples of 8) */
   int32_t out_c, out_coff;    /* channels per pixel of the output buffer, first output channel             */
   int32_t act;                /* CsrAct                                                                    */
   int32_t out_mode;           /* CsrOutMode                                                                */
-  float   scale1;             /* v = act(conv+bias); if res1: v = v*scale1 + res1; if res2: v = v*scale2+res2 */
+  int32_t in_up2;             /* 1: F.interpolate(scale_factor=2, mode="nearest") is applied to the input first
+                                 (esrgan.py:94,97); executed as four 2x2 sub-pixel convs on the (h,w) input   */
+  int32_t transposed;         /* 1: weight is the FORWARD layer's (cin_fwd=cout, cout_fwd=cin) OIHW tensor and the
+                                 conv computed is its input gradient (flipped taps, swapped channel roles)    */
+  float   scale1;             /* v = act(conv+bias); if res1: v = v*scale1 + res1; if res2: v = v*scale2+res2;
+                                 if gate: v *= (gate > 0 ? 1 : gate_neg) for output channels >= gate_from      */
   float   scale2;
   int32_t res1_c, res1_coff;  /* residual buffers: bf16 NHWC with res*_c channels per pixel                */
   int32_t res2_c, res2_coff;
+  int32_t gate_c, gate_coff, gate_from;   /* gate buffer: bf16 NHWC (saved forward activations)            */
+  float   gate_neg;
 } CsrConvDesc;
 
 /* ---- library ------------------------------------------------------------------------------- */
@@ -120,11 +127,11 @@ int     csr_generator_forward(const CsrNetDesc* net, const void* packed, const f
                               int32_t n, int32_t h, int32_t w, void* stream);
 
 /* ---- single convolution (building block; used by the parity tests) --------------------------
- * in: bf16 NHWC (n,h,w,in_c); weight fp32 OIHW (cout,cin,kh,kw); bias fp32 (cout).
+ * in: bf16 NHWC (n,h,w,in_c); weight fp32 OIHW (cout,cin,kh,kw); bias fp32 (cout) or NULL (= zeros).
  * scratch: >= csr_conv2d_scratch_bytes() device bytes for the packed weights.                   */
 size_t  csr_conv2d_scratch_bytes(const CsrConvDesc* d);
 int     csr_conv2d_nhwc(const CsrConvDesc* d, const void* in, const float* weight, const float* bias,
-                        void* out, const void* res1, const void* res2,
+                        void* out, const void* res1, const void* res2, const void* gate,
                         void* scratch, size_t scratch_bytes, void* stream);
 
 /* ---- layout helpers -------------------------------------------------------------------------- */

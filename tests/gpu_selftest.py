@@ -132,10 +132,11 @@ def case_conv_epilogues():
     e = float((got - want).abs().max())
     print(f"  residual epilogue: max_err {e:.4g}", "OK" if e < 3e-2 else "FAIL")
     ok &= e < 3e-2
-    # nearest x2 replicate store
-    out = ops.conv2d_nhwc(to_nhwc(x), wt.cuda(), b.cuda(), act="lrelu", out_mode="nhwc_up2")
+    # nearest x2 on the input, then conv + lrelu (four sub-pixel phases)
+    out = ops.conv2d_nhwc(to_nhwc(x), wt.cuda(), b.cuda(), act="lrelu", in_up2=True)
     got = out.float().cpu().permute(0, 3, 1, 2)
-    want = torch.nn.functional.interpolate(torch.nn.functional.leaky_relu(y, 0.2), scale_factor=2, mode="nearest")
+    up = torch.nn.functional.interpolate(bf16r(x), scale_factor=2, mode="nearest")
+    want = torch.nn.functional.leaky_relu(torch.nn.functional.conv2d(up, wt, b, padding=1), 0.2)
     e = float((got - want).abs().max())
     print(f"  up2 epilogue: shape {tuple(got.shape)} max_err {e:.4g}", "OK" if e < 3e-2 else "FAIL")
     ok &= e < 3e-2

@@ -50,6 +50,8 @@ CONV_CASES = [
     (1, 40, 40, 64, 32, 1, "relu", 64),        # srcnn.conv2
     (1, 40, 40, 32, 1, 5, "none", 64),         # srcnn.conv3
     (1, 113, 113, 64, 64, 3, "lrelu", 64),     # Europe-extent LR raster
+    (2, 9, 11, 64, 24, 3, "relu", 64),         # cout multiple of 8 but not 16
+    (1, 7, 33, 64, 20, 3, "none", 64),         # ragged cout: per-element store path
 ]
 
 
@@ -89,11 +91,13 @@ def test_conv_epilogue_variants():
     buf = _nhwc(r2, 64)
     ops.conv2d_nhwc(_nhwc(x, 64), wt.cuda(), b.cuda(), out=buf, res1=_nhwc(r1, 64), scale1=0.2, res2=buf, scale2=0.2)
     assert float((buf.float().cpu().permute(0, 3, 1, 2) - want).abs().max()) <= 2.0 ** -7
-    # lrelu + nearest x2 (esrgan.py:94)
-    out = ops.conv2d_nhwc(_nhwc(x, 64), wt.cuda(), b.cuda(), act="lrelu", out_mode="nhwc_up2")
-    want = F.interpolate(F.leaky_relu(y, 0.2), scale_factor=2, mode="nearest")
+    # nearest x2 then conv + lrelu (esrgan.py:94,97): executed as four 2x2 sub-pixel convs with summed weights
+    out = ops.conv2d_nhwc(_nhwc(x, 64), wt.cuda(), b.cuda(), act="lrelu", in_up2=True)
+    up = F.interpolate(_bf(x), scale_factor=2, mode="nearest")
+    want = F.leaky_relu(F.conv2d(up.double(), wt.double(), b.double(), padding=1), 0.2).float()
     assert out.shape == (n, 2 * h, 2 * w, 64)
-    assert float((out.float().cpu().permute(0, 3, 1, 2) - want).abs().max()) <= 2.0 ** -7
+    # phase weights are sums of up to four bf16-rounded-after-summing taps: compare against fp32 weights, bf16 tolerance
+    assert float((out.float().cpu().permute(0, 3, 1, 2) - want).abs().max()) <= 2.0 ** -6
     # fp32 planar (final layer)
     w1 = (torch.rand((1, 64, 5, 5), generator=g) * 2 - 1) / 40
     b1 = torch.rand((1,), generator=g)
@@ -108,6 +112,42 @@ def test_conv_epilogue_variants():
     got = cat[..., 64:80].float().cpu().permute(0, 3, 1, 2)
     assert float((got - _ref_conv(x, w16, b16, "lrelu")).abs().max()) <= 2.0 ** -7
     assert bool((cat[..., 80:] == 0).all()) and bool((cat[..., :64] == _nhwc(x, 64)).all())
+    # per-element store path (option 4) must agree bit-for-bit with the TMA-store path
+    from climsr_b200._lib import lib
+    a = ops.conv2d_nhwc(_nhwc(x, 64), wt.cuda(), b.cuda(), act="lrelu")
+    lib.csr_set_option(4, 1)
+    try:
+        c = ops.conv2d_nhwc(_nhwc(x, 64), wt.cuda(), b.cuda(), act="lrelu")
+    finally:
+        lib.csr_set_option(4, 0)
+    assert torch.equal(a, c)
+
+
+def test_conv_transposed_and_gate():
+    """Input-gradient conv (transposed/flipped weights) with in-place accumulate and LeakyReLU-derivative gate: the building
+    block of the dense-block backward (autograd of esrgan.py:33-38)."""
+    from climsr_b200 import ops
+    g = torch.Generator().manual_seed(11)
+    n, h, w = 2, 13, 21
+    cin_f, cout_f = 80, 16                       # forward conv2 of an RDB: 80 -> 16
+    wt = (torch.rand((cout_f, cin_f, 3, 3), generator=g) * 2 - 1) / 20
+    gy = torch.rand((n, cout_f, h, w), generator=g) * 2 - 1
+    acc0 = torch.rand((n, cin_f, h, w), generator=g) * 2 - 1          # gradient already accumulated in the buffer
+    fwd = torch.rand((n, cin_f, h, w), generator=g) * 2 - 1           # saved forward activations (sign -> lrelu')
+    want = F.conv_transpose2d(_bf(gy).double(), _bf(wt).double(), padding=1).float() + _bf(acc0)
+    gate = torch.where(_bf(fwd) > 0, 1.0, 0.2)
+    gate[:, :64] = 1.0
+    want = want * gate
+    gbuf = torch.zeros((n, h, w, 128), dtype=torch.bfloat16).cuda()
+    gbuf[..., :cin_f] = acc0.permute(0, 2, 3, 1).to(torch.bfloat16).cuda()
+    gbuf[..., 80:96] = gy.permute(0, 2, 3, 1).to(torch.bfloat16).cuda()
+    fbuf = torch.zeros((n, h, w, 128), dtype=torch.bfloat16).cuda()
+    fbuf[..., :cin_f] = fwd.permute(0, 2, 3, 1).to(torch.bfloat16).cuda()
+    ops.conv2d_nhwc(gbuf, wt.cuda(), None, in_coff=80, transposed=True, out=gbuf, out_coff=0, res1=gbuf, scale1=1.0,
+                    gate=fbuf, gate_from=64)
+    got = gbuf[..., :cin_f].float().cpu().permute(0, 3, 1, 2)
+    assert float((got - want).abs().max()) <= 2.0 ** -7 * max(1.0, float(want.abs().max()))
+    assert torch.equal(gbuf[..., 80:96].cpu(), gy.permute(0, 2, 3, 1).to(torch.bfloat16))
 
 
 def _run_generator(sd, x, elev, mask, in_ch, nb, gc):
