@@ -23,6 +23,8 @@ static long long* g_trace = nullptr;
 static int g_opt_force_sw = 0;
 static int g_opt_max_slots = 8;
 static int g_opt_no_tma_store = 0;
+static int g_opt_two_acc = 0;
+static int g_opt_force_generic = 0;
 
 static int fail(int code, const char* fmt, ...) {
   va_list ap;
@@ -85,26 +87,6 @@ static int encode_act_map(CUtensorMap* m, const void* base, int N, int H, int W,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(CSR_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for N%d H%d W%d C%d box %dx%d", (int)r, N, H, W, C, box_w, box_h);
-  return CSR_OK;
-}
-
-// Output view of one launch: conv-output pixel (y, x) of image n lives at buffer pixel (y*sy + oy, x*sx + ox) of an
-// (N, out_H, out_W, C) bf16 NHWC buffer (sy = sx = 1 for a plain conv; 2 with (oy, ox) = the sub-pixel phase of a
-// nearest-x2 + conv layer).  Box = n_store channels x TW x TH x 1; rows of 128 B are staged 128B-swizzled.
-static int encode_out_map(CUtensorMap* m, void* base, int N, int H, int W, int C, int out_H, int out_W, int sy, int sx, int oy, int ox,
-                          int box_c, int box_w, int box_h) {
-  EncodeTiledFn fn = get_encode_fn();
-  if (!fn) return fail(CSR_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
-  uint8_t* b = reinterpret_cast<uint8_t*>(base) + ((size_t)oy * out_W + ox) * C * 2;
-  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
-  cuuint64_t strides[3] = {(cuuint64_t)sx * C * 2, (cuuint64_t)sy * out_W * C * 2, (cuuint64_t)out_H * out_W * C * 2};
-  cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
-  cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, b, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  box_c * 2 == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS)
-    return fail(CSR_ERR_CUDA, "cuTensorMapEncodeTiled (output) failed (%d) for N%d H%d W%d C%d box %dx%dx%d", (int)r, N, H, W, C, box_c, box_w, box_h);
   return CSR_OK;
 }
 
@@ -223,7 +205,7 @@ static int choose_tiling(int H, int W, int KH, int KW, int w_bytes, int n_kblock
     const int win_bytes = win_rows * SW * 128;
     const int slot_bytes = (int)align_up(win_bytes, 1024);
     const int stage_bytes = stage_row_bytes ? (int)align_up((size_t)TH * TW * stage_row_bytes, 1024) : 0;
-    const int fixed = 1024 + (int)align_up(w_bytes, 128) + 256 + 512 + 2 * stage_bytes;
+    const int fixed = 1024 + (int)align_up(w_bytes, 128) + 256 + 512 + (stage_row_bytes <= 64 ? 4 : 2) * stage_bytes;
     const int slots = std::min(g_opt_max_slots, (kSmemLimit - fixed) / slot_bytes);
     if (slots < 1) continue;
     const double tiles = (double)ceil_div(H, TH) * ceil_div(W, TW);
@@ -242,7 +224,7 @@ static int choose_tiling(int H, int W, int KH, int KW, int w_bytes, int n_kblock
 // One launch: parameters + its tensor maps.
 struct ConvLaunch {
   ConvParams p;
-  CUtensorMap tmap, tmap_out;
+  CUtensorMap tmap;
   size_t w_off = 0, b_off = 0;  // offsets into the packed blob (resolved at forward time)
   bool final_out = false;       // fp32-planar output that IS the caller's `out` tensor
 };
@@ -273,7 +255,7 @@ static int build_conv(const PackLayer& pl, const PackPart& pp, int N, int H, int
   p.w_bytes = pp.w_bytes;
   const int up = pp.phase >= 0 ? 2 : 1;
   const bool tma_out = io.out_kind == kOutBf16 && pp.n_store % 8 == 0 && !g_opt_no_tma_store;
-  p.store_mode = tma_out ? kStoreTma : io.out_kind == kOutBf16 ? kStoreDirect : io.out_kind == kOutF32Planar ? kStoreF32Planar : kStoreF32Nhwc;
+  p.store_mode = tma_out ? kStoreStaged : io.out_kind == kOutBf16 ? kStoreDirect : io.out_kind == kOutF32Planar ? kStoreF32Planar : kStoreF32Nhwc;
   p.stage_row_bytes = tma_out ? pp.n_store * 2 : 0;
   Tiling tl;
   int rc = choose_tiling(H, W, pp.kh, pp.kw, p.w_bytes, p.n_kblocks, p.stage_row_bytes, &tl);
@@ -284,14 +266,22 @@ static int build_conv(const PackLayer& pl, const PackPart& pp, int N, int H, int
   p.tiles_x = ceil_div(W, p.TW);
   p.tiles_y = ceil_div(H, p.TH);
   p.num_tiles = p.tiles_x * p.tiles_y * N;
+  p.tiles_per_img = p.tiles_x * p.tiles_y;
+  if ((long long)p.tiles_x * p.tiles_y * N >= (1 << 24) || p.tiles_per_img >= (1 << 16))
+    return fail(CSR_ERR_UNSUPPORTED, "too many tiles (%d x %d x %d) for one launch", p.tiles_x, p.tiles_y, N);
+  p.magic_img = ((1ull << 40) / (unsigned)p.tiles_per_img) + 1;
+  p.magic_row = ((1ull << 40) / (unsigned)p.tiles_x) + 1;
   p.win_rows = tl.win_rows; p.win_bytes = tl.win_bytes; p.slot_bytes = tl.slot_bytes; p.n_slots = tl.n_slots;
   p.stage_bytes = tl.stage_bytes;
+  // four tiles in flight in the epilogue when four accumulators fit in TMEM and a warp then owns <= 4 chunks of 8 channels
+  p.n_acc = (4 * p.KW * p.npad <= 512 && p.npad <= 32 && !g_opt_two_acc) ? 4 : 2;
   int cols = 32;
-  while (cols < 2 * p.KW * p.npad) cols *= 2;
+  while (cols < p.n_acc * p.KW * p.npad) cols *= 2;
   if (cols > 512 || p.KW * p.npad > 256) return fail(CSR_ERR_UNSUPPORTED, "KW*npad = %d exceeds the UMMA N / TMEM budget", p.KW * p.npad);
   p.tmem_cols = cols;
   p.trace = g_trace;
   p.use_pdl = g_opt_pdl;
+  p.force_generic = g_opt_force_generic;
   p.act = io.act;
   p.s1 = io.s1; p.s2 = io.s2;
   p.r1 = io.r1; p.r1_C = io.r1_C; p.r1_coff = io.r1_coff + pp.co_lo;
@@ -305,15 +295,7 @@ static int build_conv(const PackLayer& pl, const PackPart& pp, int N, int H, int
   p.out_H = up * H; p.out_W = up * W;
   cl->w_off = pp.w_off; cl->b_off = pp.b_off;
   if (conv_smem_bytes(p) > (size_t)kSmemLimit) return fail(CSR_ERR_UNSUPPORTED, "conv needs %zu bytes of shared memory", conv_smem_bytes(p));
-  rc = encode_act_map(&cl->tmap, io.in, N, H, W, io.in_C, p.SW, p.win_rows);
-  if (rc) return rc;
-  if (tma_out) {
-    rc = encode_out_map(&cl->tmap_out, io.out, N, H, W, io.out_C, p.out_H, p.out_W, up, up, p.out_oy, p.out_ox, pp.n_store, p.TW, p.TH);
-    if (rc) return rc;
-  } else {
-    cl->tmap_out = cl->tmap;
-  }
-  return CSR_OK;
+  return encode_act_map(&cl->tmap, io.in, N, H, W, io.in_C, p.SW, p.win_rows);
 }
 
 // ------------------------------------------------------------------------------------------- plan
@@ -471,7 +453,9 @@ int csr_set_option(int32_t key, int32_t value) {
     case 1: g_opt_pdl = value ? 1 : 0; return CSR_OK;      // programmatic dependent launch on/off
     case 2: g_opt_force_sw = value; return CSR_OK;
     case 3: g_opt_max_slots = value < 1 ? 1 : value; return CSR_OK;
-    case 4: g_opt_no_tma_store = value ? 1 : 0; return CSR_OK;   // debug: per-element global stores instead of TMA
+    case 4: g_opt_no_tma_store = value ? 1 : 0; return CSR_OK;
+    case 5: g_opt_two_acc = value ? 1 : 0; return CSR_OK;
+    case 6: g_opt_force_generic = value ? 1 : 0; return CSR_OK;  // debug: runtime-switched kernels only        // debug: never use four accumulator buffers   // debug: per-element global stores instead of the staged copy-out
     default: return fail(CSR_ERR_BAD_ARG, "unknown option key %d", key);
   }
 }
@@ -572,7 +556,7 @@ int csr_plan_forward(CsrPlan* P, const void* packed, const float* x, const float
     cl.p.wpk = pk + cl.w_off;
     cl.p.bias = reinterpret_cast<const float*>(pk + cl.b_off);
     if (cl.final_out) cl.p.out = out;
-    int e = launch_conv_tc(cl.p, cl.tmap, cl.tmap_out, P->sms, s);
+    int e = launch_conv_tc(cl.p, cl.tmap, P->sms, s);
     if (e) return fail(CSR_ERR_CUDA, "conv launch %zu failed: %s", i, cudaGetErrorString((cudaError_t)e));
     ++g_launches;
   }
@@ -643,7 +627,7 @@ int csr_conv2d_nhwc(const CsrConvDesc* d, const void* in, const float* weight, c
     if (rc) return rc;
     cl.p.wpk = base + pp.w_off;
     cl.p.bias = reinterpret_cast<const float*>(base + pp.b_off);
-    int e = launch_conv_tc(cl.p, cl.tmap, cl.tmap_out, di.sms, s);
+    int e = launch_conv_tc(cl.p, cl.tmap, di.sms, s);
     if (e) return fail(CSR_ERR_CUDA, "conv launch failed: %s", cudaGetErrorString((cudaError_t)e));
     g_launches += 3;
   }

@@ -19,9 +19,10 @@
 // Roles: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane) + TMEM owner, warps 2..17 = epilogue (four warps
 // per TMEM lane quadrant, each owning every 4th 8-channel chunk).  Accumulators are double buffered in TMEM so the
 // epilogue of tile i overlaps the MMAs of tile i+1; the layer's packed weights stay resident in shared memory for the
-// whole persistent CTA.  bf16 outputs are staged in a (swizzled) shared-memory tile and written with one bulk tensor
-// store per tile (TMA clips rows/columns outside the image; a strided output map scatters a sub-pixel phase of the
-// nearest-x2 + conv layers).  Programmatic dependent launch: everything before griddepcontrol.wait (barrier init, TMEM
+// whole persistent CTA.  bf16 outputs are staged in a (swizzled) shared-memory tile and copied out in 16-byte pieces,
+// whole pixel rows per warp instruction (a strided output view scatters a sub-pixel phase of the nearest-x2 + conv
+// layers).  A bulk tensor (TMA) store was measured first: it queues behind the producer's prefetched TMA loads in the
+// SM's TMA pipe and stalled its issuing warp for 1000-2700 clk per tile, so the copy-out uses LDS.128 + STG.128.  Programmatic dependent launch: everything before griddepcontrol.wait (barrier init, TMEM
 // alloc, weight/bias loads) overlaps the tail of the previous layer's kernel.
 //
 // Replaces one nn.Conv2d(+LeakyReLU/ReLU, *0.2+x, cat, nearest-x2) call site of the reference generator:
@@ -38,26 +39,30 @@ namespace {
 
 #define CSR_TRACE(role, tile_it, ev)                                                                                  \
   do {                                                                                                                \
-    if (p.trace && blockIdx.x == 0 && (tile_it) < 64) p.trace[((role) * 64 + (tile_it)) * 4 + (ev)] = clock64();      \
+    if (p.trace && blockIdx.x == 0 && (tile_it) < 64) p.trace[((role) * 64 + (tile_it)) * 8 + (ev)] = clock64();      \
   } while (0)
 
 struct Tile {
   int n, y0, x0;
 };
 
+// t / d for 0 <= t < 2^24, d < 2^16 via a host-computed reciprocal (floor(2^40/d) + 1): one 64-bit multiply, no division.
+__device__ __forceinline__ int fast_div(int t, unsigned long long magic) {
+  return static_cast<int>((static_cast<unsigned long long>(static_cast<unsigned>(t)) * magic) >> 40);
+}
+
 __device__ __forceinline__ Tile decode_tile(const ConvParams& p, int t) {
-  const int per_img = p.tiles_x * p.tiles_y;
   Tile r;
-  r.n = t / per_img;
-  const int rem = t - r.n * per_img;
-  const int ty = rem / p.tiles_x;
+  r.n = fast_div(t, p.magic_img);
+  const int rem = t - r.n * p.tiles_per_img;
+  const int ty = fast_div(rem, p.magic_row);
   r.y0 = ty * p.TH;
   r.x0 = (rem - ty * p.tiles_x) * p.TW;
   return r;
 }
 
 __device__ __forceinline__ float apply_act(float v, int act) {
-  if (act == 1) return v >= 0.f ? v : 0.2f * v;
+  if (act == 1) return fmaxf(v, 0.2f * v);
   if (act == 2) return fmaxf(v, 0.f);
   return v;
 }
@@ -98,25 +103,31 @@ __device__ __forceinline__ uint4 ldg16(const void* base, size_t pix, int C, int 
 
 }  // namespace
 
-template <int KW_T>   // compile-time horizontal tap count (0 = runtime p.KW, taps gathered one at a time)
+// Compile-time specialisation of the epilogue (it is instruction-issue bound, so every runtime switch costs):
+//   KW_T  horizontal taps (0 = runtime p.KW, taps gathered one at a time);  PW_T left padding when KW_T > 0
+//   ACT_T activation (-1 = runtime p.act);  RES_T bit0 r1, bit1 r2, bit2 gate (-1 = runtime pointers)
+//   ST_T  1 = staged bf16 stores only, -1 = runtime p.store_mode
+template <int KW_T, int PW_T, int ACT_T, int RES_T, int ST_T>
 __global__ void __launch_bounds__(kConvThreads, 1)
-conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_out) {
+conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment: the 128B-swizzle pattern repeats every 8 rows x 128 B.
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t slots_addr = smem_base;
-  const uint32_t stage_addr = slots_addr + static_cast<uint32_t>(p.n_slots) * p.slot_bytes;   // 2 staging buffers (TMA store)
-  const uint32_t w_addr = stage_addr + 2u * p.stage_bytes;
+  const uint32_t stage_addr = slots_addr + static_cast<uint32_t>(p.n_slots) * p.slot_bytes;   // one staging buffer per epilogue group
+  const uint32_t w_addr = stage_addr + static_cast<uint32_t>(p.n_acc) * p.stage_bytes;
   const uint32_t bias_addr = w_addr + ((p.w_bytes + 127) & ~127);
   const uint32_t bar_addr = bias_addr + 256;            // up to 64 fp32 biases
-  // barriers: [0] weights, [1..S] a_full, [1+S..2S] a_empty, then acc_full[2], acc_empty[2]
+  // barriers: [0] weights, [1..S] a_full, [1+S..2S] a_empty, then acc_full[4], acc_empty[4]
   const int S = p.n_slots;
+  const int NA = p.n_acc;                               // accumulator buffers in TMEM == epilogue groups (2 or 4)
+  const int wpg = kEpilogueWarps / NA;                  // warps per epilogue group
   auto bar_w = bar_addr;
   auto bar_a_full = [&](int s) { return bar_addr + 8u * (1 + s); };
   auto bar_a_empty = [&](int s) { return bar_addr + 8u * (1 + S + s); };
   auto bar_acc_full = [&](int b) { return bar_addr + 8u * (1 + 2 * S + b); };
-  auto bar_acc_empty = [&](int b) { return bar_addr + 8u * (3 + 2 * S + b); };
-  const uint32_t tmem_slot_addr = bar_addr + 8u * (5 + 2 * S);
+  auto bar_acc_empty = [&](int b) { return bar_addr + 8u * (5 + 2 * S + b); };
+  const uint32_t tmem_slot_addr = bar_addr + 8u * (9 + 2 * S);
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   float* bias_s = reinterpret_cast<float*>(smem_gen + (bias_addr - smem_base));
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot_addr - smem_base));
@@ -130,15 +141,14 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap, con
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmap);
-    tma_prefetch_desc(&tmap_out);
     mbar_init(bar_w, 1);
     for (int s = 0; s < S; ++s) {
       mbar_init(bar_a_full(s), 1);
       mbar_init(bar_a_empty(s), 1);
     }
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < NA; ++b) {
       mbar_init(bar_acc_full(b), 1);
-      mbar_init(bar_acc_empty(b), kEpilogueWarps);
+      mbar_init(bar_acc_empty(b), wpg);
     }
     fence_mbar_init();
     fence_proxy_async_smem();
@@ -198,12 +208,11 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap, con
     const uint32_t a_lbo = (16u >> 4) << 16, b_lbo = (128u >> 4) << 16;
     mbar_wait(bar_w, 0);
     tc_fence_after();
-    int slot = 0, it = 0;
-    uint32_t phase = 0;
+    int slot = 0, it = 0, buf = 0;
+    uint32_t phase = 0, acc_phase = 0;
     for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
-      const int buf = it & 1;
       if (lane == 0) CSR_TRACE(1, it, 0);
-      mbar_wait(bar_acc_empty(buf), ((it >> 1) & 1) ^ 1);
+      mbar_wait(bar_acc_empty(buf), acc_phase ^ 1);
       tc_fence_after();
       if (lane == 0) CSR_TRACE(1, it, 1);
       const uint32_t d_tmem = tmem_base + buf * nmma;
@@ -229,136 +238,186 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap, con
         if (kb == p.n_kblocks - 1 && lane == 0) CSR_TRACE(1, it, 3);
         if (++slot == S) { slot = 0; phase ^= 1; }
       }
+      if (++buf == NA) { buf = 0; acc_phase ^= 1; }
     }
   } else {
-    // ===================== epilogue: warps 2..17; TMEM lane quadrant = warp % 4, chunk group = (warp-2) / 4 ==========
+    // ===================== epilogue: warps 2..17 in NA groups; group g owns accumulator buffer g and every NA-th tile ====
+    // TMEM lane quadrant = warp % 4 (hardware rule); inside a group, warp j handles 8-channel chunks j/4, j/4 + wpg/4, ...
+    // Each group runs its own latency chain (wait accumulator -> TMEM loads -> shuffle-sum -> stage -> bulk store), so NA
+    // tiles are in flight in the epilogue while the MMA warp fills the next buffer.  The code is instruction-issue bound
+    // (16 warps share 4 schedulers): everything tile-invariant is hoisted and per-pixel address arithmetic only exists on
+    // the paths that need it (residual / gate / direct stores).
+    const int ew = warp - 2;
+    const int g = ew / wpg;                              // epilogue group == accumulator buffer
+    const int wj = ew - g * wpg;                         // warp within the group
     const int lane_grp = warp & 3;
-    const int grp = (warp - 2) >> 2;                     // 0..3: owns 8-channel chunks grp, grp+4
-    const bool issuer = (threadIdx.x == 64);             // first epilogue thread issues the bulk tensor stores
+    const int sub = wj >> 2;                             // first chunk of this warp
+    const int cstep = wpg >> 2;                          // chunk stride (1 or 2)
+    const int gthreads = wpg * 32;
+    const bool tracer = (threadIdx.x == 64);
     const int m = lane_grp * 32 + lane;
     const int ty = m >> p.sw_shift;
     const int tx = m & (p.SW - 1);                       // window column
     const int n_chunks = p.npad >> 3;
-    const bool col_ok = (tx >= p.PW) && (tx < p.PW + p.TW);
-    const int srow = ty * p.TW + (tx - p.PW);            // staging row of this thread's pixel
-    const bool tma_store = (p.store_mode == kStoreTma);
-    int it = 0;
-    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
-      const Tile tl = decode_tile(p, t);
-      const int buf = it & 1;
-      const int y = tl.y0 + ty;
-      const int x = tl.x0 - p.PW + tx;
-      const bool valid = col_ok && (y < p.H) && (x < p.W);
-      const size_t pix = (static_cast<size_t>(tl.n) * p.H + y) * p.W + x;
-      // residual / gate operands do not depend on the accumulator: fetch them before waiting for the MMAs
-      uint4 q1[2], q2[2], qg[2];
+    const int PW = KW_T ? PW_T : p.PW;
+    const bool col_ok = (tx >= PW) && (tx < PW + p.TW);
+    const int srow = ty * p.TW + (tx - PW);              // staging row of this thread's pixel
+    const int act = ACT_T >= 0 ? ACT_T : p.act;
+    const bool has_r1 = RES_T >= 0 ? (RES_T & 1) != 0 : p.r1 != nullptr;
+    const bool has_r2 = RES_T >= 0 ? (RES_T & 2) != 0 : p.r2 != nullptr;
+    const bool has_gate = RES_T >= 0 ? (RES_T & 4) != 0 : p.gate != nullptr;
+    const bool tma_store = ST_T >= 0 ? ST_T == 1 : (p.store_mode == kStoreStaged);
+    const bool need_pix = !tma_store || has_r1 || has_r2 || has_gate;    // warp-uniform
+    const uint32_t swz = (p.stage_row_bytes == 128) ? static_cast<uint32_t>(srow & 7) : 0u;   // SWIZZLE_128B staging rows
+    const uint32_t srow_addr = stage_addr + static_cast<uint32_t>(g) * p.stage_bytes + static_cast<uint32_t>(srow * p.stage_row_bytes);
+    const uint32_t sbuf = stage_addr + static_cast<uint32_t>(g) * p.stage_bytes;
+    const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16) + g * nmma;
+    const int d0 = -PW, d1 = 1 - PW, d2 = 2 - PW;
+    // Staged stores: the group's output tile sits in shared memory as TH*TW rows of stage_row_bytes; it is copied out in
+    // 16-byte pieces, consecutive lanes taking consecutive pieces of a pixel row (full 32..128-byte segments per pixel).
+    // Piece -> (row, column, channel group) is tile-invariant, so it is decoded once here.
+    const int rp = p.stage_row_bytes >> 4;               // 16-byte pieces per staged pixel
+    const int n_pieces = p.TH * p.TW * rp;
+    uint32_t pc_s[4], pc_d[4], pc_yx[4];
+    if (tma_store) {
+      const int tid_g = wj * 32 + lane;
 #pragma unroll
-      for (int ci = 0; ci < 2; ++ci) {
-        const int ch0 = (grp + 4 * ci) * 8;
-        const bool on = valid && (ch0 < p.n_store);
-        q1[ci] = (on && p.r1) ? ldg16(p.r1, pix, p.r1_C, p.r1_coff + ch0) : make_uint4(0, 0, 0, 0);
-        q2[ci] = (on && p.r2) ? ldg16(p.r2, pix, p.r2_C, p.r2_coff + ch0) : make_uint4(0, 0, 0, 0);
-        qg[ci] = (on && p.gate && ch0 >= p.gate_from) ? ldg16(p.gate, pix, p.gate_C, p.gate_coff + ch0)
-                                                       : make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);
+      for (int k = 0; k < 4; ++k) {
+        const int i = tid_g + k * gthreads;
+        const int sr = i / rp, c = i - sr * rp;
+        const int dy = sr / p.TW, dx = sr - dy * p.TW;
+        const uint32_t z = (p.stage_row_bytes == 128) ? static_cast<uint32_t>(sr & 7) : 0u;
+        pc_s[k] = sbuf + static_cast<uint32_t>(sr * p.stage_row_bytes) + ((static_cast<uint32_t>(c) ^ z) << 4);
+        pc_d[k] = static_cast<uint32_t>((dy * p.out_sy * p.out_W + dx * p.out_sx) * p.out_C + c * 8);
+        pc_yx[k] = (i < n_pieces) ? ((static_cast<uint32_t>(dy) << 16) | static_cast<uint32_t>(dx)) : 0xffffffffu;
       }
-      if (threadIdx.x == 64) CSR_TRACE(2, it, 0);
-      mbar_wait(bar_acc_full(buf), (it >> 1) & 1);
-      tc_fence_after();
-      if (threadIdx.x == 64) CSR_TRACE(2, it, 1);
-      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16) + buf * nmma;
-      float v[2][8];
+    }
+    uint32_t acc_phase = 0;
+    for (int it = g; ; it += NA, acc_phase ^= 1) {
+      const int t = blockIdx.x + it * static_cast<int>(gridDim.x);
+      if (t >= p.num_tiles) break;
+      if (tracer) CSR_TRACE(2, it, 3);
+      const Tile tl = decode_tile(p, t);
+      bool valid = false;
+      size_t pix = 0;
+      int y = 0, x = 0;
+      // residual / gate operands do not depend on the accumulator: fetch them before waiting for the MMAs
+      uint4 q1[4], q2[4];
+      if (need_pix) {
+        y = tl.y0 + ty;
+        x = tl.x0 - PW + tx;
+        valid = col_ok && (y < p.H) && (x < p.W);
+        pix = (static_cast<size_t>(tl.n) * p.H + y) * p.W + x;
 #pragma unroll
-      for (int ci = 0; ci < 2; ++ci) {
-        const int c = grp + 4 * ci;
+        for (int j = 0; j < 4; ++j) {
+          const int ch0 = (sub + j * cstep) * 8;
+          const bool on = valid && (ch0 < p.n_store);
+          q1[j] = (on && has_r1) ? ldg16(p.r1, pix, p.r1_C, p.r1_coff + ch0) : make_uint4(0, 0, 0, 0);
+          if (has_gate)   // the gate shares the second operand slot with r2 (the host never sets both)
+            q2[j] = (on && ch0 >= p.gate_from) ? ldg16(p.gate, pix, p.gate_C, p.gate_coff + ch0)
+                                               : make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);
+          else
+            q2[j] = (on && has_r2) ? ldg16(p.r2, pix, p.r2_C, p.r2_coff + ch0) : make_uint4(0, 0, 0, 0);
+        }
+      }
+      if (tma_store) named_bar_sync(1 + g, gthreads);   // every thread of the group has copied out the previous tile
+      if (tracer) CSR_TRACE(2, it, 0);
+      mbar_wait(bar_acc_full(g), acc_phase);
+      tc_fence_after();
+      if (tracer) CSR_TRACE(2, it, 1);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c = sub + j * cstep;
         if (c < n_chunks) {                               // warp-uniform
           const int ch0 = c * 8;
-#pragma unroll
-          for (int i = 0; i < 8; ++i) v[ci][i] = bias_s[ch0 + i];
+          float v[8];
+          {
+            const float4 b0 = *reinterpret_cast<const float4*>(bias_s + ch0);
+            const float4 b1 = *reinterpret_cast<const float4*>(bias_s + ch0 + 4);
+            v[0] = b0.x; v[1] = b0.y; v[2] = b0.z; v[3] = b0.w; v[4] = b1.x; v[5] = b1.y; v[6] = b1.z; v[7] = b1.w;
+          }
           if constexpr (KW_T == 1) {
             uint32_t r0[8];
             tmem_ld8(t_addr + ch0, r0);
             tmem_ld_wait();
-            gather_add8(v[ci], r0, 0, lane);
+            gather_add8(v, r0, 0, lane);
           } else if constexpr (KW_T == 2) {
             uint32_t r0[8], r1[8];
             tmem_ld8(t_addr + ch0, r0);
             tmem_ld8(t_addr + p.npad + ch0, r1);
             tmem_ld_wait();
-            gather_add8(v[ci], r0, -p.PW, lane);
-            gather_add8(v[ci], r1, 1 - p.PW, lane);
+            gather_add8(v, r0, d0, lane);
+            gather_add8(v, r1, d1, lane);
           } else if constexpr (KW_T == 3) {
             uint32_t r0[8], r1[8], r2[8];
             tmem_ld8(t_addr + ch0, r0);
             tmem_ld8(t_addr + p.npad + ch0, r1);
             tmem_ld8(t_addr + 2 * p.npad + ch0, r2);
             tmem_ld_wait();
-            gather_add8(v[ci], r0, -p.PW, lane);
-            gather_add8(v[ci], r1, 1 - p.PW, lane);
-            gather_add8(v[ci], r2, 2 - p.PW, lane);
+            gather_add8(v, r0, d0, lane);
+            gather_add8(v, r1, d1, lane);
+            gather_add8(v, r2, d2, lane);
           } else {
             for (int dx = 0; dx < KW; ++dx) {
               uint32_t r[8];
               tmem_ld8(t_addr + dx * p.npad + ch0, r);
               tmem_ld_wait();
-              gather_add8(v[ci], r, dx - p.PW, lane);
+              gather_add8(v, r, dx - PW, lane);
             }
           }
 #pragma unroll
-          for (int i = 0; i < 8; ++i) v[ci][i] = apply_act(v[ci][i], p.act);
-          if (p.r1) fma_residual8(v[ci], q1[ci], p.s1);
-          if (p.r2) fma_residual8(v[ci], q2[ci], p.s2);
-          if (p.gate) gate8(v[ci], qg[ci], p.gate_neg);
-        }
-      }
-      // all TMEM reads of this warp are complete (wait::ld above): hand the accumulator buffer back to the MMA warp
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_acc_empty(buf));
-
-      if (tma_store) {
-        const uint32_t sbuf = stage_addr + static_cast<uint32_t>(it & 1) * p.stage_bytes;
-        if (issuer) bulk_wait_group_read<1>();            // the store issued two tiles ago has finished reading this buffer
-        named_bar_sync(1, kEpilogueThreads);
-        if (col_ok) {
-#pragma unroll
-          for (int ci = 0; ci < 2; ++ci) {
-            const int c = grp + 4 * ci;
-            if (c * 8 < p.n_store) {
-              const int cs = (p.stage_row_bytes == 128) ? (c ^ (srow & 7)) : c;    // SWIZZLE_128B staging for 64-channel rows
-              st_shared_v4(sbuf + srow * p.stage_row_bytes + cs * 16, pack_bf16x2(v[ci][0], v[ci][1]), pack_bf16x2(v[ci][2], v[ci][3]),
-                           pack_bf16x2(v[ci][4], v[ci][5]), pack_bf16x2(v[ci][6], v[ci][7]));
-            }
+          for (int i = 0; i < 8; ++i) v[i] = apply_act(v[i], act);
+          if (need_pix) {
+            if (has_r1) fma_residual8(v, q1[j], p.s1);
+            if (has_gate) gate8(v, q2[j], p.gate_neg);
+            else if (has_r2) fma_residual8(v, q2[j], p.s2);
           }
-        }
-        fence_proxy_async_smem();
-        named_bar_sync(1, kEpilogueThreads);
-        if (issuer) {
-          tma_store_4d(&tmap_out, sbuf, p.out_coff, tl.x0, tl.y0, tl.n);
-          bulk_commit_group();
-        }
-      } else if (valid) {
-        const size_t opix = (static_cast<size_t>(tl.n) * p.out_H + (y * p.out_sy + p.out_oy)) * p.out_W + (x * p.out_sx + p.out_ox);
-        if (p.store_mode == kStoreF32Planar) {
-          if (grp == 0) reinterpret_cast<float*>(p.out)[opix] = v[0][0];
-        } else {
+          if (tma_store) {
+            if (col_ok && ch0 < p.n_store)
+              st_shared_v4(srow_addr + ((static_cast<uint32_t>(c) ^ swz) << 4), pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
+                           pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+          } else if (valid) {
+            const size_t opix = (static_cast<size_t>(tl.n) * p.out_H + (y * p.out_sy + p.out_oy)) * p.out_W + (x * p.out_sx + p.out_ox);
+            if (p.store_mode == kStoreF32Planar) {
+              if (c == 0) reinterpret_cast<float*>(p.out)[opix] = v[0];
+            } else {
 #pragma unroll
-          for (int ci = 0; ci < 2; ++ci) {
-            const int ch0 = (grp + 4 * ci) * 8;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              if (ch0 + i < p.n_store) {
-                if (p.store_mode == kStoreF32Nhwc)
-                  reinterpret_cast<float*>(p.out)[opix * p.out_C + p.out_coff + ch0 + i] = v[ci][i];
-                else
-                  reinterpret_cast<__nv_bfloat16*>(p.out)[opix * p.out_C + p.out_coff + ch0 + i] = __float2bfloat16_rn(v[ci][i]);
+              for (int i = 0; i < 8; ++i) {
+                if (ch0 + i < p.n_store) {
+                  if (p.store_mode == kStoreF32Nhwc)
+                    reinterpret_cast<float*>(p.out)[opix * p.out_C + p.out_coff + ch0 + i] = v[i];
+                  else
+                    reinterpret_cast<__nv_bfloat16*>(p.out)[opix * p.out_C + p.out_coff + ch0 + i] = __float2bfloat16_rn(v[i]);
+                }
               }
             }
           }
         }
       }
-      if (threadIdx.x == 64) CSR_TRACE(2, it, 2);
+      if (tracer) CSR_TRACE(2, it, 4);
+      // all TMEM reads of this warp are complete (wait::ld above): hand the accumulator buffer back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_acc_empty(g));
+      if (tma_store) {
+        named_bar_sync(1 + g, gthreads);                  // the staged tile is complete
+        if (tracer) CSR_TRACE(2, it, 7);
+        __nv_bfloat16* tile_out = reinterpret_cast<__nv_bfloat16*>(p.out) +
+            ((static_cast<size_t>(tl.n) * p.out_H + (tl.y0 * p.out_sy + p.out_oy)) * p.out_W + (tl.x0 * p.out_sx + p.out_ox)) * p.out_C +
+            p.out_coff;
+        const uint32_t lim = (static_cast<uint32_t>(min(p.H - tl.y0, 0x7fff)) << 16) | static_cast<uint32_t>(min(p.W - tl.x0, 0x7fff));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          // piece inside the image: dy < H - y0 and dx < W - x0 (both halves compared at once; 0xffffffff = no piece)
+          const bool ok = ((pc_yx[k] >> 16) < (lim >> 16)) && ((pc_yx[k] & 0xffffu) < (lim & 0xffffu));
+          if (ok) {
+            const uint4 val = ld_shared_v4(pc_s[k]);
+            *reinterpret_cast<uint4*>(tile_out + pc_d[k]) = val;
+          }
+        }
+      }
+      if (tracer) CSR_TRACE(2, it, 2);
     }
-    if (tma_store && issuer) bulk_wait_group<0>();        // all bulk stores of this CTA have completed
   }
 
   tc_fence_before();
@@ -371,17 +430,18 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap, con
 }
 
 size_t conv_smem_bytes(const ConvParams& p) {
-  return 1024 /*alignment slack*/ + static_cast<size_t>(p.n_slots) * p.slot_bytes + 2 * static_cast<size_t>(p.stage_bytes) +
-         ((p.w_bytes + 127) & ~127) + 256 /*bias*/ + 8 * (5 + 2 * p.n_slots) + 16;
+  return 1024 /*alignment slack*/ + static_cast<size_t>(p.n_slots) * p.slot_bytes + static_cast<size_t>(p.n_acc) * p.stage_bytes +
+         ((p.w_bytes + 127) & ~127) + 256 /*bias*/ + 8 * (9 + 2 * p.n_slots) + 16;
 }
 
-template <int KW_T>
-static int launch_t(const ConvParams& p, const CUtensorMap& tmap, const CUtensorMap& tmap_out, int num_sms, cudaStream_t stream) {
+template <int KW_T, int PW_T, int ACT_T, int RES_T, int ST_T>
+static int launch_t(const ConvParams& p, const CUtensorMap& tmap, int num_sms, cudaStream_t stream) {
   const size_t smem = conv_smem_bytes(p);
   if (smem > static_cast<size_t>(kSmemLimit)) return static_cast<int>(cudaErrorInvalidValue);
   static bool configured = false;
+  auto kern = conv_tc_kernel<KW_T, PW_T, ACT_T, RES_T, ST_T>;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<KW_T>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
     if (e != cudaSuccess) return static_cast<int>(e);
     configured = true;
   }
@@ -395,15 +455,32 @@ static int launch_t(const ConvParams& p, const CUtensorMap& tmap, const CUtensor
   attr[0].val.programmaticStreamSerializationAllowed = p.use_pdl ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return static_cast<int>(cudaLaunchKernelEx(&cfg, conv_tc_kernel<KW_T>, p, tmap, tmap_out));
+  return static_cast<int>(cudaLaunchKernelEx(&cfg, kern, p, tmap));
 }
 
-int launch_conv_tc(const ConvParams& p, const CUtensorMap& tmap, const CUtensorMap& tmap_out, int num_sms, cudaStream_t stream) {
+int launch_conv_tc(const ConvParams& p, const CUtensorMap& tmap, int num_sms, cudaStream_t stream) {
+  const int res = (p.r1 ? 1 : 0) | (p.r2 ? 2 : 0) | (p.gate ? 4 : 0);
+  const bool staged = p.store_mode == kStoreStaged;
+  if ((res & 6) == 6) return static_cast<int>(cudaErrorInvalidValue);   // r2 and gate share an operand slot
+#define CSR_CASE(KW_, PW_, ACT_, RES_)                                                                     \
+  if (staged && !p.force_generic && p.KW == KW_ && p.PW == PW_ && p.act == ACT_ && res == RES_)            \
+    return launch_t<KW_, PW_, ACT_, RES_, 1>(p, tmap, num_sms, stream);
+  // the layer shapes of the generator forward (esrgan.py / srcnn.py) ...
+  CSR_CASE(3, 1, 1, 0)   // RDB conv1-4, HRconv: lrelu
+  CSR_CASE(3, 1, 0, 0)   // conv_first
+  CSR_CASE(3, 1, 0, 1)   // RDB conv5 (*0.2 + x), trunk_conv (+ fea)
+  CSR_CASE(3, 1, 0, 3)   // RDB3 conv5 (*0.2 + x, *0.2 + x_rrdb)
+  CSR_CASE(2, 0, 1, 0)   // upconv sub-pixel phases
+  CSR_CASE(2, 1, 1, 0)
+  CSR_CASE(1, 0, 2, 0)   // srcnn.conv1 (x-im2col folded), srcnn.conv2: relu
+  // ... and of its backward (input-gradient convs: accumulate in place, LeakyReLU-derivative gate)
+  CSR_CASE(3, 1, 0, 5)
+  CSR_CASE(3, 1, 0, 4)
+#undef CSR_CASE
   switch (p.KW) {
-    case 1: return launch_t<1>(p, tmap, tmap_out, num_sms, stream);
-    case 2: return launch_t<2>(p, tmap, tmap_out, num_sms, stream);
-    case 3: return launch_t<3>(p, tmap, tmap_out, num_sms, stream);
-    default: return launch_t<0>(p, tmap, tmap_out, num_sms, stream);
+    case 1: return launch_t<1, 0, -1, -1, -1>(p, tmap, num_sms, stream);
+    case 3: if (p.PW == 1) return launch_t<3, 1, -1, -1, -1>(p, tmap, num_sms, stream);
+    default: return launch_t<0, 0, -1, -1, -1>(p, tmap, num_sms, stream);
   }
 }
 

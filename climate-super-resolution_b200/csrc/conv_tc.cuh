@@ -14,7 +14,7 @@ constexpr int kSmemLimit = 232448;    // 227 KB opt-in dynamic shared memory per
 constexpr int kMaxNpad = 64;          // output channels per launch part (epilogue: <= 2 chunks of 8 per warp)
 
 enum StoreMode {
-  kStoreTma = 0,        // bf16 NHWC through a swizzled shared-memory staging tile + cp.async.bulk.tensor store
+  kStoreStaged = 0,     // bf16 NHWC through a swizzled shared-memory staging tile, copied out as whole pixel rows
   kStoreDirect = 1,     // bf16 NHWC, per-element global stores (ragged channel counts)
   kStoreF32Planar = 2,  // fp32 (N,1,H,W), channel 0 only
   kStoreF32Nhwc = 3     // fp32 NHWC (n_store channels per pixel, pitch out_C): gradient / debug outputs
@@ -31,14 +31,17 @@ struct ConvParams {
   int n_store;     // real output channels
   // tiling: a tile is TH rows x SW window columns of which TW = SW-(KW-1) are real outputs (columns [PW, PW+TW))
   int SW, sw_shift, TH, TW;
-  int tiles_x, tiles_y, num_tiles;
+  int tiles_x, tiles_y, num_tiles, tiles_per_img;
+  unsigned long long magic_img, magic_row;   // floor(2^40/d)+1 for d = tiles_per_img, tiles_x (num_tiles < 2^24)
   int win_rows;    // TH + KH - 1
   int win_bytes;   // win_rows * SW * 128  (== TMA box bytes per 64-channel k-block)
   int slot_bytes;  // win_bytes rounded up to 1024
   int n_kblocks;   // ceil(cin / 64)
   int n_slots;     // activation-window ring depth
   int w_bytes;     // packed weights: KH * (cin/16) * KW * npad * 32
-  int tmem_cols;   // power of two >= max(32, 2*KW*npad)
+  int n_acc;       // accumulator buffers in TMEM == epilogue warp groups (2 or 4); n_acc * KW * npad <= 512
+  int tmem_cols;   // power of two >= max(32, n_acc*KW*npad)
+  int force_generic;  // debug: skip the compile-time specialised kernels
   int use_pdl;     // launch with programmatic stream serialization (prologue overlaps the previous kernel's tail)
   // epilogue:  v = act(acc + bias);  if r1: v = v*s1 + r1;  if r2: v = v*s2 + r2;  if gate: v *= (gate > 0 ? 1 : gate_neg)
   const float* bias;   // [npad] fp32 (zero padded)
@@ -50,18 +53,16 @@ struct ConvParams {
   const void* gate; int gate_C, gate_coff; int gate_from; float gate_neg;   // applied to output channels >= gate_from
   void* out; int out_C, out_coff;
   int store_mode;      // StoreMode
-  int out_sy, out_sx, out_oy, out_ox;   // direct modes: output pixel (y,x) lives at (y*out_sy+out_oy, x*out_sx+out_ox)
-  int out_H, out_W;                     // spatial size of the output buffer (direct modes)
-  int stage_row_bytes; // kStoreTma: bytes per staged pixel (n_store * 2: 16..128)
+  int out_sy, out_sx, out_oy, out_ox;   // conv-output pixel (y,x) lives at buffer pixel (y*out_sy+out_oy, x*out_sx+out_ox)
+  int out_H, out_W;                     // spatial size of the output buffer
+  int stage_row_bytes; // kStoreStaged: bytes per staged pixel (n_store * 2: 16..128)
   int stage_bytes;     // one staging buffer (TH*TW*stage_row_bytes rounded up to 1024)
   long long* trace;    // debug: per-role clock64 timestamps of CTA 0 (nullptr = off), [3 roles][64 tiles][4 events]
 };
 
 // Returns cudaError_t (as int).
 //   tmap_in : 4-D (C, W, H, N) bf16 map, box (64, SW, win_rows, 1), SWIZZLE_128B, zero OOB fill (= the conv padding)
-//   tmap_out: 4-D (C, W, H, N) bf16 map (possibly strided: one sub-pixel phase), box (n_store, TW, TH, 1); ignored
-//             unless store_mode == kStoreTma
 size_t conv_smem_bytes(const ConvParams& p);
-int launch_conv_tc(const ConvParams& p, const CUtensorMap& tmap_in, const CUtensorMap& tmap_out, int num_sms, cudaStream_t stream);
+int launch_conv_tc(const ConvParams& p, const CUtensorMap& tmap_in, int num_sms, cudaStream_t stream);
 
 }  // namespace csr

@@ -96,8 +96,8 @@ int         csr_device_check(void);
 /* debug / tuning knobs (key, value); unknown keys return CSR_ERR_BAD_ARG. */
 int         csr_set_option(int32_t key, int32_t value);
 int64_t     csr_kernel_launch_count(void);           /* kernels launched by this library so far   */
-/* debug: device buffer of 3*64*4 int64 receiving per-role clock64 timestamps of CTA 0 for convs built afterwards
- * (NULL switches tracing off).  Layout [role: producer, mma, epilogue][tile 0..63][event 0..3].                   */
+/* debug: device buffer of 3*64*8 int64 receiving per-role clock64 timestamps of CTA 0 for convs built afterwards
+ * (NULL switches tracing off).  Layout [role: producer, mma, epilogue][tile 0..63][event 0..7].                   */
 int         csr_debug_set_trace(void* device_buffer);
 
 /* ---- weights --------------------------------------------------------------------------------

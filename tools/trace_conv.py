@@ -14,7 +14,7 @@ def run(name, n, h, w, cin, cout, k, in_c, act="lrelu", out_coff=0):
     x = torch.zeros((n, h, w, in_c), dtype=torch.bfloat16, device="cuda")
     wt = torch.rand((cout, cin, k, k), device="cuda") - 0.5
     b = torch.rand((cout,), device="cuda")
-    trace = torch.zeros(3 * 64 * 4, dtype=torch.int64, device="cuda")
+    trace = torch.zeros(3 * 64 * 8, dtype=torch.int64, device="cuda")
     out = torch.zeros((n, h, w, max(in_c, 64)), dtype=torch.bfloat16, device="cuda") if cout > 1 else None
     for rep in range(2):
         lib.csr_debug_set_trace(trace.data_ptr())
@@ -24,19 +24,24 @@ def run(name, n, h, w, cin, cout, k, in_c, act="lrelu", out_coff=0):
             ops.conv2d_nhwc(x, wt, b, act=act)
         torch.cuda.synchronize()
     lib.csr_debug_set_trace(None)
-    t = trace.cpu().view(3, 64, 4)
+    t = trace.cpu().view(3, 64, 8)
     t0 = int(t[0, 0, 0])
     print(f"== {name}: n{n} {h}x{w} cin{cin} cout{cout} k{k}")
-    print(" tile | prod: wait_empty_start wait_done | mma: start accempty_ok afull_ok issued | epi: start accfull_ok done")
-    for i in range(0, 18):
+    print(" tile | prod: wait_empty_start wait_done | mma: start accempty_ok afull_ok issued | epi: loop_top prefetched accfull_ok math_done bar1 staged bar2 stored")
+    for i in range(0, 10):
         if int(t[1, i, 0]) == 0:
             break
         r = lambda v: int(v) - t0  # noqa: E731
         print(f" {i:4d} | {r(t[0,i,0]):8d} {r(t[0,i,1]):8d} | {r(t[1,i,0]):8d} {r(t[1,i,1]):8d} {r(t[1,i,2]):8d} {r(t[1,i,3]):8d} | "
-              f"{r(t[2,i,0]):8d} {r(t[2,i,1]):8d} {r(t[2,i,2]):8d}")
+              f"{r(t[2,i,3]):8d} {r(t[2,i,0]):8d} {r(t[2,i,1]):8d} {r(t[2,i,4]):8d} {r(t[2,i,5]):8d} {r(t[2,i,6]):8d} {r(t[2,i,7]):8d} {r(t[2,i,2]):8d}")
 
 
 if __name__ == "__main__":
+    if os.environ.get("CSR_SLOTS"):
+        lib.csr_set_option(3, int(os.environ["CSR_SLOTS"]))
+    if os.environ.get("CSR_ONLY"):
+        run("HRconv", 16, 256, 256, 64, 64, 3, 64)
+        sys.exit(0)
     run("rdb.conv1", 64, 64, 64, 64, 16, 3, 128, out_coff=64)
     run("rdb.conv5", 64, 64, 64, 128, 64, 3, 128, act="none")
     run("HRconv", 16, 256, 256, 64, 64, 3, 64)
