@@ -25,6 +25,8 @@ static int g_opt_max_slots = 8;
 static int g_opt_no_tma_store = 0;
 static int g_opt_two_acc = 0;
 static int g_opt_force_generic = 0;
+static int g_opt_one_mma = 0;
+static int g_opt_no_direct32 = 1;   // measured: no gain over staging on cfg2 (tools/ab_bench.py), kept as an option
 
 static int fail(int code, const char* fmt, ...) {
   va_list ap;
@@ -260,6 +262,17 @@ static int build_conv(const PackLayer& pl, const PackPart& pp, int N, int H, int
   Tiling tl;
   int rc = choose_tiling(H, W, pp.kh, pp.kw, p.w_bytes, p.n_kblocks, p.stage_row_bytes, &tl);
   if (rc) return rc;
+  if (tma_out && tl.n_slots < 2 * p.n_kblocks && pp.n_store % 16 == 0 && io.out_C % 16 == 0 && (io.out_coff + pp.co_lo) % 16 == 0 &&
+      !g_opt_no_direct32) {
+    // The resident weights leave too little shared memory for staging AND a window ring that prefetches across tiles
+    // (RDB conv5: 144 KB of weights): store whole 32-byte sectors straight from registers instead.
+    Tiling t2;
+    if (choose_tiling(H, W, pp.kh, pp.kw, p.w_bytes, p.n_kblocks, 0, &t2) == CSR_OK && t2.n_slots >= 2 * p.n_kblocks) {
+      tl = t2;
+      p.store_mode = kStoreDirect32;
+      p.stage_row_bytes = 0;
+    }
+  }
   p.SW = tl.SW; p.TH = tl.TH; p.TW = tl.TW;
   p.sw_shift = 0;
   while ((1 << p.sw_shift) < p.SW) ++p.sw_shift;
@@ -274,6 +287,7 @@ static int build_conv(const PackLayer& pl, const PackPart& pp, int N, int H, int
   p.win_rows = tl.win_rows; p.win_bytes = tl.win_bytes; p.slot_bytes = tl.slot_bytes; p.n_slots = tl.n_slots;
   p.stage_bytes = tl.stage_bytes;
   // four tiles in flight in the epilogue when four accumulators fit in TMEM and a warp then owns <= 4 chunks of 8 channels
+  p.n_mma = g_opt_one_mma ? 1 : 2;
   p.n_acc = (4 * p.KW * p.npad <= 512 && p.npad <= 32 && !g_opt_two_acc) ? 4 : 2;
   int cols = 32;
   while (cols < p.n_acc * p.KW * p.npad) cols *= 2;
@@ -455,7 +469,9 @@ int csr_set_option(int32_t key, int32_t value) {
     case 3: g_opt_max_slots = value < 1 ? 1 : value; return CSR_OK;
     case 4: g_opt_no_tma_store = value ? 1 : 0; return CSR_OK;
     case 5: g_opt_two_acc = value ? 1 : 0; return CSR_OK;
-    case 6: g_opt_force_generic = value ? 1 : 0; return CSR_OK;  // debug: runtime-switched kernels only        // debug: never use four accumulator buffers   // debug: per-element global stores instead of the staged copy-out
+    case 6: g_opt_force_generic = value ? 1 : 0; return CSR_OK;
+    case 7: g_opt_one_mma = value ? 1 : 0; return CSR_OK;
+    case 8: g_opt_no_direct32 = value ? 1 : 0; return CSR_OK;    // 0: allow unstaged 32-byte stores when staging starves the window ring        // debug: a single MMA issuer warp  // debug: runtime-switched kernels only        // debug: never use four accumulator buffers   // debug: per-element global stores instead of the staged copy-out
     default: return fail(CSR_ERR_BAD_ARG, "unknown option key %d", key);
   }
 }

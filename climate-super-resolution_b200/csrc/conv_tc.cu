@@ -16,8 +16,8 @@
 // the same window read from byte offset dy*SW*128: only the descriptor start address changes between taps (UMMA
 // applies the 128B swizzle on absolute smem address bits, so any 128-byte-aligned start works - verified on HW).
 //
-// Roles: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane) + TMEM owner, warps 2..17 = epilogue (four warps
-// per TMEM lane quadrant, each owning every 4th 8-channel chunk).  Accumulators are double buffered in TMEM so the
+// Roles: warp 0 = TMA producer, warps 1-2 = MMA issuers on alternate tiles (warp 1 owns TMEM), warps 3..18 = epilogue in
+// 2 or 4 independent groups (each group covers the four TMEM lane quadrants and owns one accumulator buffer).  Accumulators are double buffered in TMEM so the
 // epilogue of tile i overlaps the MMAs of tile i+1; the layer's packed weights stay resident in shared memory for the
 // whole persistent CTA.  bf16 outputs are staged in a (swizzled) shared-memory tile and copied out in 16-byte pieces,
 // whole pixel rows per warp instruction (a strided output view scatters a sub-pixel phase of the nearest-x2 + conv
@@ -106,7 +106,7 @@ __device__ __forceinline__ uint4 ldg16(const void* base, size_t pix, int C, int 
 // Compile-time specialisation of the epilogue (it is instruction-issue bound, so every runtime switch costs):
 //   KW_T  horizontal taps (0 = runtime p.KW, taps gathered one at a time);  PW_T left padding when KW_T > 0
 //   ACT_T activation (-1 = runtime p.act);  RES_T bit0 r1, bit1 r2, bit2 gate (-1 = runtime pointers)
-//   ST_T  1 = staged bf16 stores only, -1 = runtime p.store_mode
+//   ST_T  1 = staged bf16 stores only, 2 = direct 32-byte bf16 stores only, -1 = runtime p.store_mode
 template <int KW_T, int PW_T, int ACT_T, int RES_T, int ST_T>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
@@ -127,10 +127,11 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
   auto bar_a_empty = [&](int s) { return bar_addr + 8u * (1 + S + s); };
   auto bar_acc_full = [&](int b) { return bar_addr + 8u * (1 + 2 * S + b); };
   auto bar_acc_empty = [&](int b) { return bar_addr + 8u * (5 + 2 * S + b); };
-  const uint32_t tmem_slot_addr = bar_addr + 8u * (9 + 2 * S);
+  const uint32_t tmem_slot_addr = bar_addr + 8u * (9 + 2 * S);       // [0] TMEM base, [1..2] issuer progress words
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   float* bias_s = reinterpret_cast<float*>(smem_gen + (bias_addr - smem_base));
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot_addr - smem_base));
+  volatile uint32_t* progress = tmem_slot + 1;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -140,6 +141,8 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
   griddep_launch_dependents();
 
   if (threadIdx.x == 0) {
+    progress[0] = 0;
+    progress[1] = 0;
     tma_prefetch_desc(&tmap);
     mbar_init(bar_w, 1);
     for (int s = 0; s < S; ++s) {
@@ -195,10 +198,17 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
         if (++slot == S) { slot = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    // All 32 lanes run the warp-uniform control flow; one elected lane issues.  Per MMA only the 14-bit start-address
-    // fields of the two descriptors change.
+  } else if (warp <= kMmaWarps) {
+    if (warp > p.n_mma) goto done;                       // single-issuer launches: warp 2 idles
+    // ===================== MMA issuers (warps 1 and 2 take alternate tiles) =====================
+    // tcgen05.mma issue proceeds at execution pace (the issuing thread stalls while the tensor pipe is busy), so with a
+    // single issuer the ~600 clk of mbarrier round trips between tiles leave the pipe idle.  With two issuers one warp's
+    // waits overlap the other warp's MMAs.  Both issuers share the window-slot ring.  A parity wait is only unambiguous if
+    // the waiter is at most one phase ahead of the barrier, so before waiting for ring entry e an issuer makes sure entry
+    // e - n_slots (the previous fill of the same slot) has been seen full: trivially true for its own entries, and read
+    // from the other issuer's progress word otherwise.  All 32 lanes run the warp-uniform control flow; one elected lane issues.  Per
+    // MMA only the 14-bit start-address fields of the two descriptors change.
+    const int mw = warp - 1;
     const uint32_t idesc = make_idesc_bf16(kTileM, nmma);
     const uint32_t b_step16 = static_cast<uint32_t>(nmma * 32) >> 4;          // one (dy,kstep) weight block in 16-byte units
     const uint32_t kb_w16 = static_cast<uint32_t>(p.KH * 4) * b_step16;       // one full k-block of weights
@@ -208,16 +218,35 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
     const uint32_t a_lbo = (16u >> 4) << 16, b_lbo = (128u >> 4) << 16;
     mbar_wait(bar_w, 0);
     tc_fence_after();
-    int slot = 0, it = 0, buf = 0;
+    // window-slot ring position of k-block 0 of this warp's first tile (the ring is shared by both issuers: tile `it`
+    // owns ring entries it*n_kblocks .. it*n_kblocks + n_kblocks-1)
+    int slot = 0, buf = mw;
     uint32_t phase = 0, acc_phase = 0;
-    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
+    auto ring_advance = [&](int steps) {
+      for (int i = 0; i < steps; ++i)
+        if (++slot == S) { slot = 0; phase ^= 1; }
+    };
+    if (mw) ring_advance(p.n_kblocks);
+    int entry = mw * p.n_kblocks;                                            // ring entry index of (tile, kb)
+    for (int it = mw; ; it += p.n_mma) {
+      const int t = blockIdx.x + it * static_cast<int>(gridDim.x);
+      if (t >= p.num_tiles) break;
       if (lane == 0) CSR_TRACE(1, it, 0);
       mbar_wait(bar_acc_empty(buf), acc_phase ^ 1);
       tc_fence_after();
       if (lane == 0) CSR_TRACE(1, it, 1);
       const uint32_t d_tmem = tmem_base + buf * nmma;
-      for (int kb = 0; kb < p.n_kblocks; ++kb) {
+      for (int kb = 0; kb < p.n_kblocks; ++kb, ++entry) {
+        if (p.n_mma > 1) {
+          const int need = entry - S;
+          if (need >= 0 && ((need / p.n_kblocks) & 1) != mw) {
+            uint32_t spins = 0;
+            while (progress[1 - mw] <= static_cast<uint32_t>(need))
+              if (++spins > (1u << 24)) mbar_timeout(0xdead0000u + mw, need);
+          }
+        }
         mbar_wait(bar_a_full(slot), phase);
+        if (p.n_mma > 1) progress[mw] = static_cast<uint32_t>(entry) + 1u;
         tc_fence_after();
         if (kb == 0 && lane == 0) CSR_TRACE(1, it, 2);
         const int ks_here = min(4, ksteps_total - kb * 4);
@@ -236,25 +265,30 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
         }
         __syncwarp();
         if (kb == p.n_kblocks - 1 && lane == 0) CSR_TRACE(1, it, 3);
-        if (++slot == S) { slot = 0; phase ^= 1; }
+        ring_advance(1);
       }
-      if (++buf == NA) { buf = 0; acc_phase ^= 1; }
+      if (p.n_mma > 1) {                                                   // skip the other issuer's tile
+        ring_advance(p.n_kblocks);
+        entry += p.n_kblocks;
+      }
+      buf += p.n_mma;
+      if (buf >= NA) { buf -= NA; acc_phase ^= 1; }
     }
   } else {
-    // ===================== epilogue: warps 2..17 in NA groups; group g owns accumulator buffer g and every NA-th tile ====
+    // ===================== epilogue: 16 warps in NA groups; group g owns accumulator buffer g and every NA-th tile ====
     // TMEM lane quadrant = warp % 4 (hardware rule); inside a group, warp j handles 8-channel chunks j/4, j/4 + wpg/4, ...
     // Each group runs its own latency chain (wait accumulator -> TMEM loads -> shuffle-sum -> stage -> bulk store), so NA
     // tiles are in flight in the epilogue while the MMA warp fills the next buffer.  The code is instruction-issue bound
     // (16 warps share 4 schedulers): everything tile-invariant is hoisted and per-pixel address arithmetic only exists on
     // the paths that need it (residual / gate / direct stores).
-    const int ew = warp - 2;
+    const int ew = warp - 1 - kMmaWarps;
     const int g = ew / wpg;                              // epilogue group == accumulator buffer
     const int wj = ew - g * wpg;                         // warp within the group
     const int lane_grp = warp & 3;
     const int sub = wj >> 2;                             // first chunk of this warp
     const int cstep = wpg >> 2;                          // chunk stride (1 or 2)
     const int gthreads = wpg * 32;
-    const bool tracer = (threadIdx.x == 64);
+    const bool tracer = (ew == 0 && lane == 0);
     const int m = lane_grp * 32 + lane;
     const int ty = m >> p.sw_shift;
     const int tx = m & (p.SW - 1);                       // window column
@@ -310,7 +344,7 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
         pix = (static_cast<size_t>(tl.n) * p.H + y) * p.W + x;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const int ch0 = (sub + j * cstep) * 8;
+          const int ch0 = (2 * (sub + (j >> 1) * cstep) + (j & 1)) * 8;
           const bool on = valid && (ch0 < p.n_store);
           q1[j] = (on && has_r1) ? ldg16(p.r1, pix, p.r1_C, p.r1_coff + ch0) : make_uint4(0, 0, 0, 0);
           if (has_gate)   // the gate shares the second operand slot with r2 (the host never sets both)
@@ -325,9 +359,10 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
       mbar_wait(bar_acc_full(g), acc_phase);
       tc_fence_after();
       if (tracer) CSR_TRACE(2, it, 1);
+      uint4 held = make_uint4(0, 0, 0, 0);                // first half of a 32-byte direct store
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const int c = sub + j * cstep;
+        const int c = 2 * (sub + (j >> 1) * cstep) + (j & 1);   // adjacent chunk pairs: 16 channels = one 32-byte sector
         if (c < n_chunks) {                               // warp-uniform
           const int ch0 = c * 8;
           float v[8];
@@ -378,7 +413,15 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
                            pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
           } else if (valid) {
             const size_t opix = (static_cast<size_t>(tl.n) * p.out_H + (y * p.out_sy + p.out_oy)) * p.out_W + (x * p.out_sx + p.out_ox);
-            if (p.store_mode == kStoreF32Planar) {
+            const int smode = ST_T == 2 ? static_cast<int>(kStoreDirect32) : p.store_mode;
+            if (smode == kStoreDirect32) {
+              // whole 32-byte sectors per lane (16 channels): no partial-sector writes reach L2
+              uint4 o;
+              o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]); o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+              if ((j & 1) == 0) held = o;
+              else if (ch0 < p.n_store)
+                st_global_v8(reinterpret_cast<__nv_bfloat16*>(p.out) + opix * p.out_C + p.out_coff + ch0 - 8, held, o);
+            } else if (smode == kStoreF32Planar) {
               if (c == 0) reinterpret_cast<float*>(p.out)[opix] = v[0];
             } else {
 #pragma unroll
@@ -420,6 +463,7 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
     }
   }
 
+done:
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -431,7 +475,7 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
 
 size_t conv_smem_bytes(const ConvParams& p) {
   return 1024 /*alignment slack*/ + static_cast<size_t>(p.n_slots) * p.slot_bytes + static_cast<size_t>(p.n_acc) * p.stage_bytes +
-         ((p.w_bytes + 127) & ~127) + 256 /*bias*/ + 8 * (9 + 2 * p.n_slots) + 16;
+         ((p.w_bytes + 127) & ~127) + 256 /*bias*/ + 8 * (9 + 2 * p.n_slots) + 32;
 }
 
 template <int KW_T, int PW_T, int ACT_T, int RES_T, int ST_T>
@@ -460,22 +504,24 @@ static int launch_t(const ConvParams& p, const CUtensorMap& tmap, int num_sms, c
 
 int launch_conv_tc(const ConvParams& p, const CUtensorMap& tmap, int num_sms, cudaStream_t stream) {
   const int res = (p.r1 ? 1 : 0) | (p.r2 ? 2 : 0) | (p.gate ? 4 : 0);
-  const bool staged = p.store_mode == kStoreStaged;
   if ((res & 6) == 6) return static_cast<int>(cudaErrorInvalidValue);   // r2 and gate share an operand slot
-#define CSR_CASE(KW_, PW_, ACT_, RES_)                                                                     \
-  if (staged && !p.force_generic && p.KW == KW_ && p.PW == PW_ && p.act == ACT_ && res == RES_)            \
-    return launch_t<KW_, PW_, ACT_, RES_, 1>(p, tmap, num_sms, stream);
+#define CSR_CASE(KW_, PW_, ACT_, RES_, ST_)                                                                  \
+  if (p.store_mode == (ST_ == 1 ? kStoreStaged : kStoreDirect32) && !p.force_generic && p.KW == KW_ && p.PW == PW_ && \
+      p.act == ACT_ && res == RES_)                                                                          \
+    return launch_t<KW_, PW_, ACT_, RES_, ST_>(p, tmap, num_sms, stream);
   // the layer shapes of the generator forward (esrgan.py / srcnn.py) ...
-  CSR_CASE(3, 1, 1, 0)   // RDB conv1-4, HRconv: lrelu
-  CSR_CASE(3, 1, 0, 0)   // conv_first
-  CSR_CASE(3, 1, 0, 1)   // RDB conv5 (*0.2 + x), trunk_conv (+ fea)
-  CSR_CASE(3, 1, 0, 3)   // RDB3 conv5 (*0.2 + x, *0.2 + x_rrdb)
-  CSR_CASE(2, 0, 1, 0)   // upconv sub-pixel phases
-  CSR_CASE(2, 1, 1, 0)
-  CSR_CASE(1, 0, 2, 0)   // srcnn.conv1 (x-im2col folded), srcnn.conv2: relu
+  CSR_CASE(3, 1, 1, 0, 1)   // RDB conv1-4, HRconv: lrelu
+  CSR_CASE(3, 1, 0, 0, 1)   // conv_first
+  CSR_CASE(3, 1, 0, 1, 1)   // RDB conv5 (*0.2 + x), trunk_conv (+ fea)
+  CSR_CASE(3, 1, 0, 3, 1)   // RDB3 conv5 (*0.2 + x, *0.2 + x_rrdb)
+  CSR_CASE(3, 1, 0, 1, 2)   // ... the same with unstaged stores (weights leave no room for staging + a deep window ring)
+  CSR_CASE(3, 1, 0, 3, 2)
+  CSR_CASE(2, 0, 1, 0, 1)   // upconv sub-pixel phases
+  CSR_CASE(2, 1, 1, 0, 1)
+  CSR_CASE(1, 0, 2, 0, 1)   // srcnn.conv1 (x-im2col folded), srcnn.conv2: relu
   // ... and of its backward (input-gradient convs: accumulate in place, LeakyReLU-derivative gate)
-  CSR_CASE(3, 1, 0, 5)
-  CSR_CASE(3, 1, 0, 4)
+  CSR_CASE(3, 1, 0, 5, 1)
+  CSR_CASE(3, 1, 0, 4, 1)
 #undef CSR_CASE
   switch (p.KW) {
     case 1: return launch_t<1, 0, -1, -1, -1>(p, tmap, num_sms, stream);

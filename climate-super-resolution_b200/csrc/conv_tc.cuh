@@ -8,7 +8,8 @@ namespace csr {
 
 constexpr int kEpilogueWarps = 16;    // four warps per TMEM lane quadrant, each owning every 4th 8-channel chunk
 constexpr int kEpilogueThreads = kEpilogueWarps * 32;
-constexpr int kConvThreads = 64 + kEpilogueThreads;   // warp0 TMA producer, warp1 MMA issuer (+TMEM alloc), then epilogue
+constexpr int kMmaWarps = 2;          // MMA issuer warps taking alternate tiles
+constexpr int kConvThreads = 32 * (1 + kMmaWarps) + kEpilogueThreads;   // warp0 TMA producer, warps 1-2 MMA issuers, then epilogue
 constexpr int kTileM = 128;           // window positions (UMMA M) per tile = TH * SW
 constexpr int kSmemLimit = 232448;    // 227 KB opt-in dynamic shared memory per CTA on sm_100
 constexpr int kMaxNpad = 64;          // output channels per launch part (epilogue: <= 2 chunks of 8 per warp)
@@ -17,7 +18,9 @@ enum StoreMode {
   kStoreStaged = 0,     // bf16 NHWC through a swizzled shared-memory staging tile, copied out as whole pixel rows
   kStoreDirect = 1,     // bf16 NHWC, per-element global stores (ragged channel counts)
   kStoreF32Planar = 2,  // fp32 (N,1,H,W), channel 0 only
-  kStoreF32Nhwc = 3     // fp32 NHWC (n_store channels per pixel, pitch out_C): gradient / debug outputs
+  kStoreF32Nhwc = 3,    // fp32 NHWC (n_store channels per pixel, pitch out_C): gradient / debug outputs
+  kStoreDirect32 = 4    // bf16 NHWC, one 32-byte store per lane and 16-channel chunk pair straight from registers
+                        // (no staging; n_store, out_C and out_coff multiples of 16)
 };
 
 struct ConvParams {
@@ -39,6 +42,7 @@ struct ConvParams {
   int n_kblocks;   // ceil(cin / 64)
   int n_slots;     // activation-window ring depth
   int w_bytes;     // packed weights: KH * (cin/16) * KW * npad * 32
+  int n_mma;       // MMA issuer warps in use (2; 1 = debug)
   int n_acc;       // accumulator buffers in TMEM == epilogue warp groups (2 or 4); n_acc * KW * npad <= 512
   int tmem_cols;   // power of two >= max(32, n_acc*KW*npad)
   int force_generic;  // debug: skip the compile-time specialised kernels
