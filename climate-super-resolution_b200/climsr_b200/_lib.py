@@ -31,13 +31,19 @@ class ConvDesc(C.Structure):
                 ("gate_c", C.c_int32), ("gate_coff", C.c_int32), ("gate_from", C.c_int32), ("gate_neg", C.c_float)]
 
 
+class WgradDesc(C.Structure):
+    _fields_ = [("n", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("cin", C.c_int32), ("cout", C.c_int32),
+                ("kh", C.c_int32), ("kw", C.c_int32), ("x_c", C.c_int32), ("x_coff", C.c_int32), ("g_c", C.c_int32),
+                ("g_coff", C.c_int32), ("in_up2", C.c_int32), ("scale", C.c_float)]
+
+
 def _load():
     if not os.path.exists(LIB_PATH):
         raise CsrError(f"{LIB_PATH} is missing: build it with `python climate-super-resolution_b200/build.py` "
                        "(no CPU fallback exists for this path)")
     L = C.CDLL(LIB_PATH)
     vp, i32, sz, f32 = C.c_void_p, C.c_int32, C.c_size_t, C.c_float
-    nd, cd = C.POINTER(NetDesc), C.POINTER(ConvDesc)
+    nd, cd, wd = C.POINTER(NetDesc), C.POINTER(ConvDesc), C.POINTER(WgradDesc)
     sig = {
         "csr_abi_version": (C.c_int, []),
         "csr_last_error": (C.c_char_p, []),
@@ -57,6 +63,8 @@ def _load():
         "csr_generator_forward": (C.c_int, [nd, vp, vp, vp, vp, vp, vp, sz, i32, i32, i32, vp]),
         "csr_conv2d_scratch_bytes": (sz, [cd]),
         "csr_conv2d_nhwc": (C.c_int, [cd, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]),
+        "csr_conv2d_wgrad_scratch_bytes": (sz, [wd]),
+        "csr_conv2d_wgrad": (C.c_int, [wd, vp, vp, vp, vp, vp, sz, vp]),
         "csr_nchw_f32_to_nhwc_bf16": (C.c_int, [vp, vp, i32, i32, i32, i32, i32, i32, vp]),
         "csr_nhwc_bf16_to_nchw_f32": (C.c_int, [vp, vp, i32, i32, i32, i32, i32, i32, vp]),
         "csr_metrics_scratch_bytes": (sz, [i32, i32, i32]),
@@ -73,7 +81,7 @@ lib = _load()
 EXPORTS = ("csr_abi_version", "csr_last_error", "csr_device_check", "csr_set_option", "csr_kernel_launch_count", "csr_debug_set_trace", "csr_num_layers",
            "csr_layer_shape", "csr_packed_weight_bytes", "csr_pack_weights", "csr_workspace_bytes", "csr_plan_create",
            "csr_plan_forward", "csr_plan_num_launches", "csr_plan_destroy", "csr_generator_forward", "csr_conv2d_scratch_bytes",
-           "csr_conv2d_nhwc", "csr_nchw_f32_to_nhwc_bf16", "csr_nhwc_bf16_to_nchw_f32", "csr_metrics_scratch_bytes",
+           "csr_conv2d_nhwc", "csr_conv2d_wgrad_scratch_bytes", "csr_conv2d_wgrad", "csr_nchw_f32_to_nhwc_bf16", "csr_nhwc_bf16_to_nchw_f32", "csr_metrics_scratch_bytes",
            "csr_masked_metrics")
 
 

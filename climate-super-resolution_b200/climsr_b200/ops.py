@@ -7,7 +7,7 @@ from typing import Optional
 import torch
 from torch import Tensor
 
-from ._lib import ConvDesc, check, current_stream_ptr, lib
+from ._lib import ConvDesc, WgradDesc, check, current_stream_ptr, lib
 
 ACT = {"none": 0, "lrelu": 1, "relu": 2}
 OUT_MODE = {"nhwc": 0, "f32_planar": 2, "f32_nhwc": 3}
@@ -70,3 +70,21 @@ def conv2d_nhwc(inp: Tensor, weight: Tensor, bias: Optional[Tensor], *, act: str
                               gate.data_ptr() if gate is not None else None,
                               scratch.data_ptr(), nbytes, current_stream_ptr()), "csr_conv2d_nhwc")
     return out
+
+
+def conv2d_wgrad(x: Tensor, g: Tensor, weight_shape, *, x_coff: int = 0, g_coff: int = 0, in_up2: bool = False, scale: float = 1.0,
+                 dw: Optional[Tensor] = None, db: Optional[Tensor] = None, want_bias: bool = True):
+    """Weight / bias gradient of a KxK 'same' conv: x (n,h,w,Cx) bf16 input, g (n,h,w,Cg) bf16 output gradient
+    (2h x 2w when in_up2).  Accumulates into dw (cout,cin,kh,kw) / db (cout) fp32 (allocated zeroed when None)."""
+    n, h, w, x_c = x.shape
+    cout, cin, kh, kw = weight_shape
+    if dw is None:
+        dw = torch.zeros(weight_shape, dtype=torch.float32, device=x.device)
+    if db is None and want_bias:
+        db = torch.zeros((cout,), dtype=torch.float32, device=x.device)
+    d = WgradDesc(n, h, w, cin, cout, kh, kw, x_c, x_coff, g.shape[-1], g_coff, int(in_up2), scale)
+    nbytes = lib.csr_conv2d_wgrad_scratch_bytes(C.byref(d))
+    scratch = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=x.device)
+    check(lib.csr_conv2d_wgrad(C.byref(d), x.data_ptr(), g.data_ptr(), dw.data_ptr(), db.data_ptr() if db is not None else None,
+                               scratch.data_ptr(), nbytes, current_stream_ptr()), "csr_conv2d_wgrad")
+    return dw, db

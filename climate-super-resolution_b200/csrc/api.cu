@@ -12,6 +12,7 @@
 #include "conv_tc.cuh"
 #include "elementwise.cuh"
 #include "metrics.cuh"
+#include "wgrad_tc.cuh"
 
 namespace csr {
 
@@ -26,6 +27,7 @@ static int g_opt_no_tma_store = 0;
 static int g_opt_two_acc = 0;
 static int g_opt_force_generic = 0;
 static int g_opt_one_mma = 0;
+static int g_dbg_wgrad[5] = {0, 0, 0, 0, 0};   // a_lbo, a_sbo, b_lbo, b_sbo, flags overrides of the MN-major descriptors
 static int g_opt_no_direct32 = 1;   // measured: no gain over staging on cfg2 (tools/ab_bench.py), kept as an option
 
 static int fail(int code, const char* fmt, ...) {
@@ -312,6 +314,133 @@ static int build_conv(const PackLayer& pl, const PackPart& pp, int N, int H, int
   return encode_act_map(&cl->tmap, io.in, N, H, W, io.in_C, p.SW, p.win_rows);
 }
 
+// ------------------------------------------------------------------------------------------- weight gradient
+struct WgradLaunch {
+  WgradParams p;
+  CUtensorMap tx0, tx1, tg0, tg1;
+};
+
+// One vertical tap of one 128-input-channel chunk: x channels [xc0, xc0+128) (beyond the buffer pitch -> zeros), output
+// gradients gA channels [gA_c0, +64) and optionally gB channels [gB_c0, +64) as GEMM columns [0,64) / [64,128).
+static int build_wgrad(int N, int H, int W, int KW, int PW, int dy_off, const void* x, int x_C, int xc0, const void* gA, int gA_C, int gA_c0,
+                       const void* gB, int gB_C, int gB_c0, int n_cols, float* dacc, int ld_n, WgradLaunch* wl) {
+  if (n_cols % 16 || n_cols < 16 || n_cols > 128) return fail(CSR_ERR_UNSUPPORTED, "wgrad: n_cols %d", n_cols);
+  if (x_C % 8 || gA_C % 8 || xc0 % 8 || gA_c0 % 8) return fail(CSR_ERR_BAD_ARG, "wgrad: channel pitch/offset must be multiples of 8");
+  WgradParams& p = wl->p;
+  memset(&p, 0, sizeof(p));
+  p.N = N; p.H = H; p.W = W; p.KW = KW; p.PW = PW; p.dy_off = dy_off;
+  double best = -1;
+  for (int SW = 16; SW <= 32; SW *= 2) {
+    const int TW = SW - (KW - 1);
+    if (TW < 1) continue;
+    const int TH = 128 / SW;
+    const double eff = (double)H * W / ((double)ceil_div(H, TH) * ceil_div(W, TW) * 128);
+    if (eff > best) { best = eff; p.SW = SW; p.TH = TH; p.TW = TW; }
+  }
+  if (best < 0) return fail(CSR_ERR_UNSUPPORTED, "wgrad: kernel width %d too large", KW);
+  while ((1 << p.sw_shift) < p.SW) ++p.sw_shift;
+  p.tiles_x = ceil_div(W, p.TW); p.tiles_y = ceil_div(H, p.TH);
+  p.tiles_per_img = p.tiles_x * p.tiles_y;
+  p.num_tiles = p.tiles_per_img * N;
+  if ((long long)p.tiles_per_img * N >= (1 << 24) || p.tiles_per_img >= (1 << 16)) return fail(CSR_ERR_UNSUPPORTED, "wgrad: too many tiles");
+  p.magic_img = ((1ull << 40) / (unsigned)p.tiles_per_img) + 1;
+  p.magic_row = ((1ull << 40) / (unsigned)p.tiles_x) + 1;
+  p.n_xbox = 2; p.n_gbox = gB ? 2 : 1; p.M = 128; p.n_cols = n_cols;
+  p.x_box_bytes = (p.TH + 1) * p.SW * 128;
+  p.g_box_bytes = p.TH * p.SW * 128;
+  p.x_slack = 1024;
+  p.stage_bytes = p.n_xbox * (p.x_slack + p.x_box_bytes) + p.n_gbox * p.g_box_bytes;
+  p.n_stages = std::min(4, (kSmemLimit - 2048) / p.stage_bytes);
+  if (p.n_stages < 1) return fail(CSR_ERR_UNSUPPORTED, "wgrad: stage does not fit shared memory");
+  int cols = 32;
+  while (cols < KW * n_cols) cols *= 2;
+  if (cols > 512) return fail(CSR_ERR_UNSUPPORTED, "wgrad: KW*n_cols = %d exceeds TMEM", KW * n_cols);
+  p.tmem_cols = cols;
+  p.xc0[0] = xc0; p.xc0[1] = xc0 + 64;
+  p.gc0[0] = gA_c0; p.gc0[1] = gB_c0;
+  p.dacc = dacc; p.ld_n = ld_n;
+  p.dbg_a_lbo = g_dbg_wgrad[0]; p.dbg_a_sbo = g_dbg_wgrad[1]; p.dbg_b_lbo = g_dbg_wgrad[2]; p.dbg_b_sbo = g_dbg_wgrad[3];
+  p.dbg_flags = g_dbg_wgrad[4];
+  int rc = encode_act_map(&wl->tx0, x, N, H, W, x_C, p.SW, p.TH + 1);
+  if (rc) return rc;
+  wl->tx1 = wl->tx0;
+  rc = encode_act_map(&wl->tg0, gA, N, H, W, gA_C, p.SW, p.TH);
+  if (rc) return rc;
+  wl->tg1 = wl->tg0;
+  if (gB) {
+    rc = encode_act_map(&wl->tg1, gB, N, H, W, gB_C, p.SW, p.TH);
+    if (rc) return rc;
+  }
+  return CSR_OK;
+}
+
+// Weight (and bias) gradient of one conv layer, accumulated into dw / db (fp32 OIHW / (cout)):
+//   dw += scale * sum_p g[p][co] x[p + tap][ci]   over executed taps; see wgrad_scatter_kernel for fold / phase.
+// x: (N,H,W,x_C) bf16 (the layer's INPUT, low resolution for an up2 layer); g: gradient w.r.t. the layer's pre-activation
+// output.  For phase >= 0, g is the (2H, 2W) buffer and the phase's pixels are read through a strided view.
+struct WgradLayer {
+  int cout, cin, kh, kw, fold, up2;
+};
+static size_t wgrad_scratch_floats(const WgradLayer& L) {
+  const int ekh = L.up2 ? 2 : L.kh, ekw = L.up2 ? 2 : (L.fold ? 1 : L.kw);
+  const int ld_n = (L.cout + 15) / 16 * 16;
+  return (size_t)ekh * ekw * 128 * ld_n;
+}
+
+static int encode_phase_map(CUtensorMap* m, const void* base, int N, int H, int W, int C, int phase, int box_w, int box_h) {
+  // pixels (2y + a, 2x + b) of an (N, 2H, 2W, C) buffer as an (N, H, W, C) tensor
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return fail(CSR_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  const int a = phase >> 1, b = phase & 1;
+  const uint8_t* bp = reinterpret_cast<const uint8_t*>(base) + ((size_t)a * 2 * W + b) * C * 2;
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)2 * C * 2, (cuuint64_t)2 * 2 * W * C * 2, (cuuint64_t)4 * H * W * C * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<uint8_t*>(bp), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(CSR_ERR_CUDA, "cuTensorMapEncodeTiled (phase view) failed (%d)", (int)r);
+  return CSR_OK;
+}
+
+static int run_wgrad_layer(const WgradLayer& L, int N, int H, int W, const void* x, int x_C, int x_coff, const void* g, int g_C, int g_coff,
+                           float scale, float* dw, float* db, float* scratch, int sms, cudaStream_t s, long long* launches) {
+  const int ld_n = (L.cout + 15) / 16 * 16;
+  if (ld_n > 128) return fail(CSR_ERR_UNSUPPORTED, "wgrad: cout %d > 128", L.cout);
+  const int ecin = L.fold ? L.cin * L.kw : L.cin;
+  const int ekh = L.up2 ? 2 : L.kh, ekw = L.up2 ? 2 : (L.fold ? 1 : L.kw);
+  const size_t nfl = (size_t)ekh * ekw * 128 * ld_n;
+  for (int phase = L.up2 ? 0 : -1; phase < (L.up2 ? 4 : 0); ++phase) {
+    const int ph = L.up2 ? 1 - (phase >> 1) : L.kh / 2;
+    const int pw = L.up2 ? 1 - (phase & 1) : (L.fold ? 0 : L.kw / 2);
+    for (int ci0 = 0; ci0 < ecin; ci0 += 128) {
+      CSR_CUDA(cudaMemsetAsync(scratch, 0, nfl * sizeof(float), s));
+      for (int dy = 0; dy < ekh; ++dy) {
+        WgradLaunch wl;
+        int rc = build_wgrad(N, H, W, ekw, pw, dy - ph, x, x_C, x_coff + ci0, g, g_C, g_coff, nullptr, 0, 0, ld_n,
+                             scratch + (size_t)dy * ekw * 128 * ld_n, ld_n, &wl);
+        if (rc) return rc;
+        if (phase >= 0) {
+          rc = encode_phase_map(&wl.tg0, g, N, H, W, g_C, phase, wl.p.SW, wl.p.TH);
+          if (rc) return rc;
+          wl.tg1 = wl.tg0;
+        }
+        int e = launch_wgrad_tc(wl.p, wl.tx0, wl.tx1, wl.tg0, wl.tg1, sms, s);
+        if (e) return fail(CSR_ERR_CUDA, "wgrad launch failed: %s", cudaGetErrorString((cudaError_t)e));
+        ++*launches;
+      }
+      CSR_CUDA(launch_wgrad_scatter(scratch, ld_n, dw, L.cout, L.cin, L.kh, L.kw, L.fold, phase, ci0, std::min(128, ecin - ci0), 0, scale, s));
+      ++*launches;
+    }
+  }
+  if (db) {
+    const long npix = (long)N * H * W * (L.up2 ? 4 : 1);
+    CSR_CUDA(launch_bias_grad(g, npix, g_C, g_coff, L.cout, scale, db, s));
+    ++*launches;
+  }
+  return CSR_OK;
+}
+
 // ------------------------------------------------------------------------------------------- plan
 }  // namespace csr
 
@@ -472,6 +601,7 @@ int csr_set_option(int32_t key, int32_t value) {
     case 6: g_opt_force_generic = value ? 1 : 0; return CSR_OK;
     case 7: g_opt_one_mma = value ? 1 : 0; return CSR_OK;
     case 8: g_opt_no_direct32 = value ? 1 : 0; return CSR_OK;    // 0: allow unstaged 32-byte stores when staging starves the window ring        // debug: a single MMA issuer warp  // debug: runtime-switched kernels only        // debug: never use four accumulator buffers   // debug: per-element global stores instead of the staged copy-out
+    case 20: case 21: case 22: case 23: case 24: g_dbg_wgrad[key - 20] = value; return CSR_OK;
     default: return fail(CSR_ERR_BAD_ARG, "unknown option key %d", key);
   }
 }
@@ -648,6 +778,31 @@ int csr_conv2d_nhwc(const CsrConvDesc* d, const void* in, const float* weight, c
     g_launches += 3;
   }
   return CSR_OK;
+}
+
+// ---- single-layer weight gradient (building block; used by the parity tests) ---------------------------
+size_t csr_conv2d_wgrad_scratch_bytes(const CsrWgradDesc* d) {
+  if (!d || d->cout < 1 || d->cout > 128) return 0;
+  WgradLayer L = {d->cout, d->cin, d->kh, d->kw, 0, d->in_up2 ? 1 : 0};
+  return wgrad_scratch_floats(L) * sizeof(float);
+}
+
+int csr_conv2d_wgrad(const CsrWgradDesc* d, const void* x, const void* g, float* dw, float* db, void* scratch, size_t scratch_bytes,
+                     void* stream) {
+  if (!d || !x || !g || !dw || !scratch) return fail(CSR_ERR_BAD_ARG, "null pointer");
+  if (d->n < 1 || d->h < 1 || d->w < 1 || d->cin < 1 || d->cout < 1 || d->cout > 128) return fail(CSR_ERR_BAD_ARG, "bad wgrad shape");
+  if (!(d->kh & 1) || !(d->kw & 1) || d->kh > 9 || d->kw > 9) return fail(CSR_ERR_UNSUPPORTED, "kernel %dx%d", d->kh, d->kw);
+  if (d->in_up2 && (d->kh != 3 || d->kw != 3)) return fail(CSR_ERR_UNSUPPORTED, "nearest-x2 input needs a 3x3 kernel");
+  WgradLayer L = {d->cout, d->cin, d->kh, d->kw, 0, d->in_up2 ? 1 : 0};
+  if (scratch_bytes < wgrad_scratch_floats(L) * sizeof(float)) return fail(CSR_ERR_WORKSPACE, "wgrad scratch too small");
+  DeviceInfo di;
+  int rc = device_info(&di);
+  if (rc) return rc;
+  long long launches = 0;
+  rc = run_wgrad_layer(L, d->n, d->h, d->w, x, d->x_c, d->x_coff, g, d->g_c, d->g_coff, d->scale, dw, db, reinterpret_cast<float*>(scratch),
+                       di.sms, reinterpret_cast<cudaStream_t>(stream), &launches);
+  g_launches += launches;
+  return rc;
 }
 
 // ---- layout helpers -----------------------------------------------------------------------------------

@@ -149,6 +149,87 @@ __global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ src, float
   }
 }
 
+// ---- weight-gradient post-processing ---------------------------------------------------------------------
+// dacc: fp32 [KH_e][KW_e][128][ld_n] sums produced by wgrad_tc_kernel (executed taps KH_e x KW_e, rows = executed input
+// channel - ci0, columns = output channel + col0).  Adds scale * dacc into the layer's OIHW gradient:
+//   plain : dw[co][ci][dy][dx]                          += dacc[dy][dx][ci - ci0][col0 + co]
+//   fold  : dw[co][c][dy][dx]  (executed channel dx*cin+c, KW_e = 1)  += dacc[dy][0][dx*cin + c - ci0][col0 + co]
+//   phase : executed 2x2 taps (ry, rx) of sub-pixel phase (a,b) feed every 3x3 tap they were summed from
+__global__ void wgrad_scatter_kernel(const float* __restrict__ dacc, int ld_n, float* __restrict__ dw, int cout, int cin, int kh, int kw,
+                                     int fold, int phase, int ci0, int ci_n, int col0, float scale) {
+  const int ekh = phase >= 0 ? 2 : kh;
+  const int ekw = phase >= 0 ? 2 : (fold ? 1 : kw);
+  const long total = static_cast<long>(ekh) * ekw * ci_n * cout;
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const int co = i % cout;
+    long r = i / cout;
+    const int cl = r % ci_n;                               // executed input channel - ci0
+    r /= ci_n;
+    const int dx = r % ekw, dy = r / ekw;
+    const float v = scale * dacc[((static_cast<long>(dy) * ekw + dx) * 128 + cl) * ld_n + col0 + co];
+    const int ce = ci0 + cl;                               // executed input channel
+    if (phase >= 0) {
+      if (ce >= cin) continue;
+      int y0, y1, x0, x1;
+      phase_taps(phase >> 1, dy, &y0, &y1);
+      phase_taps(phase & 1, dx, &x0, &x1);
+      for (int yy = y0; yy <= y1; ++yy)
+        for (int xx = x0; xx <= x1; ++xx) atomicAdd(&dw[((static_cast<long>(co) * cin + ce) * kh + yy) * kw + xx], v);
+    } else if (fold) {
+      if (ce >= cin * kw) continue;
+      const int fx = ce / cin, c = ce - fx * cin;
+      dw[((static_cast<long>(co) * cin + c) * kh + dy) * kw + fx] += v;
+    } else {
+      if (ce >= cin) continue;
+      dw[((static_cast<long>(co) * cin + ce) * kh + dy) * kw + dx] += v;
+    }
+  }
+}
+
+// db[co] += scale * sum over pixels of g[p][coff + co]   (bf16 NHWC, pitch C).  One block per pixel range, fp32 atomics.
+__global__ void bias_grad_kernel(const __nv_bfloat16* __restrict__ g, long npix, int C, int coff, int cout, float scale, float* __restrict__ db) {
+  extern __shared__ float red[];                           // [blockDim.x / cout_pad rows][cout_pad]
+  const int cpad = (cout + 7) & ~7;
+  const int lanes_per_pix = cpad >> 3;                     // one thread loads 8 channels (16 B)
+  const int pix_per_iter = blockDim.x / lanes_per_pix;
+  const int sub = threadIdx.x % lanes_per_pix, prow = threadIdx.x / lanes_per_pix;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (prow < pix_per_iter) {
+    for (long pix = blockIdx.x * static_cast<long>(pix_per_iter) + prow; pix < npix; pix += static_cast<long>(gridDim.x) * pix_per_iter) {
+      const uint4 v = *reinterpret_cast<const uint4*>(g + pix * C + coff + sub * 8);
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        acc[2 * k] += bf16lo(w[k]);
+        acc[2 * k + 1] += bf16hi(w[k]);
+      }
+    }
+  }
+  for (int k = 0; k < 8; ++k) red[threadIdx.x * 8 + k] = acc[k];
+  __syncthreads();
+  if (threadIdx.x < cout) {
+    const int s2 = threadIdx.x >> 3, k = threadIdx.x & 7;
+    float t = 0.f;
+    for (int r = 0; r < pix_per_iter; ++r) t += red[(r * lanes_per_pix + s2) * 8 + k];
+    atomicAdd(&db[threadIdx.x], scale * t);
+  }
+}
+
+// db[0] += scale * sum(g) for an fp32 planar single-channel gradient
+__global__ void bias_grad_planar_kernel(const float* __restrict__ g, long n, float scale, float* __restrict__ db) {
+  float acc = 0.f;
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n; i += static_cast<long>(gridDim.x) * blockDim.x) acc += g[i];
+  for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  __shared__ float part[32];
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t = threadIdx.x < (blockDim.x >> 5) ? part[threadIdx.x] : 0.f;
+    for (int o = 16; o; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (threadIdx.x == 0) atomicAdd(db, scale * t);
+  }
+}
+
 static inline int grid_for(long total, int block, int cap = 148 * 16) {
   long g = (total + block - 1) / block;
   if (g > cap) g = cap;
@@ -183,6 +264,22 @@ cudaError_t launch_nhwc_to_nchw(const void* src, float* dst, int n, int c, int h
   const long per = static_cast<long>(h) * w, total = per * n * c;
   nhwc_to_nchw_kernel<<<grid_for(total, 256), 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(src), dst, per, total, c, src_c,
                                                            src_coff);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_wgrad_scatter(const float* dacc, int ld_n, float* dw, int cout, int cin, int kh, int kw, int fold, int phase, int ci0,
+                                 int ci_n, int col0, float scale, cudaStream_t s) {
+  const int ekh = phase >= 0 ? 2 : kh, ekw = phase >= 0 ? 2 : (fold ? 1 : kw);
+  const long total = static_cast<long>(ekh) * ekw * ci_n * cout;
+  wgrad_scatter_kernel<<<grid_for(total, 256), 256, 0, s>>>(dacc, ld_n, dw, cout, cin, kh, kw, fold, phase, ci0, ci_n, col0, scale);
+  return cudaGetLastError();
+}
+cudaError_t launch_bias_grad(const void* g, long npix, int C, int coff, int cout, float scale, float* db, cudaStream_t s) {
+  bias_grad_kernel<<<148 * 2, 256, 256 * 8 * sizeof(float), s>>>(reinterpret_cast<const __nv_bfloat16*>(g), npix, C, coff, cout, scale, db);
+  return cudaGetLastError();
+}
+cudaError_t launch_bias_grad_planar(const float* g, long n, float scale, float* db, cudaStream_t s) {
+  bias_grad_planar_kernel<<<148 * 2, 256, 0, s>>>(g, n, scale, db);
   return cudaGetLastError();
 }
 

@@ -134,6 +134,23 @@ int     csr_conv2d_nhwc(const CsrConvDesc* d, const void* in, const float* weigh
                         void* out, const void* res1, const void* res2, const void* gate,
                         void* scratch, size_t scratch_bytes, void* stream);
 
+/* ---- single-layer weight gradient (building block of csr_plan_backward; used by the parity tests) ---
+ * dw (cout,cin,kh,kw) += scale * d/dW of conv2d(x, W) against the output gradient g;  db (cout) += scale * sum(g).
+ * x: bf16 NHWC (n,h,w,x_c), input channels [x_coff, x_coff+cin);  g: bf16 NHWC gradient w.r.t. the conv output,
+ * channels [g_coff, g_coff+cout), spatial (h,w) - or (2h,2w) when in_up2 (nearest-x2 applied to x first).
+ * <- autograd of nn.Conv2d (convolution_backward, weight part) at every call site of esrgan.py:33-38,90-100.      */
+typedef struct CsrWgradDesc {
+  int32_t n, h, w;
+  int32_t cin, cout, kh, kw;
+  int32_t x_c, x_coff;
+  int32_t g_c, g_coff;
+  int32_t in_up2;
+  float   scale;
+} CsrWgradDesc;
+size_t  csr_conv2d_wgrad_scratch_bytes(const CsrWgradDesc* d);
+int     csr_conv2d_wgrad(const CsrWgradDesc* d, const void* x, const void* g, float* dw, float* db,
+                         void* scratch, size_t scratch_bytes, void* stream);
+
 /* ---- layout helpers -------------------------------------------------------------------------- */
 /* fp32 NCHW (n,c,h,w) -> bf16 NHWC (n,h,w,dst_c) channels [0,c), channels [c, zero_to) zeroed.  */
 int     csr_nchw_f32_to_nhwc_bf16(const float* src, void* dst, int32_t n, int32_t c, int32_t h, int32_t w,
