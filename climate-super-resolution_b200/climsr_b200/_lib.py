@@ -60,6 +60,12 @@ def _load():
         "csr_plan_forward": (C.c_int, [vp, vp, vp, vp, vp, vp, vp]),
         "csr_plan_num_launches": (C.c_int, [vp]),
         "csr_plan_destroy": (None, [vp]),
+        "csr_train_workspace_bytes": (sz, [nd, i32, i32, i32]),
+        "csr_train_plan_create": (C.c_int, [nd, i32, i32, i32, vp, sz, C.POINTER(vp)]),
+        "csr_packed_weight_bytes_bwd": (sz, [nd]),
+        "csr_pack_weights_bwd": (C.c_int, [nd, C.POINTER(vp), vp, sz, vp]),
+        "csr_plan_backward": (C.c_int, [vp, vp, vp, C.POINTER(vp), C.POINTER(vp), vp]),
+        "csr_plan_num_backward_ops": (C.c_int, [vp]),
         "csr_generator_forward": (C.c_int, [nd, vp, vp, vp, vp, vp, vp, sz, i32, i32, i32, vp]),
         "csr_conv2d_scratch_bytes": (sz, [cd]),
         "csr_conv2d_nhwc": (C.c_int, [cd, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]),
@@ -80,7 +86,8 @@ def _load():
 lib = _load()
 EXPORTS = ("csr_abi_version", "csr_last_error", "csr_device_check", "csr_set_option", "csr_kernel_launch_count", "csr_debug_set_trace", "csr_num_layers",
            "csr_layer_shape", "csr_packed_weight_bytes", "csr_pack_weights", "csr_workspace_bytes", "csr_plan_create",
-           "csr_plan_forward", "csr_plan_num_launches", "csr_plan_destroy", "csr_generator_forward", "csr_conv2d_scratch_bytes",
+           "csr_plan_forward", "csr_plan_num_launches", "csr_plan_destroy", "csr_train_workspace_bytes", "csr_train_plan_create",
+           "csr_packed_weight_bytes_bwd", "csr_pack_weights_bwd", "csr_plan_backward", "csr_plan_num_backward_ops", "csr_generator_forward", "csr_conv2d_scratch_bytes",
            "csr_conv2d_nhwc", "csr_conv2d_wgrad_scratch_bytes", "csr_conv2d_wgrad", "csr_nchw_f32_to_nhwc_bf16", "csr_nhwc_bf16_to_nchw_f32", "csr_metrics_scratch_bytes",
            "csr_masked_metrics")
 

@@ -1,9 +1,64 @@
-"""Training path of the generator (autograd through the CUDA forward).  Backward kernels: not built yet."""
+"""Training path of the generator: torch.autograd.Function over csr_plan_forward / csr_plan_backward.
+
+Replaces the autograd graph PyTorch would record for ESRGANGenerator.forward (climsr/models/esrgan.py:89-102) when
+Lightning calls loss.backward() (climsr/task/pl_generator_pre_training.py:18-33).  Forward runs on a *training plan*
+(every dense block keeps its concat buffer, the HR tail keeps its activations); backward runs the input-gradient convs
+(same tcgen05 conv kernel, transposed/flipped weight packs) and the weight-gradient GEMMs and hands fp32 gradients of
+all 2*L parameters back to autograd, so optimizers / DDP / gradient clipping see ordinary ``.grad`` tensors.
+Gradients w.r.t. x, elev and mask are not produced (they are data in the reference's training loop).
+"""
 from __future__ import annotations
 
-from ._lib import CsrError
+import ctypes as C
+
+import torch
+
+from ._lib import CsrError, check, current_stream_ptr, lib
+
+
+class GeneratorFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, module, x, elev, mask, *params):
+        n, _, h, w = x.shape
+        dev = x.device
+        xs = x.detach().contiguous().float()
+        es = elev.detach().to(dev).contiguous().float()
+        ms = mask.detach().to(dev).contiguous().float()
+        packed = module.packed_weights()
+        plan = module._plan(n, h, w, dev, train=True)
+        out = torch.empty((n, 1, 4 * h, 4 * w), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            check(lib.csr_plan_forward(plan, packed.data_ptr(), xs.data_ptr(), es.data_ptr(), ms.data_ptr(), out.data_ptr(),
+                                       current_stream_ptr()), "csr_plan_forward")
+        module._fwd_serial += 1
+        ctx.module, ctx.plan, ctx.serial, ctx.dev = module, plan, module._fwd_serial, dev
+        ctx.shapes = [tuple(p.shape) for p in params]
+        ctx.set_materialize_grads(False)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        module = ctx.module
+        n_in = 4 + len(ctx.shapes)
+        if grad_out is None:
+            return (None,) * n_in
+        if ctx.serial != module._fwd_serial:
+            raise CsrError("climsr_b200: backward() must follow the forward() that produced this output (the training plan keeps "
+                           "the saved activations of the latest forward only)")
+        dev = ctx.dev
+        go = grad_out.detach().contiguous().float()
+        packed_bwd = module.packed_weights_bwd()
+        n = len(ctx.shapes) // 2
+        grads = [torch.zeros(s, dtype=torch.float32, device=dev) for s in ctx.shapes]
+        dw, db = (C.c_void_p * n)(), (C.c_void_p * n)()
+        for i in range(n):
+            dw[i], db[i] = grads[2 * i].data_ptr(), grads[2 * i + 1].data_ptr()
+        with torch.cuda.device(dev):
+            check(lib.csr_plan_backward(ctx.plan, packed_bwd.data_ptr(), go.data_ptr(), dw, db, current_stream_ptr()), "csr_plan_backward")
+        return (None, None, None, None) + tuple(grads)
 
 
 def generator_apply(module, x, elev, mask):
-    raise CsrError("climsr_b200: generator backward (dgrad/wgrad kernels) is not implemented yet; "
-                   "call the generator under torch.no_grad() / module.eval() with requires_grad_(False)")
+    pairs = module._ordered_params()
+    flat = [p for wb in pairs for p in wb]
+    return GeneratorFunction.apply(module, x, elev, mask, *flat)

@@ -78,6 +78,9 @@ class ESRGANGenerator(nn.Module):
         self._packed: Optional[Tensor] = None
         self._packed_key: Optional[Tuple] = None
         self._plans: Dict[Tuple, Tuple[int, Tensor]] = {}
+        self._packed_bwd: Optional[Tensor] = None
+        self._packed_bwd_key: Optional[Tuple] = None
+        self._fwd_serial = 0
 
     # ------------------------------------------------------------------ weights
     def _ordered_params(self):
@@ -124,18 +127,42 @@ class ESRGANGenerator(nn.Module):
         self._packed_key = key
         return self._packed
 
+    def packed_weights_bwd(self) -> Tensor:
+        """Transposed / flipped bf16 tiles for the input-gradient convs; rebuilt when any weight changed."""
+        pairs = self._ordered_params()
+        dev = pairs[0][0].device
+        key = (dev,) + tuple((w.data_ptr(), w._version) for w, _ in pairs)
+        if self._packed_bwd is not None and key == self._packed_bwd_key:
+            return self._packed_bwd
+        nbytes = lib.csr_packed_weight_bytes_bwd(C.byref(self._desc))
+        if self._packed_bwd is None or self._packed_bwd.device != dev:
+            self._packed_bwd = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        n = len(pairs)
+        keep = []
+        wp = (C.c_void_p * n)()
+        for i, (w, _) in enumerate(pairs):
+            wc = w.detach().contiguous().float()
+            keep.append(wc)
+            wp[i] = wc.data_ptr()
+        with torch.cuda.device(dev):
+            check(lib.csr_pack_weights_bwd(C.byref(self._desc), wp, self._packed_bwd.data_ptr(), nbytes, current_stream_ptr()),
+                  "csr_pack_weights_bwd")
+        self._packed_bwd_key = key
+        return self._packed_bwd
+
     # ------------------------------------------------------------------ plan cache
-    def _plan(self, n: int, h: int, w: int, dev: torch.device):
-        key = (n, h, w, dev)
+    def _plan(self, n: int, h: int, w: int, dev: torch.device, train: bool = False):
+        key = (n, h, w, dev, train)
         hit = self._plans.get(key)
         if hit is not None:
             return hit[0]
-        nbytes = lib.csr_workspace_bytes(C.byref(self._desc), n, h, w)
+        nbytes = (lib.csr_train_workspace_bytes if train else lib.csr_workspace_bytes)(C.byref(self._desc), n, h, w)
         ws = torch.empty(nbytes + 1024, dtype=torch.uint8, device=dev)
         base = (ws.data_ptr() + 1023) // 1024 * 1024
         plan = C.c_void_p()
         with torch.cuda.device(dev):
-            check(lib.csr_plan_create(C.byref(self._desc), n, h, w, base, nbytes, C.byref(plan)), "csr_plan_create")
+            create = lib.csr_train_plan_create if train else lib.csr_plan_create
+            check(create(C.byref(self._desc), n, h, w, base, nbytes, C.byref(plan)), "csr_plan_create")
         if len(self._plans) >= 4:   # bound the cached workspaces
             for _, (p, _t) in list(self._plans.items()):
                 lib.csr_plan_destroy(p)

@@ -102,6 +102,8 @@ struct LayerSpec {
   int up2 = 0;             // 1: the layer's input is nearest-x2 upsampled first (esrgan.py:94,97): executed as four
                            //    sub-pixel phases, each a 2x2 conv over the low-resolution input with summed weights
   int transposed = 0;      // 1: input-gradient conv: weight read as w[ci][co][KH-1-dy][KW-1-dx] (autograd of the layer)
+  float wscale = 1.f;      // constant folded into the packed weights
+  int src = -1;            // backward tables: index of the forward layer whose weight tensor is packed
   int ekw() const { return fold ? 1 : kw; }
   int ecin() const { return fold ? cin * kw : cin; }
 };
@@ -172,8 +174,9 @@ static std::vector<PackLayer> pack_layout(const std::vector<LayerSpec>& layers, 
       for (int lo = 0; lo < npad_full; lo += per) {
         PackPart pp;
         pp.kh = kh; pp.kw = kw;
-        pp.ph = L.up2 ? 1 - (phase >> 1) : L.kh / 2;
-        pp.pw = L.up2 ? 1 - (phase & 1) : L.ekw() / 2;
+        // sub-pixel phase (a,b): rows (y-1+a, y+a) -> PH = 1-a; its input gradient is the flipped correlation -> PH' = a
+        pp.ph = L.up2 ? (L.transposed ? (phase >> 1) : 1 - (phase >> 1)) : L.kh / 2;
+        pp.pw = L.up2 ? (L.transposed ? (phase & 1) : 1 - (phase & 1)) : L.ekw() / 2;
         pp.phase = phase;
         pp.co_lo = lo;
         pp.npad = std::min(per, npad_full - lo);
@@ -444,23 +447,45 @@ static int run_wgrad_layer(const WgradLayer& L, int N, int H, int W, const void*
 // ------------------------------------------------------------------------------------------- plan
 }  // namespace csr
 
+// Backward op list entry (training plans).
+struct BwdOp {
+  enum Kind { kConv, kWgrad, kScatter, kBias, kBiasPlanar, kScale, kMemset, kGoutPack } kind;
+  csr::ConvLaunch conv;          // kConv (dgrad); w_off/b_off index the BACKWARD packed blob
+  csr::WgradLaunch wg;           // kWgrad
+  // kScatter / kBias*: which forward layer's gradient, and how
+  int layer = -1, fold = 0, phase = -1, ci0 = 0, ci_n = 0, col0 = 0, ld_n = 0;
+  float scale = 1.f;
+  const void* src = nullptr; void* dst = nullptr;   // kScale (bf16 NHWC 64 ch: dst = scale*src), kBias (g buffer), kMemset
+  long count = 0; int C = 0, coff = 0, cout = 0;
+};
+
 struct CsrPlan {
   CsrNetDesc net;
   int N, h, w;
   int sms;
-  std::vector<csr::ConvLaunch> convs;   // in execution order
+  int train = 0;
+  std::vector<csr::ConvLaunch> convs;   // forward, in execution order
   int idx_srcnn1;                       // the SRCNN x-im2col pack kernel runs right before this conv
   void* xin; void* sin; float* tlast;
   size_t packed_bytes;
+  // training
+  std::vector<BwdOp> bwd;
+  std::vector<csr::LayerSpec> fwd_layers;
+  void* gout_nhwc = nullptr;            // (N,H,W,16) bf16: dL/dout in channel 0
+  float* dacc = nullptr;                // fp32 scratch of the weight-gradient GEMMs
+  size_t packed_bwd_bytes = 0;
 };
 
 namespace csr {
 
 struct WsLayout {
-  size_t xin, fea0, cat[3], t0, m1, hrA, hrB, hrC, tlast, total;
+  size_t xin, fea0, t0, m1, hrA, hrB, hrC, hrD, hrE, tlast, total;
+  std::vector<size_t> cat;              // 3 rotating concat buffers (inference) or one per RDB + 1 (training: saved state)
+  // training only
+  size_t gO, gT, gP, gQ, gm1, gt0, gtmp, gcat[3], dacc;
   int ccat;
 };
-static WsLayout ws_layout(const CsrNetDesc& d, int N, int h, int w) {
+static WsLayout ws_layout(const CsrNetDesc& d, int N, int h, int w, int train) {
   WsLayout L;
   const size_t lr = (size_t)N * h * w, mid = lr * 4, hr = lr * 16;
   L.ccat = (int)align_up(d.nf + 4 * d.gc, 64);
@@ -468,27 +493,53 @@ static WsLayout ws_layout(const CsrNetDesc& d, int N, int h, int w) {
   auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 1024); return o; };
   L.xin = take(lr * 64 * 2);
   L.fea0 = take(lr * 64 * 2);
-  for (int i = 0; i < 3; ++i) L.cat[i] = take(lr * L.ccat * 2);
+  const int ncat = train ? 3 * d.nb + 1 : 3;
+  for (int i = 0; i < ncat; ++i) L.cat.push_back(take(lr * L.ccat * 2));
   L.t0 = take(lr * 64 * 2);    // trunk_conv + skip
   L.m1 = take(mid * 64 * 2);   // upconv1 output (2h x 2w)
-  L.hrA = take(hr * 64 * 2);   // upconv2 output, later srcnn.conv1 output
-  L.hrB = take(hr * 64 * 2);   // HRconv output, later srcnn.conv2 output
+  L.hrA = take(hr * 64 * 2);   // upconv2 output
+  L.hrB = take(hr * 64 * 2);   // HRconv output
   L.hrC = take(hr * 64 * 2);   // SRCNN input [out, elev, mask] x 9 horizontal taps
   L.tlast = take(hr * 4);      // conv_last output, fp32 planar
+  if (train) {
+    L.hrD = take(hr * 64 * 2); // srcnn.conv1 output (inference: reuses hrA)
+    L.hrE = take(hr * 64 * 2); // srcnn.conv2 output (inference: reuses hrB)
+    L.gO = take(hr * 16 * 2);  // dL/dout, channel 0 of a 16-channel pitch
+    L.gT = take(hr * 16 * 2);  // dL/d(conv_last output), channel 0
+    L.gP = take(hr * 64 * 2);  // ping-pong gradient maps of the HR tail
+    L.gQ = take(hr * 64 * 2);
+    L.gm1 = take(mid * 64 * 2);
+    L.gt0 = take(lr * 64 * 2);
+    L.gtmp = take(lr * 64 * 2);
+    for (int i = 0; i < 3; ++i) L.gcat[i] = take(lr * L.ccat * 2);
+    L.dacc = take((size_t)9 * 128 * 128 * 4 * 2);
+  } else {
+    L.hrD = L.hrA; L.hrE = L.hrB;
+    L.gO = L.gT = L.gP = L.gQ = L.gm1 = L.gt0 = L.gtmp = L.dacc = 0;
+    L.gcat[0] = L.gcat[1] = L.gcat[2] = 0;
+  }
   L.total = off;
   return L;
+}
+
+static ConvIO io_of(const void* in, int in_C, void* out, int out_C, int out_coff, int act) {
+  ConvIO io;
+  io.in = in; io.in_C = in_C; io.out = out; io.out_C = out_C; io.out_coff = out_coff; io.act = act;
+  return io;
 }
 
 static int plan_build(CsrPlan* P, void* ws) {
   const CsrNetDesc& d = P->net;
   const int N = P->N, h = P->h, w = P->w;
-  const WsLayout L = ws_layout(d, N, h, w);
+  const WsLayout L = ws_layout(d, N, h, w, P->train);
   uint8_t* base = reinterpret_cast<uint8_t*>(ws);
   void* xin = base + L.xin; void* fea0 = base + L.fea0;
-  void* cat[3] = {base + L.cat[0], base + L.cat[1], base + L.cat[2]};
+  auto cat = [&](int j) -> void* { return base + L.cat[P->train ? j : j % 3]; };
   void* t0 = base + L.t0; void* m1 = base + L.m1; void* hrA = base + L.hrA; void* hrB = base + L.hrB; void* hrC = base + L.hrC;
+  void* hrD = base + L.hrD; void* hrE = base + L.hrE;
   P->xin = xin; P->sin = hrC; P->tlast = reinterpret_cast<float*>(base + L.tlast);
   const std::vector<LayerSpec> layers = layer_table(d);
+  P->fwd_layers = layers;
   size_t total = 0;
   const std::vector<PackLayer> packs = pack_layout(layers, &total);
   P->packed_bytes = total;
@@ -505,40 +556,38 @@ static int plan_build(CsrPlan* P, void* ws) {
     if (advance) ++li;
     return CSR_OK;
   };
-  auto io_of = [](const void* in, int in_C, void* out, int out_C, int out_coff, int act) {
-    ConvIO io;
-    io.in = in; io.in_C = in_C; io.out = out; io.out_C = out_C; io.out_coff = out_coff; io.act = act;
-    return io;
-  };
   int rc;
-  // conv_first (esrgan.py:90) has two consumers: the first RRDB (reads x from concat buffer A) and the trunk skip-add
-  // 33 layers later (A is overwritten by then).  The layer is tiny (K = 16), so it is simply run into both places.
+  // conv_first (esrgan.py:90) has two consumers: the first RRDB (reads x from its concat buffer) and the trunk skip-add
+  // 33 layers later.  The layer is tiny (K = 16), so it is simply run into both places.
   rc = add(h, w, io_of(xin, 64, fea0, 64, 0, CSR_ACT_NONE), false);
   if (rc) return rc;
-  rc = add(h, w, io_of(xin, 64, cat[0], C, 0, CSR_ACT_NONE));
+  rc = add(h, w, io_of(xin, 64, cat(0), C, 0, CSR_ACT_NONE));
   if (rc) return rc;
   for (int i = 0; i < d.nb; ++i) {
-    // RRDB i: its input x lives in channels [0,nf) of concat buffer A; the three RDBs rotate A->B->C->A, so A's x
-    // survives until RDB3's epilogue reads it as the RRDB residual and overwrites it in place.
+    // RRDB i: its input x lives in channels [0,nf) of concat buffer 3i.  Inference rotates three buffers A->B->C->A, so
+    // A's x survives until RDB3's epilogue reads it as the RRDB residual and overwrites it in place; training keeps one
+    // buffer per RDB (the saved activations of the backward pass).
     for (int r = 0; r < 3; ++r) {
-      void* src = cat[r];
-      void* dst = cat[(r + 1) % 3];
+      const int j = 3 * i + r;
+      void* src = cat(j);
+      void* dst = P->train ? cat(j + 1) : (r < 2 ? cat(j + 1) : cat(3 * i));
       for (int k = 1; k <= 4; ++k) {
         // x_k = lrelu(conv_k(cat(x, x1..x_{k-1})))  written into its concat slice  (esrgan.py:33-36)
         rc = add(h, w, io_of(src, C, src, C, nf + (k - 1) * gc, CSR_ACT_LRELU02));
         if (rc) return rc;
       }
       // x5*0.2 + x  (esrgan.py:37-38); RDB3 additionally applies the RRDB residual out*0.2 + x_rrdb (esrgan.py:54)
-      ConvIO io = io_of(src, C, r < 2 ? dst : cat[0], C, 0, CSR_ACT_NONE);
+      ConvIO io = io_of(src, C, dst, C, 0, CSR_ACT_NONE);
       io.r1 = src; io.r1_C = C; io.s1 = 0.2f;
-      if (r == 2) { io.r2 = cat[0]; io.r2_C = C; io.s2 = 0.2f; }
+      if (r == 2) { io.r2 = cat(3 * i); io.r2_C = C; io.s2 = 0.2f; }
       rc = add(h, w, io);
       if (rc) return rc;
     }
   }
+  void* trunk_out = P->train ? cat(3 * d.nb) : cat(0);
   // trunk_conv + skip (esrgan.py:91-92)
   {
-    ConvIO io = io_of(cat[0], C, t0, 64, 0, CSR_ACT_NONE);
+    ConvIO io = io_of(trunk_out, C, t0, 64, 0, CSR_ACT_NONE);
     io.r1 = fea0; io.r1_C = 64; io.s1 = 1.f;
     rc = add(h, w, io);
     if (rc) return rc;
@@ -559,18 +608,282 @@ static int plan_build(CsrPlan* P, void* ws) {
     if (rc) return rc;
   }
   P->idx_srcnn1 = (int)P->convs.size();
-  rc = add(H, W, io_of(hrC, 64, hrA, 64, 0, CSR_ACT_RELU));     // srcnn.conv1 (9x1 folded)
+  rc = add(H, W, io_of(hrC, 64, hrD, 64, 0, CSR_ACT_RELU));     // srcnn.conv1 (9x1 folded)
   if (rc) return rc;
-  rc = add(H, W, io_of(hrA, 64, hrB, 64, 0, CSR_ACT_RELU));     // srcnn.conv2 1x1
+  rc = add(H, W, io_of(hrD, 64, hrE, 64, 0, CSR_ACT_RELU));     // srcnn.conv2 1x1
   if (rc) return rc;
   {
-    ConvIO io = io_of(hrB, 64, nullptr, 1, 0, CSR_ACT_NONE);    // srcnn.conv3 5x5 -> the caller's output tensor
+    ConvIO io = io_of(hrE, 64, nullptr, 1, 0, CSR_ACT_NONE);    // srcnn.conv3 5x5 -> the caller's output tensor
     io.out_kind = kOutF32Planar;
     rc = add(H, W, io);
     if (rc) return rc;
     P->convs.back().final_out = true;
   }
   return rc;
+}
+
+// ------------------------------------------------------------------------------------------- backward plan
+// Backward layer table: one input-gradient conv per forward layer that needs it, in the order they are packed.
+//   index 3*nb*5 ... see bwd_layer_table(); `src` = forward layer index whose OIHW weight is packed transposed.
+static int fwd_index_rdb(int i, int r, int k) { return 1 + (i * 3 + r) * 5 + (k - 1); }   // conv_first is layer 0
+
+static std::vector<LayerSpec> bwd_layer_table(const CsrNetDesc& d, const std::vector<LayerSpec>& f) {
+  std::vector<LayerSpec> v;
+  auto T = [&](int src, float wscale, int up2 = 0) {
+    LayerSpec L = f[src];
+    LayerSpec t;
+    t.name = L.name + ".dgrad";
+    t.cout = L.cin; t.cin = L.cout; t.kh = L.kh; t.kw = L.kw;
+    t.fold = 0; t.up2 = up2; t.transposed = 1; t.wscale = wscale; t.src = src;
+    v.push_back(t);
+  };
+  const int base_tail = 1 + d.nb * 15;                    // trunk_conv
+  // order of use in csr_plan_backward: srcnn.conv3, conv2, conv1, conv_last, HRconv, upconv2, upconv1, trunk_conv, RDBs reversed
+  T(base_tail + 7, 1.f);                                  // srcnn.conv3
+  T(base_tail + 6, 1.f);                                  // srcnn.conv2
+  T(base_tail + 5, 1.f);                                  // srcnn.conv1 (un-folded 9x9 transposed; only d/d(out) = channel 0 is used)
+  T(base_tail + 4, 1.f);                                  // conv_last
+  T(base_tail + 3, 1.f);                                  // HRconv
+  T(base_tail + 2, 1.f, 1);                               // upconv2 (four transposed sub-pixel phases)
+  T(base_tail + 1, 1.f, 1);                               // upconv1
+  T(base_tail + 0, 1.f);                                  // trunk_conv
+  for (int i = d.nb - 1; i >= 0; --i)
+    for (int r = 2; r >= 0; --r) {
+      T(fwd_index_rdb(i, r, 5), 0.2f);                    // conv5: d(x5*0.2 + x)/dx5 folded into the weights
+      for (int k = 4; k >= 1; --k) T(fwd_index_rdb(i, r, k), 1.f);
+    }
+  return v;
+}
+
+static int bwd_build(CsrPlan* P, void* ws) {
+  const CsrNetDesc& d = P->net;
+  const int N = P->N, h = P->h, w = P->w, H = 4 * h, W = 4 * w;
+  const WsLayout L = ws_layout(d, N, h, w, 1);
+  uint8_t* base = reinterpret_cast<uint8_t*>(ws);
+  auto cat = [&](int j) -> void* { return base + L.cat[j]; };
+  void* xin = base + L.xin;
+  void* t0 = base + L.t0; void* m1 = base + L.m1; void* hrA = base + L.hrA; void* hrB = base + L.hrB; void* hrC = base + L.hrC;
+  void* hrD = base + L.hrD; void* hrE = base + L.hrE;
+  void* gO = base + L.gO; void* gT = base + L.gT; void* gP = base + L.gP; void* gQ = base + L.gQ; void* gm1 = base + L.gm1;
+  void* gt0 = base + L.gt0; void* gtmp = base + L.gtmp;
+  void* gcat[3] = {base + L.gcat[0], base + L.gcat[1], base + L.gcat[2]};
+  float* dacc = reinterpret_cast<float*>(base + L.dacc);
+  P->gout_nhwc = gO; P->dacc = dacc;
+  const std::vector<LayerSpec>& F = P->fwd_layers;
+  const std::vector<LayerSpec> B = bwd_layer_table(d, F);
+  size_t total = 0;
+  const std::vector<PackLayer> packs = pack_layout(B, &total);
+  P->packed_bwd_bytes = total;
+  const int C = L.ccat, nf = d.nf, gc = d.gc;
+  const int base_tail = 1 + d.nb * 15;
+  int bi = 0;                                             // next backward layer
+  std::vector<BwdOp>& ops = P->bwd;
+
+  auto dgrad = [&](int Hh, int Ww, const ConvIO& io, const void* phase_src = nullptr, int src_H = 0, int src_W = 0) -> int {
+    const PackLayer& pl = packs[bi];
+    const bool up2 = B[bi].up2 != 0;
+    int launch = 0;
+    for (const PackPart& pp : pl.parts) {
+      BwdOp op;
+      op.kind = BwdOp::kConv;
+      ConvIO io2 = io;
+      if (up2) {
+        // phases accumulate into the same low-resolution gradient: first writes, later ones add, the last one gates
+        if (pp.phase > 0) { io2.r1 = io.out; io2.r1_C = io.out_C; io2.r1_coff = io.out_coff; io2.s1 = 1.f; }
+        if (pp.phase < 3) io2.gate = nullptr;
+      }
+      // build as a plain (non-up2) conv on the low-resolution grid: output view is dense, INPUT view is the strided phase
+      PackPart q = pp;
+      if (up2) q.phase = -1;
+      int rc = build_conv(pl, q, N, Hh, Ww, io2, &op.conv);
+      if (rc) return rc;
+      if (up2) {
+        rc = encode_phase_map(&op.conv.tmap, phase_src, N, Hh, Ww, io.in_C, pp.phase, op.conv.p.SW, op.conv.p.win_rows);
+        if (rc) return rc;
+      }
+      ops.push_back(op);
+      ++launch;
+    }
+    ++bi;
+    return CSR_OK;
+  };
+  auto wgrad_plain = [&](int layer, int Hh, int Ww, const void* x, int x_C, int x_coff, const void* g, int g_C, int g_coff, float scale,
+                         bool planar_bias = false, const float* gplanar = nullptr) -> int {
+    const LayerSpec& Ls = F[layer];
+    const int ld_n = (Ls.cout + 15) / 16 * 16;
+    const int ecin = Ls.fold ? Ls.cin * Ls.kw : Ls.cin;
+    const int ekh = Ls.up2 ? 2 : Ls.kh, ekw = Ls.up2 ? 2 : (Ls.fold ? 1 : Ls.kw);
+    for (int phase = Ls.up2 ? 0 : -1; phase < (Ls.up2 ? 4 : 0); ++phase) {
+      const int ph = Ls.up2 ? 1 - (phase >> 1) : Ls.kh / 2;
+      const int pw = Ls.up2 ? 1 - (phase & 1) : (Ls.fold ? 0 : Ls.kw / 2);
+      for (int ci0 = 0; ci0 < ecin; ci0 += 128) {
+        BwdOp ms; ms.kind = BwdOp::kMemset; ms.dst = dacc; ms.count = (long)ekh * ekw * 128 * ld_n * 4;
+        ops.push_back(ms);
+        for (int dy = 0; dy < ekh; ++dy) {
+          BwdOp op; op.kind = BwdOp::kWgrad;
+          int rc = build_wgrad(N, Hh, Ww, ekw, pw, dy - ph, x, x_C, x_coff + ci0, g, g_C, g_coff, nullptr, 0, 0, ld_n,
+                               dacc + (size_t)dy * ekw * 128 * ld_n, ld_n, &op.wg);
+          if (rc) return rc;
+          if (phase >= 0) {
+            rc = encode_phase_map(&op.wg.tg0, g, N, Hh, Ww, g_C, phase, op.wg.p.SW, op.wg.p.TH);
+            if (rc) return rc;
+            op.wg.tg1 = op.wg.tg0;
+          }
+          ops.push_back(op);
+        }
+        BwdOp sc; sc.kind = BwdOp::kScatter; sc.layer = layer; sc.fold = Ls.fold; sc.phase = phase; sc.ci0 = ci0;
+        sc.ci_n = std::min(128, ecin - ci0); sc.col0 = 0; sc.ld_n = ld_n; sc.scale = scale;
+        ops.push_back(sc);
+      }
+    }
+    BwdOp bo;
+    if (planar_bias) {
+      bo.kind = BwdOp::kBiasPlanar; bo.layer = layer; bo.src = gplanar; bo.count = (long)N * H * W; bo.scale = scale;
+    } else {
+      bo.kind = BwdOp::kBias; bo.layer = layer; bo.src = g; bo.count = (long)N * Hh * Ww * (Ls.up2 ? 4 : 1); bo.C = g_C; bo.coff = g_coff;
+      bo.cout = Ls.cout; bo.scale = scale;
+    }
+    ops.push_back(bo);
+    return CSR_OK;
+  };
+  auto gated = [&](ConvIO io, const void* gate, int gate_C, int gate_coff, int gate_from, float neg) {
+    io.gate = gate; io.gate_C = gate_C; io.gate_coff = gate_coff; io.gate_from = gate_from; io.gate_neg = neg;
+    return io;
+  };
+  auto accum = [&](ConvIO io) {
+    io.r1 = io.out; io.r1_C = io.out_C; io.r1_coff = io.out_coff; io.s1 = 1.f;
+    return io;
+  };
+
+  int rc;
+  // ---- SRCNN tail (srcnn.py:13-18) -------------------------------------------------------------------------------
+  { BwdOp op; op.kind = BwdOp::kGoutPack; ops.push_back(op); }                        // dL/dout fp32 planar -> gO channel 0
+  rc = wgrad_plain(base_tail + 7, H, W, hrE, 64, 0, gO, 16, 0, 1.f);                  // srcnn.conv3
+  if (rc) return rc;
+  rc = dgrad(H, W, gated(io_of(gO, 16, gP, 64, 0, CSR_ACT_NONE), hrE, 64, 0, 0, 0.f));  // -> d/d relu(conv2) * relu'
+  if (rc) return rc;
+  rc = wgrad_plain(base_tail + 6, H, W, hrD, 64, 0, gP, 64, 0, 1.f);                  // srcnn.conv2
+  if (rc) return rc;
+  rc = dgrad(H, W, gated(io_of(gP, 64, gQ, 64, 0, CSR_ACT_NONE), hrD, 64, 0, 0, 0.f));
+  if (rc) return rc;
+  rc = wgrad_plain(base_tail + 5, H, W, hrC, 64, 0, gQ, 64, 0, 1.f);                  // srcnn.conv1 (folded 9x1 over 27 ch)
+  if (rc) return rc;
+  rc = dgrad(H, W, io_of(gQ, 64, gT, 16, 0, CSR_ACT_NONE));                           // d/d[out, elev, mask]; channel 0 is used
+  if (rc) return rc;
+  // ---- conv_last, HRconv (esrgan.py:99) ----------------------------------------------------------------------------
+  rc = wgrad_plain(base_tail + 4, H, W, hrB, 64, 0, gT, 16, 0, 1.f);
+  if (rc) return rc;
+  rc = dgrad(H, W, gated(io_of(gT, 16, gP, 64, 0, CSR_ACT_NONE), hrB, 64, 0, 0, 0.2f));
+  if (rc) return rc;
+  rc = wgrad_plain(base_tail + 3, H, W, hrA, 64, 0, gP, 64, 0, 1.f);
+  if (rc) return rc;
+  rc = dgrad(H, W, gated(io_of(gP, 64, gQ, 64, 0, CSR_ACT_NONE), hrA, 64, 0, 0, 0.2f));
+  if (rc) return rc;
+  // ---- upconv2 / upconv1 (esrgan.py:94,97): nearest-x2 + conv, transposed phase by phase ---------------------------
+  rc = wgrad_plain(base_tail + 2, 2 * h, 2 * w, m1, 64, 0, gQ, 64, 0, 1.f);
+  if (rc) return rc;
+  rc = dgrad(2 * h, 2 * w, gated(io_of(gQ, 64, gm1, 64, 0, CSR_ACT_NONE), m1, 64, 0, 0, 0.2f), gQ);
+  if (rc) return rc;
+  rc = wgrad_plain(base_tail + 1, h, w, t0, 64, 0, gm1, 64, 0, 1.f);
+  if (rc) return rc;
+  rc = dgrad(h, w, io_of(gm1, 64, gt0, 64, 0, CSR_ACT_NONE), gm1);
+  if (rc) return rc;
+  // ---- trunk_conv + skip (esrgan.py:91-92): gt0 is also the skip-path gradient of conv_first's output --------------
+  rc = wgrad_plain(base_tail + 0, h, w, cat(3 * d.nb), C, 0, gt0, 64, 0, 1.f);
+  if (rc) return rc;
+  int Pb = 0;                                             // gcat buffer whose channels [0,64) hold dL/d(RRDB output)
+  rc = dgrad(h, w, io_of(gt0, 64, gcat[Pb], C, 0, CSR_ACT_NONE));
+  if (rc) return rc;
+  // ---- RRDB trunk, reversed (esrgan.py:32-38, 50-54) ----------------------------------------------------------------
+  for (int i = d.nb - 1; i >= 0; --i) {
+    const int Qb = (Pb + 1) % 3, Rb = (Pb + 2) % 3;
+    // out = RDB3_out*0.2 + x_rrdb: the gradient entering RDB3 is 0.2*G
+    { BwdOp op; op.kind = BwdOp::kScale; op.src = gcat[Pb]; op.C = C; op.dst = gtmp; op.count = (long)N * h * w; op.scale = 0.2f; ops.push_back(op); }
+    const void* gin = gtmp; int gin_C = 64;
+    int outb[3] = {Qb, Rb, Qb};                           // RDB3 -> Q, RDB2 -> R, RDB1 -> Q (free again)
+    for (int r = 2; r >= 0; --r) {
+      const int j = 3 * i + r;
+      void* gc_ = gcat[outb[2 - r]];
+      // conv5 dgrad (weights pre-scaled by 0.2) + identity path: channels [0,64) += g_out; slice 4 becomes final -> gate
+      {
+        ConvIO io = gated(io_of(gin, gin_C, gc_, C, 0, CSR_ACT_NONE), cat(j), C, 0, nf + 3 * gc, 0.2f);
+        io.r1 = gin; io.r1_C = gin_C; io.r1_coff = 0; io.s1 = 1.f;
+        // r1 only exists for channels [0,64): build_conv offsets it per part, so restrict it to the first part below
+        const PackLayer& pl = packs[bi];
+        for (const PackPart& pp : pl.parts) {
+          BwdOp op; op.kind = BwdOp::kConv;
+          ConvIO io2 = io;
+          if (pp.co_lo >= nf) io2.r1 = nullptr;
+          if (pp.co_lo + pp.n_store <= nf + 3 * gc) io2.gate = nullptr;
+          rc = build_conv(pl, pp, N, h, w, io2, &op.conv);
+          if (rc) return rc;
+          ops.push_back(op);
+        }
+        ++bi;
+      }
+      // weight gradients of the whole dense block as ONE GEMM per vertical tap: x = the block's concat buffer (128 ch),
+      // g columns [0,64) = gated gradients of x1..x4 (concat-gradient slices), columns [64,128) = g_out (conv5, scale 0.2)
+      // -- issued after the conv1..4 input-gradient chain below has finalised every slice.
+      for (int k = 4; k >= 1; --k) {
+        const int cin_k = nf + (k - 1) * gc;
+        ConvIO io = accum(io_of(gc_, C, gc_, C, 0, CSR_ACT_NONE));
+        io.cin_off = cin_k;                                // reads the finalised, gated slice of x_k
+        if (k >= 2) io = gated(io, cat(j), C, 0, nf + (k - 2) * gc, 0.2f);
+        if (k == 1 && r == 0) { io.r2 = gcat[Pb]; io.r2_C = C; io.r2_coff = 0; io.s2 = 1.f; }   // + G (RRDB identity path)
+        const PackLayer& pl = packs[bi];
+        for (const PackPart& pp : pl.parts) {
+          BwdOp op; op.kind = BwdOp::kConv;
+          ConvIO io2 = io;
+          if (io2.gate && pp.co_lo + pp.n_store <= io.gate_from) io2.gate = nullptr;
+          rc = build_conv(pl, pp, N, h, w, io2, &op.conv);
+          if (rc) return rc;
+          ops.push_back(op);
+        }
+        ++bi;
+      }
+      // dense-block weight gradients
+      {
+        const int ncols_a = 4 * gc;                        // x1..x4 gradient slices
+        if (C > 128 || ncols_a > 64) {
+          // gc = 32: concat pitch 192 -> per-layer weight gradients
+          for (int k = 1; k <= 4; ++k) {
+            rc = wgrad_plain(fwd_index_rdb(i, r, k), h, w, cat(j), C, 0, gc_, C, nf + (k - 1) * gc, 1.f);
+            if (rc) return rc;
+          }
+          rc = wgrad_plain(fwd_index_rdb(i, r, 5), h, w, cat(j), C, 0, gin, gin_C, 0, 0.2f);
+          if (rc) return rc;
+        } else {
+          BwdOp ms; ms.kind = BwdOp::kMemset; ms.dst = dacc; ms.count = (long)9 * 128 * 128 * 4;
+          ops.push_back(ms);
+          for (int dy = 0; dy < 3; ++dy) {
+            BwdOp op; op.kind = BwdOp::kWgrad;
+            rc = build_wgrad(N, h, w, 3, 1, dy - 1, cat(j), C, 0, gc_, C, nf, gin, gin_C, 0, 128, dacc + (size_t)dy * 3 * 128 * 128, 128, &op.wg);
+            if (rc) return rc;
+            ops.push_back(op);
+          }
+          for (int k = 1; k <= 5; ++k) {
+            const int layer = fwd_index_rdb(i, r, k);
+            BwdOp sc; sc.kind = BwdOp::kScatter; sc.layer = layer; sc.ci0 = 0; sc.ci_n = (k < 5) ? nf + (k - 1) * gc : nf + 4 * gc;
+            sc.col0 = (k < 5) ? (k - 1) * gc : 64; sc.ld_n = 128; sc.scale = (k < 5) ? 1.f : 0.2f;
+            ops.push_back(sc);
+            BwdOp bo; bo.kind = BwdOp::kBias; bo.layer = layer; bo.count = (long)N * h * w; bo.cout = F[layer].cout;
+            if (k < 5) { bo.src = gc_; bo.C = C; bo.coff = nf + (k - 1) * gc; bo.scale = 1.f; }
+            else { bo.src = gin; bo.C = gin_C; bo.coff = 0; bo.scale = 0.2f; }
+            ops.push_back(bo);
+          }
+        }
+      }
+      gin = gc_; gin_C = C;                                // channels [0,64) of this buffer = dL/d(input of RDB r) = g_out of RDB r-1
+    }
+    Pb = Qb;                                               // RDB1 wrote dL/d(RRDB input) (incl. + G) into Q[0:64]
+  }
+  // ---- conv_first (esrgan.py:90): total gradient of its output = trunk path (gcat[Pb][0:64]) + skip path (gt0) ----
+  rc = wgrad_plain(0, h, w, xin, 64, 0, gcat[Pb], C, 0, 1.f);
+  if (rc) return rc;
+  rc = wgrad_plain(0, h, w, xin, 64, 0, gt0, 64, 0, 1.f);
+  if (rc) return rc;
+  if (bi != (int)B.size()) return fail(CSR_ERR_BAD_ARG, "internal: backward table mismatch (%d of %zu)", bi, B.size());
+  return CSR_OK;
 }
 
 }  // namespace csr
@@ -651,7 +964,7 @@ int csr_pack_weights(const CsrNetDesc* net, const float* const* w, const float* 
     if (!w[i] || !b[i]) return fail(CSR_ERR_BAD_ARG, "null weight/bias pointer for layer %zu", i);
     for (const PackPart& pp : packs[i].parts) {
       CSR_CUDA(launch_pack_weight(w[i], base + pp.w_off, layers[i].cout, layers[i].cin, layers[i].kh, layers[i].kw, layers[i].fold,
-                                  pp.phase, 0, pp.co_lo, pp.npad, packs[i].cin_pad, s));
+                                  pp.phase, layers[i].transposed, layers[i].wscale, pp.co_lo, pp.npad, packs[i].cin_pad, s));
       CSR_CUDA(launch_pack_bias(b[i], reinterpret_cast<float*>(base + pp.b_off), layers[i].cout, pp.co_lo, pp.npad, s));
       g_launches += 2;
     }
@@ -661,27 +974,134 @@ int csr_pack_weights(const CsrNetDesc* net, const float* const* w, const float* 
 
 size_t csr_workspace_bytes(const CsrNetDesc* net, int32_t n, int32_t h, int32_t w) {
   if (check_net(net) || n < 1 || h < 1 || w < 1) return 0;
-  return ws_layout(*net, n, h, w).total;
+  return ws_layout(*net, n, h, w, 0).total;
 }
 
-int csr_plan_create(const CsrNetDesc* net, int32_t n, int32_t h, int32_t w, void* workspace, size_t workspace_bytes, CsrPlan** plan) {
+size_t csr_train_workspace_bytes(const CsrNetDesc* net, int32_t n, int32_t h, int32_t w) {
+  if (check_net(net) || n < 1 || h < 1 || w < 1) return 0;
+  return ws_layout(*net, n, h, w, 1).total;
+}
+
+static int plan_create_impl(const CsrNetDesc* net, int32_t n, int32_t h, int32_t w, void* workspace, size_t workspace_bytes, int train,
+                            CsrPlan** plan) {
   int rc = check_net(net);
   if (rc) return rc;
   if (!plan || !workspace) return fail(CSR_ERR_BAD_ARG, "null pointer");
   if (n < 1 || h < 1 || w < 1) return fail(CSR_ERR_BAD_ARG, "non-positive shape n=%d h=%d w=%d", n, h, w);
   if (reinterpret_cast<uintptr_t>(workspace) % 1024) return fail(CSR_ERR_BAD_ARG, "workspace must be 1024-byte aligned");
-  const size_t need = ws_layout(*net, n, h, w).total;
-  if (workspace_bytes < need) return fail(CSR_ERR_WORKSPACE, "workspace %zu < %zu bytes", workspace_bytes, need);
+  const WsLayout L = ws_layout(*net, n, h, w, train);
+  if (workspace_bytes < L.total) return fail(CSR_ERR_WORKSPACE, "workspace %zu < %zu bytes", workspace_bytes, L.total);
   DeviceInfo di;
   rc = device_info(&di);
   if (rc) return rc;
   CsrPlan* P = new CsrPlan();
-  P->net = *net; P->N = n; P->h = h; P->w = w; P->sms = di.sms;
+  P->net = *net; P->N = n; P->h = h; P->w = w; P->sms = di.sms; P->train = train;
   rc = plan_build(P, workspace);
+  if (!rc && train) {
+    rc = bwd_build(P, workspace);
+    if (!rc) {
+      // the narrow gradient maps are read 16 channels wide but written 1-3 channels wide: start them from zero
+      uint8_t* base = reinterpret_cast<uint8_t*>(workspace);
+      const size_t hr16 = (size_t)n * h * w * 16 * 16 * 2;
+      cudaError_t e = cudaMemset(base + L.gO, 0, hr16);
+      if (e == cudaSuccess) e = cudaMemset(base + L.gT, 0, hr16);
+      if (e != cudaSuccess) rc = fail(CSR_ERR_CUDA, "cudaMemset: %s", cudaGetErrorString(e));
+    }
+  }
   if (rc) { delete P; return rc; }
   *plan = P;
   return CSR_OK;
 }
+
+int csr_plan_create(const CsrNetDesc* net, int32_t n, int32_t h, int32_t w, void* workspace, size_t workspace_bytes, CsrPlan** plan) {
+  return plan_create_impl(net, n, h, w, workspace, workspace_bytes, 0, plan);
+}
+
+int csr_train_plan_create(const CsrNetDesc* net, int32_t n, int32_t h, int32_t w, void* workspace, size_t workspace_bytes, CsrPlan** plan) {
+  return plan_create_impl(net, n, h, w, workspace, workspace_bytes, 1, plan);
+}
+
+size_t csr_packed_weight_bytes_bwd(const CsrNetDesc* net) {
+  if (check_net(net)) return 0;
+  size_t total = 0;
+  pack_layout(bwd_layer_table(*net, layer_table(*net)), &total);
+  return total;
+}
+
+int csr_pack_weights_bwd(const CsrNetDesc* net, const float* const* w, void* packed, size_t packed_bytes, void* stream) {
+  int rc = check_net(net);
+  if (rc) return rc;
+  if (!w || !packed) return fail(CSR_ERR_BAD_ARG, "null pointer");
+  const auto fl = layer_table(*net);
+  const auto layers = bwd_layer_table(*net, fl);
+  size_t total = 0;
+  const auto packs = pack_layout(layers, &total);
+  if (packed_bytes < total) return fail(CSR_ERR_WORKSPACE, "packed buffer %zu < %zu bytes", packed_bytes, total);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  uint8_t* base = reinterpret_cast<uint8_t*>(packed);
+  for (size_t i = 0; i < layers.size(); ++i) {
+    const float* src = w[layers[i].src];
+    if (!src) return fail(CSR_ERR_BAD_ARG, "null weight pointer for layer %d", layers[i].src);
+    for (const PackPart& pp : packs[i].parts) {
+      CSR_CUDA(launch_pack_weight(src, base + pp.w_off, layers[i].cout, layers[i].cin, layers[i].kh, layers[i].kw, 0, pp.phase, 1,
+                                  layers[i].wscale, pp.co_lo, pp.npad, packs[i].cin_pad, s));
+      CSR_CUDA(launch_pack_bias(nullptr, reinterpret_cast<float*>(base + pp.b_off), 0, pp.co_lo, pp.npad, s));
+      g_launches += 2;
+    }
+  }
+  return CSR_OK;
+}
+
+int csr_plan_backward(CsrPlan* P, const void* packed_bwd, const float* grad_out, float* const* dw, float* const* db, void* stream) {
+  if (!P || !packed_bwd || !grad_out || !dw || !db) return fail(CSR_ERR_BAD_ARG, "null pointer");
+  if (!P->train) return fail(CSR_ERR_BAD_ARG, "csr_plan_backward needs a plan made by csr_train_plan_create");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const uint8_t* pk = reinterpret_cast<const uint8_t*>(packed_bwd);
+  const int H = 4 * P->h, W = 4 * P->w;
+  for (BwdOp& op : P->bwd) {
+    switch (op.kind) {
+      case BwdOp::kGoutPack:
+        CSR_CUDA(launch_nchw_to_nhwc(grad_out, P->gout_nhwc, P->N, 1, H, W, 16, 16, s));
+        break;
+      case BwdOp::kConv: {
+        op.conv.p.wpk = pk + op.conv.w_off;
+        op.conv.p.bias = reinterpret_cast<const float*>(pk + op.conv.b_off);
+        int e = launch_conv_tc(op.conv.p, op.conv.tmap, P->sms, s);
+        if (e) return fail(CSR_ERR_CUDA, "dgrad launch failed: %s", cudaGetErrorString((cudaError_t)e));
+        break;
+      }
+      case BwdOp::kWgrad: {
+        int e = launch_wgrad_tc(op.wg.p, op.wg.tx0, op.wg.tx1, op.wg.tg0, op.wg.tg1, P->sms, s);
+        if (e) return fail(CSR_ERR_CUDA, "wgrad launch failed: %s", cudaGetErrorString((cudaError_t)e));
+        break;
+      }
+      case BwdOp::kScatter: {
+        const LayerSpec& L = P->fwd_layers[op.layer];
+        if (!dw[op.layer]) return fail(CSR_ERR_BAD_ARG, "null weight-gradient pointer for layer %d", op.layer);
+        CSR_CUDA(launch_wgrad_scatter(P->dacc, op.ld_n, dw[op.layer], L.cout, L.cin, L.kh, L.kw, op.fold, op.phase, op.ci0, op.ci_n, op.col0,
+                                      op.scale, s));
+        break;
+      }
+      case BwdOp::kBias:
+        if (!db[op.layer]) return fail(CSR_ERR_BAD_ARG, "null bias-gradient pointer for layer %d", op.layer);
+        CSR_CUDA(launch_bias_grad(op.src, op.count, op.C, op.coff, op.cout, op.scale, db[op.layer], s));
+        break;
+      case BwdOp::kBiasPlanar:
+        CSR_CUDA(launch_bias_grad_planar(reinterpret_cast<const float*>(op.src), op.count, op.scale, db[op.layer], s));
+        break;
+      case BwdOp::kScale:
+        CSR_CUDA(launch_scale_copy64(op.src, op.C, op.dst, op.count, op.scale, s));
+        break;
+      case BwdOp::kMemset:
+        CSR_CUDA(cudaMemsetAsync(op.dst, 0, op.count, s));
+        break;
+    }
+    ++g_launches;
+  }
+  return CSR_OK;
+}
+
+int csr_plan_num_backward_ops(const CsrPlan* plan) { return plan ? (int)plan->bwd.size() : 0; }
 
 int csr_plan_num_launches(const CsrPlan* plan) { return plan ? (int)plan->convs.size() + 2 : 0; }
 
@@ -765,7 +1185,7 @@ int csr_conv2d_nhwc(const CsrConvDesc* d, const void* in, const float* weight, c
   io.r2 = res2; io.r2_C = d->res2_c; io.r2_coff = d->res2_coff; io.s2 = d->scale2;
   io.gate = gate; io.gate_C = d->gate_c; io.gate_coff = d->gate_coff; io.gate_from = d->gate_from; io.gate_neg = d->gate_neg;
   for (const PackPart& pp : packs[0].parts) {
-    CSR_CUDA(launch_pack_weight(weight, base + pp.w_off, L.cout, L.cin, L.kh, L.kw, 0, pp.phase, L.transposed, pp.co_lo, pp.npad,
+    CSR_CUDA(launch_pack_weight(weight, base + pp.w_off, L.cout, L.cin, L.kh, L.kw, 0, pp.phase, L.transposed, 1.f, pp.co_lo, pp.npad,
                                 packs[0].cin_pad, s));
     CSR_CUDA(launch_pack_bias(bias, reinterpret_cast<float*>(base + pp.b_off), bias ? L.cout : 0, pp.co_lo, pp.npad, s));
     ConvLaunch cl;

@@ -16,14 +16,16 @@ namespace csr {
 //   phase >= 0 : sub-pixel phase (a,b) = (phase>>1, phase&1) of "nearest-x2 upsample then 3x3 conv" (esrgan.py:94,97):
 //                a 2x2 conv over the low-resolution input whose tap (ry, rx) is the SUM of the 3x3 taps that land on
 //                the same source pixel: a=0: ry0<-{0}, ry1<-{1,2};  a=1: ry0<-{0,1}, ry1<-{2}  (same in x)
-//   transposed : input-gradient conv of the layer: w_src[ci][co][KH-1-dy][KW-1-dx] with w_src of shape (cin, cout, kh, kw)
+//   transposed : input-gradient conv of the layer: w_src[ci][co][KH-1-dy][KW-1-dx] with w_src of shape (cin, cout, kh, kw);
+//                combined with phase >= 0 it is the input gradient of that sub-pixel phase (flipped 2x2 summed taps)
+//   wscale     : constant folded into the packed weights (0.2 residual scaling on the gradient path)
 __device__ __forceinline__ void phase_taps(int a, int r, int* lo, int* hi) {
   if (a == 0) { *lo = r == 0 ? 0 : 1; *hi = r == 0 ? 0 : 2; }
   else        { *lo = r == 0 ? 0 : 2; *hi = r == 0 ? 1 : 2; }
 }
 
 __global__ void pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ dst, int cout, int cin, int kh,
-                                   int kw, int fold, int phase, int transposed, int co_lo, int npad, int cin_pad) {
+                                   int kw, int fold, int phase, int transposed, float wscale, int co_lo, int npad, int cin_pad) {
   // executed taps
   const int ekh = phase >= 0 ? 2 : kh;
   const int ekw = phase >= 0 ? 2 : (fold ? 1 : kw);
@@ -61,17 +63,20 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* _
         dx = ci / cin;
         ci -= dx * cin;
       }
+      // source indices: the forward layer's OIHW tensor is (cout, cin, kh, kw), or (cin, cout, kh, kw) when transposed
+      const int s_o = transposed ? ci : co, s_i = transposed ? co : ci;
+      const int s_in = transposed ? cout : cin;            // channels-per-output-filter of the source tensor
+      const int sdy = transposed ? ekh - 1 - dy : dy, sdx = transposed ? ekw - 1 - dx : dx;
       if (phase >= 0) {
         int y0, y1, x0, x1;
-        phase_taps(phase >> 1, dy, &y0, &y1);
-        phase_taps(phase & 1, dx, &x0, &x1);
+        phase_taps(phase >> 1, sdy, &y0, &y1);
+        phase_taps(phase & 1, sdx, &x0, &x1);
         for (int yy = y0; yy <= y1; ++yy)
-          for (int xx = x0; xx <= x1; ++xx) v += w[((static_cast<long>(co) * cin + ci) * kh + yy) * kw + xx];
-      } else if (transposed) {
-        v = w[((static_cast<long>(ci) * cout + co) * kh + (kh - 1 - dy)) * kw + (kw - 1 - dx)];
+          for (int xx = x0; xx <= x1; ++xx) v += w[((static_cast<long>(s_o) * s_in + s_i) * kh + yy) * kw + xx];
       } else {
-        v = w[((static_cast<long>(co) * cin + ci) * kh + dy) * kw + dx];
+        v = w[((static_cast<long>(s_o) * s_in + s_i) * kh + sdy) * kw + sdx];
       }
+      v *= wscale;
     }
     dst[i] = __float2bfloat16_rn(v);
   }
@@ -230,6 +235,23 @@ __global__ void bias_grad_planar_kernel(const float* __restrict__ g, long n, flo
   }
 }
 
+// dst[p][0:64] = scale * src[p][0:64]   (bf16 NHWC, src pitch src_C, dst pitch 64): the 0.2 of `out*0.2 + x` (esrgan.py:54)
+// on the gradient path.  One thread per 8 channels.
+__global__ void scale_copy64_kernel(const __nv_bfloat16* __restrict__ src, int src_C, __nv_bfloat16* __restrict__ dst, long npix, float scale) {
+  const long total = npix * 8;
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const long pix = i >> 3;
+    const int c8 = static_cast<int>(i & 7);
+    const uint4 v = *reinterpret_cast<const uint4*>(src + pix * src_C + c8 * 8);
+    uint4 o;
+    o.x = pack_bf16x2(bf16lo(v.x) * scale, bf16hi(v.x) * scale);
+    o.y = pack_bf16x2(bf16lo(v.y) * scale, bf16hi(v.y) * scale);
+    o.z = pack_bf16x2(bf16lo(v.z) * scale, bf16hi(v.z) * scale);
+    o.w = pack_bf16x2(bf16lo(v.w) * scale, bf16hi(v.w) * scale);
+    *reinterpret_cast<uint4*>(dst + pix * 64 + c8 * 8) = o;
+  }
+}
+
 static inline int grid_for(long total, int block, int cap = 148 * 16) {
   long g = (total + block - 1) / block;
   if (g > cap) g = cap;
@@ -238,11 +260,11 @@ static inline int grid_for(long total, int block, int cap = 148 * 16) {
 }
 
 cudaError_t launch_pack_weight(const float* w, void* dst, int cout, int cin, int kh, int kw, int fold, int phase, int transposed,
-                               int co_lo, int npad, int cin_pad, cudaStream_t s) {
+                               float wscale, int co_lo, int npad, int cin_pad, cudaStream_t s) {
   const int ekh = phase >= 0 ? 2 : kh, ekw = phase >= 0 ? 2 : (fold ? 1 : kw);
   const long total = static_cast<long>(ekh) * ekw * (cin_pad >> 4) * npad * 16;
   pack_weight_kernel<<<grid_for(total, 256), 256, 0, s>>>(w, reinterpret_cast<__nv_bfloat16*>(dst), cout, cin, kh, kw, fold, phase,
-                                                          transposed, co_lo, npad, cin_pad);
+                                                          transposed, wscale, co_lo, npad, cin_pad);
   return cudaGetLastError();
 }
 cudaError_t launch_pack_bias(const float* b, float* dst, int cout, int co_lo, int npad, cudaStream_t s) {
@@ -280,6 +302,12 @@ cudaError_t launch_bias_grad(const void* g, long npix, int C, int coff, int cout
 }
 cudaError_t launch_bias_grad_planar(const float* g, long n, float scale, float* db, cudaStream_t s) {
   bias_grad_planar_kernel<<<148 * 2, 256, 0, s>>>(g, n, scale, db);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_scale_copy64(const void* src, int src_C, void* dst, long npix, float scale, cudaStream_t s) {
+  scale_copy64_kernel<<<grid_for(npix * 8, 256), 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(src), src_C,
+                                                              reinterpret_cast<__nv_bfloat16*>(dst), npix, scale);
   return cudaGetLastError();
 }
 

@@ -3,7 +3,7 @@
 
 namespace csr {
 cudaError_t launch_pack_weight(const float* w, void* dst, int cout, int cin, int kh, int kw, int fold, int phase, int transposed,
-                               int co_lo, int npad, int cin_pad, cudaStream_t s);
+                               float wscale, int co_lo, int npad, int cin_pad, cudaStream_t s);
 cudaError_t launch_pack_bias(const float* b, float* dst, int cout, int co_lo, int npad, cudaStream_t s);
 cudaError_t launch_nchw_to_nhwc(const float* src, void* dst, int n, int c, int h, int w, int dst_c, int zero_to, cudaStream_t s);
 cudaError_t launch_pack_srcnn_in(const float* t, const float* elev, const float* mask, void* dst, int W, long total_pix, int dst_c,
@@ -13,4 +13,5 @@ cudaError_t launch_wgrad_scatter(const float* dacc, int ld_n, float* dw, int cou
                                  int ci_n, int col0, float scale, cudaStream_t s);
 cudaError_t launch_bias_grad(const void* g, long npix, int C, int coff, int cout, float scale, float* db, cudaStream_t s);
 cudaError_t launch_bias_grad_planar(const float* g, long n, float scale, float* db, cudaStream_t s);
+cudaError_t launch_scale_copy64(const void* src, int src_C, void* dst, long npix, float scale, cudaStream_t s);
 }  // namespace csr

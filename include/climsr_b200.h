@@ -126,6 +126,22 @@ int     csr_generator_forward(const CsrNetDesc* net, const void* packed, const f
                               void* workspace, size_t workspace_bytes,
                               int32_t n, int32_t h, int32_t w, void* stream);
 
+/* ---- generator training step -------------------------------------------------------------------
+ * A training plan keeps every dense block's concat buffer and the HR-tail activations (the saved state autograd would
+ * keep).  csr_plan_forward works on it unchanged; csr_plan_backward then ACCUMULATES (+=) d loss / d weight and
+ * d loss / d bias of every conv layer into dw[i] / db[i] (HOST arrays of csr_num_layers() DEVICE pointers, fp32, the
+ * parameters' OIHW / (cout) shapes) given grad_out = d loss / d out, fp32 (N,1,4h,4w).
+ * <- autograd backward of ESRGANGenerator.forward (esrgan.py:89-102), invoked by Lightning's loss.backward().       */
+size_t  csr_train_workspace_bytes(const CsrNetDesc* net, int32_t n, int32_t h, int32_t w);
+int     csr_train_plan_create(const CsrNetDesc* net, int32_t n, int32_t h, int32_t w,
+                              void* workspace, size_t workspace_bytes, CsrPlan** plan);
+size_t  csr_packed_weight_bytes_bwd(const CsrNetDesc* net);
+/* transposed / flipped bf16 weight tiles of the input-gradient convolutions (w as for csr_pack_weights)           */
+int     csr_pack_weights_bwd(const CsrNetDesc* net, const float* const* w, void* packed, size_t packed_bytes, void* stream);
+int     csr_plan_backward(CsrPlan* plan, const void* packed_bwd, const float* grad_out,
+                          float* const* dw, float* const* db, void* stream);
+int     csr_plan_num_backward_ops(const CsrPlan* plan);
+
 /* ---- single convolution (building block; used by the parity tests) --------------------------
  * in: bf16 NHWC (n,h,w,in_c); weight fp32 OIHW (cout,cin,kh,kw); bias fp32 (cout) or NULL (= zeros).
  * scratch: >= csr_conv2d_scratch_bytes() device bytes for the packed weights.                   */
