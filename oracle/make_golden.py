@@ -12,7 +12,7 @@ has no /root/reference; tests there read only the committed .npz files.
 Fixtures
   gen_tiny_refinit.npz  - reference ctor + torch.manual_seed(0) default init (nb=1, gc=16, in=2 as in
                           tests/models/test_esrgan.py:10-12); FULL state_dict + inputs + output + L1 grads of
-                          three representative weights.
+                          three representative weights + MSE-loss grads (all biases, six weights, all norms).
   gen_hydra_seeded.npz  - Hydra cfg (nb=11, gc=16, in=4) with oracle.synth.make_state_dict(seed=0) weights
                           loaded through load_state_dict(strict=True): inputs are re-derivable from seeds, only
                           the output (and its gain=4 "trained-like" variant) is stored.
@@ -52,6 +52,24 @@ def tiny_refinit():
         blob["sd/" + k] = v.numpy()
     for k in ("conv_first.weight", "RRDB_trunk.0.RDB2.conv3.weight", "srcnn.conv3.bias"):
         blob["grad/" + k] = dict(net.named_parameters())[k].grad.numpy()
+    # MSE-loss gradients (smooth in sr, unlike L1's sign): every bias, six representative weights, and the norm of each
+    # parameter gradient - the fixture that pins the backward path (tests/test_gpu_backward.py)
+    net.zero_grad()
+    hr2 = synth.make_targets(torch.zeros(2, 1, 32, 32), seed=21)["hr"] * 8.0
+    loss2 = torch.nn.functional.mse_loss(net(x, elev, mask), hr2)
+    loss2.backward()
+    blob["hr_mse"] = hr2.numpy()
+    blob["loss_mse"] = loss2.detach().numpy()
+    full = ("conv_first.weight", "RRDB_trunk.0.RDB1.conv1.weight", "RRDB_trunk.0.RDB3.conv5.weight", "upconv2.weight",
+            "conv_last.weight", "srcnn.conv1.weight")
+    names, norms = [], []
+    for k, p in net.named_parameters():
+        names.append(k)
+        norms.append(float(p.grad.norm()))
+        if k.endswith(".bias") or k in full:
+            blob["gradmse/" + k] = p.grad.numpy()
+    blob["gradmse_names"] = np.array(names)
+    blob["gradmse_norms"] = np.array(norms, dtype=np.float64)
     np.savez_compressed(os.path.join(OUT, "gen_tiny_refinit.npz"), **blob)
     print("tiny_refinit", sr.shape, float(sr.std()), float(loss))
 
@@ -83,5 +101,6 @@ if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
     tiny_refinit()
-    seeded("gen_hydra_seeded", 4, 11, 16, 2, 16, 16)
-    seeded("gen_default_seeded", 4, 23, 32, 1, 12, 12)
+    if "--tiny-only" not in sys.argv:
+        seeded("gen_hydra_seeded", 4, 11, 16, 2, 16, 16)
+        seeded("gen_default_seeded", 4, 23, 32, 1, 12, 12)

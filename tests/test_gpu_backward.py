@@ -1,0 +1,148 @@
+"""GPU parity of the generator training step: weight-gradient GEMM, input-gradient convs and
+the whole csr_plan_backward chain against fp32 autograd of the oracle / golden gradients of the reference module.
+
+Tolerance.  Activations and gradient maps are stored in bf16 (fp32 accumulate).  Running the UNMODIFIED reference fully
+in bf16 (oracle calibration) reproduces its own fp32 gradients only to a relative L2 error of
+0.6 % (srcnn.conv3) ... 2.5 % (conv_last, srcnn.conv1) ... 9 % (first RDB), cosine >= 0.995; this path is held to the
+same envelope: cosine >= 0.99 and relative L2 <= 0.15 for every parameter, <= 0.06 for the weights of the four layers
+nearest the loss.
+Single kernels are held to bf16 rounding of their own operands (exact operands -> <= 1e-3 relative).
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+WGRAD_CASES = [
+    # n, h, w, cin, cout, k, up2
+    (1, 8, 14, 64, 16, 1, 0),
+    (1, 8, 14, 128, 64, 1, 0),
+    (2, 16, 16, 80, 16, 3, 0),          # RDB conv2
+    (2, 33, 45, 128, 64, 3, 0),         # RDB conv5, ragged tiles
+    (1, 20, 40, 32, 1, 5, 0),           # srcnn.conv3
+    (1, 12, 20, 64, 64, 3, 1),          # upconv (nearest x2 on the input): four phase GEMMs scattered into 3x3
+    (1, 24, 24, 192, 64, 3, 0),         # gc=32 conv5: two 128-channel chunks
+    (1, 1, 1, 64, 64, 3, 0),            # single pixel
+    (1, 113, 113, 64, 64, 3, 0),        # Europe-extent LR raster
+]
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout,k,up2", WGRAD_CASES)
+def test_wgrad_matches_autograd(n, h, w, cin, cout, k, up2):
+    from climsr_b200 import ops
+    g = torch.Generator().manual_seed(n * 100 + h + cin + k)
+    x = (torch.rand((n, cin, h, w), generator=g) * 2 - 1).to(torch.bfloat16).float()
+    s = 2 if up2 else 1
+    gy = (torch.rand((n, cout, s * h, s * w), generator=g) * 2 - 1).to(torch.bfloat16).float()
+    wt = torch.zeros((cout, cin, k, k), dtype=torch.float64, requires_grad=True)
+    xin = F.interpolate(x, scale_factor=2, mode="nearest") if up2 else x
+    (dw_ref,) = torch.autograd.grad(F.conv2d(xin.double(), wt, None, padding=k // 2), wt, gy.double())
+    db_ref = gy.double().sum(dim=(0, 2, 3))
+    xb = torch.zeros((n, h, w, (cin + 63) // 64 * 64), dtype=torch.bfloat16)
+    xb[..., :cin] = x.permute(0, 2, 3, 1).to(torch.bfloat16)
+    gb = torch.full((n, s * h, s * w, 64), 3.0, dtype=torch.bfloat16)      # channels >= cout must never be used
+    gb[..., :cout] = gy.permute(0, 2, 3, 1).to(torch.bfloat16)
+    dw = torch.ones((cout, cin, k, k), device="cuda")                        # accumulate semantics: dw += scale * grad
+    db = torch.ones((cout,), device="cuda")
+    ops.conv2d_wgrad(xb.cuda(), gb.cuda(), (cout, cin, k, k), in_up2=bool(up2), scale=0.5, dw=dw, db=db)
+    ew = float(((dw.cpu().double() - 1) * 2 - dw_ref).abs().max()) / max(1.0, float(dw_ref.abs().max()))
+    eb = float(((db.cpu().double() - 1) * 2 - db_ref).abs().max()) / max(1.0, float(db_ref.abs().max()))
+    assert ew <= 1e-3 and eb <= 1e-3, (ew, eb)
+
+
+def _train_step(sd, x, elev, mask, hr, in_ch, nb, gc, loss="mse"):
+    from climsr_b200.models import ESRGANGenerator
+    net = ESRGANGenerator(in_ch, 1, 64, nb, gc)
+    net.load_state_dict(sd)
+    net = net.cuda().train()
+    sr = net(x.cuda(), elev.cuda(), mask.cuda())
+    lv = F.mse_loss(sr, hr.cuda()) if loss == "mse" else F.l1_loss(sr, hr.cuda())
+    lv.backward()
+    return sr.detach().cpu(), float(lv.detach()), {k: p.grad.detach().cpu() for k, p in net.named_parameters()}, net
+
+
+def _check_grads(got, want, near_loss=("srcnn.conv3", "srcnn.conv2", "srcnn.conv1", "conv_last")):
+    for k, ref in want.items():
+        g = got[k]
+        assert torch.isfinite(g).all(), k
+        rel = float((g - ref).norm() / (ref.norm() + 1e-30))
+        cos = float(F.cosine_similarity(g.flatten().double(), ref.flatten().double(), dim=0))
+        assert cos >= 0.99, (k, cos)
+        # bias gradients are sums with heavy cancellation (conv_last.bias is a single scalar): they get the loose bound
+        tight = k.endswith(".weight") and k.rsplit(".", 1)[0] in near_loss
+        assert rel <= (0.06 if tight else 0.15), (k, rel)
+
+
+@pytest.mark.parametrize("in_ch,nb,gc,n,h,w", [(2, 1, 16, 2, 16, 16), (4, 2, 16, 1, 20, 12), (3, 1, 32, 1, 12, 12)])
+def test_generator_backward_matches_oracle(in_ch, nb, gc, n, h, w):
+    """Hydra-style (gc=16: dense-block weight-gradient GEMM) and class-default-style (gc=32: per-layer GEMMs, 192-channel
+    concat pitch) blocks, ragged rasters."""
+    from oracle import generator as og
+    from oracle import synth
+    sd = synth.make_state_dict(in_ch, 1, 64, nb, gc, seed=5)
+    x, elev, mask = synth.make_inputs(n, in_ch, h, w, seed=6)
+    hr = torch.rand((n, 1, 4 * h, 4 * w), generator=torch.Generator().manual_seed(7)) * 2 - 1
+    sr_ref, loss_ref, grads_ref = og.generator_forward_backward(sd, x, elev, mask, hr, loss="mse")
+    sr, lv, grads, _ = _train_step(sd, x, elev, mask, hr, in_ch, nb, gc)
+    assert float((sr - sr_ref).abs().max()) <= 1e-2
+    assert abs(lv - float(loss_ref)) <= 1e-3 * max(1.0, float(loss_ref))
+    _check_grads(grads, grads_ref)
+
+
+def test_generator_backward_matches_reference_golden(golden_dir):
+    """Weights, inputs, targets and gradients all produced by the UNMODIFIED reference module (oracle/make_golden.py)."""
+    z = np.load(os.path.join(golden_dir, "gen_tiny_refinit.npz"))
+    sd = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd/")}
+    x, elev, mask, hr = (torch.from_numpy(z[k]) for k in ("x", "elev", "mask", "hr_mse"))
+    _, lv, grads, _ = _train_step(sd, x, elev, mask, hr, 2, 1, 16)
+    assert abs(lv - float(z["loss_mse"])) <= 1e-3 * float(z["loss_mse"])
+    want = {k[len("gradmse/"):]: torch.from_numpy(z[k]) for k in z.files if k.startswith("gradmse/")}
+    assert len(want) >= 30
+    _check_grads(grads, want)
+    for name, norm in zip(z["gradmse_names"], z["gradmse_norms"]):
+        assert abs(float(grads[str(name)].norm()) - float(norm)) <= 0.15 * float(norm), name
+
+
+def test_training_step_semantics():
+    """(1) gradients accumulate across backward calls like autograd's; (2) an optimizer step repacks the weights and changes
+    the output; (3) a stale backward (another forward ran in between) is refused; (4) eval/no_grad takes the inference plan."""
+    from climsr_b200 import CsrError
+    from climsr_b200.models import ESRGANGenerator
+    torch.manual_seed(0)
+    net = ESRGANGenerator(3, 1, 64, 1, 16).cuda().train()
+    g = torch.Generator().manual_seed(3)
+    x = (torch.rand((2, 3, 12, 12), generator=g) * 2 - 1).cuda()
+    elev = torch.rand((2, 1, 48, 48), generator=g).cuda()
+    mask = (torch.rand((2, 1, 48, 48), generator=g) > 0.3).float().cuda()
+    hr = (torch.rand((2, 1, 48, 48), generator=g) * 2 - 1).cuda()
+    opt = torch.optim.AdamW(net.parameters(), lr=1e-3)
+    out1 = net(x, elev, mask)
+    F.l1_loss(out1, hr).backward()
+    g1 = net.conv_last.weight.grad.clone()
+    F.l1_loss(net(x, elev, mask), hr).backward()
+    assert torch.allclose(net.conv_last.weight.grad, 2 * g1, rtol=1e-3, atol=1e-7)
+    opt.step()
+    out2 = net(x, elev, mask)
+    assert not torch.equal(out1, out2)
+    stale = net(x, elev, mask)
+    _ = net(x, elev, mask)
+    with pytest.raises(CsrError):
+        stale.sum().backward()
+    net.eval()
+    with torch.no_grad():
+        out3 = net(x, elev, mask)
+    assert out3.requires_grad is False and torch.allclose(out3, out2.detach(), atol=1e-6)
+    losses = []
+    net.train()
+    opt = torch.optim.AdamW(net.parameters(), lr=2e-4)
+    for _ in range(12):
+        opt.zero_grad()
+        lv = F.l1_loss(net(x, elev, mask), hr)
+        lv.backward()
+        opt.step()
+        losses.append(float(lv.detach()))
+    assert losses[-1] < losses[0]                      # the step actually descends
