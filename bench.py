@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Headline benchmark: ESRGAN/RRDBNet generator inference throughput (HR-output Mpixel/s) on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg2_default|cfg1]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg2_default|cfg1|cfg3|...]
+                    [--mode infer|train]
 
 Workload (BASELINE.json configs[1]): Hydra generator (nf=64, nb=11, gc=16, in_channels=4), batch 64 of 256x256 HR tiles
 (LR 64x64) per GPU, synthetic inputs, random-init weights.  One "step" = one generator forward over the batch.
@@ -35,6 +36,11 @@ WORKLOADS = {
     "cfg2_default": (4, 23, 32, 64, 64, 64),    # class-default RRDBNet
     "cfg2_lr256": (4, 11, 16, 4, 256, 256),     # LR-tile reading (LR 256^2 -> HR 1024^2), reduced batch
     "cfg1": (4, 11, 16, 16, 32, 32),            # BASELINE configs[0] shape
+    "cfg3": (4, 11, 16, 16, 32, 32),            # BASELINE configs[2] generator part: per-GPU batch 16 of HR 128^2 (GAN experiment batch)
+    "cfg3_b192": (4, 11, 16, 192, 32, 32),      # ... and the pre-training experiment batch (192 per GPU)
+    "cfg4": (3, 11, 16, 1, 113, 113),           # Europe-extent raster, in=3
+    "cfg4_global": (3, 11, 16, 1, 360, 720),    # global CRU-TS grid 360x720 -> 1440x2880
+    "cfg5": (3, 11, 16, 48, 113, 113),          # 4 variables x 12 months of Europe-extent rasters
 }
 
 
@@ -258,6 +264,116 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_train(args):
+    """Generator training step (generator part): forward on a training plan, L1 pixel loss
+    (core/task.py:141), backward (dgrad + wgrad kernels), bucketed bf16 gradient all-reduce when N > 1, fused AdamW step
+    (conf/optimizers/adamw.yaml: lr 1e-4, wd 1e-4).  One rank per GPU, per-GPU batch fixed -> weak scaling."""
+    import torch
+    import torch.distributed as dist
+    from climsr_b200 import device_check, kernel_launch_count, losses
+    from climsr_b200.models import ESRGANGenerator
+    from climsr_b200.parallel import GradientBucketer
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    device_check()
+    dev = torch.device("cuda", local)
+    in_ch, nb, gc, tiles, h, w = WORKLOADS[args.workload]
+    H, W = 4 * h, 4 * w
+    torch.manual_seed(0)
+    net = ESRGANGenerator(in_ch, 1, 64, nb, gc).to(dev).train()
+    opt = torch.optim.AdamW(net.parameters(), lr=1e-4, weight_decay=1e-4, fused=True)
+    bucketer = GradientBucketer(net.parameters(), bucket_mb=4.0, comm_dtype=torch.bfloat16)
+    g = torch.Generator().manual_seed(1 + rank)
+    x = torch.rand((tiles, in_ch, h, w), generator=g) * 2 - 1
+    mask = (torch.rand((tiles, 1, H, W), generator=g) > 0.3).float()
+    elev = (torch.rand((tiles, 1, H, W), generator=g) * 2 - 1) * mask
+    hr = torch.rand((tiles, 1, H, W), generator=g) * 2 - 1
+    host = [t.pin_memory() for t in (x, elev, mask, hr)]
+    xd, ed, md, hd = (t.to(dev) for t in (x, elev, mask, hr))
+    loss_host = torch.empty((), dtype=torch.float32).pin_memory()
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        lv = losses.l1_loss(net(xd, ed, md), hd)
+        lv.backward()
+        bucketer.allreduce()
+        opt.step()
+        return lv
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for _ in range(max(args.warmup, 3)):
+        lv = step()
+    barrier()
+    first_loss = float(lv)
+    l0 = kernel_launch_count()
+    with ClockSampler(local) as clk:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            lv = step()
+        e1.record()
+        barrier()
+        ms_step = max_over_ranks(e0.elapsed_time(e1) / args.steps)
+    launches = kernel_launch_count() - l0
+    last_loss = float(lv)
+    # end to end: batch from pinned host memory each step, loss read back
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        for d, s in zip((xd, ed, md, hd), host):
+            d.copy_(s, non_blocking=True)
+        loss_host.copy_(step().detach(), non_blocking=True)
+    e1.record()
+    barrier()
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1) / args.steps)
+    px_step = tiles * H * W
+    fl = 3.0 * flops_per_hr_pixel(in_ch, 64, nb, gc)          # fwd + dgrad + wgrad (SURVEY.md section 8d)
+    peaks = load_peaks()
+    achieved = px_step * fl / (ms_step * 1e-3) / 1e12
+    line = {
+        "metric": "generator_train_hr_mpixel_per_s", "value": world * px_step / (ms_step * 1e-3) / 1e6, "unit": "Mpixel/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"{args.workload} train: RRDBNet generator nf=64 nb={nb} gc={gc} in={in_ch}, batch {tiles}/GPU LR {h}x{w} -> HR {H}x{W}; "
+                               "forward + L1 loss + backward (dgrad/wgrad kernels) + bf16 bucketed all-reduce + fused AdamW; bf16 activations/"
+                               "gradients, fp32 accumulate and master weights",
+                   "l2_policy": "saved activations + gradients of a step exceed the 126 MB L2 for batch >= 16; no flush needed",
+                   "parallelism": f"data parallel x{world}, {len(bucketer.buckets)} gradient buckets {bucketer.bucket_bytes()} bytes"},
+        "e2e": {"value": world * px_step / (ms_e2e * 1e-3) / 1e6, "unit": "Mpixel/s",
+                "h2d_bytes_per_step": int(sum(t.numel() for t in host)) * 4, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e},
+        "gpu_launches": int(launches), "clocks": clk.summary(),
+        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
+                     "frac": achieved / peaks["bf16_sustained"], "traffic": None,
+                     "peak_source": f"{peaks['source']} bf16_tflops_sustained (burst {peaks['bf16_burst']})",
+                     "note": "algorithmic 3x forward FLOPs of the step / step time"},
+        "loss_first": first_loss, "loss_last": last_loss,
+    }
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -266,9 +382,12 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default="infer", choices=["infer", "train"])
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.mode == "train":
+        run_train(args)
     else:
         run_ours(args)
 

@@ -73,6 +73,9 @@ def _load():
         "csr_conv2d_wgrad": (C.c_int, [wd, vp, vp, vp, vp, vp, sz, vp]),
         "csr_nchw_f32_to_nhwc_bf16": (C.c_int, [vp, vp, i32, i32, i32, i32, i32, i32, vp]),
         "csr_nhwc_bf16_to_nchw_f32": (C.c_int, [vp, vp, i32, i32, i32, i32, i32, i32, vp]),
+        "csr_pixel_loss_scratch_bytes": (sz, [C.c_int64]),
+        "csr_l1_loss": (C.c_int, [vp, vp, vp, C.c_int64, vp, vp, sz, vp]),
+        "csr_mse_loss": (C.c_int, [vp, vp, vp, C.c_int64, vp, vp, sz, vp]),
         "csr_metrics_scratch_bytes": (sz, [i32, i32, i32]),
         "csr_masked_metrics": (C.c_int, [vp, vp, vp, vp, vp, vp, f32, f32, f32, f32, i32, i32, i32, vp, vp, sz, vp]),
     }
@@ -88,8 +91,8 @@ EXPORTS = ("csr_abi_version", "csr_last_error", "csr_device_check", "csr_set_opt
            "csr_layer_shape", "csr_packed_weight_bytes", "csr_pack_weights", "csr_workspace_bytes", "csr_plan_create",
            "csr_plan_forward", "csr_plan_num_launches", "csr_plan_destroy", "csr_train_workspace_bytes", "csr_train_plan_create",
            "csr_packed_weight_bytes_bwd", "csr_pack_weights_bwd", "csr_plan_backward", "csr_plan_num_backward_ops", "csr_generator_forward", "csr_conv2d_scratch_bytes",
-           "csr_conv2d_nhwc", "csr_conv2d_wgrad_scratch_bytes", "csr_conv2d_wgrad", "csr_nchw_f32_to_nhwc_bf16", "csr_nhwc_bf16_to_nchw_f32", "csr_metrics_scratch_bytes",
-           "csr_masked_metrics")
+           "csr_conv2d_nhwc", "csr_conv2d_wgrad_scratch_bytes", "csr_conv2d_wgrad", "csr_nchw_f32_to_nhwc_bf16", "csr_nhwc_bf16_to_nchw_f32", "csr_pixel_loss_scratch_bytes", "csr_l1_loss", "csr_mse_loss",
+           "csr_metrics_scratch_bytes", "csr_masked_metrics")
 
 
 def check(rc: int, what: str = "") -> None:

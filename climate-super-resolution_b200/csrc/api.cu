@@ -11,6 +11,7 @@
 #include "../../include/climsr_b200.h"
 #include "conv_tc.cuh"
 #include "elementwise.cuh"
+#include "loss.cuh"
 #include "metrics.cuh"
 #include "wgrad_tc.cuh"
 
@@ -1242,6 +1243,29 @@ int csr_nhwc_bf16_to_nchw_f32(const void* src, float* dst, int32_t n, int32_t c,
   CSR_CUDA(launch_nhwc_to_nchw(src, dst, n, c, h, w, src_c, src_coff, reinterpret_cast<cudaStream_t>(stream)));
   ++g_launches;
   return CSR_OK;
+}
+
+// ---- pixel loss (value + gradient in one pass) ---------------------------------------------------------
+size_t csr_pixel_loss_scratch_bytes(int64_t numel) { return numel > 0 ? (size_t)pixel_loss_blocks(numel) * sizeof(double) : 0; }
+
+static int pixel_loss(int mode, const float* sr, const float* hr, float* grad, int64_t numel, float* out, void* scratch, size_t scratch_bytes,
+                      void* stream) {
+  if (!sr || !hr || !out || !scratch) return fail(CSR_ERR_BAD_ARG, "null pointer");
+  if (numel < 1) return fail(CSR_ERR_BAD_ARG, "numel must be positive");
+  if (scratch_bytes < csr_pixel_loss_scratch_bytes(numel)) return fail(CSR_ERR_WORKSPACE, "loss scratch too small");
+  if ((reinterpret_cast<uintptr_t>(sr) | reinterpret_cast<uintptr_t>(hr) | reinterpret_cast<uintptr_t>(grad)) % 16)
+    return fail(CSR_ERR_BAD_ARG, "sr / hr / grad must be 16-byte aligned");
+  cudaError_t e = launch_pixel_loss(mode, sr, hr, grad, numel, out, reinterpret_cast<double*>(scratch), reinterpret_cast<cudaStream_t>(stream));
+  g_launches += 2;
+  if (e != cudaSuccess) return fail(CSR_ERR_CUDA, "loss launch failed: %s", cudaGetErrorString(e));
+  return CSR_OK;
+}
+
+int csr_l1_loss(const float* sr, const float* hr, float* grad, int64_t numel, float* out, void* scratch, size_t scratch_bytes, void* stream) {
+  return pixel_loss(0, sr, hr, grad, numel, out, scratch, scratch_bytes, stream);
+}
+int csr_mse_loss(const float* sr, const float* hr, float* grad, int64_t numel, float* out, void* scratch, size_t scratch_bytes, void* stream) {
+  return pixel_loss(1, sr, hr, grad, numel, out, scratch, scratch_bytes, stream);
 }
 
 // ---- metrics ------------------------------------------------------------------------------------------

@@ -175,6 +175,15 @@ int     csr_nchw_f32_to_nhwc_bf16(const float* src, void* dst, int32_t n, int32_
 int     csr_nhwc_bf16_to_nchw_f32(const void* src, float* dst, int32_t n, int32_t c, int32_t h, int32_t w,
                                   int32_t src_c, int32_t src_coff, void* stream);
 
+/* ---- pixel loss of the training step: mean over all numel elements, value AND gradient in one HBM pass --------
+ * out[0] = mean |sr - hr| (L1, esrgan) or mean (sr - hr)^2 (MSE, srcnn);  grad (nullable, numel floats) = d out / d sr.
+ * scratch: csr_pixel_loss_scratch_bytes(numel).  <- self.loss(sr, hr), core/task.py:141, pl_generator_pre_training.py:29-30 */
+size_t  csr_pixel_loss_scratch_bytes(int64_t numel);
+int     csr_l1_loss(const float* sr, const float* hr, float* grad, int64_t numel, float* out,
+                    void* scratch, size_t scratch_bytes, void* stream);
+int     csr_mse_loss(const float* sr, const float* hr, float* grad, int64_t numel, float* out,
+                     void* scratch, size_t scratch_bytes, void* stream);
+
 /* ---- masked loss + metrics (one fused HBM pass + SSIM pass) ----------------------------------
  * sr, hr, original, mask: fp32 (N,1,H,W).  mn/mx: fp32 (N) per-sample min/max (min-max scaler) or
  * NULL with zmean/zstd used instead (z-score).  out: CSR_NUM_METRICS floats (device), see enum.   */
