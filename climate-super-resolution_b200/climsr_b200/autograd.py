@@ -24,7 +24,9 @@ class GeneratorFunction(torch.autograd.Function):
         xs = x.detach().contiguous().float()
         es = elev.detach().to(dev).contiguous().float()
         ms = mask.detach().to(dev).contiguous().float()
-        packed = module.packed_weights()
+        # optimizers (fused AdamW in particular) update parameters without bumping the version counters the inference
+        # path keys its pack cache on: training always repacks
+        packed = module.packed_weights(force=True)
         plan = module._plan(n, h, w, dev, train=True)
         out = torch.empty((n, 1, 4 * h, 4 * w), dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
@@ -47,9 +49,14 @@ class GeneratorFunction(torch.autograd.Function):
                            "the saved activations of the latest forward only)")
         dev = ctx.dev
         go = grad_out.detach().contiguous().float()
-        packed_bwd = module.packed_weights_bwd()
+        packed_bwd = module.packed_weights_bwd(force=True)
         n = len(ctx.shapes) // 2
-        grads = [torch.zeros(s, dtype=torch.float32, device=dev) for s in ctx.shapes]
+        sizes = [int(torch.Size(s).numel()) for s in ctx.shapes]
+        flat = torch.zeros(sum((k + 3) // 4 * 4 for k in sizes), dtype=torch.float32, device=dev)      # one memset, 16-byte aligned views
+        grads, off = [], 0
+        for s, k in zip(ctx.shapes, sizes):
+            grads.append(flat[off:off + k].view(s))
+            off += (k + 3) // 4 * 4
         dw, db = (C.c_void_p * n)(), (C.c_void_p * n)()
         for i in range(n):
             dw[i], db[i] = grads[2 * i].data_ptr(), grads[2 * i + 1].data_ptr()

@@ -85,6 +85,8 @@ class ESRGANGenerator(nn.Module):
     # ------------------------------------------------------------------ weights
     def _ordered_params(self):
         """(weight, bias) pairs in state_dict order == csr layer order."""
+        if getattr(self, "_ordered_cache", None) is not None:
+            return self._ordered_cache
         n = lib.csr_num_layers(C.byref(self._desc))
         if n < 0:
             check(n, "csr_num_layers")
@@ -99,14 +101,15 @@ class ESRGANGenerator(nn.Module):
             if tuple(w.shape) != tuple(shape):
                 raise CsrError(f"parameter {key}.weight has shape {tuple(w.shape)}, expected {tuple(shape)}")
             out.append((w, b))
+        self._ordered_cache = out
         return out
 
-    def packed_weights(self) -> Tensor:
+    def packed_weights(self, force: bool = False) -> Tensor:
         """bf16 UMMA weight tiles + fp32 biases; rebuilt when any parameter changed (optimizer step, load_state_dict)."""
         pairs = self._ordered_params()
         dev = pairs[0][0].device
         key = (dev,) + tuple((p.data_ptr(), p._version) for wb in pairs for p in wb)
-        if self._packed is not None and key == self._packed_key:
+        if self._packed is not None and key == self._packed_key and not force:
             return self._packed
         if dev.type != "cuda":
             raise CsrError("ESRGANGenerator parameters must live on a CUDA (B200) device; there is no CPU path")
@@ -127,12 +130,12 @@ class ESRGANGenerator(nn.Module):
         self._packed_key = key
         return self._packed
 
-    def packed_weights_bwd(self) -> Tensor:
+    def packed_weights_bwd(self, force: bool = False) -> Tensor:
         """Transposed / flipped bf16 tiles for the input-gradient convs; rebuilt when any weight changed."""
         pairs = self._ordered_params()
         dev = pairs[0][0].device
         key = (dev,) + tuple((w.data_ptr(), w._version) for w, _ in pairs)
-        if self._packed_bwd is not None and key == self._packed_bwd_key:
+        if self._packed_bwd is not None and key == self._packed_bwd_key and not force:
             return self._packed_bwd
         nbytes = lib.csr_packed_weight_bytes_bwd(C.byref(self._desc))
         if self._packed_bwd is None or self._packed_bwd.device != dev:

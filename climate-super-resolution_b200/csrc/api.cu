@@ -5,6 +5,8 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -326,7 +328,7 @@ struct WgradLaunch {
 
 // One vertical tap of one 128-input-channel chunk: x channels [xc0, xc0+128) (beyond the buffer pitch -> zeros), output
 // gradients gA channels [gA_c0, +64) and optionally gB channels [gB_c0, +64) as GEMM columns [0,64) / [64,128).
-static int build_wgrad(int N, int H, int W, int KW, int PW, int dy_off, const void* x, int x_C, int xc0, const void* gA, int gA_C, int gA_c0,
+static int build_wgrad(int sms, int N, int H, int W, int KW, int PW, int dy_off, const void* x, int x_C, int xc0, const void* gA, int gA_C, int gA_c0,
                        const void* gB, int gB_C, int gB_c0, int n_cols, float* dacc, int ld_n, WgradLaunch* wl) {
   if (n_cols % 16 || n_cols < 16 || n_cols > 128) return fail(CSR_ERR_UNSUPPORTED, "wgrad: n_cols %d", n_cols);
   if (x_C % 8 || gA_C % 8 || xc0 % 8 || gA_c0 % 8) return fail(CSR_ERR_BAD_ARG, "wgrad: channel pitch/offset must be multiples of 8");
@@ -363,6 +365,7 @@ static int build_wgrad(int N, int H, int W, int KW, int PW, int dy_off, const vo
   p.xc0[0] = xc0; p.xc0[1] = xc0 + 64;
   p.gc0[0] = gA_c0; p.gc0[1] = gB_c0;
   p.dacc = dacc; p.ld_n = ld_n;
+  p.n_parts = std::min(p.num_tiles, sms);
   p.dbg_a_lbo = g_dbg_wgrad[0]; p.dbg_a_sbo = g_dbg_wgrad[1]; p.dbg_b_lbo = g_dbg_wgrad[2]; p.dbg_b_sbo = g_dbg_wgrad[3];
   p.dbg_flags = g_dbg_wgrad[4];
   int rc = encode_act_map(&wl->tx0, x, N, H, W, x_C, p.SW, p.TH + 1);
@@ -385,10 +388,11 @@ static int build_wgrad(int N, int H, int W, int KW, int PW, int dy_off, const vo
 struct WgradLayer {
   int cout, cin, kh, kw, fold, up2;
 };
+constexpr int kMaxParts = 160;   // >= SM count: per-CTA partial-sum slices
 static size_t wgrad_scratch_floats(const WgradLayer& L) {
   const int ekh = L.up2 ? 2 : L.kh, ekw = L.up2 ? 2 : (L.fold ? 1 : L.kw);
   const int ld_n = (L.cout + 15) / 16 * 16;
-  return (size_t)ekh * ekw * 128 * ld_n;
+  return (size_t)ekh * kMaxParts * ekw * 128 * ld_n;
 }
 
 static int encode_phase_map(CUtensorMap* m, const void* base, int N, int H, int W, int C, int phase, int box_w, int box_h) {
@@ -413,16 +417,18 @@ static int run_wgrad_layer(const WgradLayer& L, int N, int H, int W, const void*
   if (ld_n > 128) return fail(CSR_ERR_UNSUPPORTED, "wgrad: cout %d > 128", L.cout);
   const int ecin = L.fold ? L.cin * L.kw : L.cin;
   const int ekh = L.up2 ? 2 : L.kh, ekw = L.up2 ? 2 : (L.fold ? 1 : L.kw);
-  const size_t nfl = (size_t)ekh * ekw * 128 * ld_n;
+  if (sms > kMaxParts) return fail(CSR_ERR_UNSUPPORTED, "wgrad: %d SMs > %d", sms, kMaxParts);
+  const long dy_stride = (long)kMaxParts * ekw * 128 * ld_n;
   for (int phase = L.up2 ? 0 : -1; phase < (L.up2 ? 4 : 0); ++phase) {
     const int ph = L.up2 ? 1 - (phase >> 1) : L.kh / 2;
     const int pw = L.up2 ? 1 - (phase & 1) : (L.fold ? 0 : L.kw / 2);
     for (int ci0 = 0; ci0 < ecin; ci0 += 128) {
-      CSR_CUDA(cudaMemsetAsync(scratch, 0, nfl * sizeof(float), s));
+      int n_parts = 0;
       for (int dy = 0; dy < ekh; ++dy) {
         WgradLaunch wl;
-        int rc = build_wgrad(N, H, W, ekw, pw, dy - ph, x, x_C, x_coff + ci0, g, g_C, g_coff, nullptr, 0, 0, ld_n,
-                             scratch + (size_t)dy * ekw * 128 * ld_n, ld_n, &wl);
+        int rc = build_wgrad(sms, N, H, W, ekw, pw, dy - ph, x, x_C, x_coff + ci0, g, g_C, g_coff, nullptr, 0, 0, ld_n,
+                             scratch + (size_t)dy * dy_stride, ld_n, &wl);
+        n_parts = wl.p.n_parts;
         if (rc) return rc;
         if (phase >= 0) {
           rc = encode_phase_map(&wl.tg0, g, N, H, W, g_C, phase, wl.p.SW, wl.p.TH);
@@ -433,13 +439,15 @@ static int run_wgrad_layer(const WgradLayer& L, int N, int H, int W, const void*
         if (e) return fail(CSR_ERR_CUDA, "wgrad launch failed: %s", cudaGetErrorString((cudaError_t)e));
         ++*launches;
       }
-      CSR_CUDA(launch_wgrad_scatter(scratch, ld_n, dw, L.cout, L.cin, L.kh, L.kw, L.fold, phase, ci0, std::min(128, ecin - ci0), 0, scale, s));
+      CSR_CUDA(launch_wgrad_scatter(scratch, ld_n, n_parts, dy_stride, dw, L.cout, L.cin, L.kh, L.kw, L.fold, phase, ci0,
+                                    std::min(128, ecin - ci0), 0, scale, s));
       ++*launches;
     }
   }
   if (db) {
     const long npix = (long)N * H * W * (L.up2 ? 4 : 1);
-    CSR_CUDA(launch_bias_grad(g, npix, g_C, g_coff, L.cout, scale, db, s));
+    float* dbs[1] = {db};
+    CSR_CUDA(launch_bias_grad(g, npix, g_C, g_coff, L.cout, scale, dbs, 1, s));
     ++*launches;
   }
   return CSR_OK;
@@ -454,7 +462,9 @@ struct BwdOp {
   csr::ConvLaunch conv;          // kConv (dgrad); w_off/b_off index the BACKWARD packed blob
   csr::WgradLaunch wg;           // kWgrad
   // kScatter / kBias*: which forward layer's gradient, and how
-  int layer = -1, fold = 0, phase = -1, ci0 = 0, ci_n = 0, col0 = 0, ld_n = 0;
+  int layer = -1, fold = 0, phase = -1, ci0 = 0, ci_n = 0, col0 = 0, ld_n = 0, n_parts = 0, nseg = 1;
+  long dy_stride = 0;
+  int seg_layers[4] = {-1, -1, -1, -1};   // kBias with nseg > 1: one forward layer per channel segment
   float scale = 1.f;
   const void* src = nullptr; void* dst = nullptr;   // kScale (bf16 NHWC 64 ch: dst = scale*src), kBias (g buffer), kMemset
   long count = 0; int C = 0, coff = 0, cout = 0;
@@ -513,7 +523,7 @@ static WsLayout ws_layout(const CsrNetDesc& d, int N, int h, int w, int train) {
     L.gt0 = take(lr * 64 * 2);
     L.gtmp = take(lr * 64 * 2);
     for (int i = 0; i < 3; ++i) L.gcat[i] = take(lr * L.ccat * 2);
-    L.dacc = take((size_t)9 * 128 * 128 * 4 * 2);
+    L.dacc = take((size_t)9 * kMaxParts * 128 * 128 * 4);   // per-CTA partial sums of the weight-gradient GEMMs
   } else {
     L.hrD = L.hrA; L.hrE = L.hrB;
     L.gO = L.gT = L.gP = L.gQ = L.gm1 = L.gt0 = L.gtmp = L.dacc = 0;
@@ -717,14 +727,15 @@ static int bwd_build(CsrPlan* P, void* ws) {
     for (int phase = Ls.up2 ? 0 : -1; phase < (Ls.up2 ? 4 : 0); ++phase) {
       const int ph = Ls.up2 ? 1 - (phase >> 1) : Ls.kh / 2;
       const int pw = Ls.up2 ? 1 - (phase & 1) : (Ls.fold ? 0 : Ls.kw / 2);
+      const long dy_stride = (long)kMaxParts * ekw * 128 * ld_n;
       for (int ci0 = 0; ci0 < ecin; ci0 += 128) {
-        BwdOp ms; ms.kind = BwdOp::kMemset; ms.dst = dacc; ms.count = (long)ekh * ekw * 128 * ld_n * 4;
-        ops.push_back(ms);
+        int n_parts = 0;
         for (int dy = 0; dy < ekh; ++dy) {
           BwdOp op; op.kind = BwdOp::kWgrad;
-          int rc = build_wgrad(N, Hh, Ww, ekw, pw, dy - ph, x, x_C, x_coff + ci0, g, g_C, g_coff, nullptr, 0, 0, ld_n,
-                               dacc + (size_t)dy * ekw * 128 * ld_n, ld_n, &op.wg);
+          int rc = build_wgrad(P->sms, N, Hh, Ww, ekw, pw, dy - ph, x, x_C, x_coff + ci0, g, g_C, g_coff, nullptr, 0, 0, ld_n,
+                               dacc + (size_t)dy * dy_stride, ld_n, &op.wg);
           if (rc) return rc;
+          n_parts = op.wg.p.n_parts;
           if (phase >= 0) {
             rc = encode_phase_map(&op.wg.tg0, g, N, Hh, Ww, g_C, phase, op.wg.p.SW, op.wg.p.TH);
             if (rc) return rc;
@@ -733,7 +744,7 @@ static int bwd_build(CsrPlan* P, void* ws) {
           ops.push_back(op);
         }
         BwdOp sc; sc.kind = BwdOp::kScatter; sc.layer = layer; sc.fold = Ls.fold; sc.phase = phase; sc.ci0 = ci0;
-        sc.ci_n = std::min(128, ecin - ci0); sc.col0 = 0; sc.ld_n = ld_n; sc.scale = scale;
+        sc.ci_n = std::min(128, ecin - ci0); sc.col0 = 0; sc.ld_n = ld_n; sc.scale = scale; sc.n_parts = n_parts; sc.dy_stride = dy_stride;
         ops.push_back(sc);
       }
     }
@@ -854,23 +865,31 @@ static int bwd_build(CsrPlan* P, void* ws) {
           rc = wgrad_plain(fwd_index_rdb(i, r, 5), h, w, cat(j), C, 0, gin, gin_C, 0, 0.2f);
           if (rc) return rc;
         } else {
-          BwdOp ms; ms.kind = BwdOp::kMemset; ms.dst = dacc; ms.count = (long)9 * 128 * 128 * 4;
-          ops.push_back(ms);
+          const long dy_stride = (long)kMaxParts * 3 * 128 * 128;
+          int n_parts = 0;
           for (int dy = 0; dy < 3; ++dy) {
             BwdOp op; op.kind = BwdOp::kWgrad;
-            rc = build_wgrad(N, h, w, 3, 1, dy - 1, cat(j), C, 0, gc_, C, nf, gin, gin_C, 0, 128, dacc + (size_t)dy * 3 * 128 * 128, 128, &op.wg);
+            rc = build_wgrad(P->sms, N, h, w, 3, 1, dy - 1, cat(j), C, 0, gc_, C, nf, gin, gin_C, 0, 128, dacc + (size_t)dy * dy_stride, 128,
+                             &op.wg);
             if (rc) return rc;
+            n_parts = op.wg.p.n_parts;
             ops.push_back(op);
           }
           for (int k = 1; k <= 5; ++k) {
             const int layer = fwd_index_rdb(i, r, k);
             BwdOp sc; sc.kind = BwdOp::kScatter; sc.layer = layer; sc.ci0 = 0; sc.ci_n = (k < 5) ? nf + (k - 1) * gc : nf + 4 * gc;
-            sc.col0 = (k < 5) ? (k - 1) * gc : 64; sc.ld_n = 128; sc.scale = (k < 5) ? 1.f : 0.2f;
+            sc.col0 = (k < 5) ? (k - 1) * gc : 64; sc.ld_n = 128; sc.scale = (k < 5) ? 1.f : 0.2f; sc.n_parts = n_parts; sc.dy_stride = dy_stride;
             ops.push_back(sc);
-            BwdOp bo; bo.kind = BwdOp::kBias; bo.layer = layer; bo.count = (long)N * h * w; bo.cout = F[layer].cout;
-            if (k < 5) { bo.src = gc_; bo.C = C; bo.coff = nf + (k - 1) * gc; bo.scale = 1.f; }
-            else { bo.src = gin; bo.C = gin_C; bo.coff = 0; bo.scale = 0.2f; }
+          }
+          // bias gradients: the four narrow convs in one pass over the gradient-concat slices, conv5 from g_out
+          {
+            BwdOp bo; bo.kind = BwdOp::kBias; bo.count = (long)N * h * w; bo.cout = 4 * gc; bo.nseg = 4;
+            for (int k = 1; k <= 4; ++k) bo.seg_layers[k - 1] = fwd_index_rdb(i, r, k);
+            bo.layer = bo.seg_layers[0]; bo.src = gc_; bo.C = C; bo.coff = nf; bo.scale = 1.f;
             ops.push_back(bo);
+            BwdOp b5; b5.kind = BwdOp::kBias; b5.layer = fwd_index_rdb(i, r, 5); b5.count = (long)N * h * w; b5.cout = nf;
+            b5.src = gin; b5.C = gin_C; b5.coff = 0; b5.scale = 0.2f;
+            ops.push_back(b5);
           }
         }
       }
@@ -950,6 +969,27 @@ size_t csr_packed_weight_bytes(const CsrNetDesc* net) {
   return total;
 }
 
+// Batched pack: the job table lives on the device, cached per destination blob and re-uploaded only when it changes
+// (parameter storage moved).  One kernel launch packs every layer part.
+static int run_pack_jobs(const std::vector<PackJob>& jobs, void* key, cudaStream_t s) {
+  struct Cached { std::vector<PackJob> host; PackJob* dev = nullptr; };
+  static std::map<void*, Cached> cache;
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lock(mu);
+  Cached& c = cache[key];
+  const size_t bytes = jobs.size() * sizeof(PackJob);
+  const bool same = c.dev && c.host.size() == jobs.size() && memcmp(c.host.data(), jobs.data(), bytes) == 0;
+  if (!same) {
+    if (c.dev && c.host.size() != jobs.size()) { cudaFree(c.dev); c.dev = nullptr; }
+    if (!c.dev) CSR_CUDA(cudaMalloc(&c.dev, bytes));
+    c.host = jobs;
+    CSR_CUDA(cudaMemcpyAsync(c.dev, c.host.data(), bytes, cudaMemcpyHostToDevice, s));
+  }
+  CSR_CUDA(launch_pack_jobs(c.dev, (int)jobs.size(), s));
+  ++g_launches;
+  return CSR_OK;
+}
+
 int csr_pack_weights(const CsrNetDesc* net, const float* const* w, const float* const* b, void* packed, size_t packed_bytes,
                      void* stream) {
   int rc = check_net(net);
@@ -961,16 +1001,14 @@ int csr_pack_weights(const CsrNetDesc* net, const float* const* w, const float* 
   if (packed_bytes < total) return fail(CSR_ERR_WORKSPACE, "packed buffer %zu < %zu bytes", packed_bytes, total);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   uint8_t* base = reinterpret_cast<uint8_t*>(packed);
+  std::vector<PackJob> jobs;
   for (size_t i = 0; i < layers.size(); ++i) {
     if (!w[i] || !b[i]) return fail(CSR_ERR_BAD_ARG, "null weight/bias pointer for layer %zu", i);
-    for (const PackPart& pp : packs[i].parts) {
-      CSR_CUDA(launch_pack_weight(w[i], base + pp.w_off, layers[i].cout, layers[i].cin, layers[i].kh, layers[i].kw, layers[i].fold,
-                                  pp.phase, layers[i].transposed, layers[i].wscale, pp.co_lo, pp.npad, packs[i].cin_pad, s));
-      CSR_CUDA(launch_pack_bias(b[i], reinterpret_cast<float*>(base + pp.b_off), layers[i].cout, pp.co_lo, pp.npad, s));
-      g_launches += 2;
-    }
+    for (const PackPart& pp : packs[i].parts)
+      jobs.push_back({w[i], b[i], base + pp.w_off, reinterpret_cast<float*>(base + pp.b_off), layers[i].cout, layers[i].cin, layers[i].kh,
+                      layers[i].kw, layers[i].fold, pp.phase, layers[i].transposed, layers[i].wscale, pp.co_lo, pp.npad, packs[i].cin_pad});
   }
-  return CSR_OK;
+  return run_pack_jobs(jobs, packed, s);
 }
 
 size_t csr_workspace_bytes(const CsrNetDesc* net, int32_t n, int32_t h, int32_t w) {
@@ -1040,17 +1078,15 @@ int csr_pack_weights_bwd(const CsrNetDesc* net, const float* const* w, void* pac
   if (packed_bytes < total) return fail(CSR_ERR_WORKSPACE, "packed buffer %zu < %zu bytes", packed_bytes, total);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   uint8_t* base = reinterpret_cast<uint8_t*>(packed);
+  std::vector<PackJob> jobs;
   for (size_t i = 0; i < layers.size(); ++i) {
     const float* src = w[layers[i].src];
     if (!src) return fail(CSR_ERR_BAD_ARG, "null weight pointer for layer %d", layers[i].src);
-    for (const PackPart& pp : packs[i].parts) {
-      CSR_CUDA(launch_pack_weight(src, base + pp.w_off, layers[i].cout, layers[i].cin, layers[i].kh, layers[i].kw, 0, pp.phase, 1,
-                                  layers[i].wscale, pp.co_lo, pp.npad, packs[i].cin_pad, s));
-      CSR_CUDA(launch_pack_bias(nullptr, reinterpret_cast<float*>(base + pp.b_off), 0, pp.co_lo, pp.npad, s));
-      g_launches += 2;
-    }
+    for (const PackPart& pp : packs[i].parts)
+      jobs.push_back({src, nullptr, base + pp.w_off, reinterpret_cast<float*>(base + pp.b_off), layers[i].cout, layers[i].cin, layers[i].kh,
+                      layers[i].kw, 0, pp.phase, 1, layers[i].wscale, pp.co_lo, pp.npad, packs[i].cin_pad});
   }
-  return CSR_OK;
+  return run_pack_jobs(jobs, packed, s);
 }
 
 int csr_plan_backward(CsrPlan* P, const void* packed_bwd, const float* grad_out, float* const* dw, float* const* db, void* stream) {
@@ -1079,14 +1115,19 @@ int csr_plan_backward(CsrPlan* P, const void* packed_bwd, const float* grad_out,
       case BwdOp::kScatter: {
         const LayerSpec& L = P->fwd_layers[op.layer];
         if (!dw[op.layer]) return fail(CSR_ERR_BAD_ARG, "null weight-gradient pointer for layer %d", op.layer);
-        CSR_CUDA(launch_wgrad_scatter(P->dacc, op.ld_n, dw[op.layer], L.cout, L.cin, L.kh, L.kw, op.fold, op.phase, op.ci0, op.ci_n, op.col0,
-                                      op.scale, s));
+        CSR_CUDA(launch_wgrad_scatter(P->dacc, op.ld_n, op.n_parts, op.dy_stride, dw[op.layer], L.cout, L.cin, L.kh, L.kw, op.fold, op.phase,
+                                      op.ci0, op.ci_n, op.col0, op.scale, s));
         break;
       }
-      case BwdOp::kBias:
-        if (!db[op.layer]) return fail(CSR_ERR_BAD_ARG, "null bias-gradient pointer for layer %d", op.layer);
-        CSR_CUDA(launch_bias_grad(op.src, op.count, op.C, op.coff, op.cout, op.scale, db[op.layer], s));
+      case BwdOp::kBias: {
+        float* dbs[4] = {nullptr, nullptr, nullptr, nullptr};
+        for (int q = 0; q < op.nseg; ++q) {
+          dbs[q] = db[op.nseg > 1 ? op.seg_layers[q] : op.layer];
+          if (!dbs[q]) return fail(CSR_ERR_BAD_ARG, "null bias-gradient pointer for layer %d", op.layer);
+        }
+        CSR_CUDA(launch_bias_grad(op.src, op.count, op.C, op.coff, op.cout, op.scale, dbs, op.nseg, s));
         break;
+      }
       case BwdOp::kBiasPlanar:
         CSR_CUDA(launch_bias_grad_planar(reinterpret_cast<const float*>(op.src), op.count, op.scale, db[op.layer], s));
         break;

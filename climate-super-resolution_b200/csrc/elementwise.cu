@@ -24,8 +24,9 @@ __device__ __forceinline__ void phase_taps(int a, int r, int* lo, int* hi) {
   else        { *lo = r == 0 ? 0 : 2; *hi = r == 0 ? 1 : 2; }
 }
 
-__global__ void pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ dst, int cout, int cin, int kh,
-                                   int kw, int fold, int phase, int transposed, float wscale, int co_lo, int npad, int cin_pad) {
+__device__ __forceinline__ void pack_weight_body(const float* __restrict__ w, __nv_bfloat16* __restrict__ dst, int cout, int cin, int kh,
+                                                 int kw, int fold, int phase, int transposed, float wscale, int co_lo, int npad, int cin_pad,
+                                                 long first, long step) {
   // executed taps
   const int ekh = phase >= 0 ? 2 : kh;
   const int ekw = phase >= 0 ? 2 : (fold ? 1 : kw);
@@ -33,7 +34,7 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* _
   const int full_kb = ksteps >> 2, rem = ksteps & 3;
   const int groups = (ekw * npad) >> 3;
   const long total = static_cast<long>(ekh) * ksteps * ekw * npad * 16;
-  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long>(gridDim.x) * blockDim.x) {
+  for (long i = first; i < total; i += step) {
     const int e = i & 7;
     const int row = (i >> 3) & 7;
     const int kchunk = (i >> 6) & 1;
@@ -80,6 +81,21 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* _
     }
     dst[i] = __float2bfloat16_rn(v);
   }
+}
+
+__global__ void pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ dst, int cout, int cin, int kh,
+                                   int kw, int fold, int phase, int transposed, float wscale, int co_lo, int npad, int cin_pad) {
+  pack_weight_body(w, dst, cout, cin, kh, kw, fold, phase, transposed, wscale, co_lo, npad, cin_pad,
+                   blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x, static_cast<long>(gridDim.x) * blockDim.x);
+}
+
+// All layers of the generator in ONE launch (training repacks every optimizer step: ~360 layer parts): blockIdx.y = job.
+__global__ void pack_jobs_kernel(const PackJob* __restrict__ jobs) {
+  const PackJob j = jobs[blockIdx.y];
+  pack_weight_body(j.w, reinterpret_cast<__nv_bfloat16*>(j.dst), j.cout, j.cin, j.kh, j.kw, j.fold, j.phase, j.transposed, j.wscale, j.co_lo,
+                   j.npad, j.cin_pad, blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x, static_cast<long>(gridDim.x) * blockDim.x);
+  if (blockIdx.x == 0 && threadIdx.x < j.npad)
+    j.bdst[threadIdx.x] = (j.b && j.co_lo + static_cast<int>(threadIdx.x) < j.cout) ? j.b[j.co_lo + threadIdx.x] : 0.f;
 }
 
 __global__ void pack_bias_kernel(const float* __restrict__ b, float* __restrict__ dst, int cout, int co_lo, int npad) {
@@ -155,13 +171,14 @@ __global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ src, float
 }
 
 // ---- weight-gradient post-processing ---------------------------------------------------------------------
-// dacc: fp32 [KH_e][KW_e][128][ld_n] sums produced by wgrad_tc_kernel (executed taps KH_e x KW_e, rows = executed input
-// channel - ci0, columns = output channel + col0).  Adds scale * dacc into the layer's OIHW gradient:
+// dacc: fp32 [KH_e][n_parts][KW_e][128][ld_n] per-CTA partial sums produced by wgrad_tc_kernel (executed taps KH_e x KW_e,
+// rows = executed input channel - ci0, columns = output channel + col0).  Reduces over the parts (fixed order ->
+// deterministic) and adds scale * sum into the layer's OIHW gradient:
 //   plain : dw[co][ci][dy][dx]                          += dacc[dy][dx][ci - ci0][col0 + co]
 //   fold  : dw[co][c][dy][dx]  (executed channel dx*cin+c, KW_e = 1)  += dacc[dy][0][dx*cin + c - ci0][col0 + co]
 //   phase : executed 2x2 taps (ry, rx) of sub-pixel phase (a,b) feed every 3x3 tap they were summed from
-__global__ void wgrad_scatter_kernel(const float* __restrict__ dacc, int ld_n, float* __restrict__ dw, int cout, int cin, int kh, int kw,
-                                     int fold, int phase, int ci0, int ci_n, int col0, float scale) {
+__global__ void wgrad_scatter_kernel(const float* __restrict__ dacc, int ld_n, int n_parts, long dy_stride, float* __restrict__ dw, int cout,
+                                     int cin, int kh, int kw, int fold, int phase, int ci0, int ci_n, int col0, float scale) {
   const int ekh = phase >= 0 ? 2 : kh;
   const int ekw = phase >= 0 ? 2 : (fold ? 1 : kw);
   const long total = static_cast<long>(ekh) * ekw * ci_n * cout;
@@ -171,7 +188,12 @@ __global__ void wgrad_scatter_kernel(const float* __restrict__ dacc, int ld_n, f
     const int cl = r % ci_n;                               // executed input channel - ci0
     r /= ci_n;
     const int dx = r % ekw, dy = r / ekw;
-    const float v = scale * dacc[((static_cast<long>(dy) * ekw + dx) * 128 + cl) * ld_n + col0 + co];
+    // dacc: [dy (stride dy_stride)][part][dx][128][ld_n]
+    const float* src = dacc + dy * dy_stride + (static_cast<long>(dx) * 128 + cl) * ld_n + col0 + co;
+    const long part_stride = static_cast<long>(ekw) * 128 * ld_n;
+    float acc = 0.f;
+    for (int q = 0; q < n_parts; ++q) acc += src[q * part_stride];
+    const float v = scale * acc;
     const int ce = ci0 + cl;                               // executed input channel
     if (phase >= 0) {
       if (ce >= cin) continue;
@@ -192,7 +214,13 @@ __global__ void wgrad_scatter_kernel(const float* __restrict__ dacc, int ld_n, f
 }
 
 // db[co] += scale * sum over pixels of g[p][coff + co]   (bf16 NHWC, pitch C).  One block per pixel range, fp32 atomics.
-__global__ void bias_grad_kernel(const __nv_bfloat16* __restrict__ g, long npix, int C, int coff, int cout, float scale, float* __restrict__ db) {
+// Channel co goes to segment co / seg_ch (its own bias-gradient vector): one pass serves the four narrow convs of a
+// dense block whose output gradients sit side by side in the gradient concat buffer.
+struct BiasSegs {
+  float* db[4];
+};
+__global__ void bias_grad_kernel(const __nv_bfloat16* __restrict__ g, long npix, int C, int coff, int cout, float scale, BiasSegs segs,
+                                 int seg_ch) {
   extern __shared__ float red[];                           // [blockDim.x / cout_pad rows][cout_pad]
   const int cpad = (cout + 7) & ~7;
   const int lanes_per_pix = cpad >> 3;                     // one thread loads 8 channels (16 B)
@@ -216,7 +244,8 @@ __global__ void bias_grad_kernel(const __nv_bfloat16* __restrict__ g, long npix,
     const int s2 = threadIdx.x >> 3, k = threadIdx.x & 7;
     float t = 0.f;
     for (int r = 0; r < pix_per_iter; ++r) t += red[(r * lanes_per_pix + s2) * 8 + k];
-    atomicAdd(&db[threadIdx.x], scale * t);
+    const int sg = threadIdx.x / seg_ch;
+    atomicAdd(&segs.db[sg][threadIdx.x - sg * seg_ch], scale * t);
   }
 }
 
@@ -289,15 +318,19 @@ cudaError_t launch_nhwc_to_nchw(const void* src, float* dst, int n, int c, int h
   return cudaGetLastError();
 }
 
-cudaError_t launch_wgrad_scatter(const float* dacc, int ld_n, float* dw, int cout, int cin, int kh, int kw, int fold, int phase, int ci0,
-                                 int ci_n, int col0, float scale, cudaStream_t s) {
+cudaError_t launch_wgrad_scatter(const float* dacc, int ld_n, int n_parts, long dy_stride, float* dw, int cout, int cin, int kh, int kw, int fold,
+                                 int phase, int ci0, int ci_n, int col0, float scale, cudaStream_t s) {
   const int ekh = phase >= 0 ? 2 : kh, ekw = phase >= 0 ? 2 : (fold ? 1 : kw);
   const long total = static_cast<long>(ekh) * ekw * ci_n * cout;
-  wgrad_scatter_kernel<<<grid_for(total, 256), 256, 0, s>>>(dacc, ld_n, dw, cout, cin, kh, kw, fold, phase, ci0, ci_n, col0, scale);
+  wgrad_scatter_kernel<<<grid_for(total, 256), 256, 0, s>>>(dacc, ld_n, n_parts, dy_stride, dw, cout, cin, kh, kw, fold, phase, ci0, ci_n,
+                                                            col0, scale);
   return cudaGetLastError();
 }
-cudaError_t launch_bias_grad(const void* g, long npix, int C, int coff, int cout, float scale, float* db, cudaStream_t s) {
-  bias_grad_kernel<<<148 * 2, 256, 256 * 8 * sizeof(float), s>>>(reinterpret_cast<const __nv_bfloat16*>(g), npix, C, coff, cout, scale, db);
+cudaError_t launch_bias_grad(const void* g, long npix, int C, int coff, int cout, float scale, float* const* db, int nseg, cudaStream_t s) {
+  BiasSegs segs;
+  for (int i = 0; i < 4; ++i) segs.db[i] = db[i < nseg ? i : 0];
+  bias_grad_kernel<<<148 * 2, 256, 256 * 8 * sizeof(float), s>>>(reinterpret_cast<const __nv_bfloat16*>(g), npix, C, coff, cout, scale, segs,
+                                                                 cout / nseg);
   return cudaGetLastError();
 }
 cudaError_t launch_bias_grad_planar(const float* g, long n, float scale, float* db, cudaStream_t s) {
@@ -308,6 +341,11 @@ cudaError_t launch_bias_grad_planar(const float* g, long n, float scale, float* 
 cudaError_t launch_scale_copy64(const void* src, int src_C, void* dst, long npix, float scale, cudaStream_t s) {
   scale_copy64_kernel<<<grid_for(npix * 8, 256), 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(src), src_C,
                                                               reinterpret_cast<__nv_bfloat16*>(dst), npix, scale);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_pack_jobs(const PackJob* jobs_dev, int njobs, cudaStream_t s) {
+  pack_jobs_kernel<<<dim3(16, njobs), 256, 0, s>>>(jobs_dev);
   return cudaGetLastError();
 }
 

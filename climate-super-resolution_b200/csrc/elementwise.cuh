@@ -2,6 +2,12 @@
 #include <cuda_runtime.h>
 
 namespace csr {
+// one layer part of a batched weight pack (see pack_weight_kernel for the field meanings)
+struct PackJob {
+  const float* w; const float* b; void* dst; float* bdst;
+  int cout, cin, kh, kw, fold, phase, transposed; float wscale; int co_lo, npad, cin_pad;
+};
+cudaError_t launch_pack_jobs(const PackJob* jobs_dev, int njobs, cudaStream_t s);
 cudaError_t launch_pack_weight(const float* w, void* dst, int cout, int cin, int kh, int kw, int fold, int phase, int transposed,
                                float wscale, int co_lo, int npad, int cin_pad, cudaStream_t s);
 cudaError_t launch_pack_bias(const float* b, float* dst, int cout, int co_lo, int npad, cudaStream_t s);
@@ -9,9 +15,10 @@ cudaError_t launch_nchw_to_nhwc(const float* src, void* dst, int n, int c, int h
 cudaError_t launch_pack_srcnn_in(const float* t, const float* elev, const float* mask, void* dst, int W, long total_pix, int dst_c,
                                  cudaStream_t s);
 cudaError_t launch_nhwc_to_nchw(const void* src, float* dst, int n, int c, int h, int w, int src_c, int src_coff, cudaStream_t s);
-cudaError_t launch_wgrad_scatter(const float* dacc, int ld_n, float* dw, int cout, int cin, int kh, int kw, int fold, int phase, int ci0,
-                                 int ci_n, int col0, float scale, cudaStream_t s);
-cudaError_t launch_bias_grad(const void* g, long npix, int C, int coff, int cout, float scale, float* db, cudaStream_t s);
+cudaError_t launch_wgrad_scatter(const float* dacc, int ld_n, int n_parts, long dy_stride, float* dw, int cout, int cin, int kh, int kw, int fold,
+                                 int phase, int ci0, int ci_n, int col0, float scale, cudaStream_t s);
+// db: nseg (1..4) bias-gradient vectors; channel co of the cout channels goes to db[co / (cout/nseg)]
+cudaError_t launch_bias_grad(const void* g, long npix, int C, int coff, int cout, float scale, float* const* db, int nseg, cudaStream_t s);
 cudaError_t launch_bias_grad_planar(const float* g, long n, float scale, float* db, cudaStream_t s);
 cudaError_t launch_scale_copy64(const void* src, int src_C, void* dst, long npix, float scale, cudaStream_t s);
 }  // namespace csr

@@ -11,8 +11,8 @@
 // One launch handles one vertical tap: the x window is loaded at row offset dy_off, and the horizontal taps are read
 // from the same window at flattened pixel offsets dx-PW (the halo trick of the forward kernel, transposed).  Columns
 // of the g tile that belong to the neighbouring tiles are zeroed in shared memory so every pixel is counted once.
-// Accumulators stay resident in TMEM over ALL tiles of the persistent CTA; one epilogue at the end adds the CTA's
-// partial sums to the global fp32 accumulation buffer with red.add.f32.
+// Accumulators stay resident in TMEM over ALL tiles of the persistent CTA; one epilogue at the end stores the CTA's
+// partial sums to its slice of a global fp32 buffer, reduced over CTAs by the scatter kernel.
 #include "ptx.cuh"
 #include "wgrad_tc.cuh"
 
@@ -171,16 +171,18 @@ wgrad_tc_kernel(const WgradParams p, const __grid_constant__ CUtensorMap tx0, co
     if (blockIdx.x < p.num_tiles) {
       mbar_wait(bar_done, 0);
       tc_fence_after();
+      // this CTA's partial sums go to its own slice of the accumulation buffer ([cta][dx][128][ld_n], plain stores);
+      // the scatter kernel reduces over CTAs.  (fp32 atomics onto 49 K shared addresses from 148 CTAs were measured at
+      // ~100 us per launch - 5x the GEMM itself.)
+      float* base = p.dacc + static_cast<size_t>(blockIdx.x) * p.KW * 128 * p.ld_n;
       for (int dx = 0; dx < p.KW; ++dx) {
-        float* dst = p.dacc + (static_cast<size_t>(dx) * 128 + ci) * p.ld_n;
+        float* dst = base + (static_cast<size_t>(dx) * 128 + ci) * p.ld_n;
         for (int c = 0; c < p.n_cols; c += 8) {
           uint32_t r[8];
           tmem_ld8(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + dx * p.n_cols + c, r);
           tmem_ld_wait();
-          if (ci < p.M) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) atomicAdd(dst + c + i, __uint_as_float(r[i]));
-          }
+          *reinterpret_cast<uint4*>(dst + c) = make_uint4(r[0], r[1], r[2], r[3]);
+          *reinterpret_cast<uint4*>(dst + c + 4) = make_uint4(r[4], r[5], r[6], r[7]);
         }
       }
     }
@@ -209,7 +211,7 @@ int launch_wgrad_tc(const WgradParams& p, const CUtensorMap& tx0, const CUtensor
     if (e != cudaSuccess) return static_cast<int>(e);
     configured = true;
   }
-  const int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
+  const int grid = p.n_parts;
   wgrad_tc_kernel<<<grid, kWgradThreads, smem, stream>>>(p, tx0, tx1, tg0, tg1);
   return static_cast<int>(cudaGetLastError());
 }

@@ -26,7 +26,8 @@ struct WgradParams {
   int stage_bytes, n_stages;
   int tmem_cols;
   int xc0[2], gc0[2];        // first channel of each box inside its buffer
-  float* dacc;               // fp32 [KW][M][ld_n] accumulation buffer (global, atomically added)
+  float* dacc;               // fp32 [n_parts][KW][128][ld_n]: one partial-sum slice per CTA
+  int n_parts;               // grid size = min(num_tiles, SMs)
   int ld_n;
   // debug overrides of the MN-major descriptor fields (0 = default)
   int dbg_a_lbo, dbg_a_sbo, dbg_b_lbo, dbg_b_sbo, dbg_flags;
