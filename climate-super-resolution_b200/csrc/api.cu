@@ -107,6 +107,8 @@ struct LayerSpec {
   int transposed = 0;      // 1: input-gradient conv: weight read as w[ci][co][KH-1-dy][KW-1-dx] (autograd of the layer)
   float wscale = 1.f;      // constant folded into the packed weights
   int src = -1;            // backward tables: index of the forward layer whose weight tensor is packed
+  struct Block { int src, ci_lo, n, src_ci_off, src_cin; float wscale; };
+  std::vector<Block> blocks;   // backward tables: executed input-channel blocks gathered from several forward layers
   int ekw() const { return fold ? 1 : kw; }
   int ecin() const { return fold ? cin * kw : cin; }
 };
@@ -658,11 +660,23 @@ static std::vector<LayerSpec> bwd_layer_table(const CsrNetDesc& d, const std::ve
   T(base_tail + 2, 1.f, 1);                               // upconv2 (four transposed sub-pixel phases)
   T(base_tail + 1, 1.f, 1);                               // upconv1
   T(base_tail + 0, 1.f);                                  // trunk_conv
+  // Dense blocks, mirrored: with the gradient concat [g_y | g4 | g3 | g2 | g1] (g_y = gradient of the block output, g_k =
+  // gated gradient of x_k), the gradient of x_s is ONE conv over [g_y | g4 .. g_{s+1}] whose input-channel blocks come
+  // from conv5 (x0.2: out = x5*0.2 + x), conv4, ..., conv_{s+1}, each restricted to its input-channel slice of x_s.
   for (int i = d.nb - 1; i >= 0; --i)
-    for (int r = 2; r >= 0; --r) {
-      T(fwd_index_rdb(i, r, 5), 0.2f);                    // conv5: d(x5*0.2 + x)/dx5 folded into the weights
-      for (int k = 4; k >= 1; --k) T(fwd_index_rdb(i, r, k), 1.f);
-    }
+    for (int r = 2; r >= 0; --r)
+      for (int sidx = 4; sidx >= 0; --sidx) {             // x4, x3, x2, x1, then x (sidx 0)
+        LayerSpec t;
+        t.name = f[fwd_index_rdb(i, r, 5)].name + ".dgrad_x" + std::to_string(sidx);
+        t.cout = sidx ? d.gc : d.nf;
+        t.cin = d.nf + (4 - sidx) * d.gc;
+        t.kh = t.kw = 3; t.transposed = 1; t.src = fwd_index_rdb(i, r, 5);
+        const int slice_off = sidx ? d.nf + (sidx - 1) * d.gc : 0;       // x_s inside the forward concat
+        t.blocks.push_back({fwd_index_rdb(i, r, 5), 0, d.nf, slice_off, d.nf + 4 * d.gc, 0.2f});
+        for (int j = 4; j > sidx; --j)
+          t.blocks.push_back({fwd_index_rdb(i, r, j), d.nf + (4 - j) * d.gc, d.gc, slice_off, d.nf + (j - 1) * d.gc, 1.f});
+        v.push_back(t);
+      }
   return v;
 }
 
@@ -676,7 +690,7 @@ static int bwd_build(CsrPlan* P, void* ws) {
   void* t0 = base + L.t0; void* m1 = base + L.m1; void* hrA = base + L.hrA; void* hrB = base + L.hrB; void* hrC = base + L.hrC;
   void* hrD = base + L.hrD; void* hrE = base + L.hrE;
   void* gO = base + L.gO; void* gT = base + L.gT; void* gP = base + L.gP; void* gQ = base + L.gQ; void* gm1 = base + L.gm1;
-  void* gt0 = base + L.gt0; void* gtmp = base + L.gtmp;
+  void* gt0 = base + L.gt0;
   void* gcat[3] = {base + L.gcat[0], base + L.gcat[1], base + L.gcat[2]};
   float* dacc = reinterpret_cast<float*>(base + L.dacc);
   P->gout_nhwc = gO; P->dacc = dacc;
@@ -762,10 +776,6 @@ static int bwd_build(CsrPlan* P, void* ws) {
     io.gate = gate; io.gate_C = gate_C; io.gate_coff = gate_coff; io.gate_from = gate_from; io.gate_neg = neg;
     return io;
   };
-  auto accum = [&](ConvIO io) {
-    io.r1 = io.out; io.r1_C = io.out_C; io.r1_coff = io.out_coff; io.s1 = 1.f;
-    return io;
-  };
 
   int rc;
   // ---- SRCNN tail (srcnn.py:13-18) -------------------------------------------------------------------------------
@@ -807,70 +817,51 @@ static int bwd_build(CsrPlan* P, void* ws) {
   rc = dgrad(h, w, io_of(gt0, 64, gcat[Pb], C, 0, CSR_ACT_NONE));
   if (rc) return rc;
   // ---- RRDB trunk, reversed (esrgan.py:32-38, 50-54) ----------------------------------------------------------------
+  // Per dense block one gradient concat buffer Gb = [g_y (64) | g4 | g3 | g2 | g1] (bwd_layer_table): four narrow convs
+  // fill the slices (each gated by the LeakyReLU derivative of its forward activation), one wide conv produces the
+  // gradient of the block input (+ identity path) into the NEXT block-to-process's Gb[0:64].  Mirrors the forward cost.
   for (int i = d.nb - 1; i >= 0; --i) {
     const int Qb = (Pb + 1) % 3, Rb = (Pb + 2) % 3;
-    // out = RDB3_out*0.2 + x_rrdb: the gradient entering RDB3 is 0.2*G
-    { BwdOp op; op.kind = BwdOp::kScale; op.src = gcat[Pb]; op.C = C; op.dst = gtmp; op.count = (long)N * h * w; op.scale = 0.2f; ops.push_back(op); }
-    const void* gin = gtmp; int gin_C = 64;
-    int outb[3] = {Qb, Rb, Qb};                           // RDB3 -> Q, RDB2 -> R, RDB1 -> Q (free again)
+    // out = RDB3_out*0.2 + x_rrdb: the gradient entering RDB3 is 0.2*G  ->  Gb(RDB3)[0:64]
+    { BwdOp op; op.kind = BwdOp::kScale; op.src = gcat[Pb]; op.C = C; op.dst = gcat[Qb]; op.coff = C; op.count = (long)N * h * w; op.scale = 0.2f;
+      ops.push_back(op); }
+    const int gbuf[3] = {Qb, Rb, Qb};                     // Gb of RDB3, RDB2, RDB1
+    const int xout[3] = {Rb, Qb, Rb};                     // where each block's input gradient goes: the next Gb[0:64]
     for (int r = 2; r >= 0; --r) {
       const int j = 3 * i + r;
-      void* gc_ = gcat[outb[2 - r]];
-      // conv5 dgrad (weights pre-scaled by 0.2) + identity path: channels [0,64) += g_out; slice 4 becomes final -> gate
-      {
-        ConvIO io = gated(io_of(gin, gin_C, gc_, C, 0, CSR_ACT_NONE), cat(j), C, 0, nf + 3 * gc, 0.2f);
-        io.r1 = gin; io.r1_C = gin_C; io.r1_coff = 0; io.s1 = 1.f;
-        // r1 only exists for channels [0,64): build_conv offsets it per part, so restrict it to the first part below
+      void* Gb = gcat[gbuf[2 - r]];
+      void* Xo = gcat[xout[2 - r]];
+      for (int sidx = 4; sidx >= 1; --sidx) {
+        // g_s = lrelu'(x_s) * conv_T([g_y | g4 .. g_{s+1}])  ->  Gb slice of x_s
+        ConvIO io = io_of(Gb, C, Gb, C, nf + (4 - sidx) * gc, CSR_ACT_NONE);
+        io = gated(io, cat(j), C, nf + (sidx - 1) * gc, 0, 0.2f);
         const PackLayer& pl = packs[bi];
         for (const PackPart& pp : pl.parts) {
           BwdOp op; op.kind = BwdOp::kConv;
-          ConvIO io2 = io;
-          if (pp.co_lo >= nf) io2.r1 = nullptr;
-          if (pp.co_lo + pp.n_store <= nf + 3 * gc) io2.gate = nullptr;
-          rc = build_conv(pl, pp, N, h, w, io2, &op.conv);
+          rc = build_conv(pl, pp, N, h, w, io, &op.conv);
           if (rc) return rc;
           ops.push_back(op);
         }
         ++bi;
       }
-      // weight gradients of the whole dense block as ONE GEMM per vertical tap: x = the block's concat buffer (128 ch),
-      // g columns [0,64) = gated gradients of x1..x4 (concat-gradient slices), columns [64,128) = g_out (conv5, scale 0.2)
-      // -- issued after the conv1..4 input-gradient chain below has finalised every slice.
-      for (int k = 4; k >= 1; --k) {
-        const int cin_k = nf + (k - 1) * gc;
-        ConvIO io = accum(io_of(gc_, C, gc_, C, 0, CSR_ACT_NONE));
-        io.cin_off = cin_k;                                // reads the finalised, gated slice of x_k
-        if (k >= 2) io = gated(io, cat(j), C, 0, nf + (k - 2) * gc, 0.2f);
-        if (k == 1 && r == 0) { io.r2 = gcat[Pb]; io.r2_C = C; io.r2_coff = 0; io.s2 = 1.f; }   // + G (RRDB identity path)
-        const PackLayer& pl = packs[bi];
-        for (const PackPart& pp : pl.parts) {
-          BwdOp op; op.kind = BwdOp::kConv;
-          ConvIO io2 = io;
-          if (io2.gate && pp.co_lo + pp.n_store <= io.gate_from) io2.gate = nullptr;
-          rc = build_conv(pl, pp, N, h, w, io2, &op.conv);
-          if (rc) return rc;
-          ops.push_back(op);
-        }
-        ++bi;
-      }
-      // dense-block weight gradients
+      // weight gradients of the whole dense block as ONE GEMM per vertical tap (gc = 16): x = the block's forward concat
+      // buffer (128 ch), g columns [0,64) = [g4 g3 g2 g1], columns [64,128) = g_y (conv5, scale 0.2).  Issued before the
+      // input-gradient conv below, whose output may overwrite a buffer another block's GEMM has just read.
       {
-        const int ncols_a = 4 * gc;                        // x1..x4 gradient slices
-        if (C > 128 || ncols_a > 64) {
+        if (C > 128 || 4 * gc > 64) {
           // gc = 32: concat pitch 192 -> per-layer weight gradients
           for (int k = 1; k <= 4; ++k) {
-            rc = wgrad_plain(fwd_index_rdb(i, r, k), h, w, cat(j), C, 0, gc_, C, nf + (k - 1) * gc, 1.f);
+            rc = wgrad_plain(fwd_index_rdb(i, r, k), h, w, cat(j), C, 0, Gb, C, nf + (4 - k) * gc, 1.f);
             if (rc) return rc;
           }
-          rc = wgrad_plain(fwd_index_rdb(i, r, 5), h, w, cat(j), C, 0, gin, gin_C, 0, 0.2f);
+          rc = wgrad_plain(fwd_index_rdb(i, r, 5), h, w, cat(j), C, 0, Gb, C, 0, 0.2f);
           if (rc) return rc;
         } else {
           const long dy_stride = (long)kMaxParts * 3 * 128 * 128;
           int n_parts = 0;
           for (int dy = 0; dy < 3; ++dy) {
             BwdOp op; op.kind = BwdOp::kWgrad;
-            rc = build_wgrad(P->sms, N, h, w, 3, 1, dy - 1, cat(j), C, 0, gc_, C, nf, gin, gin_C, 0, 128, dacc + (size_t)dy * dy_stride, 128,
-                             &op.wg);
+            rc = build_wgrad(P->sms, N, h, w, 3, 1, dy - 1, cat(j), C, 0, Gb, C, nf, Gb, C, 0, 128, dacc + (size_t)dy * dy_stride, 128, &op.wg);
             if (rc) return rc;
             n_parts = op.wg.p.n_parts;
             ops.push_back(op);
@@ -878,24 +869,36 @@ static int bwd_build(CsrPlan* P, void* ws) {
           for (int k = 1; k <= 5; ++k) {
             const int layer = fwd_index_rdb(i, r, k);
             BwdOp sc; sc.kind = BwdOp::kScatter; sc.layer = layer; sc.ci0 = 0; sc.ci_n = (k < 5) ? nf + (k - 1) * gc : nf + 4 * gc;
-            sc.col0 = (k < 5) ? (k - 1) * gc : 64; sc.ld_n = 128; sc.scale = (k < 5) ? 1.f : 0.2f; sc.n_parts = n_parts; sc.dy_stride = dy_stride;
+            sc.col0 = (k < 5) ? (4 - k) * gc : 64; sc.ld_n = 128; sc.scale = (k < 5) ? 1.f : 0.2f; sc.n_parts = n_parts; sc.dy_stride = dy_stride;
             ops.push_back(sc);
           }
-          // bias gradients: the four narrow convs in one pass over the gradient-concat slices, conv5 from g_out
-          {
-            BwdOp bo; bo.kind = BwdOp::kBias; bo.count = (long)N * h * w; bo.cout = 4 * gc; bo.nseg = 4;
-            for (int k = 1; k <= 4; ++k) bo.seg_layers[k - 1] = fwd_index_rdb(i, r, k);
-            bo.layer = bo.seg_layers[0]; bo.src = gc_; bo.C = C; bo.coff = nf; bo.scale = 1.f;
-            ops.push_back(bo);
-            BwdOp b5; b5.kind = BwdOp::kBias; b5.layer = fwd_index_rdb(i, r, 5); b5.count = (long)N * h * w; b5.cout = nf;
-            b5.src = gin; b5.C = gin_C; b5.coff = 0; b5.scale = 0.2f;
-            ops.push_back(b5);
-          }
+          // bias gradients: the four narrow convs in one pass over the gradient-concat slices, conv5 from g_y
+          BwdOp bo; bo.kind = BwdOp::kBias; bo.count = (long)N * h * w; bo.cout = 4 * gc; bo.nseg = 4;
+          for (int q = 0; q < 4; ++q) bo.seg_layers[q] = fwd_index_rdb(i, r, 4 - q);      // slice order g4, g3, g2, g1
+          bo.layer = bo.seg_layers[0]; bo.src = Gb; bo.C = C; bo.coff = nf; bo.scale = 1.f;
+          ops.push_back(bo);
+          BwdOp b5; b5.kind = BwdOp::kBias; b5.layer = fwd_index_rdb(i, r, 5); b5.count = (long)N * h * w; b5.cout = nf;
+          b5.src = Gb; b5.C = C; b5.coff = 0; b5.scale = 0.2f;
+          ops.push_back(b5);
         }
       }
-      gin = gc_; gin_C = C;                                // channels [0,64) of this buffer = dL/d(input of RDB r) = g_out of RDB r-1
+      // gradient of the block input: conv_T([g_y | g4 | g3 | g2 | g1]) + g_y (identity path of x5*0.2 + x)
+      // (+ G for RDB1: identity path of the RRDB, out*0.2 + x_rrdb)
+      {
+        ConvIO io = io_of(Gb, C, Xo, C, 0, CSR_ACT_NONE);
+        io.r1 = Gb; io.r1_C = C; io.r1_coff = 0; io.s1 = 1.f;
+        if (r == 0) { io.r2 = gcat[Pb]; io.r2_C = C; io.r2_coff = 0; io.s2 = 1.f; }
+        const PackLayer& pl = packs[bi];
+        for (const PackPart& pp : pl.parts) {
+          BwdOp op; op.kind = BwdOp::kConv;
+          rc = build_conv(pl, pp, N, h, w, io, &op.conv);
+          if (rc) return rc;
+          ops.push_back(op);
+        }
+        ++bi;
+      }
     }
-    Pb = Qb;                                               // RDB1 wrote dL/d(RRDB input) (incl. + G) into Q[0:64]
+    Pb = Rb;                                               // RDB1 wrote dL/d(RRDB input) (incl. + G) into R[0:64]
   }
   // ---- conv_first (esrgan.py:90): total gradient of its output = trunk path (gcat[Pb][0:64]) + skip path (gt0) ----
   rc = wgrad_plain(0, h, w, xin, 64, 0, gcat[Pb], C, 0, 1.f);
@@ -1006,7 +1009,7 @@ int csr_pack_weights(const CsrNetDesc* net, const float* const* w, const float* 
     if (!w[i] || !b[i]) return fail(CSR_ERR_BAD_ARG, "null weight/bias pointer for layer %zu", i);
     for (const PackPart& pp : packs[i].parts)
       jobs.push_back({w[i], b[i], base + pp.w_off, reinterpret_cast<float*>(base + pp.b_off), layers[i].cout, layers[i].cin, layers[i].kh,
-                      layers[i].kw, layers[i].fold, pp.phase, layers[i].transposed, layers[i].wscale, pp.co_lo, pp.npad, packs[i].cin_pad});
+                      layers[i].kw, layers[i].fold, pp.phase, layers[i].transposed, layers[i].wscale, pp.co_lo, pp.npad, packs[i].cin_pad, 0, 0, 0, 0});
   }
   return run_pack_jobs(jobs, packed, s);
 }
@@ -1080,11 +1083,22 @@ int csr_pack_weights_bwd(const CsrNetDesc* net, const float* const* w, void* pac
   uint8_t* base = reinterpret_cast<uint8_t*>(packed);
   std::vector<PackJob> jobs;
   for (size_t i = 0; i < layers.size(); ++i) {
-    const float* src = w[layers[i].src];
-    if (!src) return fail(CSR_ERR_BAD_ARG, "null weight pointer for layer %d", layers[i].src);
-    for (const PackPart& pp : packs[i].parts)
-      jobs.push_back({src, nullptr, base + pp.w_off, reinterpret_cast<float*>(base + pp.b_off), layers[i].cout, layers[i].cin, layers[i].kh,
-                      layers[i].kw, 0, pp.phase, 1, layers[i].wscale, pp.co_lo, pp.npad, packs[i].cin_pad});
+    const LayerSpec& L = layers[i];
+    for (const PackPart& pp : packs[i].parts) {
+      float* bdst = reinterpret_cast<float*>(base + pp.b_off);
+      if (L.blocks.empty()) {
+        if (!w[L.src]) return fail(CSR_ERR_BAD_ARG, "null weight pointer for layer %d", L.src);
+        jobs.push_back({w[L.src], nullptr, base + pp.w_off, bdst, L.cout, L.cin, L.kh, L.kw, 0, pp.phase, 1, L.wscale, pp.co_lo, pp.npad,
+                        packs[i].cin_pad, 0, 0, 0, 0});
+      } else {
+        for (size_t bk = 0; bk < L.blocks.size(); ++bk) {
+          const LayerSpec::Block& B = L.blocks[bk];
+          if (!w[B.src]) return fail(CSR_ERR_BAD_ARG, "null weight pointer for layer %d", B.src);
+          jobs.push_back({w[B.src], nullptr, base + pp.w_off, bk == 0 ? bdst : nullptr, L.cout, L.cin, L.kh, L.kw, 0, pp.phase, 1, B.wscale,
+                          pp.co_lo, pp.npad, packs[i].cin_pad, B.ci_lo, B.n, B.src_ci_off, B.src_cin});
+        }
+      }
+    }
   }
   return run_pack_jobs(jobs, packed, s);
 }
@@ -1132,7 +1146,7 @@ int csr_plan_backward(CsrPlan* P, const void* packed_bwd, const float* grad_out,
         CSR_CUDA(launch_bias_grad_planar(reinterpret_cast<const float*>(op.src), op.count, op.scale, db[op.layer], s));
         break;
       case BwdOp::kScale:
-        CSR_CUDA(launch_scale_copy64(op.src, op.C, op.dst, op.count, op.scale, s));
+        CSR_CUDA(launch_scale_copy64(op.src, op.C, op.dst, op.coff, op.count, op.scale, s));
         break;
       case BwdOp::kMemset:
         CSR_CUDA(cudaMemsetAsync(op.dst, 0, op.count, s));

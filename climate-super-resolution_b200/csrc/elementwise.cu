@@ -26,7 +26,7 @@ __device__ __forceinline__ void phase_taps(int a, int r, int* lo, int* hi) {
 
 __device__ __forceinline__ void pack_weight_body(const float* __restrict__ w, __nv_bfloat16* __restrict__ dst, int cout, int cin, int kh,
                                                  int kw, int fold, int phase, int transposed, float wscale, int co_lo, int npad, int cin_pad,
-                                                 long first, long step) {
+                                                 int ci_lo, int ci_n, int src_ci_off, int src_cin, long first, long step) {
   // executed taps
   const int ekh = phase >= 0 ? 2 : kh;
   const int ekw = phase >= 0 ? 2 : (fold ? 1 : kw);
@@ -57,6 +57,8 @@ __device__ __forceinline__ void pack_weight_body(const float* __restrict__ w, __
     int dx = rr / npad;
     const int co = co_lo + (rr - dx * npad);
     int ci = (kb * 4 + ks) * 16 + kchunk * 8 + e;
+    // block jobs fill only executed input channels [ci_lo, ci_lo + ci_n) (another job of the same layer fills the rest)
+    if (ci_n > 0 && (ci < ci_lo || ci >= ci_lo + ci_n)) continue;
     float v = 0.f;
     const int cin_eff = fold ? cin * kw : cin;
     if (co < cout && ci < cin_eff) {
@@ -65,8 +67,9 @@ __device__ __forceinline__ void pack_weight_body(const float* __restrict__ w, __
         ci -= dx * cin;
       }
       // source indices: the forward layer's OIHW tensor is (cout, cin, kh, kw), or (cin, cout, kh, kw) when transposed
-      const int s_o = transposed ? ci : co, s_i = transposed ? co : ci;
-      const int s_in = transposed ? cout : cin;            // channels-per-output-filter of the source tensor
+      // (block jobs: source output channel = ci - ci_lo, source input channel = co + src_ci_off of a (ci_n, src_cin, kh, kw) tensor)
+      const int s_o = transposed ? ci - ci_lo : co, s_i = transposed ? co + src_ci_off : ci;
+      const int s_in = transposed ? (src_cin ? src_cin : cout) : cin;   // channels-per-output-filter of the source tensor
       const int sdy = transposed ? ekh - 1 - dy : dy, sdx = transposed ? ekw - 1 - dx : dx;
       if (phase >= 0) {
         int y0, y1, x0, x1;
@@ -85,7 +88,7 @@ __device__ __forceinline__ void pack_weight_body(const float* __restrict__ w, __
 
 __global__ void pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ dst, int cout, int cin, int kh,
                                    int kw, int fold, int phase, int transposed, float wscale, int co_lo, int npad, int cin_pad) {
-  pack_weight_body(w, dst, cout, cin, kh, kw, fold, phase, transposed, wscale, co_lo, npad, cin_pad,
+  pack_weight_body(w, dst, cout, cin, kh, kw, fold, phase, transposed, wscale, co_lo, npad, cin_pad, 0, 0, 0, 0,
                    blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x, static_cast<long>(gridDim.x) * blockDim.x);
 }
 
@@ -93,8 +96,9 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* _
 __global__ void pack_jobs_kernel(const PackJob* __restrict__ jobs) {
   const PackJob j = jobs[blockIdx.y];
   pack_weight_body(j.w, reinterpret_cast<__nv_bfloat16*>(j.dst), j.cout, j.cin, j.kh, j.kw, j.fold, j.phase, j.transposed, j.wscale, j.co_lo,
-                   j.npad, j.cin_pad, blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x, static_cast<long>(gridDim.x) * blockDim.x);
-  if (blockIdx.x == 0 && threadIdx.x < j.npad)
+                   j.npad, j.cin_pad, j.ci_lo, j.ci_n, j.src_ci_off, j.src_cin, blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x,
+                   static_cast<long>(gridDim.x) * blockDim.x);
+  if (blockIdx.x == 0 && threadIdx.x < j.npad && j.bdst)
     j.bdst[threadIdx.x] = (j.b && j.co_lo + static_cast<int>(threadIdx.x) < j.cout) ? j.b[j.co_lo + threadIdx.x] : 0.f;
 }
 
@@ -264,9 +268,10 @@ __global__ void bias_grad_planar_kernel(const float* __restrict__ g, long n, flo
   }
 }
 
-// dst[p][0:64] = scale * src[p][0:64]   (bf16 NHWC, src pitch src_C, dst pitch 64): the 0.2 of `out*0.2 + x` (esrgan.py:54)
+// dst[p][0:64] = scale * src[p][0:64]   (bf16 NHWC, pitches src_C / dst_C): the 0.2 of `out*0.2 + x` (esrgan.py:54)
 // on the gradient path.  One thread per 8 channels.
-__global__ void scale_copy64_kernel(const __nv_bfloat16* __restrict__ src, int src_C, __nv_bfloat16* __restrict__ dst, long npix, float scale) {
+__global__ void scale_copy64_kernel(const __nv_bfloat16* __restrict__ src, int src_C, __nv_bfloat16* __restrict__ dst, int dst_C, long npix,
+                                    float scale) {
   const long total = npix * 8;
   for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long>(gridDim.x) * blockDim.x) {
     const long pix = i >> 3;
@@ -277,7 +282,7 @@ __global__ void scale_copy64_kernel(const __nv_bfloat16* __restrict__ src, int s
     o.y = pack_bf16x2(bf16lo(v.y) * scale, bf16hi(v.y) * scale);
     o.z = pack_bf16x2(bf16lo(v.z) * scale, bf16hi(v.z) * scale);
     o.w = pack_bf16x2(bf16lo(v.w) * scale, bf16hi(v.w) * scale);
-    *reinterpret_cast<uint4*>(dst + pix * 64 + c8 * 8) = o;
+    *reinterpret_cast<uint4*>(dst + pix * dst_C + c8 * 8) = o;
   }
 }
 
@@ -338,9 +343,9 @@ cudaError_t launch_bias_grad_planar(const float* g, long n, float scale, float* 
   return cudaGetLastError();
 }
 
-cudaError_t launch_scale_copy64(const void* src, int src_C, void* dst, long npix, float scale, cudaStream_t s) {
+cudaError_t launch_scale_copy64(const void* src, int src_C, void* dst, int dst_C, long npix, float scale, cudaStream_t s) {
   scale_copy64_kernel<<<grid_for(npix * 8, 256), 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(src), src_C,
-                                                              reinterpret_cast<__nv_bfloat16*>(dst), npix, scale);
+                                                              reinterpret_cast<__nv_bfloat16*>(dst), dst_C, npix, scale);
   return cudaGetLastError();
 }
 

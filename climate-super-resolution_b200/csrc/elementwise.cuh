@@ -6,6 +6,8 @@ namespace csr {
 struct PackJob {
   const float* w; const float* b; void* dst; float* bdst;
   int cout, cin, kh, kw, fold, phase, transposed; float wscale; int co_lo, npad, cin_pad;
+  int ci_lo, ci_n, src_ci_off, src_cin;   // block jobs (ci_n > 0): fill executed input channels [ci_lo, ci_lo+ci_n) from a source
+                                          // tensor of shape (ci_n, src_cin, kh, kw), its input channels offset by src_ci_off
 };
 cudaError_t launch_pack_jobs(const PackJob* jobs_dev, int njobs, cudaStream_t s);
 cudaError_t launch_pack_weight(const float* w, void* dst, int cout, int cin, int kh, int kw, int fold, int phase, int transposed,
@@ -20,5 +22,5 @@ cudaError_t launch_wgrad_scatter(const float* dacc, int ld_n, int n_parts, long 
 // db: nseg (1..4) bias-gradient vectors; channel co of the cout channels goes to db[co / (cout/nseg)]
 cudaError_t launch_bias_grad(const void* g, long npix, int C, int coff, int cout, float scale, float* const* db, int nseg, cudaStream_t s);
 cudaError_t launch_bias_grad_planar(const float* g, long n, float scale, float* db, cudaStream_t s);
-cudaError_t launch_scale_copy64(const void* src, int src_C, void* dst, long npix, float scale, cudaStream_t s);
+cudaError_t launch_scale_copy64(const void* src, int src_C, void* dst, int dst_C, long npix, float scale, cudaStream_t s);
 }  // namespace csr
