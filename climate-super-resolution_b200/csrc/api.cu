@@ -330,13 +330,13 @@ struct WgradLaunch {
 
 // One vertical tap of one 128-input-channel chunk: x channels [xc0, xc0+128) (beyond the buffer pitch -> zeros), output
 // gradients gA channels [gA_c0, +64) and optionally gB channels [gB_c0, +64) as GEMM columns [0,64) / [64,128).
-static int build_wgrad(int sms, int N, int H, int W, int KW, int PW, int dy_off, const void* x, int x_C, int xc0, const void* gA, int gA_C, int gA_c0,
-                       const void* gB, int gB_C, int gB_c0, int n_cols, float* dacc, int ld_n, WgradLaunch* wl) {
+static int build_wgrad(int sms, int N, int H, int W, int KW, int PW, int dy_off, int n_dy, const void* x, int x_C, int xc0, const void* gA, int gA_C,
+                       int gA_c0, const void* gB, int gB_C, int gB_c0, int n_cols, float* dacc, long part_stride, int ld_n, WgradLaunch* wl) {
   if (n_cols % 16 || n_cols < 16 || n_cols > 128) return fail(CSR_ERR_UNSUPPORTED, "wgrad: n_cols %d", n_cols);
   if (x_C % 8 || gA_C % 8 || xc0 % 8 || gA_c0 % 8) return fail(CSR_ERR_BAD_ARG, "wgrad: channel pitch/offset must be multiples of 8");
   WgradParams& p = wl->p;
   memset(&p, 0, sizeof(p));
-  p.N = N; p.H = H; p.W = W; p.KW = KW; p.PW = PW; p.dy_off = dy_off;
+  p.N = N; p.H = H; p.W = W; p.KW = KW; p.PW = PW; p.dy_off = dy_off; p.n_dy = n_dy;
   double best = -1;
   for (int SW = 16; SW <= 32; SW *= 2) {
     const int TW = SW - (KW - 1);
@@ -354,23 +354,23 @@ static int build_wgrad(int sms, int N, int H, int W, int KW, int PW, int dy_off,
   p.magic_img = ((1ull << 40) / (unsigned)p.tiles_per_img) + 1;
   p.magic_row = ((1ull << 40) / (unsigned)p.tiles_x) + 1;
   p.n_xbox = 2; p.n_gbox = gB ? 2 : 1; p.M = 128; p.n_cols = n_cols;
-  p.x_box_bytes = (p.TH + 1) * p.SW * 128;
+  p.x_box_bytes = (p.TH + n_dy) * p.SW * 128;
   p.g_box_bytes = p.TH * p.SW * 128;
   p.x_slack = 1024;
   p.stage_bytes = p.n_xbox * (p.x_slack + p.x_box_bytes) + p.n_gbox * p.g_box_bytes;
   p.n_stages = std::min(4, (kSmemLimit - 2048) / p.stage_bytes);
   if (p.n_stages < 1) return fail(CSR_ERR_UNSUPPORTED, "wgrad: stage does not fit shared memory");
   int cols = 32;
-  while (cols < KW * n_cols) cols *= 2;
-  if (cols > 512) return fail(CSR_ERR_UNSUPPORTED, "wgrad: KW*n_cols = %d exceeds TMEM", KW * n_cols);
+  while (cols < n_dy * KW * n_cols) cols *= 2;
+  if (cols > 512) return fail(CSR_ERR_UNSUPPORTED, "wgrad: n_dy*KW*n_cols = %d exceeds TMEM", n_dy * KW * n_cols);
   p.tmem_cols = cols;
   p.xc0[0] = xc0; p.xc0[1] = xc0 + 64;
   p.gc0[0] = gA_c0; p.gc0[1] = gB_c0;
-  p.dacc = dacc; p.ld_n = ld_n;
+  p.dacc = dacc; p.ld_n = ld_n; p.part_stride = part_stride;
   p.n_parts = std::min(p.num_tiles, sms);
   p.dbg_a_lbo = g_dbg_wgrad[0]; p.dbg_a_sbo = g_dbg_wgrad[1]; p.dbg_b_lbo = g_dbg_wgrad[2]; p.dbg_b_sbo = g_dbg_wgrad[3];
   p.dbg_flags = g_dbg_wgrad[4];
-  int rc = encode_act_map(&wl->tx0, x, N, H, W, x_C, p.SW, p.TH + 1);
+  int rc = encode_act_map(&wl->tx0, x, N, H, W, x_C, p.SW, p.TH + n_dy);
   if (rc) return rc;
   wl->tx1 = wl->tx0;
   rc = encode_act_map(&wl->tg0, gA, N, H, W, gA_C, p.SW, p.TH);
@@ -396,6 +396,8 @@ static size_t wgrad_scratch_floats(const WgradLayer& L) {
   const int ld_n = (L.cout + 15) / 16 * 16;
   return (size_t)ekh * kMaxParts * ekw * 128 * ld_n;
 }
+// vertical taps per launch: as many as fit the 512 TMEM columns
+static int wgrad_taps_per_launch(int ekw, int n_cols) { return std::max(1, 512 / (ekw * n_cols)); }
 
 static int encode_phase_map(CUtensorMap* m, const void* base, int N, int H, int W, int C, int phase, int box_w, int box_h) {
   // pixels (2y + a, 2x + b) of an (N, 2H, 2W, C) buffer as an (N, H, W, C) tensor
@@ -420,16 +422,17 @@ static int run_wgrad_layer(const WgradLayer& L, int N, int H, int W, const void*
   const int ecin = L.fold ? L.cin * L.kw : L.cin;
   const int ekh = L.up2 ? 2 : L.kh, ekw = L.up2 ? 2 : (L.fold ? 1 : L.kw);
   if (sms > kMaxParts) return fail(CSR_ERR_UNSUPPORTED, "wgrad: %d SMs > %d", sms, kMaxParts);
-  const long dy_stride = (long)kMaxParts * ekw * 128 * ld_n;
+  const long part_stride = (long)ekh * ekw * 128 * ld_n;
+  const int per = wgrad_taps_per_launch(ekw, ld_n);
   for (int phase = L.up2 ? 0 : -1; phase < (L.up2 ? 4 : 0); ++phase) {
     const int ph = L.up2 ? 1 - (phase >> 1) : L.kh / 2;
     const int pw = L.up2 ? 1 - (phase & 1) : (L.fold ? 0 : L.kw / 2);
     for (int ci0 = 0; ci0 < ecin; ci0 += 128) {
       int n_parts = 0;
-      for (int dy = 0; dy < ekh; ++dy) {
+      for (int dy = 0; dy < ekh; dy += per) {
         WgradLaunch wl;
-        int rc = build_wgrad(sms, N, H, W, ekw, pw, dy - ph, x, x_C, x_coff + ci0, g, g_C, g_coff, nullptr, 0, 0, ld_n,
-                             scratch + (size_t)dy * dy_stride, ld_n, &wl);
+        int rc = build_wgrad(sms, N, H, W, ekw, pw, dy - ph, std::min(per, ekh - dy), x, x_C, x_coff + ci0, g, g_C, g_coff, nullptr, 0, 0, ld_n,
+                             scratch + (size_t)dy * ekw * 128 * ld_n, part_stride, ld_n, &wl);
         n_parts = wl.p.n_parts;
         if (rc) return rc;
         if (phase >= 0) {
@@ -441,9 +444,9 @@ static int run_wgrad_layer(const WgradLayer& L, int N, int H, int W, const void*
         if (e) return fail(CSR_ERR_CUDA, "wgrad launch failed: %s", cudaGetErrorString((cudaError_t)e));
         ++*launches;
       }
-      CSR_CUDA(launch_wgrad_scatter(scratch, ld_n, n_parts, dy_stride, dw, L.cout, L.cin, L.kh, L.kw, L.fold, phase, ci0,
-                                    std::min(128, ecin - ci0), 0, scale, s));
-      ++*launches;
+      CSR_CUDA(launch_wgrad_reduce(scratch, part_stride, n_parts, part_stride, s));
+      CSR_CUDA(launch_wgrad_scatter(scratch, ld_n, dw, L.cout, L.cin, L.kh, L.kw, L.fold, phase, ci0, std::min(128, ecin - ci0), 0, scale, s));
+      *launches += 2;
     }
   }
   if (db) {
@@ -460,7 +463,7 @@ static int run_wgrad_layer(const WgradLayer& L, int N, int H, int W, const void*
 
 // Backward op list entry (training plans).
 struct BwdOp {
-  enum Kind { kConv, kWgrad, kScatter, kBias, kBiasPlanar, kScale, kMemset, kGoutPack } kind;
+  enum Kind { kConv, kWgrad, kReduce, kScatter, kBias, kBiasPlanar, kScale, kMemset, kGoutPack } kind;
   csr::ConvLaunch conv;          // kConv (dgrad); w_off/b_off index the BACKWARD packed blob
   csr::WgradLaunch wg;           // kWgrad
   // kScatter / kBias*: which forward layer's gradient, and how
@@ -741,13 +744,14 @@ static int bwd_build(CsrPlan* P, void* ws) {
     for (int phase = Ls.up2 ? 0 : -1; phase < (Ls.up2 ? 4 : 0); ++phase) {
       const int ph = Ls.up2 ? 1 - (phase >> 1) : Ls.kh / 2;
       const int pw = Ls.up2 ? 1 - (phase & 1) : (Ls.fold ? 0 : Ls.kw / 2);
-      const long dy_stride = (long)kMaxParts * ekw * 128 * ld_n;
+      const long part_stride = (long)ekh * ekw * 128 * ld_n;
+      const int per = wgrad_taps_per_launch(ekw, ld_n);
       for (int ci0 = 0; ci0 < ecin; ci0 += 128) {
         int n_parts = 0;
-        for (int dy = 0; dy < ekh; ++dy) {
+        for (int dy = 0; dy < ekh; dy += per) {
           BwdOp op; op.kind = BwdOp::kWgrad;
-          int rc = build_wgrad(P->sms, N, Hh, Ww, ekw, pw, dy - ph, x, x_C, x_coff + ci0, g, g_C, g_coff, nullptr, 0, 0, ld_n,
-                               dacc + (size_t)dy * dy_stride, ld_n, &op.wg);
+          int rc = build_wgrad(P->sms, N, Hh, Ww, ekw, pw, dy - ph, std::min(per, ekh - dy), x, x_C, x_coff + ci0, g, g_C, g_coff, nullptr, 0, 0,
+                               ld_n, dacc + (size_t)dy * ekw * 128 * ld_n, part_stride, ld_n, &op.wg);
           if (rc) return rc;
           n_parts = op.wg.p.n_parts;
           if (phase >= 0) {
@@ -757,8 +761,10 @@ static int bwd_build(CsrPlan* P, void* ws) {
           }
           ops.push_back(op);
         }
+        BwdOp rd; rd.kind = BwdOp::kReduce; rd.n_parts = n_parts; rd.dy_stride = part_stride; rd.count = part_stride;
+        ops.push_back(rd);
         BwdOp sc; sc.kind = BwdOp::kScatter; sc.layer = layer; sc.fold = Ls.fold; sc.phase = phase; sc.ci0 = ci0;
-        sc.ci_n = std::min(128, ecin - ci0); sc.col0 = 0; sc.ld_n = ld_n; sc.scale = scale; sc.n_parts = n_parts; sc.dy_stride = dy_stride;
+        sc.ci_n = std::min(128, ecin - ci0); sc.col0 = 0; sc.ld_n = ld_n; sc.scale = scale;
         ops.push_back(sc);
       }
     }
@@ -857,19 +863,21 @@ static int bwd_build(CsrPlan* P, void* ws) {
           rc = wgrad_plain(fwd_index_rdb(i, r, 5), h, w, cat(j), C, 0, Gb, C, 0, 0.2f);
           if (rc) return rc;
         } else {
-          const long dy_stride = (long)kMaxParts * 3 * 128 * 128;
+          const long part_stride = (long)9 * 128 * 128;
           int n_parts = 0;
           for (int dy = 0; dy < 3; ++dy) {
             BwdOp op; op.kind = BwdOp::kWgrad;
-            rc = build_wgrad(P->sms, N, h, w, 3, 1, dy - 1, cat(j), C, 0, Gb, C, nf, Gb, C, 0, 128, dacc + (size_t)dy * dy_stride, 128, &op.wg);
+            rc = build_wgrad(P->sms, N, h, w, 3, 1, dy - 1, 1, cat(j), C, 0, Gb, C, nf, Gb, C, 0, 128, dacc + (size_t)dy * 3 * 128 * 128, part_stride,
+                             128, &op.wg);
             if (rc) return rc;
             n_parts = op.wg.p.n_parts;
             ops.push_back(op);
           }
+          { BwdOp rd; rd.kind = BwdOp::kReduce; rd.n_parts = n_parts; rd.dy_stride = part_stride; rd.count = part_stride; ops.push_back(rd); }
           for (int k = 1; k <= 5; ++k) {
             const int layer = fwd_index_rdb(i, r, k);
             BwdOp sc; sc.kind = BwdOp::kScatter; sc.layer = layer; sc.ci0 = 0; sc.ci_n = (k < 5) ? nf + (k - 1) * gc : nf + 4 * gc;
-            sc.col0 = (k < 5) ? (4 - k) * gc : 64; sc.ld_n = 128; sc.scale = (k < 5) ? 1.f : 0.2f; sc.n_parts = n_parts; sc.dy_stride = dy_stride;
+            sc.col0 = (k < 5) ? (4 - k) * gc : 64; sc.ld_n = 128; sc.scale = (k < 5) ? 1.f : 0.2f;
             ops.push_back(sc);
           }
           // bias gradients: the four narrow convs in one pass over the gradient-concat slices, conv5 from g_y
@@ -1126,11 +1134,14 @@ int csr_plan_backward(CsrPlan* P, const void* packed_bwd, const float* grad_out,
         if (e) return fail(CSR_ERR_CUDA, "wgrad launch failed: %s", cudaGetErrorString((cudaError_t)e));
         break;
       }
+      case BwdOp::kReduce:
+        CSR_CUDA(launch_wgrad_reduce(P->dacc, op.dy_stride, op.n_parts, op.count, s));
+        break;
       case BwdOp::kScatter: {
         const LayerSpec& L = P->fwd_layers[op.layer];
         if (!dw[op.layer]) return fail(CSR_ERR_BAD_ARG, "null weight-gradient pointer for layer %d", op.layer);
-        CSR_CUDA(launch_wgrad_scatter(P->dacc, op.ld_n, op.n_parts, op.dy_stride, dw[op.layer], L.cout, L.cin, L.kh, L.kw, op.fold, op.phase,
-                                      op.ci0, op.ci_n, op.col0, op.scale, s));
+        CSR_CUDA(launch_wgrad_scatter(P->dacc, op.ld_n, dw[op.layer], L.cout, L.cin, L.kh, L.kw, op.fold, op.phase, op.ci0, op.ci_n, op.col0,
+                                      op.scale, s));
         break;
       }
       case BwdOp::kBias: {

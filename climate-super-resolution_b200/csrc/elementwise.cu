@@ -175,13 +175,25 @@ __global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ src, float
 }
 
 // ---- weight-gradient post-processing ---------------------------------------------------------------------
-// dacc: fp32 [KH_e][n_parts][KW_e][128][ld_n] per-CTA partial sums produced by wgrad_tc_kernel (executed taps KH_e x KW_e,
-// rows = executed input channel - ci0, columns = output channel + col0).  Reduces over the parts (fixed order ->
-// deterministic) and adds scale * sum into the layer's OIHW gradient:
+// dacc: fp32 [KH_e][KW_e][128][ld_n] sums (wgrad_tc_kernel's per-CTA partials after wgrad_reduce_kernel; executed taps
+// KH_e x KW_e, rows = executed input channel - ci0, columns = output channel + col0).  Adds scale * dacc into the layer's
+// OIHW gradient:
 //   plain : dw[co][ci][dy][dx]                          += dacc[dy][dx][ci - ci0][col0 + co]
 //   fold  : dw[co][c][dy][dx]  (executed channel dx*cin+c, KW_e = 1)  += dacc[dy][0][dx*cin + c - ci0][col0 + co]
 //   phase : executed 2x2 taps (ry, rx) of sub-pixel phase (a,b) feed every 3x3 tap they were summed from
-__global__ void wgrad_scatter_kernel(const float* __restrict__ dacc, int ld_n, int n_parts, long dy_stride, float* __restrict__ dw, int cout,
+// part 0 += parts 1..n_parts-1 (fixed order -> deterministic), fully coalesced
+__global__ void wgrad_reduce_kernel(float* __restrict__ dacc, long part_stride, int n_parts, long n4) {
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n4; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    float4 a = reinterpret_cast<const float4*>(dacc)[i];
+    for (int q = 1; q < n_parts; ++q) {
+      const float4 b = reinterpret_cast<const float4*>(dacc + q * part_stride)[i];
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    reinterpret_cast<float4*>(dacc)[i] = a;
+  }
+}
+
+__global__ void wgrad_scatter_kernel(const float* __restrict__ dacc, int ld_n, float* __restrict__ dw, int cout,
                                      int cin, int kh, int kw, int fold, int phase, int ci0, int ci_n, int col0, float scale) {
   const int ekh = phase >= 0 ? 2 : kh;
   const int ekw = phase >= 0 ? 2 : (fold ? 1 : kw);
@@ -192,12 +204,7 @@ __global__ void wgrad_scatter_kernel(const float* __restrict__ dacc, int ld_n, i
     const int cl = r % ci_n;                               // executed input channel - ci0
     r /= ci_n;
     const int dx = r % ekw, dy = r / ekw;
-    // dacc: [dy (stride dy_stride)][part][dx][128][ld_n]
-    const float* src = dacc + dy * dy_stride + (static_cast<long>(dx) * 128 + cl) * ld_n + col0 + co;
-    const long part_stride = static_cast<long>(ekw) * 128 * ld_n;
-    float acc = 0.f;
-    for (int q = 0; q < n_parts; ++q) acc += src[q * part_stride];
-    const float v = scale * acc;
+    const float v = scale * dacc[((static_cast<long>(dy) * ekw + dx) * 128 + cl) * ld_n + col0 + co];
     const int ce = ci0 + cl;                               // executed input channel
     if (phase >= 0) {
       if (ce >= cin) continue;
@@ -232,7 +239,23 @@ __global__ void bias_grad_kernel(const __nv_bfloat16* __restrict__ g, long npix,
   const int sub = threadIdx.x % lanes_per_pix, prow = threadIdx.x / lanes_per_pix;
   float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (prow < pix_per_iter) {
-    for (long pix = blockIdx.x * static_cast<long>(pix_per_iter) + prow; pix < npix; pix += static_cast<long>(gridDim.x) * pix_per_iter) {
+    const long stride = static_cast<long>(gridDim.x) * pix_per_iter;
+    long pix = blockIdx.x * static_cast<long>(pix_per_iter) + prow;
+    for (; pix + 3 * stride < npix; pix += 4 * stride) {   // four independent 16-byte loads in flight per thread
+      uint4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = *reinterpret_cast<const uint4*>(g + (pix + u * stride) * C + coff + sub * 8);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          acc[2 * k] += bf16lo(w[k]);
+          acc[2 * k + 1] += bf16hi(w[k]);
+        }
+      }
+    }
+    for (; pix < npix; pix += stride) {
       const uint4 v = *reinterpret_cast<const uint4*>(g + pix * C + coff + sub * 8);
       const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
@@ -323,12 +346,16 @@ cudaError_t launch_nhwc_to_nchw(const void* src, float* dst, int n, int c, int h
   return cudaGetLastError();
 }
 
-cudaError_t launch_wgrad_scatter(const float* dacc, int ld_n, int n_parts, long dy_stride, float* dw, int cout, int cin, int kh, int kw, int fold,
+cudaError_t launch_wgrad_reduce(float* dacc, long part_stride, int n_parts, long nfloats, cudaStream_t s) {
+  if (n_parts <= 1) return cudaSuccess;
+  wgrad_reduce_kernel<<<grid_for(nfloats / 4, 256, 148 * 8), 256, 0, s>>>(dacc, part_stride, n_parts, nfloats / 4);
+  return cudaGetLastError();
+}
+cudaError_t launch_wgrad_scatter(const float* dacc, int ld_n, float* dw, int cout, int cin, int kh, int kw, int fold,
                                  int phase, int ci0, int ci_n, int col0, float scale, cudaStream_t s) {
   const int ekh = phase >= 0 ? 2 : kh, ekw = phase >= 0 ? 2 : (fold ? 1 : kw);
   const long total = static_cast<long>(ekh) * ekw * ci_n * cout;
-  wgrad_scatter_kernel<<<grid_for(total, 256), 256, 0, s>>>(dacc, ld_n, n_parts, dy_stride, dw, cout, cin, kh, kw, fold, phase, ci0, ci_n,
-                                                            col0, scale);
+  wgrad_scatter_kernel<<<grid_for(total, 256), 256, 0, s>>>(dacc, ld_n, dw, cout, cin, kh, kw, fold, phase, ci0, ci_n, col0, scale);
   return cudaGetLastError();
 }
 cudaError_t launch_bias_grad(const void* g, long npix, int C, int coff, int cout, float scale, float* const* db, int nseg, cudaStream_t s) {

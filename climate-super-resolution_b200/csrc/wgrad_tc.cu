@@ -8,8 +8,8 @@
 //
 //   D_dx[ci][co] (fp32, TMEM, 128 lanes x n_cols columns per horizontal tap)  +=  X_shift(dx)[K=16 pixels][128 ci]^T * G[K][n_cols]
 //
-// One launch handles one vertical tap: the x window is loaded at row offset dy_off, and the horizontal taps are read
-// from the same window at flattened pixel offsets dx-PW (the halo trick of the forward kernel, transposed).  Columns
+// One launch handles n_dy consecutive vertical taps (as many as fit the 512 TMEM columns): the x window is loaded once
+// at row offset dy_off and every tap (dyi, dx) reads it at the flattened pixel offset dyi*SW + dx - PW (the halo trick of the forward kernel, transposed).  Columns
 // of the g tile that belong to the neighbouring tiles are zeroed in shared memory so every pixel is counted once.
 // Accumulators stay resident in TMEM over ALL tiles of the persistent CTA; one epilogue at the end stores the CTA's
 // partial sums to its slice of a global fp32 buffer, reduced over CTAs by the scatter kernel.
@@ -120,14 +120,16 @@ wgrad_tc_kernel(const WgradParams p, const __grid_constant__ CUtensorMap tx0, co
       tc_fence_after();
       const uint32_t sb = smem_base + stage * p.stage_bytes;
       if (elect_one()) {
-        for (int dx = 0; dx < p.KW; ++dx) {
-          const uint32_t d_tmem = tmem_base + dx * p.n_cols;
-          // flattened pixel shift of this tap inside the window: dx - PW lines of 128 B
-          const uint32_t a0 = sb + p.x_slack + static_cast<uint32_t>((dx - p.PW) * 128);
-          for (int j = 0; j < 8; ++j) {
-            const uint32_t a_lo = (((a0 + j * 2048u) >> 4) & 0x3FFFu) | a_lo_fixed;
-            const uint32_t b_lo = (((sb + g_off + j * 2048u) >> 4) & 0x3FFFu) | b_lo_fixed;
-            umma_bf16_split(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, (first && j == 0) ? 0u : 1u);
+        for (int dyi = 0; dyi < p.n_dy; ++dyi) {
+          for (int dx = 0; dx < p.KW; ++dx) {
+            const uint32_t d_tmem = tmem_base + (dyi * p.KW + dx) * p.n_cols;
+            // flattened pixel shift of this tap inside the window: dyi rows + (dx - PW) pixels, 128 B each
+            const uint32_t a0 = sb + p.x_slack + static_cast<uint32_t>((dyi * p.SW + dx - p.PW) * 128);
+            for (int j = 0; j < 8; ++j) {
+              const uint32_t a_lo = (((a0 + j * 2048u) >> 4) & 0x3FFFu) | a_lo_fixed;
+              const uint32_t b_lo = (((sb + g_off + j * 2048u) >> 4) & 0x3FFFu) | b_lo_fixed;
+              umma_bf16_split(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, (first && j == 0) ? 0u : 1u);
+            }
           }
         }
         umma_commit(bar_empty(stage));
@@ -174,12 +176,12 @@ wgrad_tc_kernel(const WgradParams p, const __grid_constant__ CUtensorMap tx0, co
       // this CTA's partial sums go to its own slice of the accumulation buffer ([cta][dx][128][ld_n], plain stores);
       // the scatter kernel reduces over CTAs.  (fp32 atomics onto 49 K shared addresses from 148 CTAs were measured at
       // ~100 us per launch - 5x the GEMM itself.)
-      float* base = p.dacc + static_cast<size_t>(blockIdx.x) * p.KW * 128 * p.ld_n;
-      for (int dx = 0; dx < p.KW; ++dx) {
-        float* dst = base + (static_cast<size_t>(dx) * 128 + ci) * p.ld_n;
+      float* base = p.dacc + static_cast<size_t>(blockIdx.x) * p.part_stride;
+      for (int tp = 0; tp < p.n_dy * p.KW; ++tp) {
+        float* dst = base + (static_cast<size_t>(tp) * 128 + ci) * p.ld_n;
         for (int c = 0; c < p.n_cols; c += 8) {
           uint32_t r[8];
-          tmem_ld8(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + dx * p.n_cols + c, r);
+          tmem_ld8(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + tp * p.n_cols + c, r);
           tmem_ld_wait();
           *reinterpret_cast<uint4*>(dst + c) = make_uint4(r[0], r[1], r[2], r[3]);
           *reinterpret_cast<uint4*>(dst + c + 4) = make_uint4(r[4], r[5], r[6], r[7]);
