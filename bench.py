@@ -61,6 +61,30 @@ def load_peaks():
     return {"bf16_burst": 1590.0, "bf16_sustained": 1400.0, "hbm": 6650.0, "source": "fallback"}
 
 
+class _stdout_to_stderr:
+    """NCCL prints its version banner on stdout at communicator creation; the bench contract is ONE JSON line on stdout."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self._saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *a):
+        sys.stdout.flush()
+        os.dup2(self._saved, 1)
+        os.close(self._saved)
+
+
+def init_distributed(local):
+    import torch
+    import torch.distributed as dist
+    with _stdout_to_stderr():
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.barrier()
+        torch.cuda.synchronize()
+
+
 class ClockSampler:
     """Samples SM clock and throttle reasons of one GPU while the timed region runs (pynvml, 100 ms period)."""
 
@@ -170,7 +194,7 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        init_distributed(local)
     device_check()
     dev = torch.device("cuda", local)
     in_ch, nb, gc, tiles, h, w = WORKLOADS[args.workload]
@@ -281,7 +305,7 @@ def run_train(args):
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        init_distributed(local)
     device_check()
     dev = torch.device("cuda", local)
     in_ch, nb, gc, tiles, h, w = WORKLOADS[args.workload]
@@ -322,7 +346,7 @@ def run_train(args):
     for _ in range(max(args.warmup, 3)):
         lv = step()
     barrier()
-    first_loss = float(lv)
+    first_loss = float(lv.detach())
     l0 = kernel_launch_count()
     with ClockSampler(local) as clk:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -334,7 +358,7 @@ def run_train(args):
         barrier()
         ms_step = max_over_ranks(e0.elapsed_time(e1) / args.steps)
     launches = kernel_launch_count() - l0
-    last_loss = float(lv)
+    last_loss = float(lv.detach())
     # end to end: batch from pinned host memory each step, loss read back
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()

@@ -64,8 +64,13 @@ class GradientBucketer:
         ctx = torch.cuda.stream(self._stream) if on_cuda else _null()
         with ctx:
             for bucket in self.buckets:
-                grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in bucket]
-                flat = torch.cat([g.reshape(-1).to(self.comm_dtype or g.dtype) for g in grads])
+                for p in bucket:
+                    if p.grad is None:
+                        p.grad = torch.zeros_like(p)
+                # one concatenation + one cast per bucket (not per parameter): the step must not become launch-bound
+                flat = torch.cat([p.grad.reshape(-1) for p in bucket])
+                if self.comm_dtype is not None and flat.dtype != self.comm_dtype:
+                    flat = flat.to(self.comm_dtype)
                 work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
                 self._pending.append((bucket, flat, work))
 
@@ -80,15 +85,9 @@ class GradientBucketer:
         with ctx:
             for bucket, flat, work in self._pending:
                 work.wait()
-                off = 0
-                for p in bucket:
-                    n = p.numel()
-                    avg = (flat[off:off + n].to(torch.float32) * inv).view_as(p)
-                    if p.grad is None:
-                        p.grad = avg.clone()
-                    else:
-                        p.grad.copy_(avg)
-                    off += n
+                avg = flat.to(torch.float32).mul_(inv)
+                parts = torch.split(avg, [p.numel() for p in bucket])
+                torch._foreach_copy_([p.grad for p in bucket], [t.view_as(p) for t, p in zip(parts, bucket)])   # one multi-tensor kernel
         if on_cuda:
             done = torch.cuda.Event()
             done.record(self._stream)
