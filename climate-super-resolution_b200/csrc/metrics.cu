@@ -40,9 +40,9 @@ __device__ __forceinline__ void acc_pixel(Acc& a, float sr, float hr, float orig
   a.s[9] += d * d;
   a.s[10] += org;
   a.s[11] += org * org;
-  a.s[12] += 2.f * d / fmaxf(fabsf(org) + fabsf(dsr), kMapeEps);
+  a.s[12] += __fdividef(2.f * d, fmaxf(fabsf(org) + fabsf(dsr), kMapeEps));   // fast division: 2 ulp, metrics are held to 1e-4
   const float dn = fabsf(srn - hrn);
-  a.s[13] += dn / fmaxf(fabsf(hrn), kMapeEps);
+  a.s[13] += __fdividef(dn, fmaxf(fabsf(hrn), kMapeEps));
   a.s[14] += dn;
   a.s[15] += dn * dn;
   a.mn[0] = fminf(a.mn[0], org); a.mx[0] = fmaxf(a.mx[0], org);
@@ -130,24 +130,41 @@ metrics_pass1_kernel(const float* __restrict__ sr, const float* __restrict__ hr,
   }
 }
 
-// Single block: fixed-order reduction of the pass-1 partials -> totals[kPart] (double) and SSIM constants c1,c2.
-__global__ void metrics_reduce1_kernel(const double* __restrict__ partials, int nblocks, double* __restrict__ totals, float* __restrict__ c12) {
-  __shared__ double sh[kPart];
-  if (threadIdx.x < kPart) {
-    const int i = threadIdx.x;
-    double v = partials[i];
-    for (int b = 1; b < nblocks; ++b) {
-      const double q = partials[static_cast<long>(b) * kPart + i];
-      if (i < kSums) v += q;
-      else v = ((i - kSums) & 1) ? fmax(v, q) : fmin(v, q);
+// Single block of 256 threads: fixed-order (deterministic) tree reduction of the pass-1 partials -> totals[kPart] (double)
+// and the SSIM constants c1, c2.  Thread t owns partial-block slice t, t+256, ... for every quantity; the tree then
+// combines the 256 lane sums in a fixed pattern.
+__global__ void __launch_bounds__(256)
+metrics_reduce1_kernel(const double* __restrict__ partials, int nblocks, double* __restrict__ totals, float* __restrict__ c12) {
+  __shared__ double sh[kPart][256];
+  __shared__ double tot[kPart];
+  const int t = threadIdx.x;
+  for (int i = 0; i < kPart; ++i) {
+    const bool is_sum = i < kSums, is_max = ((i - kSums) & 1) != 0;
+    double v = is_sum ? 0.0 : (is_max ? -DBL_MAX : DBL_MAX);
+    for (int bk = t; bk < nblocks; bk += 256) {
+      const double q = partials[static_cast<long>(bk) * kPart + i];
+      v = is_sum ? v + q : (is_max ? fmax(v, q) : fmin(v, q));
     }
-    totals[i] = v;
-    sh[i] = v;
+    sh[i][t] = v;
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
+  for (int stride = 128; stride > 0; stride >>= 1) {
+    if (t < stride)
+      for (int i = 0; i < kPart; ++i) {
+        const bool is_sum = i < kSums, is_max = ((i - kSums) & 1) != 0;
+        const double a = sh[i][t], q = sh[i][t + stride];
+        sh[i][t] = is_sum ? a + q : (is_max ? fmax(a, q) : fmin(a, q));
+      }
+    __syncthreads();
+  }
+  if (t < kPart) {
+    totals[t] = sh[t][0];
+    tot[t] = sh[t][0];
+  }
+  __syncthreads();
+  if (t == 0) {
     // torchmetrics SSIM: data_range = max(p.max()-p.min(), t.max()-t.min()); c = (k*range)^2
-    const double range = fmax(sh[kSums + 3] - sh[kSums + 2], sh[kSums + 5] - sh[kSums + 4]);
+    const double range = fmax(tot[kSums + 3] - tot[kSums + 2], tot[kSums + 5] - tot[kSums + 4]);
     c12[0] = static_cast<float>((0.01 * range) * (0.01 * range));
     c12[1] = static_cast<float>((0.03 * range) * (0.03 * range));
   }
@@ -219,11 +236,20 @@ ssim_kernel(const float* __restrict__ sr, const float* __restrict__ hr, const fl
 }
 
 // Single block: SSIM partial sum + closed forms of the 16 metrics and the two losses.
-__global__ void metrics_final_kernel(const double* __restrict__ totals, const double* __restrict__ ssim_partials, int n_ssim, double n_pix,
-                                     double n_ssim_pix, float* __restrict__ out) {
+__global__ void __launch_bounds__(256)
+metrics_final_kernel(const double* __restrict__ totals, const double* __restrict__ ssim_partials, int n_ssim, double n_pix,
+                     double n_ssim_pix, float* __restrict__ out) {
+  __shared__ double sh[256];
+  double part = 0;
+  for (int i = threadIdx.x; i < n_ssim; i += 256) part += ssim_partials[i];      // fixed assignment + fixed tree: deterministic
+  sh[threadIdx.x] = part;
+  __syncthreads();
+  for (int stride = 128; stride > 0; stride >>= 1) {
+    if (threadIdx.x < stride) sh[threadIdx.x] += sh[threadIdx.x + stride];
+    __syncthreads();
+  }
   if (threadIdx.x != 0) return;
-  double ssim = 0;
-  for (int i = 0; i < n_ssim; ++i) ssim += ssim_partials[i];
+  const double ssim = sh[0];
   const double* t = totals;
   for (int k = 0; k < 8; ++k) out[k] = static_cast<float>(t[k] / n_pix);             // RegressionAccuracy.compute
   const double mse = t[9] / n_pix;
@@ -243,7 +269,7 @@ __global__ void metrics_final_kernel(const double* __restrict__ totals, const do
 
 int p1_blocks_per_image(int n, long hw) {
   long want = (hw / 4 + kP1Threads * 4 - 1) / (kP1Threads * 4);   // >= 4 groups per thread
-  long cap = (148L * 8 + n - 1) / n;
+  long cap = (148L * 4 + n - 1) / n;
   if (want > cap) want = cap;
   if (want < 1) want = 1;
   return static_cast<int>(want);
@@ -282,9 +308,9 @@ cudaError_t launch_masked_metrics(const float* sr, const float* hr, const float*
   float* c12 = reinterpret_cast<float*>(totals + kPart);
   double* ssim_part = reinterpret_cast<double*>(reinterpret_cast<uint8_t*>(c12) + 64);
   metrics_pass1_kernel<<<dim3(bpi, n), kP1Threads, 0, s>>>(sr, hr, orig, mask, mn, mx, zmean, zstd, ra, rb, hw, partials);
-  metrics_reduce1_kernel<<<1, 32, 0, s>>>(partials, bpi * n, totals, c12);
+  metrics_reduce1_kernel<<<1, 256, 0, s>>>(partials, bpi * n, totals, c12);
   ssim_kernel<<<dim3(gx, gy, n), 256, 0, s>>>(sr, hr, mask, h, w, c12, ssim_part);
-  metrics_final_kernel<<<1, 32, 0, s>>>(totals, ssim_part, ssim_blocks, static_cast<double>(hw) * n,
+  metrics_final_kernel<<<1, 256, 0, s>>>(totals, ssim_part, ssim_blocks, static_cast<double>(hw) * n,
                                         static_cast<double>(n) * (h - 10) * (w - 10), out);
   *launches = 4;
   return cudaGetLastError();
