@@ -30,6 +30,7 @@ static int g_opt_no_tma_store = 0;
 static int g_opt_two_acc = 0;
 static int g_opt_force_generic = 0;
 static int g_opt_one_mma = 0;
+static int g_opt_no_single_group = 1;   // measured: merging the groups buys a 3rd window slot for RDB conv5 but the single group then paces the tile (no net gain)
 static int g_dbg_wgrad[5] = {0, 0, 0, 0, 0};   // a_lbo, a_sbo, b_lbo, b_sbo, flags overrides of the MN-major descriptors
 static int g_opt_no_direct32 = 1;   // measured: no gain over staging on cfg2 (tools/ab_bench.py), kept as an option
 
@@ -204,7 +205,7 @@ static std::vector<PackLayer> pack_layout(const std::vector<LayerSpec>& layers, 
 struct Tiling {
   int SW, TH, TW, win_rows, win_bytes, slot_bytes, n_slots, stage_bytes;
 };
-static int choose_tiling(int H, int W, int KH, int KW, int w_bytes, int n_kblocks, int stage_row_bytes, Tiling* out) {
+static int choose_tiling(int H, int W, int KH, int KW, int w_bytes, int n_kblocks, int stage_row_bytes, int n_stage, Tiling* out) {
   double best = -1;
   for (int SW = 16; SW <= 128; SW *= 2) {
     if (g_opt_force_sw && SW != g_opt_force_sw) continue;
@@ -217,7 +218,7 @@ static int choose_tiling(int H, int W, int KH, int KW, int w_bytes, int n_kblock
     const int win_bytes = win_rows * SW * 128;
     const int slot_bytes = (int)align_up(win_bytes, 1024);
     const int stage_bytes = stage_row_bytes ? (int)align_up((size_t)TH * TW * stage_row_bytes, 1024) : 0;
-    const int fixed = 1024 + (int)align_up(w_bytes, 128) + 256 + 512 + (stage_row_bytes <= 64 ? 4 : 2) * stage_bytes;
+    const int fixed = 1024 + (int)align_up(w_bytes, 128) + 256 + 512 + n_stage * stage_bytes;
     const int slots = std::min(g_opt_max_slots, (kSmemLimit - fixed) / slot_bytes);
     if (slots < 1) continue;
     const double tiles = (double)ceil_div(H, TH) * ceil_div(W, TW);
@@ -269,15 +270,28 @@ static int build_conv(const PackLayer& pl, const PackPart& pp, int N, int H, int
   const bool tma_out = io.out_kind == kOutBf16 && pp.n_store % 8 == 0 && !g_opt_no_tma_store;
   p.store_mode = tma_out ? kStoreStaged : io.out_kind == kOutBf16 ? kStoreDirect : io.out_kind == kOutF32Planar ? kStoreF32Planar : kStoreF32Nhwc;
   p.stage_row_bytes = tma_out ? pp.n_store * 2 : 0;
+  // four tiles in flight in the epilogue when four accumulators fit in TMEM and a warp then owns <= 4 chunks of 8 channels
+  p.n_acc = (4 * p.KW * p.npad <= 512 && p.npad <= 32 && !g_opt_two_acc) ? 4 : 2;
+  p.n_groups = p.n_acc;
   Tiling tl;
-  int rc = choose_tiling(H, W, pp.kh, pp.kw, p.w_bytes, p.n_kblocks, p.stage_row_bytes, &tl);
+  int rc = choose_tiling(H, W, pp.kh, pp.kw, p.w_bytes, p.n_kblocks, p.stage_row_bytes, p.n_groups, &tl);
   if (rc) return rc;
+  if (tma_out && p.n_groups == 2 && tl.n_slots < 3 && !g_opt_no_single_group) {
+    // Weights leave little shared memory (RDB conv5: 144 KB): one epilogue group (16 warps, still two accumulator
+    // buffers) needs one staging buffer instead of two, which buys a third window slot - the MMAs of such a layer take
+    // far longer than its epilogue, and with two slots every tile waited ~2400 clk for its TMA load.
+    Tiling t1;
+    if (choose_tiling(H, W, pp.kh, pp.kw, p.w_bytes, p.n_kblocks, p.stage_row_bytes, 1, &t1) == CSR_OK && t1.n_slots > tl.n_slots) {
+      tl = t1;
+      p.n_groups = 1;
+    }
+  }
   if (tma_out && tl.n_slots < 2 * p.n_kblocks && pp.n_store % 16 == 0 && io.out_C % 16 == 0 && (io.out_coff + pp.co_lo) % 16 == 0 &&
       !g_opt_no_direct32) {
     // The resident weights leave too little shared memory for staging AND a window ring that prefetches across tiles
     // (RDB conv5: 144 KB of weights): store whole 32-byte sectors straight from registers instead.
     Tiling t2;
-    if (choose_tiling(H, W, pp.kh, pp.kw, p.w_bytes, p.n_kblocks, 0, &t2) == CSR_OK && t2.n_slots >= 2 * p.n_kblocks) {
+    if (choose_tiling(H, W, pp.kh, pp.kw, p.w_bytes, p.n_kblocks, 0, 0, &t2) == CSR_OK && t2.n_slots >= 2 * p.n_kblocks) {
       tl = t2;
       p.store_mode = kStoreDirect32;
       p.stage_row_bytes = 0;
@@ -296,9 +310,7 @@ static int build_conv(const PackLayer& pl, const PackPart& pp, int N, int H, int
   p.magic_row = ((1ull << 40) / (unsigned)p.tiles_x) + 1;
   p.win_rows = tl.win_rows; p.win_bytes = tl.win_bytes; p.slot_bytes = tl.slot_bytes; p.n_slots = tl.n_slots;
   p.stage_bytes = tl.stage_bytes;
-  // four tiles in flight in the epilogue when four accumulators fit in TMEM and a warp then owns <= 4 chunks of 8 channels
   p.n_mma = g_opt_one_mma ? 1 : 2;
-  p.n_acc = (4 * p.KW * p.npad <= 512 && p.npad <= 32 && !g_opt_two_acc) ? 4 : 2;
   int cols = 32;
   while (cols < p.n_acc * p.KW * p.npad) cols *= 2;
   if (cols > 512 || p.KW * p.npad > 256) return fail(CSR_ERR_UNSUPPORTED, "KW*npad = %d exceeds the UMMA N / TMEM budget", p.KW * p.npad);
@@ -944,6 +956,7 @@ int csr_set_option(int32_t key, int32_t value) {
     case 5: g_opt_two_acc = value ? 1 : 0; return CSR_OK;
     case 6: g_opt_force_generic = value ? 1 : 0; return CSR_OK;
     case 7: g_opt_one_mma = value ? 1 : 0; return CSR_OK;
+    case 9: g_opt_no_single_group = value ? 1 : 0; return CSR_OK;  // 0: one epilogue group (one staging buffer) when that deepens the window ring
     case 8: g_opt_no_direct32 = value ? 1 : 0; return CSR_OK;    // 0: allow unstaged 32-byte stores when staging starves the window ring        // debug: a single MMA issuer warp  // debug: runtime-switched kernels only        // debug: never use four accumulator buffers   // debug: per-element global stores instead of the staged copy-out
     case 20: case 21: case 22: case 23: case 24: g_dbg_wgrad[key - 20] = value; return CSR_OK;
     default: return fail(CSR_ERR_BAD_ARG, "unknown option key %d", key);

@@ -115,13 +115,14 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t slots_addr = smem_base;
   const uint32_t stage_addr = slots_addr + static_cast<uint32_t>(p.n_slots) * p.slot_bytes;   // one staging buffer per epilogue group
-  const uint32_t w_addr = stage_addr + static_cast<uint32_t>(p.n_acc) * p.stage_bytes;
+  const uint32_t w_addr = stage_addr + static_cast<uint32_t>(p.n_groups) * p.stage_bytes;
   const uint32_t bias_addr = w_addr + ((p.w_bytes + 127) & ~127);
   const uint32_t bar_addr = bias_addr + 256;            // up to 64 fp32 biases
   // barriers: [0] weights, [1..S] a_full, [1+S..2S] a_empty, then acc_full[4], acc_empty[4]
   const int S = p.n_slots;
-  const int NA = p.n_acc;                               // accumulator buffers in TMEM == epilogue groups (2 or 4)
-  const int wpg = kEpilogueWarps / NA;                  // warps per epilogue group
+  const int NA = p.n_acc;                               // accumulator buffers in TMEM (2 or 4)
+  const int NG = p.n_groups;                            // epilogue warp groups (1, 2 or 4; NG <= NA): tiles in flight in the epilogue
+  const int wpg = kEpilogueWarps / NG;                  // warps per epilogue group
   auto bar_w = bar_addr;
   auto bar_a_full = [&](int s) { return bar_addr + 8u * (1 + s); };
   auto bar_a_empty = [&](int s) { return bar_addr + 8u * (1 + S + s); };
@@ -275,18 +276,18 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
       if (buf >= NA) { buf -= NA; acc_phase ^= 1; }
     }
   } else {
-    // ===================== epilogue: 16 warps in NA groups; group g owns accumulator buffer g and every NA-th tile ====
+    // ===================== epilogue: 16 warps in NG groups; group g takes every NG-th tile (accumulator buffer = tile % NA) ===
     // TMEM lane quadrant = warp % 4 (hardware rule); inside a group, warp j handles 8-channel chunks j/4, j/4 + wpg/4, ...
     // Each group runs its own latency chain (wait accumulator -> TMEM loads -> shuffle-sum -> stage -> bulk store), so NA
     // tiles are in flight in the epilogue while the MMA warp fills the next buffer.  The code is instruction-issue bound
     // (16 warps share 4 schedulers): everything tile-invariant is hoisted and per-pixel address arithmetic only exists on
     // the paths that need it (residual / gate / direct stores).
     const int ew = warp - 1 - kMmaWarps;
-    const int g = ew / wpg;                              // epilogue group == accumulator buffer
+    const int g = ew / wpg;                              // epilogue group
     const int wj = ew - g * wpg;                         // warp within the group
     const int lane_grp = warp & 3;
     const int sub = wj >> 2;                             // first chunk of this warp
-    const int cstep = wpg >> 2;                          // chunk stride (1 or 2)
+    const int cstep = wpg >> 2;                          // chunk-pair stride (1, 2 or 4)
     const int gthreads = wpg * 32;
     const bool tracer = (ew == 0 && lane == 0);
     const int m = lane_grp * 32 + lane;
@@ -305,7 +306,7 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
     const uint32_t swz = (p.stage_row_bytes == 128) ? static_cast<uint32_t>(srow & 7) : 0u;   // SWIZZLE_128B staging rows
     const uint32_t srow_addr = stage_addr + static_cast<uint32_t>(g) * p.stage_bytes + static_cast<uint32_t>(srow * p.stage_row_bytes);
     const uint32_t sbuf = stage_addr + static_cast<uint32_t>(g) * p.stage_bytes;
-    const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16) + g * nmma;
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16);
     const int d0 = -PW, d1 = 1 - PW, d2 = 2 - PW;
     // Staged stores: the group's output tile sits in shared memory as TH*TW rows of stage_row_bytes; it is copied out in
     // 16-byte pieces, consecutive lanes taking consecutive pieces of a pixel row (full 32..128-byte segments per pixel).
@@ -326,8 +327,9 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
         pc_yx[k] = (i < n_pieces) ? ((static_cast<uint32_t>(dy) << 16) | static_cast<uint32_t>(dx)) : 0xffffffffu;
       }
     }
+    int buf = g % NA;
     uint32_t acc_phase = 0;
-    for (int it = g; ; it += NA, acc_phase ^= 1) {
+    for (int it = g; ; it += NG) {
       const int t = blockIdx.x + it * static_cast<int>(gridDim.x);
       if (t >= p.num_tiles) break;
       if (tracer) CSR_TRACE(2, it, 3);
@@ -356,7 +358,8 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
       }
       if (tma_store) named_bar_sync(1 + g, gthreads);   // every thread of the group has copied out the previous tile
       if (tracer) CSR_TRACE(2, it, 0);
-      mbar_wait(bar_acc_full(g), acc_phase);
+      const uint32_t t_addr = t_lane + buf * nmma;
+      mbar_wait(bar_acc_full(buf), acc_phase);
       tc_fence_after();
       if (tracer) CSR_TRACE(2, it, 1);
       uint4 held = make_uint4(0, 0, 0, 0);                // first half of a 32-byte direct store
@@ -441,7 +444,7 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
       // all TMEM reads of this warp are complete (wait::ld above): hand the accumulator buffer back to the MMA warp
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_acc_empty(g));
+      if (lane == 0) mbar_arrive(bar_acc_empty(buf));
       if (tma_store) {
         named_bar_sync(1 + g, gthreads);                  // the staged tile is complete
         if (tracer) CSR_TRACE(2, it, 7);
@@ -460,6 +463,8 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
         }
       }
       if (tracer) CSR_TRACE(2, it, 2);
+      buf += NG;
+      if (buf >= NA) { buf -= NA; acc_phase ^= 1; }
     }
   }
 
@@ -474,7 +479,7 @@ done:
 }
 
 size_t conv_smem_bytes(const ConvParams& p) {
-  return 1024 /*alignment slack*/ + static_cast<size_t>(p.n_slots) * p.slot_bytes + static_cast<size_t>(p.n_acc) * p.stage_bytes +
+  return 1024 /*alignment slack*/ + static_cast<size_t>(p.n_slots) * p.slot_bytes + static_cast<size_t>(p.n_groups) * p.stage_bytes +
          ((p.w_bytes + 127) & ~127) + 256 /*bias*/ + 8 * (9 + 2 * p.n_slots) + 32;
 }
 

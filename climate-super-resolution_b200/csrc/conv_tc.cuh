@@ -43,7 +43,8 @@ struct ConvParams {
   int n_slots;     // activation-window ring depth
   int w_bytes;     // packed weights: KH * (cin/16) * KW * npad * 32
   int n_mma;       // MMA issuer warps in use (2; 1 = debug)
-  int n_acc;       // accumulator buffers in TMEM == epilogue warp groups (2 or 4); n_acc * KW * npad <= 512
+  int n_acc;       // accumulator buffers in TMEM (2 or 4); n_acc * KW * npad <= 512
+  int n_groups;    // epilogue warp groups (1, 2 or 4, <= n_acc and dividing it): one staging buffer each
   int tmem_cols;   // power of two >= max(32, n_acc*KW*npad)
   int force_generic;  // debug: skip the compile-time specialised kernels
   int use_pdl;     // launch with programmatic stream serialization (prologue overlaps the previous kernel's tail)

@@ -39,6 +39,12 @@ def run(name, n, h, w, cin, cout, k, in_c, act="lrelu", out_coff=0):
 if __name__ == "__main__":
     if os.environ.get("CSR_SLOTS"):
         lib.csr_set_option(3, int(os.environ["CSR_SLOTS"]))
+    if os.environ.get("CSR_DIRECT32"):
+        lib.csr_set_option(8, 0)
+    if os.environ.get("CSR_CONV5"):
+        x = None
+        run("rdb.conv5+res", 64, 64, 64, 128, 64, 3, 128, act="none")
+        sys.exit(0)
     if os.environ.get("CSR_ONLY"):
         run("HRconv", 16, 256, 256, 64, 64, 3, 64)
         sys.exit(0)
