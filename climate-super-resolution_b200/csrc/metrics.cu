@@ -197,33 +197,56 @@ ssim_kernel(const float* __restrict__ sr, const float* __restrict__ hr, const fl
     s_t[r][c] = land ? phr[q] : 0.f;
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < kSI * kST; i += blockDim.x) {
-    const int r = i / kST, c = i - r * kST;
-    float a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0;
+  // Horizontal pass with a register sliding window: one thread = 8 consecutive outputs of one row (18 loads of p and t
+  // instead of 8 x 22) - the filter is shared-memory-load bound, not FMA bound.
+  float gk[11];
 #pragma unroll
-    for (int k = 0; k < 11; ++k) {
-      const float g = c_gauss[k], p = s_p[r][c + k], t = s_t[r][c + k];
-      a0 += g * p; a1 += g * t; a2 += g * p * p; a3 += g * t * t; a4 += g * p * t;
+  for (int k = 0; k < 11; ++k) gk[k] = c_gauss[k];
+  for (int task = threadIdx.x; task < kSI * (kST / 8); task += blockDim.x) {
+    const int r = task / (kST / 8), c0 = (task - r * (kST / 8)) * 8;
+    float pv[18], tv[18];
+#pragma unroll
+    for (int k = 0; k < 18; ++k) { pv[k] = s_p[r][c0 + k]; tv[k] = s_t[r][c0 + k]; }
+#pragma unroll
+    for (int o = 0; o < 8; ++o) {
+      float a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0;
+#pragma unroll
+      for (int k = 0; k < 11; ++k) {
+        const float g = gk[k], pp = pv[o + k], tt = tv[o + k];
+        a0 += g * pp; a1 += g * tt; a2 += g * pp * pp; a3 += g * tt * tt; a4 += g * pp * tt;
+      }
+      s_h[0][r][c0 + o] = a0; s_h[1][r][c0 + o] = a1; s_h[2][r][c0 + o] = a2; s_h[3][r][c0 + o] = a3; s_h[4][r][c0 + o] = a4;
     }
-    s_h[0][r][c] = a0; s_h[1][r][c] = a1; s_h[2][r][c] = a2; s_h[3][r][c] = a3; s_h[4][r][c] = a4;
   }
   __syncthreads();
   const float c1 = c12[0], c2 = c12[1];
   double local = 0;
-  for (int i = threadIdx.x; i < kST * kST; i += blockDim.x) {
-    const int r = i / kST, c = i - r * kST;
-    const int y = oy + r, x = ox + c;
-    if (y >= H - 5 || x >= W - 5) continue;
-    float m[5] = {0, 0, 0, 0, 0};
+  // Vertical pass: one thread = 4 consecutive output rows of one column (14 loads per map instead of 4 x 11).
+  for (int task = threadIdx.x; task < kST * (kST / 4); task += blockDim.x) {
+    const int c = task % kST, r0 = (task / kST) * 4;
+    float m[4][5];
 #pragma unroll
-    for (int k = 0; k < 11; ++k) {
-      const float g = c_gauss[k];
+    for (int o = 0; o < 4; ++o)
 #pragma unroll
-      for (int q = 0; q < 5; ++q) m[q] += g * s_h[q][r + k][c];
+      for (int q = 0; q < 5; ++q) m[o][q] = 0.f;
+#pragma unroll
+    for (int q = 0; q < 5; ++q) {
+      float col[14];
+#pragma unroll
+      for (int k = 0; k < 14; ++k) col[k] = s_h[q][r0 + k][c];
+#pragma unroll
+      for (int o = 0; o < 4; ++o)
+#pragma unroll
+        for (int k = 0; k < 11; ++k) m[o][q] += gk[k] * col[o + k];
     }
-    const float mu_p2 = m[0] * m[0], mu_t2 = m[1] * m[1], mu_pt = m[0] * m[1];
-    const float sp = m[2] - mu_p2, st = m[3] - mu_t2, spt = m[4] - mu_pt;
-    local += static_cast<double>(((2.f * mu_pt + c1) * (2.f * spt + c2)) / ((mu_p2 + mu_t2 + c1) * (sp + st + c2)));
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+      const int y = oy + r0 + o, x = ox + c;
+      if (y >= H - 5 || x >= W - 5) continue;
+      const float mu_p2 = m[o][0] * m[o][0], mu_t2 = m[o][1] * m[o][1], mu_pt = m[o][0] * m[o][1];
+      const float sp = m[o][2] - mu_p2, st = m[o][3] - mu_t2, spt = m[o][4] - mu_pt;
+      local += static_cast<double>(((2.f * mu_pt + c1) * (2.f * spt + c2)) / ((mu_p2 + mu_t2 + c1) * (sp + st + c2)));
+    }
   }
   local = warp_sum(local);
   if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = local;
