@@ -51,17 +51,18 @@ class GeneratorFunction(torch.autograd.Function):
         go = grad_out.detach().contiguous().float()
         packed_bwd = module.packed_weights_bwd(force=True)
         n = len(ctx.shapes) // 2
-        sizes = [int(torch.Size(s).numel()) for s in ctx.shapes]
-        flat = torch.zeros(sum((k + 3) // 4 * 4 for k in sizes), dtype=torch.float32, device=dev)      # one memset, 16-byte aligned views
-        grads, off = [], 0
-        for s, k in zip(ctx.shapes, sizes):
-            grads.append(flat[off:off + k].view(s))
-            off += (k + 3) // 4 * 4
-        dw, db = (C.c_void_p * n)(), (C.c_void_p * n)()
-        for i in range(n):
-            dw[i], db[i] = grads[2 * i].data_ptr(), grads[2 * i + 1].data_ptr()
+        # one flat gradient buffer in the plan's layout (csr_plan_grad_offset): written by a single (graph-replayed) call
+        flat = torch.empty(lib.csr_plan_grad_floats(ctx.plan), dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
-            check(lib.csr_plan_backward(ctx.plan, packed_bwd.data_ptr(), go.data_ptr(), dw, db, current_stream_ptr()), "csr_plan_backward")
+            check(lib.csr_plan_backward_flat(ctx.plan, packed_bwd.data_ptr(), go.data_ptr(), flat.data_ptr(), current_stream_ptr()),
+                  "csr_plan_backward_flat")
+        offs = module._grad_offsets(ctx.plan)
+        grads = []
+        for i in range(n):
+            for j in (0, 1):
+                shape = ctx.shapes[2 * i + j]
+                k = int(torch.Size(shape).numel())
+                grads.append(flat[offs[2 * i + j]:offs[2 * i + j] + k].view(shape))
         return (None, None, None, None) + tuple(grads)
 
 

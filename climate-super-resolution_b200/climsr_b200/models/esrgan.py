@@ -173,6 +173,20 @@ class ESRGANGenerator(nn.Module):
         self._plans[key] = (plan.value, ws)
         return plan.value
 
+    def _grad_offsets(self, plan):
+        cache = getattr(self, "_goff_cache", None)
+        if cache is not None and cache[0] == plan:
+            return cache[1]
+        n = lib.csr_num_layers(C.byref(self._desc))
+        offs = []
+        v = C.c_size_t()
+        for i in range(n):
+            for j in (0, 1):
+                check(lib.csr_plan_grad_offset(plan, i, j, C.byref(v)), "csr_plan_grad_offset")
+                offs.append(int(v.value))
+        self._goff_cache = (plan, offs)
+        return offs
+
     def __del__(self):
         try:
             for p, _t in self._plans.values():

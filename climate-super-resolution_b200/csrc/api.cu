@@ -30,6 +30,8 @@ static int g_opt_no_tma_store = 0;
 static int g_opt_two_acc = 0;
 static int g_opt_force_generic = 0;
 static int g_opt_one_mma = 0;
+static int g_opt_graphs = 1;
+static int g_opt_graph_max_px = 1 << 21;   // forward: replay a CUDA graph up to this many HR pixels per call (larger batches are GPU-bound)
 static int g_opt_no_single_group = 1;   // measured: merging the groups buys a 3rd window slot for RDB conv5 but the single group then paces the tile (no net gain)
 static int g_dbg_wgrad[5] = {0, 0, 0, 0, 0};   // a_lbo, a_sbo, b_lbo, b_sbo, flags overrides of the MN-major descriptors
 static int g_opt_no_direct32 = 1;   // measured: no gain over staging on cfg2 (tools/ab_bench.py), kept as an option
@@ -496,6 +498,14 @@ struct CsrPlan {
   int idx_srcnn1;                       // the SRCNN x-im2col pack kernel runs right before this conv
   void* xin; void* sin; float* tlast;
   size_t packed_bytes;
+  // CUDA-graph replay (launch-bound batches: a forward is ~180 launches, a training step ~800): the launch sequence is
+  // captured once per packed-weight blob with plan-owned staging buffers for every pointer that changes between calls
+  struct GraphCache { cudaGraphExec_t exec = nullptr; const void* packed = nullptr; bool failed = false; long launches = 0; int calls = 0; };
+  GraphCache g_fwd, g_bwd;
+  float* sx = nullptr; float* selev = nullptr; float* smask = nullptr; float* sout = nullptr;   // staged inputs / output (fp32)
+  float* sgout = nullptr; float* sgrad = nullptr;                                                // staged dL/dout, flat gradients
+  std::vector<size_t> grad_off;          // per layer: float offset of dW, db inside the flat gradient buffer (2 entries each)
+  size_t grad_floats = 0;
   // training
   std::vector<BwdOp> bwd;
   std::vector<csr::LayerSpec> fwd_layers;
@@ -508,6 +518,7 @@ namespace csr {
 
 struct WsLayout {
   size_t xin, fea0, t0, m1, hrA, hrB, hrC, hrD, hrE, tlast, total;
+  size_t sx, selev, smask, sout, sgout, sgrad;   // graph staging
   std::vector<size_t> cat;              // 3 rotating concat buffers (inference) or one per RDB + 1 (training: saved state)
   // training only
   size_t gO, gT, gP, gQ, gm1, gt0, gtmp, gcat[3], dacc;
@@ -529,7 +540,16 @@ static WsLayout ws_layout(const CsrNetDesc& d, int N, int h, int w, int train) {
   L.hrB = take(hr * 64 * 2);   // HRconv output
   L.hrC = take(hr * 64 * 2);   // SRCNN input [out, elev, mask] x 9 horizontal taps
   L.tlast = take(hr * 4);      // conv_last output, fp32 planar
+  L.sx = take(lr * d.in_channels * 4);
+  L.selev = take(hr * 4);
+  L.smask = take(hr * 4);
+  L.sout = take(hr * 4);
+  L.sgout = L.sgrad = 0;
   if (train) {
+    L.sgout = take(hr * 4);
+    size_t gf = 0;
+    for (const LayerSpec& Ls : layer_table(d)) gf += align_up((size_t)Ls.cout * Ls.cin * Ls.kh * Ls.kw, 4) + align_up((size_t)Ls.cout, 4);
+    L.sgrad = take(gf * 4);
     L.hrD = take(hr * 64 * 2); // srcnn.conv1 output (inference: reuses hrA)
     L.hrE = take(hr * 64 * 2); // srcnn.conv2 output (inference: reuses hrB)
     L.gO = take(hr * 16 * 2);  // dL/dout, channel 0 of a 16-channel pitch
@@ -566,8 +586,19 @@ static int plan_build(CsrPlan* P, void* ws) {
   void* t0 = base + L.t0; void* m1 = base + L.m1; void* hrA = base + L.hrA; void* hrB = base + L.hrB; void* hrC = base + L.hrC;
   void* hrD = base + L.hrD; void* hrE = base + L.hrE;
   P->xin = xin; P->sin = hrC; P->tlast = reinterpret_cast<float*>(base + L.tlast);
+  P->sx = reinterpret_cast<float*>(base + L.sx); P->selev = reinterpret_cast<float*>(base + L.selev);
+  P->smask = reinterpret_cast<float*>(base + L.smask); P->sout = reinterpret_cast<float*>(base + L.sout);
   const std::vector<LayerSpec> layers = layer_table(d);
   P->fwd_layers = layers;
+  {
+    size_t off = 0;
+    for (const LayerSpec& Ls : layers) {
+      P->grad_off.push_back(off); off += align_up((size_t)Ls.cout * Ls.cin * Ls.kh * Ls.kw, 4);
+      P->grad_off.push_back(off); off += align_up((size_t)Ls.cout, 4);
+    }
+    P->grad_floats = off;
+  }
+  if (P->train) { P->sgout = reinterpret_cast<float*>(base + L.sgout); P->sgrad = reinterpret_cast<float*>(base + L.sgrad); }
   size_t total = 0;
   const std::vector<PackLayer> packs = pack_layout(layers, &total);
   P->packed_bytes = total;
@@ -956,6 +987,8 @@ int csr_set_option(int32_t key, int32_t value) {
     case 5: g_opt_two_acc = value ? 1 : 0; return CSR_OK;
     case 6: g_opt_force_generic = value ? 1 : 0; return CSR_OK;
     case 7: g_opt_one_mma = value ? 1 : 0; return CSR_OK;
+    case 11: g_opt_graphs = value ? 1 : 0; return CSR_OK;        // CUDA-graph replay of plan forward / backward_flat
+    case 12: g_opt_graph_max_px = value; return CSR_OK;
     case 9: g_opt_no_single_group = value ? 1 : 0; return CSR_OK;  // 0: one epilogue group (one staging buffer) when that deepens the window ring
     case 8: g_opt_no_direct32 = value ? 1 : 0; return CSR_OK;    // 0: allow unstaged 32-byte stores when staging starves the window ring        // debug: a single MMA issuer warp  // debug: runtime-switched kernels only        // debug: never use four accumulator buffers   // debug: per-element global stores instead of the staged copy-out
     case 20: case 21: case 22: case 23: case 24: g_dbg_wgrad[key - 20] = value; return CSR_OK;
@@ -1124,10 +1157,105 @@ int csr_pack_weights_bwd(const CsrNetDesc* net, const float* const* w, void* pac
   return run_pack_jobs(jobs, packed, s);
 }
 
+}  // extern "C"
+
+// Run `body` (a launch sequence on stream s) through a cached CUDA graph: captured at the second call for a given packed
+// blob (the first call runs directly, so one-time attribute / symbol setup never happens inside a capture) and replayed
+// afterwards.  Any capture / instantiate failure falls back to direct launches for the lifetime of the plan.
+template <typename Body>
+static int run_graphed(CsrPlan::GraphCache& gc, const void* packed, cudaStream_t s, Body body) {
+  if (!g_opt_graphs || gc.failed) return body(s);
+  if (gc.exec && gc.packed == packed) {
+    CSR_CUDA(cudaGraphLaunch(gc.exec, s));
+    g_launches += gc.launches;
+    return CSR_OK;
+  }
+  if (gc.packed != packed) { gc.packed = packed; gc.calls = 0; if (gc.exec) { cudaGraphExecDestroy(gc.exec); gc.exec = nullptr; } }
+  if (gc.calls++ == 0) return body(s);
+  // capture on a private stream (the caller's may be the legacy default stream, which cannot be captured); the
+  // instantiated graph is then launched into the caller's stream
+  static thread_local cudaStream_t cs = nullptr;
+  if (!cs && cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); gc.failed = true; return body(s); }
+  const long l0 = g_launches.load();
+  {
+    const cudaError_t eb = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal);
+    if (eb != cudaSuccess) { fail(CSR_ERR_CUDA, "graph: begin capture: %s", cudaGetErrorString(eb)); cudaGetLastError(); gc.failed = true; return body(s); }
+  }
+  const int rc = body(cs);
+  cudaGraph_t graph = nullptr;
+  const cudaError_t e = cudaStreamEndCapture(cs, &graph);
+  const long captured = g_launches.load() - l0;
+  g_launches -= captured;                                 // nothing ran yet
+  if (rc != CSR_OK || e != cudaSuccess || !graph) {
+    const std::string inner = g_err;
+    fail(CSR_ERR_CUDA, "graph: capture failed (rc %d, end capture: %s; %s)", rc, cudaGetErrorString(e), inner.c_str());
+    cudaGetLastError();
+    if (graph) cudaGraphDestroy(graph);
+    gc.failed = true;
+    return body(s);
+  }
+  cudaGraphExec_t exec = nullptr;
+  const cudaError_t ei = cudaGraphInstantiate(&exec, graph, 0);
+  if (ei != cudaSuccess) {
+    fail(CSR_ERR_CUDA, "graph: instantiate: %s", cudaGetErrorString(ei));
+    cudaGetLastError();
+    cudaGraphDestroy(graph);
+    gc.failed = true;
+    return body(s);
+  }
+  cudaGraphDestroy(graph);
+  gc.exec = exec;
+  gc.launches = captured;
+  CSR_CUDA(cudaGraphLaunch(gc.exec, s));
+  g_launches += gc.launches;
+  return CSR_OK;
+}
+
+extern "C" {
+
+static int backward_launches(CsrPlan* P, const void* packed_bwd, const float* grad_out, float* const* dw, float* const* db, cudaStream_t s);
+
 int csr_plan_backward(CsrPlan* P, const void* packed_bwd, const float* grad_out, float* const* dw, float* const* db, void* stream) {
   if (!P || !packed_bwd || !grad_out || !dw || !db) return fail(CSR_ERR_BAD_ARG, "null pointer");
   if (!P->train) return fail(CSR_ERR_BAD_ARG, "csr_plan_backward needs a plan made by csr_train_plan_create");
+  return backward_launches(P, packed_bwd, grad_out, dw, db, reinterpret_cast<cudaStream_t>(stream));
+}
+
+size_t csr_plan_grad_floats(const CsrPlan* P) { return P ? P->grad_floats : 0; }
+
+// 1 = a CUDA graph is instantiated and being replayed, 0 = not (yet), -1 = capture failed (direct launches)
+int csr_plan_graph_status(const CsrPlan* P, int32_t backward) {
+  if (!P) return 0;
+  const CsrPlan::GraphCache& g = backward ? P->g_bwd : P->g_fwd;
+  return g.failed ? -1 : (g.exec ? 1 : 0);
+}
+
+int csr_plan_grad_offset(const CsrPlan* P, int32_t layer, int32_t is_bias, size_t* offset) {
+  if (!P || !offset || layer < 0 || 2 * (size_t)layer + 1 >= P->grad_off.size()) return fail(CSR_ERR_BAD_ARG, "bad layer index");
+  *offset = P->grad_off[2 * layer + (is_bias ? 1 : 0)];
+  return CSR_OK;
+}
+
+int csr_plan_backward_flat(CsrPlan* P, const void* packed_bwd, const float* grad_out, float* flat_grads, void* stream) {
+  if (!P || !packed_bwd || !grad_out || !flat_grads) return fail(CSR_ERR_BAD_ARG, "null pointer");
+  if (!P->train) return fail(CSR_ERR_BAD_ARG, "csr_plan_backward_flat needs a plan made by csr_train_plan_create");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const size_t nl = P->fwd_layers.size();
+  const size_t hr_bytes = (size_t)P->N * 16 * P->h * P->w * sizeof(float);
+  // the replayed graph works on plan-owned buffers: stage dL/dout in, copy the flat gradients out
+  CSR_CUDA(cudaMemcpyAsync(P->sgout, grad_out, hr_bytes, cudaMemcpyDeviceToDevice, s));
+  std::vector<float*> dw(nl), db(nl);
+  for (size_t i = 0; i < nl; ++i) { dw[i] = P->sgrad + P->grad_off[2 * i]; db[i] = P->sgrad + P->grad_off[2 * i + 1]; }
+  int rc = run_graphed(P->g_bwd, packed_bwd, s, [&](cudaStream_t st) -> int {
+    CSR_CUDA(cudaMemsetAsync(P->sgrad, 0, P->grad_floats * sizeof(float), st));
+    return backward_launches(P, packed_bwd, P->sgout, dw.data(), db.data(), st);
+  });
+  if (rc) return rc;
+  CSR_CUDA(cudaMemcpyAsync(flat_grads, P->sgrad, P->grad_floats * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  return CSR_OK;
+}
+
+static int backward_launches(CsrPlan* P, const void* packed_bwd, const float* grad_out, float* const* dw, float* const* db, cudaStream_t s) {
   const uint8_t* pk = reinterpret_cast<const uint8_t*>(packed_bwd);
   const int H = 4 * P->h, W = 4 * P->w;
   for (BwdOp& op : P->bwd) {
@@ -1185,11 +1313,31 @@ int csr_plan_num_backward_ops(const CsrPlan* plan) { return plan ? (int)plan->bw
 
 int csr_plan_num_launches(const CsrPlan* plan) { return plan ? (int)plan->convs.size() + 2 : 0; }
 
-void csr_plan_destroy(CsrPlan* plan) { delete plan; }
+void csr_plan_destroy(CsrPlan* plan) {
+  if (!plan) return;
+  if (plan->g_fwd.exec) cudaGraphExecDestroy(plan->g_fwd.exec);
+  if (plan->g_bwd.exec) cudaGraphExecDestroy(plan->g_bwd.exec);
+  delete plan;
+}
+
+static int forward_launches(CsrPlan* P, const void* packed, const float* x, const float* elev, const float* mask, float* out, cudaStream_t s);
 
 int csr_plan_forward(CsrPlan* P, const void* packed, const float* x, const float* elev, const float* mask, float* out, void* stream) {
   if (!P || !packed || !x || !elev || !mask || !out) return fail(CSR_ERR_BAD_ARG, "null pointer");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  // Graph replay pays three staging copies; it wins when the forward is launch-bound (small rasters / batches).
+  const size_t hr_px = (size_t)P->N * 16 * P->h * P->w;
+  if (!g_opt_graphs || P->g_fwd.failed || hr_px > (size_t)g_opt_graph_max_px) return forward_launches(P, packed, x, elev, mask, out, s);
+  CSR_CUDA(cudaMemcpyAsync(P->sx, x, (size_t)P->N * P->net.in_channels * P->h * P->w * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  CSR_CUDA(cudaMemcpyAsync(P->selev, elev, hr_px * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  CSR_CUDA(cudaMemcpyAsync(P->smask, mask, hr_px * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  int rc = run_graphed(P->g_fwd, packed, s, [&](cudaStream_t st) -> int { return forward_launches(P, packed, P->sx, P->selev, P->smask, P->sout, st); });
+  if (rc) return rc;
+  CSR_CUDA(cudaMemcpyAsync(out, P->sout, hr_px * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  return CSR_OK;
+}
+
+static int forward_launches(CsrPlan* P, const void* packed, const float* x, const float* elev, const float* mask, float* out, cudaStream_t s) {
   const uint8_t* pk = reinterpret_cast<const uint8_t*>(packed);
   CSR_CUDA(launch_nchw_to_nhwc(x, P->xin, P->N, P->net.in_channels, P->h, P->w, 64, 16, s));
   ++g_launches;

@@ -141,6 +141,15 @@ int     csr_pack_weights_bwd(const CsrNetDesc* net, const float* const* w, void*
 int     csr_plan_backward(CsrPlan* plan, const void* packed_bwd, const float* grad_out,
                           float* const* dw, float* const* db, void* stream);
 int     csr_plan_num_backward_ops(const CsrPlan* plan);
+/* Same backward, all gradients in ONE flat fp32 buffer (OVERWRITTEN, not accumulated): layer i's dW at float offset
+ * csr_plan_grad_offset(plan, i, 0), its db at csr_plan_grad_offset(plan, i, 1) (every tensor starts 16-byte aligned),
+ * csr_plan_grad_floats() floats in total.  With stable buffers the ~800 launches of a step replay as one CUDA graph.   */
+size_t  csr_plan_grad_floats(const CsrPlan* plan);
+/* 1 = the plan's forward (backward != 0: backward_flat) launch sequence is being replayed as a CUDA graph, 0 = not (yet),
+ * -1 = capture failed and the plan launches directly.                                                              */
+int     csr_plan_graph_status(const CsrPlan* plan, int32_t backward);
+int     csr_plan_grad_offset(const CsrPlan* plan, int32_t layer, int32_t is_bias, size_t* offset);
+int     csr_plan_backward_flat(CsrPlan* plan, const void* packed_bwd, const float* grad_out, float* flat_grads, void* stream);
 
 /* ---- single convolution (building block; used by the parity tests) --------------------------
  * in: bf16 NHWC (n,h,w,in_c); weight fp32 OIHW (cout,cin,kh,kw); bias fp32 (cout) or NULL (= zeros).
