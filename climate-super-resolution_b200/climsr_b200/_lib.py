@@ -70,6 +70,8 @@ def _load():
         "csr_plan_graph_status": (C.c_int, [vp, i32]),
         "csr_plan_grad_offset": (C.c_int, [vp, i32, i32, C.POINTER(sz)]),
         "csr_plan_backward_flat": (C.c_int, [vp, vp, vp, vp, vp]),
+        "csr_plan_backward_segments": (C.c_int, [vp, i32]),
+        "csr_plan_backward_flat_seg": (C.c_int, [vp, vp, vp, vp, i32, C.POINTER(sz), C.POINTER(sz), vp]),
         "csr_generator_forward": (C.c_int, [nd, vp, vp, vp, vp, vp, vp, sz, i32, i32, i32, vp]),
         "csr_conv2d_scratch_bytes": (sz, [cd]),
         "csr_conv2d_nhwc": (C.c_int, [cd, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]),
@@ -95,7 +97,7 @@ EXPORTS = ("csr_abi_version", "csr_last_error", "csr_device_check", "csr_set_opt
            "csr_layer_shape", "csr_packed_weight_bytes", "csr_pack_weights", "csr_workspace_bytes", "csr_plan_create",
            "csr_plan_forward", "csr_plan_num_launches", "csr_plan_destroy", "csr_train_workspace_bytes", "csr_train_plan_create",
            "csr_packed_weight_bytes_bwd", "csr_pack_weights_bwd", "csr_plan_backward", "csr_plan_num_backward_ops", "csr_plan_grad_floats", "csr_plan_graph_status", "csr_plan_grad_offset",
-           "csr_plan_backward_flat", "csr_generator_forward", "csr_conv2d_scratch_bytes",
+           "csr_plan_backward_flat", "csr_plan_backward_segments", "csr_plan_backward_flat_seg", "csr_generator_forward", "csr_conv2d_scratch_bytes",
            "csr_conv2d_nhwc", "csr_conv2d_wgrad_scratch_bytes", "csr_conv2d_wgrad", "csr_nchw_f32_to_nhwc_bf16", "csr_nhwc_bf16_to_nchw_f32", "csr_pixel_loss_scratch_bytes", "csr_l1_loss", "csr_mse_loss",
            "csr_metrics_scratch_bytes", "csr_masked_metrics")
 

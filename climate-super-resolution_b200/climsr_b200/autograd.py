@@ -53,9 +53,21 @@ class GeneratorFunction(torch.autograd.Function):
         n = len(ctx.shapes) // 2
         # one flat gradient buffer in the plan's layout (csr_plan_grad_offset): written by a single (graph-replayed) call
         flat = torch.empty(lib.csr_plan_grad_floats(ctx.plan), dtype=torch.float32, device=dev)
+        sync = getattr(module, "_grad_sync", None)
         with torch.cuda.device(dev):
-            check(lib.csr_plan_backward_flat(ctx.plan, packed_bwd.data_ptr(), go.data_ptr(), flat.data_ptr(), current_stream_ptr()),
-                  "csr_plan_backward_flat")
+            if sync is not None and sync.world > 1:
+                # segmented backward: each finished gradient slice is all-reduced on a side stream while the next segment runs
+                nseg = module._backward_segments(ctx.plan, sync.nseg)
+                lo, hi = C.c_size_t(), C.c_size_t()
+                pending = []
+                for k in range(nseg):
+                    check(lib.csr_plan_backward_flat_seg(ctx.plan, packed_bwd.data_ptr(), go.data_ptr(), flat.data_ptr(), k, C.byref(lo),
+                                                         C.byref(hi), current_stream_ptr()), "csr_plan_backward_flat_seg")
+                    sync.reduce_slice_async(flat, int(lo.value), int(hi.value), pending)
+                sync.finish(flat, pending)
+            else:
+                check(lib.csr_plan_backward_flat(ctx.plan, packed_bwd.data_ptr(), go.data_ptr(), flat.data_ptr(), current_stream_ptr()),
+                      "csr_plan_backward_flat")
         offs = module._grad_offsets(ctx.plan)
         grads = []
         for i in range(n):

@@ -81,6 +81,7 @@ class ESRGANGenerator(nn.Module):
         self._packed_bwd: Optional[Tensor] = None
         self._packed_bwd_key: Optional[Tuple] = None
         self._fwd_serial = 0
+        self._grad_sync = None
 
     # ------------------------------------------------------------------ weights
     def _ordered_params(self):
@@ -172,6 +173,21 @@ class ESRGANGenerator(nn.Module):
             self._plans.clear()
         self._plans[key] = (plan.value, ws)
         return plan.value
+
+    def set_grad_sync(self, sync) -> None:
+        """Data-parallel training: a climsr_b200.parallel.BackwardGradSync makes backward() return gradients that are already
+        averaged over the process group, their all-reduce overlapped with the backward kernels."""
+        self._grad_sync = sync
+
+    def _backward_segments(self, plan, nseg: int) -> int:
+        cache = getattr(self, "_seg_cache", None)
+        if cache is not None and cache[0] == (plan, nseg):
+            return cache[1]
+        n = lib.csr_plan_backward_segments(plan, nseg)
+        if n < 0:
+            check(n, "csr_plan_backward_segments")
+        self._seg_cache = ((plan, nseg), n)
+        return n
 
     def _grad_offsets(self, plan):
         cache = getattr(self, "_goff_cache", None)

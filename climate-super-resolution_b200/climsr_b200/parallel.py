@@ -99,6 +99,72 @@ class GradientBucketer:
         self.wait()
 
 
+class BackwardGradSync:
+    """Gradient all-reduce overlapped with the generator's backward (the DDP-hook equivalent for a one-node backward).
+
+    ``ESRGANGenerator.set_grad_sync(BackwardGradSync(...))`` makes the generator's autograd node run its backward in
+    ``nseg`` segments (csr_plan_backward_flat_seg).  Layers finish in reverse order, so after each segment a growing
+    suffix of the flat gradient buffer is final: that slice is cast to ``comm_dtype`` and all-reduced on a side stream
+    behind an event while the next segment's kernels run on the compute stream.  The node returns averaged gradients, so
+    nothing is left to do after ``loss.backward()``.
+
+    Measured on 2 x B200 (cfg3 generator step): 12.1 ms with this overlap vs 7.3 ms with ``GradientBucketer`` after backward
+    (6.9 ms on one GPU).  The persistent conv / wgrad grids occupy all 148 SMs with one CTA each; a concurrent NCCL kernel
+    takes a few SMs and every conv launch that overlaps it needs a second wave.  Overlap therefore only pays once the
+    compute grids leave SMs free - kept as an option, not the default.
+    """
+
+    def __init__(self, nseg: int = 4, comm_dtype: Optional[torch.dtype] = torch.bfloat16, process_group=None):
+        self.nseg = max(1, int(nseg))
+        self.comm_dtype = comm_dtype
+        self.group = process_group
+        self._stream = None
+        self.last_ranges: List[tuple] = []
+
+    @property
+    def world(self) -> int:
+        return dist.get_world_size(self.group) if dist.is_initialized() else 1
+
+    def stream(self, dev) -> "torch.cuda.Stream":
+        if self._stream is None:
+            self._stream = torch.cuda.Stream(device=dev)
+        return self._stream
+
+    def reduce_slice_async(self, flat: torch.Tensor, lo: int, hi: int, pending: list) -> None:
+        """Called by the autograd node right after a segment: flat[lo:hi] is final on the compute stream."""
+        if hi <= lo or self.world == 1:
+            return
+        dev = flat.device
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream(dev))
+        comm = self.stream(dev)
+        with torch.cuda.stream(comm):
+            comm.wait_event(ready)
+            part = flat[lo:hi]
+            buf = part.to(self.comm_dtype) if self.comm_dtype is not None and self.comm_dtype != part.dtype else part
+            work = dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+            pending.append((lo, hi, buf, work))
+
+    def finish(self, flat: torch.Tensor, pending: list) -> None:
+        if not pending:
+            return
+        dev = flat.device
+        comm = self.stream(dev)
+        inv = 1.0 / self.world
+        with torch.cuda.stream(comm):
+            for lo, hi, buf, work in pending:
+                work.wait()
+                if buf.data_ptr() == flat[lo:hi].data_ptr():
+                    flat[lo:hi].mul_(inv)
+                else:
+                    torch.mul(buf.to(torch.float32), inv, out=flat[lo:hi])
+            done = torch.cuda.Event()
+            done.record(comm)
+        torch.cuda.current_stream(dev).wait_event(done)
+        flat.record_stream(comm)
+        self.last_ranges = [(lo, hi) for lo, hi, _, _ in pending]
+
+
 class _null:
     def __enter__(self):
         return self

@@ -502,6 +502,10 @@ struct CsrPlan {
   // captured once per packed-weight blob with plan-owned staging buffers for every pointer that changes between calls
   struct GraphCache { cudaGraphExec_t exec = nullptr; const void* packed = nullptr; bool failed = false; long launches = 0; int calls = 0; };
   GraphCache g_fwd, g_bwd;
+  // segmented backward (gradient all-reduce overlap): segment k runs ops [seg_op[k], seg_op[k+1]) and completes the flat
+  // gradient floats [seg_lo[k], seg_hi[k]) (layers finish in reverse order, so the completed part is a growing suffix)
+  std::vector<size_t> seg_op, seg_lo, seg_hi;
+  std::vector<GraphCache> g_seg;
   float* sx = nullptr; float* selev = nullptr; float* smask = nullptr; float* sout = nullptr;   // staged inputs / output (fp32)
   float* sgout = nullptr; float* sgrad = nullptr;                                                // staged dL/dout, flat gradients
   std::vector<size_t> grad_off;          // per layer: float offset of dW, db inside the flat gradient buffer (2 entries each)
@@ -1213,7 +1217,8 @@ static int run_graphed(CsrPlan::GraphCache& gc, const void* packed, cudaStream_t
 
 extern "C" {
 
-static int backward_launches(CsrPlan* P, const void* packed_bwd, const float* grad_out, float* const* dw, float* const* db, cudaStream_t s);
+static int backward_launches(CsrPlan* P, const void* packed_bwd, const float* grad_out, float* const* dw, float* const* db, cudaStream_t s,
+                             size_t op_lo = 0, size_t op_hi = (size_t)-1);
 
 int csr_plan_backward(CsrPlan* P, const void* packed_bwd, const float* grad_out, float* const* dw, float* const* db, void* stream) {
   if (!P || !packed_bwd || !grad_out || !dw || !db) return fail(CSR_ERR_BAD_ARG, "null pointer");
@@ -1236,6 +1241,74 @@ int csr_plan_grad_offset(const CsrPlan* P, int32_t layer, int32_t is_bias, size_
   return CSR_OK;
 }
 
+int csr_plan_backward_segments(CsrPlan* P, int32_t nseg) {
+  if (!P || !P->train) return fail(CSR_ERR_BAD_ARG, "needs a plan made by csr_train_plan_create");
+  if (nseg < 1) return fail(CSR_ERR_BAD_ARG, "nseg must be positive");
+  // last op that writes each layer's gradient
+  const size_t nl = P->fwd_layers.size();
+  std::vector<size_t> last(nl, 0);
+  for (size_t oi = 0; oi < P->bwd.size(); ++oi) {
+    const BwdOp& op = P->bwd[oi];
+    if (op.kind == BwdOp::kScatter || op.kind == BwdOp::kBiasPlanar) last[op.layer] = oi;
+    if (op.kind == BwdOp::kBias)
+      for (int q = 0; q < op.nseg; ++q) last[op.nseg > 1 ? op.seg_layers[q] : op.layer] = oi;
+  }
+  // done_after[oi] = lowest float offset such that every layer at or above it is complete once ops [0, oi] have run
+  std::vector<size_t> done_at(P->bwd.size() + 1, P->grad_floats);
+  {
+    std::vector<size_t> order(nl);
+    for (size_t i = 0; i < nl; ++i) order[i] = i;
+    // walk layers from the last one down while they are complete
+    for (size_t oi = 0; oi < P->bwd.size(); ++oi) {
+      size_t lo = P->grad_floats;
+      for (size_t li = nl; li-- > 0;) {
+        if (last[li] <= oi) lo = P->grad_off[2 * li]; else break;
+      }
+      done_at[oi + 1] = lo;
+    }
+  }
+  P->seg_op.clear(); P->seg_lo.clear(); P->seg_hi.clear();
+  for (auto& g : P->g_seg) if (g.exec) cudaGraphExecDestroy(g.exec);
+  P->g_seg.clear();
+  size_t prev_op = 0, prev_lo = P->grad_floats;
+  for (int k = 1; k <= nseg; ++k) {
+    const size_t target = P->grad_floats - P->grad_floats * k / nseg;      // completed suffix should reach down to here
+    size_t oi = prev_op;
+    if (k == nseg) oi = P->bwd.size();
+    else
+      while (oi < P->bwd.size() && done_at[oi] > target) ++oi;
+    if (oi <= prev_op && k < nseg) continue;
+    P->seg_op.push_back(prev_op);
+    P->seg_lo.push_back(done_at[oi]);
+    P->seg_hi.push_back(prev_lo);
+    prev_op = oi; prev_lo = done_at[oi];
+  }
+  P->seg_op.push_back(P->bwd.size());
+  P->g_seg.resize(P->seg_lo.size());
+  return (int)P->seg_lo.size();
+}
+
+int csr_plan_backward_flat_seg(CsrPlan* P, const void* packed_bwd, const float* grad_out, float* flat_grads, int32_t seg, size_t* lo, size_t* hi,
+                               void* stream) {
+  if (!P || !packed_bwd || !grad_out || !flat_grads || !lo || !hi) return fail(CSR_ERR_BAD_ARG, "null pointer");
+  if (!P->train || seg < 0 || (size_t)seg >= P->seg_lo.size()) return fail(CSR_ERR_BAD_ARG, "bad segment (call csr_plan_backward_segments first)");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const size_t nl = P->fwd_layers.size();
+  if (seg == 0)
+    CSR_CUDA(cudaMemcpyAsync(P->sgout, grad_out, (size_t)P->N * 16 * P->h * P->w * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  std::vector<float*> dw(nl), db(nl);
+  for (size_t i = 0; i < nl; ++i) { dw[i] = P->sgrad + P->grad_off[2 * i]; db[i] = P->sgrad + P->grad_off[2 * i + 1]; }
+  const size_t o0 = P->seg_op[seg], o1 = P->seg_op[seg + 1];
+  int rc = run_graphed(P->g_seg[seg], packed_bwd, s, [&](cudaStream_t st) -> int {
+    if (seg == 0) CSR_CUDA(cudaMemsetAsync(P->sgrad, 0, P->grad_floats * sizeof(float), st));
+    return backward_launches(P, packed_bwd, P->sgout, dw.data(), db.data(), st, o0, o1);
+  });
+  if (rc) return rc;
+  *lo = P->seg_lo[seg]; *hi = P->seg_hi[seg];
+  if (*hi > *lo) CSR_CUDA(cudaMemcpyAsync(flat_grads + *lo, P->sgrad + *lo, (*hi - *lo) * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  return CSR_OK;
+}
+
 int csr_plan_backward_flat(CsrPlan* P, const void* packed_bwd, const float* grad_out, float* flat_grads, void* stream) {
   if (!P || !packed_bwd || !grad_out || !flat_grads) return fail(CSR_ERR_BAD_ARG, "null pointer");
   if (!P->train) return fail(CSR_ERR_BAD_ARG, "csr_plan_backward_flat needs a plan made by csr_train_plan_create");
@@ -1255,10 +1328,13 @@ int csr_plan_backward_flat(CsrPlan* P, const void* packed_bwd, const float* grad
   return CSR_OK;
 }
 
-static int backward_launches(CsrPlan* P, const void* packed_bwd, const float* grad_out, float* const* dw, float* const* db, cudaStream_t s) {
+static int backward_launches(CsrPlan* P, const void* packed_bwd, const float* grad_out, float* const* dw, float* const* db, cudaStream_t s,
+                             size_t op_lo, size_t op_hi) {
   const uint8_t* pk = reinterpret_cast<const uint8_t*>(packed_bwd);
   const int H = 4 * P->h, W = 4 * P->w;
-  for (BwdOp& op : P->bwd) {
+  op_hi = std::min(op_hi, P->bwd.size());
+  for (size_t oi = op_lo; oi < op_hi; ++oi) {
+    BwdOp& op = P->bwd[oi];
     switch (op.kind) {
       case BwdOp::kGoutPack:
         CSR_CUDA(launch_nchw_to_nhwc(grad_out, P->gout_nhwc, P->N, 1, H, W, 16, 16, s));
@@ -1317,6 +1393,7 @@ void csr_plan_destroy(CsrPlan* plan) {
   if (!plan) return;
   if (plan->g_fwd.exec) cudaGraphExecDestroy(plan->g_fwd.exec);
   if (plan->g_bwd.exec) cudaGraphExecDestroy(plan->g_bwd.exec);
+  for (auto& g : plan->g_seg) if (g.exec) cudaGraphExecDestroy(g.exec);
   delete plan;
 }
 

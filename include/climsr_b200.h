@@ -150,6 +150,13 @@ size_t  csr_plan_grad_floats(const CsrPlan* plan);
 int     csr_plan_graph_status(const CsrPlan* plan, int32_t backward);
 int     csr_plan_grad_offset(const CsrPlan* plan, int32_t layer, int32_t is_bias, size_t* offset);
 int     csr_plan_backward_flat(CsrPlan* plan, const void* packed_bwd, const float* grad_out, float* flat_grads, void* stream);
+/* Segmented form for overlapping the data-parallel gradient exchange with the rest of backward: split the op list into
+ * (at most) nseg segments (returns the number made); segment k, run in order 0..n-1, completes the flat gradient floats
+ * [*lo, *hi) - a suffix of the buffer that grows downwards, because layers finish in reverse order - and copies exactly
+ * that range into flat_grads, so the caller can all-reduce it on another stream while later segments compute.       */
+int     csr_plan_backward_segments(CsrPlan* plan, int32_t nseg);
+int     csr_plan_backward_flat_seg(CsrPlan* plan, const void* packed_bwd, const float* grad_out, float* flat_grads,
+                                   int32_t seg, size_t* lo, size_t* hi, void* stream);
 
 /* ---- single convolution (building block; used by the parity tests) --------------------------
  * in: bf16 NHWC (n,h,w,in_c); weight fp32 OIHW (cout,cin,kh,kw); bias fp32 (cout) or NULL (= zeros).
