@@ -61,21 +61,37 @@ __device__ __forceinline__ Tile decode_tile(const ConvParams& p, int t) {
   return r;
 }
 
-__device__ __forceinline__ float apply_act(float v, int act) {
-  if (act == 1) return fmaxf(v, 0.2f * v);
-  if (act == 2) return fmaxf(v, 0.f);
-  return v;
+// The epilogue is instruction-issue bound: its fp32 arithmetic uses the packed two-wide forms (FADD2 / FMUL2 / FFMA2).
+__device__ __forceinline__ void apply_act8(float (&v)[8], int act) {
+  if (act == 1) {                                       // LeakyReLU(0.2) = max(v, 0.2 v)
+#pragma unroll
+    for (int j = 0; j < 8; j += 2) {
+      const float2 t = __fmul2_rn(make_float2(v[j], v[j + 1]), make_float2(0.2f, 0.2f));
+      v[j] = fmaxf(v[j], t.x);
+      v[j + 1] = fmaxf(v[j + 1], t.y);
+    }
+  } else if (act == 2) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+  }
 }
 
 // acc[j] += value of raw[j] held by lane (lane + delta); delta == 0 -> own value.  Executed by all 32 lanes.
 __device__ __forceinline__ void gather_add8(float (&acc)[8], const uint32_t (&raw)[8], int delta, int lane) {
+  float s[8];
   if (delta == 0) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] += __uint_as_float(raw[j]);
+    for (int j = 0; j < 8; ++j) s[j] = __uint_as_float(raw[j]);
   } else {
     const int src = (lane + delta) & 31;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] += __uint_as_float(__shfl_sync(0xffffffffu, raw[j], src));
+    for (int j = 0; j < 8; ++j) s[j] = __uint_as_float(__shfl_sync(0xffffffffu, raw[j], src));
+  }
+#pragma unroll
+  for (int j = 0; j < 8; j += 2) {
+    const float2 t = __fadd2_rn(make_float2(acc[j], acc[j + 1]), make_float2(s[j], s[j + 1]));
+    acc[j] = t.x;
+    acc[j + 1] = t.y;
   }
 }
 
@@ -83,8 +99,9 @@ __device__ __forceinline__ void fma_residual8(float (&v)[8], const uint4& r, flo
   const uint32_t w[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    v[2 * i] = v[2 * i] * scale + bf16lo(w[i]);
-    v[2 * i + 1] = v[2 * i + 1] * scale + bf16hi(w[i]);
+    const float2 t = __ffma2_rn(make_float2(v[2 * i], v[2 * i + 1]), make_float2(scale, scale), make_float2(bf16lo(w[i]), bf16hi(w[i])));
+    v[2 * i] = t.x;
+    v[2 * i + 1] = t.y;
   }
 }
 
@@ -403,8 +420,7 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
               gather_add8(v, r, dx - PW, lane);
             }
           }
-#pragma unroll
-          for (int i = 0; i < 8; ++i) v[i] = apply_act(v[i], act);
+          apply_act8(v, act);
           if (need_pix) {
             if (has_r1) fma_residual8(v, q1[j], p.s1);
             if (has_gate) gate8(v, q2[j], p.gate_neg);
