@@ -459,7 +459,7 @@ static int run_wgrad_layer(const WgradLayer& L, int N, int H, int W, const void*
         ++*launches;
       }
       CSR_CUDA(launch_wgrad_reduce(scratch, part_stride, n_parts, part_stride, s));
-      CSR_CUDA(launch_wgrad_scatter(scratch, ld_n, dw, L.cout, L.cin, L.kh, L.kw, L.fold, phase, ci0, std::min(128, ecin - ci0), 0, scale, s));
+      CSR_CUDA(launch_wgrad_scatter(scratch, ld_n, dw, L.cout, L.cin, L.kh, L.kw, L.fold, phase, ci0, std::min(128, ecin - ci0), 0, scale, 0, s));
       *launches += 2;
     }
   }
@@ -477,12 +477,14 @@ static int run_wgrad_layer(const WgradLayer& L, int N, int H, int W, const void*
 
 // Backward op list entry (training plans).
 struct BwdOp {
-  enum Kind { kConv, kWgrad, kReduce, kScatter, kBias, kBiasPlanar, kScale, kMemset, kGoutPack } kind;
+  enum Kind { kConv, kWgrad, kReduce, kScatter, kBias, kBiasPlanar, kScale, kMemset, kGcol } kind;
   csr::ConvLaunch conv;          // kConv (dgrad); w_off/b_off index the BACKWARD packed blob
   csr::WgradLaunch wg;           // kWgrad
   // kScatter / kBias*: which forward layer's gradient, and how
   int layer = -1, fold = 0, phase = -1, ci0 = 0, ci_n = 0, col0 = 0, ld_n = 0, n_parts = 0, nseg = 1;
   long dy_stride = 0;
+  int taps_t = 0;                         // kScatter: columns are taps of a single-output-channel layer (dw[ci][tap])
+  int kh = 0, kw = 0;                     // kGcol: taps; src planar fp32 (C == 0) or bf16 NHWC pitch C; dst pitch coff
   int seg_layers[4] = {-1, -1, -1, -1};   // kBias with nseg > 1: one forward layer per channel segment
   float scale = 1.f;
   const void* src = nullptr; void* dst = nullptr;   // kScale (bf16 NHWC 64 ch: dst = scale*src), kBias (g buffer), kMemset
@@ -525,7 +527,7 @@ struct WsLayout {
   size_t sx, selev, smask, sout, sgout, sgrad;   // graph staging
   std::vector<size_t> cat;              // 3 rotating concat buffers (inference) or one per RDB + 1 (training: saved state)
   // training only
-  size_t gO, gT, gP, gQ, gm1, gt0, gtmp, gcat[3], dacc;
+  size_t gO, gcolB, gT, gP, gQ, gm1, gt0, gtmp, gcat[3], dacc;
   int ccat;
 };
 static WsLayout ws_layout(const CsrNetDesc& d, int N, int h, int w, int train) {
@@ -556,7 +558,8 @@ static WsLayout ws_layout(const CsrNetDesc& d, int N, int h, int w, int train) {
     L.sgrad = take(gf * 4);
     L.hrD = take(hr * 64 * 2); // srcnn.conv1 output (inference: reuses hrA)
     L.hrE = take(hr * 64 * 2); // srcnn.conv2 output (inference: reuses hrB)
-    L.gO = take(hr * 16 * 2);  // dL/dout, channel 0 of a 16-channel pitch
+    L.gO = take(hr * 32 * 2);  // im2col of dL/dout: 25 taps of srcnn.conv3 (32-channel pitch)
+    L.gcolB = take(hr * 16 * 2);  // im2col of dL/d(conv_last output): 9 taps (16-channel pitch)
     L.gT = take(hr * 16 * 2);  // dL/d(conv_last output), channel 0
     L.gP = take(hr * 64 * 2);  // ping-pong gradient maps of the HR tail
     L.gQ = take(hr * 64 * 2);
@@ -567,7 +570,7 @@ static WsLayout ws_layout(const CsrNetDesc& d, int N, int h, int w, int train) {
     L.dacc = take((size_t)9 * kMaxParts * 128 * 128 * 4);   // per-CTA partial sums of the weight-gradient GEMMs
   } else {
     L.hrD = L.hrA; L.hrE = L.hrB;
-    L.gO = L.gT = L.gP = L.gQ = L.gm1 = L.gt0 = L.gtmp = L.dacc = 0;
+    L.gO = L.gcolB = L.gT = L.gP = L.gQ = L.gm1 = L.gt0 = L.gtmp = L.dacc = 0;
     L.gcat[0] = L.gcat[1] = L.gcat[2] = 0;
   }
   L.total = off;
@@ -702,10 +705,17 @@ static std::vector<LayerSpec> bwd_layer_table(const CsrNetDesc& d, const std::ve
   };
   const int base_tail = 1 + d.nb * 15;                    // trunk_conv
   // order of use in csr_plan_backward: srcnn.conv3, conv2, conv1, conv_last, HRconv, upconv2, upconv1, trunk_conv, RDBs reversed
-  T(base_tail + 7, 1.f);                                  // srcnn.conv3
+  auto C1 = [&](int src) {                                // cout == 1 layer: d/dx = 1x1 conv over the output-gradient im2col
+    LayerSpec L = f[src];
+    LayerSpec t;
+    t.name = L.name + ".dgrad_cols";
+    t.cout = L.cin; t.cin = L.kh * L.kw; t.kh = t.kw = 1; t.transposed = 0; t.src = src;   // (1,cin,KH,KW) read as (cin,taps,1,1)
+    v.push_back(t);
+  };
+  C1(base_tail + 7);                                      // srcnn.conv3
   T(base_tail + 6, 1.f);                                  // srcnn.conv2
   T(base_tail + 5, 1.f);                                  // srcnn.conv1 (un-folded 9x9 transposed; only d/d(out) = channel 0 is used)
-  T(base_tail + 4, 1.f);                                  // conv_last
+  C1(base_tail + 4);                                      // conv_last
   T(base_tail + 3, 1.f);                                  // HRconv
   T(base_tail + 2, 1.f, 1);                               // upconv2 (four transposed sub-pixel phases)
   T(base_tail + 1, 1.f, 1);                               // upconv1
@@ -739,7 +749,7 @@ static int bwd_build(CsrPlan* P, void* ws) {
   void* xin = base + L.xin;
   void* t0 = base + L.t0; void* m1 = base + L.m1; void* hrA = base + L.hrA; void* hrB = base + L.hrB; void* hrC = base + L.hrC;
   void* hrD = base + L.hrD; void* hrE = base + L.hrE;
-  void* gO = base + L.gO; void* gT = base + L.gT; void* gP = base + L.gP; void* gQ = base + L.gQ; void* gm1 = base + L.gm1;
+  void* gO = base + L.gO; void* gcolB = base + L.gcolB; void* gT = base + L.gT; void* gP = base + L.gP; void* gQ = base + L.gQ; void* gm1 = base + L.gm1;
   void* gt0 = base + L.gt0;
   void* gcat[3] = {base + L.gcat[0], base + L.gcat[1], base + L.gcat[2]};
   float* dacc = reinterpret_cast<float*>(base + L.dacc);
@@ -825,6 +835,26 @@ static int bwd_build(CsrPlan* P, void* ws) {
     ops.push_back(bo);
     return CSR_OK;
   };
+  // weight gradient of a single-output-channel layer as ONE 1x1 GEMM: x (cin channels) against the im2col of its output
+  // gradient (taps as columns); the scatter writes dw[ci][tap]
+  auto wgrad_cols = [&](int layer, int Hh, int Ww, const void* x, int x_C, const void* gcol, int gcol_C) -> int {
+    const LayerSpec& Ls = F[layer];
+    const int ntaps = Ls.kh * Ls.kw;
+    const int ld_n = (ntaps + 15) / 16 * 16;
+    const long part_stride = (long)128 * ld_n;
+    for (int ci0 = 0; ci0 < Ls.cin; ci0 += 128) {
+      BwdOp op; op.kind = BwdOp::kWgrad;
+      int rc = build_wgrad(P->sms, N, Hh, Ww, 1, 0, 0, 1, x, x_C, ci0, gcol, gcol_C, 0, nullptr, 0, 0, ld_n, dacc, part_stride, ld_n, &op.wg);
+      if (rc) return rc;
+      ops.push_back(op);
+      BwdOp rd; rd.kind = BwdOp::kReduce; rd.n_parts = op.wg.p.n_parts; rd.dy_stride = part_stride; rd.count = part_stride;
+      ops.push_back(rd);
+      BwdOp sc; sc.kind = BwdOp::kScatter; sc.layer = layer; sc.ci0 = ci0; sc.ci_n = std::min(128, Ls.cin - ci0); sc.col0 = 0; sc.ld_n = ld_n;
+      sc.scale = 1.f; sc.taps_t = ntaps;
+      ops.push_back(sc);
+    }
+    return CSR_OK;
+  };
   auto gated = [&](ConvIO io, const void* gate, int gate_C, int gate_coff, int gate_from, float neg) {
     io.gate = gate; io.gate_C = gate_C; io.gate_coff = gate_coff; io.gate_from = gate_from; io.gate_neg = neg;
     return io;
@@ -832,10 +862,12 @@ static int bwd_build(CsrPlan* P, void* ws) {
 
   int rc;
   // ---- SRCNN tail (srcnn.py:13-18) -------------------------------------------------------------------------------
-  { BwdOp op; op.kind = BwdOp::kGoutPack; ops.push_back(op); }                        // dL/dout fp32 planar -> gO channel 0
-  rc = wgrad_plain(base_tail + 7, H, W, hrE, 64, 0, gO, 16, 0, 1.f);                  // srcnn.conv3
+  // srcnn.conv3 (32 -> 1, 5x5): im2col of dL/dout (25 taps as channels) makes both of its gradients 1x1 GEMMs
+  { BwdOp op; op.kind = BwdOp::kGcol; op.src = nullptr; op.C = 0; op.dst = gO; op.coff = 32; op.kh = 5; op.kw = 5; ops.push_back(op); }
+  rc = wgrad_cols(base_tail + 7, H, W, hrE, 64, gO, 32);
   if (rc) return rc;
-  rc = dgrad(H, W, gated(io_of(gO, 16, gP, 64, 0, CSR_ACT_NONE), hrE, 64, 0, 0, 0.f));  // -> d/d relu(conv2) * relu'
+  { BwdOp bo; bo.kind = BwdOp::kBiasPlanar; bo.layer = base_tail + 7; bo.src = nullptr; bo.count = (long)N * H * W; bo.scale = 1.f; ops.push_back(bo); }
+  rc = dgrad(H, W, gated(io_of(gO, 32, gP, 64, 0, CSR_ACT_NONE), hrE, 64, 0, 0, 0.f));  // -> d/d relu(conv2) * relu'
   if (rc) return rc;
   rc = wgrad_plain(base_tail + 6, H, W, hrD, 64, 0, gP, 64, 0, 1.f);                  // srcnn.conv2
   if (rc) return rc;
@@ -846,9 +878,12 @@ static int bwd_build(CsrPlan* P, void* ws) {
   rc = dgrad(H, W, io_of(gQ, 64, gT, 16, 0, CSR_ACT_NONE));                           // d/d[out, elev, mask]; channel 0 is used
   if (rc) return rc;
   // ---- conv_last, HRconv (esrgan.py:99) ----------------------------------------------------------------------------
-  rc = wgrad_plain(base_tail + 4, H, W, hrB, 64, 0, gT, 16, 0, 1.f);
+  { BwdOp op; op.kind = BwdOp::kGcol; op.src = gT; op.C = 16; op.dst = gcolB; op.coff = 16; op.kh = 3; op.kw = 3; ops.push_back(op); }
+  rc = wgrad_cols(base_tail + 4, H, W, hrB, 64, gcolB, 16);
   if (rc) return rc;
-  rc = dgrad(H, W, gated(io_of(gT, 16, gP, 64, 0, CSR_ACT_NONE), hrB, 64, 0, 0, 0.2f));
+  { BwdOp bo; bo.kind = BwdOp::kBias; bo.layer = base_tail + 4; bo.src = gT; bo.count = (long)N * H * W; bo.C = 16; bo.coff = 0; bo.cout = 1;
+    bo.scale = 1.f; ops.push_back(bo); }
+  rc = dgrad(H, W, gated(io_of(gcolB, 16, gP, 64, 0, CSR_ACT_NONE), hrB, 64, 0, 0, 0.2f));
   if (rc) return rc;
   rc = wgrad_plain(base_tail + 3, H, W, hrA, 64, 0, gP, 64, 0, 1.f);
   if (rc) return rc;
@@ -1103,8 +1138,7 @@ static int plan_create_impl(const CsrNetDesc* net, int32_t n, int32_t h, int32_t
       // the narrow gradient maps are read 16 channels wide but written 1-3 channels wide: start them from zero
       uint8_t* base = reinterpret_cast<uint8_t*>(workspace);
       const size_t hr16 = (size_t)n * h * w * 16 * 16 * 2;
-      cudaError_t e = cudaMemset(base + L.gO, 0, hr16);
-      if (e == cudaSuccess) e = cudaMemset(base + L.gT, 0, hr16);
+      cudaError_t e = cudaMemset(base + L.gT, 0, hr16);
       if (e != cudaSuccess) rc = fail(CSR_ERR_CUDA, "cudaMemset: %s", cudaGetErrorString(e));
     }
   }
@@ -1146,7 +1180,7 @@ int csr_pack_weights_bwd(const CsrNetDesc* net, const float* const* w, void* pac
       float* bdst = reinterpret_cast<float*>(base + pp.b_off);
       if (L.blocks.empty()) {
         if (!w[L.src]) return fail(CSR_ERR_BAD_ARG, "null weight pointer for layer %d", L.src);
-        jobs.push_back({w[L.src], nullptr, base + pp.w_off, bdst, L.cout, L.cin, L.kh, L.kw, 0, pp.phase, 1, L.wscale, pp.co_lo, pp.npad,
+        jobs.push_back({w[L.src], nullptr, base + pp.w_off, bdst, L.cout, L.cin, L.kh, L.kw, 0, pp.phase, L.transposed, L.wscale, pp.co_lo, pp.npad,
                         packs[i].cin_pad, 0, 0, 0, 0});
       } else {
         for (size_t bk = 0; bk < L.blocks.size(); ++bk) {
@@ -1336,8 +1370,8 @@ static int backward_launches(CsrPlan* P, const void* packed_bwd, const float* gr
   for (size_t oi = op_lo; oi < op_hi; ++oi) {
     BwdOp& op = P->bwd[oi];
     switch (op.kind) {
-      case BwdOp::kGoutPack:
-        CSR_CUDA(launch_nchw_to_nhwc(grad_out, P->gout_nhwc, P->N, 1, H, W, 16, 16, s));
+      case BwdOp::kGcol:
+        CSR_CUDA(launch_gcol_pack(op.src ? op.src : grad_out, op.C, op.dst, op.coff, H, W, (long)P->N * H * W, op.kh, op.kw, s));
         break;
       case BwdOp::kConv: {
         op.conv.p.wpk = pk + op.conv.w_off;
@@ -1357,8 +1391,8 @@ static int backward_launches(CsrPlan* P, const void* packed_bwd, const float* gr
       case BwdOp::kScatter: {
         const LayerSpec& L = P->fwd_layers[op.layer];
         if (!dw[op.layer]) return fail(CSR_ERR_BAD_ARG, "null weight-gradient pointer for layer %d", op.layer);
-        CSR_CUDA(launch_wgrad_scatter(P->dacc, op.ld_n, dw[op.layer], L.cout, L.cin, L.kh, L.kw, op.fold, op.phase, op.ci0, op.ci_n, op.col0,
-                                      op.scale, s));
+        CSR_CUDA(launch_wgrad_scatter(P->dacc, op.ld_n, dw[op.layer], op.taps_t ? op.taps_t : L.cout, L.cin, op.taps_t ? 1 : L.kh, op.taps_t ? 1 : L.kw, op.fold, op.phase, op.ci0, op.ci_n, op.col0,
+                                      op.scale, op.taps_t, s));
         break;
       }
       case BwdOp::kBias: {
@@ -1371,7 +1405,7 @@ static int backward_launches(CsrPlan* P, const void* packed_bwd, const float* gr
         break;
       }
       case BwdOp::kBiasPlanar:
-        CSR_CUDA(launch_bias_grad_planar(reinterpret_cast<const float*>(op.src), op.count, op.scale, db[op.layer], s));
+        CSR_CUDA(launch_bias_grad_planar(op.src ? reinterpret_cast<const float*>(op.src) : grad_out, op.count, op.scale, db[op.layer], s));
         break;
       case BwdOp::kScale:
         CSR_CUDA(launch_scale_copy64(op.src, op.C, op.dst, op.coff, op.count, op.scale, s));

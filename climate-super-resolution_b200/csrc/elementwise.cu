@@ -194,7 +194,7 @@ __global__ void wgrad_reduce_kernel(float* __restrict__ dacc, long part_stride, 
 }
 
 __global__ void wgrad_scatter_kernel(const float* __restrict__ dacc, int ld_n, float* __restrict__ dw, int cout,
-                                     int cin, int kh, int kw, int fold, int phase, int ci0, int ci_n, int col0, float scale) {
+                                     int cin, int kh, int kw, int fold, int phase, int ci0, int ci_n, int col0, float scale, int taps_t) {
   const int ekh = phase >= 0 ? 2 : kh;
   const int ekw = phase >= 0 ? 2 : (fold ? 1 : kw);
   const long total = static_cast<long>(ekh) * ekw * ci_n * cout;
@@ -206,6 +206,11 @@ __global__ void wgrad_scatter_kernel(const float* __restrict__ dacc, int ld_n, f
     const int dx = r % ekw, dy = r / ekw;
     const float v = scale * dacc[((static_cast<long>(dy) * ekw + dx) * 128 + cl) * ld_n + col0 + co];
     const int ce = ci0 + cl;                               // executed input channel
+    if (taps_t) {
+      // 1x1 GEMM against an output-gradient im2col: column co is tap co of a (1, cin, KH, KW) weight -> dw[ci][tap]
+      if (ce < cin) dw[static_cast<long>(ce) * cout + co] += v;
+      continue;
+    }
     if (phase >= 0) {
       if (ce >= cin) continue;
       int y0, y1, x0, x1;
@@ -309,6 +314,34 @@ __global__ void scale_copy64_kernel(const __nv_bfloat16* __restrict__ src, int s
   }
 }
 
+// Output-gradient im2col for single-output-channel convs (conv_last 64->1 3x3, srcnn.conv3 32->1 5x5): channel t = dy*KW+dx
+// of pixel q holds g at pixel q - (dy-PH, dx-PW) (zero outside the image).  With it both gradients of such a layer are
+// 1x1 GEMMs: d/dx[q][ci] = sum_t gcol[q][t] w[ci][t] and dW[ci][t] = sum_q x[q][ci] gcol[q][t] - K (or N) = taps instead
+// of one tiny MMA per tap.  src: fp32 planar (N,1,H,W) when src_C == 0, else bf16 NHWC channel 0 of pitch src_C.
+__global__ void gcol_pack_kernel(const void* __restrict__ src, int src_C, __nv_bfloat16* __restrict__ dst, int dst_C, int H, int W, long total_pix,
+                                 int KH, int KW) {
+  const int PH = KH / 2, PW = KW / 2;
+  const long hw = static_cast<long>(H) * W;
+  for (long q = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; q < total_pix; q += static_cast<long>(gridDim.x) * blockDim.x) {
+    const long n = q / hw;
+    const int r = static_cast<int>(q - n * hw);
+    const int y = r / W, x = r - y * W;
+    __nv_bfloat16* o = dst + q * dst_C;
+    int t = 0;
+    for (int dy = 0; dy < KH; ++dy)
+      for (int dx = 0; dx < KW; ++dx, ++t) {
+        const int ys = y - (dy - PH), xs = x - (dx - PW);
+        float v = 0.f;
+        if (ys >= 0 && ys < H && xs >= 0 && xs < W) {
+          const long p = n * hw + static_cast<long>(ys) * W + xs;
+          v = src_C ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(src)[p * src_C]) : reinterpret_cast<const float*>(src)[p];
+        }
+        o[t] = __float2bfloat16_rn(v);
+      }
+    for (; t < dst_C; ++t) o[t] = __float2bfloat16_rn(0.f);
+  }
+}
+
 static inline int grid_for(long total, int block, int cap = 148 * 16) {
   long g = (total + block - 1) / block;
   if (g > cap) g = cap;
@@ -352,10 +385,10 @@ cudaError_t launch_wgrad_reduce(float* dacc, long part_stride, int n_parts, long
   return cudaGetLastError();
 }
 cudaError_t launch_wgrad_scatter(const float* dacc, int ld_n, float* dw, int cout, int cin, int kh, int kw, int fold,
-                                 int phase, int ci0, int ci_n, int col0, float scale, cudaStream_t s) {
+                                 int phase, int ci0, int ci_n, int col0, float scale, int taps_t, cudaStream_t s) {
   const int ekh = phase >= 0 ? 2 : kh, ekw = phase >= 0 ? 2 : (fold ? 1 : kw);
   const long total = static_cast<long>(ekh) * ekw * ci_n * cout;
-  wgrad_scatter_kernel<<<grid_for(total, 256), 256, 0, s>>>(dacc, ld_n, dw, cout, cin, kh, kw, fold, phase, ci0, ci_n, col0, scale);
+  wgrad_scatter_kernel<<<grid_for(total, 256), 256, 0, s>>>(dacc, ld_n, dw, cout, cin, kh, kw, fold, phase, ci0, ci_n, col0, scale, taps_t);
   return cudaGetLastError();
 }
 cudaError_t launch_bias_grad(const void* g, long npix, int C, int coff, int cout, float scale, float* const* db, int nseg, cudaStream_t s) {
@@ -378,6 +411,12 @@ cudaError_t launch_scale_copy64(const void* src, int src_C, void* dst, int dst_C
 
 cudaError_t launch_pack_jobs(const PackJob* jobs_dev, int njobs, cudaStream_t s) {
   pack_jobs_kernel<<<dim3(16, njobs), 256, 0, s>>>(jobs_dev);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_gcol_pack(const void* src, int src_C, void* dst, int dst_C, int H, int W, long total_pix, int KH, int KW, cudaStream_t s) {
+  gcol_pack_kernel<<<grid_for(total_pix, 256, 148 * 16), 256, 0, s>>>(src, src_C, reinterpret_cast<__nv_bfloat16*>(dst), dst_C, H, W, total_pix,
+                                                                     KH, KW);
   return cudaGetLastError();
 }
 
