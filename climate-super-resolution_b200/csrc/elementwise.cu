@@ -318,27 +318,38 @@ __global__ void scale_copy64_kernel(const __nv_bfloat16* __restrict__ src, int s
 // of pixel q holds g at pixel q - (dy-PH, dx-PW) (zero outside the image).  With it both gradients of such a layer are
 // 1x1 GEMMs: d/dx[q][ci] = sum_t gcol[q][t] w[ci][t] and dW[ci][t] = sum_q x[q][ci] gcol[q][t] - K (or N) = taps instead
 // of one tiny MMA per tap.  src: fp32 planar (N,1,H,W) when src_C == 0, else bf16 NHWC channel 0 of pitch src_C.
-__global__ void gcol_pack_kernel(const void* __restrict__ src, int src_C, __nv_bfloat16* __restrict__ dst, int dst_C, int H, int W, long total_pix,
-                                 int KH, int KW) {
-  const int PH = KH / 2, PW = KW / 2;
+template <int KH, int KW, int DST_C>
+__global__ void gcol_pack_kernel(const void* __restrict__ src, int src_C, __nv_bfloat16* __restrict__ dst, int H, int W, long total_pix) {
+  constexpr int PH = KH / 2, PW = KW / 2;
   const long hw = static_cast<long>(H) * W;
   for (long q = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; q < total_pix; q += static_cast<long>(gridDim.x) * blockDim.x) {
     const long n = q / hw;
     const int r = static_cast<int>(q - n * hw);
     const int y = r / W, x = r - y * W;
-    __nv_bfloat16* o = dst + q * dst_C;
-    int t = 0;
+    float v[DST_C];
+#pragma unroll
+    for (int t = 0; t < DST_C; ++t) v[t] = 0.f;
+#pragma unroll
     for (int dy = 0; dy < KH; ++dy)
-      for (int dx = 0; dx < KW; ++dx, ++t) {
+#pragma unroll
+      for (int dx = 0; dx < KW; ++dx) {
         const int ys = y - (dy - PH), xs = x - (dx - PW);
-        float v = 0.f;
         if (ys >= 0 && ys < H && xs >= 0 && xs < W) {
           const long p = n * hw + static_cast<long>(ys) * W + xs;
-          v = src_C ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(src)[p * src_C]) : reinterpret_cast<const float*>(src)[p];
+          v[dy * KW + dx] = src_C ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(src)[p * src_C])
+                                  : __ldg(reinterpret_cast<const float*>(src) + p);
         }
-        o[t] = __float2bfloat16_rn(v);
       }
-    for (; t < dst_C; ++t) o[t] = __float2bfloat16_rn(0.f);
+    uint4* o = reinterpret_cast<uint4*>(dst + q * DST_C);     // one pixel = DST_C/8 16-byte stores
+#pragma unroll
+    for (int k = 0; k < DST_C / 8; ++k) {
+      uint4 a;
+      a.x = pack_bf16x2(v[8 * k + 0], v[8 * k + 1]);
+      a.y = pack_bf16x2(v[8 * k + 2], v[8 * k + 3]);
+      a.z = pack_bf16x2(v[8 * k + 4], v[8 * k + 5]);
+      a.w = pack_bf16x2(v[8 * k + 6], v[8 * k + 7]);
+      o[k] = a;
+    }
   }
 }
 
@@ -415,8 +426,11 @@ cudaError_t launch_pack_jobs(const PackJob* jobs_dev, int njobs, cudaStream_t s)
 }
 
 cudaError_t launch_gcol_pack(const void* src, int src_C, void* dst, int dst_C, int H, int W, long total_pix, int KH, int KW, cudaStream_t s) {
-  gcol_pack_kernel<<<grid_for(total_pix, 256, 148 * 16), 256, 0, s>>>(src, src_C, reinterpret_cast<__nv_bfloat16*>(dst), dst_C, H, W, total_pix,
-                                                                     KH, KW);
+  __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(dst);
+  const int grid = grid_for(total_pix, 128, 148 * 32);
+  if (KH == 5 && KW == 5 && dst_C == 32) gcol_pack_kernel<5, 5, 32><<<grid, 128, 0, s>>>(src, src_C, d, H, W, total_pix);
+  else if (KH == 3 && KW == 3 && dst_C == 16) gcol_pack_kernel<3, 3, 16><<<grid, 128, 0, s>>>(src, src_C, d, H, W, total_pix);
+  else return cudaErrorInvalidValue;
   return cudaGetLastError();
 }
 
