@@ -32,6 +32,11 @@ static int g_opt_force_generic = 0;
 static int g_opt_one_mma = 0;
 static int g_opt_graphs = 1;
 static int g_opt_graph_max_px = 1 << 21;   // forward: replay a CUDA graph up to this many HR pixels per call (larger batches are GPU-bound)
+static int g_opt_issue_order = 1;       // MMA warps take strict turns tile by tile: 0 never, 1 in CTA-pair launches, 2 in every launch
+static int g_opt_trace_cta = 0;         // debug: CTA recorded by csr_debug_set_trace
+static int g_opt_pair = 0;              // CTA-pair (cta_group::2) launches for 3x3 layers with >= 96 KB of weights.  Measured (cfg2): MMAs run at the
+                                        // 108 clk/MMA pair rate instead of ~140, but two SMs in lock-step on two accumulators expose the epilogue:
+                                        // 6.11 vs 5.90 ms per step, so it stays off by default
 static int g_opt_no_single_group = 1;   // measured: merging the groups buys a 3rd window slot for RDB conv5 but the single group then paces the tile (no net gain)
 static int g_dbg_wgrad[5] = {0, 0, 0, 0, 0};   // a_lbo, a_sbo, b_lbo, b_sbo, flags overrides of the MN-major descriptors
 static int g_opt_no_direct32 = 1;   // measured: no gain over staging on cfg2 (tools/ab_bench.py), kept as an option
@@ -276,9 +281,23 @@ static int build_conv(const PackLayer& pl, const PackPart& pp, int N, int H, int
   p.n_acc = (4 * p.KW * p.npad <= 512 && p.npad <= 32 && !g_opt_two_acc) ? 4 : 2;
   p.n_groups = p.n_acc;
   Tiling tl;
-  int rc = choose_tiling(H, W, pp.kh, pp.kw, p.w_bytes, p.n_kblocks, p.stage_row_bytes, p.n_groups, &tl);
+  int rc = CSR_OK;
+  // CTA pair (tcgen05 cta_group::2) for 3x3 layers with >= 96 KB of weights (RDB conv5 and the matching input-gradient
+  // convs): each CTA keeps half of the weights, so the window ring gets 5 slots instead of 2.  Needs an even tile count
+  // (the two CTAs of a pair always work on adjacent tiles) and one of the specialised epilogues.
+  const int res_bits = (io.r1 ? 1 : 0) | (io.r2 ? 2 : 0) | (io.gate ? 4 : 0);
+  if (g_opt_pair && tma_out && p.KW == 3 && p.PW == 1 && (p.KW * p.npad) % 16 == 0 && p.w_bytes >= 96 * 1024 && io.act == CSR_ACT_NONE &&
+      (res_bits == 1 || res_bits == 3 || res_bits == 4 || res_bits == 5) && !g_opt_force_generic) {
+    Tiling tp;
+    if (choose_tiling(H, W, pp.kh, pp.kw, p.w_bytes / 2, p.n_kblocks, p.stage_row_bytes, p.n_groups, &tp) == CSR_OK &&
+        (((long long)ceil_div(W, tp.TW) * ceil_div(H, tp.TH) * N) & 1) == 0) {
+      tl = tp;
+      p.pair = 1;
+    }
+  }
+  if (!p.pair) rc = choose_tiling(H, W, pp.kh, pp.kw, p.w_bytes, p.n_kblocks, p.stage_row_bytes, p.n_groups, &tl);
   if (rc) return rc;
-  if (tma_out && p.n_groups == 2 && tl.n_slots < 3 && !g_opt_no_single_group) {
+  if (!p.pair && tma_out && p.n_groups == 2 && tl.n_slots < 3 && !g_opt_no_single_group) {
     // Weights leave little shared memory (RDB conv5: 144 KB): one epilogue group (16 warps, still two accumulator
     // buffers) needs one staging buffer instead of two, which buys a third window slot - the MMAs of such a layer take
     // far longer than its epilogue, and with two slots every tile waited ~2400 clk for its TMA load.
@@ -288,7 +307,7 @@ static int build_conv(const PackLayer& pl, const PackPart& pp, int N, int H, int
       p.n_groups = 1;
     }
   }
-  if (tma_out && tl.n_slots < 2 * p.n_kblocks && pp.n_store % 16 == 0 && io.out_C % 16 == 0 && (io.out_coff + pp.co_lo) % 16 == 0 &&
+  if (!p.pair && tma_out && tl.n_slots < 2 * p.n_kblocks && pp.n_store % 16 == 0 && io.out_C % 16 == 0 && (io.out_coff + pp.co_lo) % 16 == 0 &&
       !g_opt_no_direct32) {
     // The resident weights leave too little shared memory for staging AND a window ring that prefetches across tiles
     // (RDB conv5: 144 KB of weights): store whole 32-byte sectors straight from registers instead.
@@ -313,11 +332,13 @@ static int build_conv(const PackLayer& pl, const PackPart& pp, int N, int H, int
   p.win_rows = tl.win_rows; p.win_bytes = tl.win_bytes; p.slot_bytes = tl.slot_bytes; p.n_slots = tl.n_slots;
   p.stage_bytes = tl.stage_bytes;
   p.n_mma = g_opt_one_mma ? 1 : 2;
+  p.issue_order = (p.n_mma == 2) && (g_opt_issue_order == 2 || (g_opt_issue_order == 1 && p.pair));
   int cols = 32;
   while (cols < p.n_acc * p.KW * p.npad) cols *= 2;
   if (cols > 512 || p.KW * p.npad > 256) return fail(CSR_ERR_UNSUPPORTED, "KW*npad = %d exceeds the UMMA N / TMEM budget", p.KW * p.npad);
   p.tmem_cols = cols;
   p.trace = g_trace;
+  p.trace_cta = g_opt_trace_cta;
   p.use_pdl = g_opt_pdl;
   p.force_generic = g_opt_force_generic;
   p.act = io.act;
@@ -1028,6 +1049,9 @@ int csr_set_option(int32_t key, int32_t value) {
     case 7: g_opt_one_mma = value ? 1 : 0; return CSR_OK;
     case 11: g_opt_graphs = value ? 1 : 0; return CSR_OK;        // CUDA-graph replay of plan forward / backward_flat
     case 12: g_opt_graph_max_px = value; return CSR_OK;
+    case 14: g_opt_issue_order = value; return CSR_OK;
+    case 15: g_opt_trace_cta = value; return CSR_OK;
+    case 13: g_opt_pair = value ? 1 : 0; return CSR_OK;          // CTA-pair launches (default off)
     case 9: g_opt_no_single_group = value ? 1 : 0; return CSR_OK;  // 0: one epilogue group (one staging buffer) when that deepens the window ring
     case 8: g_opt_no_direct32 = value ? 1 : 0; return CSR_OK;    // 0: allow unstaged 32-byte stores when staging starves the window ring        // debug: a single MMA issuer warp  // debug: runtime-switched kernels only        // debug: never use four accumulator buffers   // debug: per-element global stores instead of the staged copy-out
     case 20: case 21: case 22: case 23: case 24: g_dbg_wgrad[key - 20] = value; return CSR_OK;

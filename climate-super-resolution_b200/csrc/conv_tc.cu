@@ -39,7 +39,7 @@ namespace {
 
 #define CSR_TRACE(role, tile_it, ev)                                                                                  \
   do {                                                                                                                \
-    if (p.trace && blockIdx.x == 0 && (tile_it) < 64) p.trace[((role) * 64 + (tile_it)) * 8 + (ev)] = clock64();      \
+    if (p.trace && blockIdx.x == p.trace_cta && (tile_it) < 64) p.trace[((role) * 64 + (tile_it)) * 8 + (ev)] = clock64();      \
   } while (0)
 
 struct Tile {
@@ -124,7 +124,10 @@ __device__ __forceinline__ uint4 ldg16(const void* base, size_t pix, int C, int 
 //   KW_T  horizontal taps (0 = runtime p.KW, taps gathered one at a time);  PW_T left padding when KW_T > 0
 //   ACT_T activation (-1 = runtime p.act);  RES_T bit0 r1, bit1 r2, bit2 gate (-1 = runtime pointers)
 //   ST_T  1 = staged bf16 stores only, 2 = direct 32-byte bf16 stores only, -1 = runtime p.store_mode
-template <int KW_T, int PW_T, int ACT_T, int RES_T, int ST_T>
+//   PAIR_T 1 = CTA pair (cluster of 2, tcgen05 cta_group::2): the two CTAs take adjacent tiles, the leader issues one
+//          M = 256 MMA for both, and each CTA keeps only HALF of the layer's weights resident (B rows [0,N/2) / [N/2,N)),
+//          which is what buys RDB conv5 (144 KB of weights) a window ring deep enough to prefetch across tiles.
+template <int KW_T, int PW_T, int ACT_T, int RES_T, int ST_T, int PAIR_T = 0>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
   extern __shared__ uint8_t smem_raw[];
@@ -133,7 +136,9 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
   const uint32_t slots_addr = smem_base;
   const uint32_t stage_addr = slots_addr + static_cast<uint32_t>(p.n_slots) * p.slot_bytes;   // one staging buffer per epilogue group
   const uint32_t w_addr = stage_addr + static_cast<uint32_t>(p.n_groups) * p.stage_bytes;
-  const uint32_t bias_addr = w_addr + ((p.w_bytes + 127) & ~127);
+  const uint32_t crank = PAIR_T ? cluster_ctarank() : 0u;   // rank in the CTA pair; rank 0 (leader) issues the MMAs
+  const int w_local = PAIR_T ? (p.w_bytes >> 1) : p.w_bytes;  // resident weight bytes of this CTA
+  const uint32_t bias_addr = w_addr + ((w_local + 127) & ~127);
   const uint32_t bar_addr = bias_addr + 256;            // up to 64 fp32 biases
   // barriers: [0] weights, [1..S] a_full, [1+S..2S] a_empty, then acc_full[4], acc_empty[4]
   const int S = p.n_slots;
@@ -145,7 +150,11 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
   auto bar_a_empty = [&](int s) { return bar_addr + 8u * (1 + S + s); };
   auto bar_acc_full = [&](int b) { return bar_addr + 8u * (1 + 2 * S + b); };
   auto bar_acc_empty = [&](int b) { return bar_addr + 8u * (5 + 2 * S + b); };
-  const uint32_t tmem_slot_addr = bar_addr + 8u * (9 + 2 * S);       // [0] TMEM base, [1..2] issuer progress words
+  auto bar_token = [&](int w) { return bar_addr + 8u * (9 + 2 * S + w); };   // "MMA warp w has issued its tile" (issue_order)
+  const uint32_t tmem_slot_addr = bar_addr + 8u * (11 + 2 * S);      // [0] TMEM base, [1..2] issuer progress words
+  // CTA pair: the barriers the LEADER waits on (weights, a_full, acc_empty) live in the leader's shared memory; the peer
+  // reaches them through the cluster window at the same offsets.
+  const uint32_t lead_off = PAIR_T ? (map_to_cta(bar_addr, 0) - bar_addr) : 0u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   float* bias_s = reinterpret_cast<float*>(smem_gen + (bias_addr - smem_base));
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot_addr - smem_base));
@@ -161,29 +170,47 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
   if (threadIdx.x == 0) {
     progress[0] = 0;
     progress[1] = 0;
+    mbar_init(bar_token(0), 1);
+    mbar_init(bar_token(1), 1);
     tma_prefetch_desc(&tmap);
-    mbar_init(bar_w, 1);
+    mbar_init(bar_w, (PAIR_T && crank == 0) ? 2 : 1);     // pair leader: + the peer's "my half has landed" arrival
     for (int s = 0; s < S; ++s) {
       mbar_init(bar_a_full(s), 1);
       mbar_init(bar_a_empty(s), 1);
     }
     for (int b = 0; b < NA; ++b) {
       mbar_init(bar_acc_full(b), 1);
-      mbar_init(bar_acc_empty(b), wpg);
+      mbar_init(bar_acc_empty(b), PAIR_T ? 2 * wpg : wpg);   // pair: the epilogue warps of both CTAs release the leader's buffer
     }
     fence_mbar_init();
     fence_proxy_async_smem();
+  }
+  if constexpr (PAIR_T) cluster_sync_all();               // both CTAs' barriers exist before anything arrives on them remotely
+  if (threadIdx.x == 0) {
     // layer weights (constant data, not produced by the previous kernel): resident for the whole CTA
-    mbar_arrive_expect_tx(bar_w, p.w_bytes);
     const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.wpk);
-    for (int off = 0; off < p.w_bytes; off += 32768) {
-      const int nbytes = min(32768, p.w_bytes - off);
-      bulk_load(w_addr + off, wsrc + off, nbytes, bar_w);
+    if constexpr (PAIR_T) {
+      // every (k-block, dy, k-step) block of N rows x 16 K: this CTA keeps rows [crank*N/2, +N/2)
+      const int full = (KW_T ? KW_T : p.KW) * p.npad * 32, half = full >> 1;
+      mbar_arrive_expect_tx(bar_w, w_local);
+      for (int off = 0, loc = 0; off < p.w_bytes; off += full, loc += half)
+        bulk_load(w_addr + loc, wsrc + off + crank * half, half, bar_w);
+    } else {
+      mbar_arrive_expect_tx(bar_w, p.w_bytes);
+      for (int off = 0; off < p.w_bytes; off += 32768) {
+        const int nbytes = min(32768, p.w_bytes - off);
+        bulk_load(w_addr + off, wsrc + off, nbytes, bar_w);
+      }
     }
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot_addr, p.tmem_cols);
-    tmem_relinquish();
+    if constexpr (PAIR_T) {
+      tmem_alloc_pair(tmem_slot_addr, p.tmem_cols);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(tmem_slot_addr, p.tmem_cols);
+      tmem_relinquish();
+    }
   }
   for (int i = threadIdx.x; i < p.npad; i += blockDim.x) bias_s[i] = p.bias[i];
   tc_fence_before();
@@ -208,9 +235,13 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
         mbar_wait(bar_a_empty(slot), phase ^ 1);
         if (kb == 0 && lane == 0) CSR_TRACE(0, pit, 1);
         if (elect_one()) {
-          mbar_arrive_expect_tx(bar_a_full(slot), p.win_bytes);
-          tma_load_4d(slots_addr + slot * p.slot_bytes, &tmap, bar_a_full(slot), p.cin_off + kb * 64, tl.x0 - p.PW, tl.y0 - p.PH,
-                      tl.n);
+          // pair: both CTAs' windows are counted on the leader's barrier, which the MMA issuer waits on
+          if (crank == 0) mbar_arrive_expect_tx(bar_a_full(slot), PAIR_T ? 2 * p.win_bytes : p.win_bytes);
+          if constexpr (PAIR_T)
+            tma_load_4d_pair(slots_addr + slot * p.slot_bytes, &tmap, bar_a_full(slot) + lead_off, p.cin_off + kb * 64, tl.x0 - p.PW,
+                             tl.y0 - p.PH, tl.n);
+          else
+            tma_load_4d(slots_addr + slot * p.slot_bytes, &tmap, bar_a_full(slot), p.cin_off + kb * 64, tl.x0 - p.PW, tl.y0 - p.PH, tl.n);
         }
         __syncwarp();
         if (++slot == S) { slot = 0; phase ^= 1; }
@@ -218,6 +249,13 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
     }
   } else if (warp <= kMmaWarps) {
     if (warp > p.n_mma) goto done;                       // single-issuer launches: warp 2 idles
+    if (PAIR_T && crank != 0) {                          // CTA pair: only the leader issues; the peer reports its weight half
+      if (warp == 1) {
+        mbar_wait(bar_w, 0);
+        if (lane == 0) mbar_arrive_cluster(bar_w + lead_off);
+      }
+      goto done;
+    }
     // ===================== MMA issuers (warps 1 and 2 take alternate tiles) =====================
     // tcgen05.mma issue proceeds at execution pace (the issuing thread stalls while the tensor pipe is busy), so with a
     // single issuer the ~600 clk of mbarrier round trips between tiles leave the pipe idle.  With two issuers one warp's
@@ -227,8 +265,8 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
     // from the other issuer's progress word otherwise.  All 32 lanes run the warp-uniform control flow; one elected lane issues.  Per
     // MMA only the 14-bit start-address fields of the two descriptors change.
     const int mw = warp - 1;
-    const uint32_t idesc = make_idesc_bf16(kTileM, nmma);
-    const uint32_t b_step16 = static_cast<uint32_t>(nmma * 32) >> 4;          // one (dy,kstep) weight block in 16-byte units
+    const uint32_t idesc = make_idesc_bf16(PAIR_T ? 2 * kTileM : kTileM, nmma);
+    const uint32_t b_step16 = static_cast<uint32_t>(nmma * (PAIR_T ? 16 : 32)) >> 4;   // one (dy,kstep) weight block in 16-byte units
     const uint32_t kb_w16 = static_cast<uint32_t>(p.KH * 4) * b_step16;       // one full k-block of weights
     const uint32_t row16 = static_cast<uint32_t>(p.SW) * 8u;                  // one window row (SW pixels x 128 B)
     const uint32_t a_hi = (1024u >> 4) | (1u << 14) | (2u << 29);             // SBO 1024 B, version 1, 128B swizzle
@@ -259,13 +297,24 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
           const int need = entry - S;
           if (need >= 0 && ((need / p.n_kblocks) & 1) != mw) {
             uint32_t spins = 0;
-            while (progress[1 - mw] <= static_cast<uint32_t>(need))
-              if (++spins > (1u << 24)) mbar_timeout(0xdead0000u + mw, need);
+            while (progress[1 - mw] <= static_cast<uint32_t>(need)) {
+              __nanosleep(32);
+              if (++spins > (1u << 22)) mbar_timeout(0xdead0000u + mw, need);
+            }
           }
         }
         mbar_wait(bar_a_full(slot), phase);
         if (p.n_mma > 1) progress[mw] = static_cast<uint32_t>(entry) + 1u;
         tc_fence_after();
+        if (p.issue_order && kb == 0 && it > 0) {
+          // The tensor pipe executes MMAs in issue order.  With a deep window ring both issuers would interleave their
+          // tiles MMA by MMA, finish both accumulators at the same moment and then leave the pipe idle while both
+          // epilogues run; taking turns (tile it starts once tile it-1 is fully issued) keeps one accumulator draining
+          // while the other fills.
+          // (an mbarrier, not a shared-memory spin: a spinning warp steals issue slots from the epilogue warps on its
+          // scheduler.)  Strict alternation keeps the waiter at most one phase behind, so the parity is unambiguous.
+          mbar_wait(bar_token(1 - mw), static_cast<uint32_t>((it - 1) / p.n_mma) & 1u);
+        }
         if (kb == 0 && lane == 0) CSR_TRACE(1, it, 2);
         const int ks_here = min(4, ksteps_total - kb * 4);
         uint32_t a16 = ((slots_addr + slot * p.slot_bytes) >> 4) | a_lbo;
@@ -274,15 +323,24 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
           uint32_t acc = kb ? 1u : 0u;
           for (int dy = 0; dy < p.KH; ++dy, a16 += row16) {
             for (int ks = 0; ks < ks_here; ++ks, b16 += b_step16) {
-              umma_bf16_split(d_tmem, a16 + ks * 2, a_hi, b16, b_hi, idesc, acc);
+              if constexpr (PAIR_T) umma_bf16_split_pair(d_tmem, a16 + ks * 2, a_hi, b16, b_hi, idesc, acc);
+              else umma_bf16_split(d_tmem, a16 + ks * 2, a_hi, b16, b_hi, idesc, acc);
               acc = 1;
             }
           }
-          umma_commit(bar_a_empty(slot));                                  // window slot reusable once these MMAs have read it
-          if (kb == p.n_kblocks - 1) umma_commit(bar_acc_full(buf));       // accumulator complete -> epilogue
+          if constexpr (PAIR_T) {
+            umma_commit_pair(bar_a_empty(slot));                           // both CTAs' window slots
+            if (kb == p.n_kblocks - 1) umma_commit_pair(bar_acc_full(buf));
+          } else {
+            umma_commit(bar_a_empty(slot));                                // window slot reusable once these MMAs have read it
+            if (kb == p.n_kblocks - 1) umma_commit(bar_acc_full(buf));     // accumulator complete -> epilogue
+          }
         }
         __syncwarp();
-        if (kb == p.n_kblocks - 1 && lane == 0) CSR_TRACE(1, it, 3);
+        if (kb == p.n_kblocks - 1 && lane == 0) {
+          if (p.issue_order) mbar_arrive(bar_token(mw));
+          CSR_TRACE(1, it, 3);
+        }
         ring_advance(1);
       }
       if (p.n_mma > 1) {                                                   // skip the other issuer's tile
@@ -460,7 +518,10 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
       // all TMEM reads of this warp are complete (wait::ld above): hand the accumulator buffer back to the MMA warp
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_acc_empty(buf));
+      if (lane == 0) {
+        if constexpr (PAIR_T) mbar_arrive_cluster(bar_acc_empty(buf) + lead_off);
+        else mbar_arrive(bar_acc_empty(buf));
+      }
       if (tma_store) {
         named_bar_sync(1 + g, gthreads);                  // the staged tile is complete
         if (tracer) CSR_TRACE(2, it, 7);
@@ -487,24 +548,26 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
 done:
   tc_fence_before();
   __syncthreads();
+  if constexpr (PAIR_T) cluster_sync_all();              // the leader's MMAs read the peer's shared memory and TMEM until here
   if (warp == 1) {
     __syncwarp();
     tc_fence_after();
-    tmem_dealloc(tmem_base, p.tmem_cols);
+    if constexpr (PAIR_T) tmem_dealloc_pair(tmem_base, p.tmem_cols);
+    else tmem_dealloc(tmem_base, p.tmem_cols);
   }
 }
 
 size_t conv_smem_bytes(const ConvParams& p) {
   return 1024 /*alignment slack*/ + static_cast<size_t>(p.n_slots) * p.slot_bytes + static_cast<size_t>(p.n_groups) * p.stage_bytes +
-         ((p.w_bytes + 127) & ~127) + 256 /*bias*/ + 8 * (9 + 2 * p.n_slots) + 32;
+         (((p.pair ? p.w_bytes / 2 : p.w_bytes) + 127) & ~127) + 256 /*bias*/ + 8 * (11 + 2 * p.n_slots) + 32;
 }
 
-template <int KW_T, int PW_T, int ACT_T, int RES_T, int ST_T>
+template <int KW_T, int PW_T, int ACT_T, int RES_T, int ST_T, int PAIR_T = 0>
 static int launch_t(const ConvParams& p, const CUtensorMap& tmap, int num_sms, cudaStream_t stream) {
   const size_t smem = conv_smem_bytes(p);
   if (smem > static_cast<size_t>(kSmemLimit)) return static_cast<int>(cudaErrorInvalidValue);
   static bool configured = false;
-  auto kern = conv_tc_kernel<KW_T, PW_T, ACT_T, RES_T, ST_T>;
+  auto kern = conv_tc_kernel<KW_T, PW_T, ACT_T, RES_T, ST_T, PAIR_T>;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
     if (e != cudaSuccess) return static_cast<int>(e);
@@ -512,20 +575,37 @@ static int launch_t(const ConvParams& p, const CUtensorMap& tmap, int num_sms, c
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(p.num_tiles < num_sms ? p.num_tiles : num_sms);
+  if (PAIR_T) cfg.gridDim.x &= ~1u;                       // whole pairs (the host only selects pair mode for an even tile count)
   cfg.blockDim = dim3(kConvThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = p.use_pdl ? 1 : 0;
+  attr[1].id = cudaLaunchAttributeClusterDimension;
+  attr[1].val.clusterDim.x = 2;
+  attr[1].val.clusterDim.y = 1;
+  attr[1].val.clusterDim.z = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = PAIR_T ? 2 : 1;
   return static_cast<int>(cudaLaunchKernelEx(&cfg, kern, p, tmap));
 }
 
 int launch_conv_tc(const ConvParams& p, const CUtensorMap& tmap, int num_sms, cudaStream_t stream) {
   const int res = (p.r1 ? 1 : 0) | (p.r2 ? 2 : 0) | (p.gate ? 4 : 0);
   if ((res & 6) == 6) return static_cast<int>(cudaErrorInvalidValue);   // r2 and gate share an operand slot
+  if (p.pair) {
+    // CTA-pair variants: 3x3 layers whose resident weights would otherwise starve the window ring
+    if (p.store_mode != kStoreStaged || p.KW != 3 || p.PW != 1 || p.act != 0 || (p.num_tiles & 1) || p.force_generic)
+      return static_cast<int>(cudaErrorInvalidValue);
+    switch (res) {
+      case 1: return launch_t<3, 1, 0, 1, 1, 1>(p, tmap, num_sms, stream);
+      case 3: return launch_t<3, 1, 0, 3, 1, 1>(p, tmap, num_sms, stream);
+      case 4: return launch_t<3, 1, 0, 4, 1, 1>(p, tmap, num_sms, stream);
+      case 5: return launch_t<3, 1, 0, 5, 1, 1>(p, tmap, num_sms, stream);
+      default: return static_cast<int>(cudaErrorInvalidValue);
+    }
+  }
 #define CSR_CASE(KW_, PW_, ACT_, RES_, ST_)                                                                  \
   if (p.store_mode == (ST_ == 1 ? kStoreStaged : kStoreDirect32) && !p.force_generic && p.KW == KW_ && p.PW == PW_ && \
       p.act == ACT_ && res == RES_)                                                                          \

@@ -47,6 +47,9 @@ struct ConvParams {
   int n_groups;    // epilogue warp groups (1, 2 or 4, <= n_acc and dividing it): one staging buffer each
   int tmem_cols;   // power of two >= max(32, n_acc*KW*npad)
   int force_generic;  // debug: skip the compile-time specialised kernels
+  int issue_order; // 1 = the two MMA warps take strict turns tile by tile (only meaningful with n_mma == 2)
+  int trace_cta;   // debug: the CTA whose role timestamps go to `trace`
+  int pair;        // 1 = CTA-pair launch (cluster of 2, M = 256 MMAs, half of the weights resident per CTA); needs an even tile count
   int use_pdl;     // launch with programmatic stream serialization (prologue overlaps the previous kernel's tail)
   // epilogue:  v = act(acc + bias);  if r1: v = v*s1 + r1;  if r2: v = v*s2 + r2;  if gate: v *= (gate > 0 ? 1 : gate_neg)
   const float* bias;   // [npad] fp32 (zero padded)

@@ -123,6 +123,33 @@ def test_conv_epilogue_variants():
     assert torch.equal(a, c)
 
 
+def test_conv_cta_pair_matches_single_cta():
+    """CTA-pair launches (tcgen05 cta_group::2, option 13; off by default) of the RDB conv5 shape - 128 -> 64 channels with
+    the x5*0.2 + x residuals of esrgan.py:38,54 - must reproduce the single-CTA kernel bit for bit: same MMAs, same
+    accumulation order, only the operand halves come from two CTAs."""
+    from climsr_b200 import ops
+    from climsr_b200._lib import lib
+    g = torch.Generator().manual_seed(21)
+    n, h, w = 4, 16, 60                          # 4 x 4 x 2 = 32 tiles: an even count, which pair mode needs
+    x = torch.rand((n, 128, h, w), generator=g) * 2 - 1
+    wt = (torch.rand((64, 128, 3, 3), generator=g) * 2 - 1) / 34
+    b = torch.rand((64,), generator=g) - 0.5
+    r2 = torch.rand((n, 64, h, w), generator=g) * 2 - 1
+    xin = _nhwc(x, 128)
+    outs = []
+    for pair in (0, 1):
+        lib.csr_set_option(13, pair)
+        try:
+            o1 = ops.conv2d_nhwc(xin, wt.cuda(), b.cuda(), res1=xin, scale1=0.2)
+            o2 = ops.conv2d_nhwc(xin, wt.cuda(), b.cuda(), res1=xin, scale1=0.2, res2=_nhwc(r2, 64), scale2=0.2)
+        finally:
+            lib.csr_set_option(13, 0)
+        outs.append((o1, o2))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    want = _ref_conv(x, wt, b, "none") * 0.2 + _bf(x[:, :64])
+    assert float((outs[1][0].float().cpu().permute(0, 3, 1, 2) - want).abs().max()) <= 2.0 ** -7 * max(1.0, float(want.abs().max()))
+
+
 def test_conv_transposed_and_gate():
     """Input-gradient conv (transposed/flipped weights) with in-place accumulate and LeakyReLU-derivative gate: the building
     block of the dense-block backward (autograd of esrgan.py:33-38)."""
@@ -322,7 +349,7 @@ def test_pixel_losses_value_and_gradient(shape):
         lr = ref(b, hr.double())
         (lo * 3.0).backward()
         (lr * 3.0).backward()
-        assert abs(float(lo) - float(lr)) <= 1e-6 * max(1.0, abs(float(lr)))
+        assert abs(float(lo.detach()) - float(lr.detach())) <= 1e-6 * max(1.0, abs(float(lr.detach())))
         assert float((a.grad.cpu().double() - b.grad).abs().max()) <= 1e-6 * float(b.grad.abs().max() + 1e-30) + 1e-12
     with torch.no_grad():
         assert losses.l1_loss(sr.cuda(), hr.cuda()).requires_grad is False

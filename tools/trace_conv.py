@@ -10,8 +10,9 @@ from climsr_b200 import ops  # noqa: E402
 from climsr_b200._lib import lib  # noqa: E402
 
 
-def run(name, n, h, w, cin, cout, k, in_c, act="lrelu", out_coff=0):
+def run(name, n, h, w, cin, cout, k, in_c, act="lrelu", out_coff=0, res=False):
     x = torch.zeros((n, h, w, in_c), dtype=torch.bfloat16, device="cuda")
+    kw = dict(res1=x, scale1=0.2) if res else {}
     wt = torch.rand((cout, cin, k, k), device="cuda") - 0.5
     b = torch.rand((cout,), device="cuda")
     trace = torch.zeros(3 * 64 * 8, dtype=torch.int64, device="cuda")
@@ -19,17 +20,25 @@ def run(name, n, h, w, cin, cout, k, in_c, act="lrelu", out_coff=0):
     for rep in range(2):
         lib.csr_debug_set_trace(trace.data_ptr())
         if out is not None:
-            ops.conv2d_nhwc(x, wt, b, act=act, out=out, out_coff=out_coff)
+            ops.conv2d_nhwc(x, wt, b, act=act, out=out, out_coff=out_coff, **kw)
         else:
             ops.conv2d_nhwc(x, wt, b, act=act)
         torch.cuda.synchronize()
     lib.csr_debug_set_trace(None)
+    if out is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(50):
+            ops.conv2d_nhwc(x, wt, b, act=act, out=out, out_coff=out_coff, **kw)
+        e1.record()
+        torch.cuda.synchronize()
+        print(f"== {name}: {e0.elapsed_time(e1) / 50 * 1e3:.1f} us per launch (50 back-to-back, includes host packing)")
     t = trace.cpu().view(3, 64, 8)
     t0 = int(t[0, 0, 0])
     print(f"== {name}: n{n} {h}x{w} cin{cin} cout{cout} k{k}")
     print(" tile | prod: wait_empty_start wait_done | mma: start accempty_ok afull_ok issued | epi: loop_top prefetched accfull_ok math_done bar1 staged bar2 stored")
     for i in range(0, 10):
-        if int(t[1, i, 0]) == 0:
+        if int(t[0, i, 0]) == 0:
             break
         r = lambda v: int(v) - t0  # noqa: E731
         print(f" {i:4d} | {r(t[0,i,0]):8d} {r(t[0,i,1]):8d} | {r(t[1,i,0]):8d} {r(t[1,i,1]):8d} {r(t[1,i,2]):8d} {r(t[1,i,3]):8d} | "
@@ -43,7 +52,12 @@ if __name__ == "__main__":
         lib.csr_set_option(8, 0)
     if os.environ.get("CSR_CONV5"):
         x = None
-        run("rdb.conv5+res", 64, 64, 64, 128, 64, 3, 128, act="none")
+        for pair, cta in ((0, 0), (1, 0), (1, 1)):
+            lib.csr_set_option(13, pair)
+            lib.csr_set_option(15, cta)
+            run(f"rdb.conv5+res pair={pair} cta={cta}", 64, 64, 64, 128, 64, 3, 128, act="none", res=True)
+        lib.csr_set_option(13, 0)
+        lib.csr_set_option(15, 0)
         sys.exit(0)
     if os.environ.get("CSR_ONLY"):
         run("HRconv", 16, 256, 256, 64, 64, 3, 64)
