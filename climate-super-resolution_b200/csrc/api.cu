@@ -33,6 +33,8 @@ static int g_opt_one_mma = 0;
 static int g_opt_graphs = 1;
 static int g_opt_graph_max_px = 1 << 21;   // forward: replay a CUDA graph up to this many HR pixels per call (larger batches are GPU-bound)
 static int g_opt_issue_order = 1;       // MMA warps take strict turns tile by tile: 0 never, 1 in CTA-pair launches, 2 in every launch
+static int g_opt_narrow_box = 1;        // 16- / 32-channel window boxes for layers over <= 16 / 32 input channels
+static int g_opt_regroup = 1;           // dense blocks regrouped by source in the forward (see fwd_exec_table)
 static int g_opt_trace_cta = 0;         // debug: CTA recorded by csr_debug_set_trace
 static int g_opt_pair = 0;              // CTA-pair (cta_group::2) launches for 3x3 layers with >= 96 KB of weights.  Measured (cfg2): MMAs run at the
                                         // 108 clk/MMA pair rate instead of ~140, but two SMs in lock-step on two accumulators expose the epilogue:
@@ -91,15 +93,16 @@ static EncodeTiledFn get_encode_fn() {
 
 // NHWC bf16 activation buffer as a 4-D (C, W, H, N) tensor; box = 64 channels x box_w x box_h x 1, 128B swizzle,
 // out-of-bounds -> zeros (this IS the convolution's zero padding).
-static int encode_act_map(CUtensorMap* m, const void* base, int N, int H, int W, int C, int box_w, int box_h) {
+static int encode_act_map(CUtensorMap* m, const void* base, int N, int H, int W, int C, int box_w, int box_h, int box_c = 64) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return fail(CSR_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
   cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-  cuuint32_t box[4] = {64, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+  cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+  const CUtensorMapSwizzle swz = box_c == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : box_c == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(CSR_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for N%d H%d W%d C%d box %dx%d", (int)r, N, H, W, C, box_w, box_h);
   return CSR_OK;
@@ -116,7 +119,12 @@ struct LayerSpec {
   float wscale = 1.f;      // constant folded into the packed weights
   int src = -1;            // backward tables: index of the forward layer whose weight tensor is packed
   struct Block { int src, ci_lo, n, src_ci_off, src_cin; float wscale; };
-  std::vector<Block> blocks;   // backward tables: executed input-channel blocks gathered from several forward layers
+  // backward tables (transposed): executed input-channel blocks gathered from several forward layers;
+  // forward execution table: executed OUTPUT-channel blocks [ci_lo, ci_lo+n) = filters of layer `src` over its input
+  // channels [src_ci_off, src_ci_off + cin)
+  std::vector<Block> blocks;
+  int block_bias = 0;      // forward blocks: 1 = the bias segments come from the source layers, 0 = zero bias
+  int act_upto = 0;        // forward blocks: > 0 = the layer's LeakyReLU applies to output channels < act_upto only
   int ekw() const { return fold ? 1 : kw; }
   int ecin() const { return fold ? cin * kw : cin; }
 };
@@ -150,6 +158,35 @@ static std::vector<LayerSpec> layer_table(const CsrNetDesc& d) {
   v.push_back({"srcnn.conv1", 64, 3, 9, 9, 1});
   v.push_back({"srcnn.conv2", 32, 64, 1, 1});
   v.push_back({"srcnn.conv3", d.out_channels, 32, 5, 5});
+  return v;
+}
+
+// Forward EXECUTION table.  Same length and order as the state_dict table, but each dense block (esrgan.py:32-38) is
+// regrouped by source: since x_k = lrelu(W_k * [x, x1..x_{k-1}]) and the first 64 input channels of every conv_k are the
+// block input x, ONE launch computes conv1 and the x-parts of conv2..conv4 side by side (64 -> 4*gc channels, UMMA
+// N = 3*64 instead of 3*16 for the same A-tile reads) and writes [x1 | p2 | p3 | p4] into the concat slots of x1..x4;
+// conv_k (k = 2..4) then only runs over x1..x_{k-1} ((k-1)*gc input channels) and adds p_k - read from the very slot it
+// overwrites - before its LeakyReLU.  66 narrow MMAs per tile become 12 wide + 18 narrow ones and conv2..4 read one
+// 64-channel box instead of two.  p_k passes through bf16 once (the concat buffer's type).
+static int fwd_index_rdb(int i, int r, int k);
+static std::vector<LayerSpec> fwd_exec_table(const CsrNetDesc& d, const std::vector<LayerSpec>& f) {
+  std::vector<LayerSpec> v = f;
+  for (size_t i = 0; i < v.size(); ++i) v[i].src = (int)i;
+  if (!g_opt_regroup) return v;
+  for (int i = 0; i < d.nb; ++i)
+    for (int r = 0; r < 3; ++r) {
+      LayerSpec& X = v[fwd_index_rdb(i, r, 1)];
+      X.name += "+x_parts";
+      X.cout = 4 * d.gc; X.cin = d.nf; X.block_bias = 1; X.act_upto = d.gc;
+      for (int k = 1; k <= 4; ++k)
+        X.blocks.push_back({fwd_index_rdb(i, r, k), (k - 1) * d.gc, d.gc, 0, d.nf + (k - 1) * d.gc, 1.f});
+      for (int k = 2; k <= 4; ++k) {
+        LayerSpec& Lk = v[fwd_index_rdb(i, r, k)];
+        Lk.name += ".dense_part";
+        Lk.cin = (k - 1) * d.gc;
+        Lk.blocks.push_back({fwd_index_rdb(i, r, k), 0, d.gc, d.nf, d.nf + (k - 1) * d.gc, 1.f});
+      }
+    }
   return v;
 }
 
@@ -212,7 +249,8 @@ static std::vector<PackLayer> pack_layout(const std::vector<LayerSpec>& layers, 
 struct Tiling {
   int SW, TH, TW, win_rows, win_bytes, slot_bytes, n_slots, stage_bytes;
 };
-static int choose_tiling(int H, int W, int KH, int KW, int w_bytes, int n_kblocks, int stage_row_bytes, int n_stage, Tiling* out) {
+static int choose_tiling(int H, int W, int KH, int KW, int w_bytes, int n_kblocks, int stage_row_bytes, int n_stage, Tiling* out,
+                         int row_bytes = 128) {
   double best = -1;
   for (int SW = 16; SW <= 128; SW *= 2) {
     if (g_opt_force_sw && SW != g_opt_force_sw) continue;
@@ -222,7 +260,7 @@ static int choose_tiling(int H, int W, int KH, int KW, int w_bytes, int n_kblock
     if (TW < 1) continue;
     const int TH = kTileM / SW;
     const int win_rows = TH + KH - 1;
-    const int win_bytes = win_rows * SW * 128;
+    const int win_bytes = win_rows * SW * row_bytes;
     const int slot_bytes = (int)align_up(win_bytes, 1024);
     const int stage_bytes = stage_row_bytes ? (int)align_up((size_t)TH * TW * stage_row_bytes, 1024) : 0;
     const int fixed = 1024 + (int)align_up(w_bytes, 128) + 256 + 512 + n_stage * stage_bytes;
@@ -255,6 +293,8 @@ struct ConvIO {
   void* out = nullptr; int out_C = 0, out_coff = 0; int out_kind = kOutBf16;
   int act = CSR_ACT_NONE;
   const void* r1 = nullptr; int r1_C = 0, r1_coff = 0; float s1 = 1.f;
+  int r1_pre = 0;          // r1 is added before the activation
+  int act_upto = 0;        // > 0: LeakyReLU on output channels < act_upto only (of the whole layer, before the cout split)
   const void* r2 = nullptr; int r2_C = 0, r2_coff = 0; float s2 = 1.f;
   const void* gate = nullptr; int gate_C = 0, gate_coff = 0, gate_from = 0; float gate_neg = 0.2f;
 };
@@ -295,14 +335,19 @@ static int build_conv(const PackLayer& pl, const PackPart& pp, int N, int H, int
       p.pair = 1;
     }
   }
-  if (!p.pair) rc = choose_tiling(H, W, pp.kh, pp.kw, p.w_bytes, p.n_kblocks, p.stage_row_bytes, p.n_groups, &tl);
+  // Layers over <= 32 input channels (the dense-block parts over x1 / x1,x2) only move those channels: 32- or 64-byte
+  // window rows with the matching TMA / UMMA swizzle instead of a whole 64-channel box.  These launches are bound by
+  // the bytes the SM can take in per clock, not by MMAs.
+  p.box_c = 64;
+  if (g_opt_narrow_box && p.n_kblocks == 1 && !p.pair) p.box_c = p.cin <= 16 ? 16 : p.cin <= 32 ? 32 : 64;
+  if (!p.pair) rc = choose_tiling(H, W, pp.kh, pp.kw, p.w_bytes, p.n_kblocks, p.stage_row_bytes, p.n_groups, &tl, p.box_c * 2);
   if (rc) return rc;
   if (!p.pair && tma_out && p.n_groups == 2 && tl.n_slots < 3 && !g_opt_no_single_group) {
     // Weights leave little shared memory (RDB conv5: 144 KB): one epilogue group (16 warps, still two accumulator
     // buffers) needs one staging buffer instead of two, which buys a third window slot - the MMAs of such a layer take
     // far longer than its epilogue, and with two slots every tile waited ~2400 clk for its TMA load.
     Tiling t1;
-    if (choose_tiling(H, W, pp.kh, pp.kw, p.w_bytes, p.n_kblocks, p.stage_row_bytes, 1, &t1) == CSR_OK && t1.n_slots > tl.n_slots) {
+    if (choose_tiling(H, W, pp.kh, pp.kw, p.w_bytes, p.n_kblocks, p.stage_row_bytes, 1, &t1, p.box_c * 2) == CSR_OK && t1.n_slots > tl.n_slots) {
       tl = t1;
       p.n_groups = 1;
     }
@@ -312,7 +357,7 @@ static int build_conv(const PackLayer& pl, const PackPart& pp, int N, int H, int
     // The resident weights leave too little shared memory for staging AND a window ring that prefetches across tiles
     // (RDB conv5: 144 KB of weights): store whole 32-byte sectors straight from registers instead.
     Tiling t2;
-    if (choose_tiling(H, W, pp.kh, pp.kw, p.w_bytes, p.n_kblocks, 0, 0, &t2) == CSR_OK && t2.n_slots >= 2 * p.n_kblocks) {
+    if (choose_tiling(H, W, pp.kh, pp.kw, p.w_bytes, p.n_kblocks, 0, 0, &t2, p.box_c * 2) == CSR_OK && t2.n_slots >= 2 * p.n_kblocks) {
       tl = t2;
       p.store_mode = kStoreDirect32;
       p.stage_row_bytes = 0;
@@ -342,6 +387,12 @@ static int build_conv(const PackLayer& pl, const PackPart& pp, int N, int H, int
   p.use_pdl = g_opt_pdl;
   p.force_generic = g_opt_force_generic;
   p.act = io.act;
+  if (io.act_upto > 0 && io.act == CSR_ACT_LRELU02) {
+    const int upto = io.act_upto - pp.co_lo;               // in this part's channels
+    if (upto <= 0) p.act = CSR_ACT_NONE;
+    else if (upto < pp.n_store) { p.act = 3; p.act_upto = upto; }
+  }
+  p.r1_pre = io.r1 ? io.r1_pre : 0;
   p.s1 = io.s1; p.s2 = io.s2;
   p.r1 = io.r1; p.r1_C = io.r1_C; p.r1_coff = io.r1_coff + pp.co_lo;
   p.r2 = io.r2; p.r2_C = io.r2_C; p.r2_coff = io.r2_coff + pp.co_lo;
@@ -354,7 +405,7 @@ static int build_conv(const PackLayer& pl, const PackPart& pp, int N, int H, int
   p.out_H = up * H; p.out_W = up * W;
   cl->w_off = pp.w_off; cl->b_off = pp.b_off;
   if (conv_smem_bytes(p) > (size_t)kSmemLimit) return fail(CSR_ERR_UNSUPPORTED, "conv needs %zu bytes of shared memory", conv_smem_bytes(p));
-  return encode_act_map(&cl->tmap, io.in, N, H, W, io.in_C, p.SW, p.win_rows);
+  return encode_act_map(&cl->tmap, io.in, N, H, W, io.in_C, p.SW, p.win_rows, p.box_c);
 }
 
 // ------------------------------------------------------------------------------------------- weight gradient
@@ -628,7 +679,8 @@ static int plan_build(CsrPlan* P, void* ws) {
   }
   if (P->train) { P->sgout = reinterpret_cast<float*>(base + L.sgout); P->sgrad = reinterpret_cast<float*>(base + L.sgrad); }
   size_t total = 0;
-  const std::vector<PackLayer> packs = pack_layout(layers, &total);
+  const std::vector<LayerSpec> exec = fwd_exec_table(d, layers);
+  const std::vector<PackLayer> packs = pack_layout(exec, &total);
   P->packed_bytes = total;
   const int C = L.ccat, nf = d.nf, gc = d.gc;
   int li = 0;
@@ -660,7 +712,16 @@ static int plan_build(CsrPlan* P, void* ws) {
       void* dst = P->train ? cat(j + 1) : (r < 2 ? cat(j + 1) : cat(3 * i));
       for (int k = 1; k <= 4; ++k) {
         // x_k = lrelu(conv_k(cat(x, x1..x_{k-1})))  written into its concat slice  (esrgan.py:33-36)
-        rc = add(h, w, io_of(src, C, src, C, nf + (k - 1) * gc, CSR_ACT_LRELU02));
+        ConvIO io = io_of(src, C, src, C, nf + (k - 1) * gc, CSR_ACT_LRELU02);
+        if (g_opt_regroup) {
+          if (k == 1) {
+            io.act_upto = gc;                                // [x1 | p2 | p3 | p4] -> channels [nf, nf + 4 gc)
+          } else {
+            io.cin_off = nf;                                 // reads x1..x_{k-1} only ...
+            io.r1 = src; io.r1_C = C; io.r1_coff = nf + (k - 1) * gc; io.r1_pre = 1;   // ... and adds p_k from its own slot
+          }
+        }
+        rc = add(h, w, io);
         if (rc) return rc;
       }
       // x5*0.2 + x  (esrgan.py:37-38); RDB3 additionally applies the RRDB residual out*0.2 + x_rrdb (esrgan.py:54)
@@ -1050,6 +1111,8 @@ int csr_set_option(int32_t key, int32_t value) {
     case 11: g_opt_graphs = value ? 1 : 0; return CSR_OK;        // CUDA-graph replay of plan forward / backward_flat
     case 12: g_opt_graph_max_px = value; return CSR_OK;
     case 14: g_opt_issue_order = value; return CSR_OK;
+    case 17: g_opt_narrow_box = value ? 1 : 0; return CSR_OK;
+    case 16: g_opt_regroup = value ? 1 : 0; return CSR_OK;       // takes effect for weights packed / plans created afterwards
     case 15: g_opt_trace_cta = value; return CSR_OK;
     case 13: g_opt_pair = value ? 1 : 0; return CSR_OK;          // CTA-pair launches (default off)
     case 9: g_opt_no_single_group = value ? 1 : 0; return CSR_OK;  // 0: one epilogue group (one staging buffer) when that deepens the window ring
@@ -1085,7 +1148,8 @@ int csr_layer_shape(const CsrNetDesc* net, int32_t i, int32_t shape4[4], char* n
 size_t csr_packed_weight_bytes(const CsrNetDesc* net) {
   if (check_net(net)) return 0;
   size_t total = 0;
-  pack_layout(layer_table(*net), &total);
+  const auto t = layer_table(*net);
+  pack_layout(fwd_exec_table(*net, t), &total);
   return total;
 }
 
@@ -1115,7 +1179,7 @@ int csr_pack_weights(const CsrNetDesc* net, const float* const* w, const float* 
   int rc = check_net(net);
   if (rc) return rc;
   if (!w || !b || !packed) return fail(CSR_ERR_BAD_ARG, "null pointer");
-  const auto layers = layer_table(*net);
+  const auto layers = fwd_exec_table(*net, layer_table(*net));
   size_t total = 0;
   const auto packs = pack_layout(layers, &total);
   if (packed_bytes < total) return fail(CSR_ERR_WORKSPACE, "packed buffer %zu < %zu bytes", packed_bytes, total);
@@ -1124,9 +1188,18 @@ int csr_pack_weights(const CsrNetDesc* net, const float* const* w, const float* 
   std::vector<PackJob> jobs;
   for (size_t i = 0; i < layers.size(); ++i) {
     if (!w[i] || !b[i]) return fail(CSR_ERR_BAD_ARG, "null weight/bias pointer for layer %zu", i);
-    for (const PackPart& pp : packs[i].parts)
-      jobs.push_back({w[i], b[i], base + pp.w_off, reinterpret_cast<float*>(base + pp.b_off), layers[i].cout, layers[i].cin, layers[i].kh,
-                      layers[i].kw, layers[i].fold, pp.phase, layers[i].transposed, layers[i].wscale, pp.co_lo, pp.npad, packs[i].cin_pad, 0, 0, 0, 0});
+    const LayerSpec& L = layers[i];
+    for (const PackPart& pp : packs[i].parts) {
+      float* bdst = reinterpret_cast<float*>(base + pp.b_off);
+      if (L.blocks.empty()) {
+        jobs.push_back({w[i], b[i], base + pp.w_off, bdst, L.cout, L.cin, L.kh, L.kw, L.fold, pp.phase, L.transposed, L.wscale, pp.co_lo, pp.npad,
+                        packs[i].cin_pad, 0, 0, 0, 0});
+      } else {
+        for (const LayerSpec::Block& B : L.blocks)         // output-channel blocks gathered from several state_dict layers
+          jobs.push_back({w[B.src], L.block_bias ? b[B.src] : nullptr, base + pp.w_off, bdst, L.cout, L.cin, L.kh, L.kw, 0, pp.phase, 0,
+                          B.wscale, pp.co_lo, pp.npad, packs[i].cin_pad, B.ci_lo, B.n, B.src_ci_off, B.src_cin});
+      }
+    }
   }
   return run_pack_jobs(jobs, packed, s);
 }

@@ -122,7 +122,8 @@ __device__ __forceinline__ uint4 ldg16(const void* base, size_t pix, int C, int 
 
 // Compile-time specialisation of the epilogue (it is instruction-issue bound, so every runtime switch costs):
 //   KW_T  horizontal taps (0 = runtime p.KW, taps gathered one at a time);  PW_T left padding when KW_T > 0
-//   ACT_T activation (-1 = runtime p.act);  RES_T bit0 r1, bit1 r2, bit2 gate (-1 = runtime pointers)
+//   ACT_T activation (-1 = runtime p.act; 3 = LeakyReLU on channels below p.act_upto only);  RES_T bit0 r1, bit1 r2,
+//         bit2 gate, bit3 r1 is added BEFORE the activation (-1 = runtime pointers / p.r1_pre)
 //   ST_T  1 = staged bf16 stores only, 2 = direct 32-byte bf16 stores only, -1 = runtime p.store_mode
 //   PAIR_T 1 = CTA pair (cluster of 2, tcgen05 cta_group::2): the two CTAs take adjacent tiles, the leader issues one
 //          M = 256 MMA for both, and each CTA keeps only HALF of the layer's weights resident (B rows [0,N/2) / [N/2,N)),
@@ -268,8 +269,11 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
     const uint32_t idesc = make_idesc_bf16(PAIR_T ? 2 * kTileM : kTileM, nmma);
     const uint32_t b_step16 = static_cast<uint32_t>(nmma * (PAIR_T ? 16 : 32)) >> 4;   // one (dy,kstep) weight block in 16-byte units
     const uint32_t kb_w16 = static_cast<uint32_t>(p.KH * 4) * b_step16;       // one full k-block of weights
-    const uint32_t row16 = static_cast<uint32_t>(p.SW) * 8u;                  // one window row (SW pixels x 128 B)
-    const uint32_t a_hi = (1024u >> 4) | (1u << 14) | (2u << 29);             // SBO 1024 B, version 1, 128B swizzle
+    // A window: one pixel = one row of box_c channels (128 / 64 / 32 bytes, swizzled with the matching TMA mode)
+    const uint32_t row_bytes = static_cast<uint32_t>(p.box_c) * 2u;
+    const uint32_t row16 = static_cast<uint32_t>(p.SW) * (row_bytes >> 4);    // one window row (SW pixels)
+    const uint32_t a_layout = p.box_c == 64 ? 2u : p.box_c == 32 ? 4u : 6u;   // SWIZZLE_128B / 64B / 32B
+    const uint32_t a_hi = ((8u * row_bytes) >> 4) | (1u << 14) | (a_layout << 29);   // SBO = 8 rows, version 1
     const uint32_t b_hi = (256u >> 4) | (1u << 14);                           // SBO 256 B, version 1, no swizzle
     const uint32_t a_lbo = (16u >> 4) << 16, b_lbo = (128u >> 4) << 16;
     mbar_wait(bar_w, 0);
@@ -328,6 +332,7 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
               acc = 1;
             }
           }
+          if (kb == p.n_kblocks - 1) CSR_TRACE(1, it, 4);
           if constexpr (PAIR_T) {
             umma_commit_pair(bar_a_empty(slot));                           // both CTAs' window slots
             if (kb == p.n_kblocks - 1) umma_commit_pair(bar_acc_full(buf));
@@ -335,6 +340,7 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
             umma_commit(bar_a_empty(slot));                                // window slot reusable once these MMAs have read it
             if (kb == p.n_kblocks - 1) umma_commit(bar_acc_full(buf));     // accumulator complete -> epilogue
           }
+          if (kb == p.n_kblocks - 1) CSR_TRACE(1, it, 5);
         }
         __syncwarp();
         if (kb == p.n_kblocks - 1 && lane == 0) {
@@ -349,6 +355,7 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
       }
       buf += p.n_mma;
       if (buf >= NA) { buf -= NA; acc_phase ^= 1; }
+      if (lane == 0) CSR_TRACE(1, it, 6);
     }
   } else {
     // ===================== epilogue: 16 warps in NG groups; group g takes every NG-th tile (accumulator buffer = tile % NA) ===
@@ -376,6 +383,7 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
     const bool has_r1 = RES_T >= 0 ? (RES_T & 1) != 0 : p.r1 != nullptr;
     const bool has_r2 = RES_T >= 0 ? (RES_T & 2) != 0 : p.r2 != nullptr;
     const bool has_gate = RES_T >= 0 ? (RES_T & 4) != 0 : p.gate != nullptr;
+    const bool r1_pre = RES_T >= 0 ? (RES_T & 8) != 0 : p.r1_pre != 0;    // r1 is a partial pre-activation sum (dense-block regrouping)
     const bool tma_store = ST_T >= 0 ? ST_T == 1 : (p.store_mode == kStoreStaged);
     const bool need_pix = !tma_store || has_r1 || has_r2 || has_gate;    // warp-uniform
     const uint32_t swz = (p.stage_row_bytes == 128) ? static_cast<uint32_t>(srow & 7) : 0u;   // SWIZZLE_128B staging rows
@@ -478,9 +486,14 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
               gather_add8(v, r, dx - PW, lane);
             }
           }
-          apply_act8(v, act);
+          if (r1_pre) fma_residual8(v, q1[j], 1.f);
+          if (act == 3) {
+            if (ch0 < p.act_upto) apply_act8(v, 1);
+          } else {
+            apply_act8(v, act);
+          }
           if (need_pix) {
-            if (has_r1) fma_residual8(v, q1[j], p.s1);
+            if (has_r1 && !r1_pre) fma_residual8(v, q1[j], p.s1);
             if (has_gate) gate8(v, q2[j], p.gate_neg);
             else if (has_r2) fma_residual8(v, q2[j], p.s2);
           }
@@ -592,7 +605,7 @@ static int launch_t(const ConvParams& p, const CUtensorMap& tmap, int num_sms, c
 }
 
 int launch_conv_tc(const ConvParams& p, const CUtensorMap& tmap, int num_sms, cudaStream_t stream) {
-  const int res = (p.r1 ? 1 : 0) | (p.r2 ? 2 : 0) | (p.gate ? 4 : 0);
+  const int res = (p.r1 ? 1 : 0) | (p.r2 ? 2 : 0) | (p.gate ? 4 : 0) | ((p.r1 && p.r1_pre) ? 8 : 0);
   if ((res & 6) == 6) return static_cast<int>(cudaErrorInvalidValue);   // r2 and gate share an operand slot
   if (p.pair) {
     // CTA-pair variants: 3x3 layers whose resident weights would otherwise starve the window ring
@@ -617,6 +630,8 @@ int launch_conv_tc(const ConvParams& p, const CUtensorMap& tmap, int num_sms, cu
   CSR_CASE(3, 1, 0, 3, 1)   // RDB3 conv5 (*0.2 + x, *0.2 + x_rrdb)
   CSR_CASE(3, 1, 0, 1, 2)   // ... the same with unstaged stores (weights leave no room for staging + a deep window ring)
   CSR_CASE(3, 1, 0, 3, 2)
+  CSR_CASE(3, 1, 3, 0, 1)   // dense block regrouped by source: conv1 and the x-parts of conv2-4 in one launch (lrelu on conv1's channels)
+  CSR_CASE(3, 1, 1, 9, 1)   // ... conv2-4 over x1..x_{k-1} only, the x-part added before the lrelu
   CSR_CASE(2, 0, 1, 0, 1)   // upconv sub-pixel phases
   CSR_CASE(2, 1, 1, 0, 1)
   CSR_CASE(1, 0, 2, 0, 1)   // srcnn.conv1 (x-im2col folded), srcnn.conv2: relu

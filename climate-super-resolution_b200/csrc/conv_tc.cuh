@@ -49,12 +49,15 @@ struct ConvParams {
   int force_generic;  // debug: skip the compile-time specialised kernels
   int issue_order; // 1 = the two MMA warps take strict turns tile by tile (only meaningful with n_mma == 2)
   int trace_cta;   // debug: the CTA whose role timestamps go to `trace`
+  int box_c;       // channels per window pixel in shared memory: 64 (128-byte rows), or 32 / 16 for single-k-block layers with cin <= 32 / 16
   int pair;        // 1 = CTA-pair launch (cluster of 2, M = 256 MMAs, half of the weights resident per CTA); needs an even tile count
   int use_pdl;     // launch with programmatic stream serialization (prologue overlaps the previous kernel's tail)
-  // epilogue:  v = act(acc + bias);  if r1: v = v*s1 + r1;  if r2: v = v*s2 + r2;  if gate: v *= (gate > 0 ? 1 : gate_neg)
+  // epilogue:  v = act(acc + bias [+ r1 if r1_pre]);  if r1 (not r1_pre): v = v*s1 + r1;  if r2: v = v*s2 + r2;  if gate: v *= (gate > 0 ? 1 : gate_neg)
   const float* bias;   // [npad] fp32 (zero padded)
   const void* wpk;     // packed bf16 weights (global), layout [kblock][dy][kstep in kblock][KW*npad/8][2][8][8]
-  int act;             // 0 none, 1 leaky-relu 0.2, 2 relu
+  int act;             // 0 none, 1 leaky-relu 0.2, 2 relu, 3 leaky-relu 0.2 on output channels < act_upto only
+  int act_upto;
+  int r1_pre;          // 1: r1 is added BEFORE the activation (v = act(acc + bias + r1)) instead of after it
   float s1, s2;
   const void* r1; int r1_C, r1_coff;
   const void* r2; int r2_C, r2_coff;

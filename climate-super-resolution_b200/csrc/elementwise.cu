@@ -58,7 +58,10 @@ __device__ __forceinline__ void pack_weight_body(const float* __restrict__ w, __
     const int co = co_lo + (rr - dx * npad);
     int ci = (kb * 4 + ks) * 16 + kchunk * 8 + e;
     // block jobs fill only executed input channels [ci_lo, ci_lo + ci_n) (another job of the same layer fills the rest)
-    if (ci_n > 0 && (ci < ci_lo || ci >= ci_lo + ci_n)) continue;
+    if (ci_n > 0) {
+      const int cb = transposed ? ci : co;                // output-channel blocks for forward (non-transposed) layers
+      if (cb < ci_lo || cb >= ci_lo + ci_n) continue;
+    }
     float v = 0.f;
     const int cin_eff = fold ? cin * kw : cin;
     if (co < cout && ci < cin_eff) {
@@ -68,8 +71,10 @@ __device__ __forceinline__ void pack_weight_body(const float* __restrict__ w, __
       }
       // source indices: the forward layer's OIHW tensor is (cout, cin, kh, kw), or (cin, cout, kh, kw) when transposed
       // (block jobs: source output channel = ci - ci_lo, source input channel = co + src_ci_off of a (ci_n, src_cin, kh, kw) tensor)
-      const int s_o = transposed ? ci - ci_lo : co, s_i = transposed ? co + src_ci_off : ci;
-      const int s_in = transposed ? (src_cin ? src_cin : cout) : cin;   // channels-per-output-filter of the source tensor
+      // forward block jobs: source output channel = co - ci_lo, source input channel = ci + src_ci_off
+      const int s_o = transposed ? ci - ci_lo : (ci_n > 0 ? co - ci_lo : co);
+      const int s_i = transposed ? co + src_ci_off : (ci_n > 0 ? ci + src_ci_off : ci);
+      const int s_in = transposed ? (src_cin ? src_cin : cout) : (ci_n > 0 ? src_cin : cin);   // channels-per-output-filter of the source tensor
       const int sdy = transposed ? ekh - 1 - dy : dy, sdx = transposed ? ekw - 1 - dx : dx;
       if (phase >= 0) {
         int y0, y1, x0, x1;
@@ -98,8 +103,14 @@ __global__ void pack_jobs_kernel(const PackJob* __restrict__ jobs) {
   pack_weight_body(j.w, reinterpret_cast<__nv_bfloat16*>(j.dst), j.cout, j.cin, j.kh, j.kw, j.fold, j.phase, j.transposed, j.wscale, j.co_lo,
                    j.npad, j.cin_pad, j.ci_lo, j.ci_n, j.src_ci_off, j.src_cin, blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x,
                    static_cast<long>(gridDim.x) * blockDim.x);
-  if (blockIdx.x == 0 && threadIdx.x < j.npad && j.bdst)
-    j.bdst[threadIdx.x] = (j.b && j.co_lo + static_cast<int>(threadIdx.x) < j.cout) ? j.b[j.co_lo + threadIdx.x] : 0.f;
+  if (blockIdx.x == 0 && threadIdx.x < j.npad && j.bdst) {
+    const int co = j.co_lo + static_cast<int>(threadIdx.x);
+    if (j.ci_n > 0 && !j.transposed) {                    // forward block job: only its own bias segment
+      if (co >= j.ci_lo && co < j.ci_lo + j.ci_n) j.bdst[threadIdx.x] = j.b ? j.b[co - j.ci_lo] : 0.f;
+    } else {
+      j.bdst[threadIdx.x] = (j.b && co < j.cout) ? j.b[co] : 0.f;
+    }
+  }
 }
 
 __global__ void pack_bias_kernel(const float* __restrict__ b, float* __restrict__ dst, int cout, int co_lo, int npad) {

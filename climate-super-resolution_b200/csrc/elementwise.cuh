@@ -6,8 +6,11 @@ namespace csr {
 struct PackJob {
   const float* w; const float* b; void* dst; float* bdst;
   int cout, cin, kh, kw, fold, phase, transposed; float wscale; int co_lo, npad, cin_pad;
-  int ci_lo, ci_n, src_ci_off, src_cin;   // block jobs (ci_n > 0): fill executed input channels [ci_lo, ci_lo+ci_n) from a source
-                                          // tensor of shape (ci_n, src_cin, kh, kw), its input channels offset by src_ci_off
+  // block jobs (ci_n > 0): fill only the executed channel block [ci_lo, ci_lo+ci_n) from a source tensor of shape
+  // (ci_n, src_cin, kh, kw) whose input channels are offset by src_ci_off.  transposed: the block is a range of executed
+  // INPUT channels (dense-block backward); otherwise a range of executed OUTPUT channels (dense-block forward regrouped by
+  // source: several layers' filters over the same input side by side), the bias segment included.
+  int ci_lo, ci_n, src_ci_off, src_cin;
 };
 cudaError_t launch_pack_jobs(const PackJob* jobs_dev, int njobs, cudaStream_t s);
 cudaError_t launch_pack_weight(const float* w, void* dst, int cout, int cin, int kh, int kw, int fold, int phase, int transposed,

@@ -10,9 +10,11 @@ from climsr_b200 import ops  # noqa: E402
 from climsr_b200._lib import lib  # noqa: E402
 
 
-def run(name, n, h, w, cin, cout, k, in_c, act="lrelu", out_coff=0, res=False):
+def run(name, n, h, w, cin, cout, k, in_c, act="lrelu", out_coff=0, res=False, in_coff=0):
     x = torch.zeros((n, h, w, in_c), dtype=torch.bfloat16, device="cuda")
     kw = dict(res1=x, scale1=0.2) if res else {}
+    if in_coff:
+        kw["in_coff"] = in_coff
     wt = torch.rand((cout, cin, k, k), device="cuda") - 0.5
     b = torch.rand((cout,), device="cuda")
     trace = torch.zeros(3 * 64 * 8, dtype=torch.int64, device="cuda")
@@ -41,6 +43,10 @@ def run(name, n, h, w, cin, cout, k, in_c, act="lrelu", out_coff=0, res=False):
         if int(t[0, i, 0]) == 0:
             break
         r = lambda v: int(v) - t0  # noqa: E731
+        if os.environ.get("CSR_MMA_DETAIL"):
+            print(f" {i:4d} | mma: start {r(t[1,i,0])} accempty_ok {r(t[1,i,1])} afull_ok {r(t[1,i,2])} mmas_issued {r(t[1,i,4])} "
+                  f"commits_issued {r(t[1,i,5])} synced {r(t[1,i,3])} loop_end {r(t[1,i,6])}")
+            continue
         print(f" {i:4d} | {r(t[0,i,0]):8d} {r(t[0,i,1]):8d} | {r(t[1,i,0]):8d} {r(t[1,i,1]):8d} {r(t[1,i,2]):8d} {r(t[1,i,3]):8d} | "
               f"{r(t[2,i,3]):8d} {r(t[2,i,0]):8d} {r(t[2,i,1]):8d} {r(t[2,i,4]):8d} {r(t[2,i,5]):8d} {r(t[2,i,6]):8d} {r(t[2,i,7]):8d} {r(t[2,i,2]):8d}")
 
@@ -58,6 +64,11 @@ if __name__ == "__main__":
             run(f"rdb.conv5+res pair={pair} cta={cta}", 64, 64, 64, 128, 64, 3, 128, act="none", res=True)
         lib.csr_set_option(13, 0)
         lib.csr_set_option(15, 0)
+        sys.exit(0)
+    if os.environ.get("CSR_DENSE"):
+        run("dense x-pass 64->64", 64, 64, 64, 64, 64, 3, 128, out_coff=64)
+        run("dense conv2 part 16->16", 64, 64, 64, 16, 16, 3, 128, out_coff=80, in_coff=64)
+        run("dense conv4 part 48->16", 64, 64, 64, 48, 16, 3, 128, out_coff=112, in_coff=64)
         sys.exit(0)
     if os.environ.get("CSR_ONLY"):
         run("HRconv", 16, 256, 256, 64, 64, 3, 64)
