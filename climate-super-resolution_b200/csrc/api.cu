@@ -33,8 +33,11 @@ static int g_opt_one_mma = 0;
 static int g_opt_graphs = 1;
 static int g_opt_graph_max_px = 1 << 21;   // forward: replay a CUDA graph up to this many HR pixels per call (larger batches are GPU-bound)
 static int g_opt_issue_order = 1;       // MMA warps take strict turns tile by tile: 0 never, 1 in CTA-pair launches, 2 in every launch
+static int g_opt_eight_acc = 1;         // eight accumulator buffers for two-tile windows when TMEM has room (KW*npad <= 64)
+static int g_opt_tall = 1;              // two M tiles per window for thin layers
 static int g_opt_narrow_box = 1;        // 16- / 32-channel window boxes for layers over <= 16 / 32 input channels
-static int g_opt_regroup = 1;           // dense blocks regrouped by source in the forward (see fwd_exec_table)
+static int g_opt_regroup = 0;           // dense blocks regrouped by source in the forward (see fwd_exec_table): -3 % alone, but the plain
+                                        // layout gains more from two-tile windows (5.76 vs 5.85 ms), so it is off by default
 static int g_opt_trace_cta = 0;         // debug: CTA recorded by csr_debug_set_trace
 static int g_opt_pair = 0;              // CTA-pair (cta_group::2) launches for 3x3 layers with >= 96 KB of weights.  Measured (cfg2): MMAs run at the
                                         // 108 clk/MMA pair rate instead of ~140, but two SMs in lock-step on two accumulators expose the epilogue:
@@ -248,9 +251,10 @@ static std::vector<PackLayer> pack_layout(const std::vector<LayerSpec>& layers, 
 // ------------------------------------------------------------------------------------------- tiling
 struct Tiling {
   int SW, TH, TW, win_rows, win_bytes, slot_bytes, n_slots, stage_bytes;
+  double eff;   // useful fraction of the MMA rows (with the small penalties applied by choose_tiling)
 };
 static int choose_tiling(int H, int W, int KH, int KW, int w_bytes, int n_kblocks, int stage_row_bytes, int n_stage, Tiling* out,
-                         int row_bytes = 128) {
+                         int row_bytes = 128, int tall = 1) {
   double best = -1;
   for (int SW = 16; SW <= 128; SW *= 2) {
     if (g_opt_force_sw && SW != g_opt_force_sw) continue;
@@ -259,20 +263,20 @@ static int choose_tiling(int H, int W, int KH, int KW, int w_bytes, int n_kblock
     const int TW = SW - (KW - 1);
     if (TW < 1) continue;
     const int TH = kTileM / SW;
-    const int win_rows = TH + KH - 1;
+    const int win_rows = tall * TH + KH - 1;
     const int win_bytes = win_rows * SW * row_bytes;
     const int slot_bytes = (int)align_up(win_bytes, 1024);
     const int stage_bytes = stage_row_bytes ? (int)align_up((size_t)TH * TW * stage_row_bytes, 1024) : 0;
     const int fixed = 1024 + (int)align_up(w_bytes, 128) + 256 + 512 + n_stage * stage_bytes;
     const int slots = std::min(g_opt_max_slots, (kSmemLimit - fixed) / slot_bytes);
     if (slots < 1) continue;
-    const double tiles = (double)ceil_div(H, TH) * ceil_div(W, TW);
+    const double tiles = (double)ceil_div(H, TH * tall) * ceil_div(W, TW) * tall;
     double eff = (double)H * W / (tiles * kTileM);
     if (slots < std::min(2, n_kblocks + 1)) eff *= 0.7;  // no load/MMA overlap
     eff -= 1e-4 * win_bytes / (double)(kTileM * 128);    // tie-break: less halo traffic
     if (eff > best) {
       best = eff;
-      *out = {SW, TH, TW, win_rows, win_bytes, slot_bytes, slots, stage_bytes};
+      *out = {SW, TH, TW, win_rows, win_bytes, slot_bytes, slots, stage_bytes, eff};
     }
   }
   if (best < 0) return fail(CSR_ERR_UNSUPPORTED, "no tile shape fits shared memory (weights %d bytes, %dx%d kernel)", w_bytes, KH, KW);
@@ -340,7 +344,21 @@ static int build_conv(const PackLayer& pl, const PackPart& pp, int N, int H, int
   // the bytes the SM can take in per clock, not by MMAs.
   p.box_c = 64;
   if (g_opt_narrow_box && p.n_kblocks == 1 && !p.pair) p.box_c = p.cin <= 16 ? 16 : p.cin <= 32 ? 32 : 64;
+  // Thin layers (<= 32 output channels: four accumulator buffers) are bound by the per-tile work of the producer and
+  // MMA-issuer warps (~110 / ~250 scalar instructions at ~5 clk each), not by MMAs or bytes: give them windows of two M
+  // tiles, which halves that work per tile and shrinks the halo from 6/4 to 10/8 rows.
   if (!p.pair) rc = choose_tiling(H, W, pp.kh, pp.kw, p.w_bytes, p.n_kblocks, p.stage_row_bytes, p.n_groups, &tl, p.box_c * 2);
+  if (!rc && g_opt_tall && !p.pair && p.n_acc == 4 && p.n_groups == 4) {
+    Tiling t2;   // taken unless the second M tile would mostly hang below the image
+    if (choose_tiling(H, W, pp.kh, pp.kw, p.w_bytes, p.n_kblocks, p.stage_row_bytes, p.n_groups, &t2, p.box_c * 2, 2) == CSR_OK &&
+        t2.eff >= 0.85 * tl.eff && t2.n_slots >= 2) {
+      tl = t2;
+      p.tall_shift = 1;
+      // two issuers x two M tiles fill four accumulators at once: with eight, the next windows' MMAs overlap the
+      // epilogue of these four instead of waiting for it
+      if (8 * p.KW * p.npad <= 512 && g_opt_eight_acc) p.n_acc = 8;
+    }
+  }
   if (rc) return rc;
   if (!p.pair && tma_out && p.n_groups == 2 && tl.n_slots < 3 && !g_opt_no_single_group) {
     // Weights leave little shared memory (RDB conv5: 144 KB): one epilogue group (16 warps, still two accumulator
@@ -367,7 +385,7 @@ static int build_conv(const PackLayer& pl, const PackPart& pp, int N, int H, int
   p.sw_shift = 0;
   while ((1 << p.sw_shift) < p.SW) ++p.sw_shift;
   p.tiles_x = ceil_div(W, p.TW);
-  p.tiles_y = ceil_div(H, p.TH);
+  p.tiles_y = ceil_div(H, p.TH << p.tall_shift);          // windows
   p.num_tiles = p.tiles_x * p.tiles_y * N;
   p.tiles_per_img = p.tiles_x * p.tiles_y;
   if ((long long)p.tiles_x * p.tiles_y * N >= (1 << 24) || p.tiles_per_img >= (1 << 16))
@@ -1111,6 +1129,8 @@ int csr_set_option(int32_t key, int32_t value) {
     case 11: g_opt_graphs = value ? 1 : 0; return CSR_OK;        // CUDA-graph replay of plan forward / backward_flat
     case 12: g_opt_graph_max_px = value; return CSR_OK;
     case 14: g_opt_issue_order = value; return CSR_OK;
+    case 19: g_opt_eight_acc = value ? 1 : 0; return CSR_OK;
+    case 18: g_opt_tall = value ? 1 : 0; return CSR_OK;
     case 17: g_opt_narrow_box = value ? 1 : 0; return CSR_OK;
     case 16: g_opt_regroup = value ? 1 : 0; return CSR_OK;       // takes effect for weights packed / plans created afterwards
     case 15: g_opt_trace_cta = value; return CSR_OK;

@@ -51,12 +51,13 @@ __device__ __forceinline__ int fast_div(int t, unsigned long long magic) {
   return static_cast<int>((static_cast<unsigned long long>(static_cast<unsigned>(t)) * magic) >> 40);
 }
 
+template <int TALL_T>
 __device__ __forceinline__ Tile decode_tile(const ConvParams& p, int t) {
   Tile r;
   r.n = fast_div(t, p.magic_img);
   const int rem = t - r.n * p.tiles_per_img;
   const int ty = fast_div(rem, p.magic_row);
-  r.y0 = ty * p.TH;
+  r.y0 = ty * (p.TH << TALL_T);                          // window origin: a window holds 1 or 2 vertically adjacent M tiles
   r.x0 = (rem - ty * p.tiles_x) * p.TW;
   return r;
 }
@@ -128,7 +129,8 @@ __device__ __forceinline__ uint4 ldg16(const void* base, size_t pix, int C, int 
 //   PAIR_T 1 = CTA pair (cluster of 2, tcgen05 cta_group::2): the two CTAs take adjacent tiles, the leader issues one
 //          M = 256 MMA for both, and each CTA keeps only HALF of the layer's weights resident (B rows [0,N/2) / [N/2,N)),
 //          which is what buys RDB conv5 (144 KB of weights) a window ring deep enough to prefetch across tiles.
-template <int KW_T, int PW_T, int ACT_T, int RES_T, int ST_T, int PAIR_T = 0>
+//   TALL_T 1 = two M tiles per window (ConvParams::tall_shift), compile-time so that the common kernels carry none of it
+template <int KW_T, int PW_T, int ACT_T, int RES_T, int ST_T, int PAIR_T = 0, int TALL_T = 0>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
   extern __shared__ uint8_t smem_raw[];
@@ -141,18 +143,18 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
   const int w_local = PAIR_T ? (p.w_bytes >> 1) : p.w_bytes;  // resident weight bytes of this CTA
   const uint32_t bias_addr = w_addr + ((w_local + 127) & ~127);
   const uint32_t bar_addr = bias_addr + 256;            // up to 64 fp32 biases
-  // barriers: [0] weights, [1..S] a_full, [1+S..2S] a_empty, then acc_full[4], acc_empty[4]
+  // barriers: [0] weights, [1..S] a_full, [1+S..2S] a_empty, then acc_full[8], acc_empty[8], token[2]
   const int S = p.n_slots;
-  const int NA = p.n_acc;                               // accumulator buffers in TMEM (2 or 4)
+  const int NA = p.n_acc;                               // accumulator buffers in TMEM (2, 4 or 8)
   const int NG = p.n_groups;                            // epilogue warp groups (1, 2 or 4; NG <= NA): tiles in flight in the epilogue
   const int wpg = kEpilogueWarps / NG;                  // warps per epilogue group
   auto bar_w = bar_addr;
   auto bar_a_full = [&](int s) { return bar_addr + 8u * (1 + s); };
   auto bar_a_empty = [&](int s) { return bar_addr + 8u * (1 + S + s); };
   auto bar_acc_full = [&](int b) { return bar_addr + 8u * (1 + 2 * S + b); };
-  auto bar_acc_empty = [&](int b) { return bar_addr + 8u * (5 + 2 * S + b); };
-  auto bar_token = [&](int w) { return bar_addr + 8u * (9 + 2 * S + w); };   // "MMA warp w has issued its tile" (issue_order)
-  const uint32_t tmem_slot_addr = bar_addr + 8u * (11 + 2 * S);      // [0] TMEM base, [1..2] issuer progress words
+  auto bar_acc_empty = [&](int b) { return bar_addr + 8u * (9 + 2 * S + b); };
+  auto bar_token = [&](int w) { return bar_addr + 8u * (17 + 2 * S + w); };  // "MMA warp w has issued its tile" (issue_order)
+  const uint32_t tmem_slot_addr = bar_addr + 8u * (19 + 2 * S);      // [0] TMEM base, [1..2] issuer progress words
   // CTA pair: the barriers the LEADER waits on (weights, a_full, acc_empty) live in the leader's shared memory; the peer
   // reaches them through the cluster window at the same offsets.
   const uint32_t lead_off = PAIR_T ? (map_to_cta(bar_addr, 0) - bar_addr) : 0u;
@@ -230,7 +232,7 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
     int slot = 0, pit = 0;
     uint32_t phase = 0;
     for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++pit) {
-      const Tile tl = decode_tile(p, t);
+      const Tile tl = decode_tile<TALL_T>(p, t);
       for (int kb = 0; kb < p.n_kblocks; ++kb) {
         if (kb == 0 && lane == 0) CSR_TRACE(0, pit, 0);
         mbar_wait(bar_a_empty(slot), phase ^ 1);
@@ -280,7 +282,8 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
     tc_fence_after();
     // window-slot ring position of k-block 0 of this warp's first tile (the ring is shared by both issuers: tile `it`
     // owns ring entries it*n_kblocks .. it*n_kblocks + n_kblocks-1)
-    int slot = 0, buf = mw;
+    constexpr int tall = 1 << TALL_T;                    // M tiles per window (2: thin layers, see ConvParams::tall_shift)
+    int slot = 0, buf = mw * tall;
     uint32_t phase = 0, acc_phase = 0;
     auto ring_advance = [&](int steps) {
       for (int i = 0; i < steps; ++i)
@@ -293,6 +296,7 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
       if (t >= p.num_tiles) break;
       if (lane == 0) CSR_TRACE(1, it, 0);
       mbar_wait(bar_acc_empty(buf), acc_phase ^ 1);
+      if constexpr (TALL_T) mbar_wait(bar_acc_empty(buf + 1), acc_phase ^ 1);
       tc_fence_after();
       if (lane == 0) CSR_TRACE(1, it, 1);
       const uint32_t d_tmem = tmem_base + buf * nmma;
@@ -324,21 +328,37 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
         uint32_t a16 = ((slots_addr + slot * p.slot_bytes) >> 4) | a_lbo;
         uint32_t b16 = ((w_addr >> 4) + static_cast<uint32_t>(kb) * kb_w16) | b_lbo;
         if (elect_one()) {
-          uint32_t acc = kb ? 1u : 0u;
-          for (int dy = 0; dy < p.KH; ++dy, a16 += row16) {
-            for (int ks = 0; ks < ks_here; ++ks, b16 += b_step16) {
-              if constexpr (PAIR_T) umma_bf16_split_pair(d_tmem, a16 + ks * 2, a_hi, b16, b_hi, idesc, acc);
-              else umma_bf16_split(d_tmem, a16 + ks * 2, a_hi, b16, b_hi, idesc, acc);
-              acc = 1;
+          const bool last_kb = kb == p.n_kblocks - 1;
+          if constexpr (TALL_T == 0) {
+            uint32_t acc = kb ? 1u : 0u;
+            for (int dy = 0; dy < p.KH; ++dy, a16 += row16) {
+              for (int ks = 0; ks < ks_here; ++ks, b16 += b_step16) {
+                if constexpr (PAIR_T) umma_bf16_split_pair(d_tmem, a16 + ks * 2, a_hi, b16, b_hi, idesc, acc);
+                else umma_bf16_split(d_tmem, a16 + ks * 2, a_hi, b16, b_hi, idesc, acc);
+                acc = 1;
+              }
+            }
+          } else {
+            for (int hh = 0; hh < 2; ++hh) {               // M tile hh of the window: window rows [hh*TH, hh*TH + TH + KH - 1)
+              uint32_t acc = kb ? 1u : 0u;
+              uint32_t ah = a16 + static_cast<uint32_t>(hh * p.TH) * row16, bh = b16;
+              const uint32_t dh = d_tmem + static_cast<uint32_t>(hh * nmma);
+              for (int dy = 0; dy < p.KH; ++dy, ah += row16) {
+                for (int ks = 0; ks < ks_here; ++ks, bh += b_step16) {
+                  umma_bf16_split(dh, ah + ks * 2, a_hi, bh, b_hi, idesc, acc);
+                  acc = 1;
+                }
+              }
+              if (last_kb && hh == 0) umma_commit(bar_acc_full(buf));   // upper tile done: its epilogue can start
             }
           }
-          if (kb == p.n_kblocks - 1) CSR_TRACE(1, it, 4);
+          if (last_kb) CSR_TRACE(1, it, 4);
           if constexpr (PAIR_T) {
             umma_commit_pair(bar_a_empty(slot));                           // both CTAs' window slots
-            if (kb == p.n_kblocks - 1) umma_commit_pair(bar_acc_full(buf));
+            if (last_kb) umma_commit_pair(bar_acc_full(buf));
           } else {
             umma_commit(bar_a_empty(slot));                                // window slot reusable once these MMAs have read it
-            if (kb == p.n_kblocks - 1) umma_commit(bar_acc_full(buf));     // accumulator complete -> epilogue
+            if (last_kb) umma_commit(bar_acc_full(buf + tall - 1));        // accumulator complete -> epilogue
           }
           if (kb == p.n_kblocks - 1) CSR_TRACE(1, it, 5);
         }
@@ -353,7 +373,7 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
         ring_advance(p.n_kblocks);
         entry += p.n_kblocks;
       }
-      buf += p.n_mma;
+      buf += p.n_mma * tall;
       if (buf >= NA) { buf -= NA; acc_phase ^= 1; }
       if (lane == 0) CSR_TRACE(1, it, 6);
     }
@@ -412,11 +432,12 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
     }
     int buf = g % NA;
     uint32_t acc_phase = 0;
-    for (int it = g; ; it += NG) {
-      const int t = blockIdx.x + it * static_cast<int>(gridDim.x);
+    for (int it = g; ; it += NG) {                        // `it` counts M tiles; window = it >> tall_shift
+      const int t = blockIdx.x + (it >> TALL_T) * static_cast<int>(gridDim.x);
       if (t >= p.num_tiles) break;
       if (tracer) CSR_TRACE(2, it, 3);
-      const Tile tl = decode_tile(p, t);
+      Tile tl = decode_tile<TALL_T>(p, t);
+      if constexpr (TALL_T) tl.y0 += (it & 1) * p.TH;
       bool valid = false;
       size_t pix = 0;
       int y = 0, x = 0;
@@ -457,6 +478,8 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
             const float4 b1 = *reinterpret_cast<const float4*>(bias_s + ch0 + 4);
             v[0] = b0.x; v[1] = b0.y; v[2] = b0.z; v[3] = b0.w; v[4] = b1.x; v[5] = b1.y; v[6] = b1.z; v[7] = b1.w;
           }
+          // (issuing chunk j+1's TMEM loads ahead of chunk j's arithmetic - double-buffered or into the same registers -
+          // spills under the 104-register cap and measured 0.7 ms slower per cfg2 step)
           if constexpr (KW_T == 1) {
             uint32_t r0[8];
             tmem_ld8(t_addr + ch0, r0);
@@ -541,7 +564,8 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
         __nv_bfloat16* tile_out = reinterpret_cast<__nv_bfloat16*>(p.out) +
             ((static_cast<size_t>(tl.n) * p.out_H + (tl.y0 * p.out_sy + p.out_oy)) * p.out_W + (tl.x0 * p.out_sx + p.out_ox)) * p.out_C +
             p.out_coff;
-        const uint32_t lim = (static_cast<uint32_t>(min(p.H - tl.y0, 0x7fff)) << 16) | static_cast<uint32_t>(min(p.W - tl.x0, 0x7fff));
+        // (the lower M tile of a window may lie entirely below the image: no piece passes)
+        const uint32_t lim = (static_cast<uint32_t>(max(0, min(p.H - tl.y0, 0x7fff))) << 16) | static_cast<uint32_t>(min(p.W - tl.x0, 0x7fff));
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           // piece inside the image: dy < H - y0 and dx < W - x0 (both halves compared at once; 0xffffffff = no piece)
@@ -572,15 +596,15 @@ done:
 
 size_t conv_smem_bytes(const ConvParams& p) {
   return 1024 /*alignment slack*/ + static_cast<size_t>(p.n_slots) * p.slot_bytes + static_cast<size_t>(p.n_groups) * p.stage_bytes +
-         (((p.pair ? p.w_bytes / 2 : p.w_bytes) + 127) & ~127) + 256 /*bias*/ + 8 * (11 + 2 * p.n_slots) + 32;
+         (((p.pair ? p.w_bytes / 2 : p.w_bytes) + 127) & ~127) + 256 /*bias*/ + 8 * (19 + 2 * p.n_slots) + 32;
 }
 
-template <int KW_T, int PW_T, int ACT_T, int RES_T, int ST_T, int PAIR_T = 0>
+template <int KW_T, int PW_T, int ACT_T, int RES_T, int ST_T, int PAIR_T = 0, int TALL_T = 0>
 static int launch_t(const ConvParams& p, const CUtensorMap& tmap, int num_sms, cudaStream_t stream) {
   const size_t smem = conv_smem_bytes(p);
   if (smem > static_cast<size_t>(kSmemLimit)) return static_cast<int>(cudaErrorInvalidValue);
   static bool configured = false;
-  auto kern = conv_tc_kernel<KW_T, PW_T, ACT_T, RES_T, ST_T, PAIR_T>;
+  auto kern = conv_tc_kernel<KW_T, PW_T, ACT_T, RES_T, ST_T, PAIR_T, TALL_T>;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
     if (e != cudaSuccess) return static_cast<int>(e);
@@ -617,6 +641,21 @@ int launch_conv_tc(const ConvParams& p, const CUtensorMap& tmap, int num_sms, cu
       case 4: return launch_t<3, 1, 0, 4, 1, 1>(p, tmap, num_sms, stream);
       case 5: return launch_t<3, 1, 0, 5, 1, 1>(p, tmap, num_sms, stream);
       default: return static_cast<int>(cudaErrorInvalidValue);
+    }
+  }
+  if (p.tall_shift) {
+    // two-M-tile windows: the thin layers only (four accumulator buffers)
+    if ((p.n_acc != 4 && p.n_acc != 8) || p.n_groups != 4) return static_cast<int>(cudaErrorInvalidValue);
+    if (p.store_mode == kStoreStaged && !p.force_generic && p.KW == 3 && p.PW == 1 && p.act == 1 && res == 0)
+      return launch_t<3, 1, 1, 0, 1, 0, 1>(p, tmap, num_sms, stream);      // RDB conv1-4 (not regrouped)
+    if (p.store_mode == kStoreStaged && !p.force_generic && p.KW == 3 && p.PW == 1 && p.act == 1 && res == 9)
+      return launch_t<3, 1, 1, 9, 1, 0, 1>(p, tmap, num_sms, stream);      // RDB conv2-4 over x1..x_{k-1}
+    if (p.store_mode == kStoreStaged && !p.force_generic && p.KW == 1 && p.PW == 0 && p.act == 2 && res == 0)
+      return launch_t<1, 0, 2, 0, 1, 0, 1>(p, tmap, num_sms, stream);      // srcnn.conv2
+    switch (p.KW) {
+      case 1: return launch_t<1, 0, -1, -1, -1, 0, 1>(p, tmap, num_sms, stream);
+      case 3: if (p.PW == 1) return launch_t<3, 1, -1, -1, -1, 0, 1>(p, tmap, num_sms, stream);
+      default: return launch_t<0, 0, -1, -1, -1, 0, 1>(p, tmap, num_sms, stream);
     }
   }
 #define CSR_CASE(KW_, PW_, ACT_, RES_, ST_)                                                                  \

@@ -43,13 +43,16 @@ struct ConvParams {
   int n_slots;     // activation-window ring depth
   int w_bytes;     // packed weights: KH * (cin/16) * KW * npad * 32
   int n_mma;       // MMA issuer warps in use (2; 1 = debug)
-  int n_acc;       // accumulator buffers in TMEM (2 or 4); n_acc * KW * npad <= 512
-  int n_groups;    // epilogue warp groups (1, 2 or 4, <= n_acc and dividing it): one staging buffer each
+  int n_acc;       // accumulator buffers in TMEM (2, 4 or 8); n_acc * KW * npad <= 512
+  int n_groups;    // epilogue warp groups (1, 2 or 4; n_groups divides n_acc): one staging buffer each
   int tmem_cols;   // power of two >= max(32, n_acc*KW*npad)
   int force_generic;  // debug: skip the compile-time specialised kernels
   int issue_order; // 1 = the two MMA warps take strict turns tile by tile (only meaningful with n_mma == 2)
   int trace_cta;   // debug: the CTA whose role timestamps go to `trace`
   int box_c;       // channels per window pixel in shared memory: 64 (128-byte rows), or 32 / 16 for single-k-block layers with cin <= 32 / 16
+  int tall_shift;  // 1: a window holds TWO vertically adjacent M tiles (2*TH + KH - 1 rows, one TMA load, one MMA-issuer iteration,
+                   //    two accumulator buffers): halves the per-tile control cost of thin layers; needs n_acc == 4.  tiles_* / num_tiles
+                   //    then count windows.  0: one M tile per window
   int pair;        // 1 = CTA-pair launch (cluster of 2, M = 256 MMAs, half of the weights resident per CTA); needs an even tile count
   int use_pdl;     // launch with programmatic stream serialization (prologue overlaps the previous kernel's tail)
   // epilogue:  v = act(acc + bias [+ r1 if r1_pre]);  if r1 (not r1_pre): v = v*s1 + r1;  if r2: v = v*s2 + r2;  if gate: v *= (gate > 0 ? 1 : gate_neg)

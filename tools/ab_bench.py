@@ -19,16 +19,18 @@ VARIANTS = {
     "no_pdl": {1: 0},
     "single_group_conv5": {9: 0},
     "pair": {13: 1},
-    "no_regroup": {16: 0},
+    "regroup": {16: 1},
+    "no_eight_acc": {19: 0},
     "no_narrow_box": {17: 0},
+    "no_tall": {18: 0},
     "pair_unordered": {13: 1, 14: 0},
     "order_all": {14: 2},
 }
 
 
 def run(name, opts, n=64, h=64, w=64, steps=20):
-    for k in (1, 3, 5, 7, 8, 9, 13, 14, 16, 17):
-        lib.csr_set_option(k, {1: 1, 3: 8, 8: 1, 9: 1, 14: 1, 16: 1, 17: 1}.get(k, 0))
+    for k in (1, 3, 5, 7, 8, 9, 13, 14, 16, 17, 18, 19):
+        lib.csr_set_option(k, {1: 1, 3: 8, 8: 1, 9: 1, 14: 1, 17: 1, 18: 1, 19: 1}.get(k, 0))
     for k, v in opts.items():
         lib.csr_set_option(k, v)
     torch.manual_seed(0)
