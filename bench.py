@@ -431,6 +431,14 @@ def main():
                          "SLOWER (12.1 vs 7.3 ms at cfg3 on 2 GPUs): the conv grids are sized to all 148 SMs, so NCCL's CTAs push every "
                          "concurrent conv launch into a second wave")
     args = ap.parse_args()
+    if args.impl != "reference" and os.environ.get("CSR_OPTS"):
+        # tuning hook: CSR_OPTS="18=0,19=0" applies csr_set_option(key, value) pairs before anything is built
+        sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "climate-super-resolution_b200"))
+        from climsr_b200._lib import lib
+        for kv in os.environ["CSR_OPTS"].split(","):
+            k, v = kv.split("=")
+            if lib.csr_set_option(int(k), int(v)) != 0:
+                raise SystemExit(f"bench.py: csr_set_option({k}, {v}) failed")
     if args.impl == "reference":
         run_reference(args)
     elif args.mode == "train":

@@ -1145,8 +1145,13 @@ int csr_set_option(int32_t key, int32_t value) {
 int64_t csr_kernel_launch_count(void) { return g_launches.load(); }
 
 int csr_debug_set_trace(void* device_buffer) {
+#ifdef CSR_ENABLE_TRACE
   g_trace = reinterpret_cast<long long*>(device_buffer);
   return CSR_OK;
+#else
+  if (!device_buffer) return CSR_OK;
+  return fail(CSR_ERR_UNSUPPORTED, "this build has no pipeline tracing (rebuild with CSR_BUILD_TRACE=1 python build.py --force)");
+#endif
 }
 
 int csr_num_layers(const CsrNetDesc* net) {

@@ -37,10 +37,16 @@ namespace csr {
 
 namespace {
 
+// Per-role clock64 stamps (csr_debug_set_trace).  Compiled in only with -DCSR_ENABLE_TRACE (CSR_BUILD_TRACE=1 python
+// build.py): the ~20 stamp sites are ~2 KB of code, and the kernel has to fit the instruction cache.
+#ifdef CSR_ENABLE_TRACE
 #define CSR_TRACE(role, tile_it, ev)                                                                                  \
   do {                                                                                                                \
     if (p.trace && blockIdx.x == p.trace_cta && (tile_it) < 64) p.trace[((role) * 64 + (tile_it)) * 8 + (ev)] = clock64();      \
   } while (0)
+#else
+#define CSR_TRACE(role, tile_it, ev) do { } while (0)
+#endif
 
 struct Tile {
   int n, y0, x0;
@@ -235,7 +241,7 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
       const Tile tl = decode_tile<TALL_T>(p, t);
       for (int kb = 0; kb < p.n_kblocks; ++kb) {
         if (kb == 0 && lane == 0) CSR_TRACE(0, pit, 0);
-        mbar_wait(bar_a_empty(slot), phase ^ 1);
+        mbar_wait_spin(bar_a_empty(slot), phase ^ 1);
         if (kb == 0 && lane == 0) CSR_TRACE(0, pit, 1);
         if (elect_one()) {
           // pair: both CTAs' windows are counted on the leader's barrier, which the MMA issuer waits on
@@ -254,7 +260,7 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
     if (warp > p.n_mma) goto done;                       // single-issuer launches: warp 2 idles
     if (PAIR_T && crank != 0) {                          // CTA pair: only the leader issues; the peer reports its weight half
       if (warp == 1) {
-        mbar_wait(bar_w, 0);
+        mbar_wait_spin(bar_w, 0);
         if (lane == 0) mbar_arrive_cluster(bar_w + lead_off);
       }
       goto done;
@@ -278,7 +284,7 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
     const uint32_t a_hi = ((8u * row_bytes) >> 4) | (1u << 14) | (a_layout << 29);   // SBO = 8 rows, version 1
     const uint32_t b_hi = (256u >> 4) | (1u << 14);                           // SBO 256 B, version 1, no swizzle
     const uint32_t a_lbo = (16u >> 4) << 16, b_lbo = (128u >> 4) << 16;
-    mbar_wait(bar_w, 0);
+    mbar_wait_spin(bar_w, 0);
     tc_fence_after();
     // window-slot ring position of k-block 0 of this warp's first tile (the ring is shared by both issuers: tile `it`
     // owns ring entries it*n_kblocks .. it*n_kblocks + n_kblocks-1)
@@ -295,8 +301,8 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
       const int t = blockIdx.x + it * static_cast<int>(gridDim.x);
       if (t >= p.num_tiles) break;
       if (lane == 0) CSR_TRACE(1, it, 0);
-      mbar_wait(bar_acc_empty(buf), acc_phase ^ 1);
-      if constexpr (TALL_T) mbar_wait(bar_acc_empty(buf + 1), acc_phase ^ 1);
+      mbar_wait_spin(bar_acc_empty(buf), acc_phase ^ 1);
+      if constexpr (TALL_T) mbar_wait_spin(bar_acc_empty(buf + 1), acc_phase ^ 1);
       tc_fence_after();
       if (lane == 0) CSR_TRACE(1, it, 1);
       const uint32_t d_tmem = tmem_base + buf * nmma;
@@ -304,14 +310,11 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
         if (p.n_mma > 1) {
           const int need = entry - S;
           if (need >= 0 && ((need / p.n_kblocks) & 1) != mw) {
-            uint32_t spins = 0;
             while (progress[1 - mw] <= static_cast<uint32_t>(need)) {
-              __nanosleep(32);
-              if (++spins > (1u << 22)) mbar_timeout(0xdead0000u + mw, need);
             }
           }
         }
-        mbar_wait(bar_a_full(slot), phase);
+        mbar_wait_spin(bar_a_full(slot), phase);
         if (p.n_mma > 1) progress[mw] = static_cast<uint32_t>(entry) + 1u;
         tc_fence_after();
         if (p.issue_order && kb == 0 && it > 0) {
@@ -321,7 +324,7 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
           // while the other fills.
           // (an mbarrier, not a shared-memory spin: a spinning warp steals issue slots from the epilogue warps on its
           // scheduler.)  Strict alternation keeps the waiter at most one phase behind, so the parity is unambiguous.
-          mbar_wait(bar_token(1 - mw), static_cast<uint32_t>((it - 1) / p.n_mma) & 1u);
+          mbar_wait_spin(bar_token(1 - mw), static_cast<uint32_t>((it - 1) / p.n_mma) & 1u);
         }
         if (kb == 0 && lane == 0) CSR_TRACE(1, it, 2);
         const int ks_here = min(4, ksteps_total - kb * 4);
@@ -463,7 +466,7 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
       if (tma_store) named_bar_sync(1 + g, gthreads);   // every thread of the group has copied out the previous tile
       if (tracer) CSR_TRACE(2, it, 0);
       const uint32_t t_addr = t_lane + buf * nmma;
-      mbar_wait(bar_acc_full(buf), acc_phase);
+      mbar_wait(bar_acc_full(buf), acc_phase);             // the one bounded wait (see mbar_wait_spin)
       tc_fence_after();
       if (tracer) CSR_TRACE(2, it, 1);
       uint4 held = make_uint4(0, 0, 0, 0);                // first half of a 32-byte direct store

@@ -50,6 +50,14 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (++spins > (1u << 22)) mbar_timeout(bar, parity);
   }
 }
+// Unbounded wait, three instructions.  The conv kernel has ~20 wait sites and must stay below the ~32 KB the SM's
+// instruction cache holds (growing past it cost 9 % of the whole forward), so only ONE site per kernel keeps the
+// bounded form - the epilogue's accumulator wait, which every stalled pipeline ends up starving, so a protocol bug still
+// surfaces there as a trap instead of a hang.
+__device__ __forceinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
 
 // ---------------------------------------------------------------- programmatic dependent launch
 __device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }

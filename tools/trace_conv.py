@@ -74,6 +74,9 @@ if __name__ == "__main__":
         run("HRconv", 16, 256, 256, 64, 64, 3, 64)
         sys.exit(0)
     run("rdb.conv1", 64, 64, 64, 64, 16, 3, 128, out_coff=64)
+    run("rdb.conv4", 64, 64, 64, 112, 16, 3, 128, out_coff=112)
+    if os.environ.get("CSR_THIN"):
+        sys.exit(0)
     run("rdb.conv5", 64, 64, 64, 128, 64, 3, 128, act="none")
     run("HRconv", 16, 256, 256, 64, 64, 3, 64)
     run("conv_first", 64, 64, 64, 4, 64, 3, 64, act="none")
