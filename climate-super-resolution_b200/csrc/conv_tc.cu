@@ -131,7 +131,8 @@ __device__ __forceinline__ uint4 ldg16(const void* base, size_t pix, int C, int 
 //   KW_T  horizontal taps (0 = runtime p.KW, taps gathered one at a time);  PW_T left padding when KW_T > 0
 //   ACT_T activation (-1 = runtime p.act; 3 = LeakyReLU on channels below p.act_upto only);  RES_T bit0 r1, bit1 r2,
 //         bit2 gate, bit3 r1 is added BEFORE the activation (-1 = runtime pointers / p.r1_pre)
-//   ST_T  1 = staged bf16 stores only, 2 = direct 32-byte bf16 stores only, -1 = runtime p.store_mode
+//   ST_T  1 = staged bf16 stores only, 2 = direct 32-byte bf16 stores only, 3 = fp32 planar single-channel output only
+//         (conv_last, srcnn.conv3: just channel 0 is computed), -1 = runtime p.store_mode
 //   PAIR_T 1 = CTA pair (cluster of 2, tcgen05 cta_group::2): the two CTAs take adjacent tiles, the leader issues one
 //          M = 256 MMA for both, and each CTA keeps only HALF of the layer's weights resident (B rows [0,N/2) / [N/2,N)),
 //          which is what buys RDB conv5 (144 KB of weights) a window ring deep enough to prefetch across tiles.
@@ -398,7 +399,7 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
     const int m = lane_grp * 32 + lane;
     const int ty = m >> p.sw_shift;
     const int tx = m & (p.SW - 1);                       // window column
-    const int n_chunks = p.npad >> 3;
+    const int n_chunks = ST_T == 3 ? 1 : p.npad >> 3;     // fp32 planar output: one channel, so one chunk (and of it only v[0] is live)
     const int PW = KW_T ? PW_T : p.PW;
     const bool col_ok = (tx >= PW) && (tx < PW + p.TW);
     const int srow = ty * p.TW + (tx - PW);              // staging row of this thread's pixel
@@ -529,7 +530,7 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
                            pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
           } else if (valid) {
             const size_t opix = (static_cast<size_t>(tl.n) * p.out_H + (y * p.out_sy + p.out_oy)) * p.out_W + (x * p.out_sx + p.out_ox);
-            const int smode = ST_T == 2 ? static_cast<int>(kStoreDirect32) : p.store_mode;
+            const int smode = ST_T == 2 ? static_cast<int>(kStoreDirect32) : ST_T == 3 ? static_cast<int>(kStoreF32Planar) : p.store_mode;
             if (smode == kStoreDirect32) {
               // whole 32-byte sectors per lane (16 channels): no partial-sector writes reach L2
               uint4 o;
@@ -655,6 +656,10 @@ int launch_conv_tc(const ConvParams& p, const CUtensorMap& tmap, int num_sms, cu
       return launch_t<3, 1, 1, 9, 1, 0, 1>(p, tmap, num_sms, stream);      // RDB conv2-4 over x1..x_{k-1}
     if (p.store_mode == kStoreStaged && !p.force_generic && p.KW == 1 && p.PW == 0 && p.act == 2 && res == 0)
       return launch_t<1, 0, 2, 0, 1, 0, 1>(p, tmap, num_sms, stream);      // srcnn.conv2
+    if (p.store_mode == kStoreF32Planar && !p.force_generic && p.KW == 3 && p.PW == 1 && p.act == 0 && res == 0)
+      return launch_t<3, 1, 0, 0, 3, 0, 1>(p, tmap, num_sms, stream);      // conv_last
+    if (p.store_mode == kStoreF32Planar && !p.force_generic && p.KW == 5 && p.PW == 2 && p.act == 0 && res == 0)
+      return launch_t<5, 2, 0, 0, 3, 0, 1>(p, tmap, num_sms, stream);      // srcnn.conv3
     switch (p.KW) {
       case 1: return launch_t<1, 0, -1, -1, -1, 0, 1>(p, tmap, num_sms, stream);
       case 3: if (p.PW == 1) return launch_t<3, 1, -1, -1, -1, 0, 1>(p, tmap, num_sms, stream);
@@ -662,8 +667,8 @@ int launch_conv_tc(const ConvParams& p, const CUtensorMap& tmap, int num_sms, cu
     }
   }
 #define CSR_CASE(KW_, PW_, ACT_, RES_, ST_)                                                                  \
-  if (p.store_mode == (ST_ == 1 ? kStoreStaged : kStoreDirect32) && !p.force_generic && p.KW == KW_ && p.PW == PW_ && \
-      p.act == ACT_ && res == RES_)                                                                          \
+  if (p.store_mode == (ST_ == 1 ? kStoreStaged : ST_ == 3 ? kStoreF32Planar : kStoreDirect32) && !p.force_generic && p.KW == KW_ && \
+      p.PW == PW_ && p.act == ACT_ && res == RES_)                                                           \
     return launch_t<KW_, PW_, ACT_, RES_, ST_>(p, tmap, num_sms, stream);
   // the layer shapes of the generator forward (esrgan.py / srcnn.py) ...
   CSR_CASE(3, 1, 1, 0, 1)   // RDB conv1-4, HRconv: lrelu
@@ -677,9 +682,16 @@ int launch_conv_tc(const ConvParams& p, const CUtensorMap& tmap, int num_sms, cu
   CSR_CASE(2, 0, 1, 0, 1)   // upconv sub-pixel phases
   CSR_CASE(2, 1, 1, 0, 1)
   CSR_CASE(1, 0, 2, 0, 1)   // srcnn.conv1 (x-im2col folded), srcnn.conv2: relu
+  CSR_CASE(3, 1, 0, 0, 3)   // conv_last -> fp32 planar
+  CSR_CASE(5, 2, 0, 0, 3)   // srcnn.conv3 -> fp32 planar (the generator's output)
   // ... and of its backward (input-gradient convs: accumulate in place, LeakyReLU-derivative gate)
   CSR_CASE(3, 1, 0, 5, 1)
   CSR_CASE(3, 1, 0, 4, 1)
+  CSR_CASE(1, 0, 0, 4, 1)   // 1x1 input gradients with a ReLU / LeakyReLU gate: srcnn.conv2, and conv_last / srcnn.conv3 over the gradient im2col
+  CSR_CASE(2, 0, 0, 4, 1)   // upconv2 input gradient, transposed sub-pixel phases (first phase stores, the others accumulate)
+  CSR_CASE(2, 1, 0, 4, 1)
+  CSR_CASE(2, 0, 0, 5, 1)
+  CSR_CASE(2, 1, 0, 5, 1)
 #undef CSR_CASE
   switch (p.KW) {
     case 1: return launch_t<1, 0, -1, -1, -1>(p, tmap, num_sms, stream);
