@@ -656,6 +656,12 @@ int launch_conv_tc(const ConvParams& p, const CUtensorMap& tmap, int num_sms, cu
       return launch_t<3, 1, 1, 9, 1, 0, 1>(p, tmap, num_sms, stream);      // RDB conv2-4 over x1..x_{k-1}
     if (p.store_mode == kStoreStaged && !p.force_generic && p.KW == 1 && p.PW == 0 && p.act == 2 && res == 0)
       return launch_t<1, 0, 2, 0, 1, 0, 1>(p, tmap, num_sms, stream);      // srcnn.conv2
+    if (p.store_mode == kStoreStaged && !p.force_generic && p.KW == 3 && p.PW == 1 && p.act == 0 && res == 4)
+      return launch_t<3, 1, 0, 4, 1, 0, 1>(p, tmap, num_sms, stream);      // dense-block input gradients of x1..x4 (gated)
+    if (p.store_mode == kStoreStaged && !p.force_generic && p.KW == 3 && p.PW == 1 && p.act == 0 && res == 5)
+      return launch_t<3, 1, 0, 5, 1, 0, 1>(p, tmap, num_sms, stream);
+    if (p.store_mode == kStoreStaged && !p.force_generic && p.KW == 1 && p.PW == 0 && p.act == 0 && res == 4)
+      return launch_t<1, 0, 0, 4, 1, 0, 1>(p, tmap, num_sms, stream);      // srcnn.conv3 input gradient over the gradient im2col
     if (p.store_mode == kStoreF32Planar && !p.force_generic && p.KW == 3 && p.PW == 1 && p.act == 0 && res == 0)
       return launch_t<3, 1, 0, 0, 3, 0, 1>(p, tmap, num_sms, stream);      // conv_last
     if (p.store_mode == kStoreF32Planar && !p.force_generic && p.KW == 5 && p.PW == 2 && p.act == 0 && res == 0)
