@@ -83,3 +83,84 @@ class HostPipeline:
                 outs.append(s.out_host)
                 s.busy = False
         return outs
+
+
+class RasterPipeline:
+    """The reference's full-raster inference loop (climsr/inference/inference.py:56-82) with everything between the raw LR
+    values and the denormalised, land-masked result on the GPU.
+
+    Per batch of ``n`` rasters the reference normalises on the CPU (dataset), uploads LR + elevation + mask, runs the model,
+    calls ``.cpu()`` (a device sync) and denormalises / NaN-masks with numpy, one raster at a time.  Here the static
+    elevation and land mask are uploaded ONCE; ``submit(raw, mins, maxes)`` (pinned host tensors) enqueues: H2D of the raw
+    rasters (4 B per LR pixel instead of 12 B per LR + 8 B per HR pixel) -> ``MinMaxScaler.normalize`` + channel concat ->
+    generator -> ``MinMaxScaler.denormalize`` + NaN mask -> D2H, on three streams with ``depth`` batches in flight, and
+    returns the PREVIOUS batch's result (pinned host tensor, valid until the next ``submit``)."""
+
+    def __init__(self, net, n: int, h: int, w: int, elev: Tensor, mask: Tensor, elev_lr: Optional[Tensor] = None,
+                 mask_lr: Optional[Tensor] = None, feature_range: Tuple[float, float] = (-1.0, 1.0), device=None, depth: int = 2):
+        from .normalization import MinMaxScaler
+        self.net = net
+        self.dev = torch.device(device) if device is not None else next(net.parameters()).device
+        self.n, self.h, self.w = n, h, w
+        H, W = 4 * h, 4 * w
+        self.scaler = MinMaxScaler(feature_range=feature_range)
+        self.mask1 = mask.reshape(1, 1, H, W).to(self.dev).float().contiguous()
+        self.elev_b = elev.reshape(1, 1, H, W).to(self.dev).float().expand(n, 1, H, W).contiguous()
+        self.mask_b = self.mask1.expand(n, 1, H, W).contiguous()
+        self.extras = [t.reshape(h, w).to(self.dev).float().contiguous() for t in (elev_lr, mask_lr) if t is not None]
+        self.slots = []
+        for _ in range(depth):
+            s = type("Slot", (), {})()
+            s.raw = torch.empty((n, h, w), dtype=torch.float32, device=self.dev)
+            s.mn = torch.empty((n,), dtype=torch.float64, device=self.dev)
+            s.mx = torch.empty((n,), dtype=torch.float64, device=self.dev)
+            s.out_host = torch.empty((n, 1, H, W), dtype=torch.float32).pin_memory()
+            s.out_dev = None
+            s.h2d_done, s.compute_done, s.d2h_done = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
+            s.busy = False
+            self.slots.append(s)
+        self.h2d = torch.cuda.Stream(device=self.dev)
+        self.d2h = torch.cuda.Stream(device=self.dev)
+        self.i = 0
+
+    def submit(self, raw: Tensor, mins: Tensor, maxes: Tensor) -> Optional[Tensor]:
+        k = len(self.slots)
+        s = self.slots[self.i % k]
+        prev = self.slots[(self.i - 1) % k] if self.i > 0 else None
+        self.i += 1
+        compute = torch.cuda.current_stream(self.dev)
+        with torch.cuda.stream(self.h2d):
+            if s.busy:
+                self.h2d.wait_event(s.compute_done)
+            s.raw.copy_(raw.reshape(self.n, self.h, self.w), non_blocking=True)
+            s.mn.copy_(mins.reshape(-1).double(), non_blocking=True)
+            s.mx.copy_(maxes.reshape(-1).double(), non_blocking=True)
+            s.h2d_done.record(self.h2d)
+        compute.wait_event(s.h2d_done)
+        with torch.no_grad():
+            x = self.scaler.normalize(s.raw, s.mn, s.mx, self.extras)
+            sr = self.net(x, self.elev_b, self.mask_b)
+            s.out_dev = self.scaler.denormalize(sr, s.mn, s.mx, self.mask1)
+        s.compute_done.record(compute)
+        with torch.cuda.stream(self.d2h):
+            self.d2h.wait_event(s.compute_done)
+            s.out_dev.record_stream(self.d2h)
+            s.out_host.copy_(s.out_dev, non_blocking=True)
+            s.d2h_done.record(self.d2h)
+        s.busy = True
+        if prev is None or prev is s or not prev.busy:
+            return None
+        prev.d2h_done.synchronize()
+        prev.busy = False
+        return prev.out_host
+
+    def drain(self) -> List[Tensor]:
+        outs = []
+        k = len(self.slots)
+        for j in range(k):
+            s = self.slots[(self.i + j) % k]
+            if s.busy:
+                s.d2h_done.synchronize()
+                outs.append(s.out_host)
+                s.busy = False
+        return outs

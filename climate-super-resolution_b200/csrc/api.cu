@@ -1746,4 +1746,26 @@ int csr_masked_metrics(const float* sr, const float* hr, const float* original, 
   return CSR_OK;
 }
 
+// ---- inference pre / post-processing ---------------------------------------------------------------------------
+int csr_minmax_normalize(const float* raw, int32_t n, int32_t h, int32_t w, const double* mn, const double* mx, double range_a, double range_b,
+                         double eps, float nan_substitution, const float* extra0, const float* extra1, float* out, void* stream) {
+  if (!raw || !mn || !mx || !out) return fail(CSR_ERR_BAD_ARG, "null pointer");
+  if (n < 1 || h < 1 || w < 1 || n > 65535) return fail(CSR_ERR_BAD_ARG, "bad shape n=%d h=%d w=%d", n, h, w);
+  if (!extra0 && extra1) return fail(CSR_ERR_BAD_ARG, "extra1 given without extra0");
+  CSR_CUDA(launch_minmax_normalize(raw, n, (long)h * w, mn, mx, range_a, range_b, eps, nan_substitution, extra0, extra1, out,
+                                   reinterpret_cast<cudaStream_t>(stream)));
+  ++g_launches;
+  return CSR_OK;
+}
+
+int csr_minmax_denormalize_mask(const float* sr, const float* mask, int32_t mask_per_sample, int32_t n, int32_t h, int32_t w, const double* mn,
+                                const double* mx, double range_a, double range_b, double eps, float* out, void* stream) {
+  if (!sr || !mask || !mn || !mx || !out) return fail(CSR_ERR_BAD_ARG, "null pointer");
+  if (n < 1 || h < 1 || w < 1 || n > 65535) return fail(CSR_ERR_BAD_ARG, "bad shape n=%d h=%d w=%d", n, h, w);
+  CSR_CUDA(launch_minmax_denormalize_mask(sr, mask, mask_per_sample ? (long)h * w : 0, n, (long)h * w, mn, mx, range_a, range_b, eps, out,
+                                          reinterpret_cast<cudaStream_t>(stream)));
+  ++g_launches;
+  return CSR_OK;
+}
+
 }  // extern "C"

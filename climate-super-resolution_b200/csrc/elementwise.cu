@@ -1,5 +1,6 @@
 // Layout / packing kernels around the conv hot path (all HBM-bound, vectorised, coalesced).
 #include "elementwise.cuh"
+#include <algorithm>
 #include "ptx.cuh"
 
 namespace csr {
@@ -442,6 +443,56 @@ cudaError_t launch_gcol_pack(const void* src, int src_C, void* dst, int dst_C, i
   if (KH == 5 && KW == 5 && dst_C == 32) gcol_pack_kernel<5, 5, 32><<<grid, 128, 0, s>>>(src, src_C, d, H, W, total_pix);
   else if (KH == 3 && KW == 3 && dst_C == 16) gcol_pack_kernel<3, 3, 16><<<grid, 128, 0, s>>>(src, src_C, d, H, W, total_pix);
   else return cudaErrorInvalidValue;
+  return cudaGetLastError();
+}
+
+// ---- min-max scaler (inference pre / post-processing) ---------------------------------------------------------
+// Pure HBM streaming: 4 B read + 4 B written per value (normalize also writes the shared elevation / mask planes into the
+// batch: 12 B written per LR pixel).  Coefficients per raster as in MinMaxScaler (normalization.py:53-55): float64.
+__global__ void minmax_normalize_kernel(const float* __restrict__ raw, long hw, const double* __restrict__ mn, const double* __restrict__ mx,
+                                        double a, double b, double eps, float nan_sub, const float* __restrict__ extra0,
+                                        const float* __restrict__ extra1, float* __restrict__ out, int n_ch) {
+  const int n = blockIdx.y;
+  const double scale = (b - a) / ((mx[n] - mn[n]) + eps);
+  const double min_ = a - mn[n] * scale;
+  const float* src = raw + static_cast<long>(n) * hw;
+  float* dst = out + static_cast<long>(n) * n_ch * hw;
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < hw; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    double v = static_cast<double>(src[i]) * scale;
+    v += min_;
+    dst[i] = (v != v) ? nan_sub : static_cast<float>(v);
+    if (extra0) dst[hw + i] = extra0[i];
+    if (extra1) dst[(extra0 ? 2 : 1) * hw + i] = extra1[i];
+  }
+}
+
+__global__ void minmax_denormalize_mask_kernel(const float* __restrict__ sr, const float* __restrict__ mask, long mask_stride, long hw,
+                                               const double* __restrict__ mn, const double* __restrict__ mx, double a, double b, double eps,
+                                               float* __restrict__ out) {
+  const int n = blockIdx.y;
+  const double scale = (b - a) / ((mx[n] - mn[n]) + eps);
+  const double min_ = a - mn[n] * scale;
+  const float* src = sr + static_cast<long>(n) * hw;
+  const float* m = mask + static_cast<long>(n) * mask_stride;
+  float* dst = out + static_cast<long>(n) * hw;
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < hw; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const double v = (static_cast<double>(src[i]) - min_) / scale;
+    dst[i] = (m[i] > 0.f) ? static_cast<float>(v) : __int_as_float(0x7fc00000);
+  }
+}
+
+cudaError_t launch_minmax_normalize(const float* raw, int n, long hw, const double* mn, const double* mx, double a, double b, double eps,
+                                    float nan_sub, const float* extra0, const float* extra1, float* out, cudaStream_t s) {
+  const int n_ch = 1 + (extra0 ? 1 : 0) + (extra1 ? 1 : 0);
+  const int bx = static_cast<int>(std::min<long>((hw + 255) / 256, 148 * 8));
+  minmax_normalize_kernel<<<dim3(bx, n), 256, 0, s>>>(raw, hw, mn, mx, a, b, eps, nan_sub, extra0, extra1, out, n_ch);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_minmax_denormalize_mask(const float* sr, const float* mask, long mask_stride, int n, long hw, const double* mn,
+                                           const double* mx, double a, double b, double eps, float* out, cudaStream_t s) {
+  const int bx = static_cast<int>(std::min<long>((hw + 255) / 256, 148 * 8));
+  minmax_denormalize_mask_kernel<<<dim3(bx, n), 256, 0, s>>>(sr, mask, mask_stride, hw, mn, mx, a, b, eps, out);
   return cudaGetLastError();
 }
 

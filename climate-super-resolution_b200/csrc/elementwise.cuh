@@ -28,4 +28,11 @@ cudaError_t launch_bias_grad(const void* g, long npix, int C, int coff, int cout
 cudaError_t launch_bias_grad_planar(const float* g, long n, float scale, float* db, cudaStream_t s);
 cudaError_t launch_scale_copy64(const void* src, int src_C, void* dst, int dst_C, long npix, float scale, cudaStream_t s);
 cudaError_t launch_gcol_pack(const void* src, int src_C, void* dst, int dst_C, int H, int W, long total_pix, int KH, int KW, cudaStream_t s);
+// Min-max scaler around the inference hot path (normalization.py:37-84): float64 arithmetic, one rounding to float32.
+// normalize: out[n][0] = nan_to(raw[n] * scale_n + min__n); channels 1.. = the shared (h,w) planes extra0 / extra1.
+cudaError_t launch_minmax_normalize(const float* raw, int n, long hw, const double* mn, const double* mx, double a, double b, double eps,
+                                    float nan_sub, const float* extra0, const float* extra1, float* out, cudaStream_t s);
+// denormalize + land mask: out = mask > 0 ? (sr - min__n) / scale_n : NaN.  mask_stride = 0 (one shared mask) or hw.
+cudaError_t launch_minmax_denormalize_mask(const float* sr, const float* mask, long mask_stride, int n, long hw, const double* mn,
+                                           const double* mx, double a, double b, double eps, float* out, cudaStream_t s);
 }  // namespace csr

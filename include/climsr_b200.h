@@ -214,6 +214,24 @@ int     csr_masked_metrics(const float* sr, const float* hr, const float* origin
                            float range_a, float range_b, int32_t n, int32_t h, int32_t w,
                            float* out, void* scratch, size_t scratch_bytes, void* stream);
 
+/* ---- inference pre / post-processing on device -------------------------------------------
+ * The reference normalises each LR raster on the CPU (MinMaxScaler._normalize, climsr/data/normalization.py:37-61, called
+ * from geo_tiff_inference_dataset.py:161-166), concatenates [raster, elevation_lr, mask_lr] (:101-121), and after the
+ * forward pulls the result to the host, denormalises it with the raster's min / max (normalization.py:63-84) and writes
+ * NaN outside the land mask (climsr/inference/inference.py:73-76).  Both run here as one HBM pass each, float64
+ * arithmetic with a single rounding to float32.
+ *   raw (n,h,w) fp32 with NaN for missing values; mn, mx: n DEVICE doubles; (a, b) = feature range; eps as the scaler's.
+ *   extra0 / extra1: NULL or shared (h,w) fp32 planes appended as channels 1 (, 2) of every sample.
+ *   out: (n, 1 + number of extras, h, w) fp32 NCHW = the generator's `x`.                                               */
+int     csr_minmax_normalize(const float* raw, int32_t n, int32_t h, int32_t w, const double* mn, const double* mx,
+                             double range_a, double range_b, double eps, float nan_substitution,
+                             const float* extra0, const float* extra1, float* out, void* stream);
+/*   sr (n,1,h,w) fp32 generator output; mask fp32, (1,1,h,w) shared (mask_per_sample = 0) or (n,1,h,w);
+ *   out (n,1,h,w) fp32 = (sr - min_) / scale where mask > 0, NaN elsewhere.                                              */
+int     csr_minmax_denormalize_mask(const float* sr, const float* mask, int32_t mask_per_sample, int32_t n, int32_t h, int32_t w,
+                                    const double* mn, const double* mx, double range_a, double range_b, double eps,
+                                    float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -17,6 +17,7 @@ Fixtures
                           loaded through load_state_dict(strict=True): inputs are re-derivable from seeds, only
                           the output (and its gain=4 "trained-like" variant) is stored.
   gen_default_seeded.npz- class default (nb=23, gc=32, in=4), same recipe, smaller raster.
+  normalization.npz     - the reference's MinMaxScaler.normalize / .denormalize (+ NaN land mask) on seeded rasters.
 """
 from __future__ import annotations
 
@@ -97,10 +98,40 @@ def seeded(name, in_ch, nb, gc, n, h, w):
 GAINS = {16: (1.0, 1.5, 1.8), 32: (1.0, 1.25, 1.4)}
 
 
+def normalization():
+    """tests/golden/normalization.npz: the reference's MinMaxScaler (climsr/data/normalization.py, imported unmodified) on
+    seeded rasters with NaNs: normalize(arr, min, max) and denormalize(arr, min, max) + the NaN land mask of inference.py:75."""
+    from climsr.data.normalization import MinMaxScaler
+    rng = np.random.default_rng(12)
+    n, h, w = 3, 19, 23
+    raw = rng.uniform(-40.0, 45.0, size=(n, h, w)).astype(np.float32)
+    raw[rng.uniform(size=raw.shape) < 0.2] = np.nan                        # sea pixels of the LR raster
+    mins = np.array([-52.25, -38.5, -61.125], dtype=np.float64)            # pandas float64 columns in the reference
+    maxes = np.array([41.5, 47.75, 36.0], dtype=np.float64)
+    sc = MinMaxScaler(feature_range=(-1.0, 1.0))
+    norm = np.stack([sc.normalize(raw[i], mins[i], maxes[i]) for i in range(n)])
+    sr = rng.uniform(-1.1, 1.1, size=(n, 1, 4 * h, 4 * w)).astype(np.float32)
+    mask = rng.uniform(size=(1, 1, 4 * h, 4 * w)) > 0.3
+    post = np.empty_like(sr)
+    for i in range(n):
+        arr = sc.denormalize(sr[i, 0], mins[i], maxes[i])
+        arr[~mask[0, 0]] = np.nan                                          # inference.py:75
+        post[i, 0] = arr.astype(np.float32)
+    sc01 = MinMaxScaler()                                                  # default feature_range (0, 1)
+    norm01 = sc01.normalize(raw[0], mins[0], maxes[0])
+    np.savez_compressed(os.path.join(OUT, "normalization.npz"), raw=raw, mins=mins, maxes=maxes, norm=norm, sr=sr,
+                        mask=mask.astype(np.uint8), post=post, norm01=norm01, numpy_version=np.array(np.__version__))
+    print("normalization.npz written")
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
+    if "--normalization-only" in sys.argv:
+        normalization()
+        sys.exit(0)
     tiny_refinit()
+    normalization()
     if "--tiny-only" not in sys.argv:
         seeded("gen_hydra_seeded", 4, 11, 16, 2, 16, 16)
         seeded("gen_default_seeded", 4, 23, 32, 1, 12, 12)

@@ -398,3 +398,72 @@ def test_host_pipeline_matches_direct_calls():
     with torch.no_grad():
         for (x, e, m), o in zip(batches, got):
             assert torch.equal(net(x.cuda(), e.cuda(), m.cuda()).cpu(), o)
+
+
+def test_minmax_scaler_kernels_match_reference_golden(golden_dir):
+    """csr_minmax_normalize / csr_minmax_denormalize_mask against the reference's MinMaxScaler outputs (bit-exact: float64
+    arithmetic, one rounding) - normalization.py:37-84, inference.py:73-76."""
+    from climsr_b200.normalization import MinMaxScaler
+    g = np.load(os.path.join(golden_dir, "normalization.npz"))
+    sc = MinMaxScaler(feature_range=(-1.0, 1.0))
+    raw = torch.from_numpy(g["raw"]).cuda()
+    h, w = raw.shape[1:]
+    elev_lr = torch.rand((h, w)) * 2 - 1
+    mask_lr = (torch.rand((h, w)) > 0.3).float()
+    x = sc.normalize(raw, g["mins"], g["maxes"], [elev_lr, mask_lr]).cpu()
+    assert x.shape == (raw.shape[0], 3, h, w)
+    assert np.array_equal(x[:, 0].numpy(), g["norm"])
+    assert torch.equal(x[:, 1], elev_lr.expand(raw.shape[0], h, w)) and torch.equal(x[:, 2], mask_lr.expand(raw.shape[0], h, w))
+    assert np.array_equal(MinMaxScaler().normalize(raw[:1], g["mins"][:1], g["maxes"][:1]).cpu().numpy()[0, 0], g["norm01"])
+    sr = torch.from_numpy(g["sr"]).cuda()
+    mask = torch.from_numpy(g["mask"].astype(np.float32)).cuda()
+    post = sc.denormalize(sr, g["mins"], g["maxes"], mask).cpu().numpy()
+    assert np.array_equal(post, g["post"], equal_nan=True)
+    post_n = sc.denormalize(sr, g["mins"], g["maxes"], mask.expand(sr.shape[0], 1, -1, -1).contiguous()).cpu().numpy()
+    assert np.array_equal(post_n, g["post"], equal_nan=True)
+    with pytest.raises(ValueError):
+        sc.normalize(raw, g["mins"][:2], g["maxes"])
+
+
+def test_raster_pipeline_matches_oracle_chain():
+    """Raw LR rasters -> normalise -> generator -> denormalise -> NaN mask, all on device with overlapped copies
+    (RasterPipeline), against the oracle chain (oracle.normalization + oracle.generator) - inference.py:56-82."""
+    from climsr_b200.models import ESRGANGenerator
+    from climsr_b200.pipeline import RasterPipeline
+    from oracle import generator as og
+    from oracle import normalization as on
+    from oracle import synth
+    n, h, w = 2, 12, 20
+    sd = synth.make_state_dict(3, 1, 64, 1, 16, seed=9)
+    net = ESRGANGenerator(3, 1, 64, 1, 16)
+    net.load_state_dict(sd)
+    net = net.cuda().eval()
+    rng = np.random.default_rng(4)
+    mask = (rng.uniform(size=(1, 1, 4 * h, 4 * w)) > 0.3).astype(np.float32)
+    elev = (rng.uniform(-1, 1, size=(1, 1, 4 * h, 4 * w)).astype(np.float32)) * mask
+    elev_lr, mask_lr = elev[0, 0, ::4, ::4].copy(), mask[0, 0, ::4, ::4].copy()
+    pipe = RasterPipeline(net, n, h, w, torch.from_numpy(elev), torch.from_numpy(mask), torch.from_numpy(elev_lr), torch.from_numpy(mask_lr))
+    batches, outs = [], []
+    for b in range(3):
+        raw = rng.uniform(-30, 40, size=(n, h, w)).astype(np.float32)
+        raw[np.broadcast_to(mask_lr == 0, raw.shape)] = np.nan
+        mins = np.array([-45.5 - b, -50.25], dtype=np.float64)
+        maxes = np.array([44.0, 47.5 + b], dtype=np.float64)
+        batches.append((raw, mins, maxes))
+        r = pipe.submit(torch.from_numpy(raw).pin_memory(), torch.from_numpy(mins).pin_memory(), torch.from_numpy(maxes).pin_memory())
+        if r is not None:
+            outs.append(r.clone())
+    outs += [o.clone() for o in pipe.drain()]
+    assert len(outs) == 3
+    for (raw, mins, maxes), got in zip(batches, outs):
+        x = on.lr_input(raw, mins, maxes, elev_lr, mask_lr)
+        e = np.broadcast_to(elev, (n, 1, 4 * h, 4 * w)).copy()
+        m = np.broadcast_to(mask, (n, 1, 4 * h, 4 * w)).copy()
+        sr = og.generator_forward(sd, torch.from_numpy(x), torch.from_numpy(e), torch.from_numpy(m)).numpy()
+        want = on.postprocess(sr, mask, mins, maxes)
+        got = got.numpy()
+        assert np.array_equal(np.isnan(got), np.isnan(want))
+        land = ~np.isnan(want)
+        # 1e-2 in normalised units (bf16 path) = 1e-2 * (max - min) / 2 in physical units
+        tol = 1e-2 * (maxes - mins).max() / 2
+        assert np.abs(got[land] - want[land]).max() <= tol

@@ -115,3 +115,24 @@ def test_val_step_properties():
     # denominators are numel, not land count
     d = (om.minmax_denormalize(sr.double(), t["min"].double(), t["max"].double()) - orig.double()).abs() * mask
     assert float(out["mae"]) == pytest.approx(float(d.sum() / d.numel()), rel=1e-9)
+
+
+def test_minmax_scaler_restatement_matches_reference_golden(golden_dir):
+    """oracle/normalization.py against the reference's own MinMaxScaler (climsr/data/normalization.py:37-84, run unmodified
+    by oracle/make_golden.py): normalize with NaN substitution, denormalize + NaN land mask (inference.py:73-76)."""
+    from oracle import normalization as on
+    g = _load(golden_dir, "normalization.npz")
+    n = g["raw"].shape[0]
+    norm = np.stack([on.normalize(g["raw"][i], g["mins"][i], g["maxes"][i]) for i in range(n)])
+    assert np.array_equal(norm, g["norm"])
+    assert not np.isnan(norm).any() and np.isnan(g["raw"]).any()
+    assert np.array_equal(on.normalize(g["raw"][0], g["mins"][0], g["maxes"][0], (0.0, 1.0)), g["norm01"])
+    post = on.postprocess(g["sr"], g["mask"], g["mins"], g["maxes"])
+    assert np.array_equal(post, g["post"], equal_nan=True)
+    assert np.array_equal(np.isnan(post[:, 0]), np.broadcast_to(g["mask"][0, 0] == 0, post[:, 0].shape))
+    # round trip: denormalize(normalize(x)) == x on valid pixels (float32 rounding only)
+    valid = ~np.isnan(g["raw"][1])
+    back = on.denormalize(norm[1], g["mins"][1], g["maxes"][1])
+    assert np.abs(back[valid] - g["raw"][1][valid]).max() <= 1e-4
+    x = on.lr_input(g["raw"], g["mins"], g["maxes"], np.ones(g["raw"].shape[1:], np.float32), None)
+    assert x.shape == (n, 2) + g["raw"].shape[1:] and np.array_equal(x[:, 0], norm)

@@ -82,6 +82,41 @@ def main():
             out["cfg5_48_rasters_with_metrics"] = {"ms": ms, "rasters_per_s": 48 / ms * 1e3, "hr_mpx_s": px / ms / 1e3, "metrics_ms": ms_metrics,
                                                    "metrics_gb_s": px * 28 / ms_metrics / 1e6,
                                                    "metrics_bytes_per_px": "16 (sr,hr,original,mask fp32, pass 1) + 12 (sr,hr,mask, SSIM pass)"}
+            # the reference's inference loop over monthly rasters, host to host: raw LR values in, denormalised land-masked
+            # rasters out (RasterPipeline: static elevation / mask resident, normalise + denormalise on device, copies overlapped)
+            from climsr_b200.pipeline import HostPipeline, RasterPipeline
+            import time
+            nb_, reps = 48, 6
+            raw = (torch.rand((nb_, 113, 113)) * 70 - 35).pin_memory()
+            mins = torch.full((nb_,), -40.0, dtype=torch.float64).pin_memory()
+            maxes = torch.full((nb_,), 35.0, dtype=torch.float64).pin_memory()
+            rp = RasterPipeline(net3, nb_, 113, 113, e[:1].cpu(), m[:1].cpu(), x[0, 1].cpu(), x[0, 2].cpu())
+            for _ in range(2):
+                rp.submit(raw, mins, maxes)
+            rp.drain()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                rp.submit(raw, mins, maxes)
+            rp.drain()
+            ms_rp = (time.perf_counter() - t0) / reps * 1e3
+            hp = HostPipeline(net3, (nb_, 3, 113, 113))
+            xh, eh, mh = x.cpu().pin_memory(), e.cpu().pin_memory(), m.cpu().pin_memory()
+            for _ in range(2):
+                hp.submit(xh, eh, mh)
+            hp.drain()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                hp.submit(xh, eh, mh)
+            hp.drain()
+            ms_hp = (time.perf_counter() - t0) / reps * 1e3
+            out["cfg5_raster_pipeline_host_to_host"] = {
+                "ms_per_48_rasters": ms_rp, "rasters_per_s": nb_ / ms_rp * 1e3, "hr_mpx_s": px / ms_rp / 1e3,
+                "h2d_bytes": nb_ * 113 * 113 * 4 + 2 * nb_ * 8, "d2h_bytes": px * 4,
+                "same_through_HostPipeline_ms": ms_hp, "HostPipeline_h2d_bytes": nb_ * 3 * 113 * 113 * 4 + 2 * px * 4,
+                "note": "wall clock over 6 batches, 2 in flight; HostPipeline re-uploads elevation + mask per batch like the reference and "
+                        "returns normalised values (denormalise + NaN mask would follow on the host)"}
         # global grid as row bands: rank r takes bands r, r+world, ...
         x, e, m = inputs(1, 3, 360, 720, dev)
         bands = max(8, world)
