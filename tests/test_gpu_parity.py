@@ -150,6 +150,42 @@ def test_conv_cta_pair_matches_single_cta():
     assert float((outs[1][0].float().cpu().permute(0, 3, 1, 2) - want).abs().max()) <= 2.0 ** -7 * max(1.0, float(want.abs().max()))
 
 
+@pytest.mark.parametrize("n,h,w,cin,cout,k,in_c,in_coff", [
+    (2, 5, 33, 64, 16, 3, 128, 0),      # second M tile of the window mostly below the image
+    (1, 12, 61, 112, 16, 3, 128, 0),    # one and a half windows, two k-blocks
+    (3, 24, 24, 16, 16, 3, 128, 64),    # 16 input channels at an offset: 32-byte window rows
+    (1, 17, 40, 32, 32, 3, 64, 0),      # 32 input channels: 64-byte rows; N = 96 -> four accumulators
+    (1, 40, 40, 64, 32, 1, 64, 0),      # 1x1 (srcnn.conv2 shape)
+    (1, 21, 19, 32, 1, 5, 64, 0),       # srcnn.conv3 shape -> bf16 path here (fp32 planar is covered by the generator tests)
+])
+def test_thin_layer_variants_are_bit_identical(n, h, w, cin, cout, k, in_c, in_coff):
+    """Two-tile windows (option 18), eight accumulator buffers (19) and narrow window boxes (17) only change how tiles are
+    scheduled and how many bytes are moved: every combination must give the SAME bits as the plain kernel, and those must
+    match the fp32 reference conv."""
+    from climsr_b200 import ops
+    from climsr_b200._lib import lib
+    g = torch.Generator().manual_seed(100 + h + w)
+    x = torch.rand((n, in_c, h, w), generator=g) * 2 - 1
+    wt = (torch.rand((cout, cin, k, k), generator=g) * 2 - 1) / (3 * k * cin ** 0.5)
+    b = torch.rand((cout,), generator=g) - 0.5
+    xin = _nhwc(x, in_c)
+    outs = []
+    try:
+        for tall, acc8, narrow in ((0, 0, 0), (1, 0, 0), (1, 1, 0), (1, 1, 1), (0, 0, 1)):
+            lib.csr_set_option(18, tall)
+            lib.csr_set_option(19, acc8)
+            lib.csr_set_option(17, narrow)
+            outs.append(ops.conv2d_nhwc(xin, wt.cuda(), b.cuda(), act="lrelu", in_coff=in_coff))
+    finally:
+        for key in (17, 18, 19):
+            lib.csr_set_option(key, 1)
+    for o in outs[1:]:
+        assert torch.equal(o, outs[0])
+    want = _ref_conv(x[:, in_coff:in_coff + cin], wt, b, "lrelu")
+    got = outs[0][..., :cout].float().cpu().permute(0, 3, 1, 2)
+    assert float((got - want).abs().max()) <= 2.0 ** -7 * max(1.0, float(want.abs().max()))
+
+
 def test_conv_transposed_and_gate():
     """Input-gradient conv (transposed/flipped weights) with in-place accumulate and LeakyReLU-derivative gate: the building
     block of the dense-block backward (autograd of esrgan.py:33-38)."""
