@@ -1768,4 +1768,19 @@ int csr_minmax_denormalize_mask(const float* sr, const float* mask, int32_t mask
   return CSR_OK;
 }
 
+// ---- training-sample assembly ------------------------------------------------------------------------------------
+int csr_lr_input_from_hr(const float* hr, const float* elev, const float* mask, int32_t n, int32_t H, int32_t W, int32_t scale,
+                         const int32_t* codes, float* hr_out, float* elev_out, float* mask_out, float* x_out, void* stream) {
+  if (!hr || !elev || !mask || !x_out) return fail(CSR_ERR_BAD_ARG, "null pointer");
+  if (n < 1 || n > 65535 || H < 1 || W < 1 || scale < 1 || H % scale || W % scale)
+    return fail(CSR_ERR_BAD_ARG, "bad shape n=%d H=%d W=%d scale=%d (H and W must be multiples of scale)", n, H, W, scale);
+  const int outs = (hr_out ? 1 : 0) + (elev_out ? 1 : 0) + (mask_out ? 1 : 0);
+  if (outs != 0 && outs != 3) return fail(CSR_ERR_BAD_ARG, "hr_out, elev_out and mask_out must all be given or all be null");
+  if (codes && outs == 0) return fail(CSR_ERR_BAD_ARG, "augmentation codes need the augmented output tensors");
+  // (odd rot90 factors on non-square tiles are a caller error the kernel cannot see on the host: codes live on the device)
+  CSR_CUDA(launch_lr_input(hr, elev, mask, n, H, W, scale, codes, hr_out, elev_out, mask_out, x_out, reinterpret_cast<cudaStream_t>(stream)));
+  ++g_launches;
+  return CSR_OK;
+}
+
 }  // extern "C"

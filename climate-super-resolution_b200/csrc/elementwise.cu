@@ -496,4 +496,48 @@ cudaError_t launch_minmax_denormalize_mask(const float* sr, const float* mask, l
   return cudaGetLastError();
 }
 
+// ---- training-sample assembly -----------------------------------------------------------------------------------
+// Index work only (bit-exact).  One thread per OUTPUT HR pixel (i,j): source pixel under rot90^-1, then the flips undone;
+// every scale-th pixel in both directions also goes to the LR input x.  12 B read + 12 B written per HR pixel.
+__global__ void lr_input_kernel(const float* __restrict__ hr, const float* __restrict__ elev, const float* __restrict__ mask, int H, int W,
+                                int scale, const int* __restrict__ codes, float* __restrict__ hr_out, float* __restrict__ elev_out,
+                                float* __restrict__ mask_out, float* __restrict__ x_out) {
+  const int n = blockIdx.y;
+  const int code = codes ? codes[n] : 0;
+  const bool vf = code & 1, hf = code & 2;
+  const int k = (code >> 2) & 3;
+  const long hw = static_cast<long>(H) * W;
+  const int h = H / scale, w = W / scale;
+  const float* a = hr + n * hw;
+  const float* e = elev + n * hw;
+  const float* m = mask + n * hw;
+  for (long p = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; p < hw; p += static_cast<long>(gridDim.x) * blockDim.x) {
+    const int i = static_cast<int>(p / W), j = static_cast<int>(p - static_cast<long>(i) * W);
+    // np.rot90(m, k)[i][j] = m[i1][j1]  (square tiles when k is odd)
+    int i1 = i, j1 = j;
+    if (k == 1) { i1 = j; j1 = W - 1 - i; }
+    else if (k == 2) { i1 = H - 1 - i; j1 = W - 1 - j; }
+    else if (k == 3) { i1 = H - 1 - j; j1 = i; }
+    if (hf) j1 = W - 1 - j1;
+    if (vf) i1 = H - 1 - i1;
+    const long q = static_cast<long>(i1) * W + j1;
+    const float va = a[q], ve = e[q], vm = m[q];
+    if (hr_out) { hr_out[n * hw + p] = va; elev_out[n * hw + p] = ve; mask_out[n * hw + p] = vm; }
+    if (i % scale == 0 && j % scale == 0 && i / scale < h && j / scale < w) {
+      const long o = (static_cast<long>(n) * 3 * h + i / scale) * w + j / scale;
+      x_out[o] = va;
+      x_out[o + static_cast<long>(h) * w] = ve;
+      x_out[o + 2L * h * w] = vm;
+    }
+  }
+}
+
+cudaError_t launch_lr_input(const float* hr, const float* elev, const float* mask, int n, int H, int W, int scale, const int* codes,
+                            float* hr_out, float* elev_out, float* mask_out, float* x_out, cudaStream_t s) {
+  const long hw = static_cast<long>(H) * W;
+  const int bx = static_cast<int>(std::min<long>((hw + 255) / 256, 148 * 8));
+  lr_input_kernel<<<dim3(bx, n), 256, 0, s>>>(hr, elev, mask, H, W, scale, codes, hr_out, elev_out, mask_out, x_out);
+  return cudaGetLastError();
+}
+
 }  // namespace csr

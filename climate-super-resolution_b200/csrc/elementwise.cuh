@@ -35,4 +35,9 @@ cudaError_t launch_minmax_normalize(const float* raw, int n, long hw, const doub
 // denormalize + land mask: out = mask > 0 ? (sr - min__n) / scale_n : NaN.  mask_stride = 0 (one shared mask) or hw.
 cudaError_t launch_minmax_denormalize_mask(const float* sr, const float* mask, long mask_stride, int n, long hw, const double* mn,
                                            const double* mx, double a, double b, double eps, float* out, cudaStream_t s);
+// Training-sample assembly (climate_dataset.py:98-172): per-sample flip / rot90 of hr, elev, mask and x = [lr, elev_lr, mask_lr]
+// with lr = nearest resize by `scale` (top-left pixel of each block).  codes: n device ints (bit0 v-flip, bit1 h-flip,
+// bits 2-3 rot90 factor) or NULL; *_out may be NULL when codes is NULL.
+cudaError_t launch_lr_input(const float* hr, const float* elev, const float* mask, int n, int H, int W, int scale, const int* codes,
+                            float* hr_out, float* elev_out, float* mask_out, float* x_out, cudaStream_t s);
 }  // namespace csr

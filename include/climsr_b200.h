@@ -232,6 +232,18 @@ int     csr_minmax_denormalize_mask(const float* sr, const float* mask, int32_t 
                                     const double* mn, const double* mx, double range_a, double range_b, double eps,
                                     float* out, void* stream);
 
+/* ---- training-sample assembly on device ---------------------------------------------------
+ * The reference builds every sample on the CPU (climsr/data/sr/climate_dataset.py): random np.flipud / np.fliplr /
+ * np.rot90(k) of the HR tile, its elevation and its land mask (:152-170), LR = albumentations Resize = cv2 INTER_NEAREST by
+ * 1/scale (:84-92,172: the top-left pixel of every scale x scale block), elevation_lr and mask_lr the same way (:118,136),
+ * x = cat[lr, elevation_lr, mask_lr] (:98-121).  One pass here; index work only, bit-exact.
+ *   hr, elev, mask (n,1,H,W) fp32; H, W multiples of scale; codes: n DEVICE int32 (bit0 vertical flip, bit1 horizontal
+ *   flip, bits 2-3 rot90 factor; applied in that order; odd factors need H == W) or NULL (no augmentation).
+ *   hr_out / elev_out / mask_out (n,1,H,W): the augmented tensors (all three or none; may be NULL when codes is NULL).
+ *   x_out (n,3,H/scale,W/scale) = the generator's input.                                                                */
+int     csr_lr_input_from_hr(const float* hr, const float* elev, const float* mask, int32_t n, int32_t H, int32_t W, int32_t scale,
+                             const int32_t* codes, float* hr_out, float* elev_out, float* mask_out, float* x_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

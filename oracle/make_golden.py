@@ -18,6 +18,7 @@ Fixtures
                           the output (and its gain=4 "trained-like" variant) is stored.
   gen_default_seeded.npz- class default (nb=23, gc=32, in=4), same recipe, smaller raster.
   normalization.npz     - the reference's MinMaxScaler.normalize / .denormalize (+ NaN land mask) on seeded rasters.
+  lr_input.npz          - numpy flips / rot90 + cv2 INTER_NEAREST resize (the arithmetic behind climate_dataset.py:152-172).
 """
 from __future__ import annotations
 
@@ -124,14 +125,51 @@ def normalization():
     print("normalization.npz written")
 
 
+def lr_input():
+    """tests/golden/lr_input.npz: numpy flips / rot90 (climate_dataset.py:152-170) and cv2.resize INTER_NEAREST - what
+    albumentations' A.Resize calls (climate_dataset.py:84-92,172) - on seeded square tiles, all 16 augmentation codes."""
+    import cv2
+    rng = np.random.default_rng(21)
+    S, s = 24, 4
+    codes = np.arange(16, dtype=np.int32)
+    n = len(codes)
+    hr = rng.uniform(-1, 1, size=(n, 1, S, S)).astype(np.float32)
+    elev = rng.uniform(-1, 1, size=(n, 1, S, S)).astype(np.float32)
+    mask = (rng.uniform(size=(n, 1, S, S)) > 0.3).astype(np.float32)
+    xs, hrs, els, mks = [], [], [], []
+    for i, c in enumerate(codes):
+        a, e, m = hr[i, 0], elev[i, 0], mask[i, 0]
+        if c & 1:
+            a, e, m = np.flipud(a), np.flipud(e), np.flipud(m)
+        if c & 2:
+            a, e, m = np.fliplr(a), np.fliplr(e), np.fliplr(m)
+        k = (c >> 2) & 3
+        if k:
+            a, e, m = np.rot90(a, k), np.rot90(e, k), np.rot90(m, k)
+        a, e, m = (np.ascontiguousarray(t) for t in (a, e, m))
+        rs = lambda t: cv2.resize(t, (S // s, S // s), interpolation=cv2.INTER_NEAREST)  # noqa: E731
+        xs.append(np.stack([rs(a), rs(e), rs(m.astype(np.float32))]))
+        hrs.append(a); els.append(e); mks.append(m)
+    # a non-square, un-augmented case (Europe-extent validation rasters are not square)
+    r = rng.uniform(-1, 1, size=(20, 36)).astype(np.float32)
+    np.savez_compressed(os.path.join(OUT, "lr_input.npz"), hr=hr, elev=elev, mask=mask, codes=codes, x=np.stack(xs),
+                        hr_aug=np.stack(hrs)[:, None], elev_aug=np.stack(els)[:, None], mask_aug=np.stack(mks)[:, None],
+                        rect=r, rect_lr=cv2.resize(r, (9, 5), interpolation=cv2.INTER_NEAREST), cv2_version=np.array(cv2.__version__))
+    print("lr_input.npz written")
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
     if "--normalization-only" in sys.argv:
         normalization()
         sys.exit(0)
+    if "--lr-input-only" in sys.argv:
+        lr_input()
+        sys.exit(0)
     tiny_refinit()
     normalization()
+    lr_input()
     if "--tiny-only" not in sys.argv:
         seeded("gen_hydra_seeded", 4, 11, 16, 2, 16, 16)
         seeded("gen_default_seeded", 4, 23, 32, 1, 12, 12)

@@ -503,3 +503,35 @@ def test_raster_pipeline_matches_oracle_chain():
         # 1e-2 in normalised units (bf16 path) = 1e-2 * (max - min) / 2 in physical units
         tol = 1e-2 * (maxes - mins).max() / 2
         assert np.abs(got[land] - want[land]).max() <= tol
+
+
+def test_lr_input_kernel_matches_numpy_cv2_golden(golden_dir):
+    """csr_lr_input_from_hr against numpy flips / rot90 + cv2 INTER_NEAREST resize (climate_dataset.py:98-172): all 16
+    augmentation codes, bit-exact; un-augmented non-square rasters; a full-size batch against the oracle."""
+    from climsr_b200.data import aug_code, make_lr_batch, random_aug_codes
+    from oracle import lr_input as ol
+    g = np.load(os.path.join(golden_dir, "lr_input.npz"))
+    hr, elev, mask = (torch.from_numpy(g[k]).cuda() for k in ("hr", "elev", "mask"))
+    x, hr2, el2, mk2 = make_lr_batch(hr, elev, mask, torch.from_numpy(g["codes"]))
+    assert np.array_equal(x.cpu().numpy(), g["x"])
+    assert np.array_equal(hr2.cpu().numpy(), g["hr_aug"]) and np.array_equal(el2.cpu().numpy(), g["elev_aug"])
+    assert np.array_equal(mk2.cpu().numpy(), g["mask_aug"])
+    assert aug_code(True, False, 3) == 13
+    # no augmentation, non-square raster
+    r = torch.from_numpy(g["rect"])[None, None].cuda()
+    x0, a0, _, _ = make_lr_batch(r, r * 0.5, (r > 0).float())
+    assert np.array_equal(x0[0, 0].cpu().numpy(), g["rect_lr"]) and torch.equal(x0[0, 1], x0[0, 0] * 0.5) and a0.data_ptr() == r.data_ptr()
+    with pytest.raises(ValueError):
+        make_lr_batch(r, r, r, torch.tensor([4]))             # rot90 by 1 on a 20x36 raster
+    # training-size batch (cfg3: 16 x 128x128) with drawn codes, against the oracle
+    gen = torch.Generator().manual_seed(8)
+    n, S = 16, 128
+    hr = torch.rand((n, 1, S, S), generator=gen) * 2 - 1
+    elev = torch.rand((n, 1, S, S), generator=gen) * 2 - 1
+    mask = (torch.rand((n, 1, S, S), generator=gen) > 0.3).float()
+    codes = random_aug_codes(n, gen)
+    assert int(codes.max()) <= 15 and len(set(codes.tolist())) > 4
+    got = make_lr_batch(hr.cuda(), elev.cuda(), mask.cuda(), codes)
+    want = ol.training_batch(hr.numpy(), elev.numpy(), mask.numpy(), codes.numpy())
+    for a, b in zip(got, want):
+        assert np.array_equal(a.cpu().numpy(), b)

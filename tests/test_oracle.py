@@ -136,3 +136,19 @@ def test_minmax_scaler_restatement_matches_reference_golden(golden_dir):
     assert np.abs(back[valid] - g["raw"][1][valid]).max() <= 1e-4
     x = on.lr_input(g["raw"], g["mins"], g["maxes"], np.ones(g["raw"].shape[1:], np.float32), None)
     assert x.shape == (n, 2) + g["raw"].shape[1:] and np.array_equal(x[:, 0], norm)
+
+
+def test_lr_input_restatement_matches_numpy_cv2_golden(golden_dir):
+    """oracle/lr_input.py against numpy flips / rot90 + cv2.resize INTER_NEAREST (the arithmetic behind
+    climate_dataset.py:152-172, run by oracle/make_golden.py): all 16 augmentation codes, exact."""
+    from oracle import lr_input as ol
+    g = _load(golden_dir, "lr_input.npz")
+    x, hr, el, mk = ol.training_batch(g["hr"], g["elev"], g["mask"], g["codes"])
+    assert np.array_equal(x, g["x"]) and np.array_equal(hr, g["hr_aug"]) and np.array_equal(el, g["elev_aug"]) and np.array_equal(mk, g["mask_aug"])
+    assert np.array_equal(ol.resize_nearest(g["rect"]), g["rect_lr"])
+    x0, hr0, _, _ = ol.training_batch(g["hr"], g["elev"], g["mask"], None)
+    assert np.array_equal(hr0, g["hr"]) and np.array_equal(x0[:, 0], g["hr"][:, 0, ::4, ::4])
+    # the four rotations compose to the identity; two flips cancel
+    a = g["hr"][3, 0]
+    assert np.array_equal(ol.augment(ol.augment(a, False, False, 1), False, False, 3), a)
+    assert np.array_equal(ol.augment(ol.augment(a, True, True, 0), True, True, 0), a)
