@@ -33,6 +33,7 @@ static int g_opt_one_mma = 0;
 static int g_opt_graphs = 1;
 static int g_opt_graph_max_px = 1 << 21;   // forward: replay a CUDA graph up to this many HR pixels per call (larger batches are GPU-bound)
 static int g_opt_issue_order = 1;       // MMA warps take strict turns tile by tile: 0 never, 1 in CTA-pair launches, 2 in every launch
+static int g_opt_wgrad_atomic = 1;      // weight-gradient partial sums through red.global.add.v4.f32 instead of per-CTA slices + reduce kernel
 static int g_opt_eight_acc = 1;         // eight accumulator buffers for two-tile windows when TMEM has room (KW*npad <= 64)
 static int g_opt_tall = 1;              // two M tiles per window for thin layers
 static int g_opt_narrow_box = 1;        // 16- / 32-channel window boxes for layers over <= 16 / 32 input channels
@@ -533,12 +534,17 @@ static int run_wgrad_layer(const WgradLayer& L, int N, int H, int W, const void*
     const int pw = L.up2 ? 1 - (phase & 1) : (L.fold ? 0 : L.kw / 2);
     for (int ci0 = 0; ci0 < ecin; ci0 += 128) {
       int n_parts = 0;
+      if (g_opt_wgrad_atomic) {
+        CSR_CUDA(cudaMemsetAsync(scratch, 0, (size_t)part_stride * sizeof(float), s));
+        ++*launches;
+      }
       for (int dy = 0; dy < ekh; dy += per) {
         WgradLaunch wl;
         int rc = build_wgrad(sms, N, H, W, ekw, pw, dy - ph, std::min(per, ekh - dy), x, x_C, x_coff + ci0, g, g_C, g_coff, nullptr, 0, 0, ld_n,
                              scratch + (size_t)dy * ekw * 128 * ld_n, part_stride, ld_n, &wl);
         n_parts = wl.p.n_parts;
         if (rc) return rc;
+        wl.p.atomic = g_opt_wgrad_atomic;
         if (phase >= 0) {
           rc = encode_phase_map(&wl.tg0, g, N, H, W, g_C, phase, wl.p.SW, wl.p.TH);
           if (rc) return rc;
@@ -548,9 +554,12 @@ static int run_wgrad_layer(const WgradLayer& L, int N, int H, int W, const void*
         if (e) return fail(CSR_ERR_CUDA, "wgrad launch failed: %s", cudaGetErrorString((cudaError_t)e));
         ++*launches;
       }
-      CSR_CUDA(launch_wgrad_reduce(scratch, part_stride, n_parts, part_stride, s));
+      if (!g_opt_wgrad_atomic) {
+        CSR_CUDA(launch_wgrad_reduce(scratch, part_stride, n_parts, part_stride, s));
+        ++*launches;
+      }
       CSR_CUDA(launch_wgrad_scatter(scratch, ld_n, dw, L.cout, L.cin, L.kh, L.kw, L.fold, phase, ci0, std::min(128, ecin - ci0), 0, scale, 0, s));
-      *launches += 2;
+      ++*launches;
     }
   }
   if (db) {
@@ -840,6 +849,23 @@ static std::vector<LayerSpec> bwd_layer_table(const CsrNetDesc& d, const std::ve
   return v;
 }
 
+// Weight-gradient accumulation through L2 vector atomics (option 25, default on): each group [wgrad launches..., reduce]
+// becomes [memset of part 0, wgrad launches (atomic)...] - the reduce kernel and the per-CTA partial slices disappear.
+static void wgrad_ops_to_atomic(std::vector<BwdOp>& ops, float* dacc) {
+  if (!g_opt_wgrad_atomic) return;
+  std::vector<BwdOp> out;
+  out.reserve(ops.size());
+  for (size_t i = 0; i < ops.size(); ++i) {
+    if (ops[i].kind != BwdOp::kReduce) { out.push_back(ops[i]); continue; }
+    size_t first = out.size();
+    while (first > 0 && out[first - 1].kind == BwdOp::kWgrad) --first;
+    for (size_t j = first; j < out.size(); ++j) out[j].wg.p.atomic = 1;
+    BwdOp ms; ms.kind = BwdOp::kMemset; ms.dst = dacc; ms.count = ops[i].count * (long)sizeof(float);
+    out.insert(out.begin() + first, ms);
+  }
+  ops.swap(out);
+}
+
 static int bwd_build(CsrPlan* P, void* ws) {
   const CsrNetDesc& d = P->net;
   const int N = P->N, h = P->h, w = P->w, H = 4 * h, W = 4 * w;
@@ -1096,6 +1122,7 @@ static int bwd_build(CsrPlan* P, void* ws) {
   rc = wgrad_plain(0, h, w, xin, 64, 0, gt0, 64, 0, 1.f);
   if (rc) return rc;
   if (bi != (int)B.size()) return fail(CSR_ERR_BAD_ARG, "internal: backward table mismatch (%d of %zu)", bi, B.size());
+  wgrad_ops_to_atomic(ops, dacc);
   return CSR_OK;
 }
 
@@ -1129,6 +1156,7 @@ int csr_set_option(int32_t key, int32_t value) {
     case 11: g_opt_graphs = value ? 1 : 0; return CSR_OK;        // CUDA-graph replay of plan forward / backward_flat
     case 12: g_opt_graph_max_px = value; return CSR_OK;
     case 14: g_opt_issue_order = value; return CSR_OK;
+    case 25: g_opt_wgrad_atomic = value ? 1 : 0; return CSR_OK;  // plans created afterwards
     case 19: g_opt_eight_acc = value ? 1 : 0; return CSR_OK;
     case 18: g_opt_tall = value ? 1 : 0; return CSR_OK;
     case 17: g_opt_narrow_box = value ? 1 : 0; return CSR_OK;

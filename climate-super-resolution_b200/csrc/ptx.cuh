@@ -94,6 +94,10 @@ __device__ __forceinline__ void bulk_wait_group() { asm volatile("cp.async.bulk.
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
+// fire-and-forget vector fp32 add into global memory (sm_90+): one L2 atomic per 16 bytes
+__device__ __forceinline__ void red_add_v4_f32(float* ptr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(ptr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
 __device__ __forceinline__ void st_global_v8(void* ptr, const uint4& a, const uint4& b) {
   asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(ptr), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x),
                "r"(b.y), "r"(b.z), "r"(b.w)

@@ -176,15 +176,23 @@ wgrad_tc_kernel(const WgradParams p, const __grid_constant__ CUtensorMap tx0, co
       // this CTA's partial sums go to its own slice of the accumulation buffer ([cta][dx][128][ld_n], plain stores);
       // the scatter kernel reduces over CTAs.  (fp32 atomics onto 49 K shared addresses from 148 CTAs were measured at
       // ~100 us per launch - 5x the GEMM itself.)
-      float* base = p.dacc + static_cast<size_t>(blockIdx.x) * p.part_stride;
+      // Default (p.atomic): all CTAs add into ONE copy with 16-byte vector reds - 148 x ~200 KB of partial stores plus a
+      // reduce kernel reading them back cost ~10 us per launch and 1.5 ms per training step; the summation order over
+      // CTAs is then not fixed (last-bit run-to-run differences, like cuDNN's atomics-based weight gradients).
+      float* base = p.dacc + (p.atomic ? 0 : static_cast<size_t>(blockIdx.x) * p.part_stride);
       for (int tp = 0; tp < p.n_dy * p.KW; ++tp) {
         float* dst = base + (static_cast<size_t>(tp) * 128 + ci) * p.ld_n;
         for (int c = 0; c < p.n_cols; c += 8) {
           uint32_t r[8];
           tmem_ld8(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + tp * p.n_cols + c, r);
           tmem_ld_wait();
-          *reinterpret_cast<uint4*>(dst + c) = make_uint4(r[0], r[1], r[2], r[3]);
-          *reinterpret_cast<uint4*>(dst + c + 4) = make_uint4(r[4], r[5], r[6], r[7]);
+          if (p.atomic) {
+            red_add_v4_f32(dst + c, __uint_as_float(r[0]), __uint_as_float(r[1]), __uint_as_float(r[2]), __uint_as_float(r[3]));
+            red_add_v4_f32(dst + c + 4, __uint_as_float(r[4]), __uint_as_float(r[5]), __uint_as_float(r[6]), __uint_as_float(r[7]));
+          } else {
+            *reinterpret_cast<uint4*>(dst + c) = make_uint4(r[0], r[1], r[2], r[3]);
+            *reinterpret_cast<uint4*>(dst + c + 4) = make_uint4(r[4], r[5], r[6], r[7]);
+          }
         }
       }
     }

@@ -30,6 +30,8 @@ struct WgradParams {
   long part_stride;          // floats between the partial-sum slices of consecutive CTAs (all taps of the layer)
   int n_parts;               // grid size = min(num_tiles, SMs)
   int ld_n;
+  int atomic;                // 1: every CTA adds its sums into part 0 with red.global.add.v4.f32 (the host zeroes it first) instead of
+                             //    storing a private partial slice that a reduce kernel would have to read back
   // debug overrides of the MN-major descriptor fields (0 = default)
   int dbg_a_lbo, dbg_a_sbo, dbg_b_lbo, dbg_b_sbo, dbg_flags;
 };
