@@ -694,10 +694,10 @@ int launch_conv_tc(const ConvParams& p, const CUtensorMap& tmap, int num_sms, cu
   CSR_CASE(3, 1, 0, 5, 1)
   CSR_CASE(3, 1, 0, 4, 1)
   CSR_CASE(1, 0, 0, 4, 1)   // 1x1 input gradients with a ReLU / LeakyReLU gate: srcnn.conv2, and conv_last / srcnn.conv3 over the gradient im2col
-  CSR_CASE(2, 0, 0, 4, 1)   // upconv2 input gradient, transposed sub-pixel phases (first phase stores, the others accumulate)
-  CSR_CASE(2, 1, 0, 4, 1)
-  CSR_CASE(2, 0, 0, 5, 1)
-  CSR_CASE(2, 1, 0, 5, 1)
+  CSR_CASE(2, 0, 0, 0, 1)   // upconv input gradients, transposed sub-pixel phases: the first phase stores,
+  CSR_CASE(2, 1, 0, 1, 1)   // the others accumulate in place,
+  CSR_CASE(2, 0, 0, 1, 1)
+  CSR_CASE(2, 1, 0, 5, 1)   // and the last one of upconv2 also applies upconv1's LeakyReLU gate
 #undef CSR_CASE
   switch (p.KW) {
     case 1: return launch_t<1, 0, -1, -1, -1>(p, tmap, num_sms, stream);
