@@ -258,12 +258,12 @@ __global__ void bias_grad_kernel(const __nv_bfloat16* __restrict__ g, long npix,
   if (prow < pix_per_iter) {
     const long stride = static_cast<long>(gridDim.x) * pix_per_iter;
     long pix = blockIdx.x * static_cast<long>(pix_per_iter) + prow;
-    for (; pix + 3 * stride < npix; pix += 4 * stride) {   // four independent 16-byte loads in flight per thread
-      uint4 v[4];
+    for (; pix + 7 * stride < npix; pix += 8 * stride) {   // eight independent 16-byte loads in flight per thread
+      uint4 v[8];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) v[u] = *reinterpret_cast<const uint4*>(g + (pix + u * stride) * C + coff + sub * 8);
+      for (int u = 0; u < 8; ++u) v[u] = *reinterpret_cast<const uint4*>(g + (pix + u * stride) * C + coff + sub * 8);
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < 8; ++u) {
         const uint32_t w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -417,7 +417,7 @@ cudaError_t launch_wgrad_scatter(const float* dacc, int ld_n, float* dw, int cou
 cudaError_t launch_bias_grad(const void* g, long npix, int C, int coff, int cout, float scale, float* const* db, int nseg, cudaStream_t s) {
   BiasSegs segs;
   for (int i = 0; i < 4; ++i) segs.db[i] = db[i < nseg ? i : 0];
-  bias_grad_kernel<<<148 * 2, 256, 256 * 8 * sizeof(float), s>>>(reinterpret_cast<const __nv_bfloat16*>(g), npix, C, coff, cout, scale, segs,
+  bias_grad_kernel<<<148 * 4, 256, 256 * 8 * sizeof(float), s>>>(reinterpret_cast<const __nv_bfloat16*>(g), npix, C, coff, cout, scale, segs,
                                                                  cout / nseg);
   return cudaGetLastError();
 }
