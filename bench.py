@@ -181,6 +181,10 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+# DRAM traffic of one cfg2 forward step (all 183 launches), from the ncu pass stored as profiles/r01_dram_traffic_v4.csv
+CFG2_STEP_DRAM_BYTES = 9.72e9
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -278,7 +282,11 @@ def run_ours(args):
         "gpu_launches": int(launches),
         "clocks": clk.summary(),
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": f"{peaks['source']} bf16_tflops_sustained (burst {peaks['bf16_burst']})",
+                     "traffic": CFG2_STEP_DRAM_BYTES if args.workload == "cfg2" else None,
+                     "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum over the 183 launches of ONE cfg2 step (5.12 GB read + "
+                                     "4.60 GB written), ncu --cache-control none, profiles/r01_dram_traffic_v4.csv; a recorded constant, not "
+                                     "measured in this run",
+                     "peak_source": f"{peaks['source']} bf16_tflops_sustained (burst {peaks['bf16_burst']})",
                      "flop_per_hr_pixel": fl,
                      "note": "dominant kernel conv_tc_kernel (all conv launches of a step); algorithmic FLOPs of the whole forward / step time"},
     }
