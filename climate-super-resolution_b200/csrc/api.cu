@@ -43,7 +43,11 @@ static int g_opt_trace_cta = 0;         // debug: CTA recorded by csr_debug_set_
 static int g_opt_pair = 0;              // CTA-pair (cta_group::2) launches for 3x3 layers with >= 96 KB of weights.  Measured (cfg2): MMAs run at the
                                         // 108 clk/MMA pair rate instead of ~140, but two SMs in lock-step on two accumulators expose the epilogue:
                                         // 6.11 vs 5.90 ms per step, so it stays off by default
-static int g_opt_no_single_group = 1;   // measured: merging the groups buys a 3rd window slot for RDB conv5 but the single group then paces the tile (no net gain)
+static int g_opt_no_single_group = 3;   // epilogue groups of two-accumulator layers: 1 = always two groups of 8 warps (one tile each); 0 = one group of
+                                        // 16 warps when that deepens the window ring (RDB conv5: measured slower, the single group paces the tile);
+                                        // 2 = one group everywhere; 3 (default) = one group for layers with < 96 KB of weights and no residual /
+                                        // gate operand (HRconv, upconv, conv_first, srcnn.conv1: epilogue-bound, 16 warps on one tile shorten its
+                                        // latency chain: -2 % per inference step; the gated input-gradient convs of the backward lose with it)
 static int g_dbg_wgrad[5] = {0, 0, 0, 0, 0};   // a_lbo, a_sbo, b_lbo, b_sbo, flags overrides of the MN-major descriptors
 static int g_opt_no_direct32 = 1;   // measured: no gain over staging on cfg2 (tools/ab_bench.py), kept as an option
 
@@ -361,6 +365,14 @@ static int build_conv(const PackLayer& pl, const PackPart& pp, int N, int H, int
     }
   }
   if (rc) return rc;
+  if (!p.pair && tma_out && p.n_groups == 2 && (g_opt_no_single_group == 2 || (g_opt_no_single_group == 3 && p.w_bytes < 96 * 1024 && res_bits == 0))) {
+    // experiment: all 16 epilogue warps on one tile at a time (two chunks per warp) for every two-accumulator layer
+    Tiling t1;
+    if (choose_tiling(H, W, pp.kh, pp.kw, p.w_bytes, p.n_kblocks, p.stage_row_bytes, 1, &t1, p.box_c * 2) == CSR_OK) {
+      tl = t1;
+      p.n_groups = 1;
+    }
+  }
   if (!p.pair && tma_out && p.n_groups == 2 && tl.n_slots < 3 && !g_opt_no_single_group) {
     // Weights leave little shared memory (RDB conv5: 144 KB): one epilogue group (16 warps, still two accumulator
     // buffers) needs one staging buffer instead of two, which buys a third window slot - the MMAs of such a layer take
@@ -1163,7 +1175,7 @@ int csr_set_option(int32_t key, int32_t value) {
     case 16: g_opt_regroup = value ? 1 : 0; return CSR_OK;       // takes effect for weights packed / plans created afterwards
     case 15: g_opt_trace_cta = value; return CSR_OK;
     case 13: g_opt_pair = value ? 1 : 0; return CSR_OK;          // CTA-pair launches (default off)
-    case 9: g_opt_no_single_group = value ? 1 : 0; return CSR_OK;  // 0: one epilogue group (one staging buffer) when that deepens the window ring
+    case 9: g_opt_no_single_group = value; return CSR_OK;  // 0: one epilogue group (one staging buffer) when that deepens the window ring
     case 8: g_opt_no_direct32 = value ? 1 : 0; return CSR_OK;    // 0: allow unstaged 32-byte stores when staging starves the window ring        // debug: a single MMA issuer warp  // debug: runtime-switched kernels only        // debug: never use four accumulator buffers   // debug: per-element global stores instead of the staged copy-out
     case 20: case 21: case 22: case 23: case 24: g_dbg_wgrad[key - 20] = value; return CSR_OK;
     default: return fail(CSR_ERR_BAD_ARG, "unknown option key %d", key);

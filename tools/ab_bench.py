@@ -18,6 +18,8 @@ VARIANTS = {
     "slots3": {3: 3},
     "no_pdl": {1: 0},
     "single_group_conv5": {9: 0},
+    "single_group_all": {9: 2},
+    "two_groups": {9: 1},
     "pair": {13: 1},
     "regroup": {16: 1},
     "no_eight_acc": {19: 0},
@@ -30,7 +32,7 @@ VARIANTS = {
 
 def run(name, opts, n=64, h=64, w=64, steps=20):
     for k in (1, 3, 5, 7, 8, 9, 13, 14, 16, 17, 18, 19):
-        lib.csr_set_option(k, {1: 1, 3: 8, 8: 1, 9: 1, 14: 1, 17: 1, 18: 1, 19: 1}.get(k, 0))
+        lib.csr_set_option(k, {1: 1, 3: 8, 8: 1, 9: 3, 14: 1, 17: 1, 18: 1, 19: 1}.get(k, 0))
     for k, v in opts.items():
         lib.csr_set_option(k, v)
     torch.manual_seed(0)
