@@ -1,4 +1,6 @@
-"""Per-role pipeline trace of one conv launch (CTA 0): where does a tile's time go?  Debug tool, run on a B200."""
+"""Per-role pipeline trace of one conv launch (CTA 0): where does a tile's time go?  Debug tool, run on a B200.
+The clock stamps are compiled in only on request (they cost ~2 KB of kernel code): build the library with
+`CSR_BUILD_TRACE=1 python climate-super-resolution_b200/build.py --force` first."""
 import os
 import sys
 
