@@ -148,3 +148,25 @@ def test_training_step_semantics():
         opt.step()
         losses.append(float(lv.detach()))
     assert losses[-1] < losses[0]                      # the step actually descends
+
+
+def test_atomic_and_deterministic_weight_gradient_accumulation_agree():
+    """Option 25: weight-gradient partial sums through red.global.add.v4.f32 (default) against the deterministic per-CTA
+    slices + tree reduce.  Same products, different summation order over CTAs: equal to fp32 rounding."""
+    from climsr_b200._lib import lib
+    from oracle import synth
+    sd = synth.make_state_dict(4, 1, 64, 1, 16, seed=3)
+    x, elev, mask = synth.make_inputs(2, 4, 24, 20, seed=4)
+    hr = torch.rand((2, 1, 96, 80), generator=torch.Generator().manual_seed(5)) * 2 - 1
+    grads = []
+    try:
+        for atomic in (1, 0, 0):
+            lib.csr_set_option(25, atomic)
+            grads.append(_train_step(sd, x, elev, mask, hr, 4, 1, 16)[2])
+    finally:
+        lib.csr_set_option(25, 1)
+    for k in grads[0]:
+        if k.endswith(".weight"):                 # (bias gradients always end in a few fp32 atomics per block)
+            assert torch.equal(grads[1][k], grads[2][k]), k                  # the slice + reduce path is run-to-run deterministic
+        scale = float(grads[1][k].abs().max()) + 1e-12
+        assert float((grads[0][k] - grads[1][k]).abs().max()) <= 2e-5 * scale, k

@@ -535,3 +535,25 @@ def test_lr_input_kernel_matches_numpy_cv2_golden(golden_dir):
     want = ol.training_batch(hr.numpy(), elev.numpy(), mask.numpy(), codes.numpy())
     for a, b in zip(got, want):
         assert np.array_equal(a.cpu().numpy(), b)
+
+
+def test_dense_block_regrouping_matches_plain_forward(golden_dir):
+    """Option 16: dense blocks regrouped by source (conv1 + x-parts of conv2-4 in one wide launch, partial sums through the
+    bf16 concat slots) against the plain layer-by-layer forward and the reference golden output."""
+    from climsr_b200._lib import lib
+    from oracle import synth
+    z = np.load(os.path.join(golden_dir, "gen_hydra_seeded.npz"))
+    in_ch, nb, gc, n, h, w = (int(v) for v in z["meta"])
+    sd = synth.make_state_dict(in_ch, 1, 64, nb, gc, seed=0, gain=float(z["gains"][1]))     # the "trained-like" weight scale
+    x, elev, mask = synth.make_inputs(n, in_ch, h, w, seed=1)
+    outs = []
+    try:
+        for regroup in (0, 1):
+            lib.csr_set_option(16, regroup)
+            outs.append(_run_generator(sd, x, elev, mask, in_ch, nb, gc))
+    finally:
+        lib.csr_set_option(16, 0)
+    want = torch.from_numpy(z["sr_trained"])
+    assert float((outs[0] - want).abs().max()) <= 1e-2 and float((outs[1] - want).abs().max()) <= 1e-2
+    assert float((outs[0] - outs[1]).abs().max()) <= 1e-2
+    assert not torch.equal(outs[0], outs[1])      # the option really changes the execution (one more bf16 rounding of p_k)
