@@ -338,10 +338,12 @@ static int build_conv(const PackLayer& pl, const PackPart& pp, int N, int H, int
   if (g_opt_pair && tma_out && p.KW == 3 && p.PW == 1 && (p.KW * p.npad) % 16 == 0 && p.w_bytes >= 96 * 1024 && io.act == CSR_ACT_NONE &&
       (res_bits == 1 || res_bits == 3 || res_bits == 4 || res_bits == 5) && !g_opt_force_generic) {
     Tiling tp;
-    if (choose_tiling(H, W, pp.kh, pp.kw, p.w_bytes / 2, p.n_kblocks, p.stage_row_bytes, p.n_groups, &tp) == CSR_OK &&
+    const int pair_groups = g_opt_pair == 2 ? 1 : p.n_groups;   // 2: one 16-warp epilogue group per CTA (shorter accumulator hand-back)
+    if (choose_tiling(H, W, pp.kh, pp.kw, p.w_bytes / 2, p.n_kblocks, p.stage_row_bytes, pair_groups, &tp) == CSR_OK &&
         (((long long)ceil_div(W, tp.TW) * ceil_div(H, tp.TH) * N) & 1) == 0) {
       tl = tp;
       p.pair = 1;
+      p.n_groups = pair_groups;
     }
   }
   // Layers over <= 32 input channels (the dense-block parts over x1 / x1,x2) only move those channels: 32- or 64-byte
@@ -1174,7 +1176,7 @@ int csr_set_option(int32_t key, int32_t value) {
     case 17: g_opt_narrow_box = value ? 1 : 0; return CSR_OK;
     case 16: g_opt_regroup = value ? 1 : 0; return CSR_OK;       // takes effect for weights packed / plans created afterwards
     case 15: g_opt_trace_cta = value; return CSR_OK;
-    case 13: g_opt_pair = value ? 1 : 0; return CSR_OK;          // CTA-pair launches (default off)
+    case 13: g_opt_pair = value; return CSR_OK;                  // CTA-pair launches (default off; 2 = with one epilogue group per CTA: 5.53 vs 5.38 vs 5.15 ms without pairs)
     case 9: g_opt_no_single_group = value; return CSR_OK;  // 0: one epilogue group (one staging buffer) when that deepens the window ring
     case 8: g_opt_no_direct32 = value ? 1 : 0; return CSR_OK;    // 0: allow unstaged 32-byte stores when staging starves the window ring        // debug: a single MMA issuer warp  // debug: runtime-switched kernels only        // debug: never use four accumulator buffers   // debug: per-element global stores instead of the staged copy-out
     case 20: case 21: case 22: case 23: case 24: g_dbg_wgrad[key - 20] = value; return CSR_OK;

@@ -21,6 +21,7 @@ VARIANTS = {
     "single_group_all": {9: 2},
     "two_groups": {9: 1},
     "pair": {13: 1},
+    "pair_single_group": {13: 2},
     "regroup": {16: 1},
     "no_eight_acc": {19: 0},
     "no_narrow_box": {17: 0},
