@@ -1159,27 +1159,28 @@ int csr_device_check(void) {
 }
 
 int csr_set_option(int32_t key, int32_t value) {
+  // the table with defaults and meanings is in INTEGRATION.md section 6
   switch (key) {
-    case 1: g_opt_pdl = value ? 1 : 0; return CSR_OK;      // programmatic dependent launch on/off
-    case 2: g_opt_force_sw = value; return CSR_OK;
+    case 1: g_opt_pdl = value ? 1 : 0; return CSR_OK;              // programmatic dependent launch on/off
+    case 2: g_opt_force_sw = value; return CSR_OK;                 // debug: force the window pitch
     case 3: g_opt_max_slots = value < 1 ? 1 : value; return CSR_OK;
-    case 4: g_opt_no_tma_store = value ? 1 : 0; return CSR_OK;
-    case 5: g_opt_two_acc = value ? 1 : 0; return CSR_OK;
-    case 6: g_opt_force_generic = value ? 1 : 0; return CSR_OK;
-    case 7: g_opt_one_mma = value ? 1 : 0; return CSR_OK;
-    case 11: g_opt_graphs = value ? 1 : 0; return CSR_OK;        // CUDA-graph replay of plan forward / backward_flat
+    case 4: g_opt_no_tma_store = value ? 1 : 0; return CSR_OK;     // debug: per-element stores instead of the staged copy-out
+    case 5: g_opt_two_acc = value ? 1 : 0; return CSR_OK;          // debug: never more than two accumulator buffers
+    case 6: g_opt_force_generic = value ? 1 : 0; return CSR_OK;    // debug: runtime-switched kernels only
+    case 7: g_opt_one_mma = value ? 1 : 0; return CSR_OK;          // debug: a single MMA issuer warp
+    case 8: g_opt_no_direct32 = value ? 1 : 0; return CSR_OK;      // 0: allow unstaged 32-byte stores when staging starves the window ring
+    case 9: g_opt_no_single_group = value; return CSR_OK;          // epilogue groups of two-accumulator layers (see g_opt_no_single_group)
+    case 11: g_opt_graphs = value ? 1 : 0; return CSR_OK;          // CUDA-graph replay of plan forward / backward_flat
     case 12: g_opt_graph_max_px = value; return CSR_OK;
+    case 13: g_opt_pair = value; return CSR_OK;                    // CTA-pair launches (default off; 2 = with one epilogue group per CTA: 5.53 vs 5.38 vs 5.15 ms without pairs)
     case 14: g_opt_issue_order = value; return CSR_OK;
-    case 25: g_opt_wgrad_atomic = value ? 1 : 0; return CSR_OK;  // plans created afterwards
-    case 19: g_opt_eight_acc = value ? 1 : 0; return CSR_OK;
-    case 18: g_opt_tall = value ? 1 : 0; return CSR_OK;
-    case 17: g_opt_narrow_box = value ? 1 : 0; return CSR_OK;
-    case 16: g_opt_regroup = value ? 1 : 0; return CSR_OK;       // takes effect for weights packed / plans created afterwards
     case 15: g_opt_trace_cta = value; return CSR_OK;
-    case 13: g_opt_pair = value; return CSR_OK;                  // CTA-pair launches (default off; 2 = with one epilogue group per CTA: 5.53 vs 5.38 vs 5.15 ms without pairs)
-    case 9: g_opt_no_single_group = value; return CSR_OK;  // 0: one epilogue group (one staging buffer) when that deepens the window ring
-    case 8: g_opt_no_direct32 = value ? 1 : 0; return CSR_OK;    // 0: allow unstaged 32-byte stores when staging starves the window ring        // debug: a single MMA issuer warp  // debug: runtime-switched kernels only        // debug: never use four accumulator buffers   // debug: per-element global stores instead of the staged copy-out
+    case 16: g_opt_regroup = value ? 1 : 0; return CSR_OK;         // takes effect for weights packed / plans created afterwards
+    case 17: g_opt_narrow_box = value ? 1 : 0; return CSR_OK;
+    case 18: g_opt_tall = value ? 1 : 0; return CSR_OK;
+    case 19: g_opt_eight_acc = value ? 1 : 0; return CSR_OK;
     case 20: case 21: case 22: case 23: case 24: g_dbg_wgrad[key - 20] = value; return CSR_OK;
+    case 25: g_opt_wgrad_atomic = value ? 1 : 0; return CSR_OK;    // plans created afterwards
     default: return fail(CSR_ERR_BAD_ARG, "unknown option key %d", key);
   }
 }
