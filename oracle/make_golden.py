@@ -19,6 +19,7 @@ Fixtures
   gen_default_seeded.npz- class default (nb=23, gc=32, in=4), same recipe, smaller raster.
   normalization.npz     - the reference's MinMaxScaler.normalize / .denormalize (+ NaN land mask) on seeded rasters.
   lr_input.npz          - numpy flips / rot90 + cv2 INTER_NEAREST resize (the arithmetic behind climate_dataset.py:152-172).
+  discriminator.npz     - the reference Discriminator (default init, seed 0, train mode) + relativistic GAN losses.
 """
 from __future__ import annotations
 
@@ -125,6 +126,39 @@ def normalization():
     print("normalization.npz written")
 
 
+def discriminator():
+    """tests/golden/discriminator.npz: the reference Discriminator (climsr/models/discriminator.py, imported unmodified,
+    weights = oracle.synth.make_discriminator_state_dict(0) through load_state_dict(strict=True), .train() mode) on seeded
+    128x128 inputs: scores for a "real" and a "fake" batch,
+    the relativistic losses of pl_gan.py:28-61 computed with torch's BCEWithLogitsLoss, and the gradient of the
+    discriminator loss w.r.t. the first and last weights, plus the eval-mode scores (running statistics)."""
+    from climsr.models.discriminator import Discriminator
+    D = Discriminator()
+    D.load_state_dict(synth.make_discriminator_state_dict(seed=0), strict=True)    # names / shapes / order must match exactly
+    D.train()
+    g = torch.Generator().manual_seed(31)
+    hr = torch.rand((3, 1, 128, 128), generator=g) * 2 - 1
+    sr = (hr + 0.1 * torch.randn((3, 1, 128, 128), generator=g)).clamp(-1, 1)
+    s_real, s_fake = D(hr), D(sr)
+    bce = torch.nn.BCEWithLogitsLoss()
+    ones, zeros = torch.ones((3, 1)), torch.zeros((3, 1))
+    rf, fr = s_real - s_fake.mean(), s_fake - s_real.mean()
+    loss_g = (bce(fr, ones) + bce(rf, zeros)) / 2                       # pl_gan.py:31-39
+    loss_d = (bce(rf, ones) + bce(fr, zeros)) / 2                       # pl_gan.py:52-59
+    params = dict(D.named_parameters())
+    first, last = "feature_extraction.1.weight", "classification.1.weight"
+    g_first, g_last = torch.autograd.grad(loss_d, [params[first], params[last]])
+    D.load_state_dict(synth.make_discriminator_state_dict(seed=0), strict=True)    # undo the running-statistics updates of the two forwards
+    D.eval()
+    with torch.no_grad():
+        s_eval = D(hr)
+    np.savez_compressed(os.path.join(OUT, "discriminator.npz"), hr=hr.numpy(), sr=sr.numpy(), s_real=s_real.detach().numpy(),
+                        s_fake=s_fake.detach().numpy(), loss_g=float(loss_g.detach()), loss_d=float(loss_d.detach()),
+                        g_first=g_first.numpy(), g_last=g_last.numpy(), s_eval=s_eval.numpy(),
+                        names=np.array(list(D.state_dict().keys())))
+    print("discriminator.npz written")
+
+
 def lr_input():
     """tests/golden/lr_input.npz: numpy flips / rot90 (climate_dataset.py:152-170) and cv2.resize INTER_NEAREST - what
     albumentations' A.Resize calls (climate_dataset.py:84-92,172) - on seeded square tiles, all 16 augmentation codes."""
@@ -167,9 +201,13 @@ if __name__ == "__main__":
     if "--lr-input-only" in sys.argv:
         lr_input()
         sys.exit(0)
+    if "--discriminator-only" in sys.argv:
+        discriminator()
+        sys.exit(0)
     tiny_refinit()
     normalization()
     lr_input()
+    discriminator()
     if "--tiny-only" not in sys.argv:
         seeded("gen_hydra_seeded", 4, 11, 16, 2, 16, 16)
         seeded("gen_default_seeded", 4, 23, 32, 1, 12, 12)

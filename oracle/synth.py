@@ -94,3 +94,39 @@ def make_targets(sr: torch.Tensor, seed: int = 4) -> Dict[str, torch.Tensor]:
     mn = -60 + 40 * torch.rand((n,), generator=g2)
     mx = 20 + 30 * torch.rand((n,), generator=g2)
     return {"hr": hr, "min": mn, "max": mx}
+
+
+def make_discriminator_state_dict(seed: int = 0, in_channels: int = 1, width: int = 64, stages: int = 4) -> "OrderedDict[str, torch.Tensor]":
+    """Seeded weights with the names / shapes / order of the reference discriminator's ``state_dict``
+    (climsr/models/discriminator.py:8-40: nn.Sequential indices 1, 3, 5 (+7 per stage) for conv, BatchNorm, conv; then the
+    two valid convs; ``classification.{0,1}``).  Conv / Linear: U(-1/sqrt(fan_in), 1/sqrt(fan_in)) like the default init;
+    BatchNorm weight ~ U(0.5, 1.5), bias ~ U(-0.2, 0.2) so the affine part is exercised; fresh running statistics."""
+    g = torch.Generator().manual_seed(seed)
+    sd: "OrderedDict[str, torch.Tensor]" = OrderedDict()
+
+    def uni(shape, bound):
+        return (torch.rand(shape, generator=g) * 2 - 1) * bound
+
+    def conv(name, cout, cin, k=3):
+        b = 1.0 / math.sqrt(cin * k * k)
+        sd[name + ".weight"] = uni((cout, cin, k, k), b)
+        sd[name + ".bias"] = uni((cout,), b)
+
+    idx, cin, c = 0, in_channels, width
+    for _ in range(stages):
+        conv(f"feature_extraction.{idx + 1}", c, cin)
+        bn = f"feature_extraction.{idx + 3}"
+        sd[bn + ".weight"] = torch.rand((c,), generator=g) + 0.5
+        sd[bn + ".bias"] = uni((c,), 0.2)
+        sd[bn + ".running_mean"] = torch.zeros(c)
+        sd[bn + ".running_var"] = torch.ones(c)
+        sd[bn + ".num_batches_tracked"] = torch.tensor(0, dtype=torch.long)
+        conv(f"feature_extraction.{idx + 5}", c, c)
+        cin, c, idx = c, c * 2, idx + 7
+    conv(f"feature_extraction.{idx}", cin, cin)
+    conv(f"feature_extraction.{idx + 2}", cin, cin)
+    for name, o, i in (("classification.0", 100, 8192), ("classification.1", 1, 100)):
+        b = 1.0 / math.sqrt(i)
+        sd[name + ".weight"] = uni((o, i), b)
+        sd[name + ".bias"] = uni((o,), b)
+    return sd

@@ -152,3 +152,28 @@ def test_lr_input_restatement_matches_numpy_cv2_golden(golden_dir):
     a = g["hr"][3, 0]
     assert np.array_equal(ol.augment(ol.augment(a, False, False, 1), False, False, 3), a)
     assert np.array_equal(ol.augment(ol.augment(a, True, True, 0), True, True, 0), a)
+
+
+def test_discriminator_restatement_matches_reference_golden(golden_dir):
+    """oracle/discriminator.py (groundwork for SURVEY 8f row 2) against the reference Discriminator run unmodified by
+    oracle/make_golden.py on oracle.synth.make_discriminator_state_dict(0): train-mode scores (batch statistics), eval-mode
+    scores, the relativistic losses of pl_gan.py:28-61 and two gradients of the discriminator loss."""
+    from oracle import discriminator as od
+    g = _load(golden_dir, "discriminator.npz")
+    sd = synth.make_discriminator_state_dict(seed=0)
+    assert list(sd.keys()) == [str(k) for k in g["names"]]
+    for k in ("feature_extraction.1.weight", "classification.1.weight"):
+        sd[k].requires_grad_(True)
+    hr, sr = torch.from_numpy(g["hr"]), torch.from_numpy(g["sr"])
+    s_real, s_fake = od.discriminator_forward(sd, hr), od.discriminator_forward(sd, sr)
+    assert float((s_real.detach() - torch.from_numpy(g["s_real"])).abs().max()) <= 1e-5
+    assert float((s_fake.detach() - torch.from_numpy(g["s_fake"])).abs().max()) <= 1e-5
+    loss_g, loss_d = od.relativistic_losses(s_real, s_fake)
+    assert abs(float(loss_g) - float(g["loss_g"])) <= 1e-6 and abs(float(loss_d) - float(g["loss_d"])) <= 1e-6
+    g_first, g_last = torch.autograd.grad(loss_d, [sd["feature_extraction.1.weight"], sd["classification.1.weight"]])
+    for got, want in ((g_first, g["g_first"]), (g_last, g["g_last"])):
+        want = torch.from_numpy(want)
+        assert float((got - want).abs().max()) <= 1e-5 * max(1.0, float(want.abs().max()))
+    with torch.no_grad():
+        s_eval = od.discriminator_forward(sd, hr, training=False)
+    assert float((s_eval - torch.from_numpy(g["s_eval"])).abs().max()) <= 1e-5
