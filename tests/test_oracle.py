@@ -169,7 +169,7 @@ def test_discriminator_restatement_matches_reference_golden(golden_dir):
     assert float((s_real.detach() - torch.from_numpy(g["s_real"])).abs().max()) <= 1e-5
     assert float((s_fake.detach() - torch.from_numpy(g["s_fake"])).abs().max()) <= 1e-5
     loss_g, loss_d = od.relativistic_losses(s_real, s_fake)
-    assert abs(float(loss_g) - float(g["loss_g"])) <= 1e-6 and abs(float(loss_d) - float(g["loss_d"])) <= 1e-6
+    assert abs(float(loss_g.detach()) - float(g["loss_g"])) <= 1e-6 and abs(float(loss_d.detach()) - float(g["loss_d"])) <= 1e-6
     g_first, g_last = torch.autograd.grad(loss_d, [sd["feature_extraction.1.weight"], sd["classification.1.weight"]])
     for got, want in ((g_first, g["g_first"]), (g_last, g["g_last"])):
         want = torch.from_numpy(want)
