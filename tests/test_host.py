@@ -58,3 +58,40 @@ def test_load_state_dict_from_oracle_names():
     holder.generator = ESRGANGenerator(4, 1, 64, 2, 16)
     r = holder.load_state_dict(pref, strict=False)
     assert not r.missing_keys and not r.unexpected_keys
+
+
+def test_scaler_and_data_wrappers_refuse_cpu_and_validate_shapes():
+    """Error conventions of the drop-in boundary: no CPU fallback - CPU tensors raise CsrError before any
+    kernel is touched; shape mistakes raise ValueError like the reference's numpy / torch shape checks."""
+    from climsr_b200 import CsrError
+    from climsr_b200.data import aug_code, make_lr_batch, random_aug_codes
+    from climsr_b200.normalization import MinMaxScaler
+    sc = MinMaxScaler(feature_range=(-1.0, 1.0))
+    assert (sc.a, sc.b, sc.eps, sc.nan_substitution) == (-1.0, 1.0, 1e-8, 0.0)          # normalization.py:26-35 defaults
+    assert MinMaxScaler().feature_range == (0.0, 1.0)
+    x = torch.zeros((2, 8, 8))
+    with pytest.raises(CsrError):
+        sc.normalize(x, [0.0, 0.0], [1.0, 1.0])
+    with pytest.raises(CsrError):
+        sc.denormalize(torch.zeros((2, 1, 8, 8)), [0.0, 0.0], [1.0, 1.0])
+    with pytest.raises(CsrError):
+        make_lr_batch(torch.zeros((1, 1, 8, 8)), torch.zeros((1, 1, 8, 8)), torch.zeros((1, 1, 8, 8)))
+    # augmentation codes: bit0 vertical flip, bit1 horizontal flip, bits 2-3 rot90 factor (climate_dataset.py:152-170)
+    assert [aug_code(False, False, 0), aug_code(True, False, 0), aug_code(False, True, 0), aug_code(True, True, 3)] == [0, 1, 2, 15]
+    codes = random_aug_codes(256, torch.Generator().manual_seed(0))
+    assert codes.dtype == torch.int32 and int(codes.min()) >= 0 and int(codes.max()) <= 15
+    assert set(random_aug_codes(64, torch.Generator().manual_seed(1), v_flip=False, h_flip=False, random_90_rotation=False).tolist()) == {0}
+    # with every transform enabled all three draws occur about half of the time
+    assert 0.3 < float((codes & 1).float().mean()) < 0.7 and 0.3 < float(((codes >> 1) & 1).float().mean()) < 0.7
+
+
+def test_gradient_bucketer_layout_is_reverse_parameter_order():
+    """Buckets follow the order gradients become final in backward (last layers first), capped by bucket_mb."""
+    from climsr_b200.parallel import GradientBucketer
+    net = ESRGANGenerator(in_channels=4, out_channels=1, nf=64, nb=1, gc=16)
+    b = GradientBucketer(net.parameters(), bucket_mb=0.25, comm_dtype=torch.bfloat16)
+    flat = [p for bucket in b.buckets for p in bucket]
+    params = [p for p in net.parameters() if p.requires_grad]
+    assert len(flat) == len(params) and all(a is c for a, c in zip(flat, reversed(params)))
+    assert sum(b.bucket_bytes()) == 2 * sum(p.numel() for p in params)
+    assert all(nbytes <= 0.25 * (1 << 20) or len(bucket) == 1 for nbytes, bucket in zip(b.bucket_bytes(), b.buckets))
