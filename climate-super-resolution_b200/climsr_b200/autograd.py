@@ -33,6 +33,10 @@ class GeneratorFunction(torch.autograd.Function):
             check(lib.csr_plan_forward(plan, packed.data_ptr(), xs.data_ptr(), es.data_ptr(), ms.data_ptr(), out.data_ptr(),
                                        current_stream_ptr()), "csr_plan_forward")
         module._fwd_serial += 1
+        module._train_plan = plan
+        # an optimizer step normally follows: whatever the version counters say, the next inference forward repacks
+        module._packed_key = None
+        module._packed_bwd_key = None
         ctx.module, ctx.plan, ctx.serial, ctx.dev = module, plan, module._fwd_serial, dev
         ctx.shapes = [tuple(p.shape) for p in params]
         ctx.set_materialize_grads(False)
@@ -44,6 +48,9 @@ class GeneratorFunction(torch.autograd.Function):
         n_in = 4 + len(ctx.shapes)
         if grad_out is None:
             return (None,) * n_in
+        if ctx.needs_input_grad[1]:
+            raise CsrError("climsr_b200: the generator does not produce a gradient for its input x (it is data in the reference's "
+                           "training loop, climsr/task/pl_generator_pre_training.py:18-33); detach x or clear requires_grad")
         if ctx.serial != module._fwd_serial:
             raise CsrError("climsr_b200: backward() must follow the forward() that produced this output (the training plan keeps "
                            "the saved activations of the latest forward only)")

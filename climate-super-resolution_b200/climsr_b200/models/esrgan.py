@@ -21,6 +21,23 @@ from torch import Tensor
 
 from .._lib import CsrError, NetDesc, check, current_stream_ptr, lib
 
+# Parameter version counters do not see every update: torch.optim.*(fused=True).step() and ``p.data.mul_()`` leave
+# ``p._version`` unchanged.  A process-wide optimizer post-step hook therefore bumps this epoch, which is part of the
+# pack-cache key: the first forward after ANY optimizer step repacks.  (Direct ``.data`` surgery - EMA, SWA - must call
+# ``ESRGANGenerator.mark_weights_dirty()``.)
+_WEIGHT_EPOCH = [0]
+
+
+def _bump_weight_epoch(*_args, **_kwargs) -> None:
+    _WEIGHT_EPOCH[0] += 1
+
+
+try:   # torch >= 2.0
+    from torch.optim.optimizer import register_optimizer_step_post_hook as _reg_post_hook
+    _reg_post_hook(_bump_weight_epoch)
+except Exception:   # pragma: no cover - without the hook every forward of a module in train() mode repacks (see below)
+    _reg_post_hook = None
+
 
 class _RDBParams(nn.Module):
     """Parameter container with the names of ResidualDenseBlock (esrgan.py:17-27)."""
@@ -82,11 +99,60 @@ class ESRGANGenerator(nn.Module):
         self._packed_bwd_key: Optional[Tuple] = None
         self._fwd_serial = 0
         self._grad_sync = None
+        self._dirty = False
+        self._train_plan = None       # plan of the latest training forward: its saved activations belong to a live autograd node
+        self._ordered_cache = None
+        self._seg_cache = None
+        self._goff_cache = None
+
+    # derived device state (plans, packed blobs, pointer caches) is never copied or pickled: copy.deepcopy (EMA / SWA
+    # shadows) and torch.save(module) would otherwise duplicate raw CsrPlan* handles -> shared workspaces, double free
+    _DERIVED = ("_packed", "_packed_key", "_plans", "_packed_bwd", "_packed_bwd_key", "_ordered_cache", "_seg_cache", "_goff_cache",
+                "_train_plan", "_grad_sync")
+
+    def _reset_derived(self) -> None:
+        self._packed = self._packed_key = self._packed_bwd = self._packed_bwd_key = None
+        self._plans = {}
+        self._ordered_cache = self._seg_cache = self._goff_cache = self._train_plan = self._grad_sync = None
+        self._fwd_serial = 0
+        self._dirty = False
+
+    def __getstate__(self):
+        state = dict(self.__dict__)
+        for k in self._DERIVED:
+            state.pop(k, None)
+        return state
+
+    def __setstate__(self, state):
+        super().__setstate__(state)
+        self._reset_derived()
+
+    def __deepcopy__(self, memo):
+        import copy
+        cls = self.__class__
+        new = cls.__new__(cls)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            if k not in self._DERIVED:
+                new.__dict__[k] = copy.deepcopy(v, memo)
+        new._reset_derived()
+        return new
+
+    def mark_weights_dirty(self) -> None:
+        """Call after changing parameters behind autograd's back (``p.data`` updates): the next forward repacks."""
+        self._dirty = True
+
+    def _apply(self, fn, *args, **kwargs):
+        # .cuda() / .to() / .float(): parameter storage moves, cached pointers and plans of the old device are stale
+        out = super()._apply(fn, *args, **kwargs)
+        self._ordered_cache = None
+        self._packed_key = self._packed_bwd_key = None
+        return out
 
     # ------------------------------------------------------------------ weights
     def _ordered_params(self):
         """(weight, bias) pairs in state_dict order == csr layer order."""
-        if getattr(self, "_ordered_cache", None) is not None:
+        if self._ordered_cache is not None:
             return self._ordered_cache
         n = lib.csr_num_layers(C.byref(self._desc))
         if n < 0:
@@ -109,7 +175,9 @@ class ESRGANGenerator(nn.Module):
         """bf16 UMMA weight tiles + fp32 biases; rebuilt when any parameter changed (optimizer step, load_state_dict)."""
         pairs = self._ordered_params()
         dev = pairs[0][0].device
-        key = (dev,) + tuple((p.data_ptr(), p._version) for wb in pairs for p in wb)
+        key = (dev, _WEIGHT_EPOCH[0]) + tuple((p.data_ptr(), p._version) for wb in pairs for p in wb)
+        # a module in train() mode without the optimizer hook cannot trust version counters at all
+        force = force or self._dirty or (_reg_post_hook is None and self.training)
         if self._packed is not None and key == self._packed_key and not force:
             return self._packed
         if dev.type != "cuda":
@@ -129,6 +197,7 @@ class ESRGANGenerator(nn.Module):
             check(lib.csr_pack_weights(C.byref(self._desc), wp, bp, self._packed.data_ptr(), nbytes, current_stream_ptr()),
                   "csr_pack_weights")
         self._packed_key = key
+        self._dirty = False
         return self._packed
 
     def packed_weights_bwd(self, force: bool = False) -> Tensor:
@@ -159,6 +228,7 @@ class ESRGANGenerator(nn.Module):
         key = (n, h, w, dev, train)
         hit = self._plans.get(key)
         if hit is not None:
+            self._plans[key] = self._plans.pop(key)      # most recently used last
             return hit[0]
         nbytes = (lib.csr_train_workspace_bytes if train else lib.csr_workspace_bytes)(C.byref(self._desc), n, h, w)
         ws = torch.empty(nbytes + 1024, dtype=torch.uint8, device=dev)
@@ -167,12 +237,26 @@ class ESRGANGenerator(nn.Module):
         with torch.cuda.device(dev):
             create = lib.csr_train_plan_create if train else lib.csr_plan_create
             check(create(C.byref(self._desc), n, h, w, base, nbytes, C.byref(plan)), "csr_plan_create")
-        if len(self._plans) >= 4:   # bound the cached workspaces
-            for _, (p, _t) in list(self._plans.items()):
-                lib.csr_plan_destroy(p)
-            self._plans.clear()
+        if len(self._plans) >= 4:   # bound the cached workspaces: evict the least recently used plan ...
+            for old_key in list(self._plans.keys()):
+                old_plan = self._plans[old_key][0]
+                if old_plan == self._train_plan and len(self._plans) > 1:
+                    continue          # ... but never the one a live autograd node may still run its backward on
+                self._evict(old_key)
+                break
         self._plans[key] = (plan.value, ws)
         return plan.value
+
+    def _evict(self, key) -> None:
+        plan, _ws = self._plans.pop(key)
+        if plan == self._train_plan:
+            self._train_plan = None
+            self._fwd_serial += 1     # a backward of the evicted plan's forward now raises instead of touching freed memory
+        if self._seg_cache is not None and self._seg_cache[0][0] == plan:
+            self._seg_cache = None
+        if self._goff_cache is not None and self._goff_cache[0] == plan:
+            self._goff_cache = None
+        lib.csr_plan_destroy(plan)
 
     def set_grad_sync(self, sync) -> None:
         """Data-parallel training: a climsr_b200.parallel.BackwardGradSync makes backward() return gradients that are already
@@ -180,7 +264,7 @@ class ESRGANGenerator(nn.Module):
         self._grad_sync = sync
 
     def _backward_segments(self, plan, nseg: int) -> int:
-        cache = getattr(self, "_seg_cache", None)
+        cache = self._seg_cache
         if cache is not None and cache[0] == (plan, nseg):
             return cache[1]
         n = lib.csr_plan_backward_segments(plan, nseg)
@@ -190,7 +274,7 @@ class ESRGANGenerator(nn.Module):
         return n
 
     def _grad_offsets(self, plan):
-        cache = getattr(self, "_goff_cache", None)
+        cache = self._goff_cache
         if cache is not None and cache[0] == plan:
             return cache[1]
         n = lib.csr_num_layers(C.byref(self._desc))
@@ -205,7 +289,7 @@ class ESRGANGenerator(nn.Module):
 
     def __del__(self):
         try:
-            for p, _t in self._plans.values():
+            for p, _t in self.__dict__.get("_plans", {}).values():
                 lib.csr_plan_destroy(p)
         except Exception:
             pass

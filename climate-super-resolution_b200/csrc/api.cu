@@ -1377,7 +1377,10 @@ static int run_graphed(CsrPlan::GraphCache& gc, const void* packed, cudaStream_t
   if (gc.calls++ == 0) return body(s);
   // capture on a private stream (the caller's may be the legacy default stream, which cannot be captured); the
   // instantiated graph is then launched into the caller's stream
-  static thread_local cudaStream_t cs = nullptr;
+  static thread_local cudaStream_t cs_dev[64] = {};     // a stream belongs to the device it was created on
+  int cur_dev = 0;
+  if (cudaGetDevice(&cur_dev) != cudaSuccess || cur_dev < 0 || cur_dev >= 64) { cudaGetLastError(); gc.failed = true; return body(s); }
+  cudaStream_t& cs = cs_dev[cur_dev];
   if (!cs && cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); gc.failed = true; return body(s); }
   const long l0 = g_launches.load();
   {
@@ -1774,15 +1777,15 @@ int csr_mse_loss(const float* sr, const float* hr, float* grad, int64_t numel, f
 // ---- metrics ------------------------------------------------------------------------------------------
 size_t csr_metrics_scratch_bytes(int32_t n, int32_t h, int32_t w) { return metrics_scratch_bytes(n, h, w); }
 
-int csr_masked_metrics(const float* sr, const float* hr, const float* original, const float* mask, const float* mn, const float* mx,
-                       float zmean, float zstd, float range_a, float range_b, int32_t n, int32_t h, int32_t w, float* out, void* scratch,
-                       size_t scratch_bytes, void* stream) {
+int csr_masked_metrics(const float* sr, const float* hr, const float* original, const float* mask, const double* mn, const double* mx,
+                       float zmean, float zstd, double range_a, double range_b, double eps, int32_t n, int32_t h, int32_t w, float* out,
+                       void* scratch, size_t scratch_bytes, void* stream) {
   if (!sr || !hr || !original || !mask || !out || !scratch) return fail(CSR_ERR_BAD_ARG, "null pointer");
   if ((mn == nullptr) != (mx == nullptr)) return fail(CSR_ERR_BAD_ARG, "mn and mx must both be given or both be null");
   if (n < 1 || h < 11 || w < 11) return fail(CSR_ERR_UNSUPPORTED, "need n>=1 and h,w >= 11 (SSIM window), got %d %d %d", n, h, w);
   if (scratch_bytes < metrics_scratch_bytes(n, h, w)) return fail(CSR_ERR_WORKSPACE, "metrics scratch too small");
   int launches = 0;
-  cudaError_t e = launch_masked_metrics(sr, hr, original, mask, mn, mx, zmean, zstd, range_a, range_b, n, h, w, out, scratch,
+  cudaError_t e = launch_masked_metrics(sr, hr, original, mask, mn, mx, zmean, zstd, range_a, range_b, eps, n, h, w, out, scratch,
                                         reinterpret_cast<cudaStream_t>(stream), &launches);
   g_launches += launches;
   if (e != cudaSuccess) return fail(CSR_ERR_CUDA, "metrics launch failed: %s", cudaGetErrorString(e));

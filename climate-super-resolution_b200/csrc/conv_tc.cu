@@ -607,12 +607,15 @@ template <int KW_T, int PW_T, int ACT_T, int RES_T, int ST_T, int PAIR_T = 0, in
 static int launch_t(const ConvParams& p, const CUtensorMap& tmap, int num_sms, cudaStream_t stream) {
   const size_t smem = conv_smem_bytes(p);
   if (smem > static_cast<size_t>(kSmemLimit)) return static_cast<int>(cudaErrorInvalidValue);
-  static bool configured = false;
+  // the attribute is per device (and per template instantiation): one process may drive several GPUs
+  static bool configured[64] = {};
   auto kern = conv_tc_kernel<KW_T, PW_T, ACT_T, RES_T, ST_T, PAIR_T, TALL_T>;
-  if (!configured) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return static_cast<int>(cudaErrorInvalidDevice);
+  if (!configured[dev]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
     if (e != cudaSuccess) return static_cast<int>(e);
-    configured = true;
+    configured[dev] = true;
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(p.num_tiles < num_sms ? p.num_tiles : num_sms);

@@ -20,32 +20,45 @@ constexpr int kMinMax = 6;    // min/max of original, masked sr, masked hr
 constexpr int kPart = kSums + kMinMax;
 constexpr float kMapeEps = 1.17e-06f;
 
+// Per-thread accumulators.  T = float for the z-score scaler (the reference's StandardScaler keeps float32:
+// ``arr * std + mean`` with Python-float constants, normalization.py:115) and double for the min-max scaler: there the
+// per-sample ``min`` / ``max`` reach MinMaxScaler._denormalize as float64 (N,) tensors (pandas columns through
+// default_collate), so ``arr.permute(1,2,3,0) - min_`` promotes the denormalised tensor to float64 and every metric on it
+// - the eight |p - t| <= eps counts in particular - is evaluated in float64 (normalization.py:70-82, regression_accuracy.py:18).
+template <typename T>
 struct Acc {
-  float s[kSums];
+  float cnt[8];
+  T s[5];            // sum|d|, sum d^2, sum t, sum t^2, smape terms           (denormalised pair)
+  float sn[3];       // mape terms, sum|dn|, sum dn^2                            (normalised pair, always float32)
   float mn[3], mx[3];
 };
 
-__device__ __forceinline__ void acc_pixel(Acc& a, float sr, float hr, float orig, float mask, float dscale_inv, float dmin, bool zs,
-                                          float zmean, float zstd) {
+template <typename T>
+__device__ __forceinline__ void acc_pixel(Acc<T>& a, float sr, float hr, float orig, float mask, T dscale, T dmin, float zmean, float zstd) {
   const bool land = mask != 0.f;                        // (~mask.bool()) -> 0.0, task.py:288-291
-  const float den = zs ? sr * zstd + zmean : (sr - dmin) * dscale_inv;   // normalization.py:115 / :80-82
+  T den;
+  if constexpr (sizeof(T) == 4) den = __fadd_rn(__fmul_rn(sr, zstd), zmean);          // two roundings, like the two torch ops (no FMA)
+  else den = (static_cast<double>(sr) - dmin) / dscale;                               // out = (arr - min_) / scale: a true division
   const float srn = land ? sr : 0.f;
   const float hrn = land ? hr : 0.f;
-  const float dsr = land ? den : 0.f;
-  const float org = land ? orig : 0.f;
-  const float d = fabsf(dsr - org);
-  a.s[0] += d <= 0.1f;  a.s[1] += d <= 0.25f; a.s[2] += d <= 0.5f;  a.s[3] += d <= 0.75f;
-  a.s[4] += d <= 1.0f;  a.s[5] += d <= 1.25f; a.s[6] += d <= 1.5f;  a.s[7] += d <= 2.0f;
-  a.s[8] += d;
-  a.s[9] += d * d;
-  a.s[10] += org;
-  a.s[11] += org * org;
-  a.s[12] += __fdividef(2.f * d, fmaxf(fabsf(org) + fabsf(dsr), kMapeEps));   // fast division: 2 ulp, metrics are held to 1e-4
+  const T dsr = land ? den : static_cast<T>(0);
+  const T org = land ? static_cast<T>(orig) : static_cast<T>(0);
+  const T d = fabs(dsr - org);
+  a.cnt[0] += d <= static_cast<T>(0.1);  a.cnt[1] += d <= static_cast<T>(0.25); a.cnt[2] += d <= static_cast<T>(0.5);
+  a.cnt[3] += d <= static_cast<T>(0.75); a.cnt[4] += d <= static_cast<T>(1.0);  a.cnt[5] += d <= static_cast<T>(1.25);
+  a.cnt[6] += d <= static_cast<T>(1.5);  a.cnt[7] += d <= static_cast<T>(2.0);
+  a.s[0] += d;
+  a.s[1] += d * d;
+  a.s[2] += org;
+  a.s[3] += org * org;
+  if constexpr (sizeof(T) == 4) a.s[4] += __fdividef(2.f * d, fmaxf(fabsf(org) + fabsf(dsr), kMapeEps));   // fast division: 2 ulp, metrics are held to 1e-4
+  else a.s[4] += static_cast<double>(__fdividef(2.f * static_cast<float>(d), fmaxf(static_cast<float>(fabs(org) + fabs(dsr)), kMapeEps)));
   const float dn = fabsf(srn - hrn);
-  a.s[13] += __fdividef(dn, fmaxf(fabsf(hrn), kMapeEps));
-  a.s[14] += dn;
-  a.s[15] += dn * dn;
-  a.mn[0] = fminf(a.mn[0], org); a.mx[0] = fmaxf(a.mx[0], org);
+  a.sn[0] += __fdividef(dn, fmaxf(fabsf(hrn), kMapeEps));
+  a.sn[1] += dn;
+  a.sn[2] += dn * dn;
+  const float orgf = static_cast<float>(org);
+  a.mn[0] = fminf(a.mn[0], orgf); a.mx[0] = fmaxf(a.mx[0], orgf);
   a.mn[1] = fminf(a.mn[1], srn); a.mx[1] = fmaxf(a.mx[1], srn);
   a.mn[2] = fminf(a.mn[2], hrn); a.mx[2] = fmaxf(a.mx[2], hrn);
 }
@@ -64,24 +77,25 @@ __device__ __forceinline__ float warp_max(float v) {
 }
 
 // grid = (blocks_per_image, N).  Each thread walks groups of 4 pixels of one image.
+template <typename T>
 __global__ void __launch_bounds__(kP1Threads)
 metrics_pass1_kernel(const float* __restrict__ sr, const float* __restrict__ hr, const float* __restrict__ orig,
-                     const float* __restrict__ mask, const float* __restrict__ mn, const float* __restrict__ mx, float zmean, float zstd,
-                     float ra, float rb, long hw, double* __restrict__ partials) {
+                     const float* __restrict__ mask, const double* __restrict__ mn, const double* __restrict__ mx, float zmean, float zstd,
+                     double ra, double rb, double eps, long hw, double* __restrict__ partials) {
   const int n = blockIdx.y;
-  const bool zs = (mn == nullptr);
-  float dmin = 0.f, dscale_inv = 1.f;
-  if (!zs) {
-    // scale = (b-a)/((max-min)+eps); min_ = a - min*scale; out = (arr - min_)/scale   (normalization.py:70-82)
-    const float scale = (rb - ra) / ((mx[n] - mn[n]) + 1e-8f);
-    dmin = ra - mn[n] * scale;
-    dscale_inv = 1.f / scale;
+  T dmin = 0, dscale = 1;
+  if constexpr (sizeof(T) == 8) {
+    // scale = (b-a)/((max-min)+eps); min_ = a - min*scale; out = (arr - min_)/scale   (normalization.py:70-82), all float64
+    dscale = (rb - ra) / ((mx[n] - mn[n]) + eps);
+    dmin = ra - mn[n] * dscale;
   }
-  Acc a;
+  Acc<T> a;
 #pragma unroll
-  for (int i = 0; i < kSums; ++i) a.s[i] = 0.f;
+  for (int i = 0; i < 8; ++i) a.cnt[i] = 0.f;
 #pragma unroll
-  for (int i = 0; i < 3; ++i) { a.mn[i] = FLT_MAX; a.mx[i] = -FLT_MAX; }
+  for (int i = 0; i < 5; ++i) a.s[i] = 0;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) { a.sn[i] = 0.f; a.mn[i] = FLT_MAX; a.mx[i] = -FLT_MAX; }
   const long base = static_cast<long>(n) * hw;
   const long groups = (hw + 3) >> 2;
   const bool vec = (hw & 3) == 0;
@@ -92,13 +106,13 @@ metrics_pass1_kernel(const float* __restrict__ sr, const float* __restrict__ hr,
       const float4 h4 = __ldg(reinterpret_cast<const float4*>(hr + p));
       const float4 o4 = __ldg(reinterpret_cast<const float4*>(orig + p));
       const float4 m4 = __ldg(reinterpret_cast<const float4*>(mask + p));
-      acc_pixel(a, s4.x, h4.x, o4.x, m4.x, dscale_inv, dmin, zs, zmean, zstd);
-      acc_pixel(a, s4.y, h4.y, o4.y, m4.y, dscale_inv, dmin, zs, zmean, zstd);
-      acc_pixel(a, s4.z, h4.z, o4.z, m4.z, dscale_inv, dmin, zs, zmean, zstd);
-      acc_pixel(a, s4.w, h4.w, o4.w, m4.w, dscale_inv, dmin, zs, zmean, zstd);
+      acc_pixel<T>(a, s4.x, h4.x, o4.x, m4.x, dscale, dmin, zmean, zstd);
+      acc_pixel<T>(a, s4.y, h4.y, o4.y, m4.y, dscale, dmin, zmean, zstd);
+      acc_pixel<T>(a, s4.z, h4.z, o4.z, m4.z, dscale, dmin, zmean, zstd);
+      acc_pixel<T>(a, s4.w, h4.w, o4.w, m4.w, dscale, dmin, zmean, zstd);
     } else {
       for (int k = 0; k < 4 && g * 4 + k < hw; ++k)
-        acc_pixel(a, sr[p + k], hr[p + k], orig[p + k], mask[p + k], dscale_inv, dmin, zs, zmean, zstd);
+        acc_pixel<T>(a, sr[p + k], hr[p + k], orig[p + k], mask[p + k], dscale, dmin, zmean, zstd);
     }
   }
   __shared__ double sh_s[kP1Threads / 32][kSums];
@@ -106,7 +120,9 @@ metrics_pass1_kernel(const float* __restrict__ sr, const float* __restrict__ hr,
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
   for (int i = 0; i < kSums; ++i) {
-    const double v = warp_sum(static_cast<double>(a.s[i]));
+    // partial layout (kSums): 8 counts, sum|d|, sum d^2, sum t, sum t^2, smape, mape, l1, mse(normalised)
+    const double own = i < 8 ? static_cast<double>(a.cnt[i]) : i < 13 ? static_cast<double>(a.s[i - 8]) : static_cast<double>(a.sn[i - 13]);
+    const double v = warp_sum(own);
     if (lane == 0) sh_s[warp][i] = v;
   }
 #pragma unroll
@@ -274,7 +290,8 @@ metrics_final_kernel(const double* __restrict__ totals, const double* __restrict
   if (threadIdx.x != 0) return;
   const double ssim = sh[0];
   const double* t = totals;
-  for (int k = 0; k < 8; ++k) out[k] = static_cast<float>(t[k] / n_pix);             // RegressionAccuracy.compute
+  // RegressionAccuracy.compute: correct.float() / total - a float32 division of the rounded int64 counters
+  for (int k = 0; k < 8; ++k) out[k] = __fdiv_rn(static_cast<float>(t[k]), static_cast<float>(n_pix));
   const double mse = t[9] / n_pix;
   const double tmin = fmin(t[kSums + 0], 0.0), tmax = fmax(t[kSums + 1], 0.0);       // PSNR states start at 0.0
   const double range = tmax - tmin;
@@ -307,11 +324,16 @@ size_t metrics_scratch_bytes(int n, int h, int w) {
   return static_cast<size_t>(bpi) * n * kPart * 8 + kPart * 8 + 64 + (ssim_blocks > 0 ? ssim_blocks : 1) * 8 + 256;
 }
 
-cudaError_t launch_masked_metrics(const float* sr, const float* hr, const float* orig, const float* mask, const float* mn, const float* mx,
-                                  float zmean, float zstd, float ra, float rb, int n, int h, int w, float* out, void* scratch,
+cudaError_t launch_masked_metrics(const float* sr, const float* hr, const float* orig, const float* mask, const double* mn, const double* mx,
+                                  float zmean, float zstd, double ra, double rb, double eps, int n, int h, int w, float* out, void* scratch,
                                   cudaStream_t s, int* launches) {
-  static bool gauss_ready = false;
-  if (!gauss_ready) {
+  // __constant__ memory is per device: upload the window once per device
+  static bool gauss_ready[64] = {};
+  int dev = 0;
+  cudaError_t ed = cudaGetDevice(&dev);
+  if (ed != cudaSuccess) return ed;
+  if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+  if (!gauss_ready[dev]) {
     // torchmetrics _gaussian: exp(-(d/sigma)^2/2) normalised, d = -5..5, sigma = 1.5
     float g[11];
     double sum = 0;
@@ -319,7 +341,7 @@ cudaError_t launch_masked_metrics(const float* sr, const float* hr, const float*
     for (int i = 0; i < 11; ++i) g[i] = static_cast<float>(g[i] / sum);
     cudaError_t e = cudaMemcpyToSymbol(c_gauss, g, sizeof(g));
     if (e != cudaSuccess) return e;
-    gauss_ready = true;
+    gauss_ready[dev] = true;
   }
   const long hw = static_cast<long>(h) * w;
   const int bpi = p1_blocks_per_image(n, hw);
@@ -330,7 +352,8 @@ cudaError_t launch_masked_metrics(const float* sr, const float* hr, const float*
   double* totals = partials + static_cast<long>(bpi) * n * kPart;
   float* c12 = reinterpret_cast<float*>(totals + kPart);
   double* ssim_part = reinterpret_cast<double*>(reinterpret_cast<uint8_t*>(c12) + 64);
-  metrics_pass1_kernel<<<dim3(bpi, n), kP1Threads, 0, s>>>(sr, hr, orig, mask, mn, mx, zmean, zstd, ra, rb, hw, partials);
+  if (mn) metrics_pass1_kernel<double><<<dim3(bpi, n), kP1Threads, 0, s>>>(sr, hr, orig, mask, mn, mx, zmean, zstd, ra, rb, eps, hw, partials);
+  else metrics_pass1_kernel<float><<<dim3(bpi, n), kP1Threads, 0, s>>>(sr, hr, orig, mask, mn, mx, zmean, zstd, ra, rb, eps, hw, partials);
   metrics_reduce1_kernel<<<1, 256, 0, s>>>(partials, bpi * n, totals, c12);
   ssim_kernel<<<dim3(gx, gy, n), 256, 0, s>>>(sr, hr, mask, h, w, c12, ssim_part);
   metrics_final_kernel<<<1, 256, 0, s>>>(totals, ssim_part, ssim_blocks, static_cast<double>(hw) * n,

@@ -215,11 +215,14 @@ int launch_wgrad_tc(const WgradParams& p, const CUtensorMap& tx0, const CUtensor
                     int num_sms, cudaStream_t stream) {
   const size_t smem = wgrad_smem_bytes(p);
   if (smem > 232448) return static_cast<int>(cudaErrorInvalidValue);
-  static bool configured = false;
-  if (!configured) {
+  // the attribute is per device: one process may drive several GPUs
+  static bool configured[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return static_cast<int>(cudaErrorInvalidDevice);
+  if (!configured[dev]) {
     cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
     if (e != cudaSuccess) return static_cast<int>(e);
-    configured = true;
+    configured[dev] = true;
   }
   const int grid = p.n_parts;
   wgrad_tc_kernel<<<grid, kWgradThreads, smem, stream>>>(p, tx0, tx1, tg0, tg1);

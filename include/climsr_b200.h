@@ -20,7 +20,7 @@
  *        <- the generator state_dict (names/shapes/order)     esrgan.py:72-87, srcnn.py:9-11
  *   csr_conv2d_nhwc
  *        <- one nn.Conv2d + LeakyReLU/ReLU/residual call site esrgan.py:33-38,90-100
- *   csr_masked_metrics / csr_ssim
+ *   csr_masked_metrics
  *        <- common_val_test_step + compute_metrics            climsr/core/task.py:262-300,342-380
  *           RegressionAccuracy.update/compute                 climsr/metrics/regression_accuracy.py:15-22
  *           MinMaxScaler._denormalize / StandardScaler        climsr/data/normalization.py:63-84,115
@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define CSR_ABI_VERSION 1
+#define CSR_ABI_VERSION 2
 
 typedef enum CsrStatus {
   CSR_OK = 0,
@@ -201,8 +201,11 @@ int     csr_mse_loss(const float* sr, const float* hr, float* grad, int64_t nume
                      void* scratch, size_t scratch_bytes, void* stream);
 
 /* ---- masked loss + metrics (one fused HBM pass + SSIM pass) ----------------------------------
- * sr, hr, original, mask: fp32 (N,1,H,W).  mn/mx: fp32 (N) per-sample min/max (min-max scaler) or
- * NULL with zmean/zstd used instead (z-score).  out: CSR_NUM_METRICS floats (device), see enum.   */
+ * sr, hr, original, mask: fp32 (N,1,H,W).  mn/mx: FLOAT64 (N) per-sample min/max (min-max scaler: the
+ * reference's batch["min"] / batch["max"] are float64 tensors, so MinMaxScaler._denormalize promotes the
+ * denormalised tensor - and every metric on it, the |p-t| <= eps counts included - to float64; the kernel
+ * does the same, with the scaler's range (a, b) and eps, normalization.py:70-82), or NULL with zmean/zstd
+ * used instead (z-score: float32, normalization.py:115).  out: CSR_NUM_METRICS floats (device), see enum. */
 enum {
   CSR_M_ACC_0_1 = 0, CSR_M_ACC_0_25, CSR_M_ACC_0_5, CSR_M_ACC_0_75, CSR_M_ACC_1, CSR_M_ACC_1_25,
   CSR_M_ACC_1_5, CSR_M_ACC_2, CSR_M_PSNR, CSR_M_SSIM, CSR_M_MAE, CSR_M_MSE, CSR_M_RMSE, CSR_M_MAPE,
@@ -210,8 +213,8 @@ enum {
 };
 size_t  csr_metrics_scratch_bytes(int32_t n, int32_t h, int32_t w);
 int     csr_masked_metrics(const float* sr, const float* hr, const float* original, const float* mask,
-                           const float* mn, const float* mx, float zmean, float zstd,
-                           float range_a, float range_b, int32_t n, int32_t h, int32_t w,
+                           const double* mn, const double* mx, float zmean, float zstd,
+                           double range_a, double range_b, double eps, int32_t n, int32_t h, int32_t w,
                            float* out, void* scratch, size_t scratch_bytes, void* stream);
 
 /* ---- inference pre / post-processing on device -------------------------------------------

@@ -19,6 +19,10 @@ Fixtures
   gen_default_seeded.npz- class default (nb=23, gc=32, in=4), same recipe, smaller raster.
   normalization.npz     - the reference's MinMaxScaler.normalize / .denormalize (+ NaN land mask) on seeded rasters.
   lr_input.npz          - numpy flips / rot90 + cv2 INTER_NEAREST resize (the arithmetic behind climate_dataset.py:152-172).
+  gen_fulldepth.npz     - reference outputs at the BASELINE configs' own tile sizes and FULL depth: two cfg2 tiles (in=4, 64x64 LR,
+                          nb=11, gc=16; default and "trained-like" gain), one cfg4 Europe raster (in=3, 113x113 LR) and one
+                          class-default (nb=23, gc=32) 64x64 tile.  These exercise multi-window rows, two-tile windows with ragged
+                          last rows and all 33 / 69 in-place concat-buffer rotations, which the 16x16 fixtures never do.
   discriminator.npz     - the reference Discriminator (default init, seed 0, train mode) + relativistic GAN losses.
 """
 from __future__ import annotations
@@ -98,6 +102,30 @@ def seeded(name, in_ch, nb, gc, n, h, w):
 
 
 GAINS = {16: (1.0, 1.5, 1.8), 32: (1.0, 1.25, 1.4)}
+
+# name -> (in_ch, nb, gc, n, h, w, weight seed, input seed, gain)
+FULLDEPTH = {
+    "cfg2_default": (4, 11, 16, 2, 64, 64, 0, 41, 1.0),
+    "cfg2_trained": (4, 11, 16, 2, 64, 64, 0, 41, 1.5),
+    "cfg4_trained": (3, 11, 16, 1, 113, 113, 5, 43, 1.5),
+    "default64_trained": (4, 23, 32, 1, 64, 64, 7, 45, 1.25),
+}
+
+
+def fulldepth():
+    blob = {}
+    for name, (in_ch, nb, gc, n, h, w, wseed, iseed, gain) in FULLDEPTH.items():
+        sd = synth.make_state_dict(in_ch, 1, 64, nb, gc, seed=wseed, gain=gain)
+        net = ESRGANGenerator(in_channels=in_ch, out_channels=1, nf=64, nb=nb, gc=gc, scale_factor=4).eval()
+        net.load_state_dict(sd, strict=True)
+        x, elev, mask = synth.make_inputs(n, in_ch, h, w, seed=iseed, blocky_mask=name.startswith("cfg4"))
+        with torch.no_grad():
+            sr = net(x, elev, mask)
+        blob[name] = sr.numpy()
+        blob[name + "_meta"] = np.array([in_ch, nb, gc, n, h, w, wseed, iseed], dtype=np.int64)
+        blob[name + "_gain"] = np.array(gain)
+        print("fulldepth", name, sr.shape, "std", float(sr.std()), "absmax", float(sr.abs().max()))
+    np.savez_compressed(os.path.join(OUT, "gen_fulldepth.npz"), **blob)
 
 
 def normalization():
@@ -204,6 +232,9 @@ if __name__ == "__main__":
     if "--discriminator-only" in sys.argv:
         discriminator()
         sys.exit(0)
+    if "--fulldepth-only" in sys.argv:
+        fulldepth()
+        sys.exit(0)
     tiny_refinit()
     normalization()
     lr_input()
@@ -211,3 +242,4 @@ if __name__ == "__main__":
     if "--tiny-only" not in sys.argv:
         seeded("gen_hydra_seeded", 4, 11, 16, 2, 16, 16)
         seeded("gen_default_seeded", 4, 23, 32, 1, 12, 12)
+        fulldepth()

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     for s in _declared_symbols():
         assert hasattr(raw, s), f"{s} declared in include/climsr_b200.h but not exported"
     assert set(_declared_symbols()) == set(_lib.EXPORTS)
-    assert _lib.lib.csr_abi_version() == 1
+    assert _lib.lib.csr_abi_version() == 2
 
 
 def test_layer_table_matches_reference_state_dict_order():

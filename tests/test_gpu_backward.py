@@ -150,6 +150,91 @@ def test_training_step_semantics():
     assert losses[-1] < losses[0]                      # the step actually descends
 
 
+@pytest.mark.parametrize("fused", [True, False])
+def test_inference_after_optimizer_step_uses_the_updated_weights(fused):
+    """torch.optim.AdamW(fused=True).step() updates parameters WITHOUT bumping ``p._version``, the key of the
+    inference pack cache.  Sequence of a Lightning epoch: training forward/backward, optimizer step, then validation in eval()
+    / no_grad.  The eval forward must run on the updated weights: bit-identical to a forced repack and to a fresh module
+    loaded from the updated state_dict, and within tolerance of the oracle on those weights."""
+    from climsr_b200.models import ESRGANGenerator
+    from oracle import generator as og
+    torch.manual_seed(0)
+    net = ESRGANGenerator(3, 1, 64, 1, 16).cuda().train()
+    g = torch.Generator().manual_seed(3)
+    x = (torch.rand((2, 3, 12, 12), generator=g) * 2 - 1).cuda()
+    elev = torch.rand((2, 1, 48, 48), generator=g).cuda()
+    mask = (torch.rand((2, 1, 48, 48), generator=g) > 0.3).float().cuda()
+    hr = (torch.rand((2, 1, 48, 48), generator=g) * 2 - 1).cuda()
+    opt = torch.optim.AdamW(net.parameters(), lr=5e-3, fused=fused)
+    with torch.no_grad():
+        before = net(x, elev, mask).clone()                       # fills the inference pack cache
+    for step in range(2):
+        opt.zero_grad()
+        F.l1_loss(net(x, elev, mask), hr).backward()
+        if step == 1:
+            # GAN pattern (pl_gan.py:41-61): a frozen-generator forward between backward and the optimizer step
+            for p in net.parameters():
+                p.requires_grad_(False)
+            with torch.no_grad():
+                _ = net(x, elev, mask)
+            for p in net.parameters():
+                p.requires_grad_(True)
+        opt.step()
+    net.eval()
+    with torch.no_grad():
+        after = net(x, elev, mask).clone()
+        net.packed_weights(force=True)
+        forced = net(x, elev, mask).clone()
+    assert not torch.equal(before, after)
+    assert torch.equal(after, forced)
+    fresh = ESRGANGenerator(3, 1, 64, 1, 16)
+    fresh.load_state_dict({k: v.detach().cpu() for k, v in net.state_dict().items()})
+    fresh = fresh.cuda().eval()
+    with torch.no_grad():
+        assert torch.equal(fresh(x, elev, mask), after)
+        want = og.generator_forward({k: v.detach().cpu() for k, v in net.state_dict().items()}, x.cpu(), elev.cpu(), mask.cpu())
+    assert float((after.cpu() - want).abs().max()) <= 1e-2
+    # behind-autograd updates need the explicit mark
+    with torch.no_grad():
+        net.conv_last.bias.data.add_(0.5)
+        net.mark_weights_dirty()
+        moved = net(x, elev, mask)
+    assert float((moved - after).abs().max()) > 1e-3
+
+
+def test_plan_cache_eviction_never_frees_a_live_training_plan():
+    """with four cached plans a fifth shape used to destroy every plan, the training plan of a live autograd node
+    included.  Now the least recently used inference plan goes and the backward still runs (and matches an undisturbed one)."""
+    import copy
+    from climsr_b200.models import ESRGANGenerator
+    torch.manual_seed(0)
+    net = ESRGANGenerator(3, 1, 64, 1, 16).cuda().train()
+    g = torch.Generator().manual_seed(5)
+    mk = lambda n, h, w: ((torch.rand((n, 3, h, w), generator=g) * 2 - 1).cuda(), torch.rand((n, 1, 4 * h, 4 * w), generator=g).cuda(),  # noqa: E731
+                          (torch.rand((n, 1, 4 * h, 4 * w), generator=g) > 0.3).float().cuda())
+    x, elev, mask = mk(2, 12, 12)
+    F.l1_loss(net(x, elev, mask), torch.zeros((2, 1, 48, 48), device="cuda")).backward()
+    ref = {k: p.grad.clone() for k, p in net.named_parameters()}
+    net.zero_grad()
+    out = net(x, elev, mask)
+    with torch.no_grad():
+        for (n, h, w) in ((1, 8, 8), (1, 9, 9), (1, 10, 10), (1, 11, 11), (1, 12, 13), (1, 13, 12)):
+            net(*mk(n, h, w))
+    assert len(net._plans) <= 4
+    F.l1_loss(out, torch.zeros((2, 1, 48, 48), device="cuda")).backward()
+    for k, p in net.named_parameters():
+        scale = float(ref[k].abs().max()) + 1e-12
+        assert float((p.grad - ref[k]).abs().max()) <= 2e-5 * scale, k
+    # deep copies (EMA / SWA shadows) own their plans
+    twin = copy.deepcopy(net).eval()
+    assert twin._plans == {} and twin._packed is None
+    with torch.no_grad():
+        a = twin(x, elev, mask)
+        b = net.eval()(x, elev, mask)
+    assert torch.equal(a, b)
+    del twin
+
+
 def test_atomic_and_deterministic_weight_gradient_accumulation_agree():
     """Option 25: weight-gradient partial sums through red.global.add.v4.f32 (default) against the deterministic per-CTA
     slices + tree reduce.  Same products, different summation order over CTAs: equal to fp32 rounding."""

@@ -249,6 +249,56 @@ def test_generator_matches_reference_golden_seeded(golden_dir, name):
             assert err <= GEN_TOL, (tag, err)
 
 
+def _fulldepth_case(golden_dir, name):
+    from oracle import synth
+    z = np.load(os.path.join(golden_dir, "gen_fulldepth.npz"))
+    in_ch, nb, gc, n, h, w, wseed, iseed = (int(v) for v in z[name + "_meta"])
+    sd = synth.make_state_dict(in_ch, 1, 64, nb, gc, seed=wseed, gain=float(z[name + "_gain"]))
+    x, elev, mask = synth.make_inputs(n, in_ch, h, w, seed=iseed, blocky_mask=name.startswith("cfg4"))
+    return sd, x, elev, mask, (in_ch, nb, gc), torch.from_numpy(z[name])
+
+
+@pytest.mark.parametrize("name", ["cfg2_default", "cfg2_trained", "cfg4_trained", "default64_trained"])
+def test_generator_matches_reference_golden_fulldepth(golden_dir, name):
+    """FULL-depth outputs of the unmodified reference module at the BASELINE configs' own tile sizes: two cfg2 tiles (4x64x64 LR,
+    nb=11, gc=16: multi-window rows, two-tile windows, 33 in-place concat rotations), the cfg4 Europe raster (3x113x113: ragged
+    last windows) and a class-default (nb=23, gc=32) 64x64 tile, at default and "trained-like" weight gains."""
+    sd, x, elev, mask, (in_ch, nb, gc), want = _fulldepth_case(golden_dir, name)
+    got = _run_generator(sd, x, elev, mask, in_ch, nb, gc)
+    assert got.shape == want.shape
+    err = float((got - want).abs().max())
+    assert err <= GEN_TOL, (name, err)
+
+
+def test_cfg5_chain_generator_then_masked_metrics_matches_reference_sr(golden_dir):
+    """BASELINE cfg5 end to end: the masked validation metrics of the CUDA generator's output (CUDA metric kernels) against the
+    same metrics of the REFERENCE module's output (oracle metric restatement, float64) for the same hr / original / mask:
+    PSNR within 0.01 dB, SSIM within 1e-4 (north_star), the remaining means within 1e-3 relative."""
+    from climsr_b200._lib import METRIC_KEYS
+    from climsr_b200.metrics import masked_val_metrics_raw
+    from oracle import metrics as om
+    from oracle import synth
+    sd, x, elev, mask, (in_ch, nb, gc), sr_ref = _fulldepth_case(golden_dir, "cfg4_trained")
+    t = synth.make_targets(sr_ref, seed=4)
+    mn, mx = t["min"].double(), t["max"].double()
+    orig = om.denormalized_original(t["hr"].double(), mn, mx).float()
+    want = om.val_test_step(sr_ref, t["hr"], orig, mask, mn, mx, loss="l1")
+    from climsr_b200.models import ESRGANGenerator
+    net = ESRGANGenerator(in_ch, 1, 64, nb, gc)
+    net.load_state_dict(sd)
+    net = net.cuda().eval()
+    with torch.no_grad():
+        sr = net(x.cuda(), elev.cuda(), mask.cuda())
+        got = masked_val_metrics_raw(sr, t["hr"].cuda(), orig.cuda(), mask.cuda(), mn.cuda(), mx.cuda()).cpu()
+    v = {k: float(got[i]) for i, k in enumerate(METRIC_KEYS)}
+    assert 20.0 < float(want["psnr"]) < 50.0                      # a realistic operating point, not a degenerate one
+    assert abs(v["psnr"] - float(want["psnr"])) <= 0.01
+    assert abs(v["ssim"] - float(want["ssim"])) <= 1e-4
+    for k in ("mae", "mse", "rmse", "mape", "smape", "r2"):
+        assert abs(v[k] - float(want[k])) <= 1e-3 * max(1.0, abs(float(want[k]))), k
+    assert abs(v["l1_loss"] - float(want["loss"])) <= 1e-3 * max(1e-3, float(want["loss"]))
+
+
 @pytest.mark.parametrize("n,in_ch,h,w", [(1, 3, 113, 113), (16, 4, 32, 32), (3, 4, 20, 36), (1, 1, 9, 7)])
 def test_generator_matches_oracle_shapes(n, in_ch, h, w):
     """cfg4 (Europe extent 113x113, in=3), cfg1 (16x32x32, in=4), ragged and tiny rasters vs the oracle (Hydra cfg, nb cut to 2
@@ -333,15 +383,18 @@ def test_masked_metrics_match_oracle(n, H, W, blocky):
         mask = (F.interpolate(low, size=(H, W), mode="nearest") > 0.3).float()
     else:
         mask = (torch.rand(n, 1, H, W, generator=g) > 0.3).float()
-    orig = om.denormalized_original(t["hr"], t["min"], t["max"])
-    want = om.val_test_step(sr, t["hr"], orig, mask, t["min"], t["max"], loss="l1")
-    want_mse = om.val_test_step(sr, t["hr"], orig, mask, t["min"], t["max"], loss="mse")["loss"]
-    got = masked_val_metrics_raw(sr.cuda(), t["hr"].cuda(), orig.cuda(), mask.cuda(), t["min"].cuda(), t["max"].cuda()).cpu()
+    # batch["min"] / batch["max"] are float64 (N,) tensors in the reference; "original" is the float32 raster of the dataset
+    mn, mx = t["min"].double() + 0.1234567891234, t["max"].double() - 0.9876543219876
+    orig = om.denormalized_original(t["hr"].double(), mn, mx).float()
+    want = om.val_test_step(sr, t["hr"], orig, mask, mn, mx, loss="l1")
+    want_mse = om.val_test_step(sr, t["hr"], orig, mask, mn, mx, loss="mse")["loss"]
+    got = masked_val_metrics_raw(sr.cuda(), t["hr"].cuda(), orig.cuda(), mask.cuda(), mn.cuda(), mx.cuda()).cpu()
     for i, k in enumerate(METRIC_KEYS):
         ref = float(want["loss"]) if k == "l1_loss" else float(want_mse) if k == "mse_loss" else float(want[k])
         if k.startswith("acc@"):
-            # counts are integers; a pixel whose |error| sits within fp32 round-off of eps may flip
-            assert abs(float(got[i]) - ref) * n * H * W <= 3, k
+            # integer counts: EXACT (the kernel denormalises in float64 with the reference's operation order and a true division)
+            assert round(float(got[i]) * n * H * W) == round(ref * n * H * W), k
+            assert float(got[i]) == float(torch.tensor(ref, dtype=torch.float64).float()), k
         elif k == "psnr":
             assert abs(float(got[i]) - ref) <= 0.01, k
         elif k == "ssim":

@@ -95,3 +95,40 @@ def test_gradient_bucketer_layout_is_reverse_parameter_order():
     assert len(flat) == len(params) and all(a is c for a, c in zip(flat, reversed(params)))
     assert sum(b.bucket_bytes()) == 2 * sum(p.numel() for p in params)
     assert all(nbytes <= 0.25 * (1 << 20) or len(bucket) == 1 for nbytes, bucket in zip(b.bucket_bytes(), b.buckets))
+
+
+def test_derived_device_state_is_never_copied_or_pickled():
+    """copy.deepcopy / torch.save of the module must not duplicate raw CsrPlan* handles or packed blobs."""
+    import copy
+    import io
+    from climsr_b200.models import ESRGANGenerator
+    net = ESRGANGenerator(4, 1, 64, 2, 16)
+    net._plans[(1, 2, 3)] = (0, None)          # a null handle: csr_plan_destroy(NULL) is a no-op
+    net._packed_key = ("x",)
+    twin = copy.deepcopy(net)
+    assert twin._plans == {} and twin._packed_key is None and twin._ordered_cache is None
+    assert all(torch.equal(a, b) for a, b in zip(net.state_dict().values(), twin.state_dict().values()))
+    assert all(a.data_ptr() != b.data_ptr() for a, b in zip(net.parameters(), twin.parameters()))
+    buf = io.BytesIO()
+    torch.save(net, buf)
+    buf.seek(0)
+    back = torch.load(buf, weights_only=False)
+    assert back._plans == {} and back._packed is None and back.nb == 2
+    net._plans.clear()
+
+
+def test_optimizer_steps_invalidate_the_pack_cache_key():
+    """Fused optimizers do not bump parameter version counters; a process-wide optimizer post-step hook bumps the epoch that is
+    part of the pack-cache key (climsr_b200/models/esrgan.py)."""
+    from climsr_b200.models import ESRGANGenerator
+    from climsr_b200.models import esrgan as E
+    net = ESRGANGenerator(4, 1, 64, 1, 16)
+    for p in net.parameters():
+        p.grad = torch.zeros_like(p)
+    for opt in (torch.optim.AdamW(net.parameters(), lr=1e-3), torch.optim.SGD(net.parameters(), lr=1e-3)):
+        e0 = E._WEIGHT_EPOCH[0]
+        opt.step()
+        assert E._WEIGHT_EPOCH[0] == e0 + 1
+    assert net._dirty is False
+    net.mark_weights_dirty()
+    assert net._dirty is True

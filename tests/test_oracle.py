@@ -51,6 +51,22 @@ def test_seeded_configs_match_reference(golden_dir, name):
         assert np.abs(sr.numpy() - ref).max() <= 2e-5 * max(1.0, np.abs(ref).max())
 
 
+@pytest.mark.parametrize("name", ["cfg2_default", "cfg2_trained", "cfg4_trained", "default64_trained"])
+def test_fulldepth_configs_match_reference(golden_dir, name):
+    """Full-depth outputs of the UNMODIFIED reference module at the BASELINE configs' own tile sizes (oracle/make_golden.py
+    fulldepth()): two cfg2 tiles (64x64 LR, nb=11), the cfg4 Europe raster (113x113, in=3) and a class-default 64x64 tile."""
+    from oracle import generator as og
+    from oracle import synth
+    z = np.load(os.path.join(golden_dir, "gen_fulldepth.npz"))
+    in_ch, nb, gc, n, h, w, wseed, iseed = (int(v) for v in z[name + "_meta"])
+    sd = synth.make_state_dict(in_ch, 1, 64, nb, gc, seed=wseed, gain=float(z[name + "_gain"]))
+    x, elev, mask = synth.make_inputs(n, in_ch, h, w, seed=iseed, blocky_mask=name.startswith("cfg4"))
+    with torch.no_grad():
+        got = og.generator_forward(sd, x, elev, mask).numpy()
+    assert got.shape == z[name].shape
+    assert np.abs(got - z[name]).max() <= 2e-5 * max(1.0, np.abs(z[name]).max())
+
+
 def test_numpy_restatement_agrees_with_torch_graph():
     sd = synth.make_state_dict(3, 1, 64, 1, 16, seed=3)
     x, elev, mask = synth.make_inputs(1, 3, 6, 5, seed=7)
