@@ -15,6 +15,7 @@
 #include "elementwise.cuh"
 #include "loss.cuh"
 #include "metrics.cuh"
+#include "rdb_tc.cuh"
 #include "wgrad_tc.cuh"
 
 namespace csr {
@@ -24,6 +25,8 @@ static thread_local char g_err[512] = "";
 static std::atomic<long long> g_launches{0};
 static int g_opt_pdl = 1;
 static long long* g_trace = nullptr;
+static unsigned long long* g_timeline = nullptr;   // csr_debug_set_timeline
+static int g_timeline_cap = 0;
 static int g_opt_force_sw = 0;
 static int g_opt_max_slots = 8;
 static int g_opt_no_tma_store = 0;
@@ -40,6 +43,9 @@ static int g_opt_narrow_box = 1;        // 16- / 32-channel window boxes for lay
 static int g_opt_regroup = 0;           // dense blocks regrouped by source in the forward (see fwd_exec_table): -3 % alone, but the plain
                                         // layout gains more from two-tile windows (5.76 vs 5.85 ms), so it is off by default
 static int g_opt_trace_cta = 0;         // debug: CTA recorded by csr_debug_set_trace
+static int g_dbg_dense = 0;             // DenseParams::dbg (timing experiments)
+static int g_opt_dense = 1;             // conv1..conv4 of every gc = 16 dense block as ONE persistent launch with tile-level dependencies (rdb_tc.cu)
+static int g_opt_early = 1;             // early-release epilogue for wide residual-free layers (conv_tc.cu, EARLY_T)
 static int g_opt_pair = 0;              // CTA-pair (cta_group::2) launches for 3x3 layers with >= 96 KB of weights.  Measured (cfg2): MMAs run at the
                                         // 108 clk/MMA pair rate instead of ~140, but two SMs in lock-step on two accumulators expose the epilogue:
                                         // 6.11 vs 5.90 ms per step, so it stays off by default
@@ -294,6 +300,14 @@ struct ConvLaunch {
   CUtensorMap tmap;
   size_t w_off = 0, b_off = 0;  // offsets into the packed blob (resolved at forward time)
   bool final_out = false;       // fp32-planar output that IS the caller's `out` tensor
+  int dense = -1;               // >= 0: this entry stands for a whole dense-block launch (CsrPlan::dense[dense]), not a conv
+};
+
+// conv1..conv4 of one dense block as one launch (rdb_tc.cu)
+struct DenseLaunch {
+  DenseParams p;
+  CUtensorMap tmap;
+  size_t w_off[kDenseMaxLayers], b_off[kDenseMaxLayers];   // offsets into the packed blob (resolved at forward time)
 };
 
 enum OutKind { kOutBf16 = 0, kOutF32Planar = 1, kOutF32Nhwc = 2 };
@@ -396,6 +410,29 @@ static int build_conv(const PackLayer& pl, const PackPart& pp, int N, int H, int
       p.stage_row_bytes = 0;
     }
   }
+  // final activation code of this part (act_upto splits a LeakyReLU over the output-channel parts)
+  p.act = io.act;
+  if (io.act_upto > 0 && io.act == CSR_ACT_LRELU02) {
+    const int upto = io.act_upto - pp.co_lo;               // in this part's channels
+    if (upto <= 0) p.act = CSR_ACT_NONE;
+    else if (upto < pp.n_store) { p.act = 3; p.act_upto = upto; }
+  }
+  p.n_stage = p.n_groups;
+  // Early-release epilogue (conv_tc.cu, EARLY_T): wide residual-free layers that run with one 16-warp group.  Two staging
+  // buffers; KW <= 2 layers also get four accumulator buffers (4 x KW x 64 <= 512 TMEM columns).
+  if (g_opt_early && !p.pair && !p.tall_shift && tma_out && p.n_groups == 1 && res_bits == 0 && p.npad == 64 && pp.n_store == 64 &&
+      !g_opt_force_generic &&
+      ((p.KW == 3 && p.PW == 1 && (p.act == 0 || p.act == 1 || p.act == 3)) || (p.KW == 2 && p.PW <= 1 && p.act == 1) ||
+       (p.KW == 1 && p.PW == 0 && p.act == 2))) {
+    Tiling te;
+    if (choose_tiling(H, W, pp.kh, pp.kw, p.w_bytes, p.n_kblocks, p.stage_row_bytes, 2, &te, p.box_c * 2) == CSR_OK &&
+        te.n_slots >= std::min(2, p.n_kblocks + 1)) {
+      tl = te;
+      p.early = 1;
+      p.n_stage = 2;
+      if (4 * p.KW * p.npad <= 512 && !g_opt_two_acc) p.n_acc = 4;
+    }
+  }
   p.SW = tl.SW; p.TH = tl.TH; p.TW = tl.TW;
   p.sw_shift = 0;
   while ((1 << p.sw_shift) < p.SW) ++p.sw_shift;
@@ -419,12 +456,6 @@ static int build_conv(const PackLayer& pl, const PackPart& pp, int N, int H, int
   p.trace_cta = g_opt_trace_cta;
   p.use_pdl = g_opt_pdl;
   p.force_generic = g_opt_force_generic;
-  p.act = io.act;
-  if (io.act_upto > 0 && io.act == CSR_ACT_LRELU02) {
-    const int upto = io.act_upto - pp.co_lo;               // in this part's channels
-    if (upto <= 0) p.act = CSR_ACT_NONE;
-    else if (upto < pp.n_store) { p.act = 3; p.act_upto = upto; }
-  }
   p.r1_pre = io.r1 ? io.r1_pre : 0;
   p.s1 = io.s1; p.s2 = io.s2;
   p.r1 = io.r1; p.r1_C = io.r1_C; p.r1_coff = io.r1_coff + pp.co_lo;
@@ -610,7 +641,14 @@ struct CsrPlan {
   int sms;
   int train = 0;
   std::vector<csr::ConvLaunch> convs;   // forward, in execution order
+  std::vector<csr::DenseLaunch> dense;  // dense-block launches referenced by convs[i].dense
+  unsigned int* flags = nullptr;        // completion counters of the dense-block launches (zeroed at the start of every forward)
+  size_t flags_bytes = 0;
   int idx_srcnn1;                       // the SRCNN x-im2col pack kernel runs right before this conv
+  int srcnn_pitch = 64;                 // channel pitch of the SRCNN input im2col (27 -> 32 channels) and of srcnn.conv2's output (32 channels):
+                                        // 32 in inference plans - the TMA loads promote to whole 128/256-byte L2 lines, so a 64-channel
+                                        // pitch doubled the HBM reads of srcnn.conv1 and srcnn.conv3 -, 64 in training plans (the
+                                        // weight-gradient GEMMs read 64-channel boxes)
   void* xin; void* sin; float* tlast;
   size_t packed_bytes;
   // CUDA-graph replay (launch-bound batches: a forward is ~180 launches, a training step ~800): the launch sequence is
@@ -638,6 +676,7 @@ namespace csr {
 struct WsLayout {
   size_t xin, fea0, t0, m1, hrA, hrB, hrC, hrD, hrE, tlast, total;
   size_t sx, selev, smask, sout, sgout, sgrad;   // graph staging
+  size_t flags, flags_bytes;                     // dense-block completion counters
   std::vector<size_t> cat;              // 3 rotating concat buffers (inference) or one per RDB + 1 (training: saved state)
   // training only
   size_t gO, gcolB, gT, gP, gQ, gm1, gt0, gtmp, gcat[3], dacc;
@@ -659,6 +698,9 @@ static WsLayout ws_layout(const CsrNetDesc& d, int N, int h, int w, int train) {
   L.hrB = take(hr * 64 * 2);   // HRconv output
   L.hrC = take(hr * 64 * 2);   // SRCNN input [out, elev, mask] x 9 horizontal taps
   L.tlast = take(hr * 4);      // conv_last output, fp32 planar
+  // dense-block launches: one counter per (block, layer, window); windows are >= 8 rows x 14 columns
+  L.flags_bytes = (size_t)3 * d.nb * kDenseMaxLayers * N * ceil_div(h, 8) * ceil_div(w, 14) * sizeof(unsigned int);
+  L.flags = take(L.flags_bytes);
   L.sx = take(lr * d.in_channels * 4);
   L.selev = take(hr * 4);
   L.smask = take(hr * 4);
@@ -696,6 +738,45 @@ static ConvIO io_of(const void* in, int in_C, void* out, int out_C, int out_coff
   return io;
 }
 
+// conv1..conv4 of one gc = 16 dense block as one persistent launch (rdb_tc.cu).  `packs` / `li`: pack layout and the index of
+// the block's conv1 in it.  Returns CSR_ERR_UNSUPPORTED when no tile shape fits - the caller then falls back to four launches.
+static int build_dense(const std::vector<PackLayer>& packs, int li, int N, int H, int W, void* buf, int C, int nf, int gc, unsigned int* flags,
+                       DenseLaunch* dl) {
+  DenseParams& p = dl->p;
+  memset(&p, 0, sizeof(p));
+  if (gc != 16 || C % 8) return fail(CSR_ERR_UNSUPPORTED, "dense-block kernel: gc must be 16");
+  p.N = N; p.H = H; p.W = W; p.n_layers = 4; p.C = C; p.buf = buf; p.flags = flags; p.use_pdl = g_opt_pdl; p.dbg = g_dbg_dense;
+  int wmax = 0;
+  for (int k = 0; k < 4; ++k) {
+    const PackLayer& pl = packs[li + k];
+    if (pl.parts.size() != 1 || pl.parts[0].npad != 16 || pl.parts[0].kh != 3 || pl.parts[0].kw != 3 || pl.cin_pad != nf + k * gc)
+      return fail(CSR_ERR_UNSUPPORTED, "dense-block kernel: unexpected pack layout");
+    p.L[k].ksteps = pl.cin_pad / 16;
+    p.L[k].n_kblocks = ceil_div(pl.cin_pad, 64);
+    p.L[k].w_bytes = pl.parts[0].w_bytes;
+    p.L[k].out_coff = nf + k * gc;
+    dl->w_off[k] = pl.parts[0].w_off; dl->b_off[k] = pl.parts[0].b_off;
+    wmax = std::max(wmax, pl.parts[0].w_bytes);
+  }
+  p.wbuf_bytes = (int)align_up(wmax, 1024);
+  Tiling tl;
+  int rc = choose_tiling(H, W, 3, 3, 2 * p.wbuf_bytes, 2, 32, 4, &tl, 128, 2);
+  if (rc) return rc;
+  if (tl.n_slots < 3) return fail(CSR_ERR_UNSUPPORTED, "dense-block kernel: window ring too shallow");
+  p.SW = tl.SW; p.TH = tl.TH; p.TW = tl.TW;
+  while ((1 << p.sw_shift) < p.SW) ++p.sw_shift;
+  p.tiles_x = ceil_div(W, p.TW); p.tiles_y = ceil_div(H, 2 * p.TH);
+  p.tiles_per_img = p.tiles_x * p.tiles_y;
+  p.num_tiles = p.tiles_per_img * N;
+  if ((long long)p.tiles_per_img * N >= (1 << 24) || p.tiles_per_img >= (1 << 16)) return fail(CSR_ERR_UNSUPPORTED, "dense-block kernel: too many windows");
+  p.magic_img = ((1ull << 40) / (unsigned)p.tiles_per_img) + 1;
+  p.magic_row = ((1ull << 40) / (unsigned)p.tiles_x) + 1;
+  p.win_bytes = tl.win_bytes; p.slot_bytes = tl.slot_bytes; p.n_slots = std::min(tl.n_slots, 8);
+  p.stage_bytes = (int)align_up((size_t)p.TH * p.TW * 32, 1024);
+  if (dense_smem_bytes(p) > (size_t)kSmemLimit) return fail(CSR_ERR_UNSUPPORTED, "dense-block kernel needs %zu bytes of shared memory", dense_smem_bytes(p));
+  return encode_act_map(&dl->tmap, buf, N, H, W, C, p.SW, 2 * p.TH + 2, 64);
+}
+
 static int plan_build(CsrPlan* P, void* ws) {
   const CsrNetDesc& d = P->net;
   const int N = P->N, h = P->h, w = P->w;
@@ -708,6 +789,7 @@ static int plan_build(CsrPlan* P, void* ws) {
   P->xin = xin; P->sin = hrC; P->tlast = reinterpret_cast<float*>(base + L.tlast);
   P->sx = reinterpret_cast<float*>(base + L.sx); P->selev = reinterpret_cast<float*>(base + L.selev);
   P->smask = reinterpret_cast<float*>(base + L.smask); P->sout = reinterpret_cast<float*>(base + L.sout);
+  P->flags = reinterpret_cast<unsigned int*>(base + L.flags); P->flags_bytes = L.flags_bytes;
   const std::vector<LayerSpec> layers = layer_table(d);
   P->fwd_layers = layers;
   {
@@ -751,6 +833,21 @@ static int plan_build(CsrPlan* P, void* ws) {
       const int j = 3 * i + r;
       void* src = cat(j);
       void* dst = P->train ? cat(j + 1) : (r < 2 ? cat(j + 1) : cat(3 * i));
+      if (g_opt_dense && !g_opt_regroup && gc == 16 && !g_opt_force_generic) {
+        // conv1..conv4 as ONE persistent launch with tile-level dependencies between the layers (rdb_tc.cu)
+        DenseLaunch dl;
+        const size_t per_block = (size_t)kDenseMaxLayers * N * ceil_div(h, 8) * ceil_div(w, 14);
+        unsigned int* fl = P->flags + (size_t)j * per_block;
+        if (build_dense(packs, li, N, h, w, src, C, nf, gc, fl, &dl) == CSR_OK && (size_t)dl.p.num_tiles * kDenseMaxLayers <= per_block) {
+          ConvLaunch stub;
+          memset(&stub.p, 0, sizeof(stub.p));
+          stub.dense = (int)P->dense.size();
+          P->dense.push_back(dl);
+          P->convs.push_back(stub);
+          li += 4;
+          goto conv5;
+        }
+      }
       for (int k = 1; k <= 4; ++k) {
         // x_k = lrelu(conv_k(cat(x, x1..x_{k-1})))  written into its concat slice  (esrgan.py:33-36)
         ConvIO io = io_of(src, C, src, C, nf + (k - 1) * gc, CSR_ACT_LRELU02);
@@ -765,6 +862,7 @@ static int plan_build(CsrPlan* P, void* ws) {
         rc = add(h, w, io);
         if (rc) return rc;
       }
+    conv5:
       // x5*0.2 + x  (esrgan.py:37-38); RDB3 additionally applies the RRDB residual out*0.2 + x_rrdb (esrgan.py:54)
       ConvIO io = io_of(src, C, dst, C, 0, CSR_ACT_NONE);
       io.r1 = src; io.r1_C = C; io.s1 = 0.2f;
@@ -797,12 +895,14 @@ static int plan_build(CsrPlan* P, void* ws) {
     if (rc) return rc;
   }
   P->idx_srcnn1 = (int)P->convs.size();
-  rc = add(H, W, io_of(hrC, 64, hrD, 64, 0, CSR_ACT_RELU));     // srcnn.conv1 (9x1 folded)
+  P->srcnn_pitch = P->train ? 64 : 32;
+  const int sp = P->srcnn_pitch;
+  rc = add(H, W, io_of(hrC, sp, hrD, 64, 0, CSR_ACT_RELU));     // srcnn.conv1 (9x1 folded)
   if (rc) return rc;
-  rc = add(H, W, io_of(hrD, 64, hrE, 64, 0, CSR_ACT_RELU));     // srcnn.conv2 1x1
+  rc = add(H, W, io_of(hrD, 64, hrE, sp, 0, CSR_ACT_RELU));     // srcnn.conv2 1x1
   if (rc) return rc;
   {
-    ConvIO io = io_of(hrE, 64, nullptr, 1, 0, CSR_ACT_NONE);    // srcnn.conv3 5x5 -> the caller's output tensor
+    ConvIO io = io_of(hrE, sp, nullptr, 1, 0, CSR_ACT_NONE);    // srcnn.conv3 5x5 -> the caller's output tensor
     io.out_kind = kOutF32Planar;
     rc = add(H, W, io);
     if (rc) return rc;
@@ -1181,6 +1281,9 @@ int csr_set_option(int32_t key, int32_t value) {
     case 19: g_opt_eight_acc = value ? 1 : 0; return CSR_OK;
     case 20: case 21: case 22: case 23: case 24: g_dbg_wgrad[key - 20] = value; return CSR_OK;
     case 25: g_opt_wgrad_atomic = value ? 1 : 0; return CSR_OK;    // plans created afterwards
+    case 27: g_opt_dense = value ? 1 : 0; return CSR_OK;           // plans created afterwards
+    case 28: g_dbg_dense = value; return CSR_OK;
+    case 26: g_opt_early = value ? 1 : 0; return CSR_OK;           // early-release epilogue of the wide residual-free layers
     default: return fail(CSR_ERR_BAD_ARG, "unknown option key %d", key);
   }
 }
@@ -1195,6 +1298,14 @@ int csr_debug_set_trace(void* device_buffer) {
   if (!device_buffer) return CSR_OK;
   return fail(CSR_ERR_UNSUPPORTED, "this build has no pipeline tracing (rebuild with CSR_BUILD_TRACE=1 python build.py --force)");
 #endif
+}
+
+int csr_debug_set_timeline(void* device_u64, int32_t capacity_launches) {
+  // device buffer of 2 * capacity uint64 (init: even entries ~0ull, odd entries 0): forwards run with direct launches write
+  // [2i] = earliest CTA start (after the dependency wait) and [2i+1] = latest CTA end of launch i, in globaltimer ns
+  g_timeline = reinterpret_cast<unsigned long long*>(device_u64);
+  g_timeline_cap = device_u64 ? capacity_launches : 0;
+  return CSR_OK;
 }
 
 int csr_num_layers(const CsrNetDesc* net) {
@@ -1620,15 +1731,29 @@ static int forward_launches(CsrPlan* P, const void* packed, const float* x, cons
   const uint8_t* pk = reinterpret_cast<const uint8_t*>(packed);
   CSR_CUDA(launch_nchw_to_nhwc(x, P->xin, P->N, P->net.in_channels, P->h, P->w, 64, 16, s));
   ++g_launches;
+  if (!P->dense.empty()) CSR_CUDA(cudaMemsetAsync(P->flags, 0, P->flags_bytes, s));   // completion counters of the dense-block launches
   for (size_t i = 0; i < P->convs.size(); ++i) {
     if ((int)i == P->idx_srcnn1) {
-      CSR_CUDA(launch_pack_srcnn_in(P->tlast, elev, mask, P->sin, 4 * P->w, (long)P->N * P->h * P->w * 16, 64, s));
+      CSR_CUDA(launch_pack_srcnn_in(P->tlast, elev, mask, P->sin, 4 * P->w, (long)P->N * P->h * P->w * 16, P->srcnn_pitch, s));
       ++g_launches;
     }
     ConvLaunch& cl = P->convs[i];
+    if (cl.dense >= 0) {
+      DenseLaunch& dl = P->dense[cl.dense];
+      for (int k = 0; k < dl.p.n_layers; ++k) {
+        dl.p.L[k].wpk = pk + dl.w_off[k];
+        dl.p.L[k].bias = reinterpret_cast<const float*>(pk + dl.b_off[k]);
+      }
+      dl.p.timeline = ((int)i < g_timeline_cap) ? g_timeline : nullptr; dl.p.launch_id = (int)i;
+      int e = launch_dense_block(dl.p, dl.tmap, P->sms, s);
+      if (e) return fail(CSR_ERR_CUDA, "dense-block launch %zu failed: %s", i, cudaGetErrorString((cudaError_t)e));
+      ++g_launches;
+      continue;
+    }
     cl.p.wpk = pk + cl.w_off;
     cl.p.bias = reinterpret_cast<const float*>(pk + cl.b_off);
     if (cl.final_out) cl.p.out = out;
+    cl.p.timeline = ((int)i < g_timeline_cap) ? g_timeline : nullptr; cl.p.launch_id = (int)i;
     int e = launch_conv_tc(cl.p, cl.tmap, P->sms, s);
     if (e) return fail(CSR_ERR_CUDA, "conv launch %zu failed: %s", i, cudaGetErrorString((cudaError_t)e));
     ++g_launches;

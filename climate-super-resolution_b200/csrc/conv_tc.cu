@@ -137,7 +137,14 @@ __device__ __forceinline__ uint4 ldg16(const void* base, size_t pix, int C, int 
 //          M = 256 MMA for both, and each CTA keeps only HALF of the layer's weights resident (B rows [0,N/2) / [N/2,N)),
 //          which is what buys RDB conv5 (144 KB of weights) a window ring deep enough to prefetch across tiles.
 //   TALL_T 1 = two M tiles per window (ConvParams::tall_shift), compile-time so that the common kernels carry none of it
-template <int KW_T, int PW_T, int ACT_T, int RES_T, int ST_T, int PAIR_T = 0, int TALL_T = 0>
+//   EARLY_T 1 = wide residual-free layers (64 output channels, one 16-warp epilogue group): every warp pulls its WHOLE share of
+//          the accumulator (2 chunks x KW taps) into registers, hands the TMEM buffer back to the MMA warps at once and only
+//          then does the shuffle-sum / activation / staging; two staging buffers, so a tile costs one named barrier and the
+//          copy-out of tile i overlaps the accumulator loads of tile i+1.  (Round 1 measured these layers epilogue-bound:
+//          ~2450 clk per 128 x 64 tile against ~1400 clk of MMAs, because an accumulator stayed busy for the whole
+//          ~1000-clk arithmetic phase and only two of them fit TMEM; tools/tmem_probe.cu shows the TMEM read port itself
+//          delivers a 128 x 192 fp32 tile to 16 warps in ~260 clk.)
+template <int KW_T, int PW_T, int ACT_T, int RES_T, int ST_T, int PAIR_T = 0, int TALL_T = 0, int EARLY_T = 0>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
   extern __shared__ uint8_t smem_raw[];
@@ -145,7 +152,7 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t slots_addr = smem_base;
   const uint32_t stage_addr = slots_addr + static_cast<uint32_t>(p.n_slots) * p.slot_bytes;   // one staging buffer per epilogue group
-  const uint32_t w_addr = stage_addr + static_cast<uint32_t>(p.n_groups) * p.stage_bytes;
+  const uint32_t w_addr = stage_addr + static_cast<uint32_t>(p.n_stage) * p.stage_bytes;
   const uint32_t crank = PAIR_T ? cluster_ctarank() : 0u;   // rank in the CTA pair; rank 0 (leader) issues the MMAs
   const int w_local = PAIR_T ? (p.w_bytes >> 1) : p.w_bytes;  // resident weight bytes of this CTA
   const uint32_t bias_addr = w_addr + ((w_local + 127) & ~127);
@@ -230,6 +237,7 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
 
   // Everything below reads / writes activations of the previous layer(s): wait for the prerequisite grid.
   griddep_wait();
+  timeline_start(p.timeline, p.launch_id);
 
   const int ksteps_total = p.cin >> 4;
   const int nmma = KW * p.npad;                          // UMMA N: horizontal taps folded into the output columns
@@ -436,6 +444,71 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
     }
     int buf = g % NA;
     uint32_t acc_phase = 0;
+    if constexpr (EARLY_T) {
+      // One group of 16 warps, 64 output channels: warp (quadrant q, sub s) owns channels [16 s, 16 s + 16) of rows [32 q, 32 q + 32).
+      static_assert(KW_T >= 1 && KW_T <= 3 && RES_T == 0 && ST_T == 1 && PAIR_T == 0 && TALL_T == 0, "early-release epilogue: wide residual-free layers only");
+      const int ch_lo = sub * 16;
+      uint32_t sb = 0;                                    // staging buffer of this tile
+      for (int it = 0; ; ++it) {
+        const int t = blockIdx.x + it * static_cast<int>(gridDim.x);
+        if (t >= p.num_tiles) break;
+        if (tracer) CSR_TRACE(2, it, 3);
+        const Tile tl = decode_tile<0>(p, t);
+        const uint32_t t_addr = t_lane + buf * nmma + ch_lo;
+        mbar_wait(bar_acc_full(buf), acc_phase);           // the one bounded wait (see mbar_wait_spin)
+        tc_fence_after();
+        if (tracer) CSR_TRACE(2, it, 1);
+        uint32_t raw[2][KW_T][8];
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj)
+#pragma unroll
+          for (int dx = 0; dx < KW_T; ++dx) tmem_ld8(t_addr + dx * p.npad + jj * 8, raw[jj][dx]);
+        tmem_ld_wait();
+        // the accumulator now lives in registers: the MMA warps may refill the buffer while the arithmetic runs
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_acc_empty(buf));
+        if (tracer) CSR_TRACE(2, it, 0);
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj) {
+          const int ch0 = ch_lo + jj * 8;
+          float v[8];
+          {
+            const float4 b0 = *reinterpret_cast<const float4*>(bias_s + ch0);
+            const float4 b1 = *reinterpret_cast<const float4*>(bias_s + ch0 + 4);
+            v[0] = b0.x; v[1] = b0.y; v[2] = b0.z; v[3] = b0.w; v[4] = b1.x; v[5] = b1.y; v[6] = b1.z; v[7] = b1.w;
+          }
+#pragma unroll
+          for (int dx = 0; dx < KW_T; ++dx) gather_add8(v, raw[jj][dx], dx - PW_T, lane);
+          if (act == 3) {
+            if (ch0 < p.act_upto) apply_act8(v, 1);
+          } else {
+            apply_act8(v, act);
+          }
+          if (col_ok && ch0 < p.n_store)
+            st_shared_v4(srow_addr + sb * p.stage_bytes + ((static_cast<uint32_t>(ch0 >> 3) ^ swz) << 4), pack_bf16x2(v[0], v[1]),
+                         pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+        }
+        if (tracer) CSR_TRACE(2, it, 4);
+        named_bar_sync(1, gthreads);                      // the staged tile is complete (and every copy-out of tile it-1 has been issued)
+        if (tracer) CSR_TRACE(2, it, 7);
+        __nv_bfloat16* tile_out = reinterpret_cast<__nv_bfloat16*>(p.out) +
+            ((static_cast<size_t>(tl.n) * p.out_H + (tl.y0 * p.out_sy + p.out_oy)) * p.out_W + (tl.x0 * p.out_sx + p.out_ox)) * p.out_C +
+            p.out_coff;
+        const uint32_t lim = (static_cast<uint32_t>(max(0, min(p.H - tl.y0, 0x7fff))) << 16) | static_cast<uint32_t>(min(p.W - tl.x0, 0x7fff));
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {                     // <= 128 pixels x 8 pieces over 512 threads
+          const bool ok = ((pc_yx[k] >> 16) < (lim >> 16)) && ((pc_yx[k] & 0xffffu) < (lim & 0xffffu));
+          if (ok) {
+            const uint4 val = ld_shared_v4(pc_s[k] + sb * p.stage_bytes);
+            *reinterpret_cast<uint4*>(tile_out + pc_d[k]) = val;
+          }
+        }
+        if (tracer) CSR_TRACE(2, it, 2);
+        sb ^= 1u;
+        if (++buf >= NA) { buf = 0; acc_phase ^= 1; }
+      }
+    } else
     for (int it = g; ; it += NG) {                        // `it` counts M tiles; window = it >> tall_shift
       const int t = blockIdx.x + (it >> TALL_T) * static_cast<int>(gridDim.x);
       if (t >= p.num_tiles) break;
@@ -589,6 +662,7 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
 done:
   tc_fence_before();
   __syncthreads();
+  timeline_end(p.timeline, p.launch_id);
   if constexpr (PAIR_T) cluster_sync_all();              // the leader's MMAs read the peer's shared memory and TMEM until here
   if (warp == 1) {
     __syncwarp();
@@ -599,17 +673,17 @@ done:
 }
 
 size_t conv_smem_bytes(const ConvParams& p) {
-  return 1024 /*alignment slack*/ + static_cast<size_t>(p.n_slots) * p.slot_bytes + static_cast<size_t>(p.n_groups) * p.stage_bytes +
+  return 1024 /*alignment slack*/ + static_cast<size_t>(p.n_slots) * p.slot_bytes + static_cast<size_t>(p.n_stage) * p.stage_bytes +
          (((p.pair ? p.w_bytes / 2 : p.w_bytes) + 127) & ~127) + 256 /*bias*/ + 8 * (19 + 2 * p.n_slots) + 32;
 }
 
-template <int KW_T, int PW_T, int ACT_T, int RES_T, int ST_T, int PAIR_T = 0, int TALL_T = 0>
+template <int KW_T, int PW_T, int ACT_T, int RES_T, int ST_T, int PAIR_T = 0, int TALL_T = 0, int EARLY_T = 0>
 static int launch_t(const ConvParams& p, const CUtensorMap& tmap, int num_sms, cudaStream_t stream) {
   const size_t smem = conv_smem_bytes(p);
   if (smem > static_cast<size_t>(kSmemLimit)) return static_cast<int>(cudaErrorInvalidValue);
   // the attribute is per device (and per template instantiation): one process may drive several GPUs
   static bool configured[64] = {};
-  auto kern = conv_tc_kernel<KW_T, PW_T, ACT_T, RES_T, ST_T, PAIR_T, TALL_T>;
+  auto kern = conv_tc_kernel<KW_T, PW_T, ACT_T, RES_T, ST_T, PAIR_T, TALL_T, EARLY_T>;
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return static_cast<int>(cudaErrorInvalidDevice);
   if (!configured[dev]) {
@@ -674,6 +748,21 @@ int launch_conv_tc(const ConvParams& p, const CUtensorMap& tmap, int num_sms, cu
       case 3: if (p.PW == 1) return launch_t<3, 1, -1, -1, -1, 0, 1>(p, tmap, num_sms, stream);
       default: return launch_t<0, 0, -1, -1, -1, 0, 1>(p, tmap, num_sms, stream);
     }
+  }
+  if (p.early) {
+    // wide residual-free layers with the early-release epilogue (one 16-warp group, two staging buffers)
+    if (p.store_mode != kStoreStaged || res != 0 || p.n_groups != 1 || p.n_stage != 2 || p.npad != 64 || p.force_generic)
+      return static_cast<int>(cudaErrorInvalidValue);
+#define CSR_EARLY(KW_, PW_, ACT_) \
+    if (p.KW == KW_ && p.PW == PW_ && p.act == ACT_) return launch_t<KW_, PW_, ACT_, 0, 1, 0, 0, 1>(p, tmap, num_sms, stream);
+    CSR_EARLY(3, 1, 1)   // HRconv
+    CSR_EARLY(3, 1, 0)   // conv_first
+    CSR_EARLY(3, 1, 3)   // dense block regrouped by source: conv1 + the x-parts of conv2-4
+    CSR_EARLY(2, 0, 1)   // upconv sub-pixel phases
+    CSR_EARLY(2, 1, 1)
+    CSR_EARLY(1, 0, 2)   // srcnn.conv1 (x-im2col folded)
+#undef CSR_EARLY
+    return static_cast<int>(cudaErrorInvalidValue);
   }
 #define CSR_CASE(KW_, PW_, ACT_, RES_, ST_)                                                                  \
   if (p.store_mode == (ST_ == 1 ? kStoreStaged : ST_ == 3 ? kStoreF32Planar : kStoreDirect32) && !p.force_generic && p.KW == KW_ && \

@@ -45,6 +45,8 @@ struct ConvParams {
   int n_mma;       // MMA issuer warps in use (2; 1 = debug)
   int n_acc;       // accumulator buffers in TMEM (2, 4 or 8); n_acc * KW * npad <= 512
   int n_groups;    // epilogue warp groups (1, 2 or 4; n_groups divides n_acc): one staging buffer each
+  int n_stage;     // staging buffers in shared memory: n_groups, or 2 for the early-release epilogue
+  int early;       // 1 = early-release epilogue (conv_tc.cu, EARLY_T): wide residual-free layers, one 16-warp group
   int tmem_cols;   // power of two >= max(32, n_acc*KW*npad)
   int force_generic;  // debug: skip the compile-time specialised kernels
   int issue_order; // 1 = the two MMA warps take strict turns tile by tile (only meaningful with n_mma == 2)
@@ -72,6 +74,8 @@ struct ConvParams {
   int stage_row_bytes; // kStoreStaged: bytes per staged pixel (n_store * 2: 16..128)
   int stage_bytes;     // one staging buffer (TH*TW*stage_row_bytes rounded up to 1024)
   long long* trace;    // debug: per-role clock64 timestamps of CTA 0 (nullptr = off), [3 roles][64 tiles][4 events]
+  unsigned long long* timeline;   // debug (csr_debug_set_timeline): [2*launch_id] = earliest CTA start after griddepcontrol.wait,
+  int launch_id;                  // [2*launch_id + 1] = latest CTA end, in globaltimer ns - the in-situ timeline of a forward
 };
 
 // Returns cudaError_t (as int).

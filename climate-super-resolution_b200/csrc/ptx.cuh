@@ -63,6 +63,19 @@ __device__ __forceinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+// in-situ timeline of a launch sequence (debug): globaltimer stamps reduced over the CTAs of a launch
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void timeline_start(unsigned long long* tl, int id) {
+  if (tl && threadIdx.x == 0) atomicMin(tl + 2 * id, globaltimer_ns());
+}
+__device__ __forceinline__ void timeline_end(unsigned long long* tl, int id) {
+  if (tl && threadIdx.x == 0) atomicMax(tl + 2 * id + 1, globaltimer_ns());
+}
+
 // ---------------------------------------------------------------- TMA
 __device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");

@@ -99,6 +99,10 @@ int64_t     csr_kernel_launch_count(void);           /* kernels launched by this
 /* debug: device buffer of 3*64*8 int64 receiving per-role clock64 timestamps of CTA 0 for convs built afterwards
  * (NULL switches tracing off).  Layout [role: producer, mma, epilogue][tile 0..63][event 0..7].                   */
 int         csr_debug_set_trace(void* device_buffer);
+/* debug: in-situ timeline of the launches of csr_plan_forward (direct launches, no graph replay).  device_u64: 2 * capacity
+ * uint64 in device memory, even entries preset to ~0, odd entries to 0; launch i then leaves [2i] = earliest CTA start after
+ * its dependency wait and [2i+1] = latest CTA end, in globaltimer nanoseconds.  NULL switches it off. */
+int         csr_debug_set_timeline(void* device_u64, int32_t capacity_launches);
 
 /* ---- weights --------------------------------------------------------------------------------
  * Number of conv layers (== number of weight tensors) of the generator, in state_dict order.    */

@@ -165,7 +165,7 @@ def test_inference_after_optimizer_step_uses_the_updated_weights(fused):
     elev = torch.rand((2, 1, 48, 48), generator=g).cuda()
     mask = (torch.rand((2, 1, 48, 48), generator=g) > 0.3).float().cuda()
     hr = (torch.rand((2, 1, 48, 48), generator=g) * 2 - 1).cuda()
-    opt = torch.optim.AdamW(net.parameters(), lr=5e-3, fused=fused)
+    opt = torch.optim.AdamW(net.parameters(), lr=5e-4, fused=fused)
     with torch.no_grad():
         before = net(x, elev, mask).clone()                       # fills the inference pack cache
     for step in range(2):

