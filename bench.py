@@ -13,6 +13,12 @@ Workload (BASELINE.json configs[1]): Hydra generator (nf=64, nb=11, gc=16, in_ch
            / measured step time vs MEASURED_PEAKS.json bf16 peak
   cpu_baseline: the oracle port of the reference generator (oracle/generator.py, torch CPU fp32 == the reference's own
            ATen/oneDNN arithmetic) timed on this box's host cores on a bounded sample of the same workload
+  train  : generator training step (forward + L1 + backward + overlapped bf16 gradient all-reduce + fused AdamW) at cfg3
+           (batch 16 of HR 128^2 per GPU) and at the cfg2 batch, with the all-reduce time left exposed (every N)
+  halo_tiled: the global CRU-TS grid (LR 360x720 -> HR 1440x2880) as a 2-D grid of halo-padded tiles over the N GPUs, with
+           the max abs difference to the un-tiled run (BASELINE configs[3]; no collective on the data path)
+  gpu_eager_baseline (N = 1): the reference graph in stock PyTorch eager + cuDNN (bf16 autocast, channels_last,
+           cudnn.benchmark) on the same GPU - "the kernel to beat" of BASELINE.md section 4
 N > 1 (torchrun): independent tile batches per rank, no data-path collective -> "weak" scaling.
 --impl reference: times the reference's CPU implementation (oracle port; /root/reference does not exist on the GPU box).
 """
@@ -79,6 +85,8 @@ class _stdout_to_stderr:
 def init_distributed(local):
     import torch
     import torch.distributed as dist
+    from climsr_b200.parallel import configure_nccl_for_overlap
+    configure_nccl_for_overlap()          # NCCL_MAX_CTAS = the SMs the training plans leave to the collective
     with _stdout_to_stderr():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         dist.barrier()
@@ -181,8 +189,16 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-# DRAM traffic of one cfg2 forward step (all 183 launches), from the ncu pass stored as profiles/r01_dram_traffic_v4.csv
-CFG2_STEP_DRAM_BYTES = 9.72e9
+def recorded_dram_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum over ALL launches of one cfg2 forward, from this round's ncu pass
+    (profiles/r02_dram_traffic.json, written by tools/dram_traffic.py from the ncu csv of `bench.py --steps 2`)."""
+    p = os.path.join(ROOT, "profiles", "r02_dram_traffic.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return d.get("bytes_per_step"), d.get("note", "profiles/r02_dram_traffic.json")
+    return None, "no ncu DRAM pass recorded for this build"
+
 
 
 def run_ours(args):
@@ -267,7 +283,10 @@ def run_ours(args):
     fl = flops_per_hr_pixel(in_ch, 64, nb, gc)
     peaks = load_peaks()
     achieved = px_step * fl / (ms_step * 1e-3) / 1e12          # per GPU, TFLOP/s (algorithmic)
-    peak = peaks["bf16_sustained"]
+    # the timed region is steps x ~5 ms at full clocks, not a seconds-long power-limited run: the BURST figure is the honest
+    # denominator; the sustained one is kept beside it
+    peak = peaks["bf16_burst"]
+    traffic, traffic_note = recorded_dram_traffic() if args.workload == "cfg2" else (None, "recorded for cfg2 only")
     line = {
         "metric": "generator_inference_hr_mpixel_per_s", "value": value, "unit": "Mpixel/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -282,14 +301,24 @@ def run_ours(args):
         "gpu_launches": int(launches),
         "clocks": clk.summary(),
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                     "traffic": CFG2_STEP_DRAM_BYTES if args.workload == "cfg2" else None,
-                     "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum over the 183 launches of ONE cfg2 step (5.12 GB read + "
-                                     "4.60 GB written), ncu --cache-control none, profiles/r01_dram_traffic_v4.csv; a recorded constant, not "
-                                     "measured in this run",
-                     "peak_source": f"{peaks['source']} bf16_tflops_sustained (burst {peaks['bf16_burst']})",
+                     "frac_sustained": achieved / peaks["bf16_sustained"],
+                     "traffic": traffic, "traffic_note": traffic_note,
+                     "peak_source": f"{peaks['source']} bf16_tflops burst (sustained {peaks['bf16_sustained']})",
                      "flop_per_hr_pixel": fl,
-                     "note": "dominant kernel conv_tc_kernel (all conv launches of a step); algorithmic FLOPs of the whole forward / step time"},
+                     "note": "dominant kernels conv_tc_kernel / dense_block_kernel (all tensor-core launches of a step); algorithmic FLOPs of the "
+                             "whole forward / step time"},
     }
+    del pipe, net, out, last
+    torch.cuda.empty_cache()
+    if not args.no_extras:
+        # driver-visible at every N: the training step with its gradient exchange, and the halo-tiled global raster
+        tr_steps = max(5, min(args.steps, 20))
+        line["train"] = {"cfg3": train_measure("cfg3", tr_steps, 3, dev, world, rank, e2e=False),
+                         "cfg2_batch": train_measure("cfg2", max(5, tr_steps // 2), 3, dev, world, rank, e2e=False)}
+        line["halo_tiled"] = halo_measure(dev, world, rank)
+        if world == 1:
+            line["gpu_eager_baseline"] = gpu_eager_measure(args.workload, dev)
+            line["gpu_eager_baseline"]["speedup_of_this_path"] = line["gpu_eager_baseline"]["ms_per_step"] / ms_step
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         sample = 8 if h * w <= 64 * 64 else 1
         rate, threads, _ = cpu_reference_rate(in_ch, nb, gc, h, w, sample, 3)
@@ -301,35 +330,24 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def run_train(args):
+def train_measure(workload, steps, warmup, dev, world, rank, overlap=True, e2e=True):
     """Generator training step (generator part): forward on a training plan, L1 pixel loss
-    (core/task.py:141), backward (dgrad + wgrad kernels), bucketed bf16 gradient all-reduce when N > 1, fused AdamW step
-    (conf/optimizers/adamw.yaml: lr 1e-4, wd 1e-4).  One rank per GPU, per-GPU batch fixed -> weak scaling."""
+    (core/task.py:141), backward (dgrad + wgrad kernels), gradient all-reduce when N > 1 - by default the bf16 exchange
+    overlapped with the segmented backward (climsr_b200.parallel.attach_ddp) -, fused AdamW step (conf/optimizers/adamw.yaml:
+    lr 1e-4, wd 1e-4).  One rank per GPU, per-GPU batch fixed -> weak scaling.  Returns a dict of measurements."""
     import torch
     import torch.distributed as dist
-    from climsr_b200 import device_check, kernel_launch_count, losses
+    from climsr_b200 import kernel_launch_count, losses
     from climsr_b200.models import ESRGANGenerator
-    from climsr_b200.parallel import BackwardGradSync, GradientBucketer
+    from climsr_b200.parallel import GradientBucketer, attach_ddp
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
-    torch.cuda.set_device(local)
-    if world > 1:
-        init_distributed(local)
-    device_check()
-    dev = torch.device("cuda", local)
-    in_ch, nb, gc, tiles, h, w = WORKLOADS[args.workload]
+    in_ch, nb, gc, tiles, h, w = WORKLOADS[workload]
     H, W = 4 * h, 4 * w
     torch.manual_seed(0)
     net = ESRGANGenerator(in_ch, 1, 64, nb, gc).to(dev).train()
     opt = torch.optim.AdamW(net.parameters(), lr=1e-4, weight_decay=1e-4, fused=True)
     bucketer = GradientBucketer(net.parameters(), bucket_mb=4.0, comm_dtype=torch.bfloat16)
-    use_overlap = world > 1 and args.overlap
-    if use_overlap:
-        net.set_grad_sync(BackwardGradSync(nseg=4, comm_dtype=torch.bfloat16))
+    sync = attach_ddp(net, nseg=4, comm_dtype=torch.bfloat16) if (world > 1 and overlap) else None
     g = torch.Generator().manual_seed(1 + rank)
     x = torch.rand((tiles, in_ch, h, w), generator=g) * 2 - 1
     mask = (torch.rand((tiles, 1, H, W), generator=g) > 0.3).float()
@@ -338,12 +356,13 @@ def run_train(args):
     host = [t.pin_memory() for t in (x, elev, mask, hr)]
     xd, ed, md, hd = (t.to(dev) for t in (x, elev, mask, hr))
     loss_host = torch.empty((), dtype=torch.float32).pin_memory()
+    mode = {"sync": world > 1}
 
     def step():
         opt.zero_grad(set_to_none=True)
         lv = losses.l1_loss(net(xd, ed, md), hd)
         lv.backward()
-        if not use_overlap:
+        if mode["sync"] and sync is None:
             bucketer.allreduce()
         opt.step()
         return lv
@@ -360,33 +379,41 @@ def run_train(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    for _ in range(max(args.warmup, 3)):
+    def timed(n):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(n):
+            lv = step()
+        e1.record()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1) / n), lv
+
+    for _ in range(max(warmup, 3)):
         lv = step()
     barrier()
     first_loss = float(lv.detach())
     l0 = kernel_launch_count()
-    with ClockSampler(local) as clk:
+    with ClockSampler(dev.index) as clk:
+        ms_step, lv = timed(steps)
+    launches = kernel_launch_count() - l0
+    last_loss = float(lv.detach())
+    out = {"ms_per_step": ms_step, "mpixel_per_s": world * tiles * H * W / (ms_step * 1e-3) / 1e6, "loss_first": first_loss,
+           "loss_last": last_loss, "gpu_launches": int(launches), "clocks": clk.summary(),
+           "batch_per_gpu": tiles, "hr_tile": [H, W]}
+    if e2e:
+        # end to end: batch from pinned host memory each step, loss read back
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         e0.record()
-        for _ in range(args.steps):
-            lv = step()
+        for _ in range(steps):
+            for d, s_ in zip((xd, ed, md, hd), host):
+                d.copy_(s_, non_blocking=True)
+            loss_host.copy_(step().detach(), non_blocking=True)
         e1.record()
         barrier()
-        ms_step = max_over_ranks(e0.elapsed_time(e1) / args.steps)
-    launches = kernel_launch_count() - l0
-    last_loss = float(lv.detach())
-    # end to end: batch from pinned host memory each step, loss read back
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for _ in range(args.steps):
-        for d, s in zip((xd, ed, md, hd), host):
-            d.copy_(s, non_blocking=True)
-        loss_host.copy_(step().detach(), non_blocking=True)
-    e1.record()
-    barrier()
-    ms_e2e = max_over_ranks(e0.elapsed_time(e1) / args.steps)
+        out["ms_per_step_e2e"] = max_over_ranks(e0.elapsed_time(e1) / steps)
+        out["h2d_bytes_per_step"] = int(sum(t.numel() for t in host)) * 4
     drift = 0.0
     if world > 1:
         # replicas must stay bit-identical: same init, same averaged gradients
@@ -395,34 +422,175 @@ def run_train(args):
             dist.broadcast(ref, src=0)
             drift = max(drift, float((p_.detach() - ref).abs().max()))
         drift = max_over_ranks(drift)
-    px_step = tiles * H * W
+        # the same step WITHOUT the exchange (replicas diverge from here on; measured last): what the all-reduce leaves exposed
+        net.set_grad_sync(None)
+        mode["sync"] = False
+        ms_local, _ = timed(steps)
+        out["ms_per_step_no_exchange"] = ms_local
+        out["allreduce_exposed_ms"] = ms_step - ms_local
+    out["replica_drift_max_abs"] = drift
     fl = 3.0 * flops_per_hr_pixel(in_ch, 64, nb, gc)          # fwd + dgrad + wgrad
     peaks = load_peaks()
-    achieved = px_step * fl / (ms_step * 1e-3) / 1e12
+    achieved = tiles * H * W * fl / (ms_step * 1e-3) / 1e12
+    out["tflops_algorithmic"] = achieved
+    out["frac"] = achieved / peaks["bf16_burst"]
+    out["frac_sustained"] = achieved / peaks["bf16_sustained"]
+    out["exchange"] = ("none (1 GPU)" if world == 1 else
+                       "bf16 gradient all-reduce in 4 slices overlapped with the segmented backward (attach_ddp: 4 SMs reserved, NCCL_MAX_CTAS=4)"
+                       if sync is not None else f"{len(bucketer.buckets)} bf16 buckets all-reduced after backward")
+    del net, opt
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_train(args):
+    """--mode train: the training step as the headline line (see train_measure)."""
+    import torch
+    import torch.distributed as dist
+    from climsr_b200 import device_check
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        init_distributed(local)
+    device_check()
+    dev = torch.device("cuda", local)
+    in_ch, nb, gc, tiles, h, w = WORKLOADS[args.workload]
+    H, W = 4 * h, 4 * w
+    m = train_measure(args.workload, args.steps, args.warmup, dev, world, rank, overlap=not args.no_overlap)
+    peaks = load_peaks()
     line = {
-        "metric": "generator_train_hr_mpixel_per_s", "value": world * px_step / (ms_step * 1e-3) / 1e6, "unit": "Mpixel/s",
-        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+        "metric": "generator_train_hr_mpixel_per_s", "value": m["mpixel_per_s"], "unit": "Mpixel/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": m["ms_per_step"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": f"{args.workload} train: RRDBNet generator nf=64 nb={nb} gc={gc} in={in_ch}, batch {tiles}/GPU LR {h}x{w} -> HR {H}x{W}; "
-                               "forward + L1 loss + backward (dgrad/wgrad kernels) + bf16 bucketed all-reduce + fused AdamW; bf16 activations/"
+                               "forward + L1 loss + backward (dgrad/wgrad kernels) + gradient exchange + fused AdamW; bf16 activations/"
                                "gradients, fp32 accumulate and master weights",
                    "l2_policy": "saved activations + gradients of a step exceed the 126 MB L2 for batch >= 16; no flush needed",
-                   "parallelism": (f"data parallel x{world}, bf16 gradient all-reduce in 4 slices overlapped with the segmented backward "
-                                   f"(BackwardGradSync), max |param - rank0 param| after the run = {drift:.3g}") if use_overlap else
-                                  f"data parallel x{world}, {len(bucketer.buckets)} gradient buckets {bucketer.bucket_bytes()} bytes after backward"},
-        "e2e": {"value": world * px_step / (ms_e2e * 1e-3) / 1e6, "unit": "Mpixel/s",
-                "h2d_bytes_per_step": int(sum(t.numel() for t in host)) * 4, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e},
-        "gpu_launches": int(launches), "clocks": clk.summary(),
-        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
-                     "frac": achieved / peaks["bf16_sustained"], "traffic": None,
-                     "peak_source": f"{peaks['source']} bf16_tflops_sustained (burst {peaks['bf16_burst']})",
+                   "parallelism": f"data parallel x{world}: {m['exchange']}; max |param - rank0 param| after the run = {m['replica_drift_max_abs']:.3g}"},
+        "e2e": {"value": world * tiles * H * W / (m["ms_per_step_e2e"] * 1e-3) / 1e6, "unit": "Mpixel/s",
+                "h2d_bytes_per_step": m["h2d_bytes_per_step"], "d2h_bytes_per_step": 4, "ms_per_step": m["ms_per_step_e2e"]},
+        "gpu_launches": m["gpu_launches"], "clocks": m["clocks"],
+        "roofline": {"bound": "tensor", "achieved": m["tflops_algorithmic"], "peak": peaks["bf16_burst"], "unit": "TFLOP/s",
+                     "frac": m["frac"], "frac_sustained": m["frac_sustained"], "traffic": None,
+                     "peak_source": f"{peaks['source']} bf16_tflops burst (sustained {peaks['bf16_sustained']})",
                      "note": "algorithmic 3x forward FLOPs of the step / step time"},
-        "loss_first": first_loss, "loss_last": last_loss,
+        "loss_first": m["loss_first"], "loss_last": m["loss_last"],
+        "allreduce_exposed_ms": m.get("allreduce_exposed_ms"), "ms_per_step_no_exchange": m.get("ms_per_step_no_exchange"),
     }
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def halo_measure(dev, world, rank, steps=10, halo=8):
+    """BASELINE configs[3]: one large raster as halo-padded spatial tiles over the GPUs, no collective on the data path.  The
+    global CRU-TS grid (LR 360x720 -> HR 1440x2880, consts/cruts.py:22): a near-square 2-D grid of `world` tiles, one per
+    rank (8 tiles on one GPU, run back to back, for the accuracy figure at N = 1), against the un-tiled run on one GPU."""
+    import torch
+    import torch.distributed as dist
+    from climsr_b200.models import ESRGANGenerator
+    from climsr_b200.tiling import grid_shape, merge_tiles, tile_plan, tiled_forward_2d
+
+    in_ch, nb, gc, _, h, w = WORKLOADS["cfg4_global"]
+    torch.manual_seed(0)
+    net = ESRGANGenerator(in_ch, 1, 64, nb, gc).to(dev).eval()
+    g = torch.Generator().manual_seed(11)                      # the SAME raster on every rank (replicated input)
+    x = (torch.rand((1, in_ch, h, w), generator=g) * 2 - 1).to(dev)
+    mask = (torch.rand((1, 1, 4 * h, 4 * w), generator=g) > 0.3).float().to(dev)
+    elev = ((torch.rand((1, 1, 4 * h, 4 * w), generator=g) * 2 - 1).to(dev)) * mask
+    n_tiles = world if world > 1 else 8
+    ty, tx = grid_shape(n_tiles, h, w)
+    plan = tile_plan(h, w, ty, tx, halo)
+    mine = [i for i in range(len(plan)) if i % world == rank]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn):
+        for _ in range(3):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1) / steps
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    with torch.no_grad():
+        ms_tiled = timed(lambda: [tiled_forward_2d(net, x, elev, mask, plan[i]) for i in mine])
+        ms_full = timed(lambda: net(x, elev, mask))            # un-tiled on one GPU (every rank measures the same thing)
+        full = net(x, elev, mask)
+        parts = {i: tiled_forward_2d(net, x, elev, mask, plan[i]) for i in mine}
+        err = 0.0
+        for i, t in parts.items():
+            r, c = plan[i].rows, plan[i].cols
+            err = max(err, float((t - full[:, :, 4 * r.lo:4 * r.hi, 4 * c.lo:4 * c.hi]).abs().max()))
+        if world > 1:
+            e = torch.tensor([err], dtype=torch.float64, device=dev)
+            dist.all_reduce(e, op=dist.ReduceOp.MAX)
+            err = float(e.item())
+        else:
+            merged = merge_tiles([parts[i] for i in range(len(plan))], ty, tx)
+            assert merged.shape == full.shape
+    px = 16 * h * w
+    del net
+    torch.cuda.empty_cache()
+    return {"raster": f"LR {h}x{w} -> HR {4*h}x{4*w} (global CRU-TS grid), Cin=3", "tiles": [ty, tx], "halo_lr_px": halo,
+            "ms_tiled": ms_tiled, "ms_untiled_1gpu": ms_full, "mpixel_per_s": px / (ms_tiled * 1e-3) / 1e6,
+            "speedup_vs_untiled_1gpu": ms_full / ms_tiled, "max_abs_vs_untiled": err,
+            "note": (f"{n_tiles} tiles, one per GPU, no collective" if world > 1 else
+                     f"{n_tiles} tiles run back to back on one GPU (accuracy figure; the speed-up needs N > 1)")}
+
+
+def gpu_eager_measure(workload, dev, steps=5):
+    """"The kernel to beat" (BASELINE.md section 4): the reference generator graph (oracle port = the reference's own ATen calls)
+    in stock PyTorch eager + cuDNN on the same GPU: bf16 autocast, channels_last, cudnn.benchmark.  A baseline leg, like
+    cpu_baseline - nothing of it is on the product path."""
+    import torch
+    from oracle import generator as og
+    from oracle import synth
+    in_ch, nb, gc, tiles, h, w = WORKLOADS[workload]
+    sd = {k: v.to(dev) for k, v in synth.make_state_dict(in_ch, 1, 64, nb, gc, seed=0).items()}
+    x, elev, mask = (t.to(dev) for t in synth.make_inputs(tiles, in_ch, h, w, seed=1))
+    old = torch.backends.cudnn.benchmark
+    torch.backends.cudnn.benchmark = True
+    try:
+        sdc = {k: (v.to(memory_format=torch.channels_last) if v.dim() == 4 else v) for k, v in sd.items()}
+        xc, ec, mc = (t.contiguous(memory_format=torch.channels_last) for t in (x, elev, mask))
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+            for _ in range(3):
+                og.generator_forward(sdc, xc, ec, mc)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                og.generator_forward(sdc, xc, ec, mc)
+            e1.record()
+            torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+    finally:
+        torch.backends.cudnn.benchmark = old
+    del sd, sdc
+    torch.cuda.empty_cache()
+    px = tiles * 16 * h * w
+    return {"ms_per_step": ms, "mpixel_per_s": px / (ms * 1e-3) / 1e6,
+            "what": "oracle/generator.py graph (the reference's ATen conv / cat / leaky_relu / interpolate calls) on the GPU: torch eager, "
+                    "autocast(bf16), channels_last, cudnn.benchmark=True", "workload": workload}
 
 
 def main():
@@ -434,10 +602,10 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--mode", default="infer", choices=["infer", "train"])
-    ap.add_argument("--overlap", action="store_true",
-                    help="train: all-reduce gradient slices inside the segmented backward (BackwardGradSync) instead of after it; measured "
-                         "SLOWER (12.1 vs 7.3 ms at cfg3 on 2 GPUs): the conv grids are sized to all 148 SMs, so NCCL's CTAs push every "
-                         "concurrent conv launch into a second wave")
+    ap.add_argument("--no-overlap", action="store_true",
+                    help="train: bucketed all-reduce AFTER backward (GradientBucketer) instead of the default exchange overlapped with the "
+                         "segmented backward (attach_ddp)")
+    ap.add_argument("--no-extras", action="store_true", help="inference line only: skip the train / halo_tiled / gpu_eager_baseline measurements")
     args = ap.parse_args()
     if args.impl != "reference" and os.environ.get("CSR_OPTS"):
         # tuning hook: CSR_OPTS="18=0,19=0" applies csr_set_option(key, value) pairs before anything is built

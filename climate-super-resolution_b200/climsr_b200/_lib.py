@@ -87,6 +87,8 @@ def _load():
         "csr_masked_metrics": (C.c_int, [vp, vp, vp, vp, vp, vp, f32, f32, C.c_double, C.c_double, C.c_double, i32, i32, i32, vp, vp, sz, vp]),
         "csr_minmax_normalize": (C.c_int, [vp, i32, i32, i32, vp, vp, C.c_double, C.c_double, C.c_double, f32, vp, vp, vp, vp]),
         "csr_minmax_denormalize_mask": (C.c_int, [vp, vp, i32, i32, i32, i32, vp, vp, C.c_double, C.c_double, C.c_double, vp, vp]),
+        "csr_grad_pack_bf16": (C.c_int, [vp, vp, sz, f32, vp]),
+        "csr_grad_unpack_bf16": (C.c_int, [vp, vp, sz, f32, vp]),
         "csr_lr_input_from_hr": (C.c_int, [vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp]),
     }
     for name, (res, args) in sig.items():
@@ -103,7 +105,7 @@ EXPORTS = ("csr_abi_version", "csr_last_error", "csr_device_check", "csr_set_opt
            "csr_packed_weight_bytes_bwd", "csr_pack_weights_bwd", "csr_plan_backward", "csr_plan_num_backward_ops", "csr_plan_grad_floats", "csr_plan_graph_status", "csr_plan_grad_offset",
            "csr_plan_backward_flat", "csr_plan_backward_segments", "csr_plan_backward_flat_seg", "csr_generator_forward", "csr_conv2d_scratch_bytes",
            "csr_conv2d_nhwc", "csr_conv2d_wgrad_scratch_bytes", "csr_conv2d_wgrad", "csr_nchw_f32_to_nhwc_bf16", "csr_nhwc_bf16_to_nchw_f32", "csr_pixel_loss_scratch_bytes", "csr_l1_loss", "csr_mse_loss",
-           "csr_metrics_scratch_bytes", "csr_masked_metrics", "csr_minmax_normalize", "csr_minmax_denormalize_mask", "csr_lr_input_from_hr")
+           "csr_metrics_scratch_bytes", "csr_masked_metrics", "csr_minmax_normalize", "csr_minmax_denormalize_mask", "csr_grad_pack_bf16", "csr_grad_unpack_bf16", "csr_lr_input_from_hr")
 
 
 def check(rc: int, what: str = "") -> None:

@@ -1,24 +1,48 @@
-"""Data-parallel training of the generator: bucketed gradient all-reduce over torch.distributed (NCCL on NVLink/NVSwitch
-in production, gloo in the CPU tests), the DDP-equivalent of SURVEY.md section 8e.
+"""Data-parallel training of the generator: gradient all-reduce over torch.distributed (NCCL on NVLink/NVSwitch in
+production, gloo in the CPU tests), the DDP-equivalent of SURVEY.md section 8e.
 
-The reference trains through Lightning's DDP plugin (conf/trainer/default.yaml); its exchange step is one gradient
-all-reduce per optimizer.  Here the whole generator backward is ONE autograd node that enqueues ~800 kernels on the
-compute stream, so buckets are filled in backward order after the node returns its gradients: each bucket is flattened
-(optionally to bf16: 8.6 MB for the 4.28 M-parameter Hydra generator), all-reduced asynchronously on a side stream as
-soon as the compute stream has produced its last gradient (event wait, no host sync), averaged, and copied back.  The
-buckets' collectives overlap each other and whatever the caller enqueues next (the discriminator step in GAN training);
-``wait()`` joins them before the optimizer step.  No compute kernel is fused with the collective: the exchange is
-latency-bound (a few MB against ~9 TFLOP of backward math per step).
+The reference trains through Lightning's DDP plugin (conf/trainer/benchmark.yaml:4); its exchange step is one gradient
+all-reduce per optimizer, started from backward hooks so that it overlaps the rest of the backward.  Here the whole
+generator backward is ONE autograd node; the equivalent is ``BackwardGradSync`` (installed by ``attach_ddp``):
+
+* the node runs its backward in ``nseg`` segments (csr_plan_backward_flat_seg).  Layers finish in reverse order, so after
+  each segment a growing suffix of the plan's flat fp32 gradient buffer is final;
+* that slice goes straight from the flat buffer into one persistent bf16 exchange buffer (csr_grad_pack_bf16, pre-scaled by
+  1 / world so the sum over ranks stays in range; no torch.cat / cast / per-parameter copies), is all-reduced on a side
+  stream behind an event (no host sync) while the next segment's kernels run, and is written back as fp32
+  (csr_grad_unpack_bf16).  ``comm_dtype=None`` all-reduces the fp32 slice in place instead (the reference's numerics);
+* the backward kernels are persistent grids of one CTA per SM, so a concurrent collective used to push every overlapping
+  launch into a second wave (round 1: 12.1 vs 7.3 ms per cfg3 step on two GPUs).  ``attach_ddp`` therefore makes training
+  plans leave ``reserve_sms`` SMs free (csr_set_option(30, k)) and the caller caps NCCL to as many CTAs
+  (``NCCL_MAX_CTAS``, set before the communicator is created - bench.py does): compute and collective no longer share an SM.
+
+``GradientBucketer`` (all-reduce after backward, any module) is kept for parameters that do not come from the generator
+node - the discriminator in GAN training.
 """
 from __future__ import annotations
 
+import os
 from typing import Iterable, List, Optional
 
 import torch
 import torch.distributed as dist
 
+DEFAULT_RESERVE_SMS = 4
+
+
+def configure_nccl_for_overlap(reserve_sms: int = DEFAULT_RESERVE_SMS) -> None:
+    """Call BEFORE init_process_group: caps NCCL's CTAs to the SMs the training plans leave free."""
+    os.environ.setdefault("NCCL_MAX_CTAS", str(max(1, reserve_sms)))
+    os.environ.setdefault("NCCL_MIN_CTAS", "1")
+
+
+def _world(group) -> int:
+    return dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+
 
 class GradientBucketer:
+    """Bucketed all-reduce of ``.grad`` after backward (reverse parameter order == the order gradients become final)."""
+
     def __init__(self, params: Iterable[torch.nn.Parameter], bucket_mb: float = 4.0, comm_dtype: Optional[torch.dtype] = torch.bfloat16,
                  process_group=None):
         self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
@@ -26,7 +50,6 @@ class GradientBucketer:
         self.comm_dtype = comm_dtype
         limit = int(bucket_mb * (1 << 20))
         esize = torch.tensor([], dtype=comm_dtype or torch.float32).element_size()
-        # reverse parameter order == the order gradients become final in backward
         self.buckets: List[List[torch.nn.Parameter]] = []
         cur, cur_bytes = [], 0
         for p in reversed(self.params):
@@ -43,7 +66,7 @@ class GradientBucketer:
 
     @property
     def world(self) -> int:
-        return dist.get_world_size(self.group) if dist.is_initialized() else 1
+        return _world(self.group)
 
     def bucket_bytes(self) -> List[int]:
         esize = torch.tensor([], dtype=self.comm_dtype or torch.float32).element_size()
@@ -53,6 +76,12 @@ class GradientBucketer:
         """Start the all-reduce of every bucket (call right after loss.backward())."""
         if self.world == 1:
             return
+        missing = [i for i, p in enumerate(self.params) if p.grad is None]
+        if missing:
+            # like DDP without find_unused_parameters: ranks must agree on the set of reduced tensors, and inventing zero
+            # gradients would change the optimizer's behaviour (AdamW decay / moments of unused parameters)
+            raise RuntimeError(f"GradientBucketer: {len(missing)} parameters have no gradient (first index {missing[0]}); "
+                               "unused parameters are not supported")
         dev = self.params[0].device
         on_cuda = dev.type == "cuda"
         if on_cuda:
@@ -61,14 +90,12 @@ class GradientBucketer:
             ready = torch.cuda.Event()
             ready.record(torch.cuda.current_stream(dev))
             self._stream.wait_event(ready)
+        inv = 1.0 / self.world
         ctx = torch.cuda.stream(self._stream) if on_cuda else _null()
         with ctx:
             for bucket in self.buckets:
-                for p in bucket:
-                    if p.grad is None:
-                        p.grad = torch.zeros_like(p)
-                # one concatenation + one cast per bucket (not per parameter): the step must not become launch-bound
-                flat = torch.cat([p.grad.reshape(-1) for p in bucket])
+                # one concatenation + one cast per bucket (not per parameter); averaged BEFORE the rounding to comm_dtype
+                flat = torch.cat([p.grad.reshape(-1) for p in bucket]).mul_(inv)
                 if self.comm_dtype is not None and flat.dtype != self.comm_dtype:
                     flat = flat.to(self.comm_dtype)
                 work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
@@ -80,12 +107,11 @@ class GradientBucketer:
             return
         dev = self.params[0].device
         on_cuda = dev.type == "cuda"
-        inv = 1.0 / self.world
         ctx = torch.cuda.stream(self._stream) if on_cuda else _null()
         with ctx:
             for bucket, flat, work in self._pending:
                 work.wait()
-                avg = flat.to(torch.float32).mul_(inv)
+                avg = flat.to(torch.float32)
                 parts = torch.split(avg, [p.numel() for p in bucket])
                 torch._foreach_copy_([p.grad for p in bucket], [t.view_as(p) for t, p in zip(parts, bucket)])   # one multi-tensor kernel
         if on_cuda:
@@ -100,48 +126,61 @@ class GradientBucketer:
 
 
 class BackwardGradSync:
-    """Gradient all-reduce overlapped with the generator's backward (the DDP-hook equivalent for a one-node backward).
+    """Gradient all-reduce overlapped with the generator's backward (see the module docstring).
 
-    ``ESRGANGenerator.set_grad_sync(BackwardGradSync(...))`` makes the generator's autograd node run its backward in
-    ``nseg`` segments (csr_plan_backward_flat_seg).  Layers finish in reverse order, so after each segment a growing
-    suffix of the flat gradient buffer is final: that slice is cast to ``comm_dtype`` and all-reduced on a side stream
-    behind an event while the next segment's kernels run on the compute stream.  The node returns averaged gradients, so
-    nothing is left to do after ``loss.backward()``.
-
-    Measured on 2 x B200 (cfg3 generator step): 12.1 ms with this overlap vs 7.3 ms with ``GradientBucketer`` after backward
-    (6.9 ms on one GPU).  The persistent conv / wgrad grids occupy all 148 SMs with one CTA each; a concurrent NCCL kernel
-    takes a few SMs and every conv launch that overlaps it needs a second wave.  Overlap therefore only pays once the
-    compute grids leave SMs free - kept as an option, not the default.
+    ``ESRGANGenerator.set_grad_sync(sync)`` (or ``attach_ddp``) makes the generator's autograd node call
+    ``reduce_slice_async`` after every backward segment and ``finish`` at the end; the node then returns gradients that are
+    already averaged over the process group, so nothing is left to do after ``loss.backward()``.
     """
 
     def __init__(self, nseg: int = 4, comm_dtype: Optional[torch.dtype] = torch.bfloat16, process_group=None):
+        if comm_dtype not in (None, torch.bfloat16, torch.float32):
+            raise ValueError("comm_dtype must be torch.bfloat16 (wire format of SURVEY 8e) or None / torch.float32 (exact fp32 sum)")
         self.nseg = max(1, int(nseg))
-        self.comm_dtype = comm_dtype
+        self.comm_dtype = None if comm_dtype == torch.float32 else comm_dtype
         self.group = process_group
         self._stream = None
+        self._comm = None                 # persistent bf16 exchange buffer, same indexing as the flat gradient buffer
         self.last_ranges: List[tuple] = []
+        self.exposed_event_pairs: List[tuple] = []
 
     @property
     def world(self) -> int:
-        return dist.get_world_size(self.group) if dist.is_initialized() else 1
+        return _world(self.group)
 
     def stream(self, dev) -> "torch.cuda.Stream":
         if self._stream is None:
             self._stream = torch.cuda.Stream(device=dev)
         return self._stream
 
+    def _comm_buffer(self, flat: torch.Tensor) -> torch.Tensor:
+        if self._comm is None or self._comm.numel() != flat.numel() or self._comm.device != flat.device:
+            self._comm = torch.empty(flat.numel(), dtype=torch.bfloat16, device=flat.device)
+        return self._comm
+
     def reduce_slice_async(self, flat: torch.Tensor, lo: int, hi: int, pending: list) -> None:
         """Called by the autograd node right after a segment: flat[lo:hi] is final on the compute stream."""
         if hi <= lo or self.world == 1:
             return
         dev = flat.device
+        inv = 1.0 / self.world
+        if dev.type != "cuda":                                   # gloo tests of the host logic
+            part = flat[lo:hi]
+            buf = (part * inv).to(self.comm_dtype) if self.comm_dtype is not None else part.mul_(inv)
+            work = dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+            pending.append((lo, hi, buf, work))
+            return
+        from ._lib import check, lib
         ready = torch.cuda.Event()
         ready.record(torch.cuda.current_stream(dev))
         comm = self.stream(dev)
         with torch.cuda.stream(comm):
             comm.wait_event(ready)
-            part = flat[lo:hi]
-            buf = part.to(self.comm_dtype) if self.comm_dtype is not None and self.comm_dtype != part.dtype else part
+            if self.comm_dtype is not None:
+                buf = self._comm_buffer(flat)[lo:hi]
+                check(lib.csr_grad_pack_bf16(flat.data_ptr() + 4 * lo, buf.data_ptr(), hi - lo, inv, comm.cuda_stream), "csr_grad_pack_bf16")
+            else:
+                buf = flat[lo:hi].mul_(inv)
             work = dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
             pending.append((lo, hi, buf, work))
 
@@ -149,20 +188,42 @@ class BackwardGradSync:
         if not pending:
             return
         dev = flat.device
+        self.last_ranges = [(lo, hi) for lo, hi, _, _ in pending]
+        if dev.type != "cuda":
+            for lo, hi, buf, work in pending:
+                work.wait()
+                if buf.data_ptr() != flat[lo:hi].data_ptr():
+                    flat[lo:hi].copy_(buf.to(torch.float32))
+            return
+        from ._lib import check, lib
         comm = self.stream(dev)
-        inv = 1.0 / self.world
         with torch.cuda.stream(comm):
             for lo, hi, buf, work in pending:
                 work.wait()
-                if buf.data_ptr() == flat[lo:hi].data_ptr():
-                    flat[lo:hi].mul_(inv)
-                else:
-                    torch.mul(buf.to(torch.float32), inv, out=flat[lo:hi])
+                if self.comm_dtype is not None:
+                    check(lib.csr_grad_unpack_bf16(buf.data_ptr(), flat.data_ptr() + 4 * lo, hi - lo, 1.0, comm.cuda_stream), "csr_grad_unpack_bf16")
             done = torch.cuda.Event()
             done.record(comm)
         torch.cuda.current_stream(dev).wait_event(done)
         flat.record_stream(comm)
-        self.last_ranges = [(lo, hi) for lo, hi, _, _ in pending]
+
+
+def attach_ddp(generator, nseg: int = 4, comm_dtype: Optional[torch.dtype] = torch.bfloat16, process_group=None,
+               reserve_sms: int = DEFAULT_RESERVE_SMS) -> Optional[BackwardGradSync]:
+    """Data-parallel training of ``generator`` (a climsr_b200 ESRGANGenerator): install the overlapped gradient all-reduce and
+    make the training plans created from now on leave ``reserve_sms`` SMs to the collective.  Returns the sync object, or
+    None in a single-process run (nothing to exchange).  Call ``configure_nccl_for_overlap`` before init_process_group."""
+    if _world(process_group) == 1:
+        return None
+    params = list(generator.parameters())
+    if params and params[0].is_cuda:
+        from ._lib import check, lib
+        check(lib.csr_set_option(30, int(reserve_sms)), "csr_set_option(30)")
+    for key in list(getattr(generator, "_plans", {}).keys()):      # plans made before the reservation own all SMs: rebuild them lazily
+        generator._evict(key)
+    sync = BackwardGradSync(nseg=nseg, comm_dtype=comm_dtype, process_group=process_group)
+    generator.set_grad_sync(sync)
+    return sync
 
 
 class _null:

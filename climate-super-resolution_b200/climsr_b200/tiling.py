@@ -9,8 +9,9 @@ Two ways the generator path shards, both with NO data-path exchange step:
   borders keep the convolutions' zero padding); ``tiled_forward`` runs a band on this rank and ``merge_bands`` pastes
   the cropped HR bands.  The theoretical receptive field of the trunk (167 LR px at nb=11) exceeds the Europe raster,
   so exactness by halo is impossible in principle; the measured effective field is small (halo 8 reproduces the
-  un-tiled output to fp32 noise for random-init weights) - ``halo`` is a parameter (default 16)
-  and tests report the error against the un-tiled oracle.
+  un-tiled output to fp32 noise for random-init weights) - ``halo`` is a parameter and tests /
+  bench.py report the error against the un-tiled run.  ``tile_plan`` / ``tiled_forward_2d`` / ``merge_tiles`` cut in both
+  directions (near-square tiles carry the least halo work).
 
 Pure host logic (index arithmetic + calls into ``net``); the arithmetic runs in whatever ``net`` is - the CUDA
 generator in production, the CPU oracle in the CPU tests.
@@ -76,6 +77,50 @@ def tiled_forward(net: Callable[[Tensor, Tensor, Tensor], Tensor], x: Tensor, el
 
 def merge_bands(parts: Sequence[Tensor]) -> Tensor:
     return torch.cat(list(parts), dim=2)
+
+
+@dataclass(frozen=True)
+class Tile2D:
+    """A rectangular LR tile: rows from ``rows`` (a Band), columns from ``cols`` (a Band over the width)."""
+    rows: Band
+    cols: Band
+
+
+def grid_shape(n_tiles: int, h: int, w: int) -> Tuple[int, int]:
+    """(tiles_y, tiles_x) with tiles_y * tiles_x == n_tiles whose tiles are closest to square: least halo work per output pixel."""
+    best, best_cost = (n_tiles, 1), None
+    for ty in range(1, n_tiles + 1):
+        if n_tiles % ty:
+            continue
+        tx = n_tiles // ty
+        if ty > h or tx > w:
+            continue
+        cost = abs((h / ty) - (w / tx))
+        if best_cost is None or cost < best_cost:
+            best, best_cost = (ty, tx), cost
+    return best
+
+
+def tile_plan(h: int, w: int, tiles_y: int, tiles_x: int, halo: int = 8) -> List[Tile2D]:
+    """2-D halo-padded tile grid, row-major.  A row band of 45 LR rows with a 16-row halo reads 1.7x its own rows; a
+    180 x 180 tile of the global grid with the (sufficient, see module docstring) 8-px halo reads 1.19x."""
+    return [Tile2D(r, c) for r in band_plan(h, tiles_y, halo) for c in band_plan(w, tiles_x, halo)]
+
+
+def tiled_forward_2d(net: Callable[[Tensor, Tensor, Tensor], Tensor], x: Tensor, elev: Tensor, mask: Tensor, tile: Tile2D) -> Tensor:
+    """Run one tile (halo included), crop the halo: returns HR rows [4*rows.lo, 4*rows.hi) x columns [4*cols.lo, 4*cols.hi)."""
+    r, c = tile.rows, tile.cols
+    xs = x[:, :, r.read_lo:r.read_hi, c.read_lo:c.read_hi].contiguous()
+    es = elev[:, :, r.read_lo * SCALE:r.read_hi * SCALE, c.read_lo * SCALE:c.read_hi * SCALE].contiguous()
+    ms = mask[:, :, r.read_lo * SCALE:r.read_hi * SCALE, c.read_lo * SCALE:c.read_hi * SCALE].contiguous()
+    out = net(xs, es, ms)
+    return out[:, :, r.crop_top:r.crop_top + r.out_rows, c.crop_top:c.crop_top + c.out_rows]
+
+
+def merge_tiles(parts: Sequence[Tensor], tiles_y: int, tiles_x: int) -> Tensor:
+    """Paste row-major tiles back into the raster."""
+    rows = [torch.cat(list(parts[i * tiles_x:(i + 1) * tiles_x]), dim=3) for i in range(tiles_y)]
+    return torch.cat(rows, dim=2)
 
 
 def tiled_forward_all(net, x: Tensor, elev: Tensor, mask: Tensor, bands: int, halo: int = 16, rank: int = 0, world: int = 1,

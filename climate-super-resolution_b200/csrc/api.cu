@@ -43,9 +43,14 @@ static int g_opt_narrow_box = 1;        // 16- / 32-channel window boxes for lay
 static int g_opt_regroup = 0;           // dense blocks regrouped by source in the forward (see fwd_exec_table): -3 % alone, but the plain
                                         // layout gains more from two-tile windows (5.76 vs 5.85 ms), so it is off by default
 static int g_opt_trace_cta = 0;         // debug: CTA recorded by csr_debug_set_trace
+static int g_opt_reserve_sms = 0;       // plans created afterwards size their persistent grids to (SM count - this): the SMs left free run the
+                                        // gradient all-reduce (NCCL, capped to as many CTAs) concurrently with the backward kernels
+static int g_opt_l2_prefetch = 0;       // conv layers that stream from HBM: prefetch windows this many tile iterations ahead into L2 (cp.async.bulk.prefetch.tensor).
+                                        // Measured: no effect at depth 2/4/8 (HRconv 317-323 us either way) - the HR tail is not bound by HBM latency
 static int g_dbg_dense = 0;             // DenseParams::dbg (timing experiments)
 static int g_opt_dense = 1;             // conv1..conv4 of every gc = 16 dense block as ONE persistent launch with tile-level dependencies (rdb_tc.cu)
-static int g_opt_early = 1;             // early-release epilogue for wide residual-free layers (conv_tc.cu, EARLY_T)
+static int g_opt_early = 1;             // early-release epilogue (conv_tc.cu, EARLY_T): 1 = wide residual-free layers; 2 = also the residual layers (RDB conv5 with one
+                                        // staging buffer and a third window slot, trunk_conv): measured slower in situ (42.0 / 55.5 vs 39.6 / 51.7 us per conv5)
 static int g_opt_pair = 0;              // CTA-pair (cta_group::2) launches for 3x3 layers with >= 96 KB of weights.  Measured (cfg2): MMAs run at the
                                         // 108 clk/MMA pair rate instead of ~140, but two SMs in lock-step on two accumulators expose the epilogue:
                                         // 6.11 vs 5.90 ms per step, so it stays off by default
@@ -420,16 +425,27 @@ static int build_conv(const PackLayer& pl, const PackPart& pp, int N, int H, int
   p.n_stage = p.n_groups;
   // Early-release epilogue (conv_tc.cu, EARLY_T): wide residual-free layers that run with one 16-warp group.  Two staging
   // buffers; KW <= 2 layers also get four accumulator buffers (4 x KW x 64 <= 512 TMEM columns).
-  if (g_opt_early && !p.pair && !p.tall_shift && tma_out && p.n_groups == 1 && res_bits == 0 && p.npad == 64 && pp.n_store == 64 &&
-      !g_opt_force_generic &&
+  const bool early_plain = res_bits == 0 && p.n_groups == 1 &&
       ((p.KW == 3 && p.PW == 1 && (p.act == 0 || p.act == 1 || p.act == 3)) || (p.KW == 2 && p.PW <= 1 && p.act == 1) ||
-       (p.KW == 1 && p.PW == 0 && p.act == 2))) {
-    Tiling te;
-    if (choose_tiling(H, W, pp.kh, pp.kw, p.w_bytes, p.n_kblocks, p.stage_row_bytes, 2, &te, p.box_c * 2) == CSR_OK &&
-        te.n_slots >= std::min(2, p.n_kblocks + 1)) {
+       (p.KW == 1 && p.PW == 0 && p.act == 2));
+  // ... and the residual layers (RDB conv5, trunk_conv): with the accumulator handed back early one 16-warp group no longer
+  // paces the tile, and a single staging buffer buys RDB conv5 (144 KB of weights) a third window slot
+  const bool early_res = g_opt_early >= 2 && (res_bits == 1 || res_bits == 3) && !io.r1_pre && p.KW == 3 && p.PW == 1 && p.act == 0 && p.n_groups <= 2;
+  if (g_opt_early && !p.pair && !p.tall_shift && tma_out && p.npad == 64 && pp.n_store == 64 && !g_opt_force_generic && (early_plain || early_res)) {
+    Tiling te2, te1;
+    const bool ok2 = choose_tiling(H, W, pp.kh, pp.kw, p.w_bytes, p.n_kblocks, p.stage_row_bytes, 2, &te2, p.box_c * 2) == CSR_OK;
+    const bool ok1 = choose_tiling(H, W, pp.kh, pp.kw, p.w_bytes, p.n_kblocks, p.stage_row_bytes, 1, &te1, p.box_c * 2) == CSR_OK;
+    const int want = std::min(2 * p.n_kblocks, 4);
+    int stages = 0;
+    if (ok2 && te2.n_slots >= want) stages = 2;
+    else if (ok1 && (!ok2 || te1.n_slots > te2.n_slots)) stages = 1;
+    else if (ok2) stages = 2;
+    const Tiling& te = stages == 1 ? te1 : te2;
+    if (stages && te.n_slots >= std::min(2, p.n_kblocks + 1) && (early_plain || te.n_slots > tl.n_slots || te.n_slots >= want)) {
       tl = te;
       p.early = 1;
-      p.n_stage = 2;
+      p.n_groups = 1;
+      p.n_stage = stages;
       if (4 * p.KW * p.npad <= 512 && !g_opt_two_acc) p.n_acc = 4;
     }
   }
@@ -455,6 +471,7 @@ static int build_conv(const PackLayer& pl, const PackPart& pp, int N, int H, int
   p.trace = g_trace;
   p.trace_cta = g_opt_trace_cta;
   p.use_pdl = g_opt_pdl;
+  p.l2_prefetch = ((size_t)N * H * W * io.in_C * 2 > (size_t)48 << 20) ? g_opt_l2_prefetch : 0;   // only layers that stream from HBM
   p.force_generic = g_opt_force_generic;
   p.r1_pre = io.r1 ? io.r1_pre : 0;
   p.s1 = io.s1; p.s2 = io.s2;
@@ -1283,7 +1300,9 @@ int csr_set_option(int32_t key, int32_t value) {
     case 25: g_opt_wgrad_atomic = value ? 1 : 0; return CSR_OK;    // plans created afterwards
     case 27: g_opt_dense = value ? 1 : 0; return CSR_OK;           // plans created afterwards
     case 28: g_dbg_dense = value; return CSR_OK;
-    case 26: g_opt_early = value ? 1 : 0; return CSR_OK;           // early-release epilogue of the wide residual-free layers
+    case 29: g_opt_l2_prefetch = value; return CSR_OK;
+    case 30: g_opt_reserve_sms = value < 0 ? 0 : value; return CSR_OK;
+    case 26: g_opt_early = value; return CSR_OK;           // early-release epilogue of the wide residual-free layers
     default: return fail(CSR_ERR_BAD_ARG, "unknown option key %d", key);
   }
 }
@@ -1406,7 +1425,7 @@ static int plan_create_impl(const CsrNetDesc* net, int32_t n, int32_t h, int32_t
   rc = device_info(&di);
   if (rc) return rc;
   CsrPlan* P = new CsrPlan();
-  P->net = *net; P->N = n; P->h = h; P->w = w; P->sms = di.sms; P->train = train;
+  P->net = *net; P->N = n; P->h = h; P->w = w; P->sms = std::max(1, di.sms - (train ? g_opt_reserve_sms : 0)); P->train = train;
   rc = plan_build(P, workspace);
   if (!rc && train) {
     rc = bwd_build(P, workspace);
@@ -1935,6 +1954,22 @@ int csr_minmax_denormalize_mask(const float* sr, const float* mask, int32_t mask
   if (n < 1 || h < 1 || w < 1 || n > 65535) return fail(CSR_ERR_BAD_ARG, "bad shape n=%d h=%d w=%d", n, h, w);
   CSR_CUDA(launch_minmax_denormalize_mask(sr, mask, mask_per_sample ? (long)h * w : 0, n, (long)h * w, mn, mx, range_a, range_b, eps, out,
                                           reinterpret_cast<cudaStream_t>(stream)));
+  ++g_launches;
+  return CSR_OK;
+}
+
+// ---- gradient exchange (data-parallel training) -------------------------------------------------------------------
+int csr_grad_pack_bf16(const float* flat, void* comm_bf16, size_t n, float scale, void* stream) {
+  if (!flat || !comm_bf16) return fail(CSR_ERR_BAD_ARG, "null pointer");
+  if (n == 0) return CSR_OK;
+  CSR_CUDA(launch_grad_pack_bf16(flat, comm_bf16, (long)n, scale, std::max(2, 2 * g_opt_reserve_sms), reinterpret_cast<cudaStream_t>(stream)));
+  ++g_launches;
+  return CSR_OK;
+}
+int csr_grad_unpack_bf16(const void* comm_bf16, float* flat, size_t n, float scale, void* stream) {
+  if (!flat || !comm_bf16) return fail(CSR_ERR_BAD_ARG, "null pointer");
+  if (n == 0) return CSR_OK;
+  CSR_CUDA(launch_grad_unpack_bf16(comm_bf16, flat, (long)n, scale, std::max(2, 2 * g_opt_reserve_sms), reinterpret_cast<cudaStream_t>(stream)));
   ++g_launches;
   return CSR_OK;
 }

@@ -248,6 +248,14 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
     uint32_t phase = 0;
     for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++pit) {
       const Tile tl = decode_tile<TALL_T>(p, t);
+      if (p.l2_prefetch > 0) {
+        const int tp = t + p.l2_prefetch * static_cast<int>(gridDim.x);
+        if (tp < p.num_tiles && elect_one()) {
+          const Tile tq = decode_tile<TALL_T>(p, tp);
+          for (int kb = 0; kb < p.n_kblocks; ++kb) tma_prefetch_l2_4d(&tmap, p.cin_off + kb * 64, tq.x0 - p.PW, tq.y0 - p.PH, tq.n);
+        }
+        __syncwarp();
+      }
       for (int kb = 0; kb < p.n_kblocks; ++kb) {
         if (kb == 0 && lane == 0) CSR_TRACE(0, pit, 0);
         mbar_wait_spin(bar_a_empty(slot), phase ^ 1);
@@ -446,14 +454,30 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
     uint32_t acc_phase = 0;
     if constexpr (EARLY_T) {
       // One group of 16 warps, 64 output channels: warp (quadrant q, sub s) owns channels [16 s, 16 s + 16) of rows [32 q, 32 q + 32).
-      static_assert(KW_T >= 1 && KW_T <= 3 && RES_T == 0 && ST_T == 1 && PAIR_T == 0 && TALL_T == 0, "early-release epilogue: wide residual-free layers only");
+      static_assert(KW_T >= 1 && KW_T <= 3 && (RES_T == 0 || RES_T == 1 || RES_T == 3) && ST_T == 1 && PAIR_T == 0 && TALL_T == 0,
+                    "early-release epilogue: wide layers without gate / pre-activation addend");
       const int ch_lo = sub * 16;
       uint32_t sb = 0;                                    // staging buffer of this tile
+      const bool two_stage = p.n_stage == 2;
       for (int it = 0; ; ++it) {
         const int t = blockIdx.x + it * static_cast<int>(gridDim.x);
         if (t >= p.num_tiles) break;
         if (tracer) CSR_TRACE(2, it, 3);
         const Tile tl = decode_tile<0>(p, t);
+        // residual operands do not depend on the accumulator: fetch them before waiting for the MMAs
+        uint4 q1[2], q2[2];
+        if constexpr (RES_T != 0) {
+          const int y = tl.y0 + ty, x = tl.x0 - PW_T + tx;
+          const bool valid = col_ok && (y < p.H) && (x < p.W);
+          const size_t pix = (static_cast<size_t>(tl.n) * p.H + y) * p.W + x;
+#pragma unroll
+          for (int jj = 0; jj < 2; ++jj) {
+            const int ch0 = ch_lo + jj * 8;
+            q1[jj] = valid ? ldg16(p.r1, pix, p.r1_C, p.r1_coff + ch0) : make_uint4(0, 0, 0, 0);
+            if constexpr (RES_T == 3) q2[jj] = valid ? ldg16(p.r2, pix, p.r2_C, p.r2_coff + ch0) : make_uint4(0, 0, 0, 0);
+          }
+        }
+        if (!two_stage && it > 0) named_bar_sync(1, gthreads);   // one staging buffer: every copy-out of the previous tile has been issued
         const uint32_t t_addr = t_lane + buf * nmma + ch_lo;
         mbar_wait(bar_acc_full(buf), acc_phase);           // the one bounded wait (see mbar_wait_spin)
         tc_fence_after();
@@ -485,6 +509,8 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
           } else {
             apply_act8(v, act);
           }
+          if constexpr (RES_T != 0) fma_residual8(v, q1[jj], p.s1);
+          if constexpr (RES_T == 3) fma_residual8(v, q2[jj], p.s2);
           if (col_ok && ch0 < p.n_store)
             st_shared_v4(srow_addr + sb * p.stage_bytes + ((static_cast<uint32_t>(ch0 >> 3) ^ swz) << 4), pack_bf16x2(v[0], v[1]),
                          pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
@@ -505,7 +531,7 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
           }
         }
         if (tracer) CSR_TRACE(2, it, 2);
-        sb ^= 1u;
+        if (two_stage) sb ^= 1u;
         if (++buf >= NA) { buf = 0; acc_phase ^= 1; }
       }
     } else
@@ -751,16 +777,18 @@ int launch_conv_tc(const ConvParams& p, const CUtensorMap& tmap, int num_sms, cu
   }
   if (p.early) {
     // wide residual-free layers with the early-release epilogue (one 16-warp group, two staging buffers)
-    if (p.store_mode != kStoreStaged || res != 0 || p.n_groups != 1 || p.n_stage != 2 || p.npad != 64 || p.force_generic)
+    if (p.store_mode != kStoreStaged || p.n_groups != 1 || p.n_stage < 1 || p.n_stage > 2 || p.npad != 64 || p.force_generic)
       return static_cast<int>(cudaErrorInvalidValue);
-#define CSR_EARLY(KW_, PW_, ACT_) \
-    if (p.KW == KW_ && p.PW == PW_ && p.act == ACT_) return launch_t<KW_, PW_, ACT_, 0, 1, 0, 0, 1>(p, tmap, num_sms, stream);
-    CSR_EARLY(3, 1, 1)   // HRconv
-    CSR_EARLY(3, 1, 0)   // conv_first
-    CSR_EARLY(3, 1, 3)   // dense block regrouped by source: conv1 + the x-parts of conv2-4
-    CSR_EARLY(2, 0, 1)   // upconv sub-pixel phases
-    CSR_EARLY(2, 1, 1)
-    CSR_EARLY(1, 0, 2)   // srcnn.conv1 (x-im2col folded)
+#define CSR_EARLY(KW_, PW_, ACT_, RES_) \
+    if (p.KW == KW_ && p.PW == PW_ && p.act == ACT_ && res == RES_) return launch_t<KW_, PW_, ACT_, RES_, 1, 0, 0, 1>(p, tmap, num_sms, stream);
+    CSR_EARLY(3, 1, 1, 0)   // HRconv
+    CSR_EARLY(3, 1, 0, 0)   // conv_first
+    CSR_EARLY(3, 1, 3, 0)   // dense block regrouped by source: conv1 + the x-parts of conv2-4
+    CSR_EARLY(2, 0, 1, 0)   // upconv sub-pixel phases
+    CSR_EARLY(2, 1, 1, 0)
+    CSR_EARLY(1, 0, 2, 0)   // srcnn.conv1 (x-im2col folded)
+    CSR_EARLY(3, 1, 0, 1)   // RDB conv5 (*0.2 + x), trunk_conv (+ fea): one staging buffer when the weights leave no room for two
+    CSR_EARLY(3, 1, 0, 3)   // RDB3 conv5 (*0.2 + x, *0.2 + x_rrdb)
 #undef CSR_EARLY
     return static_cast<int>(cudaErrorInvalidValue);
   }

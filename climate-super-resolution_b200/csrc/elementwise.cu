@@ -432,6 +432,27 @@ cudaError_t launch_scale_copy64(const void* src, int src_C, void* dst, int dst_C
   return cudaGetLastError();
 }
 
+// ---- gradient exchange buffers (data-parallel training) -----------------------------------------------------------
+// bf16 wire format of the gradient all-reduce: comm[i] = bf16(scale * flat[i]) (scale = 1 / world BEFORE the rounding, so the
+// sum over ranks stays in range) and back: flat[i] = float(comm[i]).  Small grids on purpose: they run on the SMs reserved for
+// the collective while the backward kernels own the rest.
+__global__ void grad_pack_bf16_kernel(const float* __restrict__ flat, __nv_bfloat16* __restrict__ comm, long n, float scale) {
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n; i += static_cast<long>(gridDim.x) * blockDim.x)
+    comm[i] = __float2bfloat16_rn(flat[i] * scale);
+}
+__global__ void grad_unpack_bf16_kernel(const __nv_bfloat16* __restrict__ comm, float* __restrict__ flat, long n, float scale) {
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n; i += static_cast<long>(gridDim.x) * blockDim.x)
+    flat[i] = __bfloat162float(comm[i]) * scale;
+}
+cudaError_t launch_grad_pack_bf16(const float* flat, void* comm, long n, float scale, int max_blocks, cudaStream_t s) {
+  grad_pack_bf16_kernel<<<grid_for(n, 512, max_blocks), 512, 0, s>>>(flat, reinterpret_cast<__nv_bfloat16*>(comm), n, scale);
+  return cudaGetLastError();
+}
+cudaError_t launch_grad_unpack_bf16(const void* comm, float* flat, long n, float scale, int max_blocks, cudaStream_t s) {
+  grad_unpack_bf16_kernel<<<grid_for(n, 512, max_blocks), 512, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(comm), flat, n, scale);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_pack_jobs(const PackJob* jobs_dev, int njobs, cudaStream_t s) {
   pack_jobs_kernel<<<dim3(16, njobs), 256, 0, s>>>(jobs_dev);
   return cudaGetLastError();

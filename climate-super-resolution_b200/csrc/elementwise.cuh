@@ -27,6 +27,9 @@ cudaError_t launch_wgrad_scatter(const float* dacc, int ld_n, float* dw, int cou
 cudaError_t launch_bias_grad(const void* g, long npix, int C, int coff, int cout, float scale, float* const* db, int nseg, cudaStream_t s);
 cudaError_t launch_bias_grad_planar(const float* g, long n, float scale, float* db, cudaStream_t s);
 cudaError_t launch_scale_copy64(const void* src, int src_C, void* dst, int dst_C, long npix, float scale, cudaStream_t s);
+// bf16 wire format of the data-parallel gradient exchange: comm = bf16(scale * flat) / flat = scale * float(comm)
+cudaError_t launch_grad_pack_bf16(const float* flat, void* comm, long n, float scale, int max_blocks, cudaStream_t s);
+cudaError_t launch_grad_unpack_bf16(const void* comm, float* flat, long n, float scale, int max_blocks, cudaStream_t s);
 cudaError_t launch_gcol_pack(const void* src, int src_C, void* dst, int dst_C, int H, int W, long total_pix, int KH, int KW, cudaStream_t s);
 // Min-max scaler around the inference hot path (normalization.py:37-84): float64 arithmetic, one rounding to float32.
 // normalize: out[n][0] = nan_to(raw[n] * scale_n + min__n); channels 1.. = the shared (h,w) planes extra0 / extra1.

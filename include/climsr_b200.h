@@ -221,6 +221,14 @@ int     csr_masked_metrics(const float* sr, const float* hr, const float* origin
                            double range_a, double range_b, double eps, int32_t n, int32_t h, int32_t w,
                            float* out, void* scratch, size_t scratch_bytes, void* stream);
 
+/* ---- gradient exchange of data-parallel training ("bf16 gradients are reduced with NCCL over NVLink,
+ * bucketed and overlapped with backward"; replaces the gradient all-reduce of Lightning's DDP plugin, conf/trainer/
+ * benchmark.yaml:4).  The collective itself is torch.distributed / NCCL; these are the wire-format kernels around it:
+ * comm = bf16(scale * flat) with scale = 1 / world applied BEFORE the rounding, and flat = scale * float(comm).
+ * csr_set_option(30, k) makes training plans created afterwards leave k SMs free for the collective's CTAs. */
+int     csr_grad_pack_bf16(const float* flat, void* comm_bf16, size_t n, float scale, void* stream);
+int     csr_grad_unpack_bf16(const void* comm_bf16, float* flat, size_t n, float scale, void* stream);
+
 /* ---- inference pre / post-processing on device -------------------------------------------
  * The reference normalises each LR raster on the CPU (MinMaxScaler._normalize, climsr/data/normalization.py:37-61, called
  * from geo_tiff_inference_dataset.py:161-166), concatenates [raster, elevation_lr, mask_lr] (:101-121), and after the

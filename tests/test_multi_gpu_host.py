@@ -44,6 +44,31 @@ def test_tiled_forward_matches_untiled_oracle():
     assert errs[8] <= 1e-5 and errs[2] < errs[0] and errs[0] > 1e-3
 
 
+def test_2d_tile_grid_matches_untiled_oracle():
+    """2-D halo-padded tiles (climsr_b200.tiling.tile_plan): exact cover, near-square grid choice, and the merged result equals
+    the un-tiled oracle to fp32 noise at halo 8."""
+    from climsr_b200.tiling import grid_shape, merge_tiles, tile_plan, tiled_forward_2d
+    from oracle import generator as og
+    from oracle import synth
+    assert grid_shape(8, 360, 720) == (2, 4) and grid_shape(4, 360, 720) == (1, 4) or grid_shape(4, 360, 720) == (2, 2)
+    assert grid_shape(1, 10, 10) == (1, 1)
+    plan = tile_plan(30, 41, 2, 3, halo=8)
+    assert len(plan) == 6
+    cover = torch.zeros(30, 41)
+    for t in plan:
+        cover[t.rows.lo:t.rows.hi, t.cols.lo:t.cols.hi] += 1
+        assert t.rows.read_lo <= t.rows.lo and t.cols.read_hi >= t.cols.hi
+    assert bool((cover == 1).all())
+    sd = synth.make_state_dict(3, 1, 64, 1, 16, seed=0)
+    x, elev, mask = synth.make_inputs(1, 3, 30, 41, seed=1)
+    net = lambda a, b, c: og.generator_forward(sd, a, b, c)  # noqa: E731
+    with torch.no_grad():
+        full = net(x, elev, mask)
+        got = merge_tiles([tiled_forward_2d(net, x, elev, mask, t) for t in plan], 2, 3)
+    assert got.shape == full.shape
+    assert float((got - full).abs().max()) <= 1e-5
+
+
 def _worker(rank, world, port, tmp):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "climate-super-resolution_b200"))
@@ -87,6 +112,28 @@ def _worker(rank, world, port, tmp):
         b.allreduce()
         for i, p in enumerate(lin.parameters()):
             assert torch.allclose(p.grad, torch.full_like(p, 1.5 * (i + 1)))
+        # ---- (4) the overlapped path's host logic: slices of a flat gradient buffer, reduced as they "complete" (suffix first),
+        # bf16 wire format averaged BEFORE the rounding, fp32 variant exact; unused parameters are refused like DDP does
+        from climsr_b200.parallel import BackwardGradSync
+        n = 1000
+        base = torch.arange(n, dtype=torch.float32) / 7.0
+        for dtype, tol in ((torch.bfloat16, 1.2e-2), (None, 1e-6)):     # two bf16 roundings of the operands + one of the sum
+            flat = base * (rank + 1)
+            sync = BackwardGradSync(nseg=3, comm_dtype=dtype)
+            assert sync.world == 2
+            pending = []
+            for lo, hi in ((700, 1000), (300, 700), (0, 300)):
+                sync.reduce_slice_async(flat, lo, hi, pending)
+            sync.finish(flat, pending)
+            want = base * 1.5
+            assert float(((flat - want).abs() / (want.abs() + 1e-3)).max()) <= tol
+            assert sync.last_ranges == [(700, 1000), (300, 700), (0, 300)]
+        lin[0].weight.grad = None
+        try:
+            GradientBucketer(lin.parameters(), comm_dtype=None).allreduce()
+            raise AssertionError("unused parameter was not refused")
+        except RuntimeError as e:
+            assert "no gradient" in str(e)
         with open(os.path.join(tmp, f"ok{rank}"), "w") as f:
             f.write("ok")
     finally:
