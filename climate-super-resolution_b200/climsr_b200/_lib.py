@@ -28,7 +28,14 @@ class ConvDesc(C.Structure):
                 ("out_coff", C.c_int32), ("act", C.c_int32), ("out_mode", C.c_int32), ("in_up2", C.c_int32),
                 ("transposed", C.c_int32), ("scale1", C.c_float), ("scale2", C.c_float),
                 ("res1_c", C.c_int32), ("res1_coff", C.c_int32), ("res2_c", C.c_int32), ("res2_coff", C.c_int32),
-                ("gate_c", C.c_int32), ("gate_coff", C.c_int32), ("gate_from", C.c_int32), ("gate_neg", C.c_float)]
+                ("gate_c", C.c_int32), ("gate_coff", C.c_int32), ("gate_from", C.c_int32), ("gate_neg", C.c_float),
+                ("act_slope", C.c_float)]
+
+
+class View(C.Structure):
+    """CsrView: the real outputs of a layer inside its (N, hs, ws, c) buffer - pixel (i, j) at (off + step*i, off + step*j)."""
+    _fields_ = [("hs", C.c_int32), ("ws", C.c_int32), ("c", C.c_int32), ("off", C.c_int32), ("step", C.c_int32),
+                ("hl", C.c_int32), ("wl", C.c_int32)]
 
 
 class WgradDesc(C.Structure):
@@ -87,6 +94,15 @@ def _load():
         "csr_masked_metrics": (C.c_int, [vp, vp, vp, vp, vp, vp, f32, f32, C.c_double, C.c_double, C.c_double, i32, i32, i32, vp, vp, sz, vp]),
         "csr_minmax_normalize": (C.c_int, [vp, i32, i32, i32, vp, vp, C.c_double, C.c_double, C.c_double, f32, vp, vp, vp, vp]),
         "csr_minmax_denormalize_mask": (C.c_int, [vp, vp, i32, i32, i32, i32, vp, vp, C.c_double, C.c_double, C.c_double, vp, vp]),
+        "csr_disc_gather": (C.c_int, [vp, C.POINTER(View), i32, vp, i32, vp, vp, vp]),
+        "csr_disc_collect": (C.c_int, [vp, C.POINTER(View), i32, i32, vp, f32, vp, vp]),
+        "csr_disc_bn_scratch_bytes": (sz, [i32]),
+        "csr_disc_bn_forward": (C.c_int, [vp, C.POINTER(View), i32, vp, vp, f32, f32, vp, vp, i32, vp, vp, vp, vp, vp, sz, vp]),
+        "csr_disc_bn_backward": (C.c_int, [vp, C.POINTER(View), i32, i32, vp, f32, vp, vp, vp, vp, vp, sz, vp, vp, vp, vp]),
+        "csr_disc_flatten": (C.c_int, [vp, C.POINTER(View), i32, vp, vp]),
+        "csr_disc_unflatten": (C.c_int, [vp, C.POINTER(View), i32, vp, vp]),
+        "csr_linear_forward": (C.c_int, [vp, vp, vp, vp, i32, i32, i32, vp]),
+        "csr_linear_backward": (C.c_int, [vp, vp, vp, vp, vp, vp, i32, i32, i32, vp]),
         "csr_grad_pack_bf16": (C.c_int, [vp, vp, sz, f32, vp]),
         "csr_grad_unpack_bf16": (C.c_int, [vp, vp, sz, f32, vp]),
         "csr_lr_input_from_hr": (C.c_int, [vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp]),
@@ -105,7 +121,9 @@ EXPORTS = ("csr_abi_version", "csr_last_error", "csr_device_check", "csr_set_opt
            "csr_packed_weight_bytes_bwd", "csr_pack_weights_bwd", "csr_plan_backward", "csr_plan_num_backward_ops", "csr_plan_grad_floats", "csr_plan_graph_status", "csr_plan_grad_offset",
            "csr_plan_backward_flat", "csr_plan_backward_segments", "csr_plan_backward_flat_seg", "csr_generator_forward", "csr_conv2d_scratch_bytes",
            "csr_conv2d_nhwc", "csr_conv2d_wgrad_scratch_bytes", "csr_conv2d_wgrad", "csr_nchw_f32_to_nhwc_bf16", "csr_nhwc_bf16_to_nchw_f32", "csr_pixel_loss_scratch_bytes", "csr_l1_loss", "csr_mse_loss",
-           "csr_metrics_scratch_bytes", "csr_masked_metrics", "csr_minmax_normalize", "csr_minmax_denormalize_mask", "csr_grad_pack_bf16", "csr_grad_unpack_bf16", "csr_lr_input_from_hr")
+           "csr_metrics_scratch_bytes", "csr_masked_metrics", "csr_minmax_normalize", "csr_minmax_denormalize_mask", "csr_disc_gather", "csr_disc_collect", "csr_disc_bn_scratch_bytes", "csr_disc_bn_forward",
+           "csr_disc_bn_backward", "csr_disc_flatten", "csr_disc_unflatten", "csr_linear_forward", "csr_linear_backward",
+           "csr_grad_pack_bf16", "csr_grad_unpack_bf16", "csr_lr_input_from_hr")
 
 
 def check(rc: int, what: str = "") -> None:

@@ -9,7 +9,7 @@ from torch import Tensor
 
 from ._lib import ConvDesc, WgradDesc, check, current_stream_ptr, lib
 
-ACT = {"none": 0, "lrelu": 1, "relu": 2}
+ACT = {"none": 0, "lrelu": 1, "relu": 2, "lrelu_slope": 4}
 OUT_MODE = {"nhwc": 0, "f32_planar": 2, "f32_nhwc": 3}
 
 
@@ -35,7 +35,8 @@ def conv2d_nhwc(inp: Tensor, weight: Tensor, bias: Optional[Tensor], *, act: str
                 out_coff: int = 0, out_mode: str = "nhwc", in_coff: int = 0, in_up2: bool = False, transposed: bool = False,
                 res1: Optional[Tensor] = None, res1_coff: int = 0, scale1: float = 1.0,
                 res2: Optional[Tensor] = None, res2_coff: int = 0, scale2: float = 1.0,
-                gate: Optional[Tensor] = None, gate_coff: int = 0, gate_from: int = 0, gate_neg: float = 0.2) -> Tensor:
+                gate: Optional[Tensor] = None, gate_coff: int = 0, gate_from: int = 0, gate_neg: float = 0.2,
+                act_slope: float = 0.0) -> Tensor:
     """One KxK stride-1 'same' conv on a bf16 NHWC buffer via csr_conv2d_nhwc.
 
     Reads input channels [in_coff, in_coff+cin); writes act(conv+bias) (then *scale1+res1, *scale2+res2, lrelu-gate) into
@@ -60,7 +61,7 @@ def conv2d_nhwc(inp: Tensor, weight: Tensor, bias: Optional[Tensor], *, act: str
     d = ConvDesc(n, h, w, cin, cout, kh, kw, in_c, in_coff, out_c, out_coff, ACT[act], mode, int(in_up2), int(transposed),
                  scale1, scale2, res1.shape[-1] if res1 is not None else 0, res1_coff,
                  res2.shape[-1] if res2 is not None else 0, res2_coff,
-                 gate.shape[-1] if gate is not None else 0, gate_coff, gate_from, gate_neg)
+                 gate.shape[-1] if gate is not None else 0, gate_coff, gate_from, gate_neg, act_slope)
     nbytes = lib.csr_conv2d_scratch_bytes(C.byref(d))
     scratch = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=inp.device)
     wc = weight.contiguous().float()

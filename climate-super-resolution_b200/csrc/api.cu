@@ -12,6 +12,7 @@
 
 #include "../../include/climsr_b200.h"
 #include "conv_tc.cuh"
+#include "disc.cuh"
 #include "elementwise.cuh"
 #include "loss.cuh"
 #include "metrics.cuh"
@@ -602,7 +603,9 @@ static int run_wgrad_layer(const WgradLayer& L, int N, int H, int W, const void*
       }
       for (int dy = 0; dy < ekh; dy += per) {
         WgradLaunch wl;
-        int rc = build_wgrad(sms, N, H, W, ekw, pw, dy - ph, std::min(per, ekh - dy), x, x_C, x_coff + ci0, g, g_C, g_coff, nullptr, 0, 0, ld_n,
+        // output-gradient columns [64, 128) come through a second 64-channel box of the same buffer
+        int rc = build_wgrad(sms, N, H, W, ekw, pw, dy - ph, std::min(per, ekh - dy), x, x_C, x_coff + ci0, g, g_C, g_coff, ld_n > 64 ? g : nullptr,
+                             ld_n > 64 ? g_C : 0, ld_n > 64 ? g_coff + 64 : 0, ld_n,
                              scratch + (size_t)dy * ekw * 128 * ld_n, part_stride, ld_n, &wl);
         n_parts = wl.p.n_parts;
         if (rc) return rc;
@@ -1795,7 +1798,7 @@ static int conv_desc_to_layer(const CsrConvDesc* d, LayerSpec* L) {
   if (!d) return fail(CSR_ERR_BAD_ARG, "conv descriptor is null");
   if (d->n < 1 || d->h < 1 || d->w < 1 || d->cin < 1 || d->cout < 1) return fail(CSR_ERR_BAD_ARG, "non-positive conv shape");
   if (!(d->kh & 1) || !(d->kw & 1) || d->kh > 9 || d->kw > 9) return fail(CSR_ERR_UNSUPPORTED, "kernel %dx%d (odd, <= 9 supported)", d->kh, d->kw);
-  if (d->cout > 256) return fail(CSR_ERR_UNSUPPORTED, "cout %d > 256", d->cout);
+  if (d->cout > 1024) return fail(CSR_ERR_UNSUPPORTED, "cout %d > 1024", d->cout);
   if (d->out_mode != CSR_OUT_BF16_NHWC && d->out_mode != CSR_OUT_F32_PLANAR && d->out_mode != CSR_OUT_F32_NHWC)
     return fail(CSR_ERR_BAD_ARG, "unknown out_mode %d", d->out_mode);
   if (d->out_mode == CSR_OUT_F32_PLANAR && d->cout != 1) return fail(CSR_ERR_UNSUPPORTED, "fp32 planar output needs cout == 1");
@@ -1835,6 +1838,7 @@ int csr_conv2d_nhwc(const CsrConvDesc* d, const void* in, const float* weight, c
   io.r1 = res1; io.r1_C = d->res1_c; io.r1_coff = d->res1_coff; io.s1 = d->scale1;
   io.r2 = res2; io.r2_C = d->res2_c; io.r2_coff = d->res2_coff; io.s2 = d->scale2;
   io.gate = gate; io.gate_C = d->gate_c; io.gate_coff = d->gate_coff; io.gate_from = d->gate_from; io.gate_neg = d->gate_neg;
+  if (d->act == CSR_ACT_LRELU && !(d->act_slope > 0.f && d->act_slope < 1.f)) return fail(CSR_ERR_BAD_ARG, "act_slope must be in (0, 1)");
   for (const PackPart& pp : packs[0].parts) {
     CSR_CUDA(launch_pack_weight(weight, base + pp.w_off, L.cout, L.cin, L.kh, L.kw, 0, pp.phase, L.transposed, 1.f, pp.co_lo, pp.npad,
                                 packs[0].cin_pad, s));
@@ -1842,6 +1846,7 @@ int csr_conv2d_nhwc(const CsrConvDesc* d, const void* in, const float* weight, c
     ConvLaunch cl;
     rc = build_conv(packs[0], pp, d->n, d->h, d->w, io, &cl);
     if (rc) return rc;
+    cl.p.act_slope = d->act_slope;
     cl.p.wpk = base + pp.w_off;
     cl.p.bias = reinterpret_cast<const float*>(base + pp.b_off);
     int e = launch_conv_tc(cl.p, cl.tmap, di.sms, s);
@@ -1955,6 +1960,103 @@ int csr_minmax_denormalize_mask(const float* sr, const float* mask, int32_t mask
   CSR_CUDA(launch_minmax_denormalize_mask(sr, mask, mask_per_sample ? (long)h * w : 0, n, (long)h * w, mn, mx, range_a, range_b, eps, out,
                                           reinterpret_cast<cudaStream_t>(stream)));
   ++g_launches;
+  return CSR_OK;
+}
+
+// ---- discriminator path: glue between the convolutions (disc.cu) ------------------------------------------------------
+static int view_of(const CsrView* v, DiscView* out) {
+  if (!v) return fail(CSR_ERR_BAD_ARG, "view is null");
+  if (v->c < 8 || v->c % 8 || v->hs < 1 || v->ws < 1 || v->hl < 1 || v->wl < 1 || v->step < 1 || v->off < 0 ||
+      v->off + v->step * (v->hl - 1) >= v->hs || v->off + v->step * (v->wl - 1) >= v->ws)
+    return fail(CSR_ERR_BAD_ARG, "bad view hs=%d ws=%d c=%d off=%d step=%d hl=%d wl=%d", v->hs, v->ws, v->c, v->off, v->step, v->hl, v->wl);
+  *out = {v->hs, v->ws, v->c, v->off, v->step, v->hl, v->wl};
+  return CSR_OK;
+}
+int csr_disc_gather(const void* src, const CsrView* view, int32_t n, void* dst, int32_t pad, const float* scale, const float* shift, void* stream) {
+  DiscView v;
+  int rc = view_of(view, &v);
+  if (rc) return rc;
+  if (!src || !dst || n < 1 || pad < 0 || pad > 1 || (pad && (v.Hl < 2 || v.Wl < 2)) || ((scale == nullptr) != (shift == nullptr)))
+    return fail(CSR_ERR_BAD_ARG, "csr_disc_gather: bad arguments");
+  CSR_CUDA(launch_disc_gather(src, v, n, dst, pad, scale, shift, reinterpret_cast<cudaStream_t>(stream)));
+  ++g_launches;
+  return CSR_OK;
+}
+int csr_disc_collect(const void* dpad, const CsrView* view, int32_t n, int32_t pad, const void* act, float gate_neg, void* g, void* stream) {
+  DiscView v;
+  int rc = view_of(view, &v);
+  if (rc) return rc;
+  if (!dpad || !g || n < 1 || pad < 0 || pad > 1) return fail(CSR_ERR_BAD_ARG, "csr_disc_collect: bad arguments");
+  CSR_CUDA(launch_disc_collect(dpad, v, n, pad, act, gate_neg, g, reinterpret_cast<cudaStream_t>(stream)));
+  ++g_launches;
+  return CSR_OK;
+}
+size_t csr_disc_bn_scratch_bytes(int32_t c) { return c > 0 ? (size_t)2 * c * sizeof(double) : 0; }
+int csr_disc_bn_forward(const void* src, const CsrView* view, int32_t n, const float* gamma, const float* beta, float eps, float momentum,
+                        float* running_mean, float* running_var, int32_t training, float* scale, float* shift, float* mean, float* invstd,
+                        void* scratch, size_t scratch_bytes, void* stream) {
+  DiscView v;
+  int rc = view_of(view, &v);
+  if (rc) return rc;
+  if (!src || !gamma || !beta || !scale || !shift || n < 1) return fail(CSR_ERR_BAD_ARG, "csr_disc_bn_forward: null pointer");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (!training) {
+    if (!running_mean || !running_var) return fail(CSR_ERR_BAD_ARG, "eval-mode BatchNorm needs the running statistics");
+    CSR_CUDA(launch_disc_bn_eval(v.C, gamma, beta, eps, running_mean, running_var, scale, shift, s));
+    ++g_launches;
+    return CSR_OK;
+  }
+  if (!mean || !invstd || !scratch || scratch_bytes < csr_disc_bn_scratch_bytes(v.C)) return fail(CSR_ERR_WORKSPACE, "BatchNorm scratch / statistics buffers");
+  if ((running_mean == nullptr) != (running_var == nullptr)) return fail(CSR_ERR_BAD_ARG, "running_mean and running_var go together");
+  CSR_CUDA(launch_disc_bn_stats(src, v, n, reinterpret_cast<double*>(scratch), s));
+  CSR_CUDA(launch_disc_bn_finalize(reinterpret_cast<double*>(scratch), v.C, (double)n * v.Hl * v.Wl, gamma, beta, eps, momentum, running_mean,
+                                   running_var, scale, shift, mean, invstd, s));
+  g_launches += 2;
+  return CSR_OK;
+}
+int csr_disc_bn_backward(const void* dpad, const CsrView* view, int32_t n, int32_t pad, const void* act, float gate_neg, const float* gamma,
+                         const float* mean, const float* invstd, float* dy_scratch, void* scratch, size_t scratch_bytes, void* g, float* dgamma,
+                         float* dbeta, void* stream) {
+  DiscView v;
+  int rc = view_of(view, &v);
+  if (rc) return rc;
+  if (!dpad || !act || !gamma || !mean || !invstd || !dy_scratch || !g || !dgamma || !dbeta || n < 1 || pad < 0 || pad > 1)
+    return fail(CSR_ERR_BAD_ARG, "csr_disc_bn_backward: bad arguments");
+  if (!scratch || scratch_bytes < csr_disc_bn_scratch_bytes(v.C)) return fail(CSR_ERR_WORKSPACE, "BatchNorm scratch too small");
+  CSR_CUDA(launch_disc_bn_backward(dpad, v, n, pad, act, gate_neg, gamma, mean, invstd, dy_scratch, reinterpret_cast<double*>(scratch), g, dgamma,
+                                   dbeta, reinterpret_cast<cudaStream_t>(stream)));
+  g_launches += 2;
+  return CSR_OK;
+}
+int csr_disc_flatten(const void* src, const CsrView* view, int32_t n, float* feats, void* stream) {
+  DiscView v;
+  int rc = view_of(view, &v);
+  if (rc) return rc;
+  if (!src || !feats || n < 1) return fail(CSR_ERR_BAD_ARG, "null pointer");
+  CSR_CUDA(launch_disc_flatten(src, v, n, feats, reinterpret_cast<cudaStream_t>(stream)));
+  ++g_launches;
+  return CSR_OK;
+}
+int csr_disc_unflatten(const float* gfeat, const CsrView* view, int32_t n, void* g, void* stream) {
+  DiscView v;
+  int rc = view_of(view, &v);
+  if (rc) return rc;
+  if (!gfeat || !g || n < 1) return fail(CSR_ERR_BAD_ARG, "null pointer");
+  CSR_CUDA(launch_disc_unflatten(gfeat, v, n, g, reinterpret_cast<cudaStream_t>(stream)));
+  ++g_launches;
+  return CSR_OK;
+}
+int csr_linear_forward(const float* x, const float* w, const float* b, float* y, int32_t n, int32_t k, int32_t j, void* stream) {
+  if (!x || !w || !y || n < 1 || k < 1 || j < 1 || n > 65535) return fail(CSR_ERR_BAD_ARG, "csr_linear_forward: bad arguments");
+  CSR_CUDA(launch_linear_forward(x, w, b, y, n, k, j, reinterpret_cast<cudaStream_t>(stream)));
+  ++g_launches;
+  return CSR_OK;
+}
+int csr_linear_backward(const float* x, const float* w, const float* gy, float* dx, float* dw, float* db, int32_t n, int32_t k, int32_t j,
+                        void* stream) {
+  if (!x || !w || !gy || n < 1 || k < 1 || j < 1) return fail(CSR_ERR_BAD_ARG, "csr_linear_backward: bad arguments");
+  CSR_CUDA(launch_linear_backward(x, w, gy, dx, dw, db, n, k, j, reinterpret_cast<cudaStream_t>(stream)));
+  g_launches += (dx ? 1 : 0) + (dw ? 1 : 0);
   return CSR_OK;
 }
 

@@ -69,8 +69,11 @@ __device__ __forceinline__ Tile decode_tile(const ConvParams& p, int t) {
 }
 
 // The epilogue is instruction-issue bound: its fp32 arithmetic uses the packed two-wide forms (FADD2 / FMUL2 / FFMA2).
-__device__ __forceinline__ void apply_act8(float (&v)[8], int act) {
-  if (act == 1) {                                       // LeakyReLU(0.2) = max(v, 0.2 v)
+__device__ __forceinline__ void apply_act8(float (&v)[8], int act, float slope = 0.f) {
+  if (act == 4) {                                       // LeakyReLU(slope), 0 < slope < 1 (discriminator: 0.01): generic kernels only
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], slope * v[j]);
+  } else if (act == 1) {                                       // LeakyReLU(0.2) = max(v, 0.2 v)
 #pragma unroll
     for (int j = 0; j < 8; j += 2) {
       const float2 t = __fmul2_rn(make_float2(v[j], v[j + 1]), make_float2(0.2f, 0.2f));
@@ -616,7 +619,7 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
           if (act == 3) {
             if (ch0 < p.act_upto) apply_act8(v, 1);
           } else {
-            apply_act8(v, act);
+            apply_act8(v, act, p.act_slope);
           }
           if (need_pix) {
             if (has_r1 && !r1_pre) fma_residual8(v, q1[j], p.s1);

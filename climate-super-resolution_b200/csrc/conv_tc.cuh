@@ -61,8 +61,9 @@ struct ConvParams {
   // epilogue:  v = act(acc + bias [+ r1 if r1_pre]);  if r1 (not r1_pre): v = v*s1 + r1;  if r2: v = v*s2 + r2;  if gate: v *= (gate > 0 ? 1 : gate_neg)
   const float* bias;   // [npad] fp32 (zero padded)
   const void* wpk;     // packed bf16 weights (global), layout [kblock][dy][kstep in kblock][KW*npad/8][2][8][8]
-  int act;             // 0 none, 1 leaky-relu 0.2, 2 relu, 3 leaky-relu 0.2 on output channels < act_upto only
+  int act;             // 0 none, 1 leaky-relu 0.2, 2 relu, 3 leaky-relu 0.2 on output channels < act_upto only, 4 leaky-relu(act_slope)
   int act_upto;
+  float act_slope;     // act == 4: LeakyReLU negative slope
   int r1_pre;          // 1: r1 is added BEFORE the activation (v = act(acc + bias + r1)) instead of after it
   float s1, s2;
   const void* r1; int r1_C, r1_coff;

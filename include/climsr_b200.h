@@ -60,7 +60,8 @@ typedef struct CsrNetDesc {
 } CsrNetDesc;
 
 /* Epilogue of a single convolution (csr_conv2d_nhwc). */
-typedef enum CsrAct { CSR_ACT_NONE = 0, CSR_ACT_LRELU02 = 1, CSR_ACT_RELU = 2 } CsrAct;
+typedef enum CsrAct { CSR_ACT_NONE = 0, CSR_ACT_LRELU02 = 1, CSR_ACT_RELU = 2,
+                      CSR_ACT_LRELU = 4 /* LeakyReLU(CsrConvDesc::act_slope): the discriminator's 0.01 */ } CsrAct;
 typedef enum CsrOutMode {
   CSR_OUT_BF16_NHWC = 0,     /* bf16, channel slice [out_coff, out_coff+cout) of an NHWC buffer          */
   CSR_OUT_F32_PLANAR = 2,    /* fp32 (N,1,H,W); cout must be 1                                            */
@@ -86,6 +87,7 @@ typedef struct CsrConvDesc {
   int32_t res2_c, res2_coff;
   int32_t gate_c, gate_coff, gate_from;   /* gate buffer: bf16 NHWC (saved forward activations)            */
   float   gate_neg;
+  float   act_slope;          /* negative slope when act == CSR_ACT_LRELU                                   */
 } CsrConvDesc;
 
 /* ---- library ------------------------------------------------------------------------------- */
@@ -220,6 +222,38 @@ int     csr_masked_metrics(const float* sr, const float* hr, const float* origin
                            const double* mn, const double* mx, float zmean, float zstd,
                            double range_a, double range_b, double eps, int32_t n, int32_t h, int32_t w,
                            float* out, void* scratch, size_t scratch_bytes, void* stream);
+
+/* ---- discriminator path ------------------------------------------------------------------
+ * Replaces climsr.models.discriminator.Discriminator.forward (climsr/models/discriminator.py:5-46) and its autograd
+ * backward, driven four times forward / twice backward per GAN batch by climsr/task/pl_gan.py:28-61.  The 3x3 convolutions
+ * (stride 1 and 2, reflection-padded or valid) run on csr_conv2d_nhwc / csr_conv2d_wgrad over reflection-padded NHWC bf16
+ * buffers; these entry points are everything in between.  A CsrView names the real outputs of a layer inside its buffer
+ * (N, hs, ws, c): logical pixel (i, j), i < hl, j < wl, lives at (off + step*i, off + step*j) - off 1 = interior of a
+ * same-conv over a padded input, step 2 = the stride-2 convs.  All buffers bf16 NHWC unless noted.
+ *   csr_disc_gather      dst (n, hl+2*pad, wl+2*pad, c) = ReflectionPad2d(pad)(view) [* scale[c] + shift[c]: BatchNorm on load]
+ *   csr_disc_collect     its backward without BatchNorm: g (S layout) = lrelu'(act) * gathered dP on logical pixels, 0 elsewhere
+ *   csr_disc_bn_forward  nn.BatchNorm2d over the logical pixels: training = batch statistics (+ running-statistics update),
+ *                        eval = running statistics; emits scale/shift for csr_disc_gather and mean/invstd for the backward
+ *   csr_disc_bn_backward g = lrelu'(act) * BN-backward(gathered dP); dgamma / dbeta are accumulated (+=)
+ *   csr_disc_flatten / csr_disc_unflatten   x.view(N, -1) of the NCHW tensor (fp32 features) and its backward
+ *   csr_linear_forward / csr_linear_backward   nn.Linear in fp32 (8192 -> 100 -> 1); dW / db are accumulated (+=)      */
+typedef struct CsrView { int32_t hs, ws, c, off, step, hl, wl; } CsrView;
+int     csr_disc_gather(const void* src, const CsrView* view, int32_t n, void* dst, int32_t pad, const float* scale,
+                        const float* shift, void* stream);
+int     csr_disc_collect(const void* dpad, const CsrView* view, int32_t n, int32_t pad, const void* act, float gate_neg,
+                         void* g, void* stream);
+size_t  csr_disc_bn_scratch_bytes(int32_t c);
+int     csr_disc_bn_forward(const void* src, const CsrView* view, int32_t n, const float* gamma, const float* beta, float eps,
+                            float momentum, float* running_mean, float* running_var, int32_t training, float* scale,
+                            float* shift, float* mean, float* invstd, void* scratch, size_t scratch_bytes, void* stream);
+int     csr_disc_bn_backward(const void* dpad, const CsrView* view, int32_t n, int32_t pad, const void* act, float gate_neg,
+                             const float* gamma, const float* mean, const float* invstd, float* dy_scratch, void* scratch,
+                             size_t scratch_bytes, void* g, float* dgamma, float* dbeta, void* stream);
+int     csr_disc_flatten(const void* src, const CsrView* view, int32_t n, float* feats, void* stream);
+int     csr_disc_unflatten(const float* gfeat, const CsrView* view, int32_t n, void* g, void* stream);
+int     csr_linear_forward(const float* x, const float* w, const float* b, float* y, int32_t n, int32_t k, int32_t j, void* stream);
+int     csr_linear_backward(const float* x, const float* w, const float* gy, float* dx, float* dw, float* db, int32_t n,
+                            int32_t k, int32_t j, void* stream);
 
 /* ---- gradient exchange of data-parallel training ("bf16 gradients are reduced with NCCL over NVLink,
  * bucketed and overlapped with backward"; replaces the gradient all-reduce of Lightning's DDP plugin, conf/trainer/
