@@ -49,10 +49,18 @@ def _collect(dpad: Tensor, view: View, n: int, pad: int, act, gate_neg: float) -
     return g
 
 
-def _conv(p: Tensor, w: Tensor, b: Tensor, slope: float) -> Tensor:
+def _conv(p: Tensor, w: Tensor, b: Tensor, slope: float, cache=None) -> Tensor:
+    """One conv layer; ``cache`` = (scratch tensor, prepacked flag) from ``Discriminator._packed``."""
+    scratch, pre = cache if cache is not None else (None, False)
     if slope:
-        return ops.conv2d_nhwc(p, w, b, act="lrelu_slope", act_slope=slope)
-    return ops.conv2d_nhwc(p, w, b, act="none")
+        return ops.conv2d_nhwc(p, w, b, act="lrelu_slope", act_slope=slope, scratch=scratch, prepacked=pre)
+    return ops.conv2d_nhwc(p, w, b, act="none", scratch=scratch, prepacked=pre)
+
+
+def _conv_t(g: Tensor, w: Tensor, cache=None) -> Tensor:
+    """Input gradient of a conv layer (transposed / flipped weights)."""
+    scratch, pre = cache if cache is not None else (None, False)
+    return ops.conv2d_nhwc(g, w, None, transposed=True, scratch=scratch, prepacked=pre)
 
 
 def _wgrad(p: Tensor, g: Tensor, w: Tensor):
@@ -107,6 +115,40 @@ class Discriminator(nn.Module):
         self.avgpool = nn.AdaptiveAvgPool2d((512, 512))      # never called in the reference either (discriminator.py:38,42-46)
         self.classification = nn.Sequential(nn.Linear(8192, 100), nn.Linear(100, 1))
 
+    # ------------------------------------------------------------------ packed-weight cache
+    def _packed(self, conv: nn.Conv2d, transposed: bool):
+        """(scratch, prepacked) for one conv layer: the packed bf16 weight tiles are reused until the weights change - the four
+        forwards and two backwards of a GAN batch (pl_gan.py:28-61) see at most two weight versions.  Keyed like the generator's
+        pack cache: storage pointer, version counter and the process-wide optimizer-step epoch (fused optimizers do not bump
+        version counters)."""
+        from .esrgan import _WEIGHT_EPOCH
+        cache = self.__dict__.setdefault("_pack_cache", {})
+        w, b = conv.weight, conv.bias
+        key = (w.data_ptr(), w._version, b.data_ptr(), b._version, _WEIGHT_EPOCH[0], w.device)
+        ent = cache.get((id(conv), transposed))
+        if ent is not None and ent[1] == key:
+            return ent[0], True
+        nbytes = ops.conv2d_scratch_bytes(conv.out_channels, conv.in_channels, 3, 3, transposed) if not transposed else \
+            ops.conv2d_scratch_bytes(conv.in_channels, conv.out_channels, 3, 3, True)
+        scratch = ent[0] if ent is not None and ent[0].numel() >= nbytes and ent[0].device == w.device else \
+            torch.empty(max(nbytes, 16), dtype=torch.uint8, device=w.device)
+        cache[(id(conv), transposed)] = (scratch, key)
+        return scratch, False
+
+    def __getstate__(self):
+        state = dict(self.__dict__)
+        state.pop("_pack_cache", None)
+        return state
+
+    def __deepcopy__(self, memo):
+        import copy
+        new = self.__class__.__new__(self.__class__)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            if k != "_pack_cache":
+                new.__dict__[k] = copy.deepcopy(v, memo)
+        return new
+
     # ------------------------------------------------------------------ layer table
     def _layers(self):
         fe = self.feature_extraction
@@ -140,7 +182,7 @@ class Discriminator(nn.Module):
             for conv_a, bn, conv_b in stages:
                 c = conv_a.out_channels
                 pa = _gather(buf, view, n, 1, scale, shift)
-                sa = _conv(pa, f32(conv_a.weight), f32(conv_a.bias), SLOPE)
+                sa = _conv(pa, f32(conv_a.weight), f32(conv_a.bias), SLOPE, self._packed(conv_a, False))
                 va = View(view.hl + 2, view.wl + 2, c, 1, 1, view.hl, view.wl)
                 scale = torch.empty(c, dtype=torch.float32, device=dev)
                 shift = torch.empty_like(scale)
@@ -158,17 +200,17 @@ class Discriminator(nn.Module):
                                               scale.data_ptr(), shift.data_ptr(), mean.data_ptr(), invstd.data_ptr(), scratch.data_ptr(), nbytes,
                                               current_stream_ptr()), "csr_disc_bn_forward")
                 pb = _gather(sa, va, n, 1, scale, shift)
-                sb = _conv(pb, f32(conv_b.weight), f32(conv_b.bias), SLOPE)
+                sb = _conv(pb, f32(conv_b.weight), f32(conv_b.bias), SLOPE, self._packed(conv_b, False))
                 vb = View(va.hl + 2, va.wl + 2, c, 1, 2, va.hl // 2, va.wl // 2)
                 if save:
                     saved["stages"].append({"pa": pa, "sa": sa, "va": va, "mean": mean, "invstd": invstd, "pb": pb, "sb": sb, "vb": vb,
                                             "bn_training": training})
                 buf, view, scale, shift = sb, vb, None, None
             p4 = _gather(buf, view, n, 0)                                          # valid convs: no padding
-            s4 = _conv(p4, f32(conv4.weight), f32(conv4.bias), SLOPE_TAIL)
+            s4 = _conv(p4, f32(conv4.weight), f32(conv4.bias), SLOPE_TAIL, self._packed(conv4, False))
             v4 = View(view.hl, view.wl, 512, 1, 1, view.hl - 2, view.wl - 2)
             p5 = _gather(s4, v4, n, 0)
-            s5 = _conv(p5, f32(conv5.weight), f32(conv5.bias), 0.0)
+            s5 = _conv(p5, f32(conv5.weight), f32(conv5.bias), 0.0, self._packed(conv5, False))
             v5 = View(v4.hl, v4.wl, 512, 1, 1, v4.hl - 2, v4.wl - 2)
             k = 512 * v5.hl * v5.wl
             feats = torch.empty((n, k), dtype=torch.float32, device=dev)
@@ -212,11 +254,11 @@ class Discriminator(nn.Module):
             w5, w4 = f32(conv5.weight), f32(conv4.weight)
             if need_params:
                 grads[conv5] = _wgrad(sv["p5"], g5, w5)
-            dp5 = ops.conv2d_nhwc(g5, w5, None, transposed=True)
+            dp5 = _conv_t(g5, w5, self._packed(conv5, True))
             g4 = _collect(dp5, v4, n, 0, sv["s4"], SLOPE_TAIL)
             if need_params:
                 grads[conv4] = _wgrad(sv["p4"], g4, w4)
-            dp = ops.conv2d_nhwc(g4, w4, None, transposed=True)
+            dp = _conv_t(g4, w4, self._packed(conv4, True))
             pad_next = 0
             for (conv_a, bn, conv_b), st in zip(reversed(stages), reversed(sv["stages"])):
                 c = conv_a.out_channels
@@ -224,7 +266,7 @@ class Discriminator(nn.Module):
                 wb = f32(conv_b.weight)
                 if need_params:
                     grads[conv_b] = _wgrad(st["pb"], gb, wb)
-                dpb = ops.conv2d_nhwc(gb, wb, None, transposed=True)
+                dpb = _conv_t(gb, wb, self._packed(conv_b, True))
                 va = st["va"]
                 ga = torch.empty((n, va.hs, va.ws, c), dtype=torch.bfloat16, device=dev)
                 dgamma = torch.zeros(c, dtype=torch.float32, device=dev)
@@ -245,7 +287,7 @@ class Discriminator(nn.Module):
                     grads[conv_a] = _wgrad(st["pa"], ga, wa)
                 is_first = conv_a is stages[0][0]
                 if not is_first or need_dx:
-                    dp = ops.conv2d_nhwc(ga, wa, None, transposed=True)
+                    dp = _conv_t(ga, wa, self._packed(conv_a, True))
                 pad_next = 1
             dx = None
             if need_dx:

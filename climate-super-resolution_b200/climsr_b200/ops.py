@@ -36,7 +36,7 @@ def conv2d_nhwc(inp: Tensor, weight: Tensor, bias: Optional[Tensor], *, act: str
                 res1: Optional[Tensor] = None, res1_coff: int = 0, scale1: float = 1.0,
                 res2: Optional[Tensor] = None, res2_coff: int = 0, scale2: float = 1.0,
                 gate: Optional[Tensor] = None, gate_coff: int = 0, gate_from: int = 0, gate_neg: float = 0.2,
-                act_slope: float = 0.0) -> Tensor:
+                act_slope: float = 0.0, scratch: Optional[Tensor] = None, prepacked: bool = False) -> Tensor:
     """One KxK stride-1 'same' conv on a bf16 NHWC buffer via csr_conv2d_nhwc.
 
     Reads input channels [in_coff, in_coff+cin); writes act(conv+bias) (then *scale1+res1, *scale2+res2, lrelu-gate) into
@@ -63,14 +63,26 @@ def conv2d_nhwc(inp: Tensor, weight: Tensor, bias: Optional[Tensor], *, act: str
                  res2.shape[-1] if res2 is not None else 0, res2_coff,
                  gate.shape[-1] if gate is not None else 0, gate_coff, gate_from, gate_neg, act_slope)
     nbytes = lib.csr_conv2d_scratch_bytes(C.byref(d))
-    scratch = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=inp.device)
-    wc = weight.contiguous().float()
-    bc = bias.contiguous().float() if bias is not None else None
-    check(lib.csr_conv2d_nhwc(C.byref(d), inp.data_ptr(), wc.data_ptr(), bc.data_ptr() if bc is not None else None, out.data_ptr(),
+    if scratch is None:
+        if prepacked:
+            raise ValueError("prepacked=True needs the scratch buffer of the call that packed the weights")
+        scratch = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=inp.device)
+    elif scratch.numel() < nbytes:
+        raise ValueError(f"scratch holds {scratch.numel()} bytes, the layer needs {nbytes}")
+    # prepacked: `scratch` already holds this layer's packed weights / bias (same weights, same shape): skip the pack launch
+    wc = None if prepacked else weight.contiguous().float()
+    bc = bias.contiguous().float() if (bias is not None and not prepacked) else None
+    check(lib.csr_conv2d_nhwc(C.byref(d), inp.data_ptr(), wc.data_ptr() if wc is not None else None, bc.data_ptr() if bc is not None else None, out.data_ptr(),
                               res1.data_ptr() if res1 is not None else None, res2.data_ptr() if res2 is not None else None,
                               gate.data_ptr() if gate is not None else None,
                               scratch.data_ptr(), nbytes, current_stream_ptr()), "csr_conv2d_nhwc")
     return out
+
+
+def conv2d_scratch_bytes(cout: int, cin: int, kh: int, kw: int, transposed: bool = False) -> int:
+    """Bytes of packed weights + bias of one layer (shape-only query)."""
+    d = ConvDesc(1, 8, 8, cin, cout, kh, kw, 64, 0, 64, 0, 0, 0, 0, int(transposed), 1.0, 1.0, 0, 0, 0, 0, 0, 0, 0, 0.2, 0.0)
+    return int(lib.csr_conv2d_scratch_bytes(C.byref(d)))
 
 
 def conv2d_wgrad(x: Tensor, g: Tensor, weight_shape, *, x_coff: int = 0, g_coff: int = 0, in_up2: bool = False, scale: float = 1.0,

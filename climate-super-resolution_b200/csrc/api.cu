@@ -88,12 +88,26 @@ struct DeviceInfo {
 static int device_info(DeviceInfo* out) {
   int dev = 0;
   CSR_CUDA(cudaGetDevice(&dev));
-  cudaDeviceProp prop;
-  CSR_CUDA(cudaGetDeviceProperties(&prop, dev));
-  if (prop.major != 10) return fail(CSR_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library is sm_100a only", dev, prop.major, prop.minor);
+  // cudaGetDeviceProperties costs milliseconds: the single-op entry points (csr_conv2d_nhwc, csr_conv2d_wgrad - ~100 calls per
+  // discriminator step) must not pay it per call
+  static DeviceInfo cache[64];
+  static std::mutex mu;
+  if (dev >= 0 && dev < 64) {
+    std::lock_guard<std::mutex> lock(mu);
+    if (cache[dev].ok) { *out = cache[dev]; return CSR_OK; }
+  }
+  int major = 0, minor = 0, sms = 0;
+  CSR_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  CSR_CUDA(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev));
+  CSR_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  if (major != 10) return fail(CSR_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library is sm_100a only", dev, major, minor);
   out->ok = true;
-  out->sms = prop.multiProcessorCount;
+  out->sms = sms;
   out->dev = dev;
+  if (dev >= 0 && dev < 64) {
+    std::lock_guard<std::mutex> lock(mu);
+    cache[dev] = *out;
+  }
   return CSR_OK;
 }
 
@@ -1361,6 +1375,10 @@ static int run_pack_jobs(const std::vector<PackJob>& jobs, void* key, cudaStream
   static std::map<void*, Cached> cache;
   static std::mutex mu;
   std::lock_guard<std::mutex> lock(mu);
+  if (cache.size() > 512 && !cache.count(key)) {        // single-op callers hand in ever new scratch buffers: bound the table
+    for (auto& kv : cache) if (kv.second.dev) cudaFree(kv.second.dev);
+    cache.clear();
+  }
   Cached& c = cache[key];
   const size_t bytes = jobs.size() * sizeof(PackJob);
   const bool same = c.dev && c.host.size() == jobs.size() && memcmp(c.host.data(), jobs.data(), bytes) == 0;
@@ -1821,7 +1839,7 @@ int csr_conv2d_nhwc(const CsrConvDesc* d, const void* in, const float* weight, c
   LayerSpec L;
   int rc = conv_desc_to_layer(d, &L);
   if (rc) return rc;
-  if (!in || !weight || !out || !scratch) return fail(CSR_ERR_BAD_ARG, "null pointer");
+  if (!in || !out || !scratch) return fail(CSR_ERR_BAD_ARG, "null pointer");
   DeviceInfo di;
   rc = device_info(&di);
   if (rc) return rc;
@@ -1839,10 +1857,17 @@ int csr_conv2d_nhwc(const CsrConvDesc* d, const void* in, const float* weight, c
   io.r2 = res2; io.r2_C = d->res2_c; io.r2_coff = d->res2_coff; io.s2 = d->scale2;
   io.gate = gate; io.gate_C = d->gate_c; io.gate_coff = d->gate_coff; io.gate_from = d->gate_from; io.gate_neg = d->gate_neg;
   if (d->act == CSR_ACT_LRELU && !(d->act_slope > 0.f && d->act_slope < 1.f)) return fail(CSR_ERR_BAD_ARG, "act_slope must be in (0, 1)");
+  if (weight) {
+    // all parts of the layer in ONE pack launch (a 512 -> 512 layer has 32 parts).  weight == NULL: `scratch` still holds the
+    // packed weights / bias of an earlier call with the same layer shape and weights (callers cache it per weight version)
+    std::vector<PackJob> jobs;
+    for (const PackPart& pp : packs[0].parts)
+      jobs.push_back({weight, bias, base + pp.w_off, reinterpret_cast<float*>(base + pp.b_off), L.cout, L.cin, L.kh, L.kw, 0, pp.phase, L.transposed,
+                      1.f, pp.co_lo, pp.npad, packs[0].cin_pad, 0, 0, 0, 0});
+    rc = run_pack_jobs(jobs, scratch, s);
+    if (rc) return rc;
+  }
   for (const PackPart& pp : packs[0].parts) {
-    CSR_CUDA(launch_pack_weight(weight, base + pp.w_off, L.cout, L.cin, L.kh, L.kw, 0, pp.phase, L.transposed, 1.f, pp.co_lo, pp.npad,
-                                packs[0].cin_pad, s));
-    CSR_CUDA(launch_pack_bias(bias, reinterpret_cast<float*>(base + pp.b_off), bias ? L.cout : 0, pp.co_lo, pp.npad, s));
     ConvLaunch cl;
     rc = build_conv(packs[0], pp, d->n, d->h, d->w, io, &cl);
     if (rc) return rc;
@@ -1851,7 +1876,7 @@ int csr_conv2d_nhwc(const CsrConvDesc* d, const void* in, const float* weight, c
     cl.p.bias = reinterpret_cast<const float*>(base + pp.b_off);
     int e = launch_conv_tc(cl.p, cl.tmap, di.sms, s);
     if (e) return fail(CSR_ERR_CUDA, "conv launch failed: %s", cudaGetErrorString((cudaError_t)e));
-    g_launches += 3;
+    ++g_launches;
   }
   return CSR_OK;
 }

@@ -164,9 +164,10 @@ int     csr_plan_backward_segments(CsrPlan* plan, int32_t nseg);
 int     csr_plan_backward_flat_seg(CsrPlan* plan, const void* packed_bwd, const float* grad_out, float* flat_grads,
                                    int32_t seg, size_t* lo, size_t* hi, void* stream);
 
-/* ---- single convolution (building block; used by the parity tests) --------------------------
+/* ---- single convolution (building block of the discriminator path; used by the parity tests) --------------
  * in: bf16 NHWC (n,h,w,in_c); weight fp32 OIHW (cout,cin,kh,kw); bias fp32 (cout) or NULL (= zeros).
- * scratch: >= csr_conv2d_scratch_bytes() device bytes for the packed weights.                   */
+ * scratch: >= csr_conv2d_scratch_bytes() device bytes for the packed weights.  weight == NULL: `scratch` still holds the
+ * packed weights (and bias) of an earlier call for the same layer - callers cache it per weight version.              */
 size_t  csr_conv2d_scratch_bytes(const CsrConvDesc* d);
 int     csr_conv2d_nhwc(const CsrConvDesc* d, const void* in, const float* weight, const float* bias,
                         void* out, const void* res1, const void* res2, const void* gate,

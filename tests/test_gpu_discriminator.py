@@ -84,8 +84,8 @@ def test_all_gradients_and_running_statistics_match_stock_pytorch():
     conv_outs = []
     orig_conv = D._conv
 
-    def spy(p, wt, b, slope):
-        o = orig_conv(p, wt, b, slope)
+    def spy(p, wt, b, slope, cache=None):
+        o = orig_conv(p, wt, b, slope, cache)
         conv_outs.append(o)
         return o
     D._conv = spy

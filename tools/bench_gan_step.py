@@ -1,4 +1,5 @@
-"""cfg3 GAN training step: generator = this repo's CUDA path, discriminator = stock PyTorch.
+"""cfg3 GAN training step: generator AND discriminator on this repo's CUDA path (--disc cuda, default), or the
+discriminator as stock PyTorch / cuDNN (--disc torch: the round-1 configuration, kept as the comparison).
 
 One step follows climsr/task/pl_gan.py:28-108 with its two optimizers: (1) sr = G(x); loss_G = 0.01 * L1(sr, hr) +
 0.005 * relativistic-average BCE(D(hr), D(sr)) (+ 1.0 * perceptual, DISABLED here: VGG19 weights need a download,
@@ -25,7 +26,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "climate-super-resolution_b200"))
 from climsr_b200 import losses  # noqa: E402
 from climsr_b200.models import ESRGANGenerator  # noqa: E402
-from climsr_b200.parallel import GradientBucketer  # noqa: E402
+from climsr_b200.models.discriminator import Discriminator  # noqa: E402
+from climsr_b200.parallel import GradientBucketer, attach_ddp, configure_nccl_for_overlap  # noqa: E402
 
 
 def make_discriminator(width=64, stages=4):
@@ -47,16 +49,19 @@ def main():
     ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--disc", default="cuda", choices=["cuda", "torch"])
     args = ap.parse_args()
     world, rank, local = (int(os.environ.get(k, d)) for k, d in (("WORLD_SIZE", "1"), ("RANK", "0"), ("LOCAL_RANK", "0")))
     torch.cuda.set_device(local)
     if world > 1:
+        configure_nccl_for_overlap()
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     torch.manual_seed(rank)
     n, h = args.batch, 32
     G = ESRGANGenerator(4, 1, 64, 11, 16).to(dev).train()
-    D = make_discriminator().to(dev).to(memory_format=torch.channels_last).train()
+    D = (Discriminator().to(dev) if args.disc == "cuda" else make_discriminator().to(dev).to(memory_format=torch.channels_last)).train()
+    g_sync = attach_ddp(G) if world > 1 else None            # generator gradients: exchanged inside its backward
     opt_g = torch.optim.AdamW(G.parameters(), lr=1e-4, weight_decay=1e-4, fused=True)
     opt_d = torch.optim.AdamW(D.parameters(), lr=1e-4, weight_decay=1e-4, fused=True)
     bg = GradientBucketer(G.parameters(), bucket_mb=4.0)
@@ -69,6 +74,8 @@ def main():
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
 
     def d_scores(a, b):
+        if args.disc == "cuda":
+            return D(a), D(b)
         with torch.autocast("cuda", dtype=torch.bfloat16):
             return D(a).float(), D(b).float()
 
@@ -83,8 +90,12 @@ def main():
         s_real, s_fake = d_scores(hr, sr)
         adv = (relativistic(s_fake, s_real, real) + relativistic(s_real, s_fake, fake)) / 2
         loss_g = 0.01 * losses.l1_loss(sr, hr) + 0.005 * adv
+        for p_ in D.parameters():                             # Lightning's toggle_optimizer: only the generator trains here
+            p_.requires_grad_(False)
         loss_g.backward()
-        if world > 1:
+        for p_ in D.parameters():
+            p_.requires_grad_(True)
+        if world > 1 and g_sync is None:
             bg.allreduce()
         opt_g.step()
         if timed:
@@ -119,8 +130,9 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     if rank == 0:
-        print(json.dumps({"workload": f"cfg3 GAN step, batch {n}/GPU of 128x128 HR, Hydra generator (CUDA path) + stock PyTorch discriminator "
-                                      "(bf16 autocast, channels_last), perceptual term disabled", "n_gpus": world,
+        print(json.dumps({"workload": f"cfg3 GAN step, batch {n}/GPU of 128x128 HR, Hydra generator (CUDA path) + " +
+                                      ("discriminator on the CUDA path" if args.disc == "cuda" else "stock PyTorch discriminator (bf16 autocast, channels_last)") +
+                                      ", perceptual term disabled", "n_gpus": world,
                           "ms_per_step_max_over_ranks": float(t), "hr_mpx_s": world * n * 128 * 128 / float(t) / 1e3,
                           "split_ms_rank0": {"G_forward_train": ms[0], "D(hr),D(sr)_fwd + loss_G backward (through D and G) + allreduce + G step": ms[1],
                                              "G_forward_again (common_step of optimizer 1)": ms[2], "D fwd x2 + D backward + allreduce + D step": ms[3]}}))
