@@ -16,6 +16,7 @@
 #include "elementwise.cuh"
 #include "loss.cuh"
 #include "metrics.cuh"
+#include "rcan.cuh"
 #include "rdb_tc.cuh"
 #include "wgrad_tc.cuh"
 
@@ -2082,6 +2083,25 @@ int csr_linear_backward(const float* x, const float* w, const float* gy, float* 
   if (!x || !w || !gy || n < 1 || k < 1 || j < 1) return fail(CSR_ERR_BAD_ARG, "csr_linear_backward: bad arguments");
   CSR_CUDA(launch_linear_backward(x, w, gy, dx, dw, db, n, k, j, reinterpret_cast<cudaStream_t>(stream)));
   g_launches += (dx ? 1 : 0) + (dw ? 1 : 0);
+  return CSR_OK;
+}
+
+// ---- RCAN generator: glue between the convolutions (rcan.cu) ---------------------------------------------------------
+int csr_channel_attention(const void* res, const void* x, const float* w1, const float* b1, const float* w2, const float* b2, void* out,
+                          float* pooled_scratch, int32_t n, int32_t h, int32_t w, int32_t c, int32_t c_reduced, void* stream) {
+  if (!res || !x || !w1 || !b1 || !w2 || !b2 || !out || !pooled_scratch) return fail(CSR_ERR_BAD_ARG, "null pointer");
+  if (n < 1 || n > 65535 || h < 1 || w < 1 || c < 8 || c % 8 || c > 512 || c_reduced < 1 || c_reduced > c)
+    return fail(CSR_ERR_BAD_ARG, "csr_channel_attention: bad shape n=%d h=%d w=%d c=%d c_reduced=%d", n, h, w, c, c_reduced);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  CSR_CUDA(launch_channel_pool(res, n, (long)h * w, c, pooled_scratch, s));
+  CSR_CUDA(launch_ca_scale_add(res, x, pooled_scratch, w1, b1, w2, b2, out, n, (long)h * w, c, c_reduced, s));
+  g_launches += 2;
+  return CSR_OK;
+}
+int csr_pixel_shuffle2(const void* src, void* dst, int32_t n, int32_t h, int32_t w, int32_t c, void* stream) {
+  if (!src || !dst || n < 1 || h < 1 || w < 1 || c < 8 || c % 8) return fail(CSR_ERR_BAD_ARG, "csr_pixel_shuffle2: bad arguments");
+  CSR_CUDA(launch_pixel_shuffle2(src, dst, n, h, w, c, reinterpret_cast<cudaStream_t>(stream)));
+  ++g_launches;
   return CSR_OK;
 }
 

@@ -256,6 +256,17 @@ int     csr_linear_forward(const float* x, const float* w, const float* b, float
 int     csr_linear_backward(const float* x, const float* w, const float* gy, float* dx, float* dw, float* db, int32_t n,
                             int32_t k, int32_t j, void* stream);
 
+/* ---- RCAN generator (inference) ---------------------------------------------------------------
+ * climsr.models.rcan.RCAN.forward (climsr/models/rcan.py:175-186): every 3x3 conv (+ ReLU, + the ResidualGroup / body skips as
+ * epilogue residuals) runs on csr_conv2d_nhwc; these two entry points are the rest of an RCAB and of the Upsampler.
+ *   csr_channel_attention  out = res * sigmoid(W2 relu(W1 avgpool(res) + b1) + b2) + x        (CALayer + RCAB skip, rcan.py:50-101)
+ *                          res, x, out: bf16 NHWC (n,h,w,c); w1 (c_reduced, c), w2 (c, c_reduced) fp32; pooled_scratch: n*c floats
+ *   csr_pixel_shuffle2     dst (n,2h,2w,c) = nn.PixelShuffle(2)(src (n,h,w,4c))                 (Upsampler, rcan.py:30-36)          */
+int     csr_channel_attention(const void* res, const void* x, const float* w1, const float* b1, const float* w2, const float* b2,
+                              void* out, float* pooled_scratch, int32_t n, int32_t h, int32_t w, int32_t c, int32_t c_reduced,
+                              void* stream);
+int     csr_pixel_shuffle2(const void* src, void* dst, int32_t n, int32_t h, int32_t w, int32_t c, void* stream);
+
 /* ---- gradient exchange of data-parallel training ("bf16 gradients are reduced with NCCL over NVLink,
  * bucketed and overlapped with backward"; replaces the gradient all-reduce of Lightning's DDP plugin, conf/trainer/
  * benchmark.yaml:4).  The collective itself is torch.distributed / NCCL; these are the wire-format kernels around it:

@@ -23,6 +23,7 @@ Fixtures
                           nb=11, gc=16; default and "trained-like" gain), one cfg4 Europe raster (in=3, 113x113 LR) and one
                           class-default (nb=23, gc=32) 64x64 tile.  These exercise multi-window rows, two-tile windows with ragged
                           last rows and all 33 / 69 in-place concat-buffer rotations, which the 16x16 fixtures never do.
+  rcan.npz              - the reference RCAN (default init) at a reduced depth (with its state_dict) and at the Hydra depth.
   discriminator.npz     - the reference Discriminator (default init, seed 0, train mode) + relativistic GAN losses.
 """
 from __future__ import annotations
@@ -187,6 +188,30 @@ def discriminator():
     print("discriminator.npz written")
 
 
+def rcan():
+    """tests/golden/rcan.npz: the reference RCAN (climsr/models/rcan.py, imported unmodified; default init under
+    torch.manual_seed, conv weights of the body scaled so that the output is O(0.3)) on seeded inputs: a reduced depth
+    (2 groups x 3 blocks) with the names and per-tensor checksums of its state_dict, and the Hydra depth (10 x 20, conf/generator/rcan.yaml) whose weights are
+    re-derivable from the seed (only the output is stored)."""
+    from climsr.models.rcan import RCAN
+    blob = {}
+    for tag, (ng, nbk, n, h, w, seed) in {"small": (2, 3, 2, 20, 24, 0), "hydra": (10, 20, 1, 16, 16, 1)}.items():
+        torch.manual_seed(seed)
+        net = RCAN(n_resgroups=ng, n_resblocks=nbk, n_feats=64, reduction=16, scaling_factor=4, in_channels=3, out_channels=1).eval()
+        x, elev, mask = synth.make_inputs(n, 3, h, w, seed=50 + seed)
+        with torch.no_grad():
+            sr = net(x, elev, mask)
+        blob[tag] = sr.numpy()
+        blob[tag + "_meta"] = np.array([ng, nbk, n, h, w, seed], dtype=np.int64)
+        if tag == "small":
+            # the weights are re-derivable (torch.manual_seed + the same parameter creation order): pin names and per-tensor checksums
+            blob["names"] = np.array(list(net.state_dict().keys()))
+            blob["sd_sum"] = np.array([float(v.double().sum()) for v in net.state_dict().values()])
+            blob["sd_abs"] = np.array([float(v.double().abs().sum()) for v in net.state_dict().values()])
+        print("rcan", tag, sr.shape, "std", float(sr.std()), "absmax", float(sr.abs().max()))
+    np.savez_compressed(os.path.join(OUT, "rcan.npz"), **blob)
+
+
 def lr_input():
     """tests/golden/lr_input.npz: numpy flips / rot90 (climate_dataset.py:152-170) and cv2.resize INTER_NEAREST - what
     albumentations' A.Resize calls (climate_dataset.py:84-92,172) - on seeded square tiles, all 16 augmentation codes."""
@@ -232,6 +257,9 @@ if __name__ == "__main__":
     if "--discriminator-only" in sys.argv:
         discriminator()
         sys.exit(0)
+    if "--rcan-only" in sys.argv:
+        rcan()
+        sys.exit(0)
     if "--fulldepth-only" in sys.argv:
         fulldepth()
         sys.exit(0)
@@ -239,6 +267,7 @@ if __name__ == "__main__":
     normalization()
     lr_input()
     discriminator()
+    rcan()
     if "--tiny-only" not in sys.argv:
         seeded("gen_hydra_seeded", 4, 11, 16, 2, 16, 16)
         seeded("gen_default_seeded", 4, 23, 32, 1, 12, 12)

@@ -640,3 +640,31 @@ def test_dense_block_regrouping_matches_plain_forward(golden_dir):
     assert float((outs[0] - want).abs().max()) <= 1e-2 and float((outs[1] - want).abs().max()) <= 1e-2
     assert float((outs[0] - outs[1]).abs().max()) <= 1e-2
     assert not torch.equal(outs[0], outs[1])      # the option really changes the execution (one more bf16 rounding of p_k)
+
+
+@pytest.mark.parametrize("tag", ["small", "hydra"])
+def test_rcan_matches_reference_golden(golden_dir, tag):
+    """climsr_b200.models.rcan.RCAN (conv kernel + channel-attention / PixelShuffle kernels) against the outputs
+    of the UNMODIFIED reference RCAN at a reduced depth and at the Hydra depth (10 groups x 20 blocks, conf/generator/rcan.yaml),
+    default initialisation re-derived from the seed (same parameter creation order, pinned in tests/test_oracle.py)."""
+    from climsr_b200 import CsrError
+    from climsr_b200.models.rcan import RCAN
+    from oracle import synth
+    z = np.load(os.path.join(golden_dir, "rcan.npz"))
+    ng, nbk, n, h, w, seed = (int(v) for v in z[tag + "_meta"])
+    torch.manual_seed(seed)
+    net = RCAN(n_resgroups=ng, n_resblocks=nbk, n_feats=64, reduction=16, scaling_factor=4, in_channels=3, out_channels=1).cuda().eval()
+    x, elev, mask = synth.make_inputs(n, 3, h, w, seed=50 + seed)
+    with torch.no_grad():
+        got = net(x.cuda(), elev.cuda(), mask.cuda())
+        again = net(x.cuda(), elev.cuda(), mask.cuda())           # second call: cached weight packs
+    assert torch.equal(got, again)
+    assert got.shape == z[tag].shape
+    err = float((got.cpu() - torch.from_numpy(z[tag])).abs().max())
+    assert err <= GEN_TOL, (tag, err)
+    with pytest.raises(CsrError):                                 # training is not implemented for this model: loud, not silent
+        net(x.cuda(), elev.cuda(), mask.cuda())
+    with torch.no_grad():
+        net.tail[1].bias.add_(0.25)                               # in-place update -> version bump -> repack
+        moved = net(x.cuda(), elev.cuda(), mask.cuda())
+    assert float((moved - got).abs().max()) > 1e-3

@@ -193,3 +193,31 @@ def test_discriminator_restatement_matches_reference_golden(golden_dir):
     with torch.no_grad():
         s_eval = od.discriminator_forward(sd, hr, training=False)
     assert float((s_eval - torch.from_numpy(g["s_eval"])).abs().max()) <= 1e-5
+
+
+def _rcan_from_seed(cls, ng, nbk, seed):
+    torch.manual_seed(seed)
+    return cls(n_resgroups=ng, n_resblocks=nbk, n_feats=64, reduction=16, scaling_factor=4, in_channels=3, out_channels=1).eval()
+
+
+def test_rcan_restatement_and_state_dict_contract_match_reference_golden(golden_dir):
+    """oracle/rcan.py against the outputs of the UNMODIFIED reference RCAN (tests/golden/rcan.npz), with weights re-derived from
+    the seed through climsr_b200.models.rcan.RCAN - which also pins that class's parameter names and creation order (= the
+    torch.manual_seed initialisation contract) against the reference's state_dict."""
+    from climsr_b200.models.rcan import RCAN
+    from oracle import rcan as orc
+    from oracle import synth
+    z = np.load(os.path.join(golden_dir, "rcan.npz"))
+    for tag in ("small", "hydra"):
+        ng, nbk, n, h, w, seed = (int(v) for v in z[tag + "_meta"])
+        net = _rcan_from_seed(RCAN, ng, nbk, seed)
+        sd = net.state_dict()
+        if tag == "small":
+            assert list(sd.keys()) == [str(k) for k in z["names"]]
+            assert np.allclose([float(v.double().sum()) for v in sd.values()], z["sd_sum"], rtol=0, atol=1e-9)
+            assert np.allclose([float(v.double().abs().sum()) for v in sd.values()], z["sd_abs"], rtol=0, atol=1e-9)
+        x, elev, mask = synth.make_inputs(n, 3, h, w, seed=50 + seed)
+        with torch.no_grad():
+            got = orc.rcan_forward(sd, x, elev, mask, ng, nbk).numpy()
+        assert got.shape == z[tag].shape
+        assert np.abs(got - z[tag]).max() <= 2e-5
