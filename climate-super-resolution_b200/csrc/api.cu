@@ -656,7 +656,8 @@ static int run_wgrad_layer(const WgradLayer& L, int N, int H, int W, const void*
 
 // Backward op list entry (training plans).
 struct BwdOp {
-  enum Kind { kConv, kWgrad, kReduce, kScatter, kBias, kBiasPlanar, kScale, kMemset, kGcol } kind;
+  enum Kind { kConv, kWgrad, kReduce, kScatter, kBias, kBiasPlanar, kScale, kMemset, kGcol, kDense } kind;
+  csr::DenseLaunch dense;        // kDense: the four gated input-gradient convs of a dense block as one dataflow launch (rdb_tc.cu)
   csr::ConvLaunch conv;          // kConv (dgrad); w_off/b_off index the BACKWARD packed blob
   csr::WgradLaunch wg;           // kWgrad
   // kScatter / kBias*: which forward layer's gradient, and how
@@ -776,11 +777,14 @@ static ConvIO io_of(const void* in, int in_C, void* out, int out_C, int out_coff
 // conv1..conv4 of one gc = 16 dense block as one persistent launch (rdb_tc.cu).  `packs` / `li`: pack layout and the index of
 // the block's conv1 in it.  Returns CSR_ERR_UNSUPPORTED when no tile shape fits - the caller then falls back to four launches.
 static int build_dense(const std::vector<PackLayer>& packs, int li, int N, int H, int W, void* buf, int C, int nf, int gc, unsigned int* flags,
-                       DenseLaunch* dl) {
+                       DenseLaunch* dl, const void* gate = nullptr, int gate_C = 0) {
   DenseParams& p = dl->p;
   memset(&p, 0, sizeof(p));
   if (gc != 16 || C % 8) return fail(CSR_ERR_UNSUPPORTED, "dense-block kernel: gc must be 16");
   p.N = N; p.H = H; p.W = W; p.n_layers = 4; p.C = C; p.buf = buf; p.flags = flags; p.use_pdl = g_opt_pdl; p.dbg = g_dbg_dense;
+  // forward: x_{k+1} = lrelu(conv_{k+1}(...)).  backward (gate given): layer k = the gated gradient of x_{4-k}, gate = x_{4-k} of the
+  // forward concat buffer (channels nf + (3-k) gc ...), no activation
+  p.act = gate ? 0 : 1; p.gate = gate; p.gate_C = gate_C; p.gate_neg = 0.2f;
   int wmax = 0;
   for (int k = 0; k < 4; ++k) {
     const PackLayer& pl = packs[li + k];
@@ -790,6 +794,7 @@ static int build_dense(const std::vector<PackLayer>& packs, int li, int N, int H
     p.L[k].n_kblocks = ceil_div(pl.cin_pad, 64);
     p.L[k].w_bytes = pl.parts[0].w_bytes;
     p.L[k].out_coff = nf + k * gc;
+    p.L[k].gate_coff = nf + (3 - k) * gc;
     dl->w_off[k] = pl.parts[0].w_off; dl->b_off[k] = pl.parts[0].b_off;
     wmax = std::max(wmax, pl.parts[0].w_bytes);
   }
@@ -1136,6 +1141,11 @@ static int bwd_build(CsrPlan* P, void* ws) {
   };
 
   int rc;
+  if (g_opt_dense && gc == 16 && !g_opt_force_generic) {
+    // completion counters of the dense-block launches of the backward (the forward zeroed and used the same region)
+    BwdOp ms; ms.kind = BwdOp::kMemset; ms.dst = P->flags; ms.count = (long)P->flags_bytes;
+    ops.push_back(ms);
+  }
   // ---- SRCNN tail (srcnn.py:13-18) -------------------------------------------------------------------------------
   // srcnn.conv3 (32 -> 1, 5x5): im2col of dL/dout (25 taps as channels) makes both of its gradients 1x1 GEMMs
   { BwdOp op; op.kind = BwdOp::kGcol; op.src = nullptr; op.C = 0; op.dst = gO; op.coff = 32; op.kh = 5; op.kw = 5; ops.push_back(op); }
@@ -1194,7 +1204,19 @@ static int bwd_build(CsrPlan* P, void* ws) {
       const int j = 3 * i + r;
       void* Gb = gcat[gbuf[2 - r]];
       void* Xo = gcat[xout[2 - r]];
-      for (int sidx = 4; sidx >= 1; --sidx) {
+      bool dense_done = false;
+      if (g_opt_dense && gc == 16 && !g_opt_force_generic) {
+        // the four gated convs as ONE persistent launch with tile-level dependencies, like the forward's conv1..conv4
+        BwdOp op; op.kind = BwdOp::kDense;
+        const size_t per_block = (size_t)kDenseMaxLayers * N * ceil_div(h, 8) * ceil_div(w, 14);
+        unsigned int* fl = P->flags + (size_t)j * per_block;
+        if (build_dense(packs, bi, N, h, w, Gb, C, nf, gc, fl, &op.dense, cat(j), C) == CSR_OK && (size_t)op.dense.p.num_tiles * kDenseMaxLayers <= per_block) {
+          ops.push_back(op);
+          bi += 4;
+          dense_done = true;
+        }
+      }
+      for (int sidx = 4; sidx >= 1 && !dense_done; --sidx) {
         // g_s = lrelu'(x_s) * conv_T([g_y | g4 .. g_{s+1}])  ->  Gb slice of x_s
         ConvIO io = io_of(Gb, C, Gb, C, nf + (4 - sidx) * gc, CSR_ACT_NONE);
         io = gated(io, cat(j), C, nf + (sidx - 1) * gc, 0, 0.2f);
@@ -1698,6 +1720,15 @@ static int backward_launches(CsrPlan* P, const void* packed_bwd, const float* gr
         op.conv.p.bias = reinterpret_cast<const float*>(pk + op.conv.b_off);
         int e = launch_conv_tc(op.conv.p, op.conv.tmap, P->sms, s);
         if (e) return fail(CSR_ERR_CUDA, "dgrad launch failed: %s", cudaGetErrorString((cudaError_t)e));
+        break;
+      }
+      case BwdOp::kDense: {
+        for (int k = 0; k < op.dense.p.n_layers; ++k) {
+          op.dense.p.L[k].wpk = pk + op.dense.w_off[k];
+          op.dense.p.L[k].bias = reinterpret_cast<const float*>(pk + op.dense.b_off[k]);
+        }
+        int e = launch_dense_block(op.dense.p, op.dense.tmap, P->sms, s);
+        if (e) return fail(CSR_ERR_CUDA, "dense-block dgrad launch failed: %s", cudaGetErrorString((cudaError_t)e));
         break;
       }
       case BwdOp::kWgrad: {

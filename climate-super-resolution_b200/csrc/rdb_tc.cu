@@ -323,6 +323,18 @@ dense_block_kernel(const DenseParams p, const __grid_constant__ CUtensorMap tmap
       const Win w = decode_win(p, t);
       const int y0 = w.y0 + half * p.TH;
       const uint32_t t_addr = t_lane + buf * kNmma;
+      // backward form: the gate operand (saved forward activations, constant during the backward) does not depend on the
+      // accumulator - fetch it before waiting for the MMAs
+      uint4 gq[2] = {make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u), make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u)};
+      if (p.gate) {
+        const int y = y0 + ty, x = w.x0 - 1 + tx;
+        if (col_ok && y < p.H && x < p.W) {
+          const uint4* gsrc = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.gate) +
+                                                             ((static_cast<size_t>(w.n) * p.H + y) * p.W + x) * p.gate_C + p.L[l].gate_coff);
+          gq[0] = __ldg(gsrc);
+          gq[1] = __ldg(gsrc + 1);
+        }
+      }
       mbar_wait(bar_acc_full(buf), acc_par);                // bounded: a protocol bug traps here instead of hanging
       tc_fence_after();
       uint32_t raw[2][3][8];
@@ -345,11 +357,21 @@ dense_block_kernel(const DenseParams p, const __grid_constant__ CUtensorMap tmap
         gather_add8(v, raw[jj][0], -1, lane);
         gather_add8(v, raw[jj][1], 0, lane);
         gather_add8(v, raw[jj][2], 1, lane);
+        if (p.act) {
 #pragma unroll
-        for (int j = 0; j < 8; j += 2) {                    // LeakyReLU(0.2) = max(v, 0.2 v)
-          const float2 s2 = __fmul2_rn(make_float2(v[j], v[j + 1]), make_float2(0.2f, 0.2f));
-          v[j] = fmaxf(v[j], s2.x);
-          v[j + 1] = fmaxf(v[j + 1], s2.y);
+          for (int j = 0; j < 8; j += 2) {                  // LeakyReLU(0.2) = max(v, 0.2 v)
+            const float2 s2 = __fmul2_rn(make_float2(v[j], v[j + 1]), make_float2(0.2f, 0.2f));
+            v[j] = fmaxf(v[j], s2.x);
+            v[j + 1] = fmaxf(v[j + 1], s2.y);
+          }
+        }
+        if (p.gate) {                                       // LeakyReLU derivative of the forward activation (sign-preserving)
+          const uint32_t gw[4] = {gq[jj].x, gq[jj].y, gq[jj].z, gq[jj].w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            v[2 * i] *= (bf16lo(gw[i]) > 0.f) ? 1.f : p.gate_neg;
+            v[2 * i + 1] *= (bf16hi(gw[i]) > 0.f) ? 1.f : p.gate_neg;
+          }
         }
         if (col_ok)
           st_shared_v4(srow_addr + jj * 16, pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));

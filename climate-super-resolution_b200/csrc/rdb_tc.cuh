@@ -16,6 +16,7 @@ struct DenseLayerParams {
   int out_coff;      // first output channel inside the concat buffer (nf + (k-1) * gc)
   const void* wpk;   // packed bf16 weights (global), conv_tc layout [kblock][dy][kstep][3*16 rows x 16 K]
   const float* bias; // [16] fp32
+  int gate_coff;     // backward form: first channel of this layer's gate inside the gate buffer
 };
 
 struct DenseParams {
@@ -33,6 +34,12 @@ struct DenseParams {
   void* buf;         // the concat buffer: read (channels [0, 16*ksteps)) and written (out_coff) by every layer
   unsigned int* flags;   // [n_layers][num_tiles], zero before the launch: M tiles of (layer, window) whose outputs are in memory
   int use_pdl;
+  // forward: act = 1 (LeakyReLU 0.2), gate = nullptr.  Backward (the four gated input-gradient convs of a dense block, bwd_build in
+  // api.cu): act = 0 and v *= (gate > 0 ? 1 : gate_neg) with gate = the saved forward activation of the layer whose gradient this is
+  int act;
+  const void* gate;  // bf16 NHWC, pitch gate_C
+  int gate_C;
+  float gate_neg;
   unsigned long long* timeline;   // debug: see ConvParams::timeline
   int launch_id;
   int dbg;                        // timing experiments only (wrong results): bit 0 = no fence before the counter update, bit 1 = no dependency waits, bit 2 = no proxy fence
