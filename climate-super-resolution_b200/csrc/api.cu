@@ -678,6 +678,9 @@ struct CsrPlan {
   int train = 0;
   std::vector<csr::ConvLaunch> convs;   // forward, in execution order
   std::vector<csr::DenseLaunch> dense;  // dense-block launches referenced by convs[i].dense
+  std::vector<size_t> dbg_cat;          // csr_plan_buffer: byte offsets of the concat buffers / HR-tail activations inside the workspace
+  size_t dbg_tail[5] = {0, 0, 0, 0, 0};  // m1, hrA, hrB, hrD, hrE
+  int ccat = 0;
   unsigned int* flags = nullptr;        // completion counters of the dense-block launches (zeroed at the start of every forward)
   size_t flags_bytes = 0;
   int idx_srcnn1;                       // the SRCNN x-im2col pack kernel runs right before this conv
@@ -830,6 +833,8 @@ static int plan_build(CsrPlan* P, void* ws) {
   P->sx = reinterpret_cast<float*>(base + L.sx); P->selev = reinterpret_cast<float*>(base + L.selev);
   P->smask = reinterpret_cast<float*>(base + L.smask); P->sout = reinterpret_cast<float*>(base + L.sout);
   P->flags = reinterpret_cast<unsigned int*>(base + L.flags); P->flags_bytes = L.flags_bytes;
+  P->dbg_cat = L.cat; P->ccat = L.ccat;
+  P->dbg_tail[0] = L.m1; P->dbg_tail[1] = L.hrA; P->dbg_tail[2] = L.hrB; P->dbg_tail[3] = L.hrD; P->dbg_tail[4] = L.hrE;
   const std::vector<LayerSpec> layers = layer_table(d);
   P->fwd_layers = layers;
   {
@@ -1767,6 +1772,25 @@ static int backward_launches(CsrPlan* P, const void* packed_bwd, const float* gr
     }
     ++g_launches;
   }
+  return CSR_OK;
+}
+
+int csr_plan_buffer(const CsrPlan* P, int32_t kind, int32_t index, size_t* offset_bytes, int32_t* dims4) {
+  // test hook: where an activation buffer of the plan lives inside the caller's workspace (bf16 NHWC; dims4 = n, h, w, channel pitch).
+  // kind 0: concat buffer `index` (training plans keep one per dense block: [x | x1 | x2 | x3 | x4]), 1: upconv1 output, 2: upconv2 output,
+  // 3: HRconv output, 4: srcnn.conv1 output, 5: srcnn.conv2 output
+  if (!P || !offset_bytes || !dims4) return fail(CSR_ERR_BAD_ARG, "null pointer");
+  const int h = P->h, w = P->w;
+  if (kind == 0) {
+    if (index < 0 || (size_t)index >= P->dbg_cat.size()) return fail(CSR_ERR_BAD_ARG, "concat buffer index %d out of range", index);
+    *offset_bytes = P->dbg_cat[index];
+    dims4[0] = P->N; dims4[1] = h; dims4[2] = w; dims4[3] = P->ccat;
+    return CSR_OK;
+  }
+  if (kind < 1 || kind > 5) return fail(CSR_ERR_BAD_ARG, "unknown buffer kind %d", kind);
+  *offset_bytes = P->dbg_tail[kind - 1];
+  const int s = kind == 1 ? 2 : 4;
+  dims4[0] = P->N; dims4[1] = s * h; dims4[2] = s * w; dims4[3] = (kind == 5) ? P->srcnn_pitch : 64;
   return CSR_OK;
 }
 

@@ -146,6 +146,11 @@ size_t  csr_packed_weight_bytes_bwd(const CsrNetDesc* net);
 int     csr_pack_weights_bwd(const CsrNetDesc* net, const float* const* w, void* packed, size_t packed_bytes, void* stream);
 int     csr_plan_backward(CsrPlan* plan, const void* packed_bwd, const float* grad_out,
                           float* const* dw, float* const* db, void* stream);
+/* test hook: byte offset (inside the workspace given to csr_*plan_create) and dims {n, h, w, channel pitch} of a bf16 NHWC activation
+ * buffer of the plan.  kind 0: concat buffer `index` ([x | x1..x4]; one per dense block in training plans), 1: upconv1 output,
+ * 2: upconv2 output, 3: HRconv output, 4: srcnn.conv1 output, 5: srcnn.conv2 output.  The parity tests read the activation SIGNS of a
+ * training forward from these to run the fp32 oracle with the same LeakyReLU / ReLU masks. */
+int     csr_plan_buffer(const CsrPlan* plan, int32_t kind, int32_t index, size_t* offset_bytes, int32_t dims4[4]);
 int     csr_plan_num_backward_ops(const CsrPlan* plan);
 /* Same backward, all gradients in ONE flat fp32 buffer (OVERWRITTEN, not accumulated): layer i's dW at float offset
  * csr_plan_grad_offset(plan, i, 0), its db at csr_plan_grad_offset(plan, i, 1) (every tensor starts 16-byte aligned),

@@ -24,28 +24,39 @@ def _conv(sd: Dict[str, Tensor], name: str, x: Tensor, pad: int) -> Tensor:
     return F.conv2d(x, sd[name + ".weight"], sd[name + ".bias"], stride=1, padding=pad)
 
 
-def rdb_forward(sd: Dict[str, Tensor], prefix: str, x: Tensor) -> Tensor:
+def _act(x: Tensor, slope: float, masks: Optional[Dict[str, Tensor]], name: str) -> Tensor:
+    """LeakyReLU(slope) / ReLU (slope 0).  With ``masks`` the activation pattern is GIVEN (True = pass, False = * slope) instead of
+    taken from the sign of x: the bf16-emulating form the backward parity tests use - the sm_100a path's forward runs with bf16
+    activations, and the ~1 % of pre-activations whose sign that flips would otherwise dominate a gradient comparison."""
+    if masks is None:
+        return F.leaky_relu(x, slope) if slope else F.relu(x)
+    m = masks[name]
+    assert m.shape == x.shape, (name, tuple(m.shape), tuple(x.shape))
+    return x * torch.where(m, torch.ones((), dtype=x.dtype), torch.full((), slope, dtype=x.dtype))
+
+
+def rdb_forward(sd: Dict[str, Tensor], prefix: str, x: Tensor, masks: Optional[Dict[str, Tensor]] = None) -> Tensor:
     """ResidualDenseBlock.forward, climsr/models/esrgan.py:32-38."""
-    x1 = F.leaky_relu(_conv(sd, prefix + ".conv1", x, 1), 0.2)
-    x2 = F.leaky_relu(_conv(sd, prefix + ".conv2", torch.cat((x, x1), 1), 1), 0.2)
-    x3 = F.leaky_relu(_conv(sd, prefix + ".conv3", torch.cat((x, x1, x2), 1), 1), 0.2)
-    x4 = F.leaky_relu(_conv(sd, prefix + ".conv4", torch.cat((x, x1, x2, x3), 1), 1), 0.2)
+    x1 = _act(_conv(sd, prefix + ".conv1", x, 1), 0.2, masks, prefix + ".conv1")
+    x2 = _act(_conv(sd, prefix + ".conv2", torch.cat((x, x1), 1), 1), 0.2, masks, prefix + ".conv2")
+    x3 = _act(_conv(sd, prefix + ".conv3", torch.cat((x, x1, x2), 1), 1), 0.2, masks, prefix + ".conv3")
+    x4 = _act(_conv(sd, prefix + ".conv4", torch.cat((x, x1, x2, x3), 1), 1), 0.2, masks, prefix + ".conv4")
     x5 = _conv(sd, prefix + ".conv5", torch.cat((x, x1, x2, x3, x4), 1), 1)
     return x5 * 0.2 + x
 
 
-def rrdb_forward(sd: Dict[str, Tensor], prefix: str, x: Tensor) -> Tensor:
+def rrdb_forward(sd: Dict[str, Tensor], prefix: str, x: Tensor, masks: Optional[Dict[str, Tensor]] = None) -> Tensor:
     """ResidualInResidualDenseBlock.forward, esrgan.py:50-54."""
-    out = rdb_forward(sd, prefix + ".RDB1", x)
-    out = rdb_forward(sd, prefix + ".RDB2", out)
-    out = rdb_forward(sd, prefix + ".RDB3", out)
+    out = rdb_forward(sd, prefix + ".RDB1", x, masks)
+    out = rdb_forward(sd, prefix + ".RDB2", out, masks)
+    out = rdb_forward(sd, prefix + ".RDB3", out, masks)
     return out * 0.2 + x
 
 
-def srcnn_forward(sd: Dict[str, Tensor], prefix: str, x: Tensor) -> Tensor:
+def srcnn_forward(sd: Dict[str, Tensor], prefix: str, x: Tensor, masks: Optional[Dict[str, Tensor]] = None) -> Tensor:
     """SRCNN.forward, climsr/models/srcnn.py:13-18 (9x9 p4, 1x1, 5x5 p2)."""
-    out = F.relu(_conv(sd, prefix + ".conv1", x, 4))
-    out = F.relu(_conv(sd, prefix + ".conv2", out, 0))
+    out = _act(_conv(sd, prefix + ".conv1", x, 4), 0.0, masks, prefix + ".conv1")
+    out = _act(_conv(sd, prefix + ".conv2", out, 0), 0.0, masks, prefix + ".conv2")
     return _conv(sd, prefix + ".conv3", out, 2)
 
 
@@ -57,41 +68,42 @@ def count_rrdb(sd: Dict[str, Tensor]) -> int:
 
 
 def generator_forward(sd: Dict[str, Tensor], x: Tensor, elev: Tensor, mask: Tensor,
-                      taps: Optional[Dict[str, Tensor]] = None) -> Tensor:
+                      taps: Optional[Dict[str, Tensor]] = None, masks: Optional[Dict[str, Tensor]] = None) -> Tensor:
     """ESRGANGenerator.forward, esrgan.py:89-102.
 
-    ``taps`` (optional dict) receives named intermediates for layer-level parity.
+    ``taps`` (optional dict) receives named intermediates for layer-level parity; ``masks`` (optional dict: layer name ->
+    bool tensor) fixes the activation patterns (see ``_act``).
     """
     nb = count_rrdb(sd)
     fea = _conv(sd, "conv_first", x, 1)                                     # esrgan.py:90
     t = fea
     for i in range(nb):                                                     # esrgan.py:91
-        t = rrdb_forward(sd, f"RRDB_trunk.{i}", t)
+        t = rrdb_forward(sd, f"RRDB_trunk.{i}", t, masks)
         if taps is not None and i == 0:
             taps["rrdb0"] = t
     trunk = _conv(sd, "trunk_conv", t, 1)
     fea = fea + trunk                                                       # esrgan.py:92
     if taps is not None:
         taps["fea"] = fea
-    fea = F.leaky_relu(_conv(sd, "upconv1", F.interpolate(fea, scale_factor=2, mode="nearest"), 1), 0.2)  # :94
+    fea = _act(_conv(sd, "upconv1", F.interpolate(fea, scale_factor=2, mode="nearest"), 1), 0.2, masks, "upconv1")  # :94
     if "upconv2.weight" in sd:                                              # esrgan.py:96-97
-        fea = F.leaky_relu(_conv(sd, "upconv2", F.interpolate(fea, scale_factor=2, mode="nearest"), 1), 0.2)
-    out = _conv(sd, "conv_last", F.leaky_relu(_conv(sd, "HRconv", fea, 1), 0.2), 1)  # esrgan.py:99
+        fea = _act(_conv(sd, "upconv2", F.interpolate(fea, scale_factor=2, mode="nearest"), 1), 0.2, masks, "upconv2")
+    out = _conv(sd, "conv_last", _act(_conv(sd, "HRconv", fea, 1), 0.2, masks, "HRconv"), 1)  # esrgan.py:99
     if taps is not None:
         taps["conv_last"] = out
-    out = srcnn_forward(sd, "srcnn", torch.cat([out, elev, mask], 1))       # esrgan.py:100
+    out = srcnn_forward(sd, "srcnn", torch.cat([out, elev, mask], 1), masks)       # esrgan.py:100
     return out
 
 
 def generator_forward_backward(sd: Dict[str, Tensor], x: Tensor, elev: Tensor, mask: Tensor, hr: Tensor,
-                               loss: str = "l1") -> Tuple[Tensor, Tensor, Dict[str, Tensor]]:
+                               loss: str = "l1", masks: Optional[Dict[str, Tensor]] = None) -> Tuple[Tensor, Tensor, Dict[str, Tensor]]:
     """Training-step arithmetic: L1 (esrgan) / MSE (srcnn) pixel loss, core/task.py:141 and
     task/pl_generator_pre_training.py:29-30, then autograd backward (a6 in SURVEY.md section 8a).
 
     Returns (sr, loss, grads-by-name).
     """
     params = {k: v.detach().clone().requires_grad_(True) for k, v in sd.items()}
-    sr = generator_forward(params, x, elev, mask)
+    sr = generator_forward(params, x, elev, mask, masks=masks)
     lv = F.l1_loss(sr, hr) if loss == "l1" else F.mse_loss(sr, hr)
     grads = torch.autograd.grad(lv, list(params.values()))
     return sr.detach(), lv.detach(), {k: g for k, g in zip(params.keys(), grads)}

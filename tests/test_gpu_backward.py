@@ -95,6 +95,66 @@ def test_generator_backward_matches_oracle(in_ch, nb, gc, n, h, w):
     _check_grads(grads, grads_ref)
 
 
+def _plan_masks(net, n, h, w, nb, gc):
+    """Activation patterns of the latest TRAINING forward of `net`, read from its plan's saved activations (csr_plan_buffer):
+    layer name -> bool NCHW tensor (True where the stored bf16 activation is positive; LeakyReLU / ReLU preserve the sign)."""
+    import ctypes as C
+    from climsr_b200._lib import check, lib
+    plan, ws = net._plans[(n, h, w, next(net.parameters()).device, True)]
+    base = (ws.data_ptr() + 1023) // 1024 * 1024 - ws.data_ptr()
+    off, dims = C.c_size_t(), (C.c_int32 * 4)()
+
+    def view(kind, index):
+        check(lib.csr_plan_buffer(plan, kind, index, C.byref(off), C.byref(dims)), "csr_plan_buffer")
+        nn_, hh, ww, cc = (int(v) for v in dims)
+        nbytes = nn_ * hh * ww * cc * 2
+        return ws[base + off.value: base + off.value + nbytes].view(torch.bfloat16).view(nn_, hh, ww, cc)
+
+    masks = {}
+    for i in range(nb):
+        for r in range(3):
+            cat = view(0, 3 * i + r)
+            for k in range(1, 5):
+                sl = cat[..., 64 + (k - 1) * gc: 64 + k * gc]
+                masks[f"RRDB_trunk.{i}.RDB{r + 1}.conv{k}"] = (sl.float() > 0).permute(0, 3, 1, 2).cpu()
+    for name, kind, c in (("upconv1", 1, 64), ("upconv2", 2, 64), ("HRconv", 3, 64), ("srcnn.conv1", 4, 64), ("srcnn.conv2", 5, 32)):
+        masks[name] = (view(kind, 0)[..., :c].float() > 0).permute(0, 3, 1, 2).cpu()
+    return masks
+
+
+@pytest.mark.parametrize("in_ch,nb,gc,n,h,w", [(4, 2, 16, 2, 24, 20), (3, 1, 32, 1, 12, 12), (4, 3, 16, 1, 32, 32)])
+def test_generator_backward_matches_mask_matched_oracle(in_ch, nb, gc, n, h, w):
+    """the backward GRAPH held to a tight tolerance.  The fp32 oracle is run with (a) the bf16-rounded
+    weights the kernels multiply with and (b) the LeakyReLU / ReLU activation patterns of OUR forward (read from the training
+    plan's saved activations) - a bf16-emulating reference: what remains is rounding of the stored activations / gradient maps
+    (bf16) and summation order.  Every weight gradient must then agree to a relative L2 error of 2e-2 with cosine >= 0.9995
+    (the free-running comparison above needs 0.15 / 0.99 only because ~1 % of near-zero pre-activations flip their sign in bf16
+    and LeakyReLU's derivative jumps there; a missing or mis-scaled term in the backward would show up here at >= 0.2)."""
+    from oracle import generator as og
+    from oracle import synth
+    sd = synth.make_state_dict(in_ch, 1, 64, nb, gc, seed=5, gain=1.3)
+    x, elev, mask = synth.make_inputs(n, in_ch, h, w, seed=6)
+    hr = torch.rand((n, 1, 4 * h, 4 * w), generator=torch.Generator().manual_seed(7)) * 2 - 1
+    sr, lv, grads, net = _train_step(sd, x, elev, mask, hr, in_ch, nb, gc)
+    masks = _plan_masks(net, n, h, w, nb, gc)
+    sd_q = {k: (v.to(torch.bfloat16).float() if k.endswith(".weight") else v) for k, v in sd.items()}
+    x_q = x.to(torch.bfloat16).float()
+    sr_ref, loss_ref, grads_ref = og.generator_forward_backward(sd_q, x_q, elev, mask, hr, loss="mse", masks=masks)
+    assert float((sr - sr_ref).abs().max()) <= 1e-2
+    worst = ("", 0.0)
+    for k, ref in grads_ref.items():
+        g = grads[k]
+        rel = float((g - ref).norm() / (ref.norm() + 1e-30))
+        cos = float(F.cosine_similarity(g.flatten().double(), ref.flatten().double(), dim=0))
+        if rel > worst[1]:
+            worst = (k, rel)
+        if k.endswith(".weight"):
+            assert rel <= 2e-2 and cos >= 0.9995, (k, rel, cos)   # measured worst: 0.8 %
+        else:                                   # biases: short vectors of heavily cancelling sums (conv_last.bias is one scalar)
+            assert rel <= 4e-2 and cos >= 0.999, (k, rel, cos)    # measured worst: 1.1 %
+    print("worst gradient tensor", worst)
+
+
 def test_generator_backward_matches_reference_golden(golden_dir):
     """Weights, inputs, targets and gradients all produced by the UNMODIFIED reference module (oracle/make_golden.py)."""
     z = np.load(os.path.join(golden_dir, "gen_tiny_refinit.npz"))
