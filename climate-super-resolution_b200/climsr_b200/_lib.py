@@ -57,6 +57,7 @@ def _load():
         "csr_device_check": (C.c_int, []),
         "csr_set_option": (C.c_int, [i32, i32]),
         "csr_kernel_launch_count": (C.c_int64, []),
+        "csr_has_experiments": (C.c_int, []),
         "csr_debug_set_trace": (C.c_int, [vp]),
         "csr_debug_set_timeline": (C.c_int, [vp, i32]),
         "csr_num_layers": (C.c_int, [nd]),
@@ -118,7 +119,7 @@ def _load():
 
 
 lib = _load()
-EXPORTS = ("csr_abi_version", "csr_last_error", "csr_device_check", "csr_set_option", "csr_kernel_launch_count", "csr_debug_set_trace", "csr_debug_set_timeline", "csr_num_layers",
+EXPORTS = ("csr_abi_version", "csr_last_error", "csr_device_check", "csr_set_option", "csr_kernel_launch_count", "csr_has_experiments", "csr_debug_set_trace", "csr_debug_set_timeline", "csr_num_layers",
            "csr_layer_shape", "csr_packed_weight_bytes", "csr_pack_weights", "csr_workspace_bytes", "csr_plan_create",
            "csr_plan_forward", "csr_plan_num_launches", "csr_plan_destroy", "csr_train_workspace_bytes", "csr_train_plan_create",
            "csr_packed_weight_bytes_bwd", "csr_pack_weights_bwd", "csr_plan_backward", "csr_plan_num_backward_ops", "csr_plan_buffer", "csr_plan_grad_floats", "csr_plan_graph_status", "csr_plan_grad_offset",

@@ -1322,6 +1322,11 @@ int csr_device_check(void) {
 
 int csr_set_option(int32_t key, int32_t value) {
   // the table with defaults and meanings is in INTEGRATION.md section 6
+#ifndef CSR_EXPERIMENTS
+  // measured-and-rejected kernel variants are not part of the default build (conv_tc.cu launch_conv_tc)
+  if ((key == 13 && value != 0) || (key == 16 && value != 0) || (key == 8 && value == 0))
+    return fail(CSR_ERR_UNSUPPORTED, "option %d=%d selects an experimental kernel variant: rebuild with CSR_EXPERIMENTS=1 python build.py --force", key, value);
+#endif
   switch (key) {
     case 1: g_opt_pdl = value ? 1 : 0; return CSR_OK;              // programmatic dependent launch on/off
     case 2: g_opt_force_sw = value; return CSR_OK;                 // debug: force the window pitch
@@ -1353,6 +1358,14 @@ int csr_set_option(int32_t key, int32_t value) {
 }
 
 int64_t csr_kernel_launch_count(void) { return g_launches.load(); }
+
+int csr_has_experiments(void) {
+#ifdef CSR_EXPERIMENTS
+  return 1;
+#else
+  return 0;
+#endif
+}
 
 int csr_debug_set_trace(void* device_buffer) {
 #ifdef CSR_ENABLE_TRACE

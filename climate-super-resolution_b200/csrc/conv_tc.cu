@@ -741,7 +741,11 @@ static int launch_t(const ConvParams& p, const CUtensorMap& tmap, int num_sms, c
 int launch_conv_tc(const ConvParams& p, const CUtensorMap& tmap, int num_sms, cudaStream_t stream) {
   const int res = (p.r1 ? 1 : 0) | (p.r2 ? 2 : 0) | (p.gate ? 4 : 0) | ((p.r1 && p.r1_pre) ? 8 : 0);
   if ((res & 6) == 6) return static_cast<int>(cudaErrorInvalidValue);   // r2 and gate share an operand slot
+  // Measured-and-rejected variants (CTA pairs, unstaged 32-byte stores, dense blocks regrouped by source as per-layer launches)
+  // are only instantiated in a -DCSR_EXPERIMENTS build (CSR_EXPERIMENTS=1 python build.py): the default library carries the
+  // kernels that run.  DESIGN.md section 3.1 has their numbers.
   if (p.pair) {
+#ifdef CSR_EXPERIMENTS
     // CTA-pair variants: 3x3 layers whose resident weights would otherwise starve the window ring
     if (p.store_mode != kStoreStaged || p.KW != 3 || p.PW != 1 || p.act != 0 || (p.num_tiles & 1) || p.force_generic)
       return static_cast<int>(cudaErrorInvalidValue);
@@ -752,14 +756,19 @@ int launch_conv_tc(const ConvParams& p, const CUtensorMap& tmap, int num_sms, cu
       case 5: return launch_t<3, 1, 0, 5, 1, 1>(p, tmap, num_sms, stream);
       default: return static_cast<int>(cudaErrorInvalidValue);
     }
+#else
+    return static_cast<int>(cudaErrorNotSupported);
+#endif
   }
   if (p.tall_shift) {
     // two-M-tile windows: the thin layers only (four accumulator buffers)
     if ((p.n_acc != 4 && p.n_acc != 8) || p.n_groups != 4) return static_cast<int>(cudaErrorInvalidValue);
     if (p.store_mode == kStoreStaged && !p.force_generic && p.KW == 3 && p.PW == 1 && p.act == 1 && res == 0)
       return launch_t<3, 1, 1, 0, 1, 0, 1>(p, tmap, num_sms, stream);      // RDB conv1-4 (not regrouped)
+#ifdef CSR_EXPERIMENTS
     if (p.store_mode == kStoreStaged && !p.force_generic && p.KW == 3 && p.PW == 1 && p.act == 1 && res == 9)
       return launch_t<3, 1, 1, 9, 1, 0, 1>(p, tmap, num_sms, stream);      // RDB conv2-4 over x1..x_{k-1}
+#endif
     if (p.store_mode == kStoreStaged && !p.force_generic && p.KW == 1 && p.PW == 0 && p.act == 2 && res == 0)
       return launch_t<1, 0, 2, 0, 1, 0, 1>(p, tmap, num_sms, stream);      // srcnn.conv2
     if (p.store_mode == kStoreStaged && !p.force_generic && p.KW == 3 && p.PW == 1 && p.act == 0 && res == 4)
@@ -786,7 +795,9 @@ int launch_conv_tc(const ConvParams& p, const CUtensorMap& tmap, int num_sms, cu
     if (p.KW == KW_ && p.PW == PW_ && p.act == ACT_ && res == RES_) return launch_t<KW_, PW_, ACT_, RES_, 1, 0, 0, 1>(p, tmap, num_sms, stream);
     CSR_EARLY(3, 1, 1, 0)   // HRconv
     CSR_EARLY(3, 1, 0, 0)   // conv_first
+#ifdef CSR_EXPERIMENTS
     CSR_EARLY(3, 1, 3, 0)   // dense block regrouped by source: conv1 + the x-parts of conv2-4
+#endif
     CSR_EARLY(2, 0, 1, 0)   // upconv sub-pixel phases
     CSR_EARLY(2, 1, 1, 0)
     CSR_EARLY(1, 0, 2, 0)   // srcnn.conv1 (x-im2col folded)
@@ -804,10 +815,12 @@ int launch_conv_tc(const ConvParams& p, const CUtensorMap& tmap, int num_sms, cu
   CSR_CASE(3, 1, 0, 0, 1)   // conv_first
   CSR_CASE(3, 1, 0, 1, 1)   // RDB conv5 (*0.2 + x), trunk_conv (+ fea)
   CSR_CASE(3, 1, 0, 3, 1)   // RDB3 conv5 (*0.2 + x, *0.2 + x_rrdb)
+#ifdef CSR_EXPERIMENTS
   CSR_CASE(3, 1, 0, 1, 2)   // ... the same with unstaged stores (weights leave no room for staging + a deep window ring)
   CSR_CASE(3, 1, 0, 3, 2)
   CSR_CASE(3, 1, 3, 0, 1)   // dense block regrouped by source: conv1 and the x-parts of conv2-4 in one launch (lrelu on conv1's channels)
   CSR_CASE(3, 1, 1, 9, 1)   // ... conv2-4 over x1..x_{k-1} only, the x-part added before the lrelu
+#endif
   CSR_CASE(2, 0, 1, 0, 1)   // upconv sub-pixel phases
   CSR_CASE(2, 1, 1, 0, 1)
   CSR_CASE(1, 0, 2, 0, 1)   // srcnn.conv1 (x-im2col folded), srcnn.conv2: relu

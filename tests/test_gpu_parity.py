@@ -123,12 +123,19 @@ def test_conv_epilogue_variants():
     assert torch.equal(a, c)
 
 
+def _need_experiments():
+    from climsr_b200._lib import lib
+    if not lib.csr_has_experiments():
+        pytest.skip("measured-and-rejected kernel variant: only in a CSR_EXPERIMENTS=1 build")
+
+
 def test_conv_cta_pair_matches_single_cta():
     """CTA-pair launches (tcgen05 cta_group::2, option 13; off by default) of the RDB conv5 shape - 128 -> 64 channels with
     the x5*0.2 + x residuals of esrgan.py:38,54 - must reproduce the single-CTA kernel bit for bit: same MMAs, same
     accumulation order, only the operand halves come from two CTAs."""
     from climsr_b200 import ops
     from climsr_b200._lib import lib
+    _need_experiments()
     g = torch.Generator().manual_seed(21)
     n, h, w = 4, 16, 60                          # 4 x 4 x 2 = 32 tiles: an even count, which pair mode needs
     x = torch.rand((n, 128, h, w), generator=g) * 2 - 1
@@ -625,6 +632,7 @@ def test_dense_block_regrouping_matches_plain_forward(golden_dir):
     bf16 concat slots) against the plain layer-by-layer forward and the reference golden output."""
     from climsr_b200._lib import lib
     from oracle import synth
+    _need_experiments()
     z = np.load(os.path.join(golden_dir, "gen_hydra_seeded.npz"))
     in_ch, nb, gc, n, h, w = (int(v) for v in z["meta"])
     sd = synth.make_state_dict(in_ch, 1, 64, nb, gc, seed=0, gain=float(z["gains"][1]))     # the "trained-like" weight scale
