@@ -64,14 +64,8 @@ def _conv_t(g: Tensor, w: Tensor, cache=None) -> Tensor:
 
 
 def _wgrad(p: Tensor, g: Tensor, w: Tensor):
-    """Weight / bias gradient of a conv layer; the GEMM takes <= 128 output channels per call."""
-    cout = w.shape[0]
-    dw = torch.zeros_like(w, dtype=torch.float32)
-    db = torch.zeros((cout,), dtype=torch.float32, device=w.device)
-    for co in range(0, cout, 128):
-        k = min(128, cout - co)
-        ops.conv2d_wgrad(p, g, (k,) + tuple(w.shape[1:]), g_coff=co, dw=dw[co:co + k], db=db[co:co + k])
-    return dw, db
+    """Weight / bias gradient of a conv layer: one GEMM launch per layer (job mode of the weight-gradient kernel)."""
+    return ops.conv2d_wgrad(p, g, tuple(w.shape))
 
 
 class _DiscriminatorFunction(torch.autograd.Function):

@@ -651,6 +651,53 @@ static int run_wgrad_layer(const WgradLayer& L, int N, int H, int W, const void*
   return CSR_OK;
 }
 
+// Job mode (wgrad_tc.cuh): layers with many channels and few pixels (the discriminator: 64..512 channels on 130^2..6^2 grids).
+// ONE GEMM launch per layer - CTAs own (128-input-channel chunk, output-channel chunk, vertical-tap group) blocks of the weight
+// gradient and loop over pixel tiles - instead of one launch (whose 128-pixel K slices each end in ~200 KB of atomics) per block.
+static bool wgrad_jobs_applicable(const WgradLayer& L, int N, int H, int W, int sms) {
+  if (L.up2 || L.fold || L.kh != L.kw || L.kw > 3) return false;
+  const long tiles = (long)N * ceil_div(H, 4) * ceil_div(W, 30);
+  return L.cout > 128 || (L.cin > 128 && tiles < 4L * sms);
+}
+static size_t wgrad_jobs_scratch_floats(const WgradLayer& L) {
+  const int n_cols = L.cout >= 128 ? 128 : (L.cout + 15) / 16 * 16;
+  const int per = wgrad_taps_per_launch(L.kw, n_cols);
+  const long jobs = (long)ceil_div(L.cin, 128) * ceil_div(L.cout, n_cols) * ceil_div(L.kh, per);
+  return (size_t)jobs * per * L.kw * 128 * n_cols;
+}
+static int run_wgrad_layer_jobs(const WgradLayer& L, int N, int H, int W, const void* x, int x_C, int x_coff, const void* g, int g_C, int g_coff,
+                                float scale, float* dw, float* db, float* scratch, int sms, cudaStream_t s, long long* launches) {
+  const int n_cols = L.cout >= 128 ? 128 : (L.cout + 15) / 16 * 16;
+  if (L.cout > 128 && L.cout % 128) return fail(CSR_ERR_UNSUPPORTED, "wgrad: cout %d > 128 must be a multiple of 128", L.cout);
+  const int per = wgrad_taps_per_launch(L.kw, n_cols);
+  WgradLaunch wl;
+  int rc = build_wgrad(sms, N, H, W, L.kw, L.kw / 2, -(L.kh / 2), std::min(per, L.kh), x, x_C, x_coff, g, g_C, g_coff, n_cols > 64 ? g : nullptr,
+                       n_cols > 64 ? g_C : 0, n_cols > 64 ? g_coff + 64 : 0, n_cols, scratch, 0, n_cols, &wl);
+  if (rc) return rc;
+  WgradParams& p = wl.p;
+  p.jobs_ci = ceil_div(L.cin, 128); p.jobs_co = ceil_div(L.cout, n_cols); p.jobs_dy = ceil_div(L.kh, per);
+  p.KH = L.kh; p.PH = L.kh / 2; p.per_dy = per; p.x_coff = x_coff; p.g_coff = g_coff;
+  p.job_stride = (long)per * L.kw * 128 * n_cols;
+  p.ld_n = n_cols;
+  p.atomic = 1;
+  const int jobs = p.jobs_ci * p.jobs_co * p.jobs_dy;
+  p.splits = std::max(1, std::min(p.num_tiles, sms / jobs));
+  CSR_CUDA(cudaMemsetAsync(scratch, 0, (size_t)jobs * p.job_stride * sizeof(float), s));
+  int e = launch_wgrad_tc(p, wl.tx0, wl.tx1, wl.tg0, wl.tg1, sms, s);
+  if (e) return fail(CSR_ERR_CUDA, "wgrad (job mode) launch failed: %s", cudaGetErrorString((cudaError_t)e));
+  CSR_CUDA(launch_wgrad_scatter_jobs(scratch, dw, L.cout, L.cin, L.kh, L.kw, n_cols, p.jobs_co, p.jobs_dy, per, p.job_stride, scale, s));
+  *launches += 3;
+  if (db) {
+    const long npix = (long)N * H * W;
+    for (int co = 0; co < L.cout; co += 128) {
+      float* dbs[1] = {db + co};
+      CSR_CUDA(launch_bias_grad(g, npix, g_C, g_coff + co, std::min(128, L.cout - co), scale, dbs, 1, s));
+      ++*launches;
+    }
+  }
+  return CSR_OK;
+}
+
 // ------------------------------------------------------------------------------------------- plan
 }  // namespace csr
 
@@ -1952,23 +1999,32 @@ int csr_conv2d_nhwc(const CsrConvDesc* d, const void* in, const float* weight, c
 
 // ---- single-layer weight gradient (building block; used by the parity tests) ---------------------------
 size_t csr_conv2d_wgrad_scratch_bytes(const CsrWgradDesc* d) {
-  if (!d || d->cout < 1 || d->cout > 128) return 0;
+  if (!d || d->cout < 1 || d->cin < 1) return 0;
   WgradLayer L = {d->cout, d->cin, d->kh, d->kw, 0, d->in_up2 ? 1 : 0};
-  return wgrad_scratch_floats(L) * sizeof(float);
+  const size_t jobs = (!L.up2 && L.kh == L.kw && L.kw <= 3) ? wgrad_jobs_scratch_floats(L) : 0;
+  if (d->cout > 128) return jobs * sizeof(float);
+  return std::max(jobs, wgrad_scratch_floats(L)) * sizeof(float);
 }
 
 int csr_conv2d_wgrad(const CsrWgradDesc* d, const void* x, const void* g, float* dw, float* db, void* scratch, size_t scratch_bytes,
                      void* stream) {
   if (!d || !x || !g || !dw || !scratch) return fail(CSR_ERR_BAD_ARG, "null pointer");
-  if (d->n < 1 || d->h < 1 || d->w < 1 || d->cin < 1 || d->cout < 1 || d->cout > 128) return fail(CSR_ERR_BAD_ARG, "bad wgrad shape");
+  if (d->n < 1 || d->h < 1 || d->w < 1 || d->cin < 1 || d->cout < 1 || d->cout > 1024) return fail(CSR_ERR_BAD_ARG, "bad wgrad shape");
   if (!(d->kh & 1) || !(d->kw & 1) || d->kh > 9 || d->kw > 9) return fail(CSR_ERR_UNSUPPORTED, "kernel %dx%d", d->kh, d->kw);
   if (d->in_up2 && (d->kh != 3 || d->kw != 3)) return fail(CSR_ERR_UNSUPPORTED, "nearest-x2 input needs a 3x3 kernel");
   WgradLayer L = {d->cout, d->cin, d->kh, d->kw, 0, d->in_up2 ? 1 : 0};
-  if (scratch_bytes < wgrad_scratch_floats(L) * sizeof(float)) return fail(CSR_ERR_WORKSPACE, "wgrad scratch too small");
+  if (scratch_bytes < csr_conv2d_wgrad_scratch_bytes(d)) return fail(CSR_ERR_WORKSPACE, "wgrad scratch too small");
   DeviceInfo di;
   int rc = device_info(&di);
   if (rc) return rc;
   long long launches = 0;
+  if (wgrad_jobs_applicable(L, d->n, d->h, d->w, di.sms)) {
+    rc = run_wgrad_layer_jobs(L, d->n, d->h, d->w, x, d->x_c, d->x_coff, g, d->g_c, d->g_coff, d->scale, dw, db, reinterpret_cast<float*>(scratch),
+                              di.sms, reinterpret_cast<cudaStream_t>(stream), &launches);
+    g_launches += launches;
+    return rc;
+  }
+  if (d->cout > 128) return fail(CSR_ERR_UNSUPPORTED, "wgrad: cout %d > 128 needs a 3x3 (or 1x1) stride-1 layer", d->cout);
   rc = run_wgrad_layer(L, d->n, d->h, d->w, x, d->x_c, d->x_coff, g, d->g_c, d->g_coff, d->scale, dw, db, reinterpret_cast<float*>(scratch),
                        di.sms, reinterpret_cast<cudaStream_t>(stream), &launches);
   g_launches += launches;

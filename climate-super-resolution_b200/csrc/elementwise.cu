@@ -241,6 +241,21 @@ __global__ void wgrad_scatter_kernel(const float* __restrict__ dacc, int ld_n, f
   }
 }
 
+// Job-mode scatter (wgrad_tc job mode): dw[co][ci][dy][dx] += scale * dacc[job(ci/128, co/n_cols, dy/per_dy)][(dy%per_dy)*kw + dx][ci%128][co%n_cols]
+__global__ void wgrad_scatter_jobs_kernel(const float* __restrict__ dacc, float* __restrict__ dw, int cout, int cin, int kh, int kw, int n_cols,
+                                          int jobs_co, int jobs_dy, int per_dy, long job_stride, float scale) {
+  const long total = static_cast<long>(cout) * cin * kh * kw;
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const int dx = static_cast<int>(i % kw);
+    long r = i / kw;
+    const int dy = static_cast<int>(r % kh); r /= kh;
+    const int ci = static_cast<int>(r % cin);
+    const int co = static_cast<int>(r / cin);
+    const long job = (static_cast<long>(ci >> 7) * jobs_co + co / n_cols) * jobs_dy + dy / per_dy;
+    dw[i] += scale * dacc[job * job_stride + (static_cast<long>((dy % per_dy) * kw + dx) * 128 + (ci & 127)) * n_cols + co % n_cols];
+  }
+}
+
 // db[co] += scale * sum over pixels of g[p][coff + co]   (bf16 NHWC, pitch C).  One block per pixel range, fp32 atomics.
 // Channel co goes to segment co / seg_ch (its own bias-gradient vector): one pass serves the four narrow convs of a
 // dense block whose output gradients sit side by side in the gradient concat buffer.
@@ -412,6 +427,12 @@ cudaError_t launch_wgrad_scatter(const float* dacc, int ld_n, float* dw, int cou
   const int ekh = phase >= 0 ? 2 : kh, ekw = phase >= 0 ? 2 : (fold ? 1 : kw);
   const long total = static_cast<long>(ekh) * ekw * ci_n * cout;
   wgrad_scatter_kernel<<<grid_for(total, 256), 256, 0, s>>>(dacc, ld_n, dw, cout, cin, kh, kw, fold, phase, ci0, ci_n, col0, scale, taps_t);
+  return cudaGetLastError();
+}
+cudaError_t launch_wgrad_scatter_jobs(const float* dacc, float* dw, int cout, int cin, int kh, int kw, int n_cols, int jobs_co, int jobs_dy,
+                                      int per_dy, long job_stride, float scale, cudaStream_t s) {
+  const long total = static_cast<long>(cout) * cin * kh * kw;
+  wgrad_scatter_jobs_kernel<<<grid_for(total, 256), 256, 0, s>>>(dacc, dw, cout, cin, kh, kw, n_cols, jobs_co, jobs_dy, per_dy, job_stride, scale);
   return cudaGetLastError();
 }
 cudaError_t launch_bias_grad(const void* g, long npix, int C, int coff, int cout, float scale, float* const* db, int nseg, cudaStream_t s) {

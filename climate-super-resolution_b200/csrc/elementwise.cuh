@@ -23,6 +23,8 @@ cudaError_t launch_nhwc_to_nchw(const void* src, float* dst, int n, int c, int h
 cudaError_t launch_wgrad_reduce(float* dacc, long part_stride, int n_parts, long nfloats, cudaStream_t s);
 cudaError_t launch_wgrad_scatter(const float* dacc, int ld_n, float* dw, int cout, int cin, int kh, int kw, int fold,
                                  int phase, int ci0, int ci_n, int col0, float scale, int taps_t, cudaStream_t s);
+cudaError_t launch_wgrad_scatter_jobs(const float* dacc, float* dw, int cout, int cin, int kh, int kw, int n_cols, int jobs_co, int jobs_dy,
+                                      int per_dy, long job_stride, float scale, cudaStream_t s);
 // db: nseg (1..4) bias-gradient vectors; channel co of the cout channels goes to db[co / (cout/nseg)]
 cudaError_t launch_bias_grad(const void* g, long npix, int C, int coff, int cout, float scale, float* const* db, int nseg, cudaStream_t s);
 cudaError_t launch_bias_grad_planar(const float* g, long n, float scale, float* db, cudaStream_t s);

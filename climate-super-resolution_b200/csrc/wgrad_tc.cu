@@ -51,6 +51,24 @@ wgrad_tc_kernel(const WgradParams p, const __grid_constant__ CUtensorMap tx0, co
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
+  // what this CTA works on: the launch's single job (pixel tiles strided over the grid) or, in job mode, its own job
+  int xc0a = p.xc0[0], xc0b = p.xc0[1], gc0a = p.gc0[0], gc0b = p.gc0[1], dy_off = p.dy_off, n_dy = p.n_dy;
+  int t_first = blockIdx.x, t_step = gridDim.x;
+  float* out_base = p.dacc + (p.atomic ? 0 : static_cast<size_t>(blockIdx.x) * p.part_stride);
+  if (p.jobs_ci > 0) {
+    const int job = blockIdx.x / p.splits;
+    t_first = blockIdx.x - job * p.splits;
+    t_step = p.splits;
+    const int dyj = job % p.jobs_dy;
+    const int oc = (job / p.jobs_dy) % p.jobs_co;
+    const int cc = job / (p.jobs_dy * p.jobs_co);
+    xc0a = p.x_coff + cc * 128; xc0b = xc0a + 64;
+    gc0a = p.g_coff + oc * p.n_cols; gc0b = gc0a + 64;
+    dy_off = dyj * p.per_dy - p.PH;
+    n_dy = min(p.per_dy, p.KH - dyj * p.per_dy);
+    out_base = p.dacc + static_cast<size_t>(job) * p.job_stride;
+  }
+
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tx0);
     tma_prefetch_desc(&tg0);
@@ -83,7 +101,7 @@ wgrad_tc_kernel(const WgradParams p, const __grid_constant__ CUtensorMap tx0, co
     int stage = 0;
     uint32_t phase = 0;
     const uint32_t bytes = static_cast<uint32_t>(p.n_xbox * p.x_box_bytes + p.n_gbox * p.g_box_bytes);
-    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+    for (int t = t_first; t < p.num_tiles; t += t_step) {
       const int n = fast_div_w(t, p.magic_img);
       const int rem = t - n * p.tiles_per_img;
       const int tyi = fast_div_w(rem, p.magic_row);
@@ -92,10 +110,10 @@ wgrad_tc_kernel(const WgradParams p, const __grid_constant__ CUtensorMap tx0, co
       if (elect_one()) {
         const uint32_t sb = smem_base + stage * p.stage_bytes;
         mbar_arrive_expect_tx(bar_full(stage), bytes);
-        tma_load_4d(sb + p.x_slack, &tx0, bar_full(stage), p.xc0[0], x0 - p.PW, y0 + p.dy_off, n);
-        if (p.n_xbox > 1) tma_load_4d(sb + x_pitch + p.x_slack, &tx1, bar_full(stage), p.xc0[1], x0 - p.PW, y0 + p.dy_off, n);
-        tma_load_4d(sb + g_off, &tg0, bar_full(stage), p.gc0[0], x0 - p.PW, y0, n);
-        if (p.n_gbox > 1) tma_load_4d(sb + g_off + p.g_box_bytes, &tg1, bar_full(stage), p.gc0[1], x0 - p.PW, y0, n);
+        tma_load_4d(sb + p.x_slack, &tx0, bar_full(stage), xc0a, x0 - p.PW, y0 + dy_off, n);
+        if (p.n_xbox > 1) tma_load_4d(sb + x_pitch + p.x_slack, &tx1, bar_full(stage), xc0b, x0 - p.PW, y0 + dy_off, n);
+        tma_load_4d(sb + g_off, &tg0, bar_full(stage), gc0a, x0 - p.PW, y0, n);
+        if (p.n_gbox > 1) tma_load_4d(sb + g_off + p.g_box_bytes, &tg1, bar_full(stage), gc0b, x0 - p.PW, y0, n);
       }
       __syncwarp();
       if (++stage == S) { stage = 0; phase ^= 1; }
@@ -115,12 +133,12 @@ wgrad_tc_kernel(const WgradParams p, const __grid_constant__ CUtensorMap tx0, co
     int stage = 0;
     uint32_t phase = 0;
     bool first = true;
-    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+    for (int t = t_first; t < p.num_tiles; t += t_step) {
       mbar_wait(bar_ready(stage), phase);
       tc_fence_after();
       const uint32_t sb = smem_base + stage * p.stage_bytes;
       if (elect_one()) {
-        for (int dyi = 0; dyi < p.n_dy; ++dyi) {
+        for (int dyi = 0; dyi < n_dy; ++dyi) {
           for (int dx = 0; dx < p.KW; ++dx) {
             const uint32_t d_tmem = tmem_base + (dyi * p.KW + dx) * p.n_cols;
             // flattened pixel shift of this tap inside the window: dyi rows + (dx - PW) pixels, 128 B each
@@ -145,7 +163,7 @@ wgrad_tc_kernel(const WgradParams p, const __grid_constant__ CUtensorMap tx0, co
     int stage = 0;
     uint32_t phase = 0;
     const int n_halo = p.SW - p.TW;                      // columns [0,PW) and [PW+TW, SW)
-    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+    for (int t = t_first; t < p.num_tiles; t += t_step) {
       mbar_wait(bar_full(stage), phase);
       if (n_halo > 0) {
         uint8_t* gb = smem_gen + stage * p.stage_bytes + g_off;
@@ -170,7 +188,7 @@ wgrad_tc_kernel(const WgradParams p, const __grid_constant__ CUtensorMap tx0, co
     // ===================== epilogue (once): TMEM -> red.add.f32 into the global accumulation buffer ==============
     const int q = warp & 3;
     const int ci = q * 32 + lane;
-    if (blockIdx.x < p.num_tiles) {
+    if (t_first < p.num_tiles) {
       mbar_wait(bar_done, 0);
       tc_fence_after();
       // this CTA's partial sums go to its own slice of the accumulation buffer ([cta][dx][128][ld_n], plain stores);
@@ -179,8 +197,8 @@ wgrad_tc_kernel(const WgradParams p, const __grid_constant__ CUtensorMap tx0, co
       // Default (p.atomic): all CTAs add into ONE copy with 16-byte vector reds - 148 x ~200 KB of partial stores plus a
       // reduce kernel reading them back cost ~10 us per launch and 1.5 ms per training step; the summation order over
       // CTAs is then not fixed (last-bit run-to-run differences, like cuDNN's atomics-based weight gradients).
-      float* base = p.dacc + (p.atomic ? 0 : static_cast<size_t>(blockIdx.x) * p.part_stride);
-      for (int tp = 0; tp < p.n_dy * p.KW; ++tp) {
+      float* base = out_base;
+      for (int tp = 0; tp < n_dy * p.KW; ++tp) {
         float* dst = base + (static_cast<size_t>(tp) * 128 + ci) * p.ld_n;
         for (int c = 0; c < p.n_cols; c += 8) {
           uint32_t r[8];
@@ -224,7 +242,7 @@ int launch_wgrad_tc(const WgradParams& p, const CUtensorMap& tx0, const CUtensor
     if (e != cudaSuccess) return static_cast<int>(e);
     configured[dev] = true;
   }
-  const int grid = p.n_parts;
+  const int grid = p.jobs_ci > 0 ? p.jobs_ci * p.jobs_co * p.jobs_dy * p.splits : p.n_parts;
   wgrad_tc_kernel<<<grid, kWgradThreads, smem, stream>>>(p, tx0, tx1, tg0, tg1);
   return static_cast<int>(cudaGetLastError());
 }

@@ -32,6 +32,14 @@ struct WgradParams {
   int ld_n;
   int atomic;                // 1: every CTA adds its sums into part 0 with red.global.add.v4.f32 (the host zeroes it first) instead of
                              //    storing a private partial slice that a reduce kernel would have to read back
+  // Job mode (jobs_ci > 0; layers with many channels and few pixels - the discriminator): the grid is NOT split over pixels only.
+  // CTA b works on job b / splits = (ci chunk of 128, co chunk of n_cols, group of per_dy vertical taps) and, within the job, on
+  // every splits-th pixel tile; it adds its sums into the job's own block dacc + job * job_stride ([per_dy*KW][128][n_cols]).
+  // One launch then covers a whole layer (a 512 -> 512 conv: 4 x 4 x 3 jobs) instead of one launch per (chunk, chunk, tap).
+  int jobs_ci, jobs_co, jobs_dy, splits;
+  int KH, PH, per_dy;
+  int x_coff, g_coff;        // first channel of the layer's input / output gradient inside their buffers
+  long job_stride;
   // debug overrides of the MN-major descriptor fields (0 = default)
   int dbg_a_lbo, dbg_a_sbo, dbg_b_lbo, dbg_b_sbo, dbg_flags;
 };
