@@ -234,6 +234,7 @@ struct PackPart {
   int co_lo, n_store, npad;
   size_t w_off, b_off;
   int w_bytes;
+  int stream = 0;          // 1: too large to stay resident next to the window ring: streamed k-block by k-block (ConvParams::stream_w)
 };
 struct PackLayer {
   int cin_pad;
@@ -243,7 +244,7 @@ static int part_weight_bytes(int kh, int kw, int cin_pad, int npad) { return kh 
 // UMMA N = KW*npad <= 256 and two accumulator buffers of KW*npad fp32 columns must fit the 512 TMEM columns.
 static int max_npad(int kw) { return std::max(16, std::min(kMaxNpad, 256 / kw / 16 * 16)); }
 
-static std::vector<PackLayer> pack_layout(const std::vector<LayerSpec>& layers, size_t* total) {
+static std::vector<PackLayer> pack_layout(const std::vector<LayerSpec>& layers, size_t* total, bool allow_stream = false) {
   std::vector<PackLayer> out;
   size_t off = 0;
   for (const auto& L : layers) {
@@ -252,7 +253,10 @@ static std::vector<PackLayer> pack_layout(const std::vector<LayerSpec>& layers, 
     const int npad_full = (L.cout + 15) / 16 * 16;
     const int kh = L.up2 ? 2 : L.kh, kw = L.up2 ? 2 : L.ekw();
     int nsplit = 1;
-    while ((part_weight_bytes(kh, kw, pl.cin_pad, ceil_div(npad_full / 16, nsplit) * 16) > kMaxResidentWeightBytes ||
+    // layers whose 64-output-channel part would not fit next to a window ring (>= 256 input channels at 3x3) either split further
+    // (16-channel parts: 32 thin launches for 512 -> 512) or, for the single-conv API, keep 64-channel parts and stream the weights
+    const bool stream = allow_stream && !L.up2 && part_weight_bytes(kh, kw, pl.cin_pad, std::min(npad_full, max_npad(kw))) > kMaxResidentWeightBytes;
+    while (((!stream && part_weight_bytes(kh, kw, pl.cin_pad, ceil_div(npad_full / 16, nsplit) * 16) > kMaxResidentWeightBytes) ||
             ceil_div(npad_full / 16, nsplit) * 16 > max_npad(kw)) && nsplit < npad_full / 16) ++nsplit;
     const int per = ceil_div(npad_full / 16, nsplit) * 16;
     for (int phase = L.up2 ? 0 : -1; phase < (L.up2 ? 4 : 0); ++phase) {
@@ -267,6 +271,7 @@ static std::vector<PackLayer> pack_layout(const std::vector<LayerSpec>& layers, 
         pp.npad = std::min(per, npad_full - lo);
         pp.n_store = std::min(L.cout - lo, pp.npad);
         pp.w_bytes = part_weight_bytes(kh, kw, pl.cin_pad, pp.npad);
+        pp.stream = stream ? 1 : 0;
         pp.w_off = off;
         off = align_up(off + pp.w_bytes, 128);
         pp.b_off = off;
@@ -286,7 +291,7 @@ struct Tiling {
   double eff;   // useful fraction of the MMA rows (with the small penalties applied by choose_tiling)
 };
 static int choose_tiling(int H, int W, int KH, int KW, int w_bytes, int n_kblocks, int stage_row_bytes, int n_stage, Tiling* out,
-                         int row_bytes = 128, int tall = 1) {
+                         int row_bytes = 128, int tall = 1, int extra_slot_bytes = 0) {
   double best = -1;
   for (int SW = 16; SW <= 128; SW *= 2) {
     if (g_opt_force_sw && SW != g_opt_force_sw) continue;
@@ -297,7 +302,7 @@ static int choose_tiling(int H, int W, int KH, int KW, int w_bytes, int n_kblock
     const int TH = kTileM / SW;
     const int win_rows = tall * TH + KH - 1;
     const int win_bytes = win_rows * SW * row_bytes;
-    const int slot_bytes = (int)align_up(win_bytes, 1024);
+    const int slot_bytes = (int)align_up(win_bytes, 1024) + (int)align_up(extra_slot_bytes, 1024);   // + a streamed weight k-block
     const int stage_bytes = stage_row_bytes ? (int)align_up((size_t)TH * TW * stage_row_bytes, 1024) : 0;
     const int fixed = 1024 + (int)align_up(w_bytes, 128) + 256 + 512 + n_stage * stage_bytes;
     const int slots = std::min(g_opt_max_slots, (kSmemLimit - fixed) / slot_bytes);
@@ -370,7 +375,7 @@ static int build_conv(const PackLayer& pl, const PackPart& pp, int N, int H, int
   // convs): each CTA keeps half of the weights, so the window ring gets 5 slots instead of 2.  Needs an even tile count
   // (the two CTAs of a pair always work on adjacent tiles) and one of the specialised epilogues.
   const int res_bits = (io.r1 ? 1 : 0) | (io.r2 ? 2 : 0) | (io.gate ? 4 : 0);
-  if (g_opt_pair && tma_out && p.KW == 3 && p.PW == 1 && (p.KW * p.npad) % 16 == 0 && p.w_bytes >= 96 * 1024 && io.act == CSR_ACT_NONE &&
+  if (g_opt_pair && !pp.stream && tma_out && p.KW == 3 && p.PW == 1 && (p.KW * p.npad) % 16 == 0 && p.w_bytes >= 96 * 1024 && io.act == CSR_ACT_NONE &&
       (res_bits == 1 || res_bits == 3 || res_bits == 4 || res_bits == 5) && !g_opt_force_generic) {
     Tiling tp;
     const int pair_groups = g_opt_pair == 2 ? 1 : p.n_groups;   // 2: one 16-warp epilogue group per CTA (shorter accumulator hand-back)
@@ -389,7 +394,13 @@ static int build_conv(const PackLayer& pl, const PackPart& pp, int N, int H, int
   // Thin layers (<= 32 output channels: four accumulator buffers) are bound by the per-tile work of the producer and
   // MMA-issuer warps (~110 / ~250 scalar instructions at ~5 clk each), not by MMAs or bytes: give them windows of two M
   // tiles, which halves that work per tile and shrinks the halo from 6/4 to 10/8 rows.
-  if (!p.pair) rc = choose_tiling(H, W, pp.kh, pp.kw, p.w_bytes, p.n_kblocks, p.stage_row_bytes, p.n_groups, &tl, p.box_c * 2);
+  if (pp.stream) {
+    p.stream_w = 1;
+    p.n_groups = 1;                                        // one staging buffer: two (window + weight k-block) slots of ~96 KB must fit
+    p.wkb_bytes = pp.kh * 4 * pp.kw * pp.npad * 32;
+    rc = choose_tiling(H, W, pp.kh, pp.kw, 0, p.n_kblocks, p.stage_row_bytes, p.n_groups, &tl, 128, 1, p.wkb_bytes);
+    if (!rc && tl.n_slots < 2) rc = fail(CSR_ERR_UNSUPPORTED, "streamed-weight conv: window ring too shallow");
+  } else if (!p.pair) rc = choose_tiling(H, W, pp.kh, pp.kw, p.w_bytes, p.n_kblocks, p.stage_row_bytes, p.n_groups, &tl, p.box_c * 2);
   if (!rc && g_opt_tall && !p.pair && p.n_acc == 4 && p.n_groups == 4) {
     Tiling t2;   // taken unless the second M tile would mostly hang below the image
     if (choose_tiling(H, W, pp.kh, pp.kw, p.w_bytes, p.n_kblocks, p.stage_row_bytes, p.n_groups, &t2, p.box_c * 2, 2) == CSR_OK &&
@@ -477,6 +488,7 @@ static int build_conv(const PackLayer& pl, const PackPart& pp, int N, int H, int
   p.magic_img = ((1ull << 40) / (unsigned)p.tiles_per_img) + 1;
   p.magic_row = ((1ull << 40) / (unsigned)p.tiles_x) + 1;
   p.win_rows = tl.win_rows; p.win_bytes = tl.win_bytes; p.slot_bytes = tl.slot_bytes; p.n_slots = tl.n_slots;
+  p.win_slot_bytes = (int)align_up(tl.win_bytes, 1024);
   p.stage_bytes = tl.stage_bytes;
   p.n_mma = g_opt_one_mma ? 1 : 2;
   p.issue_order = (p.n_mma == 2) && (g_opt_issue_order == 2 || (g_opt_issue_order == 1 && p.pair));
@@ -1946,7 +1958,7 @@ size_t csr_conv2d_scratch_bytes(const CsrConvDesc* d) {
   LayerSpec L;
   if (conv_desc_to_layer(d, &L)) return 0;
   size_t total = 0;
-  pack_layout({L}, &total);
+  pack_layout({L}, &total, true);
   return total;
 }
 
@@ -1960,7 +1972,7 @@ int csr_conv2d_nhwc(const CsrConvDesc* d, const void* in, const float* weight, c
   rc = device_info(&di);
   if (rc) return rc;
   size_t total = 0;
-  const auto packs = pack_layout({L}, &total);
+  const auto packs = pack_layout({L}, &total, true);
   if (scratch_bytes < total) return fail(CSR_ERR_WORKSPACE, "scratch %zu < %zu bytes", scratch_bytes, total);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   uint8_t* base = reinterpret_cast<uint8_t*>(scratch);

@@ -157,7 +157,7 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
   const uint32_t stage_addr = slots_addr + static_cast<uint32_t>(p.n_slots) * p.slot_bytes;   // one staging buffer per epilogue group
   const uint32_t w_addr = stage_addr + static_cast<uint32_t>(p.n_stage) * p.stage_bytes;
   const uint32_t crank = PAIR_T ? cluster_ctarank() : 0u;   // rank in the CTA pair; rank 0 (leader) issues the MMAs
-  const int w_local = PAIR_T ? (p.w_bytes >> 1) : p.w_bytes;  // resident weight bytes of this CTA
+  const int w_local = p.stream_w ? 0 : (PAIR_T ? (p.w_bytes >> 1) : p.w_bytes);  // resident weight bytes of this CTA
   const uint32_t bias_addr = w_addr + ((w_local + 127) & ~127);
   const uint32_t bar_addr = bias_addr + 256;            // up to 64 fp32 biases
   // barriers: [0] weights, [1..S] a_full, [1+S..2S] a_empty, then acc_full[8], acc_empty[8], token[2]
@@ -206,7 +206,7 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
     fence_proxy_async_smem();
   }
   if constexpr (PAIR_T) cluster_sync_all();               // both CTAs' barriers exist before anything arrives on them remotely
-  if (threadIdx.x == 0) {
+  if (threadIdx.x == 0 && !p.stream_w) {
     // layer weights (constant data, not produced by the previous kernel): resident for the whole CTA
     const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.wpk);
     if constexpr (PAIR_T) {
@@ -264,6 +264,15 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
         mbar_wait_spin(bar_a_empty(slot), phase ^ 1);
         if (kb == 0 && lane == 0) CSR_TRACE(0, pit, 1);
         if (elect_one()) {
+          if (p.stream_w) {
+            // streamed weights: this k-block's packed weights travel with the window (same barrier)
+            const int ks_here = min(4, (p.cin >> 4) - kb * 4);
+            const int wbytes = p.KH * ks_here * (KW * p.npad) * 32;
+            mbar_arrive_expect_tx(bar_a_full(slot), p.win_bytes + wbytes);
+            const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.wpk) + static_cast<size_t>(kb) * p.wkb_bytes;
+            const uint32_t wdst = slots_addr + slot * p.slot_bytes + p.win_slot_bytes;
+            for (int off = 0; off < wbytes; off += 32768) bulk_load(wdst + off, wsrc + off, min(32768, wbytes - off), bar_a_full(slot));
+          } else
           // pair: both CTAs' windows are counted on the leader's barrier, which the MMA issuer waits on
           if (crank == 0) mbar_arrive_expect_tx(bar_a_full(slot), PAIR_T ? 2 * p.win_bytes : p.win_bytes);
           if constexpr (PAIR_T)
@@ -304,7 +313,7 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
     const uint32_t a_hi = ((8u * row_bytes) >> 4) | (1u << 14) | (a_layout << 29);   // SBO = 8 rows, version 1
     const uint32_t b_hi = (256u >> 4) | (1u << 14);                           // SBO 256 B, version 1, no swizzle
     const uint32_t a_lbo = (16u >> 4) << 16, b_lbo = (128u >> 4) << 16;
-    mbar_wait_spin(bar_w, 0);
+    if (!p.stream_w) mbar_wait_spin(bar_w, 0);
     tc_fence_after();
     // window-slot ring position of k-block 0 of this warp's first tile (the ring is shared by both issuers: tile `it`
     // owns ring entries it*n_kblocks .. it*n_kblocks + n_kblocks-1)
@@ -349,7 +358,8 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
         if (kb == 0 && lane == 0) CSR_TRACE(1, it, 2);
         const int ks_here = min(4, ksteps_total - kb * 4);
         uint32_t a16 = ((slots_addr + slot * p.slot_bytes) >> 4) | a_lbo;
-        uint32_t b16 = ((w_addr >> 4) + static_cast<uint32_t>(kb) * kb_w16) | b_lbo;
+        uint32_t b16 = (p.stream_w ? ((slots_addr + slot * p.slot_bytes + p.win_slot_bytes) >> 4)
+                                   : ((w_addr >> 4) + static_cast<uint32_t>(kb) * kb_w16)) | b_lbo;
         if (elect_one()) {
           const bool last_kb = kb == p.n_kblocks - 1;
           if constexpr (TALL_T == 0) {
@@ -703,7 +713,7 @@ done:
 
 size_t conv_smem_bytes(const ConvParams& p) {
   return 1024 /*alignment slack*/ + static_cast<size_t>(p.n_slots) * p.slot_bytes + static_cast<size_t>(p.n_stage) * p.stage_bytes +
-         (((p.pair ? p.w_bytes / 2 : p.w_bytes) + 127) & ~127) + 256 /*bias*/ + 8 * (19 + 2 * p.n_slots) + 32;
+         (((p.stream_w ? 0 : p.pair ? p.w_bytes / 2 : p.w_bytes) + 127) & ~127) + 256 /*bias*/ + 8 * (19 + 2 * p.n_slots) + 32;
 }
 
 template <int KW_T, int PW_T, int ACT_T, int RES_T, int ST_T, int PAIR_T = 0, int TALL_T = 0, int EARLY_T = 0>

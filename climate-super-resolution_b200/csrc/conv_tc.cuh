@@ -56,6 +56,10 @@ struct ConvParams {
                    //    two accumulator buffers): halves the per-tile control cost of thin layers; needs n_acc == 4.  tiles_* / num_tiles
                    //    then count windows.  0: one M tile per window
   int pair;        // 1 = CTA-pair launch (cluster of 2, M = 256 MMAs, half of the weights resident per CTA); needs an even tile count
+  int stream_w;    // 1: the layer's weights do NOT stay resident (layers with >= 256 input channels: > 150 KB per 64 output channels): every
+                   //    window slot also receives the packed weights of its 64-channel k-block (wkb_bytes, at offset win_slot_bytes)
+  int wkb_bytes;   // packed weights of one full k-block: KH * 4 * KW * npad * 32
+  int win_slot_bytes;
   int l2_prefetch; // > 0: the producer prefetches the window of the tile `l2_prefetch` iterations ahead into L2 (layers that stream from HBM)
   int use_pdl;     // launch with programmatic stream serialization (prologue overlaps the previous kernel's tail)
   // epilogue:  v = act(acc + bias [+ r1 if r1_pre]);  if r1 (not r1_pre): v = v*s1 + r1;  if r2: v = v*s2 + r2;  if gate: v *= (gate > 0 ? 1 : gate_neg)
