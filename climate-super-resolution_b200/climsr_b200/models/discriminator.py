@@ -14,6 +14,12 @@ same order, so ``load_state_dict`` of a reference checkpoint and ``torch.manual_
 
 Driven by climsr/task/pl_gan.py:28-61 (four forwards and two backwards per batch; the generator's adversarial loss needs the
 gradient w.r.t. the input through frozen discriminator weights - produced here too).  There is no CPU / cuDNN fallback.
+
+Launch overhead: one forward is ~55 small launches, forward + backward ~190, and composed call by call from Python the step was
+bound by the host (~11 us per launch).  From the third call with a given batch size on, forward and backward therefore replay
+CUDA graphs (``use_cuda_graphs``, default on): every call leases a *slot* - static input / activation / gradient buffers plus the
+graphs captured over them - until its backward has run, so D(hr) and D(sr) of one GAN batch live in two slots.  Weight packs
+are refreshed outside the graphs (csr_conv2d_pack) whenever the weights change; results are bit-identical to the eager path.
 """
 from __future__ import annotations
 
@@ -63,17 +69,20 @@ def _conv_t(g: Tensor, w: Tensor, cache=None) -> Tensor:
     return ops.conv2d_nhwc(g, w, None, transposed=True, scratch=scratch, prepacked=pre)
 
 
-def _wgrad(p: Tensor, g: Tensor, w: Tensor):
-    """Weight / bias gradient of a conv layer: one GEMM launch per layer (job mode of the weight-gradient kernel)."""
-    return ops.conv2d_wgrad(p, g, tuple(w.shape))
+def _wgrad(p: Tensor, g: Tensor, w: Tensor, out):
+    """Weight / bias gradient of a conv layer into the zeroed views ``out`` = (dw, db): one GEMM launch per layer (job mode of the
+    weight-gradient kernel)."""
+    return ops.conv2d_wgrad(p, g, tuple(w.shape), dw=out[0], db=out[1])
 
 
 class _DiscriminatorFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, module, x, *params):
-        out, saved = module._run_forward(x, save=True)
-        ctx.module, ctx.saved = module, saved
+        need_params = any(p.requires_grad for p in params)
+        out, saved, lease = module._forward_saving(x)
+        ctx.module, ctx.saved, ctx.lease = module, saved, lease
         ctx.need_param_grads = [p.requires_grad for p in params]
+        ctx.need_params = need_params
         ctx.set_materialize_grads(False)
         return out
 
@@ -82,15 +91,46 @@ class _DiscriminatorFunction(torch.autograd.Function):
         n_in = 2 + len(ctx.need_param_grads)
         if gy is None:
             return (None,) * n_in
-        dx, grads = ctx.module._run_backward(ctx.saved, gy, ctx.needs_input_grad[1], any(ctx.need_param_grads))
-        ctx.saved = None
+        dx, grads = ctx.module._backward_saved(ctx.saved, ctx.lease, gy, ctx.needs_input_grad[1], ctx.need_params)
+        ctx.saved = ctx.lease = None
         out = [None, dx]
         for need, gname in zip(ctx.need_param_grads, grads):
             out.append(gname if need else None)
         return tuple(out)
 
 
+class _Slot:
+    """Static buffers + captured graphs of one in-flight discriminator call (see the module docstring)."""
+
+    def __init__(self):
+        self.busy = False
+        self.x = None           # static input
+        self.out = None         # static scores
+        self.saved = None       # static saved activations (save slots only)
+        self.fwd = None         # torch.cuda.CUDAGraph
+        self.bwd = {}           # (need_dx, need_params) -> (graph, gy_static, dx_static, flat_static, grads views)
+
+
+class _Lease:
+    """Marks a slot free again when the autograd context that holds it goes away (backward ran, or the graph was dropped)."""
+
+    def __init__(self, slot):
+        self.slot = slot
+        slot.busy = True
+
+    def release(self):
+        if self.slot is not None:
+            self.slot.busy = False
+            self.slot = None
+
+    def __del__(self):
+        self.release()
+
+
 class Discriminator(nn.Module):
+    use_cuda_graphs = True          # replay forward / backward as CUDA graphs from the third call of a kind on
+    _EAGER_CALLS = 2                # calls of a kind that run eagerly first (module load, attribute set-up, both calls of a first GAN batch)
+
     def __init__(self, in_channels=1, out_channels=64, num_conv_block=4):
         super().__init__()
         if in_channels != 1 or out_channels != 64 or num_conv_block != 4:
@@ -111,10 +151,11 @@ class Discriminator(nn.Module):
 
     # ------------------------------------------------------------------ packed-weight cache
     def _packed(self, conv: nn.Conv2d, transposed: bool):
-        """(scratch, prepacked) for one conv layer: the packed bf16 weight tiles are reused until the weights change - the four
-        forwards and two backwards of a GAN batch (pl_gan.py:28-61) see at most two weight versions.  Keyed like the generator's
-        pack cache: storage pointer, version counter and the process-wide optimizer-step epoch (fused optimizers do not bump
-        version counters)."""
+        """(scratch, True): the layer's packed bf16 weight tiles, re-packed (csr_conv2d_pack, outside any graph) only when the
+        weights changed - the four forwards and two backwards of a GAN batch (pl_gan.py:28-61) see at most two weight versions.
+        Keyed like the generator's pack cache: storage pointer, version counter and the process-wide optimizer-step epoch (fused
+        optimizers do not bump version counters).  The scratch tensor of a layer is never reallocated, so captured graphs that
+        read it stay valid across weight updates."""
         from .esrgan import _WEIGHT_EPOCH
         cache = self.__dict__.setdefault("_pack_cache", {})
         w, b = conv.weight, conv.bias
@@ -122,16 +163,29 @@ class Discriminator(nn.Module):
         ent = cache.get((id(conv), transposed))
         if ent is not None and ent[1] == key:
             return ent[0], True
-        nbytes = ops.conv2d_scratch_bytes(conv.out_channels, conv.in_channels, 3, 3, transposed) if not transposed else \
-            ops.conv2d_scratch_bytes(conv.in_channels, conv.out_channels, 3, 3, True)
-        scratch = ent[0] if ent is not None and ent[0].numel() >= nbytes and ent[0].device == w.device else \
-            torch.empty(max(nbytes, 16), dtype=torch.uint8, device=w.device)
+        if ent is not None and ent[0].device == w.device:
+            scratch = ent[0]
+        else:
+            nbytes = ops.conv2d_scratch_bytes(conv.out_channels, conv.in_channels, 3, 3, False) if not transposed else \
+                ops.conv2d_scratch_bytes(conv.in_channels, conv.out_channels, 3, 3, True)
+            scratch = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=w.device)
+            self.__dict__["_slots"] = {}                      # new scratch storage: graphs captured over the old one are stale
+        ops.conv2d_pack(w, None if transposed else b, scratch, transposed)
         cache[(id(conv), transposed)] = (scratch, key)
-        return scratch, False
+        return scratch, True
+
+    def _refresh_packs(self, transposed: bool) -> None:
+        stages, conv4, conv5, _, _ = self._layers()
+        for conv_a, _, conv_b in stages:
+            self._packed(conv_a, transposed)
+            self._packed(conv_b, transposed)
+        self._packed(conv4, transposed)
+        self._packed(conv5, transposed)
 
     def __getstate__(self):
         state = dict(self.__dict__)
-        state.pop("_pack_cache", None)
+        for k in ("_pack_cache", "_slots", "_calls"):
+            state.pop(k, None)
         return state
 
     def __deepcopy__(self, memo):
@@ -139,7 +193,7 @@ class Discriminator(nn.Module):
         new = self.__class__.__new__(self.__class__)
         memo[id(self)] = new
         for k, v in self.__dict__.items():
-            if k != "_pack_cache":
+            if k not in ("_pack_cache", "_slots", "_calls"):
                 new.__dict__[k] = copy.deepcopy(v, memo)
         return new
 
@@ -160,7 +214,93 @@ class Discriminator(nn.Module):
         params = self._param_order()
         if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in params)):
             return _DiscriminatorFunction.apply(self, x, *params)
-        return self._run_forward(x, save=False)[0]
+        return self._forward_saving(x, save=False)[0]
+
+    # ------------------------------------------------------------------ CUDA-graph slots
+    def _graph_key(self, x: Tensor, save: bool):
+        bn_mode = tuple(self.training or not st[1].track_running_stats for st in self._layers()[0])
+        ptrs = tuple(t.data_ptr() for t in self.parameters()) + tuple(t.data_ptr() for t in self.buffers())
+        return (x.device, x.shape[0], save, bn_mode, ptrs)
+
+    def _graphs_usable(self, x: Tensor) -> bool:
+        return bool(self.use_cuda_graphs) and not torch.cuda.is_current_stream_capturing()
+
+    def _forward_saving(self, x: Tensor, save: bool = True):
+        """(scores, saved, lease).  Eager for the first calls of a kind, then a graph replay on a leased slot."""
+        with torch.cuda.device(x.device):
+            self._refresh_packs(False)
+            if not self._graphs_usable(x):
+                out, saved = self._run_forward(x, save)
+                return out, saved, None
+            key = self._graph_key(x, save)
+            calls = self.__dict__.setdefault("_calls", {})
+            calls[key] = calls.get(key, 0) + 1
+            if calls[key] <= self._EAGER_CALLS:
+                out, saved = self._run_forward(x, save)
+                return out, saved, None
+            slots = self.__dict__.setdefault("_slots", {}).setdefault(key, [])
+            slot = next((sl for sl in slots if not sl.busy), None)
+            if slot is None:
+                if len(slots) >= 8:                                # leases that never came back (graphs kept alive by the caller)
+                    out, saved = self._run_forward(x, save)
+                    return out, saved, None
+                slot = _Slot()
+                slot.x = torch.empty_like(x, dtype=torch.float32, memory_format=torch.contiguous_format)
+                slot.x.copy_(x.detach())
+                torch.cuda.current_stream().synchronize()
+                slot.fwd = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(slot.fwd):
+                    slot.out, slot.saved = self._run_forward(slot.x, save)
+                slots.append(slot)
+            else:
+                slot.x.copy_(x.detach())
+            slot.fwd.replay()
+            lease = _Lease(slot) if save else None
+            return slot.out.clone(), slot.saved, lease
+
+    def _backward_saved(self, saved, lease, gy: Tensor, need_dx: bool, need_params: bool):
+        with torch.cuda.device(gy.device):
+            if need_dx or need_params:
+                self._refresh_packs(True)
+            slot = lease.slot if lease is not None else None
+            if slot is None or not self._graphs_usable(gy):
+                res = self._run_backward(saved, gy, need_dx, need_params)
+                if lease is not None:
+                    lease.release()
+                return res
+            variant = (bool(need_dx), bool(need_params))
+            calls = self.__dict__.setdefault("_calls", {})
+            ckey = ("bwd", gy.device, saved["n"]) + variant
+            calls[ckey] = calls.get(ckey, 0) + 1
+            if calls[ckey] <= self._EAGER_CALLS:
+                res = self._run_backward(saved, gy, need_dx, need_params)
+                lease.release()
+                return res
+            ent = slot.bwd.get(variant)
+            if ent is None:
+                gys = torch.empty_like(gy, dtype=torch.float32, memory_format=torch.contiguous_format)
+                gys.copy_(gy.detach())
+                torch.cuda.current_stream().synchronize()
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    dx, grads, flat = self._run_backward(saved, gys, need_dx, need_params, return_flat=True)
+                ent = slot.bwd[variant] = (graph, gys, dx, flat, grads)
+            else:
+                ent[1].copy_(gy.detach())
+            graph, _, dx, flat, grads = ent
+            graph.replay()
+            # the static buffers are overwritten by the next replay: hand out copies (one for all parameter gradients)
+            dx_out = dx.clone() if dx is not None else None
+            if flat is not None:
+                fc = flat.clone()
+                out, off = [], 0
+                for g in grads:
+                    out.append(fc[off:off + g.numel()].view(g.shape))
+                    off += g.numel()
+            else:
+                out = grads
+            lease.release()
+            return dx_out, out
 
     # ------------------------------------------------------------------ forward
     def _run_forward(self, x: Tensor, save: bool):
@@ -220,24 +360,42 @@ class Discriminator(nn.Module):
         return y2, (saved if save else None)
 
     # ------------------------------------------------------------------ backward
-    def _run_backward(self, sv, gy: Tensor, need_dx: bool, need_params: bool):
+    def _run_backward(self, sv, gy: Tensor, need_dx: bool, need_params: bool, return_flat: bool = False):
         dev = gy.device
         n = sv["n"]
         stages, conv4, conv5, lin0, lin1 = self._layers()
         f32 = lambda t: t.detach().contiguous().float()  # noqa: E731
         grads = {}
+        # every parameter gradient is a view of ONE zeroed buffer (parameters() order): one memset instead of 24, and one copy when a
+        # graph replay hands the gradients out
+        mods = self._module_order()
+        flat = None
+        gviews = {}
+        if need_params:
+            total = sum(m.weight.numel() + m.bias.numel() for m in mods)
+            flat = torch.zeros(total, dtype=torch.float32, device=dev)
+            off = 0
+            for m in mods:
+                wv = flat[off:off + m.weight.numel()].view(m.weight.shape)
+                off += m.weight.numel()
+                bv = flat[off:off + m.bias.numel()].view(m.bias.shape)
+                off += m.bias.numel()
+                gviews[m] = (wv, bv)
+        else:                                                     # frozen parameters: BatchNorm backward still writes its two sums
+            for m in mods:
+                if isinstance(m, nn.BatchNorm2d):
+                    t = torch.zeros(2 * m.num_features, dtype=torch.float32, device=dev)
+                    gviews[m] = (t[:m.num_features], t[m.num_features:])
         with torch.cuda.device(dev):
             g2 = gy.detach().contiguous().float()
             k0, j0 = lin0.in_features, lin0.out_features
             w1, w0 = f32(lin1.weight), f32(lin0.weight)
             dy1 = torch.empty((n, j0), dtype=torch.float32, device=dev)
-            dw1 = torch.zeros_like(w1) if need_params else None
-            db1 = torch.zeros(lin1.out_features, dtype=torch.float32, device=dev) if need_params else None
+            dw1, db1 = gviews[lin1] if need_params else (None, None)
             check(lib.csr_linear_backward(sv["y1"].data_ptr(), w1.data_ptr(), g2.data_ptr(), dy1.data_ptr(), _ptr(dw1), _ptr(db1), n, j0,
                                           lin1.out_features, current_stream_ptr()), "csr_linear_backward")
             dfeat = torch.empty((n, k0), dtype=torch.float32, device=dev)
-            dw0 = torch.zeros_like(w0) if need_params else None
-            db0 = torch.zeros(j0, dtype=torch.float32, device=dev) if need_params else None
+            dw0, db0 = gviews[lin0] if need_params else (None, None)
             check(lib.csr_linear_backward(sv["feats"].data_ptr(), w0.data_ptr(), dy1.data_ptr(), dfeat.data_ptr(), _ptr(dw0), _ptr(db0), n, k0, j0,
                                           current_stream_ptr()), "csr_linear_backward")
             grads[lin1] = (dw1, db1)
@@ -247,11 +405,11 @@ class Discriminator(nn.Module):
             check(lib.csr_disc_unflatten(dfeat.data_ptr(), C.byref(v5), n, g5.data_ptr(), current_stream_ptr()), "csr_disc_unflatten")
             w5, w4 = f32(conv5.weight), f32(conv4.weight)
             if need_params:
-                grads[conv5] = _wgrad(sv["p5"], g5, w5)
+                grads[conv5] = _wgrad(sv["p5"], g5, w5, gviews[conv5])
             dp5 = _conv_t(g5, w5, self._packed(conv5, True))
             g4 = _collect(dp5, v4, n, 0, sv["s4"], SLOPE_TAIL)
             if need_params:
-                grads[conv4] = _wgrad(sv["p4"], g4, w4)
+                grads[conv4] = _wgrad(sv["p4"], g4, w4, gviews[conv4])
             dp = _conv_t(g4, w4, self._packed(conv4, True))
             pad_next = 0
             for (conv_a, bn, conv_b), st in zip(reversed(stages), reversed(sv["stages"])):
@@ -259,12 +417,11 @@ class Discriminator(nn.Module):
                 gb = _collect(dp, st["vb"], n, pad_next, st["sb"], SLOPE)
                 wb = f32(conv_b.weight)
                 if need_params:
-                    grads[conv_b] = _wgrad(st["pb"], gb, wb)
+                    grads[conv_b] = _wgrad(st["pb"], gb, wb, gviews[conv_b])
                 dpb = _conv_t(gb, wb, self._packed(conv_b, True))
                 va = st["va"]
                 ga = torch.empty((n, va.hs, va.ws, c), dtype=torch.bfloat16, device=dev)
-                dgamma = torch.zeros(c, dtype=torch.float32, device=dev)
-                dbeta = torch.zeros(c, dtype=torch.float32, device=dev)
+                dgamma, dbeta = gviews[bn]
                 gamma = f32(bn.weight)
                 if st["bn_training"]:
                     dy = torch.empty((n, va.hl, va.wl, c), dtype=torch.float32, device=dev)
@@ -278,7 +435,7 @@ class Discriminator(nn.Module):
                 grads[bn] = (dgamma, dbeta)
                 wa = f32(conv_a.weight)
                 if need_params:
-                    grads[conv_a] = _wgrad(st["pa"], ga, wa)
+                    grads[conv_a] = _wgrad(st["pa"], ga, wa, gviews[conv_a])
                 is_first = conv_a is stages[0][0]
                 if not is_first or need_dx:
                     dp = _conv_t(ga, wa, self._packed(conv_a, True))
@@ -289,9 +446,12 @@ class Discriminator(nn.Module):
                 gx = _collect(dp, v0, n, 1, None, 1.0)
                 dx = ops.nhwc_bf16_to_nchw(gx, 1)
         out = []
-        for mod in self._module_order():
+        for mod in mods:
             gw, gb_ = grads.get(mod, (None, None))
             out += [gw, gb_]
+        if return_flat:
+            # parameters() order == the flat buffer's order; missing entries (need_params False) stay None
+            return dx, out, flat
         return dx, out
 
     def _module_order(self):

@@ -79,6 +79,20 @@ def conv2d_nhwc(inp: Tensor, weight: Tensor, bias: Optional[Tensor], *, act: str
     return out
 
 
+def conv2d_pack(weight: Tensor, bias: Optional[Tensor], scratch: Tensor, transposed: bool = False) -> None:
+    """Pack one layer's weights / bias into ``scratch`` (csr_conv2d_pack) for later ``conv2d_nhwc(..., prepacked=True)`` calls."""
+    if transposed:
+        cin, cout, kh, kw = weight.shape
+    else:
+        cout, cin, kh, kw = weight.shape
+    d = ConvDesc(1, 8, 8, cin, cout, kh, kw, 64, 0, 64, 0, 0, 0, 0, int(transposed), 1.0, 1.0, 0, 0, 0, 0, 0, 0, 0, 0.2, 0.0)
+    wc = weight.detach().contiguous().float()
+    bc = bias.detach().contiguous().float() if bias is not None else None
+    with torch.cuda.device(weight.device):
+        check(lib.csr_conv2d_pack(C.byref(d), wc.data_ptr(), bc.data_ptr() if bc is not None else None, scratch.data_ptr(), scratch.numel(),
+                                  current_stream_ptr()), "csr_conv2d_pack")
+
+
 def conv2d_scratch_bytes(cout: int, cin: int, kh: int, kw: int, transposed: bool = False) -> int:
     """Bytes of packed weights + bias of one layer (shape-only query)."""
     d = ConvDesc(1, 8, 8, cin, cout, kh, kw, 64, 0, 64, 0, 0, 0, 0, int(transposed), 1.0, 1.0, 0, 0, 0, 0, 0, 0, 0, 0.2, 0.0)

@@ -701,10 +701,15 @@ static int run_wgrad_layer_jobs(const WgradLayer& L, int N, int H, int W, const 
   *launches += 3;
   if (db) {
     const long npix = (long)N * H * W;
-    for (int co = 0; co < L.cout; co += 128) {
-      float* dbs[1] = {db + co};
-      CSR_CUDA(launch_bias_grad(g, npix, g_C, g_coff + co, std::min(128, L.cout - co), scale, dbs, 1, s));
+    if (L.cout > 128 && L.cout % 128 == 0) {
+      CSR_CUDA(launch_bias_grad_wide(g, npix, g_C, g_coff, L.cout / 128, scale, db, s));
       ++*launches;
+    } else {
+      for (int co = 0; co < L.cout; co += 128) {
+        float* dbs[1] = {db + co};
+        CSR_CUDA(launch_bias_grad(g, npix, g_C, g_coff + co, std::min(128, L.cout - co), scale, dbs, 1, s));
+        ++*launches;
+      }
     }
   }
   return CSR_OK;
@@ -1962,6 +1967,27 @@ size_t csr_conv2d_scratch_bytes(const CsrConvDesc* d) {
   return total;
 }
 
+// all parts of the layer in ONE pack launch
+static int conv2d_pack_parts(const LayerSpec& L, const PackLayer& pl, const float* weight, const float* bias, void* scratch, cudaStream_t s) {
+  uint8_t* base = reinterpret_cast<uint8_t*>(scratch);
+  std::vector<PackJob> jobs;
+  for (const PackPart& pp : pl.parts)
+    jobs.push_back({weight, bias, base + pp.w_off, reinterpret_cast<float*>(base + pp.b_off), L.cout, L.cin, L.kh, L.kw, 0, pp.phase, L.transposed,
+                    1.f, pp.co_lo, pp.npad, pl.cin_pad, 0, 0, 0, 0});
+  return run_pack_jobs(jobs, scratch, s);
+}
+
+int csr_conv2d_pack(const CsrConvDesc* d, const float* weight, const float* bias, void* scratch, size_t scratch_bytes, void* stream) {
+  LayerSpec L;
+  int rc = conv_desc_to_layer(d, &L);
+  if (rc) return rc;
+  if (!weight || !scratch) return fail(CSR_ERR_BAD_ARG, "null pointer");
+  size_t total = 0;
+  const auto packs = pack_layout({L}, &total, true);
+  if (scratch_bytes < total) return fail(CSR_ERR_WORKSPACE, "scratch %zu < %zu bytes", scratch_bytes, total);
+  return conv2d_pack_parts(L, packs[0], weight, bias, scratch, reinterpret_cast<cudaStream_t>(stream));
+}
+
 int csr_conv2d_nhwc(const CsrConvDesc* d, const void* in, const float* weight, const float* bias, void* out, const void* res1,
                     const void* res2, const void* gate, void* scratch, size_t scratch_bytes, void* stream) {
   LayerSpec L;
@@ -1986,25 +2012,37 @@ int csr_conv2d_nhwc(const CsrConvDesc* d, const void* in, const float* weight, c
   io.gate = gate; io.gate_C = d->gate_c; io.gate_coff = d->gate_coff; io.gate_from = d->gate_from; io.gate_neg = d->gate_neg;
   if (d->act == CSR_ACT_LRELU && !(d->act_slope > 0.f && d->act_slope < 1.f)) return fail(CSR_ERR_BAD_ARG, "act_slope must be in (0, 1)");
   if (weight) {
-    // all parts of the layer in ONE pack launch (a 512 -> 512 layer has 32 parts).  weight == NULL: `scratch` still holds the
-    // packed weights / bias of an earlier call with the same layer shape and weights (callers cache it per weight version)
-    std::vector<PackJob> jobs;
-    for (const PackPart& pp : packs[0].parts)
-      jobs.push_back({weight, bias, base + pp.w_off, reinterpret_cast<float*>(base + pp.b_off), L.cout, L.cin, L.kh, L.kw, 0, pp.phase, L.transposed,
-                      1.f, pp.co_lo, pp.npad, packs[0].cin_pad, 0, 0, 0, 0});
-    rc = run_pack_jobs(jobs, scratch, s);
+    // weight == NULL: `scratch` still holds the packed weights / bias of an earlier call (or of csr_conv2d_pack) with the same layer
+    // shape and weights (callers cache it per weight version)
+    rc = conv2d_pack_parts(L, packs[0], weight, bias, scratch, s);
     if (rc) return rc;
   }
-  for (const PackPart& pp : packs[0].parts) {
+  // Equal output-channel parts of a residual-free layer go out as ONE launch (gridDim.y = parts): a 512-channel layer over an
+  // 8 x 8 map is 8 parts of ~16 tiles each - one after the other they would leave nine SMs in ten idle.
+  const std::vector<PackPart>& parts = packs[0].parts;
+  bool merge = parts.size() > 1 && !res1 && !res2 && !gate && d->out_mode == CSR_OUT_BF16_NHWC;
+  for (size_t i = 1; merge && i < parts.size(); ++i)
+    merge = parts[i].phase < 0 && parts[i].npad == parts[0].npad && parts[i].n_store == parts[0].npad && parts[0].n_store == parts[0].npad &&
+            parts[i].w_bytes == parts[0].w_bytes && parts[i].w_off - parts[i - 1].w_off == parts[1].w_off - parts[0].w_off &&
+            parts[i].b_off - parts[i - 1].b_off == parts[1].b_off - parts[0].b_off && parts[i].co_lo - parts[i - 1].co_lo == parts[0].npad;
+  for (size_t i = 0; i < parts.size(); ++i) {
+    const PackPart& pp = parts[i];
     ConvLaunch cl;
     rc = build_conv(packs[0], pp, d->n, d->h, d->w, io, &cl);
     if (rc) return rc;
     cl.p.act_slope = d->act_slope;
     cl.p.wpk = base + pp.w_off;
     cl.p.bias = reinterpret_cast<const float*>(base + pp.b_off);
+    if (merge) {
+      cl.p.parts = (int)parts.size();
+      cl.p.part_w_bytes = (int)(parts[1].w_off - parts[0].w_off);
+      cl.p.part_b_floats = (int)((parts[1].b_off - parts[0].b_off) / sizeof(float));
+      cl.p.part_c = parts[0].npad;
+    }
     int e = launch_conv_tc(cl.p, cl.tmap, di.sms, s);
     if (e) return fail(CSR_ERR_CUDA, "conv launch failed: %s", cudaGetErrorString((cudaError_t)e));
     ++g_launches;
+    if (merge) break;
   }
   return CSR_OK;
 }

@@ -70,7 +70,7 @@ __device__ __forceinline__ Tile decode_tile(const ConvParams& p, int t) {
 
 // The epilogue is instruction-issue bound: its fp32 arithmetic uses the packed two-wide forms (FADD2 / FMUL2 / FFMA2).
 __device__ __forceinline__ void apply_act8(float (&v)[8], int act, float slope = 0.f) {
-  if (act == 4) {                                       // LeakyReLU(slope), 0 < slope < 1 (discriminator: 0.01): generic kernels only
+  if (act == 4) {                                       // LeakyReLU(slope), 0 < slope < 1 (discriminator: 0.01 / 0.2)
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], slope * v[j]);
   } else if (act == 1) {                                       // LeakyReLU(0.2) = max(v, 0.2 v)
@@ -208,7 +208,7 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
   if constexpr (PAIR_T) cluster_sync_all();               // both CTAs' barriers exist before anything arrives on them remotely
   if (threadIdx.x == 0 && !p.stream_w) {
     // layer weights (constant data, not produced by the previous kernel): resident for the whole CTA
-    const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.wpk);
+    const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.wpk) + static_cast<size_t>(blockIdx.y) * p.part_w_bytes;
     if constexpr (PAIR_T) {
       // every (k-block, dy, k-step) block of N rows x 16 K: this CTA keeps rows [crank*N/2, +N/2)
       const int full = (KW_T ? KW_T : p.KW) * p.npad * 32, half = full >> 1;
@@ -232,7 +232,7 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
       tmem_relinquish();
     }
   }
-  for (int i = threadIdx.x; i < p.npad; i += blockDim.x) bias_s[i] = p.bias[i];
+  for (int i = threadIdx.x; i < p.npad; i += blockDim.x) bias_s[i] = p.bias[blockIdx.y * p.part_b_floats + i];
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -269,7 +269,8 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
             const int ks_here = min(4, (p.cin >> 4) - kb * 4);
             const int wbytes = p.KH * ks_here * (KW * p.npad) * 32;
             mbar_arrive_expect_tx(bar_a_full(slot), p.win_bytes + wbytes);
-            const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.wpk) + static_cast<size_t>(kb) * p.wkb_bytes;
+            const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.wpk) + static_cast<size_t>(blockIdx.y) * p.part_w_bytes +
+                                  static_cast<size_t>(kb) * p.wkb_bytes;
             const uint32_t wdst = slots_addr + slot * p.slot_bytes + p.win_slot_bytes;
             for (int off = 0; off < wbytes; off += 32768) bulk_load(wdst + off, wsrc + off, min(32768, wbytes - off), bar_a_full(slot));
           } else
@@ -533,7 +534,7 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
         if (tracer) CSR_TRACE(2, it, 7);
         __nv_bfloat16* tile_out = reinterpret_cast<__nv_bfloat16*>(p.out) +
             ((static_cast<size_t>(tl.n) * p.out_H + (tl.y0 * p.out_sy + p.out_oy)) * p.out_W + (tl.x0 * p.out_sx + p.out_ox)) * p.out_C +
-            p.out_coff;
+            p.out_coff + static_cast<int>(blockIdx.y) * p.part_c;
         const uint32_t lim = (static_cast<uint32_t>(max(0, min(p.H - tl.y0, 0x7fff))) << 16) | static_cast<uint32_t>(min(p.W - tl.x0, 0x7fff));
 #pragma unroll
         for (int k = 0; k < 2; ++k) {                     // <= 128 pixels x 8 pieces over 512 threads
@@ -649,7 +650,7 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
               o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]); o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
               if ((j & 1) == 0) held = o;
               else if (ch0 < p.n_store)
-                st_global_v8(reinterpret_cast<__nv_bfloat16*>(p.out) + opix * p.out_C + p.out_coff + ch0 - 8, held, o);
+                st_global_v8(reinterpret_cast<__nv_bfloat16*>(p.out) + opix * p.out_C + p.out_coff + static_cast<int>(blockIdx.y) * p.part_c + ch0 - 8, held, o);
             } else if (smode == kStoreF32Planar) {
               if (c == 0) reinterpret_cast<float*>(p.out)[opix] = v[0];
             } else {
@@ -657,9 +658,9 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
               for (int i = 0; i < 8; ++i) {
                 if (ch0 + i < p.n_store) {
                   if (p.store_mode == kStoreF32Nhwc)
-                    reinterpret_cast<float*>(p.out)[opix * p.out_C + p.out_coff + ch0 + i] = v[i];
+                    reinterpret_cast<float*>(p.out)[opix * p.out_C + p.out_coff + static_cast<int>(blockIdx.y) * p.part_c + ch0 + i] = v[i];
                   else
-                    reinterpret_cast<__nv_bfloat16*>(p.out)[opix * p.out_C + p.out_coff + ch0 + i] = __float2bfloat16_rn(v[i]);
+                    reinterpret_cast<__nv_bfloat16*>(p.out)[opix * p.out_C + p.out_coff + static_cast<int>(blockIdx.y) * p.part_c + ch0 + i] = __float2bfloat16_rn(v[i]);
                 }
               }
             }
@@ -679,7 +680,7 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
         if (tracer) CSR_TRACE(2, it, 7);
         __nv_bfloat16* tile_out = reinterpret_cast<__nv_bfloat16*>(p.out) +
             ((static_cast<size_t>(tl.n) * p.out_H + (tl.y0 * p.out_sy + p.out_oy)) * p.out_W + (tl.x0 * p.out_sx + p.out_ox)) * p.out_C +
-            p.out_coff;
+            p.out_coff + static_cast<int>(blockIdx.y) * p.part_c;
         // (the lower M tile of a window may lie entirely below the image: no piece passes)
         const uint32_t lim = (static_cast<uint32_t>(max(0, min(p.H - tl.y0, 0x7fff))) << 16) | static_cast<uint32_t>(min(p.W - tl.x0, 0x7fff));
 #pragma unroll
@@ -731,7 +732,10 @@ static int launch_t(const ConvParams& p, const CUtensorMap& tmap, int num_sms, c
     configured[dev] = true;
   }
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(p.num_tiles < num_sms ? p.num_tiles : num_sms);
+  // parts > 1: blockIdx.y selects the output-channel part (same geometry, weights / bias / output slice at constant strides)
+  const int parts = p.parts > 1 ? p.parts : 1;
+  const int per_part = num_sms / parts > 0 ? num_sms / parts : 1;
+  cfg.gridDim = dim3(p.num_tiles < per_part ? p.num_tiles : per_part, parts);
   if (PAIR_T) cfg.gridDim.x &= ~1u;                       // whole pairs (the host only selects pair mode for an even tile count)
   cfg.blockDim = dim3(kConvThreads);
   cfg.dynamicSmemBytes = smem;
@@ -823,6 +827,7 @@ int launch_conv_tc(const ConvParams& p, const CUtensorMap& tmap, int num_sms, cu
   // the layer shapes of the generator forward (esrgan.py / srcnn.py) ...
   CSR_CASE(3, 1, 1, 0, 1)   // RDB conv1-4, HRconv: lrelu
   CSR_CASE(3, 1, 0, 0, 1)   // conv_first
+  CSR_CASE(3, 1, 4, 0, 1)   // discriminator convs: LeakyReLU(act_slope)
   CSR_CASE(3, 1, 0, 1, 1)   // RDB conv5 (*0.2 + x), trunk_conv (+ fea)
   CSR_CASE(3, 1, 0, 3, 1)   // RDB3 conv5 (*0.2 + x, *0.2 + x_rrdb)
 #ifdef CSR_EXPERIMENTS

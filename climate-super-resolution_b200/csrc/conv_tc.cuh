@@ -62,6 +62,11 @@ struct ConvParams {
   int win_slot_bytes;
   int l2_prefetch; // > 0: the producer prefetches the window of the tile `l2_prefetch` iterations ahead into L2 (layers that stream from HBM)
   int use_pdl;     // launch with programmatic stream serialization (prologue overlaps the previous kernel's tail)
+  // Output-channel parts of ONE layer as one launch (gridDim.y = parts): every part has this launch's geometry and reads the same input;
+  // part k takes its weights at wpk + k*part_w_bytes, its bias at bias + k*part_b_floats and writes output channels out_coff + k*part_c.
+  // Used for the wide single-op layers (discriminator: 128..512 output channels over small maps), where one part per launch leaves most
+  // SMs idle.  Residual / gate operands are not offset: only residual-free launches are merged.  0 / 1 = a single part.
+  int parts, part_w_bytes, part_b_floats, part_c;
   // epilogue:  v = act(acc + bias [+ r1 if r1_pre]);  if r1 (not r1_pre): v = v*s1 + r1;  if r2: v = v*s2 + r2;  if gate: v *= (gate > 0 ? 1 : gate_neg)
   const float* bias;   // [npad] fp32 (zero padded)
   const void* wpk;     // packed bf16 weights (global), layout [kblock][dy][kstep in kblock][KW*npad/8][2][8][8]

@@ -265,6 +265,7 @@ struct BiasSegs {
 __global__ void bias_grad_kernel(const __nv_bfloat16* __restrict__ g, long npix, int C, int coff, int cout, float scale, BiasSegs segs,
                                  int seg_ch) {
   extern __shared__ float red[];                           // [blockDim.x / cout_pad rows][cout_pad]
+  coff += blockIdx.y * cout;                               // gridDim.y > 1: consecutive `cout`-channel chunks of one wide layer (nseg == 1)
   const int cpad = (cout + 7) & ~7;
   const int lanes_per_pix = cpad >> 3;                     // one thread loads 8 channels (16 B)
   const int pix_per_iter = blockDim.x / lanes_per_pix;
@@ -304,7 +305,7 @@ __global__ void bias_grad_kernel(const __nv_bfloat16* __restrict__ g, long npix,
     float t = 0.f;
     for (int r = 0; r < pix_per_iter; ++r) t += red[(r * lanes_per_pix + s2) * 8 + k];
     const int sg = threadIdx.x / seg_ch;
-    atomicAdd(&segs.db[sg][threadIdx.x - sg * seg_ch], scale * t);
+    atomicAdd(&segs.db[sg][blockIdx.y * cout + threadIdx.x - sg * seg_ch], scale * t);
   }
 }
 
@@ -440,6 +441,14 @@ cudaError_t launch_bias_grad(const void* g, long npix, int C, int coff, int cout
   for (int i = 0; i < 4; ++i) segs.db[i] = db[i < nseg ? i : 0];
   bias_grad_kernel<<<148 * 4, 256, 256 * 8 * sizeof(float), s>>>(reinterpret_cast<const __nv_bfloat16*>(g), npix, C, coff, cout, scale, segs,
                                                                  cout / nseg);
+  return cudaGetLastError();
+}
+// cout = chunks * 128 channels of one layer in one launch
+cudaError_t launch_bias_grad_wide(const void* g, long npix, int C, int coff, int chunks, float scale, float* db, cudaStream_t s) {
+  BiasSegs segs;
+  for (int i = 0; i < 4; ++i) segs.db[i] = db;
+  const int gx = 148 * 4 / chunks > 16 ? 148 * 4 / chunks : 16;
+  bias_grad_kernel<<<dim3(gx, chunks), 256, 256 * 8 * sizeof(float), s>>>(reinterpret_cast<const __nv_bfloat16*>(g), npix, C, coff, 128, scale, segs, 128);
   return cudaGetLastError();
 }
 cudaError_t launch_bias_grad_planar(const float* g, long n, float scale, float* db, cudaStream_t s) {

@@ -175,6 +175,10 @@ int     csr_plan_backward_flat_seg(CsrPlan* plan, const void* packed_bwd, const 
  * scratch: >= csr_conv2d_scratch_bytes() device bytes for the packed weights.  weight == NULL: `scratch` still holds the
  * packed weights (and bias) of an earlier call for the same layer - callers cache it per weight version.              */
 size_t  csr_conv2d_scratch_bytes(const CsrConvDesc* d);
+/* Pack only: fills `scratch` for later csr_conv2d_nhwc(..., weight = NULL, ...) calls of the same layer shape.  The pack launch
+ * reads a job table through a pageable host copy, so it cannot be stream-captured; the conv launches themselves can: callers
+ * that replay the layer inside a CUDA graph (the discriminator) pack outside of it with this call.                      */
+int     csr_conv2d_pack(const CsrConvDesc* d, const float* weight, const float* bias, void* scratch, size_t scratch_bytes, void* stream);
 int     csr_conv2d_nhwc(const CsrConvDesc* d, const void* in, const float* weight, const float* bias,
                         void* out, const void* res1, const void* res2, const void* gate,
                         void* scratch, size_t scratch_bytes, void* stream);

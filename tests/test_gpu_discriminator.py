@@ -187,3 +187,47 @@ def test_gan_training_step_call_pattern():
     val = task.validation_step(batch)
     assert "val/psnr" in val and "val/loss_G" in val and "sr" not in val
     assert all(torch.isfinite(v).all() for v in val.values())
+
+
+def test_graph_replay_matches_the_eager_path_and_follows_weight_updates():
+    """From the third call of a kind on, forward and backward replay CUDA graphs over leased static buffers (two slots while D(hr)
+    and D(sr) of one GAN batch are both in flight).  Replays must reproduce the eager path - also after an optimizer step (weight
+    packs are refreshed outside the graphs) - and hand out gradients that later replays do not overwrite."""
+    d = _make(seed=5).cuda().train()
+    e = copy.deepcopy(d)
+    e.use_cuda_graphs = False
+    opt_d = torch.optim.AdamW(d.parameters(), lr=1e-3, fused=True)
+    g = torch.Generator().manual_seed(11)
+    kept = []
+    for it in range(5):
+        xa = (torch.rand((4, 1, 128, 128), generator=g) * 2 - 1).cuda()
+        xb = (torch.rand((4, 1, 128, 128), generator=g) * 2 - 1).cuda().requires_grad_(True)
+        xb2 = xb.detach().clone().requires_grad_(True)
+        w = torch.randn((4, 1), generator=g).cuda()
+        outs = []
+        # the eager twin starts every iteration from the graphed net's state: Adam turns last-bit differences of near-zero weight
+        # gradients (the weight-gradient GEMM accumulates with atomics) into +-lr steps, so two independently stepped nets drift
+        e.load_state_dict(d.state_dict())
+        for net, xin in ((d, xb), (e, xb2)):
+            net.zero_grad(set_to_none=True)
+            sa, sb = net(xa), net(xin)                      # two calls in flight before the backward, as in pl_gan.py:51-61
+            ((sa - sb.mean()) * w).sum().backward()
+            outs.append((sa.detach().clone(), sb.detach().clone(), xin.grad.detach().clone(), [p.grad for p in net.parameters()]))
+        opt_d.step()
+        (sa_d, sb_d, dx_d, gr_d), (sa_e, sb_e, dx_e, gr_e) = outs
+        assert torch.equal(sa_d, sa_e) and torch.equal(sb_d, sb_e), it
+        assert float((dx_d - dx_e).abs().max()) <= 1e-6 * max(1.0, float(dx_e.abs().max())), it
+        for (name, _), a, b in zip(d.named_parameters(), gr_d, gr_e):
+            assert float((a - b).abs().max()) <= 2e-5 * max(1e-3, float(b.abs().max())), (it, name)
+        kept.append((gr_d[0], gr_d[0].clone()))
+    slots = d.__dict__.get("_slots", {})
+    assert slots and max(len(v) for v in slots.values()) == 2       # graphs were used, two calls in flight
+    for held, copy_ in kept:                                          # gradients handed out earlier were not overwritten by later replays
+        assert torch.equal(held, copy_)
+    for (name, b), (_, c) in zip(d.named_buffers(), e.named_buffers()):
+        assert float((b.float() - c.float()).abs().max()) <= 1e-6 * max(1.0, float(c.float().abs().max())), name
+    e.load_state_dict(d.state_dict())
+    with torch.no_grad():                                             # inference calls replay their own (no-save) graphs
+        xs = (torch.rand((4, 1, 128, 128), generator=g) * 2 - 1).cuda()
+        for _ in range(4):
+            assert torch.equal(d(xs), e(xs))

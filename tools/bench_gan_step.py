@@ -87,11 +87,11 @@ def main():
         sr = G(x, elev, mask)
         if timed:
             ev[1].record()
+        for p_ in D.parameters():                             # Lightning's toggle_optimizer (called BEFORE training_step): only the
+            p_.requires_grad_(False)                          # generator's parameters require grad while optimizer 0 is active
         s_real, s_fake = d_scores(hr, sr)
         adv = (relativistic(s_fake, s_real, real) + relativistic(s_real, s_fake, fake)) / 2
         loss_g = 0.01 * losses.l1_loss(sr, hr) + 0.005 * adv
-        for p_ in D.parameters():                             # Lightning's toggle_optimizer: only the generator trains here
-            p_.requires_grad_(False)
         loss_g.backward()
         for p_ in D.parameters():
             p_.requires_grad_(True)
