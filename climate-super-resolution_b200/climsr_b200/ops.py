@@ -56,7 +56,9 @@ def conv2d_nhwc(inp: Tensor, weight: Tensor, bias: Optional[Tensor], *, act: str
             out = torch.empty((n, 1, s * h, s * w), dtype=torch.float32, device=inp.device)
         else:
             oc = (out_coff + cout + 63) // 64 * 64
-            out = torch.zeros((n, s * h, s * w, oc), dtype=torch.float32 if mode == 3 else torch.bfloat16, device=inp.device)
+            # every channel of every pixel is written when the layer fills the buffer exactly: no zero fill needed then
+            alloc = torch.empty if (out_coff == 0 and cout == oc) else torch.zeros
+            out = alloc((n, s * h, s * w, oc), dtype=torch.float32 if mode == 3 else torch.bfloat16, device=inp.device)
     out_c = 1 if mode == 2 else out.shape[-1]
     d = ConvDesc(n, h, w, cin, cout, kh, kw, in_c, in_coff, out_c, out_coff, ACT[act], mode, int(in_up2), int(transposed),
                  scale1, scale2, res1.shape[-1] if res1 is not None else 0, res1_coff,
