@@ -50,6 +50,8 @@ static int g_opt_reserve_sms = 0;       // plans created afterwards size their p
 static int g_opt_l2_prefetch = 0;       // conv layers that stream from HBM: prefetch windows this many tile iterations ahead into L2 (cp.async.bulk.prefetch.tensor).
                                         // Measured: no effect at depth 2/4/8 (HRconv 317-323 us either way) - the HR tail is not bound by HBM latency
 static int g_dbg_dense = 0;             // DenseParams::dbg (timing experiments)
+static int g_opt_dense_min = 2;         // ... only when a block has at least this many windows per SM: with <= 1 window per CTA nothing pipelines
+                                        // across layers and the counters only cost (cfg1 / one Europe raster / cfg3: 7-10 % slower, r02 A/B)
 static int g_opt_dense = 1;             // conv1..conv4 of every gc = 16 dense block as ONE persistent launch with tile-level dependencies (rdb_tc.cu)
 static int g_opt_early = 1;             // early-release epilogue (conv_tc.cu, EARLY_T): 1 = wide residual-free layers; 2 = also the residual layers (RDB conv5 with one
                                         // staging buffer and a third window slot, trunk_conv): measured slower in situ (42.0 / 55.5 vs 39.6 / 51.7 us per conv5)
@@ -947,7 +949,8 @@ static int plan_build(CsrPlan* P, void* ws) {
         DenseLaunch dl;
         const size_t per_block = (size_t)kDenseMaxLayers * N * ceil_div(h, 8) * ceil_div(w, 14);
         unsigned int* fl = P->flags + (size_t)j * per_block;
-        if (build_dense(packs, li, N, h, w, src, C, nf, gc, fl, &dl) == CSR_OK && (size_t)dl.p.num_tiles * kDenseMaxLayers <= per_block) {
+        if (build_dense(packs, li, N, h, w, src, C, nf, gc, fl, &dl) == CSR_OK && (size_t)dl.p.num_tiles * kDenseMaxLayers <= per_block &&
+            dl.p.num_tiles >= g_opt_dense_min * P->sms) {
           ConvLaunch stub;
           memset(&stub.p, 0, sizeof(stub.p));
           stub.dense = (int)P->dense.size();
@@ -1279,7 +1282,8 @@ static int bwd_build(CsrPlan* P, void* ws) {
         BwdOp op; op.kind = BwdOp::kDense;
         const size_t per_block = (size_t)kDenseMaxLayers * N * ceil_div(h, 8) * ceil_div(w, 14);
         unsigned int* fl = P->flags + (size_t)j * per_block;
-        if (build_dense(packs, bi, N, h, w, Gb, C, nf, gc, fl, &op.dense, cat(j), C) == CSR_OK && (size_t)op.dense.p.num_tiles * kDenseMaxLayers <= per_block) {
+        if (build_dense(packs, bi, N, h, w, Gb, C, nf, gc, fl, &op.dense, cat(j), C) == CSR_OK && (size_t)op.dense.p.num_tiles * kDenseMaxLayers <= per_block &&
+            op.dense.p.num_tiles >= g_opt_dense_min * P->sms) {
           ops.push_back(op);
           bi += 4;
           dense_done = true;
@@ -1413,6 +1417,7 @@ int csr_set_option(int32_t key, int32_t value) {
     case 20: case 21: case 22: case 23: case 24: g_dbg_wgrad[key - 20] = value; return CSR_OK;
     case 25: g_opt_wgrad_atomic = value ? 1 : 0; return CSR_OK;    // plans created afterwards
     case 27: g_opt_dense = value ? 1 : 0; return CSR_OK;           // plans created afterwards
+    case 31: if (value < 0 || value > 64) return fail(CSR_ERR_BAD_ARG, "option 31: windows per SM in [0, 64]"); g_opt_dense_min = value; return CSR_OK;
     case 28: g_dbg_dense = value; return CSR_OK;
     case 29: g_opt_l2_prefetch = value; return CSR_OK;
     case 30: g_opt_reserve_sms = value < 0 ? 0 : value; return CSR_OK;

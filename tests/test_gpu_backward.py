@@ -315,3 +315,31 @@ def test_atomic_and_deterministic_weight_gradient_accumulation_agree():
             assert torch.equal(grads[1][k], grads[2][k]), k                  # the slice + reduce path is run-to-run deterministic
         scale = float(grads[1][k].abs().max()) + 1e-12
         assert float((grads[0][k] - grads[1][k]).abs().max()) <= 2e-5 * scale, k
+
+
+def test_dense_block_backward_kernel_matches_per_layer_input_gradients():
+    """The four gated input-gradient convs of a dense block as ONE dataflow launch (rdb_tc.cu, backward form; option 27, used
+    when a block has at least option-31 windows per SM) against four per-layer launches: same tiles, MMA order and epilogue
+    arithmetic, so with the deterministic weight-gradient accumulation (option 25 = 0) every gradient is bit-identical."""
+    from climsr_b200._lib import lib
+    from oracle import synth
+    sd = synth.make_state_dict(4, 1, 64, 2, 16, seed=8, gain=1.3)
+    x, elev, mask = synth.make_inputs(3, 4, 36, 28, seed=9)
+    hr = torch.rand((3, 1, 144, 112), generator=torch.Generator().manual_seed(10)) * 2 - 1
+    res = []
+    try:
+        lib.csr_set_option(25, 0)
+        lib.csr_set_option(31, 0)
+        for dense in (1, 0):
+            lib.csr_set_option(27, dense)
+            res.append(_train_step(sd, x, elev, mask, hr, 4, 2, 16))
+    finally:
+        lib.csr_set_option(25, 1)
+        lib.csr_set_option(27, 1)
+        lib.csr_set_option(31, 2)
+    assert torch.equal(res[0][0], res[1][0])                       # sr
+    for k in res[0][2]:
+        if k.endswith(".weight"):
+            assert torch.equal(res[0][2][k], res[1][2][k]), k
+        else:
+            assert float((res[0][2][k] - res[1][2][k]).abs().max()) <= 2e-5 * (float(res[1][2][k].abs().max()) + 1e-12), k
