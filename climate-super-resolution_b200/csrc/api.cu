@@ -52,6 +52,7 @@ static int g_opt_l2_prefetch = 0;       // conv layers that stream from HBM: pre
 static int g_dbg_dense = 0;             // DenseParams::dbg (timing experiments)
 static int g_opt_dense_min = 2;         // ... only when a block has at least this many windows per SM: with <= 1 window per CTA nothing pipelines
                                         // across layers and the counters only cost (cfg1 / one Europe raster / cfg3: 7-10 % slower, r02 A/B)
+static int g_opt_dense9 = 0;            // dense blocks with all nine taps folded into N = 144 (rdb9_tc.cu) instead of N = 48 (rdb_tc.cu)
 static int g_opt_dense = 1;             // conv1..conv4 of every gc = 16 dense block as ONE persistent launch with tile-level dependencies (rdb_tc.cu)
 static int g_opt_early = 1;             // early-release epilogue (conv_tc.cu, EARLY_T): 1 = wide residual-free layers; 2 = also the residual layers (RDB conv5 with one
                                         // staging buffer and a third window slot, trunk_conv): measured slower in situ (42.0 / 55.5 vs 39.6 / 51.7 us per conv5)
@@ -868,6 +869,24 @@ static int build_dense(const std::vector<PackLayer>& packs, int li, int N, int H
     wmax = std::max(wmax, pl.parts[0].w_bytes);
   }
   p.wbuf_bytes = (int)align_up(wmax, 1024);
+#ifdef CSR_EXPERIMENTS
+  if (g_opt_dense9) {
+    // all nine taps folded into N = 144 (rdb9_tc.cu): windows of 16 x 16 input pixels, 14 x 14 outputs
+    p.fold9 = 1;
+    p.SW = 16; p.sw_shift = 4; p.TH = 8; p.TW = 14;
+    p.tiles_x = ceil_div(W, 14); p.tiles_y = ceil_div(H, 14);
+    p.tiles_per_img = p.tiles_x * p.tiles_y;
+    p.num_tiles = p.tiles_per_img * N;
+    if ((long long)p.tiles_per_img * N >= (1 << 24) || p.tiles_per_img >= (1 << 16)) return fail(CSR_ERR_UNSUPPORTED, "dense-block kernel: too many windows");
+    p.magic_img = ((1ull << 40) / (unsigned)p.tiles_per_img) + 1;
+    p.magic_row = ((1ull << 40) / (unsigned)p.tiles_x) + 1;
+    p.win_bytes = 16 * 16 * 128; p.slot_bytes = p.win_bytes;
+    p.n_slots = 8;
+    while (p.n_slots > 2 && dense9_smem_bytes(p) > (size_t)kSmemLimit) --p.n_slots;
+    if (dense9_smem_bytes(p) > (size_t)kSmemLimit || p.n_slots < 3) return fail(CSR_ERR_UNSUPPORTED, "dense-block kernel (N=144): window ring too shallow");
+    return encode_act_map(&dl->tmap, buf, N, H, W, C, 16, 16, 64);
+  }
+#endif
   Tiling tl;
   int rc = choose_tiling(H, W, 3, 3, 2 * p.wbuf_bytes, 2, 32, 4, &tl, 128, 2);
   if (rc) return rc;
@@ -1392,7 +1411,7 @@ int csr_set_option(int32_t key, int32_t value) {
   // the table with defaults and meanings is in INTEGRATION.md section 6
 #ifndef CSR_EXPERIMENTS
   // measured-and-rejected kernel variants are not part of the default build (conv_tc.cu launch_conv_tc)
-  if ((key == 13 && value != 0) || (key == 16 && value != 0) || (key == 8 && value == 0))
+  if ((key == 13 && value != 0) || (key == 16 && value != 0) || (key == 8 && value == 0) || (key == 32 && value != 0))
     return fail(CSR_ERR_UNSUPPORTED, "option %d=%d selects an experimental kernel variant: rebuild with CSR_EXPERIMENTS=1 python build.py --force", key, value);
 #endif
   switch (key) {
@@ -1417,6 +1436,7 @@ int csr_set_option(int32_t key, int32_t value) {
     case 20: case 21: case 22: case 23: case 24: g_dbg_wgrad[key - 20] = value; return CSR_OK;
     case 25: g_opt_wgrad_atomic = value ? 1 : 0; return CSR_OK;    // plans created afterwards
     case 27: g_opt_dense = value ? 1 : 0; return CSR_OK;           // plans created afterwards
+    case 32: g_opt_dense9 = value ? 1 : 0; return CSR_OK;          // plans created afterwards
     case 31: if (value < 0 || value > 64) return fail(CSR_ERR_BAD_ARG, "option 31: windows per SM in [0, 64]"); g_opt_dense_min = value; return CSR_OK;
     case 28: g_dbg_dense = value; return CSR_OK;
     case 29: g_opt_l2_prefetch = value; return CSR_OK;

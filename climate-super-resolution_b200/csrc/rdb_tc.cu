@@ -415,6 +415,11 @@ size_t dense_smem_bytes(const DenseParams& p) {
 }
 
 int launch_dense_block(const DenseParams& p, const CUtensorMap& tmap, int num_sms, cudaStream_t stream) {
+#ifdef CSR_EXPERIMENTS
+  if (p.fold9) return launch_dense9_block(p, tmap, num_sms, stream);
+#else
+  if (p.fold9) return static_cast<int>(cudaErrorInvalidValue);
+#endif
   const size_t smem = dense_smem_bytes(p);
   if (smem > static_cast<size_t>(kSmemLimit) || p.n_layers < 1 || p.n_layers > kDenseMaxLayers || p.n_slots < 2)
     return static_cast<int>(cudaErrorInvalidValue);

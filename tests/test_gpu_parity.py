@@ -629,6 +629,43 @@ def test_dense_block_kernel_is_bit_identical_to_per_layer_launches(n, in_ch, h, 
     assert torch.equal(outs[0], outs[2])
 
 
+@pytest.mark.parametrize("n,in_ch,h,w,nb", [(4, 4, 64, 64, 3), (1, 3, 113, 113, 2), (3, 4, 20, 36, 2), (1, 1, 9, 7, 1), (16, 4, 32, 32, 2), (150, 4, 16, 16, 1),
+                                            (2, 4, 28, 14, 1), (1, 4, 29, 15, 1)])
+def test_dense_block_nine_tap_fold_matches_per_layer_launches(n, in_ch, h, w, nb):
+    """(Experiments build only - measured slower, see rdb9_tc.cu.)  Option 32: conv1..conv4 of every dense block with ALL NINE taps folded into the UMMA N dimension (rdb9_tc.cu: N = 144, 16 x 16
+    windows, the row-shifted accumulator rows summed in the epilogue) against four per-layer launches.  Same products, another fp32
+    summation order -> equal up to bf16 rounding flips of single activations: a small fraction of the output scale.  Shapes as in the
+    bit-identity test plus rasters that end exactly on / one past a 14-pixel window edge."""
+    _need_experiments()
+    from climsr_b200._lib import lib
+    from climsr_b200.models import ESRGANGenerator
+    from oracle import synth
+    sd = synth.make_state_dict(in_ch, 1, 64, nb, 16, seed=6, gain=1.4)
+    x, elev, mask = synth.make_inputs(n, in_ch, h, w, seed=7)
+    outs = []
+    try:
+        lib.csr_set_option(31, 0)
+        for fold9, dense in ((1, 1), (0, 0), (1, 1)):
+            lib.csr_set_option(32, fold9)
+            lib.csr_set_option(27, dense)
+            net = ESRGANGenerator(in_ch, 1, 64, nb, 16)
+            net.load_state_dict(sd)
+            net = net.cuda().eval()
+            with torch.no_grad():
+                a = net(x.cuda(), elev.cuda(), mask.cuda())
+                b = net(x.cuda(), elev.cuda(), mask.cuda())          # second call: CUDA-graph replay where the plan uses one
+            assert torch.equal(a, b)
+            outs.append(a.cpu())
+            del net
+    finally:
+        lib.csr_set_option(27, 1)
+        lib.csr_set_option(31, 2)
+        lib.csr_set_option(32, 0)
+    assert torch.equal(outs[0], outs[2])                              # run-to-run deterministic
+    scale = float(outs[1].abs().max())
+    assert float((outs[0] - outs[1]).abs().max()) <= 4e-3 * max(scale, 1.0), (float((outs[0] - outs[1]).abs().max()), scale)
+
+
 def test_dense_block_regrouping_matches_plain_forward(golden_dir):
     """Option 16: dense blocks regrouped by source (conv1 + x-parts of conv2-4 in one wide launch, partial sums through the
     bf16 concat slots) against the plain layer-by-layer forward and the reference golden output."""

@@ -196,7 +196,95 @@ void run_mma(const char* name) {
   cudaFree(d);
 }
 
+// 4. does epilogue traffic slow the MMAs down?  Warp 16 issues N = NMMA MMAs back to back while `nwarps` other warps loop over
+//    FG = 0 nothing, 1 warp shuffles, 2 16-byte shared-memory stores + loads (conflict-free), 3 FFMA only.
+template <int NMMA, int FG>
+__global__ void __launch_bounds__(544, 1) contend(int nwarps, int iters, long long* out, unsigned* sink) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tslot;
+  for (int i = threadIdx.x; i < 96 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem_raw)[i] = 0;
+  if (threadIdx.x == 0) { mbar_init(smem_u32(&bar), 1); fence_mbar_init(); fence_proxy_async_smem(); }
+  if (threadIdx.x < 32) { tmem_alloc(smem_u32(&tslot), 512); tmem_relinquish(); }
+  tc_fence_before(); __syncthreads(); tc_fence_after();
+  const uint32_t tmem = tslot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  long long t0 = 0, t1 = 0;
+  if (warp == 16) {
+    const uint32_t idesc = make_idesc_bf16(128, NMMA);
+    const uint32_t a_hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+    const uint32_t b_hi = (256u >> 4) | (1u << 14);
+    const uint32_t a_lo0 = (base >> 4) | (1u << 16);
+    const uint32_t b_lo0 = ((base + 48 * 1024) >> 4) | (8u << 16);
+    uint32_t phase = 0;
+    t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+      if (elect_one()) {
+#pragma unroll
+        for (int i = 0; i < 12; ++i) umma_bf16_split(tmem + (i & 1) * 256, a_lo0 + (i % 3) * 16 * 8 + (i & 3) * 2, a_hi, b_lo0 + i * ((NMMA * 32) >> 4), b_hi, idesc, 1);
+        umma_commit(smem_u32(&bar));
+      }
+      __syncwarp();
+      mbar_wait(smem_u32(&bar), phase); phase ^= 1;
+    }
+    t1 = clock64();
+    if (lane == 0) out[blockIdx.x] = (t1 - t0) / (12LL * iters);
+  } else if (warp < nwarps) {
+    // ~ the same wall time as the MMA loop: iters * 12 * ~80 clk
+    const uint32_t my = base + 64 * 1024 + threadIdx.x * 16;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = threadIdx.x * 0.5f + j;
+    for (int it = 0; it < iters * 6; ++it) {
+      if (FG == 1) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] += __shfl_sync(0xffffffffu, v[(j + 1) & 7], (lane + 1) & 31);
+      } else if (FG == 2) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          st_shared_v4(my, __float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3]));
+          const uint4 q = ld_shared_v4(my ^ 16u);
+          v[0] += __uint_as_float(q.x); v[1] += __uint_as_float(q.y); v[2] += __uint_as_float(q.z); v[3] += __uint_as_float(q.w);
+        }
+      } else if (FG == 3) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], 1.0001f, v[(j + 1) & 7]);
+      }
+    }
+    if (sink && v[0] + v[1] + v[2] + v[3] == 12345.f) sink[0] = 1;
+  }
+  tc_fence_before(); __syncthreads();
+  if (threadIdx.x < 32) { tc_fence_after(); tmem_dealloc(tmem, 512); }
+}
+
+template <int NMMA, int FG>
+void run_contend(const char* name) {
+  long long* d; cudaMalloc(&d, 148 * 8);
+  cudaFuncSetAttribute(contend<NMMA, FG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  for (int nw : {0, 4, 8, 16}) {
+    contend<NMMA, FG><<<148, 544, 200 * 1024>>>(nw, 200, d, nullptr);
+    cudaError_t e = cudaDeviceSynchronize();
+    long long h[148]; cudaMemcpy(h, d, 148 * 8, cudaMemcpyDeviceToHost);
+    long long mx = 0; for (int i = 0; i < 148; ++i) mx = h[i] > mx ? h[i] : mx;
+    printf("N=%3d MMAs while %2d warps run %-28s %5lld clk per MMA  %s\n", NMMA, nw, name, mx, e == cudaSuccess ? "" : cudaGetErrorString(e));
+    if (FG == 0) break;
+  }
+  cudaFree(d);
+}
+
 int main() {
+  run_contend<144, 0>("nothing");
+  run_contend<144, 1>("32 shuffles per iteration");
+  run_contend<144, 2>("4 x (STS.128 + LDS.128)");
+  run_contend<144, 3>("32 FFMA per iteration");
+  run_contend<48, 0>("nothing");
+  run_contend<48, 1>("32 shuffles per iteration");
+  run_contend<48, 2>("4 x (STS.128 + LDS.128)");
   run_mma<0>("3 taps folded: N=192");
   run_mma<1>("2 folded + 1 shifted: N=128 + N=64");
   run_mma<2>("unfolded: 3 x N=64, A shifted by 0/1/2 px");
