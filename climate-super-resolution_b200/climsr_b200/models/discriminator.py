@@ -249,7 +249,7 @@ class Discriminator(nn.Module):
                 slot.x.copy_(x.detach())
                 torch.cuda.current_stream().synchronize()
                 slot.fwd = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(slot.fwd):
+                with torch.cuda.graph(slot.fwd, capture_error_mode="thread_local"):
                     slot.out, slot.saved = self._run_forward(slot.x, save)
                 slots.append(slot)
             else:
@@ -282,7 +282,7 @@ class Discriminator(nn.Module):
                 gys.copy_(gy.detach())
                 torch.cuda.current_stream().synchronize()
                 graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(graph):
+                with torch.cuda.graph(graph, capture_error_mode="thread_local"):
                     dx, grads, flat = self._run_backward(saved, gys, need_dx, need_params, return_flat=True)
                 ent = slot.bwd[variant] = (graph, gys, dx, flat, grads)
             else:
