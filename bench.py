@@ -86,7 +86,7 @@ def init_distributed(local):
     import torch
     import torch.distributed as dist
     from climsr_b200.parallel import configure_nccl_for_overlap
-    configure_nccl_for_overlap()          # NCCL_MAX_CTAS = the SMs the training plans leave to the collective
+    configure_nccl_for_overlap(int(os.environ.get("CSR_DDP_RESERVE_SMS", "4")))   # NCCL_MAX_CTAS = the SMs the training plans leave to the collective
     with _stdout_to_stderr():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         dist.barrier()
@@ -347,7 +347,8 @@ def train_measure(workload, steps, warmup, dev, world, rank, overlap=True, e2e=T
     net = ESRGANGenerator(in_ch, 1, 64, nb, gc).to(dev).train()
     opt = torch.optim.AdamW(net.parameters(), lr=1e-4, weight_decay=1e-4, fused=True)
     bucketer = GradientBucketer(net.parameters(), bucket_mb=4.0, comm_dtype=torch.bfloat16)
-    sync = attach_ddp(net, nseg=4, comm_dtype=torch.bfloat16) if (world > 1 and overlap) else None
+    sync = attach_ddp(net, nseg=int(os.environ.get("CSR_DDP_NSEG", "2")), comm_dtype=torch.bfloat16,
+                      reserve_sms=int(os.environ.get("CSR_DDP_RESERVE_SMS", "4"))) if (world > 1 and overlap) else None
     g = torch.Generator().manual_seed(1 + rank)
     x = torch.rand((tiles, in_ch, h, w), generator=g) * 2 - 1
     mask = (torch.rand((tiles, 1, H, W), generator=g) > 0.3).float()
@@ -446,7 +447,7 @@ def train_measure(workload, steps, warmup, dev, world, rank, overlap=True, e2e=T
     out["frac"] = achieved / peaks["bf16_burst"]
     out["frac_sustained"] = achieved / peaks["bf16_sustained"]
     out["exchange"] = ("none (1 GPU)" if world == 1 else
-                       "bf16 gradient all-reduce in 4 slices overlapped with the segmented backward (attach_ddp: 4 SMs reserved, NCCL_MAX_CTAS=4)"
+                       "bf16 gradient all-reduce in 2 slices overlapped with the segmented backward (attach_ddp: 4 SMs reserved, NCCL_MAX_CTAS=4)"
                        if sync is not None else f"{len(bucketer.buckets)} bf16 buckets all-reduced after backward")
     del net, opt
     torch.cuda.empty_cache()

@@ -5,7 +5,8 @@ The reference trains through Lightning's DDP plugin (conf/trainer/benchmark.yaml
 all-reduce per optimizer, started from backward hooks so that it overlaps the rest of the backward.  Here the whole
 generator backward is ONE autograd node; the equivalent is ``BackwardGradSync`` (installed by ``attach_ddp``):
 
-* the node runs its backward in ``nseg`` segments (csr_plan_backward_flat_seg).  Layers finish in reverse order, so after
+* the node runs its backward in ``nseg`` segments (csr_plan_backward_flat_seg; default 2: at the cfg3 step two slices hide the
+  exchange completely, four cost 0.2 ms more in launches - 6.91 vs 7.11 ms on 8 GPUs).  Layers finish in reverse order, so after
   each segment a growing suffix of the plan's flat fp32 gradient buffer is final;
 * that slice goes straight from the flat buffer into one persistent bf16 exchange buffer (csr_grad_pack_bf16, pre-scaled by
   1 / world so the sum over ranks stays in range; no torch.cat / cast / per-parameter copies), is all-reduced on a side
@@ -133,7 +134,7 @@ class BackwardGradSync:
     already averaged over the process group, so nothing is left to do after ``loss.backward()``.
     """
 
-    def __init__(self, nseg: int = 4, comm_dtype: Optional[torch.dtype] = torch.bfloat16, process_group=None):
+    def __init__(self, nseg: int = 2, comm_dtype: Optional[torch.dtype] = torch.bfloat16, process_group=None):
         if comm_dtype not in (None, torch.bfloat16, torch.float32):
             raise ValueError("comm_dtype must be torch.bfloat16 (wire format of SURVEY 8e) or None / torch.float32 (exact fp32 sum)")
         self.nseg = max(1, int(nseg))
@@ -208,7 +209,7 @@ class BackwardGradSync:
         flat.record_stream(comm)
 
 
-def attach_ddp(generator, nseg: int = 4, comm_dtype: Optional[torch.dtype] = torch.bfloat16, process_group=None,
+def attach_ddp(generator, nseg: int = 2, comm_dtype: Optional[torch.dtype] = torch.bfloat16, process_group=None,
                reserve_sms: int = DEFAULT_RESERVE_SMS) -> Optional[BackwardGradSync]:
     """Data-parallel training of ``generator`` (a climsr_b200 ESRGANGenerator): install the overlapped gradient all-reduce and
     make the training plans created from now on leave ``reserve_sms`` SMs to the collective.  Returns the sync object, or
