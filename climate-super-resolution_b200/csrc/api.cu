@@ -52,7 +52,8 @@ static int g_opt_l2_prefetch = 0;       // conv layers that stream from HBM: pre
 static int g_dbg_dense = 0;             // DenseParams::dbg (timing experiments)
 static int g_opt_dense_min = 2;         // ... only when a block has at least this many windows per SM: with <= 1 window per CTA nothing pipelines
                                         // across layers and the counters only cost (cfg1 / one Europe raster / cfg3: 7-10 % slower, r02 A/B)
-static int g_opt_dense9 = 0;            // dense blocks with all nine taps folded into N = 144 (rdb9_tc.cu) instead of N = 48 (rdb_tc.cu)
+static int g_opt_fuse_tail = 1;         // inference: srcnn.conv2 inside srcnn.conv1's epilogue (second MMA over the staged tile)
+[[maybe_unused]] static int g_opt_dense9 = 0;            // dense blocks with all nine taps folded into N = 144 (rdb9_tc.cu) instead of N = 48 (rdb_tc.cu)
 static int g_opt_dense = 1;             // conv1..conv4 of every gc = 16 dense block as ONE persistent launch with tile-level dependencies (rdb_tc.cu)
 static int g_opt_early = 1;             // early-release epilogue (conv_tc.cu, EARLY_T): 1 = wide residual-free layers; 2 = also the residual layers (RDB conv5 with one
                                         // staging buffer and a third window slot, trunk_conv): measured slower in situ (42.0 / 55.5 vs 39.6 / 51.7 us per conv5)
@@ -328,6 +329,7 @@ struct ConvLaunch {
   ConvParams p;
   CUtensorMap tmap;
   size_t w_off = 0, b_off = 0;  // offsets into the packed blob (resolved at forward time)
+  size_t w2_off = 0, b2_off = 0;  // fused 1x1 successor (ConvParams::fuse2)
   bool final_out = false;       // fp32-planar output that IS the caller's `out` tensor
   int dense = -1;               // >= 0: this entry stands for a whole dense-block launch (CsrPlan::dense[dense]), not a conv
 };
@@ -1030,8 +1032,31 @@ static int plan_build(CsrPlan* P, void* ws) {
   const int sp = P->srcnn_pitch;
   rc = add(H, W, io_of(hrC, sp, hrD, 64, 0, CSR_ACT_RELU));     // srcnn.conv1 (9x1 folded)
   if (rc) return rc;
-  rc = add(H, W, io_of(hrD, 64, hrE, sp, 0, CSR_ACT_RELU));     // srcnn.conv2 1x1
-  if (rc) return rc;
+  {
+    // Inference: srcnn.conv2 (1x1, 64 -> 32, ReLU) runs inside srcnn.conv1's epilogue as a second MMA over the staged tile; the
+    // 64-channel HR map is never written (conv_tc.cu FUSE_T).  Training plans keep both layers (the backward needs the intermediate).
+    ConvLaunch& c1 = P->convs.back();
+    const PackLayer& p2 = packs[li];
+    bool fused = false;
+    if (g_opt_fuse_tail && !P->train && c1.p.early && c1.p.KW == 1 && c1.p.PW == 0 && c1.p.npad == 64 && c1.p.stage_row_bytes == 128 &&
+        p2.parts.size() == 1 && p2.parts[0].npad == 32 && p2.parts[0].w_bytes == 4096 && p2.cin_pad == 64 && sp % 8 == 0) {
+      ConvParams q = c1.p;
+      q.fuse2 = 1; q.w2_bytes = p2.parts[0].w_bytes; q.n2 = 32; q.out2 = hrE; q.out2_C = sp; q.out2_coff = 0;
+      int cols = 32;
+      while (cols < q.n_acc * q.KW * q.npad + 32) cols *= 2;
+      q.tmem_cols = cols;
+      if (cols <= 512 && conv_smem_bytes(q) <= (size_t)kSmemLimit) {
+        c1.p = q;
+        c1.w2_off = p2.parts[0].w_off; c1.b2_off = p2.parts[0].b_off;
+        ++li;                                                    // srcnn.conv2 has no launch of its own
+        fused = true;
+      }
+    }
+    if (!fused) {
+      rc = add(H, W, io_of(hrD, 64, hrE, sp, 0, CSR_ACT_RELU));   // srcnn.conv2 1x1
+      if (rc) return rc;
+    }
+  }
   {
     ConvIO io = io_of(hrE, sp, nullptr, 1, 0, CSR_ACT_NONE);    // srcnn.conv3 5x5 -> the caller's output tensor
     io.out_kind = kOutF32Planar;
@@ -1436,6 +1461,7 @@ int csr_set_option(int32_t key, int32_t value) {
     case 20: case 21: case 22: case 23: case 24: g_dbg_wgrad[key - 20] = value; return CSR_OK;
     case 25: g_opt_wgrad_atomic = value ? 1 : 0; return CSR_OK;    // plans created afterwards
     case 27: g_opt_dense = value ? 1 : 0; return CSR_OK;           // plans created afterwards
+    case 33: g_opt_fuse_tail = value ? 1 : 0; return CSR_OK;       // plans created afterwards
     case 32: g_opt_dense9 = value ? 1 : 0; return CSR_OK;          // plans created afterwards
     case 31: if (value < 0 || value > 64) return fail(CSR_ERR_BAD_ARG, "option 31: windows per SM in [0, 64]"); g_opt_dense_min = value; return CSR_OK;
     case 28: g_dbg_dense = value; return CSR_OK;
@@ -1950,6 +1976,7 @@ static int forward_launches(CsrPlan* P, const void* packed, const float* x, cons
     }
     cl.p.wpk = pk + cl.w_off;
     cl.p.bias = reinterpret_cast<const float*>(pk + cl.b_off);
+    if (cl.p.fuse2) { cl.p.w2 = pk + cl.w2_off; cl.p.b2 = reinterpret_cast<const float*>(pk + cl.b2_off); }
     if (cl.final_out) cl.p.out = out;
     cl.p.timeline = ((int)i < g_timeline_cap) ? g_timeline : nullptr; cl.p.launch_id = (int)i;
     int e = launch_conv_tc(cl.p, cl.tmap, P->sms, s);

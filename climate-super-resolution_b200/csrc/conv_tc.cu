@@ -140,6 +140,10 @@ __device__ __forceinline__ uint4 ldg16(const void* base, size_t pix, int C, int 
 //          M = 256 MMA for both, and each CTA keeps only HALF of the layer's weights resident (B rows [0,N/2) / [N/2,N)),
 //          which is what buys RDB conv5 (144 KB of weights) a window ring deep enough to prefetch across tiles.
 //   TALL_T 1 = two M tiles per window (ConvParams::tall_shift), compile-time so that the common kernels carry none of it
+//   FUSE_T 1 = (early-release epilogue only) the layer's 64-channel output never leaves the SM: the staged bf16 tile - already a K-major,
+//             128B-swizzled UMMA A operand - goes through a SECOND MMA with the weights of the following 1x1 conv (srcnn.conv2 after
+//             srcnn.conv1: 64 -> 32, srcnn.py:15-16), whose bias + ReLU output is what gets stored.  Saves the 64-channel HR map's
+//             write and re-read (2 x 537 MB at cfg2) and one launch.  Inference plans only (training saves the intermediate).
 //   EARLY_T 1 = wide residual-free layers (64 output channels, one 16-warp epilogue group): every warp pulls its WHOLE share of
 //          the accumulator (2 chunks x KW taps) into registers, hands the TMEM buffer back to the MMA warps at once and only
 //          then does the shuffle-sum / activation / staging; two staging buffers, so a tile costs one named barrier and the
@@ -147,7 +151,7 @@ __device__ __forceinline__ uint4 ldg16(const void* base, size_t pix, int C, int 
 //          ~2450 clk per 128 x 64 tile against ~1400 clk of MMAs, because an accumulator stayed busy for the whole
 //          ~1000-clk arithmetic phase and only two of them fit TMEM; tools/tmem_probe.cu shows the TMEM read port itself
 //          delivers a 128 x 192 fp32 tile to 16 warps in ~260 clk.)
-template <int KW_T, int PW_T, int ACT_T, int RES_T, int ST_T, int PAIR_T = 0, int TALL_T = 0, int EARLY_T = 0>
+template <int KW_T, int PW_T, int ACT_T, int RES_T, int ST_T, int PAIR_T = 0, int TALL_T = 0, int EARLY_T = 0, int FUSE_T = 0>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
   extern __shared__ uint8_t smem_raw[];
@@ -158,7 +162,10 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
   const uint32_t w_addr = stage_addr + static_cast<uint32_t>(p.n_stage) * p.stage_bytes;
   const uint32_t crank = PAIR_T ? cluster_ctarank() : 0u;   // rank in the CTA pair; rank 0 (leader) issues the MMAs
   const int w_local = p.stream_w ? 0 : (PAIR_T ? (p.w_bytes >> 1) : p.w_bytes);  // resident weight bytes of this CTA
-  const uint32_t bias_addr = w_addr + ((w_local + 127) & ~127);
+  // fused 1x1 successor (FUSE_T): its packed weights and bias sit right behind the layer's own weights
+  const uint32_t w2_addr = w_addr + ((w_local + 127) & ~127);
+  const uint32_t b2_addr = w2_addr + (FUSE_T ? static_cast<uint32_t>(p.w2_bytes) : 0u);
+  const uint32_t bias_addr = b2_addr + (FUSE_T ? 128u : 0u);
   const uint32_t bar_addr = bias_addr + 256;            // up to 64 fp32 biases
   // barriers: [0] weights, [1..S] a_full, [1+S..2S] a_empty, then acc_full[8], acc_empty[8], token[2]
   const int S = p.n_slots;
@@ -171,7 +178,8 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
   auto bar_acc_full = [&](int b) { return bar_addr + 8u * (1 + 2 * S + b); };
   auto bar_acc_empty = [&](int b) { return bar_addr + 8u * (9 + 2 * S + b); };
   auto bar_token = [&](int w) { return bar_addr + 8u * (17 + 2 * S + w); };  // "MMA warp w has issued its tile" (issue_order)
-  const uint32_t tmem_slot_addr = bar_addr + 8u * (19 + 2 * S);      // [0] TMEM base, [1..2] issuer progress words
+  const uint32_t bar_d2 = bar_addr + 8u * (19 + 2 * S);              // FUSE_T: the second MMA of a tile has completed
+  const uint32_t tmem_slot_addr = bar_addr + 8u * (20 + 2 * S);      // [0] TMEM base, [1..2] issuer progress words
   // CTA pair: the barriers the LEADER waits on (weights, a_full, acc_empty) live in the leader's shared memory; the peer
   // reaches them through the cluster window at the same offsets.
   const uint32_t lead_off = PAIR_T ? (map_to_cta(bar_addr, 0) - bar_addr) : 0u;
@@ -192,6 +200,7 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
     progress[1] = 0;
     mbar_init(bar_token(0), 1);
     mbar_init(bar_token(1), 1);
+    mbar_init(bar_d2, 1);
     tma_prefetch_desc(&tmap);
     mbar_init(bar_w, (PAIR_T && crank == 0) ? 2 : 1);     // pair leader: + the peer's "my half has landed" arrival
     for (int s = 0; s < S; ++s) {
@@ -216,11 +225,12 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
       for (int off = 0, loc = 0; off < p.w_bytes; off += full, loc += half)
         bulk_load(w_addr + loc, wsrc + off + crank * half, half, bar_w);
     } else {
-      mbar_arrive_expect_tx(bar_w, p.w_bytes);
+      mbar_arrive_expect_tx(bar_w, p.w_bytes + (FUSE_T ? p.w2_bytes : 0));
       for (int off = 0; off < p.w_bytes; off += 32768) {
         const int nbytes = min(32768, p.w_bytes - off);
         bulk_load(w_addr + off, wsrc + off, nbytes, bar_w);
       }
+      if constexpr (FUSE_T) bulk_load(w2_addr, p.w2, p.w2_bytes, bar_w);
     }
   }
   if (warp == 1) {
@@ -233,6 +243,10 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
     }
   }
   for (int i = threadIdx.x; i < p.npad; i += blockDim.x) bias_s[i] = p.bias[blockIdx.y * p.part_b_floats + i];
+  if constexpr (FUSE_T) {
+    float* bias2_s = reinterpret_cast<float*>(smem_gen + (b2_addr - smem_base));
+    for (int i = threadIdx.x; i < 32; i += blockDim.x) bias2_s[i] = i < p.n2 ? p.b2[i] : 0.f;
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -530,8 +544,43 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
                          pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
         }
         if (tracer) CSR_TRACE(2, it, 4);
+        if constexpr (FUSE_T) fence_proxy_async_smem();   // this thread's staged bf16 values -> visible to the tensor core's (async proxy) reads
         named_bar_sync(1, gthreads);                      // the staged tile is complete (and every copy-out of tile it-1 has been issued)
         if (tracer) CSR_TRACE(2, it, 7);
+        if constexpr (FUSE_T) {
+          // second MMA: D2[128 x 32] = staged tile [128 x 64, K-major, 128B swizzle] x W2^T, four k-steps, issued by one epilogue thread
+          const uint32_t d2_tmem = tmem_base + static_cast<uint32_t>(NA * nmma);
+          if (warp == 1 + kMmaWarps) {
+            if (it == 0) mbar_wait_spin(bar_w, 0);        // W2 arrived with the layer's own weights
+            tc_fence_after();
+            if (elect_one()) {
+              const uint32_t a16 = ((stage_addr + sb * p.stage_bytes) >> 4) | ((16u >> 4) << 16);
+              const uint32_t a_hi2 = (1024u >> 4) | (1u << 14) | (2u << 29);
+              const uint32_t b16 = (w2_addr >> 4) | ((128u >> 4) << 16);
+              const uint32_t b_hi2 = (256u >> 4) | (1u << 14);
+              const uint32_t idesc2 = make_idesc_bf16(kTileM, 32);
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) umma_bf16_split(d2_tmem, a16 + ks * 2, a_hi2, b16 + ks * ((32 * 32) >> 4), b_hi2, idesc2, ks ? 1u : 0u);
+              umma_commit(bar_d2);
+            }
+            __syncwarp();
+          }
+          mbar_wait_spin(bar_d2, static_cast<uint32_t>(it) & 1u);
+          tc_fence_after();
+          uint32_t r2[8];
+          tmem_ld8(t_lane + static_cast<uint32_t>(NA * nmma) + sub * 8, r2);
+          tmem_ld_wait();
+          tc_fence_before();
+          const int y = tl.y0 + ty, x = tl.x0 - PW_T + tx;
+          if (col_ok && y < p.H && x < p.W && sub * 8 < p.n2) {
+            const float* bias2_s = reinterpret_cast<const float*>(smem_gen + (b2_addr - smem_base)) + sub * 8;
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = fmaxf(__uint_as_float(r2[j]) + bias2_s[j], 0.f);          // bias + ReLU (srcnn.py:16)
+            __nv_bfloat16* o2 = reinterpret_cast<__nv_bfloat16*>(p.out2) + ((static_cast<size_t>(tl.n) * p.H + y) * p.W + x) * p.out2_C + p.out2_coff + sub * 8;
+            *reinterpret_cast<uint4*>(o2) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+          }
+        } else {
         __nv_bfloat16* tile_out = reinterpret_cast<__nv_bfloat16*>(p.out) +
             ((static_cast<size_t>(tl.n) * p.out_H + (tl.y0 * p.out_sy + p.out_oy)) * p.out_W + (tl.x0 * p.out_sx + p.out_ox)) * p.out_C +
             p.out_coff + static_cast<int>(blockIdx.y) * p.part_c;
@@ -543,6 +592,7 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
             const uint4 val = ld_shared_v4(pc_s[k] + sb * p.stage_bytes);
             *reinterpret_cast<uint4*>(tile_out + pc_d[k]) = val;
           }
+        }
         }
         if (tracer) CSR_TRACE(2, it, 2);
         if (two_stage) sb ^= 1u;
@@ -714,16 +764,17 @@ done:
 
 size_t conv_smem_bytes(const ConvParams& p) {
   return 1024 /*alignment slack*/ + static_cast<size_t>(p.n_slots) * p.slot_bytes + static_cast<size_t>(p.n_stage) * p.stage_bytes +
-         (((p.stream_w ? 0 : p.pair ? p.w_bytes / 2 : p.w_bytes) + 127) & ~127) + 256 /*bias*/ + 8 * (19 + 2 * p.n_slots) + 32;
+         (((p.stream_w ? 0 : p.pair ? p.w_bytes / 2 : p.w_bytes) + 127) & ~127) + (p.fuse2 ? p.w2_bytes + 128 : 0) + 256 /*bias*/ +
+         8 * (20 + 2 * p.n_slots) + 32;
 }
 
-template <int KW_T, int PW_T, int ACT_T, int RES_T, int ST_T, int PAIR_T = 0, int TALL_T = 0, int EARLY_T = 0>
+template <int KW_T, int PW_T, int ACT_T, int RES_T, int ST_T, int PAIR_T = 0, int TALL_T = 0, int EARLY_T = 0, int FUSE_T = 0>
 static int launch_t(const ConvParams& p, const CUtensorMap& tmap, int num_sms, cudaStream_t stream) {
   const size_t smem = conv_smem_bytes(p);
   if (smem > static_cast<size_t>(kSmemLimit)) return static_cast<int>(cudaErrorInvalidValue);
   // the attribute is per device (and per template instantiation): one process may drive several GPUs
   static bool configured[64] = {};
-  auto kern = conv_tc_kernel<KW_T, PW_T, ACT_T, RES_T, ST_T, PAIR_T, TALL_T, EARLY_T>;
+  auto kern = conv_tc_kernel<KW_T, PW_T, ACT_T, RES_T, ST_T, PAIR_T, TALL_T, EARLY_T, FUSE_T>;
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return static_cast<int>(cudaErrorInvalidDevice);
   if (!configured[dev]) {
@@ -805,6 +856,13 @@ int launch_conv_tc(const ConvParams& p, const CUtensorMap& tmap, int num_sms, cu
     // wide residual-free layers with the early-release epilogue (one 16-warp group, two staging buffers)
     if (p.store_mode != kStoreStaged || p.n_groups != 1 || p.n_stage < 1 || p.n_stage > 2 || p.npad != 64 || p.force_generic)
       return static_cast<int>(cudaErrorInvalidValue);
+    if (p.fuse2) {
+      // srcnn.conv1 (x-im2col folded, ReLU) + srcnn.conv2 (1x1, ReLU) in one launch
+      if (p.KW != 1 || p.PW != 0 || p.act != 2 || res != 0 || p.stage_row_bytes != 128 || p.w2_bytes != 4096 || p.n2 < 8 || p.n2 > 32 || (p.n2 & 7) ||
+          p.tmem_cols < p.n_acc * p.KW * p.npad + 32 || p.parts > 1)
+        return static_cast<int>(cudaErrorInvalidValue);
+      return launch_t<1, 0, 2, 0, 1, 0, 0, 1, 1>(p, tmap, num_sms, stream);
+    }
 #define CSR_EARLY(KW_, PW_, ACT_, RES_) \
     if (p.KW == KW_ && p.PW == PW_ && p.act == ACT_ && res == RES_) return launch_t<KW_, PW_, ACT_, RES_, 1, 0, 0, 1>(p, tmap, num_sms, stream);
     CSR_EARLY(3, 1, 1, 0)   // HRconv

@@ -67,6 +67,12 @@ struct ConvParams {
   // Used for the wide single-op layers (discriminator: 128..512 output channels over small maps), where one part per launch leaves most
   // SMs idle.  Residual / gate operands are not offset: only residual-free launches are merged.  0 / 1 = a single part.
   int parts, part_w_bytes, part_b_floats, part_c;
+  // Fused 1x1 successor (conv_tc.cu FUSE_T; early-release epilogue, KW = 1, 64 staged channels): out2[.., out2_coff + j] =
+  // relu(b2[j] + sum_c w2[j][c] * act(this layer)[c]) for j < n2 (multiple of 8, <= 32); `out` is NOT written.
+  int fuse2, w2_bytes, n2;
+  const void* w2;      // packed like a 1x1 layer with cin = 64, npad = 32: four k-step blocks of 32 rows x 16 K
+  const float* b2;
+  void* out2; int out2_C, out2_coff;
   // epilogue:  v = act(acc + bias [+ r1 if r1_pre]);  if r1 (not r1_pre): v = v*s1 + r1;  if r2: v = v*s2 + r2;  if gate: v *= (gate > 0 ? 1 : gate_neg)
   const float* bias;   // [npad] fp32 (zero padded)
   const void* wpk;     // packed bf16 weights (global), layout [kblock][dy][kstep in kblock][KW*npad/8][2][8][8]

@@ -629,6 +629,35 @@ def test_dense_block_kernel_is_bit_identical_to_per_layer_launches(n, in_ch, h, 
     assert torch.equal(outs[0], outs[2])
 
 
+@pytest.mark.parametrize("n,in_ch,h,w", [(4, 4, 64, 64), (1, 3, 113, 113), (3, 4, 20, 36), (1, 1, 9, 7), (2, 4, 5, 33)])
+def test_fused_srcnn_conv1_conv2_is_bit_identical_to_two_launches(n, in_ch, h, w):
+    """Option 33 (default on, inference plans): srcnn.conv2 (1x1, 64 -> 32, ReLU) as a second MMA over srcnn.conv1's staged bf16 tile
+    (conv_tc.cu FUSE_T) - the 64-channel HR map never reaches memory - against the two separate launches.  Same bf16 operands, same
+    four k-steps in the same order -> bit-identical outputs."""
+    from climsr_b200._lib import lib
+    from climsr_b200.models import ESRGANGenerator
+    from oracle import synth
+    sd = synth.make_state_dict(in_ch, 1, 64, 1, 16, seed=16, gain=1.2)
+    x, elev, mask = synth.make_inputs(n, in_ch, h, w, seed=17)
+    outs = []
+    try:
+        for fuse in (1, 0):
+            lib.csr_set_option(33, fuse)
+            net = ESRGANGenerator(in_ch, 1, 64, 1, 16)
+            net.load_state_dict(sd)
+            net = net.cuda().eval()
+            with torch.no_grad():
+                a = net(x.cuda(), elev.cuda(), mask.cuda())
+                b = net(x.cuda(), elev.cuda(), mask.cuda())
+            assert torch.equal(a, b)
+            outs.append(a.cpu())
+            del net
+    finally:
+        lib.csr_set_option(33, 1)
+    assert torch.isfinite(outs[0]).all()
+    assert torch.equal(outs[0], outs[1])
+
+
 @pytest.mark.parametrize("n,in_ch,h,w,nb", [(4, 4, 64, 64, 3), (1, 3, 113, 113, 2), (3, 4, 20, 36, 2), (1, 1, 9, 7, 1), (16, 4, 32, 32, 2), (150, 4, 16, 16, 1),
                                             (2, 4, 28, 14, 1), (1, 4, 29, 15, 1)])
 def test_dense_block_nine_tap_fold_matches_per_layer_launches(n, in_ch, h, w, nb):
