@@ -52,7 +52,8 @@ static int g_opt_l2_prefetch = 0;       // conv layers that stream from HBM: pre
 static int g_dbg_dense = 0;             // DenseParams::dbg (timing experiments)
 static int g_opt_dense_min = 2;         // ... only when a block has at least this many windows per SM: with <= 1 window per CTA nothing pipelines
                                         // across layers and the counters only cost (cfg1 / one Europe raster / cfg3: 7-10 % slower, r02 A/B)
-static int g_opt_fuse_tail = 1;         // inference: srcnn.conv2 inside srcnn.conv1's epilogue (second MMA over the staged tile)
+static int g_opt_fuse_tail = 3;         // inference, second MMA over the staged tile: bit 0 srcnn.conv2 inside srcnn.conv1's epilogue, bit 1 conv_last's
+                                        // nine tap planes inside HRconv's epilogue (+ tap_sum_kernel)
 [[maybe_unused]] static int g_opt_dense9 = 0;            // dense blocks with all nine taps folded into N = 144 (rdb9_tc.cu) instead of N = 48 (rdb_tc.cu)
 static int g_opt_dense = 1;             // conv1..conv4 of every gc = 16 dense block as ONE persistent launch with tile-level dependencies (rdb_tc.cu)
 static int g_opt_early = 1;             // early-release epilogue (conv_tc.cu, EARLY_T): 1 = wide residual-free layers; 2 = also the residual layers (RDB conv5 with one
@@ -211,6 +212,16 @@ static int fwd_index_rdb(int i, int r, int k);
 static std::vector<LayerSpec> fwd_exec_table(const CsrNetDesc& d, const std::vector<LayerSpec>& f) {
   std::vector<LayerSpec> v = f;
   for (size_t i = 0; i < v.size(); ++i) v[i].src = (int)i;
+  {
+    // conv_last (64 -> 1, 3x3) seen as a 1x1 layer with nine "output channels" = its nine taps: tap[t](y, x) = sum_c W[0][c][t] * in(y, x)[c].
+    // Inference runs it as a second MMA inside HRconv's epilogue (conv_tc.cu FUSE_T = 2) and sums the shifted taps afterwards
+    // (tap_sum_kernel), so HRconv's 64-channel HR map never reaches memory.  W[0][c][ky][kx] flattened is [c][t]: the transposed read
+    // of a (cout = 9, cin = 64, 1 x 1) layer.  Always the LAST entry, so state_dict indices keep their meaning.
+    LayerSpec T{"conv_last.taps", 9, d.nf, 1, 1};
+    T.transposed = 1;
+    T.src = (int)f.size() - 4;                             // conv_last
+    v.push_back(T);
+  }
   if (!g_opt_regroup) return v;
   for (int i = 0; i < d.nb; ++i)
     for (int r = 0; r < 3; ++r) {
@@ -330,6 +341,8 @@ struct ConvLaunch {
   CUtensorMap tmap;
   size_t w_off = 0, b_off = 0;  // offsets into the packed blob (resolved at forward time)
   size_t w2_off = 0, b2_off = 0;  // fused 1x1 successor (ConvParams::fuse2)
+  int tapsum = 0;               // 1: not a conv - conv_last finished from the tap planes HRconv's fused epilogue wrote (tap_sum_kernel)
+  const float* taps = nullptr; long tap_plane = 0; int tap_H = 0, tap_W = 0;
   bool final_out = false;       // fp32-planar output that IS the caller's `out` tensor
   int dense = -1;               // >= 0: this entry stands for a whole dense-block launch (CsrPlan::dense[dense]), not a conv
 };
@@ -1022,10 +1035,36 @@ static int plan_build(CsrPlan* P, void* ws) {
   if (rc) return rc;
   // conv_last -> fp32 planar temp; then [out, elev, mask] is packed (with srcnn.conv1's horizontal window) into hrC
   {
-    ConvIO io = io_of(hrB, 64, P->tlast, 1, 0, CSR_ACT_NONE);
-    io.out_kind = kOutF32Planar;
-    rc = add(H, W, io);
-    if (rc) return rc;
+    // Inference: HRconv's 64-channel output never reaches memory - its fused epilogue writes the nine tap planes of conv_last (second
+    // MMA over the staged tile, conv_tc.cu FUSE_T = 2) into hrB and tap_sum_kernel adds the shifted taps + bias into tlast.
+    ConvLaunch& hc = P->convs.back();
+    const PackLayer& pt = packs.back();                          // "conv_last.taps" (fwd_exec_table)
+    bool fused = false;
+    if ((g_opt_fuse_tail & 2) && !P->train && hc.p.early && hc.p.KW == 3 && hc.p.PW == 1 && hc.p.npad == 64 && hc.p.stage_row_bytes == 128 &&
+        pt.parts.size() == 1 && pt.parts[0].npad == 16 && pt.parts[0].w_bytes == 2048 && pt.cin_pad == 64) {
+      ConvParams q = hc.p;
+      q.fuse2 = 2; q.w2_bytes = pt.parts[0].w_bytes; q.n2 = 9; q.out2 = hrB; q.out2_plane = (long long)N * H * W;
+      int cols = 32;
+      while (cols < q.n_acc * q.KW * q.npad + 16) cols *= 2;
+      q.tmem_cols = cols;
+      if (cols <= 512 && conv_smem_bytes(q) <= (size_t)kSmemLimit && (size_t)9 * N * H * W * sizeof(float) <= (size_t)N * H * W * 64 * 2) {
+        hc.p = q;
+        hc.w2_off = pt.parts[0].w_off;
+        ConvLaunch ts;
+        memset(&ts.p, 0, sizeof(ts.p));
+        ts.tapsum = 1; ts.taps = reinterpret_cast<const float*>(hrB); ts.tap_plane = (long)N * H * W; ts.tap_H = H; ts.tap_W = W;
+        ts.b_off = packs[li].parts[0].b_off;                      // conv_last's own bias
+        P->convs.push_back(ts);
+        ++li;                                                    // conv_last has no conv launch
+        fused = true;
+      }
+    }
+    if (!fused) {
+      ConvIO io = io_of(hrB, 64, P->tlast, 1, 0, CSR_ACT_NONE);
+      io.out_kind = kOutF32Planar;
+      rc = add(H, W, io);
+      if (rc) return rc;
+    }
   }
   P->idx_srcnn1 = (int)P->convs.size();
   P->srcnn_pitch = P->train ? 64 : 32;
@@ -1038,7 +1077,7 @@ static int plan_build(CsrPlan* P, void* ws) {
     ConvLaunch& c1 = P->convs.back();
     const PackLayer& p2 = packs[li];
     bool fused = false;
-    if (g_opt_fuse_tail && !P->train && c1.p.early && c1.p.KW == 1 && c1.p.PW == 0 && c1.p.npad == 64 && c1.p.stage_row_bytes == 128 &&
+    if ((g_opt_fuse_tail & 1) && !P->train && c1.p.early && c1.p.KW == 1 && c1.p.PW == 0 && c1.p.npad == 64 && c1.p.stage_row_bytes == 128 &&
         p2.parts.size() == 1 && p2.parts[0].npad == 32 && p2.parts[0].w_bytes == 4096 && p2.cin_pad == 64 && sp % 8 == 0) {
       ConvParams q = c1.p;
       q.fuse2 = 1; q.w2_bytes = p2.parts[0].w_bytes; q.n2 = 32; q.out2 = hrE; q.out2_C = sp; q.out2_coff = 0;
@@ -1461,7 +1500,7 @@ int csr_set_option(int32_t key, int32_t value) {
     case 20: case 21: case 22: case 23: case 24: g_dbg_wgrad[key - 20] = value; return CSR_OK;
     case 25: g_opt_wgrad_atomic = value ? 1 : 0; return CSR_OK;    // plans created afterwards
     case 27: g_opt_dense = value ? 1 : 0; return CSR_OK;           // plans created afterwards
-    case 33: g_opt_fuse_tail = value ? 1 : 0; return CSR_OK;       // plans created afterwards
+    case 33: g_opt_fuse_tail = value & 3; return CSR_OK;       // plans created afterwards
     case 32: g_opt_dense9 = value ? 1 : 0; return CSR_OK;          // plans created afterwards
     case 31: if (value < 0 || value > 64) return fail(CSR_ERR_BAD_ARG, "option 31: windows per SM in [0, 64]"); g_opt_dense_min = value; return CSR_OK;
     case 28: g_dbg_dense = value; return CSR_OK;
@@ -1561,14 +1600,15 @@ int csr_pack_weights(const CsrNetDesc* net, const float* const* w, const float* 
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   uint8_t* base = reinterpret_cast<uint8_t*>(packed);
   std::vector<PackJob> jobs;
+  const size_t n_real = layer_table(*net).size();          // entries beyond it are views of other layers' weights (L.src)
   for (size_t i = 0; i < layers.size(); ++i) {
-    if (!w[i] || !b[i]) return fail(CSR_ERR_BAD_ARG, "null weight/bias pointer for layer %zu", i);
     const LayerSpec& L = layers[i];
+    if (i < n_real && (!w[i] || !b[i])) return fail(CSR_ERR_BAD_ARG, "null weight/bias pointer for layer %zu", i);
     for (const PackPart& pp : packs[i].parts) {
       float* bdst = reinterpret_cast<float*>(base + pp.b_off);
       if (L.blocks.empty()) {
-        jobs.push_back({w[i], b[i], base + pp.w_off, bdst, L.cout, L.cin, L.kh, L.kw, L.fold, pp.phase, L.transposed, L.wscale, pp.co_lo, pp.npad,
-                        packs[i].cin_pad, 0, 0, 0, 0});
+        jobs.push_back({i < n_real ? w[i] : w[L.src], i < n_real ? b[i] : nullptr, base + pp.w_off, bdst, L.cout, L.cin, L.kh, L.kw, L.fold, pp.phase,
+                        L.transposed, L.wscale, pp.co_lo, pp.npad, packs[i].cin_pad, 0, 0, 0, 0});
       } else {
         for (const LayerSpec::Block& B : L.blocks)         // output-channel blocks gathered from several state_dict layers
           jobs.push_back({w[B.src], L.block_bias ? b[B.src] : nullptr, base + pp.w_off, bdst, L.cout, L.cin, L.kh, L.kw, 0, pp.phase, 0,
@@ -1974,9 +2014,14 @@ static int forward_launches(CsrPlan* P, const void* packed, const float* x, cons
       ++g_launches;
       continue;
     }
+    if (cl.tapsum) {
+      CSR_CUDA(launch_tap_sum(cl.taps, cl.tap_plane, reinterpret_cast<const float*>(pk + cl.b_off), P->tlast, cl.tap_H, cl.tap_W, cl.tap_plane, s));
+      ++g_launches;
+      continue;
+    }
     cl.p.wpk = pk + cl.w_off;
     cl.p.bias = reinterpret_cast<const float*>(pk + cl.b_off);
-    if (cl.p.fuse2) { cl.p.w2 = pk + cl.w2_off; cl.p.b2 = reinterpret_cast<const float*>(pk + cl.b2_off); }
+    if (cl.p.fuse2) { cl.p.w2 = pk + cl.w2_off; cl.p.b2 = cl.p.fuse2 == 1 ? reinterpret_cast<const float*>(pk + cl.b2_off) : nullptr; }
     if (cl.final_out) cl.p.out = out;
     cl.p.timeline = ((int)i < g_timeline_cap) ? g_timeline : nullptr; cl.p.launch_id = (int)i;
     int e = launch_conv_tc(cl.p, cl.tmap, P->sms, s);

@@ -245,7 +245,7 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
   for (int i = threadIdx.x; i < p.npad; i += blockDim.x) bias_s[i] = p.bias[blockIdx.y * p.part_b_floats + i];
   if constexpr (FUSE_T) {
     float* bias2_s = reinterpret_cast<float*>(smem_gen + (b2_addr - smem_base));
-    for (int i = threadIdx.x; i < 32; i += blockDim.x) bias2_s[i] = i < p.n2 ? p.b2[i] : 0.f;
+    for (int i = threadIdx.x; i < 32; i += blockDim.x) bias2_s[i] = (p.b2 && i < p.n2) ? p.b2[i] : 0.f;
   }
   tc_fence_before();
   __syncthreads();
@@ -548,7 +548,9 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
         named_bar_sync(1, gthreads);                      // the staged tile is complete (and every copy-out of tile it-1 has been issued)
         if (tracer) CSR_TRACE(2, it, 7);
         if constexpr (FUSE_T) {
-          // second MMA: D2[128 x 32] = staged tile [128 x 64, K-major, 128B swizzle] x W2^T, four k-steps, issued by one epilogue thread
+          // second MMA: D2[128 x N2] = staged tile [128 rows x 64 ch, K-major, 128B swizzle] x W2^T, four k-steps, issued by one epilogue
+          // thread.  FUSE_T 1: N2 = 32 output channels of a 1x1 conv; FUSE_T 2: N2 = 16 columns = the nine taps of a 3x3 -> 1 conv.
+          constexpr int N2 = FUSE_T == 1 ? 32 : 16;
           const uint32_t d2_tmem = tmem_base + static_cast<uint32_t>(NA * nmma);
           if (warp == 1 + kMmaWarps) {
             if (it == 0) mbar_wait_spin(bar_w, 0);        // W2 arrived with the layer's own weights
@@ -558,27 +560,49 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
               const uint32_t a_hi2 = (1024u >> 4) | (1u << 14) | (2u << 29);
               const uint32_t b16 = (w2_addr >> 4) | ((128u >> 4) << 16);
               const uint32_t b_hi2 = (256u >> 4) | (1u << 14);
-              const uint32_t idesc2 = make_idesc_bf16(kTileM, 32);
+              const uint32_t idesc2 = make_idesc_bf16(kTileM, N2);
 #pragma unroll
-              for (int ks = 0; ks < 4; ++ks) umma_bf16_split(d2_tmem, a16 + ks * 2, a_hi2, b16 + ks * ((32 * 32) >> 4), b_hi2, idesc2, ks ? 1u : 0u);
+              for (int ks = 0; ks < 4; ++ks) umma_bf16_split(d2_tmem, a16 + ks * 2, a_hi2, b16 + ks * ((N2 * 32) >> 4), b_hi2, idesc2, ks ? 1u : 0u);
               umma_commit(bar_d2);
             }
             __syncwarp();
           }
           mbar_wait_spin(bar_d2, static_cast<uint32_t>(it) & 1u);
           tc_fence_after();
-          uint32_t r2[8];
-          tmem_ld8(t_lane + static_cast<uint32_t>(NA * nmma) + sub * 8, r2);
-          tmem_ld_wait();
-          tc_fence_before();
-          const int y = tl.y0 + ty, x = tl.x0 - PW_T + tx;
-          if (col_ok && y < p.H && x < p.W && sub * 8 < p.n2) {
-            const float* bias2_s = reinterpret_cast<const float*>(smem_gen + (b2_addr - smem_base)) + sub * 8;
-            float v[8];
+          if constexpr (FUSE_T == 1) {
+            uint32_t r2[8];
+            tmem_ld8(t_lane + static_cast<uint32_t>(NA * nmma) + sub * 8, r2);
+            tmem_ld_wait();
+            tc_fence_before();
+            const int y = tl.y0 + ty, x = tl.x0 - PW_T + tx;
+            if (col_ok && y < p.H && x < p.W && sub * 8 < p.n2) {
+              const float* bias2_s = reinterpret_cast<const float*>(smem_gen + (b2_addr - smem_base)) + sub * 8;
+              float v[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = fmaxf(__uint_as_float(r2[j]) + bias2_s[j], 0.f);          // bias + ReLU (srcnn.py:16)
-            __nv_bfloat16* o2 = reinterpret_cast<__nv_bfloat16*>(p.out2) + ((static_cast<size_t>(tl.n) * p.H + y) * p.W + x) * p.out2_C + p.out2_coff + sub * 8;
-            *reinterpret_cast<uint4*>(o2) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+              for (int j = 0; j < 8; ++j) v[j] = fmaxf(__uint_as_float(r2[j]) + bias2_s[j], 0.f);        // bias + ReLU (srcnn.py:16)
+              __nv_bfloat16* o2 = reinterpret_cast<__nv_bfloat16*>(p.out2) + ((static_cast<size_t>(tl.n) * p.H + y) * p.W + x) * p.out2_C + p.out2_coff + sub * 8;
+              *reinterpret_cast<uint4*>(o2) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+            }
+          } else {
+            // D2 row m belongs to STAGED row m = tile pixel (m / TW, m % TW) (the staged tile holds the TH x TW real outputs only).
+            // Warp (quadrant, sub 0) stores taps 0..7, (quadrant, sub 1) tap 8, into the fp32 tap planes out2[tap][n][y][x].
+            if (sub < 2) {
+              uint32_t r2[8];
+              tmem_ld8(t_lane + static_cast<uint32_t>(NA * nmma) + sub * 8, r2);
+              tmem_ld_wait();
+              const int py = m / p.TW, px = m - py * p.TW;
+              const int y = tl.y0 + py, x = tl.x0 + px;
+              if (m < p.TH * p.TW && y < p.H && x < p.W) {
+                float* o2 = reinterpret_cast<float*>(p.out2) + (static_cast<size_t>(tl.n) * p.H + y) * p.W + x + static_cast<size_t>(sub * 8) * p.out2_plane;
+                if (sub == 0) {
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) o2[static_cast<size_t>(j) * p.out2_plane] = __uint_as_float(r2[j]);
+                } else {
+                  o2[0] = __uint_as_float(r2[0]);
+                }
+              }
+            }
+            tc_fence_before();
           }
         } else {
         __nv_bfloat16* tile_out = reinterpret_cast<__nv_bfloat16*>(p.out) +
@@ -856,6 +880,13 @@ int launch_conv_tc(const ConvParams& p, const CUtensorMap& tmap, int num_sms, cu
     // wide residual-free layers with the early-release epilogue (one 16-warp group, two staging buffers)
     if (p.store_mode != kStoreStaged || p.n_groups != 1 || p.n_stage < 1 || p.n_stage > 2 || p.npad != 64 || p.force_generic)
       return static_cast<int>(cudaErrorInvalidValue);
+    if (p.fuse2 == 2) {
+      // HRconv (3x3, LeakyReLU) + the nine tap planes of conv_last (3x3, 64 -> 1) in one launch
+      if (p.KW != 3 || p.PW != 1 || p.act != 1 || res != 0 || p.stage_row_bytes != 128 || p.w2_bytes != 2048 || p.n2 != 9 || p.out2_plane <= 0 ||
+          p.tmem_cols < p.n_acc * p.KW * p.npad + 16 || p.parts > 1)
+        return static_cast<int>(cudaErrorInvalidValue);
+      return launch_t<3, 1, 1, 0, 1, 0, 0, 1, 2>(p, tmap, num_sms, stream);
+    }
     if (p.fuse2) {
       // srcnn.conv1 (x-im2col folded, ReLU) + srcnn.conv2 (1x1, ReLU) in one launch
       if (p.KW != 1 || p.PW != 0 || p.act != 2 || res != 0 || p.stage_row_bytes != 128 || p.w2_bytes != 4096 || p.n2 < 8 || p.n2 > 32 || (p.n2 & 7) ||

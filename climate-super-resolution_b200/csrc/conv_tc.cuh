@@ -73,6 +73,8 @@ struct ConvParams {
   const void* w2;      // packed like a 1x1 layer with cin = 64, npad = 32: four k-step blocks of 32 rows x 16 K
   const float* b2;
   void* out2; int out2_C, out2_coff;
+  // fuse2 == 2: the successor is a 3x3 -> 1 conv seen as nine 1x1 'tap' channels (n2 = 9): fp32 tap planes out2[tap * out2_plane + pixel]
+  long long out2_plane;
   // epilogue:  v = act(acc + bias [+ r1 if r1_pre]);  if r1 (not r1_pre): v = v*s1 + r1;  if r2: v = v*s2 + r2;  if gate: v *= (gate > 0 ? 1 : gate_neg)
   const float* bias;   // [npad] fp32 (zero padded)
   const void* wpk;     // packed bf16 weights (global), layout [kblock][dy][kstep in kblock][KW*npad/8][2][8][8]

@@ -451,6 +451,32 @@ cudaError_t launch_bias_grad_wide(const void* g, long npix, int C, int coff, int
   bias_grad_kernel<<<dim3(gx, chunks), 256, 256 * 8 * sizeof(float), s>>>(reinterpret_cast<const __nv_bfloat16*>(g), npix, C, coff, 128, scale, segs, 128);
   return cudaGetLastError();
 }
+// conv_last finished from its nine fp32 tap planes (conv_tc.cu FUSE_T = 2: tap[t](y, x) = sum_c W[0][c][t] * HRconv(y, x)[c]):
+//   out(n, y, x) = bias + sum_{ky,kx} tap[ky*3 + kx](n, y + ky - 1, x + kx - 1)      (zero outside the image = the conv padding)
+__global__ void tap_sum_kernel(const float* __restrict__ taps, long plane, const float* __restrict__ bias, float* __restrict__ out, int H, int W,
+                               long total) {
+  const float b = bias ? bias[0] : 0.f;
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const int x = static_cast<int>(i % W);
+    const int y = static_cast<int>((i / W) % H);
+    float acc = b;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int yy = y + ky - 1;
+      if (yy < 0 || yy >= H) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int xx = x + kx - 1;
+        if (xx >= 0 && xx < W) acc += taps[static_cast<long>(ky * 3 + kx) * plane + i + (ky - 1) * W + (kx - 1)];
+      }
+    }
+    out[i] = acc;
+  }
+}
+cudaError_t launch_tap_sum(const float* taps, long plane, const float* bias, float* out, int H, int W, long total, cudaStream_t s) {
+  tap_sum_kernel<<<grid_for(total, 256, 148 * 16), 256, 0, s>>>(taps, plane, bias, out, H, W, total);
+  return cudaGetLastError();
+}
 cudaError_t launch_bias_grad_planar(const float* g, long n, float scale, float* db, cudaStream_t s) {
   bias_grad_planar_kernel<<<148 * 2, 256, 0, s>>>(g, n, scale, db);
   return cudaGetLastError();

@@ -630,18 +630,20 @@ def test_dense_block_kernel_is_bit_identical_to_per_layer_launches(n, in_ch, h, 
 
 
 @pytest.mark.parametrize("n,in_ch,h,w", [(4, 4, 64, 64), (1, 3, 113, 113), (3, 4, 20, 36), (1, 1, 9, 7), (2, 4, 5, 33)])
-def test_fused_srcnn_conv1_conv2_is_bit_identical_to_two_launches(n, in_ch, h, w):
-    """Option 33 (default on, inference plans): srcnn.conv2 (1x1, 64 -> 32, ReLU) as a second MMA over srcnn.conv1's staged bf16 tile
-    (conv_tc.cu FUSE_T) - the 64-channel HR map never reaches memory - against the two separate launches.  Same bf16 operands, same
-    four k-steps in the same order -> bit-identical outputs."""
+def test_fused_hr_tail_matches_separate_launches(n, in_ch, h, w):
+    """Option 33 (inference plans; default 3 = both).  Bit 0: srcnn.conv2 (1x1, 64 -> 32, ReLU) as a second MMA over srcnn.conv1's staged
+    bf16 tile (conv_tc.cu FUSE_T = 1) - same bf16 operands, same four k-steps in the same order -> BIT-IDENTICAL to the two launches.
+    Bit 1: conv_last (3x3, 64 -> 1) as nine 1x1 'tap' channels computed by a second MMA inside HRconv's epilogue (FUSE_T = 2) + the
+    shifted tap sum (tap_sum_kernel) - same products, another fp32 summation order, then the bf16 rounding of the SRCNN input: equal to a
+    small fraction of the output scale.  In both cases the 64-channel HR map never reaches memory."""
     from climsr_b200._lib import lib
     from climsr_b200.models import ESRGANGenerator
     from oracle import synth
     sd = synth.make_state_dict(in_ch, 1, 64, 1, 16, seed=16, gain=1.2)
     x, elev, mask = synth.make_inputs(n, in_ch, h, w, seed=17)
-    outs = []
+    outs = {}
     try:
-        for fuse in (1, 0):
+        for fuse in (1, 0, 3, 2):
             lib.csr_set_option(33, fuse)
             net = ESRGANGenerator(in_ch, 1, 64, 1, 16)
             net.load_state_dict(sd)
@@ -650,12 +652,15 @@ def test_fused_srcnn_conv1_conv2_is_bit_identical_to_two_launches(n, in_ch, h, w
                 a = net(x.cuda(), elev.cuda(), mask.cuda())
                 b = net(x.cuda(), elev.cuda(), mask.cuda())
             assert torch.equal(a, b)
-            outs.append(a.cpu())
+            outs[fuse] = a.cpu()
             del net
     finally:
-        lib.csr_set_option(33, 1)
-    assert torch.isfinite(outs[0]).all()
-    assert torch.equal(outs[0], outs[1])
+        lib.csr_set_option(33, 3)
+    assert all(torch.isfinite(o).all() for o in outs.values())
+    assert torch.equal(outs[1], outs[0])
+    assert torch.equal(outs[3], outs[2])
+    scale = max(1.0, float(outs[0].abs().max()))
+    assert float((outs[3] - outs[0]).abs().max()) <= 2e-3 * scale, float((outs[3] - outs[0]).abs().max())
 
 
 @pytest.mark.parametrize("n,in_ch,h,w,nb", [(4, 4, 64, 64, 3), (1, 3, 113, 113, 2), (3, 4, 20, 36, 2), (1, 1, 9, 7, 1), (16, 4, 32, 32, 2), (150, 4, 16, 16, 1),
