@@ -487,6 +487,48 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
       const int ch_lo = sub * 16;
       uint32_t sb = 0;                                    // staging buffer of this tile
       const bool two_stage = p.n_stage == 2;
+      constexpr int N2 = FUSE_T == 1 ? 32 : 16;           // columns of the fused second MMA
+      Tile prev_tl = {0, 0, 0};
+      int n_done = 0;
+      // FUSE_T: read the second accumulator D2 of tile `t2` (its MMA has completed) and store the fused layer's output
+      auto consume_d2 = [&](const Tile& t2) {
+        tc_fence_after();
+        if constexpr (FUSE_T == 1) {
+          uint32_t r2[8];
+          tmem_ld8(t_lane + static_cast<uint32_t>(NA * nmma) + sub * 8, r2);
+          tmem_ld_wait();
+          tc_fence_before();
+          const int y = t2.y0 + ty, x = t2.x0 - PW_T + tx;
+          if (col_ok && y < p.H && x < p.W && sub * 8 < p.n2) {
+            const float* bias2_s = reinterpret_cast<const float*>(smem_gen + (b2_addr - smem_base)) + sub * 8;
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = fmaxf(__uint_as_float(r2[j]) + bias2_s[j], 0.f);          // bias + ReLU (srcnn.py:16)
+            __nv_bfloat16* o2 = reinterpret_cast<__nv_bfloat16*>(p.out2) + ((static_cast<size_t>(t2.n) * p.H + y) * p.W + x) * p.out2_C + p.out2_coff + sub * 8;
+            *reinterpret_cast<uint4*>(o2) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+          }
+        } else if constexpr (FUSE_T == 2) {
+          // D2 row m belongs to STAGED row m = tile pixel (m / TW, m % TW) (the staged tile holds the TH x TW real outputs only).
+          // Warp (quadrant, sub 0) stores taps 0..7, (quadrant, sub 1) tap 8, into the fp32 tap planes out2[tap][n][y][x].
+          if (sub < 2) {
+            uint32_t r2[8];
+            tmem_ld8(t_lane + static_cast<uint32_t>(NA * nmma) + sub * 8, r2);
+            tmem_ld_wait();
+            const int py = m / p.TW, px = m - py * p.TW;
+            const int y = t2.y0 + py, x = t2.x0 + px;
+            if (m < p.TH * p.TW && y < p.H && x < p.W) {
+              float* o2 = reinterpret_cast<float*>(p.out2) + (static_cast<size_t>(t2.n) * p.H + y) * p.W + x + static_cast<size_t>(sub * 8) * p.out2_plane;
+              if (sub == 0) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) o2[static_cast<size_t>(j) * p.out2_plane] = __uint_as_float(r2[j]);
+              } else {
+                o2[0] = __uint_as_float(r2[0]);
+              }
+            }
+          }
+          tc_fence_before();
+        }
+      };
       for (int it = 0; ; ++it) {
         const int t = blockIdx.x + it * static_cast<int>(gridDim.x);
         if (t >= p.num_tiles) break;
@@ -544,14 +586,20 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
                          pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
         }
         if (tracer) CSR_TRACE(2, it, 4);
-        if constexpr (FUSE_T) fence_proxy_async_smem();   // this thread's staged bf16 values -> visible to the tensor core's (async proxy) reads
+        if constexpr (FUSE_T) {
+          // the second MMA of the PREVIOUS tile has had this tile's accumulator wait, loads and arithmetic to complete (two staging
+          // buffers: it still reads the other one); with a single staging buffer its result is consumed right after the issue below
+          if (two_stage && it > 0) {
+            mbar_wait_spin(bar_d2, static_cast<uint32_t>(it - 1) & 1u);
+            consume_d2(prev_tl);
+          }
+          fence_proxy_async_smem();                       // this thread's staged bf16 values -> visible to the tensor core's (async proxy) reads
+        }
         named_bar_sync(1, gthreads);                      // the staged tile is complete (and every copy-out of tile it-1 has been issued)
         if (tracer) CSR_TRACE(2, it, 7);
         if constexpr (FUSE_T) {
           // second MMA: D2[128 x N2] = staged tile [128 rows x 64 ch, K-major, 128B swizzle] x W2^T, four k-steps, issued by one epilogue
           // thread.  FUSE_T 1: N2 = 32 output channels of a 1x1 conv; FUSE_T 2: N2 = 16 columns = the nine taps of a 3x3 -> 1 conv.
-          constexpr int N2 = FUSE_T == 1 ? 32 : 16;
-          const uint32_t d2_tmem = tmem_base + static_cast<uint32_t>(NA * nmma);
           if (warp == 1 + kMmaWarps) {
             if (it == 0) mbar_wait_spin(bar_w, 0);        // W2 arrived with the layer's own weights
             tc_fence_after();
@@ -562,48 +610,18 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
               const uint32_t b_hi2 = (256u >> 4) | (1u << 14);
               const uint32_t idesc2 = make_idesc_bf16(kTileM, N2);
 #pragma unroll
-              for (int ks = 0; ks < 4; ++ks) umma_bf16_split(d2_tmem, a16 + ks * 2, a_hi2, b16 + ks * ((N2 * 32) >> 4), b_hi2, idesc2, ks ? 1u : 0u);
+              for (int ks = 0; ks < 4; ++ks)
+                umma_bf16_split(tmem_base + static_cast<uint32_t>(NA * nmma), a16 + ks * 2, a_hi2, b16 + ks * ((N2 * 32) >> 4), b_hi2, idesc2, ks ? 1u : 0u);
               umma_commit(bar_d2);
             }
             __syncwarp();
           }
-          mbar_wait_spin(bar_d2, static_cast<uint32_t>(it) & 1u);
-          tc_fence_after();
-          if constexpr (FUSE_T == 1) {
-            uint32_t r2[8];
-            tmem_ld8(t_lane + static_cast<uint32_t>(NA * nmma) + sub * 8, r2);
-            tmem_ld_wait();
-            tc_fence_before();
-            const int y = tl.y0 + ty, x = tl.x0 - PW_T + tx;
-            if (col_ok && y < p.H && x < p.W && sub * 8 < p.n2) {
-              const float* bias2_s = reinterpret_cast<const float*>(smem_gen + (b2_addr - smem_base)) + sub * 8;
-              float v[8];
-#pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] = fmaxf(__uint_as_float(r2[j]) + bias2_s[j], 0.f);        // bias + ReLU (srcnn.py:16)
-              __nv_bfloat16* o2 = reinterpret_cast<__nv_bfloat16*>(p.out2) + ((static_cast<size_t>(tl.n) * p.H + y) * p.W + x) * p.out2_C + p.out2_coff + sub * 8;
-              *reinterpret_cast<uint4*>(o2) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
-            }
-          } else {
-            // D2 row m belongs to STAGED row m = tile pixel (m / TW, m % TW) (the staged tile holds the TH x TW real outputs only).
-            // Warp (quadrant, sub 0) stores taps 0..7, (quadrant, sub 1) tap 8, into the fp32 tap planes out2[tap][n][y][x].
-            if (sub < 2) {
-              uint32_t r2[8];
-              tmem_ld8(t_lane + static_cast<uint32_t>(NA * nmma) + sub * 8, r2);
-              tmem_ld_wait();
-              const int py = m / p.TW, px = m - py * p.TW;
-              const int y = tl.y0 + py, x = tl.x0 + px;
-              if (m < p.TH * p.TW && y < p.H && x < p.W) {
-                float* o2 = reinterpret_cast<float*>(p.out2) + (static_cast<size_t>(tl.n) * p.H + y) * p.W + x + static_cast<size_t>(sub * 8) * p.out2_plane;
-                if (sub == 0) {
-#pragma unroll
-                  for (int j = 0; j < 8; ++j) o2[static_cast<size_t>(j) * p.out2_plane] = __uint_as_float(r2[j]);
-                } else {
-                  o2[0] = __uint_as_float(r2[0]);
-                }
-              }
-            }
-            tc_fence_before();
+          if (!two_stage) {
+            mbar_wait_spin(bar_d2, static_cast<uint32_t>(it) & 1u);
+            consume_d2(tl);
           }
+          prev_tl = tl;
+          n_done = it + 1;
         } else {
         __nv_bfloat16* tile_out = reinterpret_cast<__nv_bfloat16*>(p.out) +
             ((static_cast<size_t>(tl.n) * p.out_H + (tl.y0 * p.out_sy + p.out_oy)) * p.out_W + (tl.x0 * p.out_sx + p.out_ox)) * p.out_C +
@@ -621,6 +639,12 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
         if (tracer) CSR_TRACE(2, it, 2);
         if (two_stage) sb ^= 1u;
         if (++buf >= NA) { buf = 0; acc_phase ^= 1; }
+      }
+      if constexpr (FUSE_T) {
+        if (two_stage && n_done > 0) {                    // the last tile's second MMA
+          mbar_wait_spin(bar_d2, static_cast<uint32_t>(n_done - 1) & 1u);
+          consume_d2(prev_tl);
+        }
       }
     } else
     for (int it = g; ; it += NG) {                        // `it` counts M tiles; window = it >> tall_shift
