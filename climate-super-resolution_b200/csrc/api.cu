@@ -52,6 +52,7 @@ static int g_opt_l2_prefetch = 0;       // conv layers that stream from HBM: pre
 static int g_dbg_dense = 0;             // DenseParams::dbg (timing experiments)
 static int g_opt_dense_min = 2;         // ... only when a block has at least this many windows per SM: with <= 1 window per CTA nothing pipelines
                                         // across layers and the counters only cost (cfg1 / one Europe raster / cfg3: 7-10 % slower, r02 A/B)
+static int g_opt_merge_phases = 1;      // sub-pixel phase pairs of nearest-x2 + conv as one launch (gridDim.y)
 static int g_opt_fuse_tail = 3;         // inference, second MMA over the staged tile: bit 0 srcnn.conv2 inside srcnn.conv1's epilogue, bit 1 conv_last's
                                         // nine tap planes inside HRconv's epilogue (+ tap_sum_kernel)
 [[maybe_unused]] static int g_opt_dense9 = 0;            // dense blocks with all nine taps folded into N = 144 (rdb9_tc.cu) instead of N = 48 (rdb_tc.cu)
@@ -954,11 +955,39 @@ static int plan_build(CsrPlan* P, void* ws) {
   int li = 0;
   auto add = [&](int H, int W, const ConvIO& io, bool advance = true) -> int {
     const PackLayer& pl = packs[li];
+    const size_t first = P->convs.size();
     for (const PackPart& pp : pl.parts) {
       ConvLaunch cl;
       int rc = build_conv(pl, pp, N, H, W, io, &cl);
       if (rc) return rc;
       P->convs.push_back(cl);
+    }
+    // nearest-x2 + conv = four sub-pixel phases (a, b) in phase order 2a + b: the two phases with the same b share the kernel
+    // specialisation (PW = 1 - b) and go out as ONE launch with a on gridDim.y (weights / bias at a constant stride, PH = 1 - a,
+    // output rows 2y + a): two launches instead of four, each over twice the tiles
+    if (g_opt_merge_phases && pl.parts.size() == 4 && pl.parts[0].phase == 0 && pl.parts[3].phase == 3 && !io.r1 && !io.r2 && !io.gate) {
+      ConvLaunch a0 = P->convs[first], a1 = P->convs[first + 1];
+      const ConvLaunch& c2 = P->convs[first + 2]; const ConvLaunch& c3 = P->convs[first + 3];
+      auto pair_ok = [](const ConvLaunch& u, const ConvLaunch& v) {
+        return u.p.PW == v.p.PW && u.p.KW == v.p.KW && u.p.KH == v.p.KH && u.p.num_tiles == v.p.num_tiles && u.p.SW == v.p.SW && u.p.TH == v.p.TH &&
+               u.p.n_slots == v.p.n_slots && u.p.w_bytes == v.p.w_bytes && u.p.early == v.p.early && u.p.n_acc == v.p.n_acc &&
+               u.p.out_ox == v.p.out_ox && u.p.store_mode == v.p.store_mode && v.w_off > u.w_off && v.b_off > u.b_off;
+      };
+      if (pair_ok(a0, c2) && pair_ok(a1, c3)) {
+        auto merge2 = [](ConvLaunch& u, const ConvLaunch& v) {
+          u.p.parts = 2;
+          u.p.part_w_bytes = (int)(v.w_off - u.w_off);
+          u.p.part_b_floats = (int)((v.b_off - u.b_off) / sizeof(float));
+          u.p.part_c = 0;
+          u.p.part_ph = v.p.PH - u.p.PH;
+          u.p.part_oy = v.p.out_oy - u.p.out_oy;
+        };
+        merge2(a0, c2);
+        merge2(a1, c3);
+        P->convs.resize(first);
+        P->convs.push_back(a0);
+        P->convs.push_back(a1);
+      }
     }
     if (advance) ++li;
     return CSR_OK;
@@ -1500,6 +1529,7 @@ int csr_set_option(int32_t key, int32_t value) {
     case 20: case 21: case 22: case 23: case 24: g_dbg_wgrad[key - 20] = value; return CSR_OK;
     case 25: g_opt_wgrad_atomic = value ? 1 : 0; return CSR_OK;    // plans created afterwards
     case 27: g_opt_dense = value ? 1 : 0; return CSR_OK;           // plans created afterwards
+    case 34: g_opt_merge_phases = value ? 1 : 0; return CSR_OK;    // plans created afterwards
     case 33: g_opt_fuse_tail = value & 3; return CSR_OK;       // plans created afterwards
     case 32: g_opt_dense9 = value ? 1 : 0; return CSR_OK;          // plans created afterwards
     case 31: if (value < 0 || value > 64) return fail(CSR_ERR_BAD_ARG, "option 31: windows per SM in [0, 64]"); g_opt_dense_min = value; return CSR_OK;

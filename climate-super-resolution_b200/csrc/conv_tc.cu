@@ -191,6 +191,10 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int KW = KW_T ? KW_T : p.KW;
+  // parts on gridDim.y may also differ in vertical padding and output row phase (the sub-pixel phases (a, b), a = 0 / 1, of
+  // nearest-x2 + conv: PH = 1 - a, output row offset a)
+  const int ph_eff = p.PH + static_cast<int>(blockIdx.y) * p.part_ph;
+  const int oy_eff = p.out_oy + static_cast<int>(blockIdx.y) * p.part_oy;
 
   // Let the next layer's grid start its own prologue as early as the hardware allows (PDL).
   griddep_launch_dependents();
@@ -269,7 +273,7 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
         const int tp = t + p.l2_prefetch * static_cast<int>(gridDim.x);
         if (tp < p.num_tiles && elect_one()) {
           const Tile tq = decode_tile<TALL_T>(p, tp);
-          for (int kb = 0; kb < p.n_kblocks; ++kb) tma_prefetch_l2_4d(&tmap, p.cin_off + kb * 64, tq.x0 - p.PW, tq.y0 - p.PH, tq.n);
+          for (int kb = 0; kb < p.n_kblocks; ++kb) tma_prefetch_l2_4d(&tmap, p.cin_off + kb * 64, tq.x0 - p.PW, tq.y0 - ph_eff, tq.n);
         }
         __syncwarp();
       }
@@ -292,9 +296,9 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
           if (crank == 0) mbar_arrive_expect_tx(bar_a_full(slot), PAIR_T ? 2 * p.win_bytes : p.win_bytes);
           if constexpr (PAIR_T)
             tma_load_4d_pair(slots_addr + slot * p.slot_bytes, &tmap, bar_a_full(slot) + lead_off, p.cin_off + kb * 64, tl.x0 - p.PW,
-                             tl.y0 - p.PH, tl.n);
+                             tl.y0 - ph_eff, tl.n);
           else
-            tma_load_4d(slots_addr + slot * p.slot_bytes, &tmap, bar_a_full(slot), p.cin_off + kb * 64, tl.x0 - p.PW, tl.y0 - p.PH, tl.n);
+            tma_load_4d(slots_addr + slot * p.slot_bytes, &tmap, bar_a_full(slot), p.cin_off + kb * 64, tl.x0 - p.PW, tl.y0 - ph_eff, tl.n);
         }
         __syncwarp();
         if (++slot == S) { slot = 0; phase ^= 1; }
@@ -624,7 +628,7 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
           n_done = it + 1;
         } else {
         __nv_bfloat16* tile_out = reinterpret_cast<__nv_bfloat16*>(p.out) +
-            ((static_cast<size_t>(tl.n) * p.out_H + (tl.y0 * p.out_sy + p.out_oy)) * p.out_W + (tl.x0 * p.out_sx + p.out_ox)) * p.out_C +
+            ((static_cast<size_t>(tl.n) * p.out_H + (tl.y0 * p.out_sy + oy_eff)) * p.out_W + (tl.x0 * p.out_sx + p.out_ox)) * p.out_C +
             p.out_coff + static_cast<int>(blockIdx.y) * p.part_c;
         const uint32_t lim = (static_cast<uint32_t>(max(0, min(p.H - tl.y0, 0x7fff))) << 16) | static_cast<uint32_t>(min(p.W - tl.x0, 0x7fff));
 #pragma unroll
@@ -740,7 +744,7 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
               st_shared_v4(srow_addr + ((static_cast<uint32_t>(c) ^ swz) << 4), pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
                            pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
           } else if (valid) {
-            const size_t opix = (static_cast<size_t>(tl.n) * p.out_H + (y * p.out_sy + p.out_oy)) * p.out_W + (x * p.out_sx + p.out_ox);
+            const size_t opix = (static_cast<size_t>(tl.n) * p.out_H + (y * p.out_sy + oy_eff)) * p.out_W + (x * p.out_sx + p.out_ox);
             const int smode = ST_T == 2 ? static_cast<int>(kStoreDirect32) : ST_T == 3 ? static_cast<int>(kStoreF32Planar) : p.store_mode;
             if (smode == kStoreDirect32) {
               // whole 32-byte sectors per lane (16 channels): no partial-sector writes reach L2
@@ -777,7 +781,7 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
         named_bar_sync(1 + g, gthreads);                  // the staged tile is complete
         if (tracer) CSR_TRACE(2, it, 7);
         __nv_bfloat16* tile_out = reinterpret_cast<__nv_bfloat16*>(p.out) +
-            ((static_cast<size_t>(tl.n) * p.out_H + (tl.y0 * p.out_sy + p.out_oy)) * p.out_W + (tl.x0 * p.out_sx + p.out_ox)) * p.out_C +
+            ((static_cast<size_t>(tl.n) * p.out_H + (tl.y0 * p.out_sy + oy_eff)) * p.out_W + (tl.x0 * p.out_sx + p.out_ox)) * p.out_C +
             p.out_coff + static_cast<int>(blockIdx.y) * p.part_c;
         // (the lower M tile of a window may lie entirely below the image: no piece passes)
         const uint32_t lim = (static_cast<uint32_t>(max(0, min(p.H - tl.y0, 0x7fff))) << 16) | static_cast<uint32_t>(min(p.W - tl.x0, 0x7fff));

@@ -67,6 +67,7 @@ struct ConvParams {
   // Used for the wide single-op layers (discriminator: 128..512 output channels over small maps), where one part per launch leaves most
   // SMs idle.  Residual / gate operands are not offset: only residual-free launches are merged.  0 / 1 = a single part.
   int parts, part_w_bytes, part_b_floats, part_c;
+  int part_ph, part_oy;   // ... and PH + k*part_ph, out_oy + k*part_oy (sub-pixel phase pairs of nearest-x2 + conv as one launch)
   // Fused 1x1 successor (conv_tc.cu FUSE_T; early-release epilogue, KW = 1, 64 staged channels): out2[.., out2_coff + j] =
   // relu(b2[j] + sum_c w2[j][c] * act(this layer)[c]) for j < n2 (multiple of 8, <= 32); `out` is NOT written.
   int fuse2, w2_bytes, n2;

@@ -629,6 +629,30 @@ def test_dense_block_kernel_is_bit_identical_to_per_layer_launches(n, in_ch, h, 
     assert torch.equal(outs[0], outs[2])
 
 
+@pytest.mark.parametrize("n,in_ch,h,w", [(2, 4, 64, 64), (1, 3, 113, 113), (3, 4, 20, 36), (1, 1, 9, 7)])
+def test_merged_subpixel_phase_launches_are_bit_identical(n, in_ch, h, w):
+    """Option 34 (default on): the two sub-pixel phases of nearest-x2 + conv that share a kernel specialisation run as ONE launch with
+    the vertical phase on gridDim.y (two launches per upconv instead of four).  Same tiles, same arithmetic -> bit-identical."""
+    from climsr_b200._lib import lib
+    from climsr_b200.models import ESRGANGenerator
+    from oracle import synth
+    sd = synth.make_state_dict(in_ch, 1, 64, 1, 16, seed=26, gain=1.2)
+    x, elev, mask = synth.make_inputs(n, in_ch, h, w, seed=27)
+    outs = []
+    try:
+        for merged in (1, 0):
+            lib.csr_set_option(34, merged)
+            net = ESRGANGenerator(in_ch, 1, 64, 1, 16)
+            net.load_state_dict(sd)
+            net = net.cuda().eval()
+            with torch.no_grad():
+                outs.append(net(x.cuda(), elev.cuda(), mask.cuda()).cpu())
+            del net
+    finally:
+        lib.csr_set_option(34, 1)
+    assert torch.equal(outs[0], outs[1])
+
+
 @pytest.mark.parametrize("n,in_ch,h,w", [(4, 4, 64, 64), (1, 3, 113, 113), (3, 4, 20, 36), (1, 1, 9, 7), (2, 4, 5, 33)])
 def test_fused_hr_tail_matches_separate_launches(n, in_ch, h, w):
     """Option 33 (inference plans; default 3 = both).  Bit 0: srcnn.conv2 (1x1, 64 -> 32, ReLU) as a second MMA over srcnn.conv1's staged
