@@ -995,10 +995,20 @@ static int plan_build(CsrPlan* P, void* ws) {
   int rc;
   // conv_first (esrgan.py:90) has two consumers: the first RRDB (reads x from its concat buffer) and the trunk skip-add
   // 33 layers later.  The layer is tiny (K = 16), so it is simply run into both places.
-  rc = add(h, w, io_of(xin, 64, fea0, 64, 0, CSR_ACT_NONE), false);
+  rc = add(h, w, io_of(xin, 64, cat(0), C, 0, CSR_ACT_NONE), false);
   if (rc) return rc;
-  rc = add(h, w, io_of(xin, 64, cat(0), C, 0, CSR_ACT_NONE));
-  if (rc) return rc;
+  if (g_opt_merge_phases && P->convs.size() == 1 && P->convs[0].p.early && P->convs[0].p.store_mode == kStoreStaged && P->convs[0].p.KW == 3 &&
+      P->convs[0].p.act == 0 && !P->convs[0].p.r1) {
+    // ... with the early-release epilogue the staged tile is simply stored twice (conv_tc.cu, out_dup)
+    P->convs[0].p.out_dup = fea0; P->convs[0].p.dup_C = 64; P->convs[0].p.dup_coff = 0;
+    ++li;
+  } else {
+    P->convs.clear();
+    rc = add(h, w, io_of(xin, 64, fea0, 64, 0, CSR_ACT_NONE), false);
+    if (rc) return rc;
+    rc = add(h, w, io_of(xin, 64, cat(0), C, 0, CSR_ACT_NONE));
+    if (rc) return rc;
+  }
   for (int i = 0; i < d.nb; ++i) {
     // RRDB i: its input x lives in channels [0,nf) of concat buffer 3i.  Inference rotates three buffers A->B->C->A, so
     // A's x survives until RDB3's epilogue reads it as the RRDB residual and overwrites it in place; training keeps one

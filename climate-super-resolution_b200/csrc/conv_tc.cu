@@ -637,6 +637,17 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
           if (ok) {
             const uint4 val = ld_shared_v4(pc_s[k] + sb * p.stage_bytes);
             *reinterpret_cast<uint4*>(tile_out + pc_d[k]) = val;
+            if constexpr (KW_T == 3 && ACT_T == 0 && RES_T == 0 && FUSE_T == 0) {
+              // conv_first (the only plain 3x3 layer): its output has two consumers - the first dense block reads it from its concat
+              // buffer, the trunk skip-add 33 layers later from a buffer of its own - so the tile is stored twice instead of running
+              // the layer twice
+              if (p.out_dup) {
+                const uint32_t pixoff = ((pc_yx[k] >> 16) * p.out_sy * p.out_W + (pc_yx[k] & 0xffffu) * p.out_sx);
+                __nv_bfloat16* dup = reinterpret_cast<__nv_bfloat16*>(p.out_dup) +
+                    ((static_cast<size_t>(tl.n) * p.out_H + (tl.y0 * p.out_sy + oy_eff)) * p.out_W + (tl.x0 * p.out_sx + p.out_ox)) * p.dup_C + p.dup_coff;
+                *reinterpret_cast<uint4*>(dup + static_cast<size_t>(pixoff) * p.dup_C + (pc_d[k] - pixoff * p.out_C)) = val;
+              }
+            }
           }
         }
         }

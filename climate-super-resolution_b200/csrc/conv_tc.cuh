@@ -89,6 +89,7 @@ struct ConvParams {
   const void* gate; int gate_C, gate_coff; int gate_from; float gate_neg;   // applied to output channels >= gate_from
   void* out; int out_C, out_coff;
   int store_mode;      // StoreMode
+  void* out_dup; int dup_C, dup_coff;   // early-release plain 3x3 layer (conv_first): second copy of the output (same pixels, own channel pitch)
   int out_sy, out_sx, out_oy, out_ox;   // conv-output pixel (y,x) lives at buffer pixel (y*out_sy+out_oy, x*out_sx+out_ox)
   int out_H, out_W;                     // spatial size of the output buffer
   int stage_row_bytes; // kStoreStaged: bytes per staged pixel (n_store * 2: 16..128)
