@@ -52,6 +52,8 @@ static int g_opt_l2_prefetch = 0;       // conv layers that stream from HBM: pre
 static int g_dbg_dense = 0;             // DenseParams::dbg (timing experiments)
 static int g_opt_dense_min = 2;         // ... only when a block has at least this many windows per SM: with <= 1 window per CTA nothing pipelines
                                         // across layers and the counters only cost (cfg1 / one Europe raster / cfg3: 7-10 % slower, r02 A/B)
+static int g_opt_hyb = 1;               // hybrid tap fold (conv_tc.cu HYB_T): bit 0 early-release layers (HRconv 338 -> 294 us); experiments build only:
+                                        // bit 1 conv5 / trunk_conv, bit 2 four accumulators there (measured slower: those are not epilogue-bound)
 static int g_opt_merge_phases = 1;      // sub-pixel phase pairs of nearest-x2 + conv as one launch (gridDim.y)
 static int g_opt_fuse_tail = 3;         // inference, second MMA over the staged tile: bit 0 srcnn.conv2 inside srcnn.conv1's epilogue, bit 1 conv_last's
                                         // nine tap planes inside HRconv's epilogue (+ tap_sum_kernel)
@@ -495,6 +497,25 @@ static int build_conv(const PackLayer& pl, const PackPart& pp, int N, int H, int
       if (4 * p.KW * p.npad <= 512 && !g_opt_two_acc) p.n_acc = 4;
     }
   }
+  // Hybrid tap fold (conv_tc.cu HYB_T) for the 64-channel 3x3 / 2x2 layers, which are epilogue-bound: the last horizontal tap is its own
+  // MMA on an A operand shifted by one pixel and accumulates into the previous tap's columns - a third (half) fewer accumulator
+  // columns to read and one shuffle-sum fewer, at 22 % more MMA time.  Bit 0: early-release layers, bit 1: RDB conv5 / trunk_conv,
+  // bit 2: four accumulators for the latter.
+  {
+    const bool hyb_early = (g_opt_hyb & 1) && p.early && ((p.KW == 3 && p.PW == 1) || (p.KW == 2 && p.PW <= 1));
+#ifdef CSR_EXPERIMENTS
+    const bool hyb_res = (g_opt_hyb & 2) && !p.early && p.KW == 3 && p.PW == 1 && p.act == 0 && (res_bits == 1 || res_bits == 3) && !io.r1_pre &&
+                         p.n_groups == 2;
+#else
+    const bool hyb_res = false;
+#endif
+    if ((hyb_early || hyb_res) && !p.pair && !p.tall_shift && p.store_mode == kStoreStaged && p.npad == 64 && pp.n_store == 64 && p.box_c == 64 &&
+        !p.stream_w && !g_opt_force_generic) {
+      p.hyb = 1;
+      const int acc_cols = (p.KW - 1) * p.npad;
+      if (4 * acc_cols <= 512 && !g_opt_two_acc && (p.early || (g_opt_hyb & 4))) p.n_acc = 4;
+    }
+  }
   p.SW = tl.SW; p.TH = tl.TH; p.TW = tl.TW;
   p.sw_shift = 0;
   while ((1 << p.sw_shift) < p.SW) ++p.sw_shift;
@@ -512,7 +533,7 @@ static int build_conv(const PackLayer& pl, const PackPart& pp, int N, int H, int
   p.n_mma = g_opt_one_mma ? 1 : 2;
   p.issue_order = (p.n_mma == 2) && (g_opt_issue_order == 2 || (g_opt_issue_order == 1 && p.pair));
   int cols = 32;
-  while (cols < p.n_acc * p.KW * p.npad) cols *= 2;
+  while (cols < p.n_acc * (p.hyb ? p.KW - 1 : p.KW) * p.npad) cols *= 2;
   if (cols > 512 || p.KW * p.npad > 256) return fail(CSR_ERR_UNSUPPORTED, "KW*npad = %d exceeds the UMMA N / TMEM budget", p.KW * p.npad);
   p.tmem_cols = cols;
   p.trace = g_trace;
@@ -1083,8 +1104,9 @@ static int plan_build(CsrPlan* P, void* ws) {
         pt.parts.size() == 1 && pt.parts[0].npad == 16 && pt.parts[0].w_bytes == 2048 && pt.cin_pad == 64) {
       ConvParams q = hc.p;
       q.fuse2 = 2; q.w2_bytes = pt.parts[0].w_bytes; q.n2 = 9; q.out2 = hrB; q.out2_plane = (long long)N * H * W;
+      if (q.hyb) q.n_acc = 2;                                  // hybrid fold: 2 x 128 + 16 columns (four accumulators would fill TMEM)
       int cols = 32;
-      while (cols < q.n_acc * q.KW * q.npad + 16) cols *= 2;
+      while (cols < q.n_acc * (q.hyb ? 2 : q.KW) * q.npad + 16) cols *= 2;
       q.tmem_cols = cols;
       if (cols <= 512 && conv_smem_bytes(q) <= (size_t)kSmemLimit && (size_t)9 * N * H * W * sizeof(float) <= (size_t)N * H * W * 64 * 2) {
         hc.p = q;
@@ -1514,7 +1536,7 @@ int csr_set_option(int32_t key, int32_t value) {
   // the table with defaults and meanings is in INTEGRATION.md section 6
 #ifndef CSR_EXPERIMENTS
   // measured-and-rejected kernel variants are not part of the default build (conv_tc.cu launch_conv_tc)
-  if ((key == 13 && value != 0) || (key == 16 && value != 0) || (key == 8 && value == 0) || (key == 32 && value != 0))
+  if ((key == 13 && value != 0) || (key == 16 && value != 0) || (key == 8 && value == 0) || (key == 32 && value != 0) || (key == 35 && (value & ~1)))
     return fail(CSR_ERR_UNSUPPORTED, "option %d=%d selects an experimental kernel variant: rebuild with CSR_EXPERIMENTS=1 python build.py --force", key, value);
 #endif
   switch (key) {
@@ -1539,6 +1561,7 @@ int csr_set_option(int32_t key, int32_t value) {
     case 20: case 21: case 22: case 23: case 24: g_dbg_wgrad[key - 20] = value; return CSR_OK;
     case 25: g_opt_wgrad_atomic = value ? 1 : 0; return CSR_OK;    // plans created afterwards
     case 27: g_opt_dense = value ? 1 : 0; return CSR_OK;           // plans created afterwards
+    case 35: g_opt_hyb = value; return CSR_OK;                    // plans created afterwards
     case 34: g_opt_merge_phases = value ? 1 : 0; return CSR_OK;    // plans created afterwards
     case 33: g_opt_fuse_tail = value & 3; return CSR_OK;       // plans created afterwards
     case 32: g_opt_dense9 = value ? 1 : 0; return CSR_OK;          // plans created afterwards

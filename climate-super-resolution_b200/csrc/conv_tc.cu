@@ -140,6 +140,10 @@ __device__ __forceinline__ uint4 ldg16(const void* base, size_t pix, int C, int 
 //          M = 256 MMA for both, and each CTA keeps only HALF of the layer's weights resident (B rows [0,N/2) / [N/2,N)),
 //          which is what buys RDB conv5 (144 KB of weights) a window ring deep enough to prefetch across tiles.
 //   TALL_T 1 = two M tiles per window (ConvParams::tall_shift), compile-time so that the common kernels carry none of it
+//   HYB_T 1 = (3x3, early-release epilogue) only TWO of the three horizontal taps are folded into N: per (dy, k-step) one N = 2*npad MMA
+//            (taps dx = 0, 1) plus one N = npad MMA for tap dx = 2 whose A operand starts one pixel later and which accumulates into the
+//            dx = 1 columns.  142 instead of 117 clk of MMAs, but the accumulator is 128 instead of 192 columns (four buffers instead of
+//            two) and the epilogue reads a third fewer columns and shuffles once instead of twice - these layers are epilogue-bound.
 //   FUSE_T 1 = (early-release epilogue only) the layer's 64-channel output never leaves the SM: the staged bf16 tile - already a K-major,
 //             128B-swizzled UMMA A operand - goes through a SECOND MMA with the weights of the following 1x1 conv (srcnn.conv2 after
 //             srcnn.conv1: 64 -> 32, srcnn.py:15-16), whose bias + ReLU output is what gets stored.  Saves the 64-channel HR map's
@@ -151,7 +155,7 @@ __device__ __forceinline__ uint4 ldg16(const void* base, size_t pix, int C, int 
 //          ~2450 clk per 128 x 64 tile against ~1400 clk of MMAs, because an accumulator stayed busy for the whole
 //          ~1000-clk arithmetic phase and only two of them fit TMEM; tools/tmem_probe.cu shows the TMEM read port itself
 //          delivers a 128 x 192 fp32 tile to 16 warps in ~260 clk.)
-template <int KW_T, int PW_T, int ACT_T, int RES_T, int ST_T, int PAIR_T = 0, int TALL_T = 0, int EARLY_T = 0, int FUSE_T = 0>
+template <int KW_T, int PW_T, int ACT_T, int RES_T, int ST_T, int PAIR_T = 0, int TALL_T = 0, int EARLY_T = 0, int FUSE_T = 0, int HYB_T = 0>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
   extern __shared__ uint8_t smem_raw[];
@@ -262,6 +266,7 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
 
   const int ksteps_total = p.cin >> 4;
   const int nmma = KW * p.npad;                          // UMMA N: horizontal taps folded into the output columns
+  const int nacc = HYB_T ? (KW - 1) * p.npad : nmma;     // accumulator columns per tile (hybrid fold: the last tap shares the previous tap's columns)
 
   if (warp == 0) {
     // ===================== TMA producer (whole warp walks the loop, one elected lane issues) =====================
@@ -353,7 +358,7 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
       if constexpr (TALL_T) mbar_wait_spin(bar_acc_empty(buf + 1), acc_phase ^ 1);
       tc_fence_after();
       if (lane == 0) CSR_TRACE(1, it, 1);
-      const uint32_t d_tmem = tmem_base + buf * nmma;
+      const uint32_t d_tmem = tmem_base + buf * nacc;
       for (int kb = 0; kb < p.n_kblocks; ++kb, ++entry) {
         if (p.n_mma > 1) {
           const int need = entry - S;
@@ -383,6 +388,21 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
           const bool last_kb = kb == p.n_kblocks - 1;
           if constexpr (TALL_T == 0) {
             uint32_t acc = kb ? 1u : 0u;
+            if constexpr (HYB_T) {
+              // all taps but the last folded into N (B rows [0, (KW-1) npad)); the last tap as its own MMA: A one pixel further (start
+              // address + 128 B; the hardware derives the 128B-swizzle phase from the address, base offset stays 0), B rows
+              // [(KW-1) npad, KW npad), accumulated into the columns of tap KW-2
+              const uint32_t idesc_a = make_idesc_bf16(kTileM, (KW_T - 1) * p.npad), idesc_b = make_idesc_bf16(kTileM, p.npad);
+              const uint32_t b_last = static_cast<uint32_t>((KW_T - 1) * p.npad * 32) >> 4;
+              const uint32_t d_last = d_tmem + static_cast<uint32_t>((KW_T - 2) * p.npad);
+              for (int dy = 0; dy < p.KH; ++dy, a16 += row16) {
+                for (int ks = 0; ks < ks_here; ++ks, b16 += b_step16) {
+                  umma_bf16_split(d_tmem, a16 + ks * 2, a_hi, b16, b_hi, idesc_a, acc);
+                  umma_bf16_split(d_last, a16 + 8 + ks * 2, a_hi, b16 + b_last, b_hi, idesc_b, 1u);
+                  acc = 1;
+                }
+              }
+            } else
             for (int dy = 0; dy < p.KH; ++dy, a16 += row16) {
               for (int ks = 0; ks < ks_here; ++ks, b16 += b_step16) {
                 if constexpr (PAIR_T) umma_bf16_split_pair(d_tmem, a16 + ks * 2, a_hi, b16, b_hi, idesc, acc);
@@ -499,7 +519,7 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
         tc_fence_after();
         if constexpr (FUSE_T == 1) {
           uint32_t r2[8];
-          tmem_ld8(t_lane + static_cast<uint32_t>(NA * nmma) + sub * 8, r2);
+          tmem_ld8(t_lane + static_cast<uint32_t>(NA * nacc) + sub * 8, r2);
           tmem_ld_wait();
           tc_fence_before();
           const int y = t2.y0 + ty, x = t2.x0 - PW_T + tx;
@@ -516,7 +536,7 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
           // Warp (quadrant, sub 0) stores taps 0..7, (quadrant, sub 1) tap 8, into the fp32 tap planes out2[tap][n][y][x].
           if (sub < 2) {
             uint32_t r2[8];
-            tmem_ld8(t_lane + static_cast<uint32_t>(NA * nmma) + sub * 8, r2);
+            tmem_ld8(t_lane + static_cast<uint32_t>(NA * nacc) + sub * 8, r2);
             tmem_ld_wait();
             const int py = m / p.TW, px = m - py * p.TW;
             const int y = t2.y0 + py, x = t2.x0 + px;
@@ -552,15 +572,16 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
           }
         }
         if (!two_stage && it > 0) named_bar_sync(1, gthreads);   // one staging buffer: every copy-out of the previous tile has been issued
-        const uint32_t t_addr = t_lane + buf * nmma + ch_lo;
+        const uint32_t t_addr = t_lane + buf * nacc + ch_lo;
         mbar_wait(bar_acc_full(buf), acc_phase);           // the one bounded wait (see mbar_wait_spin)
         tc_fence_after();
         if (tracer) CSR_TRACE(2, it, 1);
-        uint32_t raw[2][KW_T][8];
+        constexpr int KW_E = HYB_T ? KW_T - 1 : KW_T;      // column groups of the accumulator
+        uint32_t raw[2][KW_E][8];
 #pragma unroll
         for (int jj = 0; jj < 2; ++jj)
 #pragma unroll
-          for (int dx = 0; dx < KW_T; ++dx) tmem_ld8(t_addr + dx * p.npad + jj * 8, raw[jj][dx]);
+          for (int dx = 0; dx < KW_E; ++dx) tmem_ld8(t_addr + dx * p.npad + jj * 8, raw[jj][dx]);
         tmem_ld_wait();
         // the accumulator now lives in registers: the MMA warps may refill the buffer while the arithmetic runs
         tc_fence_before();
@@ -577,7 +598,7 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
             v[0] = b0.x; v[1] = b0.y; v[2] = b0.z; v[3] = b0.w; v[4] = b1.x; v[5] = b1.y; v[6] = b1.z; v[7] = b1.w;
           }
 #pragma unroll
-          for (int dx = 0; dx < KW_T; ++dx) gather_add8(v, raw[jj][dx], dx - PW_T, lane);
+          for (int dx = 0; dx < KW_E; ++dx) gather_add8(v, raw[jj][dx], dx - PW_T, lane);
           if (act == 3) {
             if (ch0 < p.act_upto) apply_act8(v, 1);
           } else {
@@ -615,7 +636,7 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
               const uint32_t idesc2 = make_idesc_bf16(kTileM, N2);
 #pragma unroll
               for (int ks = 0; ks < 4; ++ks)
-                umma_bf16_split(tmem_base + static_cast<uint32_t>(NA * nmma), a16 + ks * 2, a_hi2, b16 + ks * ((N2 * 32) >> 4), b_hi2, idesc2, ks ? 1u : 0u);
+                umma_bf16_split(tmem_base + static_cast<uint32_t>(NA * nacc), a16 + ks * 2, a_hi2, b16 + ks * ((N2 * 32) >> 4), b_hi2, idesc2, ks ? 1u : 0u);
               umma_commit(bar_d2);
             }
             __syncwarp();
@@ -692,7 +713,7 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
       }
       if (tma_store) named_bar_sync(1 + g, gthreads);   // every thread of the group has copied out the previous tile
       if (tracer) CSR_TRACE(2, it, 0);
-      const uint32_t t_addr = t_lane + buf * nmma;
+      const uint32_t t_addr = t_lane + buf * nacc;
       mbar_wait(bar_acc_full(buf), acc_phase);             // the one bounded wait (see mbar_wait_spin)
       tc_fence_after();
       if (tracer) CSR_TRACE(2, it, 1);
@@ -715,6 +736,18 @@ conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
             tmem_ld8(t_addr + ch0, r0);
             tmem_ld_wait();
             gather_add8(v, r0, 0, lane);
+          } else if constexpr (KW_T == 2 && HYB_T) {      // hybrid fold: both taps in one column group
+            uint32_t r0[8];
+            tmem_ld8(t_addr + ch0, r0);
+            tmem_ld_wait();
+            gather_add8(v, r0, d0, lane);
+          } else if constexpr (KW_T == 3 && HYB_T) {      // hybrid fold: tap 2 accumulated into tap 1's columns
+            uint32_t r0[8], r1[8];
+            tmem_ld8(t_addr + ch0, r0);
+            tmem_ld8(t_addr + p.npad + ch0, r1);
+            tmem_ld_wait();
+            gather_add8(v, r0, d0, lane);
+            gather_add8(v, r1, d1, lane);
           } else if constexpr (KW_T == 2) {
             uint32_t r0[8], r1[8];
             tmem_ld8(t_addr + ch0, r0);
@@ -831,13 +864,13 @@ size_t conv_smem_bytes(const ConvParams& p) {
          8 * (20 + 2 * p.n_slots) + 32;
 }
 
-template <int KW_T, int PW_T, int ACT_T, int RES_T, int ST_T, int PAIR_T = 0, int TALL_T = 0, int EARLY_T = 0, int FUSE_T = 0>
+template <int KW_T, int PW_T, int ACT_T, int RES_T, int ST_T, int PAIR_T = 0, int TALL_T = 0, int EARLY_T = 0, int FUSE_T = 0, int HYB_T = 0>
 static int launch_t(const ConvParams& p, const CUtensorMap& tmap, int num_sms, cudaStream_t stream) {
   const size_t smem = conv_smem_bytes(p);
   if (smem > static_cast<size_t>(kSmemLimit)) return static_cast<int>(cudaErrorInvalidValue);
   // the attribute is per device (and per template instantiation): one process may drive several GPUs
   static bool configured[64] = {};
-  auto kern = conv_tc_kernel<KW_T, PW_T, ACT_T, RES_T, ST_T, PAIR_T, TALL_T, EARLY_T, FUSE_T>;
+  auto kern = conv_tc_kernel<KW_T, PW_T, ACT_T, RES_T, ST_T, PAIR_T, TALL_T, EARLY_T, FUSE_T, HYB_T>;
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return static_cast<int>(cudaErrorInvalidDevice);
   if (!configured[dev]) {
@@ -922,8 +955,9 @@ int launch_conv_tc(const ConvParams& p, const CUtensorMap& tmap, int num_sms, cu
     if (p.fuse2 == 2) {
       // HRconv (3x3, LeakyReLU) + the nine tap planes of conv_last (3x3, 64 -> 1) in one launch
       if (p.KW != 3 || p.PW != 1 || p.act != 1 || res != 0 || p.stage_row_bytes != 128 || p.w2_bytes != 2048 || p.n2 != 9 || p.out2_plane <= 0 ||
-          p.tmem_cols < p.n_acc * p.KW * p.npad + 16 || p.parts > 1)
+          p.tmem_cols < p.n_acc * (p.hyb ? p.KW - 1 : p.KW) * p.npad + 16 || p.parts > 1)
         return static_cast<int>(cudaErrorInvalidValue);
+      if (p.hyb) return launch_t<3, 1, 1, 0, 1, 0, 0, 1, 2, 1>(p, tmap, num_sms, stream);
       return launch_t<3, 1, 1, 0, 1, 0, 0, 1, 2>(p, tmap, num_sms, stream);
     }
     if (p.fuse2) {
@@ -934,7 +968,10 @@ int launch_conv_tc(const ConvParams& p, const CUtensorMap& tmap, int num_sms, cu
       return launch_t<1, 0, 2, 0, 1, 0, 0, 1, 1>(p, tmap, num_sms, stream);
     }
 #define CSR_EARLY(KW_, PW_, ACT_, RES_) \
-    if (p.KW == KW_ && p.PW == PW_ && p.act == ACT_ && res == RES_) return launch_t<KW_, PW_, ACT_, RES_, 1, 0, 0, 1>(p, tmap, num_sms, stream);
+    if (p.KW == KW_ && p.PW == PW_ && p.act == ACT_ && res == RES_) {                                                                   \
+      if constexpr (KW_ >= 2) { if (p.hyb) return launch_t<KW_, PW_, ACT_, RES_, 1, 0, 0, 1, 0, 1>(p, tmap, num_sms, stream); }            \
+      return launch_t<KW_, PW_, ACT_, RES_, 1, 0, 0, 1>(p, tmap, num_sms, stream);                                                      \
+    }
     CSR_EARLY(3, 1, 1, 0)   // HRconv
     CSR_EARLY(3, 1, 0, 0)   // conv_first
 #ifdef CSR_EXPERIMENTS
@@ -956,6 +993,13 @@ int launch_conv_tc(const ConvParams& p, const CUtensorMap& tmap, int num_sms, cu
   CSR_CASE(3, 1, 1, 0, 1)   // RDB conv1-4, HRconv: lrelu
   CSR_CASE(3, 1, 0, 0, 1)   // conv_first
   CSR_CASE(3, 1, 4, 0, 1)   // discriminator convs: LeakyReLU(act_slope)
+  if (p.hyb && p.store_mode == kStoreStaged && !p.force_generic && p.KW == 3 && p.PW == 1 && p.act == 0) {   // hybrid tap fold (HYB_T)
+#ifdef CSR_EXPERIMENTS
+    if (res == 1) return launch_t<3, 1, 0, 1, 1, 0, 0, 0, 0, 1>(p, tmap, num_sms, stream);
+    if (res == 3) return launch_t<3, 1, 0, 3, 1, 0, 0, 0, 0, 1>(p, tmap, num_sms, stream);
+#endif
+    return static_cast<int>(cudaErrorInvalidValue);
+  }
   CSR_CASE(3, 1, 0, 1, 1)   // RDB conv5 (*0.2 + x), trunk_conv (+ fea)
   CSR_CASE(3, 1, 0, 3, 1)   // RDB3 conv5 (*0.2 + x, *0.2 + x_rrdb)
 #ifdef CSR_EXPERIMENTS

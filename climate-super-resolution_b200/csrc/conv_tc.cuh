@@ -46,6 +46,7 @@ struct ConvParams {
   int n_acc;       // accumulator buffers in TMEM (2, 4 or 8); n_acc * KW * npad <= 512
   int n_groups;    // epilogue warp groups (1, 2 or 4; n_groups divides n_acc): one staging buffer each
   int n_stage;     // staging buffers in shared memory: n_groups, or 2 for the early-release epilogue
+  int hyb;         // 1 = hybrid tap fold (conv_tc.cu HYB_T): 3x3 early-release layers, accumulators of 2*npad columns
   int early;       // 1 = early-release epilogue (conv_tc.cu, EARLY_T): wide residual-free layers, one 16-warp group
   int tmem_cols;   // power of two >= max(32, n_acc*KW*npad)
   int force_generic;  // debug: skip the compile-time specialised kernels

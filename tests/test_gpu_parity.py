@@ -113,13 +113,16 @@ def test_conv_epilogue_variants():
     assert float((got - _ref_conv(x, w16, b16, "lrelu")).abs().max()) <= 2.0 ** -7
     assert bool((cat[..., 80:] == 0).all()) and bool((cat[..., :64] == _nhwc(x, 64)).all())
     # per-element store path (option 4) must agree bit-for-bit with the TMA-store path
+    # (hybrid tap fold off: it only exists for staged stores and adds the last tap inside the accumulator - another summation order)
     from climsr_b200._lib import lib
-    a = ops.conv2d_nhwc(_nhwc(x, 64), wt.cuda(), b.cuda(), act="lrelu")
-    lib.csr_set_option(4, 1)
+    lib.csr_set_option(35, 0)
     try:
+        a = ops.conv2d_nhwc(_nhwc(x, 64), wt.cuda(), b.cuda(), act="lrelu")
+        lib.csr_set_option(4, 1)
         c = ops.conv2d_nhwc(_nhwc(x, 64), wt.cuda(), b.cuda(), act="lrelu")
     finally:
         lib.csr_set_option(4, 0)
+        lib.csr_set_option(35, 1)
     assert torch.equal(a, c)
 
 
@@ -627,6 +630,33 @@ def test_dense_block_kernel_is_bit_identical_to_per_layer_launches(n, in_ch, h, 
         lib.csr_set_option(31, 2)
     assert torch.equal(outs[0], outs[1])
     assert torch.equal(outs[0], outs[2])
+
+
+@pytest.mark.parametrize("n,in_ch,h,w", [(2, 4, 64, 64), (1, 3, 113, 113), (3, 4, 20, 36), (1, 1, 9, 7)])
+def test_hybrid_tap_fold_matches_full_fold(n, in_ch, h, w):
+    """Option 35 (default 1): in the epilogue-bound 64-channel early-release layers (HRconv, the upconv phases) the LAST horizontal tap
+    is an MMA of its own over an A operand shifted by one pixel (descriptor start + 128 bytes inside the 128B-swizzled window) that
+    accumulates into the previous tap's columns, instead of a third column group summed by shuffles.  Same products, the last tap is
+    added inside the accumulator instead of in the epilogue -> equal up to fp32 summation order and single bf16 rounding flips."""
+    from climsr_b200._lib import lib
+    from climsr_b200.models import ESRGANGenerator
+    from oracle import synth
+    sd = synth.make_state_dict(in_ch, 1, 64, 1, 16, seed=36, gain=1.2)
+    x, elev, mask = synth.make_inputs(n, in_ch, h, w, seed=37)
+    outs = []
+    try:
+        for hyb in (1, 0):
+            lib.csr_set_option(35, hyb)
+            net = ESRGANGenerator(in_ch, 1, 64, 1, 16)
+            net.load_state_dict(sd)
+            net = net.cuda().eval()
+            with torch.no_grad():
+                outs.append(net(x.cuda(), elev.cuda(), mask.cuda()).cpu())
+            del net
+    finally:
+        lib.csr_set_option(35, 1)
+    scale = max(1.0, float(outs[1].abs().max()))
+    assert float((outs[0] - outs[1]).abs().max()) <= 3e-3 * scale, float((outs[0] - outs[1]).abs().max())
 
 
 @pytest.mark.parametrize("n,in_ch,h,w", [(2, 4, 64, 64), (1, 3, 113, 113), (3, 4, 20, 36), (1, 1, 9, 7)])
