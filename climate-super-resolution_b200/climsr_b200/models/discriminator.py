@@ -238,7 +238,14 @@ class Discriminator(nn.Module):
             if calls[key] <= self._EAGER_CALLS:
                 out, saved = self._run_forward(x, save)
                 return out, saved, None
-            slots = self.__dict__.setdefault("_slots", {}).setdefault(key, [])
+            all_slots = self.__dict__.setdefault("_slots", {})
+            if key not in all_slots and len(all_slots) >= 6:       # many batch sizes / re-allocated parameters: drop the idle graphs
+                for k in [k for k, v in all_slots.items() if not any(sl.busy for sl in v)]:
+                    del all_slots[k]
+                if len(calls) > 64:
+                    calls.clear()
+                    calls[key] = self._EAGER_CALLS + 1
+            slots = all_slots.setdefault(key, [])
             slot = next((sl for sl in slots if not sl.busy), None)
             if slot is None:
                 if len(slots) >= 8:                                # leases that never came back (graphs kept alive by the caller)
