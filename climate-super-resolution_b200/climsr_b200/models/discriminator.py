@@ -91,6 +91,9 @@ class _DiscriminatorFunction(torch.autograd.Function):
         n_in = 2 + len(ctx.need_param_grads)
         if gy is None:
             return (None,) * n_in
+        if ctx.saved is None:
+            raise CsrError("the discriminator's saved activations were released by its first backward; a second backward through the same "
+                           "forward (retain_graph=True) is not supported - run the forward again")
         dx, grads = ctx.module._backward_saved(ctx.saved, ctx.lease, gy, ctx.needs_input_grad[1], ctx.need_params)
         ctx.saved = ctx.lease = None
         out = [None, dx]
