@@ -52,6 +52,7 @@ static int g_opt_l2_prefetch = 0;       // conv layers that stream from HBM: pre
 static int g_dbg_dense = 0;             // DenseParams::dbg (timing experiments)
 static int g_opt_dense_min = 2;         // ... only when a block has at least this many windows per SM: with <= 1 window per CTA nothing pipelines
                                         // across layers and the counters only cost (cfg1 / one Europe raster / cfg3: 7-10 % slower, r02 A/B)
+static int g_opt_tap_pack = 1;          // conv_last's tap sum fused with the SRCNN input im2col (tap_pack_kernel)
 static int g_opt_hyb = 1;               // hybrid tap fold (conv_tc.cu HYB_T): bit 0 early-release layers (HRconv 338 -> 294 us); experiments build only:
                                         // bit 1 conv5 / trunk_conv, bit 2 four accumulators there (measured slower: those are not epilogue-bound)
 static int g_opt_merge_phases = 1;      // sub-pixel phase pairs of nearest-x2 + conv as one launch (gridDim.y)
@@ -1561,6 +1562,7 @@ int csr_set_option(int32_t key, int32_t value) {
     case 20: case 21: case 22: case 23: case 24: g_dbg_wgrad[key - 20] = value; return CSR_OK;
     case 25: g_opt_wgrad_atomic = value ? 1 : 0; return CSR_OK;    // plans created afterwards
     case 27: g_opt_dense = value ? 1 : 0; return CSR_OK;           // plans created afterwards
+    case 36: g_opt_tap_pack = value ? 1 : 0; return CSR_OK;
     case 35: g_opt_hyb = value; return CSR_OK;                    // plans created afterwards
     case 34: g_opt_merge_phases = value ? 1 : 0; return CSR_OK;    // plans created afterwards
     case 33: g_opt_fuse_tail = value & 3; return CSR_OK;       // plans created afterwards
@@ -2059,9 +2061,16 @@ static int forward_launches(CsrPlan* P, const void* packed, const float* x, cons
   CSR_CUDA(launch_nchw_to_nhwc(x, P->xin, P->N, P->net.in_channels, P->h, P->w, 64, 16, s));
   ++g_launches;
   if (!P->dense.empty()) CSR_CUDA(cudaMemsetAsync(P->flags, 0, P->flags_bytes, s));   // completion counters of the dense-block launches
+  const ConvLaunch* tap_pack = nullptr;
   for (size_t i = 0; i < P->convs.size(); ++i) {
     if ((int)i == P->idx_srcnn1) {
-      CSR_CUDA(launch_pack_srcnn_in(P->tlast, elev, mask, P->sin, 4 * P->w, (long)P->N * P->h * P->w * 16, P->srcnn_pitch, s));
+      if (tap_pack) {
+        // conv_last's tap sum and the SRCNN input im2col in one pass
+        CSR_CUDA(launch_tap_pack(tap_pack->taps, tap_pack->tap_plane, reinterpret_cast<const float*>(pk + tap_pack->b_off), elev, mask, P->sin, P->N,
+                                 tap_pack->tap_H, tap_pack->tap_W, s));
+      } else {
+        CSR_CUDA(launch_pack_srcnn_in(P->tlast, elev, mask, P->sin, 4 * P->w, (long)P->N * P->h * P->w * 16, P->srcnn_pitch, s));
+      }
       ++g_launches;
     }
     ConvLaunch& cl = P->convs[i];
@@ -2077,6 +2086,7 @@ static int forward_launches(CsrPlan* P, const void* packed, const float* x, cons
       ++g_launches;
       continue;
     }
+    if (cl.tapsum && P->srcnn_pitch == 32 && g_opt_tap_pack) { tap_pack = &cl; continue; }   // finished by tap_pack_kernel right before srcnn.conv1
     if (cl.tapsum) {
       CSR_CUDA(launch_tap_sum(cl.taps, cl.tap_plane, reinterpret_cast<const float*>(pk + cl.b_off), P->tlast, cl.tap_H, cl.tap_W, cl.tap_plane, s));
       ++g_launches;

@@ -473,6 +473,78 @@ __global__ void tap_sum_kernel(const float* __restrict__ taps, long plane, const
     out[i] = acc;
   }
 }
+// tap_sum_kernel + pack_srcnn_in_kernel in one pass (inference, 32-channel im2col pitch): a block takes 256 pixels of one image row,
+// finishes conv_last for them and their 4-pixel horizontal halo from the nine tap planes, builds the 27 (32) im2col channels of every
+// pixel in shared memory and writes them out as whole lines (consecutive threads = consecutive 16-byte pieces).  The fp32 conv_last
+// plane never reaches memory and the 64 B / pixel of output leave coalesced (the per-pixel strided stores of the two-kernel form ran
+// at 3.4 TB/s).
+__global__ void __launch_bounds__(256) tap_pack_kernel(const float* __restrict__ taps, long plane, const float* __restrict__ bias,
+                                                       const float* __restrict__ elev, const float* __restrict__ mask,
+                                                       __nv_bfloat16* __restrict__ dst, int H, int W, int segs) {
+  __shared__ float ts[264], es[264], ms[264];
+  __shared__ uint4 outs[256 * 4];
+  const int seg = blockIdx.x % segs;
+  const long row = blockIdx.x / segs;                     // n * H + y
+  const int y = static_cast<int>(row % H);
+  const int x0 = seg * 256;
+  const long rowbase = row * W;
+  const float b = bias ? bias[0] : 0.f;
+  for (int i = threadIdx.x; i < 264; i += 256) {
+    const int xx = x0 - 4 + i;
+    float t = 0.f, e = 0.f, m = 0.f;
+    if (xx >= 0 && xx < W) {
+      t = b;
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        const int yy = y + ky - 1;
+        if (yy < 0 || yy >= H) continue;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const int xs = xx + kx - 1;
+          if (xs >= 0 && xs < W) t += taps[static_cast<long>(ky * 3 + kx) * plane + rowbase + (ky - 1) * W + xs];
+        }
+      }
+      e = elev[rowbase + xx];
+      m = mask[rowbase + xx];
+    }
+    ts[i] = t; es[i] = e; ms[i] = m;
+  }
+  __syncthreads();
+  const int n_here = min(256, W - x0);
+  if (static_cast<int>(threadIdx.x) < n_here) {
+    float v[32];
+#pragma unroll
+    for (int dx = 0; dx < 9; ++dx) {                      // channel dx*3 + c: pixel x + dx - 4 of (conv_last output, elevation, mask)
+      v[dx * 3 + 0] = ts[threadIdx.x + dx];
+      v[dx * 3 + 1] = es[threadIdx.x + dx];
+      v[dx * 3 + 2] = ms[threadIdx.x + dx];
+    }
+#pragma unroll
+    for (int i = 27; i < 32; ++i) v[i] = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      uint4 a;
+      a.x = pack_bf16x2(v[8 * k + 0], v[8 * k + 1]);
+      a.y = pack_bf16x2(v[8 * k + 2], v[8 * k + 3]);
+      a.z = pack_bf16x2(v[8 * k + 4], v[8 * k + 5]);
+      a.w = pack_bf16x2(v[8 * k + 6], v[8 * k + 7]);
+      outs[((threadIdx.x * 4 + k) & ~3) + ((k + (threadIdx.x >> 1)) & 3)] = a;   // rotate the four pieces of a pixel: fewer bank conflicts
+    }
+  }
+  __syncthreads();
+  uint4* o = reinterpret_cast<uint4*>(dst + (rowbase + x0) * 32);
+  for (int j = threadIdx.x; j < n_here * 4; j += 256) {
+    const int px = j >> 2, k = j & 3;
+    o[j] = outs[px * 4 + ((k + (px >> 1)) & 3)];
+  }
+}
+cudaError_t launch_tap_pack(const float* taps, long plane, const float* bias, const float* elev, const float* mask, void* dst, int N, int H, int W,
+                            cudaStream_t s) {
+  const int segs = (W + 255) / 256;
+  tap_pack_kernel<<<static_cast<unsigned>(static_cast<long>(N) * H * segs), 256, 0, s>>>(taps, plane, bias, elev, mask,
+                                                                                      reinterpret_cast<__nv_bfloat16*>(dst), H, W, segs);
+  return cudaGetLastError();
+}
 cudaError_t launch_tap_sum(const float* taps, long plane, const float* bias, float* out, int H, int W, long total, cudaStream_t s) {
   tap_sum_kernel<<<grid_for(total, 256, 148 * 16), 256, 0, s>>>(taps, plane, bias, out, H, W, total);
   return cudaGetLastError();
