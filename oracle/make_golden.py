@@ -212,6 +212,31 @@ def rcan():
     np.savez_compressed(os.path.join(OUT, "rcan.npz"), **blob)
 
 
+def rcan_grad():
+    """tests/golden/rcan_grad.npz (groundwork for RCAN training): autograd of the UNMODIFIED reference RCAN at the
+    reduced depth of rcan.npz, loss = sum(sr * w) with a seeded w.  Stored: sum and abs-sum of EVERY parameter gradient (state_dict
+    order), the full gradients of four representative tensors (first conv, a channel-attention 1x1, the last upsampler conv, srcnn.conv3)
+    and the gradient w.r.t. the LR input."""
+    from climsr.models.rcan import RCAN
+    ng, nbk, n, h, w, seed = 2, 3, 2, 20, 24, 0
+    torch.manual_seed(seed)
+    net = RCAN(n_resgroups=ng, n_resblocks=nbk, n_feats=64, reduction=16, scaling_factor=4, in_channels=3, out_channels=1).train()
+    x, elev, mask = synth.make_inputs(n, 3, h, w, seed=50 + seed)
+    x.requires_grad_(True)
+    wsum = torch.randn((n, 1, 4 * h, 4 * w), generator=torch.Generator().manual_seed(77))
+    sr = net(x, elev, mask)
+    (sr * wsum).sum().backward()
+    names = [k for k, _ in net.named_parameters()]
+    grads = [p.grad for _, p in net.named_parameters()]
+    blob = {"meta": np.array([ng, nbk, n, h, w, seed], dtype=np.int64), "names": np.array(names),
+            "g_sum": np.array([float(g.double().sum()) for g in grads]), "g_abs": np.array([float(g.double().abs().sum()) for g in grads]),
+            "dx": x.grad.numpy()}
+    for k in ("head.0.weight", "body.0.body.1.body.3.conv_du.0.weight", "tail.0.2.weight", "srcnn.conv3.weight"):
+        blob["g:" + k] = dict(net.named_parameters())[k].grad.numpy()
+    print("rcan_grad", len(names), "tensors; |dx| max", float(x.grad.abs().max()))
+    np.savez_compressed(os.path.join(OUT, "rcan_grad.npz"), **blob)
+
+
 def lr_input():
     """tests/golden/lr_input.npz: numpy flips / rot90 (climate_dataset.py:152-170) and cv2.resize INTER_NEAREST - what
     albumentations' A.Resize calls (climate_dataset.py:84-92,172) - on seeded square tiles, all 16 augmentation codes."""
@@ -259,6 +284,9 @@ if __name__ == "__main__":
         sys.exit(0)
     if "--rcan-only" in sys.argv:
         rcan()
+        sys.exit(0)
+    if "--rcan-grad-only" in sys.argv:
+        rcan_grad()
         sys.exit(0)
     if "--fulldepth-only" in sys.argv:
         fulldepth()

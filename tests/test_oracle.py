@@ -221,3 +221,32 @@ def test_rcan_restatement_and_state_dict_contract_match_reference_golden(golden_
             got = orc.rcan_forward(sd, x, elev, mask, ng, nbk).numpy()
         assert got.shape == z[tag].shape
         assert np.abs(got - z[tag]).max() <= 2e-5
+
+
+def test_rcan_oracle_gradients_match_reference_autograd_golden(golden_dir):
+    """Groundwork for RCAN training (the CUDA path is inference-only so far): autograd through oracle/rcan.py
+    reproduces the gradients of the UNMODIFIED reference module (tests/golden/rcan_grad.npz, oracle/make_golden.py --rcan-grad-only)
+    for every parameter (sum / abs-sum), four full tensors and the input."""
+    from climsr_b200.models.rcan import RCAN
+    from oracle import rcan as orc
+    from oracle import synth
+    z = np.load(os.path.join(golden_dir, "rcan_grad.npz"))
+    ng, nbk, n, h, w, seed = (int(v) for v in z["meta"])
+    net = _rcan_from_seed(RCAN, ng, nbk, seed)
+    sd = {k: v.clone().requires_grad_(True) for k, v in net.state_dict().items()}
+    x, elev, mask = synth.make_inputs(n, 3, h, w, seed=50 + seed)
+    x.requires_grad_(True)
+    wsum = torch.randn((n, 1, 4 * h, 4 * w), generator=torch.Generator().manual_seed(77))
+    (orc.rcan_forward(sd, x, elev, mask, ng, nbk) * wsum).sum().backward()
+    names = [str(k) for k in z["names"]]
+    assert names == [k for k in sd.keys()]
+    for i, k in enumerate(names):
+        g = sd[k].grad
+        assert g is not None, k
+        assert abs(float(g.double().sum()) - float(z["g_sum"][i])) <= 1e-4 * max(1.0, float(z["g_abs"][i])), k
+        assert abs(float(g.double().abs().sum()) - float(z["g_abs"][i])) <= 1e-4 * max(1.0, float(z["g_abs"][i])), k
+    for key in z.files:
+        if key.startswith("g:"):
+            ref = z[key]
+            assert np.abs(sd[key[2:]].grad.numpy() - ref).max() <= 1e-4 * max(1e-3, float(np.abs(ref).max())), key
+    assert np.abs(x.grad.numpy() - z["dx"]).max() <= 1e-4 * max(1e-3, float(np.abs(z["dx"]).max()))
